@@ -1,0 +1,400 @@
+/* include/pf_cuda.h — C ABI of the B200-native `cuda` backend for Pathfinder 3's D3D11-level
+ * rasterization pipeline (bound -> dice -> bin -> propagate -> sort -> fill -> tile).
+ *
+ * This is the drop-in boundary: what a Rust `pathfinder_cuda` crate binds with `extern "C"`
+ * (see INTEGRATION.md). Plain pointers and sizes only; no CUDA or torch types. Every entry point
+ * cites the reference interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions follow the reference's own C API (c/src/lib.rs:564-690): opaque `*Ref` handles,
+ * `Create`/`Destroy` pairs, backend-suffixed names. Unlike the reference (which panics), every
+ * fallible call returns a PFCudaStatus; PFCudaGetLastError() holds the message. The Rust wrapper
+ * turns a non-zero status into panic! to keep the reference's error behaviour.
+ *
+ * Threading: a renderer handle is single-threaded (&mut self in the reference,
+ * renderer/src/gpu/renderer.rs:350-460). Command payloads are borrowed for the duration of the
+ * call and copied before it returns (the reference shares them by move / Arc).
+ */
+#ifndef PF_CUDA_H
+#define PF_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------- */
+/* Plain types shared with the reference C API (c/src/lib.rs:118-175).                          */
+/* ------------------------------------------------------------------------------------------- */
+
+typedef struct PFColorF { float r, g, b, a; } PFColorF;
+typedef struct PFColorU { uint8_t r, g, b, a; } PFColorU;
+typedef struct PFVector2F { float x, y; } PFVector2F;
+typedef struct PFVector2I { int32_t x, y; } PFVector2I;
+typedef struct PFRectF { PFVector2F origin, lower_right; } PFRectF;
+typedef struct PFRectI { PFVector2I origin, lower_right; } PFRectI;
+/* Row-major order (c/src/lib.rs:151-163): m00 = m11(), m01 = m12(), m10 = m21(), m11 = m22(). */
+typedef struct PFMatrix2x2F { float m00, m01, m10, m11; } PFMatrix2x2F;
+typedef struct PFTransform2F { PFMatrix2x2F matrix; PFVector2F vector; } PFTransform2F;
+
+typedef int32_t PFCudaStatus;
+#define PF_CUDA_OK 0
+#define PF_CUDA_ERROR_INVALID_ARGUMENT 1
+#define PF_CUDA_ERROR_CUDA 2            /* a CUDA runtime call failed */
+#define PF_CUDA_ERROR_UNSUPPORTED 3     /* command / feature outside the hot path */
+#define PF_CUDA_ERROR_WRONG_LEVEL 4     /* a D3D9-only command: Renderer::require_d3d11 panics here
+                                           (renderer/src/gpu/renderer.rs:1349-1360) */
+#define PF_CUDA_ERROR_PROTOCOL 5        /* command outside begin_scene/end_scene, missing scene... */
+#define PF_CUDA_ERROR_NO_DEVICE 6
+
+/* Last error message of the calling thread ("" if none). Never NULL. */
+const char *PFCudaGetLastError(void);
+
+/* ------------------------------------------------------------------------------------------- */
+/* #[repr(C)] records crossing the boundary (renderer/src/gpu_data.rs). Layouts are identical.  */
+/* ------------------------------------------------------------------------------------------- */
+
+#define PF_TILE_WIDTH 16   /* renderer/src/tiles.rs:19 */
+#define PF_TILE_HEIGHT 16  /* renderer/src/tiles.rs:20 */
+#define PF_TILE_CTRL_MASK_WINDING 0x1   /* gpu_data.rs:32 */
+#define PF_TILE_CTRL_MASK_EVEN_ODD 0x2  /* gpu_data.rs:33 */
+#define PF_CURVE_IS_QUADRATIC 0x80000000u /* renderer/src/builder.rs:47 */
+#define PF_CURVE_IS_CUBIC 0x40000000u     /* renderer/src/builder.rs:48 */
+#define PF_PATH_INDEX_NONE 0xffffffffu    /* PathBatchIndex::none(), gpu_data.rs:440-445 */
+#define PF_ALPHA_TILE_ID_INVALID 0xffffffffu /* AlphaTileId::invalid(), gpu_data.rs:456-459 */
+
+typedef struct PFSegmentIndicesD3D11 {     /* gpu_data.rs:176-181 */
+    uint32_t first_point_index;
+    uint32_t flags;
+} PFSegmentIndicesD3D11;
+
+typedef struct PFSegmentsD3D11 {           /* gpu_data.rs:170-174 (Vec -> ptr,len) */
+    const PFVector2F *points;
+    size_t point_count;
+    const PFSegmentIndicesD3D11 *indices;
+    size_t index_count;
+} PFSegmentsD3D11;
+
+typedef struct PFDiceMetadataD3D11 {       /* gpu_data.rs:327-334 */
+    uint32_t global_path_id;
+    uint32_t first_global_segment_index;
+    uint32_t first_batch_segment_index;
+    uint32_t pad;
+} PFDiceMetadataD3D11;
+
+typedef struct PFTilePathInfoD3D11 {       /* gpu_data.rs:297-309 */
+    int16_t tile_min_x, tile_min_y, tile_max_x, tile_max_y;
+    uint32_t first_tile_index;
+    uint16_t color;
+    uint8_t ctrl;
+    int8_t backdrop;
+} PFTilePathInfoD3D11;
+
+typedef struct PFPropagateMetadataD3D11 {  /* gpu_data.rs:312-325 */
+    PFRectI tile_rect;
+    uint32_t tile_offset;
+    uint32_t path_index;
+    uint32_t z_write;
+    uint32_t clip_path_index;
+    uint32_t backdrop_offset;
+    uint32_t pad0, pad1, pad2;
+} PFPropagateMetadataD3D11;
+
+typedef struct PFBackdropInfoD3D11 {       /* gpu_data.rs:407-414 */
+    int32_t initial_backdrop;
+    int32_t tile_x_offset;
+    uint32_t path_index;
+} PFBackdropInfoD3D11;
+
+typedef struct PFFill {                    /* gpu_data.rs:354-363 */
+    uint16_t from_x, from_y, to_x, to_y;   /* LineSegmentU16, 4.8 fixed point inside the tile */
+    uint32_t link;
+} PFFill;
+
+typedef struct PFTileObjectPrimitive {     /* gpu_data.rs:264-275 */
+    int16_t tile_x, tile_y;
+    uint32_t alpha_tile_id;
+    uint32_t path_id;
+    uint16_t color;
+    uint8_t ctrl;
+    int8_t backdrop;
+} PFTileObjectPrimitive;
+
+typedef struct PFClip {                    /* gpu_data.rs:376-383 */
+    uint32_t dest_tile_id;
+    int32_t dest_backdrop;
+    uint32_t src_tile_id;
+    int32_t src_backdrop;
+} PFClip;
+
+/* TextureMetadataEntry (gpu_data.rs:336-344). Only solid colours are on the hot path (SURVEY.md
+ * §2 row 7): color_0_combine_mode must be 0 (None), filter 0 (None), blend_mode 0 (SrcOver). */
+typedef struct PFTextureMetadataEntry {
+    PFTransform2F color_0_transform;
+    uint32_t color_0_combine_mode;
+    PFColorU base_color;
+    uint32_t filter;
+    uint32_t blend_mode;
+} PFTextureMetadataEntry;
+
+/* PrepareTilesInfoD3D11 (gpu_data.rs:149-168) with the Vecs flattened. `backdrops` may be NULL
+ * with backdrop_count = 0, meaning "all initial backdrops are zero" (what init_backdrops,
+ * renderer/src/builder.rs:762-768, produces in PrepareMode::GPU). */
+typedef struct PFPrepareTilesInfoD3D11 {
+    const PFBackdropInfoD3D11 *backdrops;
+    size_t backdrop_count;
+    const PFPropagateMetadataD3D11 *propagate_metadata;
+    const PFDiceMetadataD3D11 *dice_metadata;
+    const PFTilePathInfoD3D11 *tile_path_info;   /* all three: path_count entries */
+    PFTransform2F transform;
+} PFPrepareTilesInfoD3D11;
+
+#define PF_PATH_SOURCE_DRAW 0  /* gpu_data.rs:142-147 */
+#define PF_PATH_SOURCE_CLIP 1
+
+typedef struct PFClippedPathInfo {         /* gpu_data.rs:183-199 */
+    uint32_t clip_batch_id;
+    uint32_t clipped_path_count;
+    uint32_t max_clipped_tile_count;
+} PFClippedPathInfo;
+
+typedef struct PFTileBatchDataD3D11 {      /* gpu_data.rs:121-140 */
+    uint32_t batch_id;
+    uint32_t path_count;
+    uint32_t tile_count;
+    uint32_t segment_count;
+    PFPrepareTilesInfoD3D11 prepare_info;
+    uint32_t path_source;
+    uint32_t has_clipped_path_info;
+    PFClippedPathInfo clipped_path_info;
+} PFTileBatchDataD3D11;
+
+/* RenderCommand (gpu_data.rs:37-105) as a tagged union. */
+typedef enum PFRenderCommandKind {
+    PF_RENDER_COMMAND_START = 0,
+    PF_RENDER_COMMAND_ALLOCATE_TEXTURE_PAGE = 1,
+    PF_RENDER_COMMAND_UPLOAD_TEXEL_DATA = 2,
+    PF_RENDER_COMMAND_DECLARE_RENDER_TARGET = 3,
+    PF_RENDER_COMMAND_UPLOAD_TEXTURE_METADATA = 4,
+    PF_RENDER_COMMAND_ADD_FILLS_D3D9 = 5,
+    PF_RENDER_COMMAND_FLUSH_FILLS_D3D9 = 6,
+    PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11 = 7,
+    PF_RENDER_COMMAND_PUSH_RENDER_TARGET = 8,
+    PF_RENDER_COMMAND_POP_RENDER_TARGET = 9,
+    PF_RENDER_COMMAND_PREPARE_CLIP_TILES_D3D11 = 10,
+    PF_RENDER_COMMAND_DRAW_TILES_D3D9 = 11,
+    PF_RENDER_COMMAND_DRAW_TILES_D3D11 = 12,
+    PF_RENDER_COMMAND_FINISH = 13
+} PFRenderCommandKind;
+
+typedef struct PFRenderCommand {
+    uint32_t kind; /* PFRenderCommandKind */
+    union {
+        struct { uint64_t path_count; uint32_t needs_readable_framebuffer; } start;
+        struct { const PFTextureMetadataEntry *entries; size_t entry_count; } upload_texture_metadata;
+        struct { PFSegmentsD3D11 draw_segments, clip_segments; } upload_scene_d3d11;
+        struct { PFTileBatchDataD3D11 batch; } prepare_clip_tiles_d3d11;
+        struct { PFTileBatchDataD3D11 tile_batch_data; uint32_t has_color_texture; } draw_tiles_d3d11;
+        struct { uint32_t render_target_id; } push_render_target;
+        struct { uint64_t cpu_build_time_ns; } finish;
+    } u;
+} PFRenderCommand;
+
+/* ------------------------------------------------------------------------------------------- */
+/* Device and renderer (replaces Renderer<D: Device>, renderer/src/gpu/renderer.rs:181-460).     */
+/* ------------------------------------------------------------------------------------------- */
+
+typedef struct PFCudaDevice *PFCudaDeviceRef;
+typedef struct PFCudaRenderer *PFCudaRendererRef;
+
+#define PF_RENDERER_LEVEL_D3D9 0x1   /* c/src/lib.rs:91 */
+#define PF_RENDERER_LEVEL_D3D11 0x2  /* c/src/lib.rs:92 */
+typedef struct PFRendererMode { uint8_t level; } PFRendererMode; /* c/src/lib.rs:199-202 */
+
+#define PF_RENDERER_OPTIONS_FLAGS_HAS_BACKGROUND_COLOR 0x1 /* c/src/lib.rs:88 */
+#define PF_RENDERER_OPTIONS_FLAGS_SHOW_DEBUG_UI 0x2        /* c/src/lib.rs:89 (ignored) */
+
+/* RendererOptions + DestFramebuffer::full_window (renderer/src/gpu/options.rs:19-33,79-119): the
+ * destination is an RGBA8 image of dest_size pixels owned by the renderer in device memory. */
+typedef struct PFCudaRendererOptions {
+    PFVector2I dest_size;
+    PFColorF background_color;
+    uint8_t flags;
+} PFCudaRendererOptions;
+
+/* Device::feature_level() analogue (gpu/src/lib.rs:32-50): always D3D11. `ordinal` is the CUDA
+ * device index (the process's LOCAL_RANK under one-process-per-GPU launches). */
+PFCudaDeviceRef PFCudaDeviceCreate(int32_t ordinal);
+void PFCudaDeviceDestroy(PFCudaDeviceRef device);
+uint8_t PFCudaDeviceGetFeatureLevel(PFCudaDeviceRef device);
+
+/* Renderer::new (gpu/renderer.rs:181-340). Takes ownership of `device` (as PFGLRendererCreate,
+ * c/src/lib.rs:601-615). The two LUTs are the decoded `textures/area-lut.png` (256x256 RGBA8) and
+ * `textures/gamma-lut.png` (256x8 L8, may be NULL: only the text filter reads it) that the
+ * reference fetches through its ResourceLoader. mode->level must be D3D11. Returns NULL on error. */
+PFCudaRendererRef PFCudaRendererCreate(PFCudaDeviceRef device, const uint8_t *area_lut_rgba8,
+                                       const uint8_t *gamma_lut_l8, const PFRendererMode *mode,
+                                       const PFCudaRendererOptions *options);
+void PFCudaRendererDestroy(PFCudaRendererRef renderer);
+
+/* Renderer::options_mut + dest_framebuffer_size_changed (gpu/renderer.rs:600-625). */
+PFCudaStatus PFCudaRendererSetOptions(PFCudaRendererRef renderer, const PFCudaRendererOptions *options);
+
+/* Renderer::begin_scene / render_command / end_scene (gpu/renderer.rs:350-460). */
+PFCudaStatus PFCudaRendererBeginScene(PFCudaRendererRef renderer);
+PFCudaStatus PFCudaRendererRenderCommand(PFCudaRendererRef renderer, const PFRenderCommand *command);
+PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef renderer);
+
+/* Reads the destination image back (row-major, top-left origin, `stride` bytes per row >= 4*w).
+ * Synchronises the renderer's stream. Replaces Device::read_pixels (gpu/src/lib.rs:100-104). */
+PFCudaStatus PFCudaRendererReadPixels(PFCudaRendererRef renderer, uint8_t *dst, size_t stride);
+/* Device pointer of the destination image (for peer copies / collectives) and its row pitch. */
+PFCudaStatus PFCudaRendererGetDestDevicePointer(PFCudaRendererRef renderer, uint64_t *device_ptr,
+                                                size_t *pitch_bytes);
+/* Redirects the destination image to caller-owned device memory (e.g. this rank's slot of an
+ * all-gather buffer); pass 0 to return to the renderer-owned image. */
+PFCudaStatus PFCudaRendererSetDestDevicePointer(PFCudaRendererRef renderer, uint64_t device_ptr,
+                                                size_t pitch_bytes);
+/* Uses the given cudaStream_t (as an integer handle) for all work; 0 = the renderer's own. */
+PFCudaStatus PFCudaRendererSetStream(PFCudaRendererRef renderer, uint64_t cuda_stream);
+/* Blocks until all submitted work is complete. */
+PFCudaStatus PFCudaRendererSynchronize(PFCudaRendererRef renderer);
+
+/* Multi-GPU strip partition (not in the reference): this renderer owns tile rows
+ * [tile_y0, tile_y1) of the frame; everything outside is neither binned, filled nor composited.
+ * tile_y0 = tile_y1 = 0 restores the full frame. */
+PFCudaStatus PFCudaRendererSetStrip(PFCudaRendererRef renderer, int32_t tile_y0, int32_t tile_y1);
+
+/* scene.view_box() as process_line_segment sees it (renderer/src/tiler.rs:194-200): segments are
+ * clipped to [min_x, max_x] x (-inf, max_y]. The RenderCommand stream does not carry it; the Rust
+ * glue sets it from Scene::view_box() before begin_scene. NULL = the destination rect (what the
+ * reference demo uses, demo/common/src/lib.rs:910-914). */
+PFCudaStatus PFCudaRendererSetViewBox(PFCudaRendererRef renderer, const PFRectF *view_box);
+
+/* RenderStats (renderer/src/gpu/perf.rs:21-30) plus the counts of this pipeline's stages. */
+typedef struct PFCudaRenderStats {
+    uint64_t path_count;
+    uint64_t fill_count;
+    uint64_t alpha_tile_count;
+    uint64_t total_tile_count;     /* dense bbox tiles (TileBatchDataD3D11.tile_count analogue) */
+    uint64_t cpu_build_time_ns;
+    uint64_t drawcall_count;       /* kernels launched this frame */
+    uint64_t gpu_bytes_allocated;
+    uint64_t gpu_bytes_committed;
+    uint64_t input_segment_count;  /* SegmentIndicesD3D11 entries diced */
+    uint64_t line_segment_count;   /* flattened segments entering bin ("segments") */
+    uint64_t tile_list_entry_count;/* tiles surviving the z-cull, summed over framebuffer tiles */
+    uint64_t column_count;
+    uint64_t host_sync_count;      /* blocking count read-backs this frame */
+} PFCudaRenderStats;
+PFCudaStatus PFCudaRendererGetStats(PFCudaRendererRef renderer, PFCudaRenderStats *stats);
+
+/* RenderTime (renderer/src/gpu/perf.rs:223-229) per stage, CUDA-event milliseconds of the last
+ * frame. Only recorded when timing is enabled. */
+typedef struct PFCudaRenderTime {
+    float upload_ms, bound_ms, dice_ms, bin_ms, propagate_ms, sort_ms, fill_tile_ms, total_ms;
+} PFCudaRenderTime;
+PFCudaStatus PFCudaRendererSetTimingEnabled(PFCudaRendererRef renderer, int32_t enabled);
+PFCudaStatus PFCudaRendererGetTimes(PFCudaRendererRef renderer, PFCudaRenderTime *times);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Stage-level read-backs for parity tests (SURVEY.md §8b "stage-level test hooks"). They copy   */
+/* the device-side lists of the LAST DrawTilesD3D11 batch in the canonical D3D9 forms the CPU     */
+/* tiler emits. Each returns the element count; when `out` is non-NULL copies min(count, cap).    */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Enables retention of per-stage lists (emission-ordered fills, alpha tile ids). Off by default. */
+PFCudaStatus PFCudaRendererSetDebugListsEnabled(PFCudaRendererRef renderer, int32_t enabled);
+/* Flattened line segments in emission order: 4 floats each + batch path index. */
+int64_t PFCudaRendererDebugCopyLines(PFCudaRendererRef renderer, float *out_lines, uint32_t *out_paths,
+                                     size_t cap);
+/* Fills in emission order (path order, then process_line_segment order), link = alpha tile id
+ * numbered in first-fill order = SequentialExecutor numbering (AddFillsD3D9 payloads). */
+int64_t PFCudaRendererDebugCopyFills(PFCudaRendererRef renderer, PFFill *out, size_t cap);
+/* Non-empty tiles in path order, row-major inside a path (DrawTileBatchD3D9.tiles,
+ * renderer/src/builder.rs:1013-1019), path_id = global draw path id. */
+int64_t PFCudaRendererDebugCopyTiles(PFCudaRendererRef renderer, PFTileObjectPrimitive *out, size_t cap);
+/* Z-buffer over the framebuffer tile rect (DrawTileBatchD3D9.z_buffer_data). rect_out = min_x,
+ * min_y, max_x, max_y in tiles. */
+int64_t PFCudaRendererDebugCopyZBuffer(PFCudaRendererRef renderer, int32_t *out, size_t cap,
+                                       int32_t rect_out[4]);
+/* Coverage masks of all alpha tiles, [alpha_tile_id][16][16] f32, unclamped, without backdrop. */
+int64_t PFCudaRendererDebugCopyAlphaMasks(PFCudaRendererRef renderer, float *out, size_t cap_tiles);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Scene side (renderer/src/scene.rs, options.rs). The host logic of the D3D11 level —            */
+/* BuiltSegments::from_scene, TileBatchDataD3D11::push, the command order of SceneBuilder::build  */
+/* (renderer/src/builder.rs:148-222,653-841,1058-1113) — mirrored in C++ because this image has    */
+/* no Rust toolchain. With Rust available the reference's own Scene produces the same commands.   */
+/* ------------------------------------------------------------------------------------------- */
+
+typedef struct PFScene *PFSceneRef;
+typedef struct PFBuildOptions *PFBuildOptionsRef;
+typedef struct PFRenderTransform *PFRenderTransformRef;
+
+#define PF_FILL_RULE_WINDING 0   /* content/src/fill.rs */
+#define PF_FILL_RULE_EVEN_ODD 1
+#define PF_BLEND_MODE_SRC_OVER 0 /* content/src/effects.rs: only SrcOver is on the hot path */
+#define PF_POINT_FLAGS_CONTROL_POINT_0 0x1 /* content/src/outline.rs PointFlags */
+#define PF_POINT_FLAGS_CONTROL_POINT_1 0x2
+#define PF_CLIP_PATH_NONE 0xffffffffu
+
+PFSceneRef PFSceneCreate(void);                 /* Scene::new, scene.rs:55-69 */
+void PFSceneDestroy(PFSceneRef scene);          /* c/src/lib.rs:786 */
+void PFSceneSetViewBox(PFSceneRef scene, const PFRectF *view_box); /* scene.rs:223-226 */
+void PFSceneGetViewBox(PFSceneRef scene, PFRectF *view_box);
+void PFSceneGetBounds(PFSceneRef scene, PFRectF *bounds);
+/* Scene::push_paint for a solid colour (scene.rs:186-190, paint.rs Palette::push_paint dedups). */
+uint16_t PFScenePushPaint(PFSceneRef scene, const PFColorU *color);
+/* Scene::push_draw_path (scene.rs:77-82). The outline is given as contours of points + flags:
+ * contour i owns points [contour_offsets[i], contour_offsets[i+1]). Returns the DrawPathId. */
+uint32_t PFScenePushDrawPath(PFSceneRef scene, const PFVector2F *points, const uint8_t *point_flags,
+                             const uint32_t *contour_offsets, uint32_t contour_count,
+                             uint16_t paint_id, uint8_t fill_rule, uint8_t blend_mode,
+                             uint32_t clip_path_id);
+/* Scene::push_clip_path (scene.rs:99-106). */
+uint32_t PFScenePushClipPath(PFSceneRef scene, const PFVector2F *points, const uint8_t *point_flags,
+                             const uint32_t *contour_offsets, uint32_t contour_count,
+                             uint8_t fill_rule, uint32_t clip_path_id);
+/* Bulk form of repeated PFScenePushDrawPath calls (large synthetic scenes): path i owns contours
+ * [path_contour_offsets[i], path_contour_offsets[i+1]). */
+PFCudaStatus PFScenePushDrawPaths(PFSceneRef scene, const PFVector2F *points, const uint8_t *point_flags,
+                                  size_t point_count, const uint32_t *contour_offsets,
+                                  size_t contour_count, const uint32_t *path_contour_offsets,
+                                  size_t path_count, const uint16_t *paint_ids,
+                                  const uint8_t *fill_rules, const uint32_t *clip_path_ids);
+uint32_t PFSceneGetDrawPathCount(PFSceneRef scene);
+uint32_t PFSceneGetEpoch(PFSceneRef scene);
+
+PFRenderTransformRef PFRenderTransformCreate2D(const PFTransform2F *transform); /* c/src/lib.rs:740 */
+void PFRenderTransformDestroy(PFRenderTransformRef transform);                  /* c/src/lib.rs:752 */
+PFBuildOptionsRef PFBuildOptionsCreate(void);                                   /* c/src/lib.rs:757 */
+void PFBuildOptionsDestroy(PFBuildOptionsRef options);                          /* c/src/lib.rs:762 */
+/* Consumes the transform (c/src/lib.rs:768-772). */
+void PFBuildOptionsSetTransform(PFBuildOptionsRef options, PFRenderTransformRef transform);
+void PFBuildOptionsSetDilation(PFBuildOptionsRef options, const PFVector2F *dilation); /* :774 */
+void PFBuildOptionsSetSubpixelAAEnabled(PFBuildOptionsRef options, int32_t enabled);   /* :780 */
+
+/* RenderCommandListener (renderer/src/options.rs:31-49): called once per command, in the order
+ * SceneBuilder::build sends them; payload pointers are valid only during the call. A non-zero
+ * return aborts the build and is returned from PFSceneBuild. */
+typedef PFCudaStatus (*PFRenderCommandListenerFn)(const PFRenderCommand *command, void *userdata);
+
+/* Scene::build at RendererLevel::D3D11 with a SequentialExecutor (scene.rs:290-297). `sink_state`
+ * carries SceneSink.last_scene across builds (scene.rs:384-396): pass the address of a
+ * zero-initialised PFSceneSinkState kept alongside the renderer. */
+typedef struct PFSceneSinkState { uint32_t has_last_scene, last_scene_id, last_scene_epoch; } PFSceneSinkState;
+PFCudaStatus PFSceneBuild(PFSceneRef scene, PFBuildOptionsRef options, PFSceneSinkState *sink_state,
+                          PFRenderCommandListenerFn listener, void *userdata);
+
+/* Scene::build_and_render (scene.rs:369-378) against the CUDA renderer: begin_scene, build with a
+ * listener forwarding to PFCudaRendererRenderCommand, end_scene. Borrows everything
+ * (as PFSceneProxyBuildAndRenderGL, c/src/lib.rs:672-681). */
+PFCudaStatus PFSceneBuildAndRenderCuda(PFSceneRef scene, PFCudaRendererRef renderer,
+                                       PFBuildOptionsRef options);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_CUDA_H */

@@ -1,0 +1,304 @@
+"""Python mirror of the `pathfinder_renderer` surface for the CUDA backend, over the C ABI.
+
+Names and call protocol follow the reference so parity tests read like its own drivers:
+  Scene / BuildOptions                    renderer/src/scene.rs:36-226, options.rs:50-61
+  Scene::build / build_and_render         renderer/src/scene.rs:290-297, 369-378
+  Renderer::{begin_scene, render_command, end_scene}   renderer/src/gpu/renderer.rs:350-460
+  RendererOptions / RendererMode / RendererLevel       renderer/src/gpu/options.rs:19-119
+All compute happens in libpf_cuda.so; nothing here has a CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from . import area_lut as _area_lut
+from .flat_scene import FlatScene
+
+FILL_DTYPE = np.dtype([("from_x", "<u2"), ("from_y", "<u2"), ("to_x", "<u2"), ("to_y", "<u2"), ("link", "<u4")])
+TILE_DTYPE = np.dtype([("tile_x", "<i2"), ("tile_y", "<i2"), ("alpha_tile_id", "<u4"), ("path_id", "<u4"),
+                       ("color", "<u2"), ("ctrl", "u1"), ("backdrop", "i1")])
+
+
+class RendererLevel:
+    D3D9 = L.PF_RENDERER_LEVEL_D3D9
+    D3D11 = L.PF_RENDERER_LEVEL_D3D11
+
+
+class Transform2F:
+    """geometry/src/transform2d.rs Transform2F: matrix [m11 m12; m21 m22] + vector."""
+
+    def __init__(self, m11=1.0, m12=0.0, m21=0.0, m22=1.0, tx=0.0, ty=0.0):
+        f = np.float32
+        self.m11, self.m12, self.m21, self.m22, self.tx, self.ty = f(m11), f(m12), f(m21), f(m22), f(tx), f(ty)
+
+    @staticmethod
+    def from_scale(sx, sy=None) -> "Transform2F":
+        return Transform2F(sx, 0, 0, sx if sy is None else sy, 0, 0)
+
+    def translate(self, tx, ty) -> "Transform2F":
+        """Transform2F::translate: from_translation(v) * self (transform2d.rs:262-266)."""
+        f = np.float32
+        return Transform2F(self.m11, self.m12, self.m21, self.m22, f(self.tx) + f(tx), f(self.ty) + f(ty))
+
+    def as_oracle_tuple(self):
+        return (self.m11, self.m21, self.m12, self.m22, self.tx, self.ty)
+
+    def _c(self) -> L.PFTransform2F:
+        return L.PFTransform2F(L.PFMatrix2x2F(self.m11, self.m12, self.m21, self.m22), L.PFVector2F(self.tx, self.ty))
+
+
+class BuildOptions:
+    """renderer/src/options.rs:50-61."""
+
+    def __init__(self, transform: Transform2F | None = None, dilation=(0.0, 0.0), subpixel_aa_enabled=False):
+        self.transform = transform
+        self.dilation = dilation
+        self.subpixel_aa_enabled = subpixel_aa_enabled
+        lib = L.lib()
+        self._h = lib.PFBuildOptionsCreate()
+        if transform is not None:
+            t = transform._c()
+            lib.PFBuildOptionsSetTransform(self._h, lib.PFRenderTransformCreate2D(C.byref(t)))
+        d = L.PFVector2F(float(dilation[0]), float(dilation[1]))
+        lib.PFBuildOptionsSetDilation(self._h, C.byref(d))
+        lib.PFBuildOptionsSetSubpixelAAEnabled(self._h, int(bool(subpixel_aa_enabled)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                L.lib().PFBuildOptionsDestroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class Scene:
+    """renderer/src/scene.rs Scene (solid-colour draw paths)."""
+
+    def __init__(self):
+        self._h = L.lib().PFSceneCreate()
+
+    @staticmethod
+    def from_flat(flat: FlatScene) -> "Scene":
+        s = Scene()
+        s.set_view_box(flat.view_box)
+        lib = L.lib()
+        remap = np.zeros(len(flat.paint_colors), dtype=np.uint16)
+        for i, c in enumerate(flat.paint_colors):
+            remap[i] = s.push_paint(c)
+        paints = np.ascontiguousarray(remap[flat.paints], dtype=np.uint16)
+        L.check(lib.PFScenePushDrawPaths(
+            s._h, flat.points.ctypes.data, flat.point_flags.ctypes.data, len(flat.points),
+            flat.contour_offsets.ctypes.data, flat.n_contours, flat.path_contour_offsets.ctypes.data,
+            flat.n_paths, paints.ctypes.data, flat.fill_rules.ctypes.data, None))
+        return s
+
+    def set_view_box(self, view_box):
+        r = L.PFRectF(L.PFVector2F(view_box[0], view_box[1]), L.PFVector2F(view_box[2], view_box[3]))
+        L.lib().PFSceneSetViewBox(self._h, C.byref(r))
+
+    def view_box(self):
+        r = L.PFRectF()
+        L.lib().PFSceneGetViewBox(self._h, C.byref(r))
+        return (r.origin.x, r.origin.y, r.lower_right.x, r.lower_right.y)
+
+    def push_paint(self, rgba) -> int:
+        c = L.PFColorU(int(rgba[0]), int(rgba[1]), int(rgba[2]), int(rgba[3]))
+        return int(L.lib().PFScenePushPaint(self._h, C.byref(c)))
+
+    def push_draw_path(self, points, point_flags, contour_offsets, paint_id, fill_rule=0, blend_mode=0,
+                       clip_path_id=0xFFFFFFFF) -> int:
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
+        fl = np.ascontiguousarray(point_flags, dtype=np.uint8)
+        co = np.ascontiguousarray(contour_offsets, dtype=np.uint32)
+        return int(L.lib().PFScenePushDrawPath(self._h, pts.ctypes.data, fl.ctypes.data, co.ctypes.data,
+                                               len(co) - 1, paint_id, fill_rule, blend_mode, clip_path_id))
+
+    def draw_path_count(self) -> int:
+        return int(L.lib().PFSceneGetDrawPathCount(self._h))
+
+    def build(self, options: BuildOptions, listener, sink_state: L.PFSceneSinkState | None = None):
+        """Scene::build at the D3D11 level: calls listener(PFRenderCommand) per command."""
+        state = sink_state if sink_state is not None else L.PFSceneSinkState()
+        errors = []
+
+        def trampoline(cmd_ptr, _userdata):
+            try:
+                listener(cmd_ptr.contents)
+                return 0
+            except L.PathfinderCudaError as e:  # propagate the renderer's status
+                errors.append(e)
+                return e.status
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+                return L.PF_CUDA_ERROR_INVALID_ARGUMENT
+
+        cb = L.LISTENER_FN(trampoline)
+        status = L.lib().PFSceneBuild(self._h, options._h, C.byref(state), cb, None)
+        if errors:
+            raise errors[0]
+        L.check(status)
+
+    def build_and_render(self, renderer: "CudaRenderer", options: BuildOptions):
+        """Scene::build_and_render (scene.rs:369-378)."""
+        L.check(L.lib().PFSceneBuildAndRenderCuda(self._h, renderer._h, options._h))
+
+    def __del__(self):
+        try:
+            if self._h:
+                L.lib().PFSceneDestroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class CudaRenderer:
+    """Renderer<CudaDevice> at RendererLevel::D3D11."""
+
+    def __init__(self, dest_size, background_color=None, device_ordinal: int = 0, level: int = RendererLevel.D3D11,
+                 area_lut: np.ndarray | None = None):
+        lib = L.lib()
+        dev = lib.PFCudaDeviceCreate(device_ordinal)
+        if not dev:
+            raise L.PathfinderCudaError(L.PF_CUDA_ERROR_NO_DEVICE, lib.PFCudaGetLastError().decode())
+        self.dest_size = (int(dest_size[0]), int(dest_size[1]))
+        lut = np.ascontiguousarray(_area_lut.generate() if area_lut is None else area_lut, dtype=np.uint8)
+        self._options = self._make_options(self.dest_size, background_color)
+        mode = L.PFRendererMode(level)
+        self._h = lib.PFCudaRendererCreate(dev, lut.ctypes.data, None, C.byref(mode), C.byref(self._options))
+        if not self._h:
+            raise L.PathfinderCudaError(L.PF_CUDA_ERROR_CUDA, lib.PFCudaGetLastError().decode())
+
+    @staticmethod
+    def _make_options(dest_size, background_color):
+        o = L.PFCudaRendererOptions()
+        o.dest_size = L.PFVector2I(dest_size[0], dest_size[1])
+        if background_color is not None:
+            o.background_color = L.PFColorF(*[float(v) for v in background_color])
+            o.flags = L.PF_RENDERER_OPTIONS_FLAGS_HAS_BACKGROUND_COLOR
+        return o
+
+    # -- protocol ---------------------------------------------------------------------------
+    def begin_scene(self):
+        L.check(L.lib().PFCudaRendererBeginScene(self._h))
+
+    def render_command(self, command: L.PFRenderCommand):
+        L.check(L.lib().PFCudaRendererRenderCommand(self._h, C.byref(command)))
+
+    def end_scene(self):
+        L.check(L.lib().PFCudaRendererEndScene(self._h))
+
+    # -- options ----------------------------------------------------------------------------
+    def set_view_box(self, view_box):
+        if view_box is None:
+            L.check(L.lib().PFCudaRendererSetViewBox(self._h, None))
+        else:
+            r = L.PFRectF(L.PFVector2F(view_box[0], view_box[1]), L.PFVector2F(view_box[2], view_box[3]))
+            L.check(L.lib().PFCudaRendererSetViewBox(self._h, C.byref(r)))
+
+    def set_strip(self, tile_y0: int, tile_y1: int):
+        L.check(L.lib().PFCudaRendererSetStrip(self._h, tile_y0, tile_y1))
+
+    def set_stream(self, cuda_stream: int):
+        L.check(L.lib().PFCudaRendererSetStream(self._h, cuda_stream))
+
+    def set_dest_device_pointer(self, ptr: int, pitch: int):
+        L.check(L.lib().PFCudaRendererSetDestDevicePointer(self._h, ptr, pitch))
+
+    def dest_device_pointer(self):
+        p, pitch = C.c_uint64(), C.c_size_t()
+        L.check(L.lib().PFCudaRendererGetDestDevicePointer(self._h, C.byref(p), C.byref(pitch)))
+        return int(p.value), int(pitch.value)
+
+    def set_debug_lists_enabled(self, enabled: bool):
+        L.check(L.lib().PFCudaRendererSetDebugListsEnabled(self._h, int(enabled)))
+
+    def set_timing_enabled(self, enabled: bool):
+        L.check(L.lib().PFCudaRendererSetTimingEnabled(self._h, int(enabled)))
+
+    def synchronize(self):
+        L.check(L.lib().PFCudaRendererSynchronize(self._h))
+
+    # -- results ----------------------------------------------------------------------------
+    def read_pixels(self, out: np.ndarray | None = None) -> np.ndarray:
+        w, h = self.dest_size
+        if out is None:
+            out = np.empty((h, w, 4), dtype=np.uint8)
+        L.check(L.lib().PFCudaRendererReadPixels(self._h, out.ctypes.data, w * 4))
+        return out
+
+    def read_pixels_into(self, host_ptr: int, stride: int):
+        L.check(L.lib().PFCudaRendererReadPixels(self._h, host_ptr, stride))
+
+    def stats(self) -> dict:
+        s = L.PFCudaRenderStats()
+        L.check(L.lib().PFCudaRendererGetStats(self._h, C.byref(s)))
+        return {n: int(getattr(s, n)) for n, _ in s._fields_}
+
+    def times(self) -> dict:
+        t = L.PFCudaRenderTime()
+        L.check(L.lib().PFCudaRendererGetTimes(self._h, C.byref(t)))
+        return {n: float(getattr(t, n)) for n, _ in t._fields_}
+
+    # -- stage-level read-backs (parity tests) --------------------------------------------------
+    @staticmethod
+    def _count(n: int) -> int:
+        if n < 0:
+            raise L.PathfinderCudaError(int(-n), L.lib().PFCudaGetLastError().decode())
+        return int(n)
+
+    def debug_lines(self):
+        lib = L.lib()
+        n = self._count(lib.PFCudaRendererDebugCopyLines(self._h, None, None, 0))
+        lines = np.zeros((n, 4), dtype=np.float32)
+        paths = np.zeros(n, dtype=np.uint32)
+        if n:
+            self._count(lib.PFCudaRendererDebugCopyLines(self._h, lines.ctypes.data, paths.ctypes.data, n))
+        return lines, paths
+
+    def debug_fills(self) -> np.ndarray:
+        lib = L.lib()
+        n = self._count(lib.PFCudaRendererDebugCopyFills(self._h, None, 0))
+        out = np.zeros(n, dtype=FILL_DTYPE)
+        if n:
+            self._count(lib.PFCudaRendererDebugCopyFills(self._h, out.ctypes.data, n))
+        return out
+
+    def debug_tiles(self) -> np.ndarray:
+        lib = L.lib()
+        n = self._count(lib.PFCudaRendererDebugCopyTiles(self._h, None, 0))
+        out = np.zeros(n, dtype=TILE_DTYPE)
+        if n:
+            self._count(lib.PFCudaRendererDebugCopyTiles(self._h, out.ctypes.data, n))
+        return out
+
+    def debug_z_buffer(self):
+        lib = L.lib()
+        rect = (C.c_int32 * 4)()
+        n = self._count(lib.PFCudaRendererDebugCopyZBuffer(self._h, None, 0, C.byref(rect)))
+        out = np.zeros(n, dtype=np.int32)
+        if n:
+            self._count(lib.PFCudaRendererDebugCopyZBuffer(self._h, out.ctypes.data, n, C.byref(rect)))
+        w, h = rect[2] - rect[0], rect[3] - rect[1]
+        return out.reshape(h, w), tuple(rect)
+
+    def debug_alpha_masks(self) -> np.ndarray:
+        lib = L.lib()
+        n = self._count(lib.PFCudaRendererDebugCopyAlphaMasks(self._h, None, 0))
+        out = np.zeros((n, 16, 16), dtype=np.float32)
+        if n:
+            self._count(lib.PFCudaRendererDebugCopyAlphaMasks(self._h, out.ctypes.data, n))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib().PFCudaRendererDestroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,735 @@
+// pathfinder_b200/csrc/kernels.cu — the pipeline stages as hand-written CUDA for sm_100a.
+//
+// Compiled with -fmad=false and without --use_fast_math: the dice and bin stages must reproduce
+// the reference CPU tiler's IEEE binary32 arithmetic operator by operator (one rounding each, no
+// FMA contraction; '/' is IEEE division), because tile / fill / backdrop lists are compared
+// bit-exactly. Where a fused multiply-add is wanted (coverage and
+// compositing, compared at 1/255) it is written explicitly with fmaf().
+//
+// Reference files restated here (paths relative to the reference checkout):
+//   dice       renderer/src/tiler.rs:166-184, content/src/segment.rs:171-183,292-360,
+//              geometry/src/transform2d.rs:123-130,312-318
+//   bin        renderer/src/tiler.rs:191-308, content/src/clip.rs:494-565,
+//              renderer/src/builder.rs:509-616
+//   propagate  renderer/src/tiler.rs:93-163 (backdrop prefix), builder.rs:1013-1029 (z-buffer)
+//   sort       shaders/d3d11/sort.cs.glsl:60-95 (painter's order + z-cull)
+//   fill       shaders/fill_area.inc.glsl:11-27, shaders/d3d11/fill_compute.inc.glsl:11-25
+//   tile       shaders/d3d11/tile.cs.glsl:71-163, shaders/tile_fragment.inc.glsl:539-614
+#include "kernels.cuh"
+
+#include "common.cuh"
+
+namespace pf {
+
+// ---------------------------------------------------------------------------------------------
+// Bit-exact scalar helpers (simd/src/x86/mod.rs semantics).
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float sse_min(float a, float b) { return a < b ? a : b; } // _mm_min_ps
+__device__ __forceinline__ float sse_max(float a, float b) { return a > b ? a : b; } // _mm_max_ps
+__device__ __forceinline__ int cvtps(float x) { return __float2int_rn(x); }          // _mm_cvtps_epi32
+
+// Largest index p in [0, n) with keys[p] <= x, for non-decreasing keys with keys[0] <= x.
+__device__ __forceinline__ uint32_t search_le(const uint32_t *__restrict__ keys, uint32_t n, uint32_t x) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(keys + mid) <= x)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ PathInfo load_path(const PathInfo *__restrict__ paths, uint32_t p) {
+    const int4 *q = reinterpret_cast<const int4 *>(paths + p);
+    int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    PathInfo r;
+    r.min_x = a.x, r.min_y = a.y, r.max_x = a.z, r.max_y = a.w;
+    r.tile_offset = b.x, r.col_offset = b.y, r.seg_batch_first = b.z, r.seg_global_first = b.w;
+    r.global_path_id = c.x, r.paint_ctrl = c.y, r.clip_path_index = c.z, r.pad = c.w;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dice — Bézier flattening by recursive halving, one thread per input segment.
+// ---------------------------------------------------------------------------------------------
+
+struct Cubic {
+    float2 p0, p1, p2, p3;
+};
+
+// Transform2F * Vector2F (geometry/src/transform2d.rs:123-130,312-318).
+__device__ __forceinline__ float2 xf_apply(const Transform &t, float2 p) {
+    if (t.identity) return p; // Outline::transform short-circuits (content/src/outline.rs:208-211)
+    float hx = t.m11 * p.x, hy = t.m21 * p.x, hz = t.m12 * p.y, hw = t.m22 * p.y;
+    return make_float2((hx + hz) + t.tx, (hy + hw) + t.ty);
+}
+
+// CubicSegment::is_flat(0.25) (content/src/segment.rs:292-300).
+__device__ __forceinline__ bool cubic_is_flat(const Cubic &c) {
+    float u0x = ((3.0f * c.p1.x - c.p0.x) - c.p0.x) - c.p3.x;
+    float u0y = ((3.0f * c.p1.y - c.p0.y) - c.p0.y) - c.p3.y;
+    float u1x = ((3.0f * c.p2.x - c.p3.x) - c.p3.x) - c.p0.x;
+    float u1y = ((3.0f * c.p2.y - c.p3.y) - c.p3.y) - c.p0.y;
+    u0x = u0x * u0x, u0y = u0y * u0y, u1x = u1x * u1x, u1y = u1y * u1y;
+    float mx = sse_max(u0x, u1x), my = sse_max(u0y, u1y);
+    return mx + my <= 1.0f; // 16 * 0.25 * 0.25
+}
+
+__device__ __forceinline__ float2 lerp_half(float2 a, float2 b) { // a + t * (b - a), t = 0.5
+    return make_float2(a.x + 0.5f * (b.x - a.x), a.y + 0.5f * (b.y - a.y));
+}
+
+constexpr int DICE_MAX_DEPTH = 40; // f32 halving collapses long before; the oracle uses the same cap
+
+template <bool EMIT>
+__global__ void __launch_bounds__(128)
+    k_dice(BatchDev b, uint32_t *__restrict__ seg_line_count, const uint32_t *__restrict__ seg_line_offset,
+           float4 *__restrict__ lines, uint32_t *__restrict__ line_path, uint32_t line_capacity) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.n_segments) return;
+    uint32_t p = search_le(b.path_seg_first, b.n_paths, s);
+    const PathInfo *pi = b.paths + p;
+    uint32_t gseg = __ldg(&pi->seg_global_first) + (s - __ldg(&pi->seg_batch_first));
+    uint2 si = __ldg(b.seg_indices + gseg);
+    const float2 *pts = b.points + si.x;
+
+    uint32_t out = EMIT ? seg_line_offset[s] : 0;
+    uint32_t n = 0;
+    auto emit_line = [&](float2 from, float2 to) {
+        if (EMIT) {
+            uint32_t o = out + n;
+            if (o < line_capacity) {
+                lines[o] = make_float4(from.x, from.y, to.x, to.y);
+                line_path[o] = p;
+            }
+        }
+        n++;
+    };
+
+    const bool is_cubic = (si.y & 0x40000000u) != 0, is_quad = (si.y & 0x80000000u) != 0;
+    if (!is_cubic && !is_quad) {
+        emit_line(xf_apply(b.xf, __ldg(pts)), xf_apply(b.xf, __ldg(pts + 1)));
+    } else {
+        Cubic cur;
+        cur.p0 = xf_apply(b.xf, __ldg(pts));
+        if (is_cubic) {
+            cur.p1 = xf_apply(b.xf, __ldg(pts + 1));
+            cur.p2 = xf_apply(b.xf, __ldg(pts + 2));
+            cur.p3 = xf_apply(b.xf, __ldg(pts + 3));
+        } else {
+            // Segment::to_cubic (content/src/segment.rs:171-183)
+            float2 c = xf_apply(b.xf, __ldg(pts + 1));
+            cur.p3 = xf_apply(b.xf, __ldg(pts + 2));
+            float2 c2 = make_float2(c.x + c.x, c.y + c.y);
+            const float third = 1.0f / 3.0f;
+            cur.p1 = make_float2((cur.p0.x + c2.x) * third, (cur.p0.y + c2.y) * third);
+            cur.p2 = make_float2((c2.x + cur.p3.x) * third, (c2.y + cur.p3.y) * third);
+        }
+        // process_segment (renderer/src/tiler.rs:166-184) with an explicit stack: left half first.
+        Cubic stack[DICE_MAX_DEPTH];
+        unsigned char depth_stack[DICE_MAX_DEPTH];
+        int sp = 0;
+        int depth = 0;
+        for (;;) {
+            if (cubic_is_flat(cur) || depth >= DICE_MAX_DEPTH) {
+                emit_line(cur.p0, cur.p3);
+                if (sp == 0) break;
+                sp--;
+                cur = stack[sp];
+                depth = depth_stack[sp];
+            } else {
+                // CubicSegment::split(0.5) (content/src/segment.rs:307-360)
+                float2 p01 = lerp_half(cur.p0, cur.p1), p12 = lerp_half(cur.p1, cur.p2),
+                       p23 = lerp_half(cur.p2, cur.p3);
+                float2 p012 = lerp_half(p01, p12), p123 = lerp_half(p12, p23);
+                float2 p0123 = lerp_half(p012, p123);
+                Cubic right;
+                right.p0 = p0123, right.p1 = p123, right.p2 = p23, right.p3 = cur.p3;
+                depth++;
+                stack[sp] = right;
+                depth_stack[sp] = (unsigned char)depth;
+                sp++;
+                cur.p1 = p01, cur.p2 = p012, cur.p3 = p0123;
+            }
+        }
+    }
+    if (!EMIT) seg_line_count[s] = n;
+}
+
+int launch_dice(bool emit, const BatchDev &b, uint32_t *seg_line_count, const uint32_t *seg_line_offset,
+                float4 *lines, uint32_t *line_path, uint32_t line_capacity, cudaStream_t stream) {
+    if (b.n_segments == 0) return 0;
+    unsigned grid = div_up(b.n_segments, 128);
+    if (emit)
+        k_dice<true><<<grid, 128, 0, stream>>>(b, seg_line_count, seg_line_offset, lines, line_path, line_capacity);
+    else
+        k_dice<false><<<grid, 128, 0, stream>>>(b, seg_line_count, seg_line_offset, lines, line_path, line_capacity);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bin — segment-to-tile lattice clipping, one thread per flattened line.
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float lerpf(float a, float b, float t) { return a + (b - a) * t; } // util.rs:25-27
+
+// clip_line_segment_to_rect (content/src/clip.rs:494-565) against
+// [vb.min_x, vb.max_x] x [-inf, vb.max_y] (renderer/src/tiler.rs:194-200).
+__device__ __forceinline__ bool clip_line(float2 &from, float2 &to, const ViewBox &vb) {
+    auto outcode = [&](float2 q) -> unsigned {
+        unsigned o = 0;
+        if (q.x < vb.min_x) o |= 1u; // LEFT
+        if (q.x > vb.max_x) o |= 2u; // RIGHT
+        if (q.y > vb.max_y) o |= 8u; // BOTTOM   (TOP is -inf: never set)
+        return o;
+    };
+    unsigned of = outcode(from), ot = outcode(to);
+    for (;;) {
+        if ((of | ot) == 0) return true;
+        if ((of & ot) != 0) return false;
+        bool clip_from = of > ot;
+        float2 point = clip_from ? from : to;
+        unsigned oc = clip_from ? of : ot;
+        if (oc & 1u) {
+            point = make_float2(vb.min_x, lerpf(from.y, to.y, (vb.min_x - from.x) / (to.x - from.x)));
+        } else if (oc & 2u) {
+            point = make_float2(vb.max_x, lerpf(from.y, to.y, (vb.max_x - from.x) / (to.x - from.x)));
+        } else if (oc & 8u) {
+            point = make_float2(lerpf(from.x, to.x, (vb.max_y - from.y) / (to.y - from.y)), vb.max_y);
+        }
+        if (clip_from) {
+            from = point;
+            of = outcode(point);
+        } else {
+            to = point;
+            ot = outcode(point);
+        }
+    }
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(128) k_bin(BatchDev b, BinArgs a) {
+    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= a.n_lines) return;
+    float4 seg = __ldg(a.lines + l);
+    uint32_t p = __ldg(a.line_path + l);
+    const PathInfo path = load_path(b.paths, p);
+    const int rect_w = path.max_x - path.min_x, rect_h = path.max_y - path.min_y;
+
+    uint32_t emitted = 0;
+    const uint32_t out_base = EMIT ? __ldg(a.line_fill_offset + l) : 0;
+
+    // ObjectBuilder::add_fill (renderer/src/builder.rs:509-553)
+    auto add_fill = [&](float2 from, float2 to, int tx, int ty) {
+        int ox = tx - path.min_x, oy = ty - path.min_y;
+        if (ox < 0 || oy < 0 || ox >= rect_w || oy >= rect_h) return; // tile_coords_to_local_index
+        float ulx = (float)tx * 16.0f, uly = (float)ty * 16.0f;
+        int fx = cvtps(sse_min(sse_max((from.x - ulx) * 256.0f, 0.0f), 4095.0f));
+        int fy = cvtps(sse_min(sse_max((from.y - uly) * 256.0f, 0.0f), 4095.0f));
+        int tx8 = cvtps(sse_min(sse_max((to.x - ulx) * 256.0f, 0.0f), 4095.0f));
+        int ty8 = cvtps(sse_min(sse_max((to.y - uly) * 256.0f, 0.0f), 4095.0f));
+        if (fx == tx8) return; // cull degenerate fills
+        uint32_t t = path.tile_offset + (uint32_t)(ox + rect_w * oy);
+        if (!EMIT) {
+            atomicAdd(a.tile_word + t, 1u);
+        } else {
+            uint32_t e = out_base + emitted;
+            uint32_t pos = atomicAdd(a.tile_fill_pos + t, 1u);
+            uint32_t from_w = (uint32_t)fx | ((uint32_t)fy << 16), to_w = (uint32_t)tx8 | ((uint32_t)ty8 << 16);
+            if (pos < a.fill_capacity) a.fills[pos] = make_uint2(from_w, to_w);
+            if (a.tile_first_fill) atomicMin(a.tile_first_fill + t, e);
+            if (a.fills_emit && e < a.fill_capacity) a.fills_emit[e] = EmitFill{from_w, to_w, t};
+        }
+        emitted++;
+    };
+    // ObjectBuilder::adjust_alpha_tile_backdrop (renderer/src/builder.rs:595-616); count pass only.
+    auto adjust_backdrop = [&](int tx, int ty, int delta) {
+        if (EMIT) return;
+        int ox = tx - path.min_x, oy = ty - path.min_y;
+        if (ox < 0 || ox >= rect_w || oy >= rect_h) return;
+        if (oy < 0) {
+            atomicAdd(a.col_backdrop + path.col_offset + ox, delta);
+            return;
+        }
+        // i8 wrapping add in the top byte of the tile word (no carry reaches the count bits).
+        atomicAdd(a.tile_word + path.tile_offset + (uint32_t)(ox + rect_w * oy), (uint32_t)delta << 24);
+    };
+
+    float2 from = make_float2(seg.x, seg.y), to = make_float2(seg.z, seg.w);
+    if (rect_w > 0 && clip_line(from, to, b.view_box)) {
+        // process_line_segment (renderer/src/tiler.rs:202-308)
+        const float tile_size = 16.0f, recip = 1.0f / 16.0f;
+        int from_tx = cvtps(floorf(from.x * recip)), from_ty = cvtps(floorf(from.y * recip));
+        int to_tx = cvtps(floorf(to.x * recip)), to_ty = cvtps(floorf(to.y * recip));
+        float vx = to.x - from.x, vy = to.y - from.y;
+        bool neg_x = vx < 0.0f, neg_y = vy < 0.0f;
+        int step_x = neg_x ? -1 : 1, step_y = neg_y ? -1 : 1;
+        float first_cross_x = (float)(from_tx + (neg_x ? 0 : 1)) * tile_size;
+        float first_cross_y = (float)(from_ty + (neg_y ? 0 : 1)) * tile_size;
+        float t_max_x = (first_cross_x - from.x) / vx;
+        float t_max_y = (first_cross_y - from.y) / vy;
+        float t_delta_x = fabsf(tile_size / vx);
+        float t_delta_y = fabsf(tile_size / vy);
+
+        float2 cur = from;
+        int tx = from_tx, ty = from_ty;
+        int last_step = 0; // 0 none, 1 X, 2 Y
+        for (;;) {
+            int next_step;
+            if (t_max_x < t_max_y)
+                next_step = 1;
+            else if (t_max_x > t_max_y)
+                next_step = 2;
+            else
+                next_step = step_x > 0 ? 1 : 2;
+            float next_t = fminf(next_step == 1 ? t_max_x : t_max_y, 1.0f);
+            if (tx == to_tx && ty == to_ty) next_step = 0;
+            float2 next = make_float2(from.x + vx * next_t, from.y + vy * next_t);
+            add_fill(cur, next, tx, ty);
+            if (step_y < 0 && next_step == 2) {
+                add_fill(next, make_float2((float)tx * tile_size, (float)ty * tile_size), tx, ty);
+            } else if (step_y > 0 && last_step == 2) {
+                add_fill(make_float2((float)tx * tile_size, (float)ty * tile_size), cur, tx, ty);
+            }
+            if (step_x < 0 && last_step == 1) {
+                adjust_backdrop(tx, ty, 1);
+            } else if (step_x > 0 && next_step == 1) {
+                adjust_backdrop(tx, ty, -1);
+            }
+            if (next_step == 0) break;
+            if (next_step == 1) {
+                if (tx == to_tx) break;
+                t_max_x += t_delta_x;
+                t_max_y += 0.0f;
+                tx += step_x;
+            } else {
+                if (ty == to_ty) break;
+                t_max_x += 0.0f;
+                t_max_y += t_delta_y;
+                ty += step_y;
+            }
+            cur = next;
+            last_step = next_step;
+        }
+    }
+    if (!EMIT) a.line_fill_count[l] = emitted;
+}
+
+int launch_bin(bool emit, const BatchDev &b, const BinArgs &args, cudaStream_t stream) {
+    if (args.n_lines == 0) return 0;
+    unsigned grid = div_up(args.n_lines, 128);
+    if (emit)
+        k_bin<true><<<grid, 128, 0, stream>>>(b, args);
+    else
+        k_bin<false><<<grid, 128, 0, stream>>>(b, args);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// propagate — backdrop prefix sums down tile columns + occluder z-writes, one thread per column.
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128)
+    k_propagate(BatchDev b, uint32_t *__restrict__ tile_word, const int32_t *__restrict__ col_backdrop,
+                int32_t *__restrict__ z_buffer) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b.n_columns) return;
+    uint32_t p = search_le(b.path_col_offset, b.n_paths, c);
+    const PathInfo path = load_path(b.paths, p);
+    const int w = path.max_x - path.min_x, h = path.max_y - path.min_y;
+    const int x = (int)(c - path.col_offset);
+    const bool z_write = (path.paint_ctrl >> 24) & 1u;
+    const int fb_w = b.fb.max_x - b.fb.min_x;
+    const int fx = path.min_x + x - b.fb.min_x;
+    const bool fx_ok = fx >= 0 && fx < fb_w;
+    int32_t backdrop = col_backdrop[c];
+    uint32_t t = path.tile_offset + (uint32_t)x;
+    for (int y = 0; y < h; y++, t += (uint32_t)w) {
+        uint32_t word = tile_word[t];
+        int delta = (int)(int8_t)(word >> 24);
+        uint32_t count = word & 0x00ffffffu;
+        int8_t b8 = (int8_t)backdrop; // backdrops[column] as i8   (renderer/src/tiler.rs:112)
+        tile_word[t] = count | ((uint32_t)(uint8_t)b8 << 24);
+        // Occluder z-write for solid tiles (renderer/src/builder.rs:1014-1028; twin:
+        // shaders/d3d11/propagate.cs.glsl:204-208). The fill rule is ignored, as in the reference.
+        if (z_write && count == 0 && b8 != 0 && fx_ok) {
+            int fy = path.min_y + y - b.fb.min_y;
+            if (fy >= 0 && fy < b.fb.max_y - b.fb.min_y)
+                atomicMax(z_buffer + (size_t)fy * fb_w + fx, (int32_t)path.global_path_id);
+        }
+        backdrop += delta; // backdrops[column] += delta (i32)   (renderer/src/tiler.rs:161)
+    }
+}
+
+int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_backdrop, int32_t *z_buffer,
+                     cudaStream_t stream) {
+    if (b.n_columns == 0) return 0;
+    k_propagate<<<div_up(b.n_columns, 128), 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sort — per-framebuffer-tile painter's-order lists with z-cull.
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+    k_list_flags(BatchDev b, const uint32_t *__restrict__ tile_word, const int32_t *__restrict__ z_buffer,
+                 uint32_t *__restrict__ tile_fb) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= b.n_tiles) return;
+    uint32_t word = __ldg(tile_word + t);
+    uint32_t result = 0xffffffffu;
+    // Empty tiles are never drawn (renderer/src/builder.rs:1014-1016).
+    if ((word & 0x00ffffffu) != 0 || (word >> 24) != 0) {
+        uint32_t p = search_le(b.path_tile_offset, b.n_paths, t);
+        const PathInfo path = load_path(b.paths, p);
+        int w = path.max_x - path.min_x;
+        uint32_t local = t - path.tile_offset;
+        int x = (int)(local % (uint32_t)w), y = (int)(local / (uint32_t)w);
+        int fx = path.min_x + x - b.fb.min_x, fy = path.min_y + y - b.fb.min_y;
+        int fb_w = b.fb.max_x - b.fb.min_x, fb_h = b.fb.max_y - b.fb.min_y;
+        if (fx >= 0 && fy >= 0 && fx < fb_w && fy < fb_h) {
+            uint32_t fbi = (uint32_t)(fy * fb_w + fx);
+            // z-cull: dropped iff path_id < z (shaders/d3d11/sort.cs.glsl:74, d3d9/tile.vs.glsl:52-56)
+            if ((int32_t)path.global_path_id >= __ldg(z_buffer + fbi)) result = fbi;
+        }
+    }
+    tile_fb[t] = result;
+}
+
+int launch_list_flags(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
+                      cudaStream_t stream) {
+    if (b.n_tiles == 0) return 0;
+    k_list_flags<<<div_up(b.n_tiles, 256), 256, 0, stream>>>(b, tile_word, z_buffer, tile_fb);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+__global__ void __launch_bounds__(256)
+    k_list_emit(uint32_t n_tiles, const uint32_t *__restrict__ tile_fb, const uint32_t *__restrict__ tile_pos,
+                uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t capacity) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    uint32_t fbi = __ldg(tile_fb + t);
+    if (fbi == 0xffffffffu) return;
+    uint32_t pos = __ldg(tile_pos + t);
+    if (pos < capacity) {
+        keys[pos] = fbi;
+        vals[pos] = t;
+    }
+}
+
+int launch_list_emit(uint32_t n_tiles, const uint32_t *tile_fb, const uint32_t *tile_pos, uint32_t *keys,
+                     uint32_t *vals, uint32_t capacity, cudaStream_t stream) {
+    if (n_tiles == 0) return 0;
+    k_list_emit<<<div_up(n_tiles, 256), 256, 0, stream>>>(n_tiles, tile_fb, tile_pos, keys, vals, capacity);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+__global__ void __launch_bounds__(256)
+    k_build_entries(BatchDev b, uint32_t n_entries, const uint32_t *__restrict__ keys,
+                    const uint32_t *__restrict__ vals, const uint32_t *__restrict__ tile_word,
+                    const uint32_t *__restrict__ tile_fill_pos, TileEntry *__restrict__ entries,
+                    uint32_t *__restrict__ fb_start, uint32_t *__restrict__ fb_end) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_entries) return;
+    uint32_t fbi = __ldg(keys + i), t = __ldg(vals + i);
+    uint32_t p = search_le(b.path_tile_offset, b.n_paths, t);
+    TileEntry e;
+    e.fill_end = __ldg(tile_fill_pos + t); // the emit pass left the cursor at the end of the run
+    e.word = __ldg(tile_word + t);
+    e.paint_ctrl = __ldg(&b.paths[p].paint_ctrl) & 0x00ffffffu;
+    e.path_id = __ldg(&b.paths[p].global_path_id);
+    *reinterpret_cast<uint4 *>(entries + i) = *reinterpret_cast<uint4 *>(&e);
+    if (i == 0 || __ldg(keys + i - 1) != fbi) fb_start[fbi] = i;
+    if (i + 1 == n_entries || __ldg(keys + i + 1) != fbi) fb_end[fbi] = i + 1;
+}
+
+int launch_build_entries(const BatchDev &b, uint32_t n_entries, const uint32_t *keys, const uint32_t *vals,
+                         const uint32_t *tile_word, const uint32_t *tile_fill_pos, TileEntry *entries,
+                         uint32_t *fb_start, uint32_t *fb_end, cudaStream_t stream) {
+    if (n_entries == 0) return 0;
+    k_build_entries<<<div_up(n_entries, 256), 256, 0, stream>>>(b, n_entries, keys, vals, tile_word, tile_fill_pos,
+                                                                 entries, fb_start, fb_end);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fill + tile (fused) — exact-area coverage from the LUT, fill rule, paint, SrcOver blend.
+// ---------------------------------------------------------------------------------------------
+
+// Coverage contributions are accumulated as integers so the sum does not depend on the order of
+// a tile's fills (the tile-grouped fill array is filled through an atomic cursor): adding
+// 1.5 * 2^8 pins the float's exponent so its mantissa is the contribution in units of 2^-15.
+constexpr float COV_MAGIC = 384.0f;
+constexpr uint32_t COV_MAGIC_BITS = 0x43c00000u;
+constexpr float COV_SCALE = 1.0f / 32768.0f;
+
+// computeCoverage (shaders/fill_area.inc.glsl:11-27) for the 4-row strip whose first pixel centre
+// is (cx, cy) in tile space; acc[k] accumulates row k.
+__device__ __forceinline__ void accumulate_fill(PackedFill f, float cx, float cy, cudaTextureObject_t lut,
+                                                uint32_t acc[4]) {
+    const float s = 1.0f / 256.0f;
+    float from_x = fmaf((float)(f.x & 0xffffu), s, -cx), from_y = fmaf((float)(f.x >> 16), s, -cy);
+    float to_x = fmaf((float)(f.y & 0xffffu), s, -cx), to_y = fmaf((float)(f.y >> 16), s, -cy);
+    float wx = fminf(fmaxf(from_x, -0.5f), 0.5f), wy = fminf(fmaxf(to_x, -0.5f), 0.5f);
+    float dX = wx - wy;
+    if (dX == 0.0f) { // the pixel column is outside the segment's x range: LUT * 0
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[k] += COV_MAGIC_BITS;
+        return;
+    }
+    bool from_left = from_x < to_x;
+    float lx = from_left ? from_x : to_x, ly = from_left ? from_y : to_y;
+    float rx = from_left ? to_x : from_x, ry = from_left ? to_y : from_y;
+    float inv = __frcp_rn(rx - lx);
+    float offset = 0.5f * (wx + wy) - lx;
+    float t = offset * inv;
+    float y = fmaf(ry - ly, t, ly);
+    float d = (ry - ly) * inv;
+    float4 tex = tex2D<float4>(lut, (y + 8.0f) * (1.0f / 16.0f), fabsf(d * dX) * (1.0f / 16.0f));
+    acc[0] += __float_as_uint(fmaf(tex.x, dX, COV_MAGIC));
+    acc[1] += __float_as_uint(fmaf(tex.y, dX, COV_MAGIC));
+    acc[2] += __float_as_uint(fmaf(tex.z, dX, COV_MAGIC));
+    acc[3] += __float_as_uint(fmaf(tex.w, dX, COV_MAGIC));
+}
+
+__device__ __forceinline__ float finish_coverage(uint32_t acc, uint32_t count) {
+    return (float)(int32_t)(acc - count * COV_MAGIC_BITS) * COV_SCALE;
+}
+
+// sampleMask (shaders/tile_fragment.inc.glsl:539-556) on coverage = mask + backdrop.
+__device__ __forceinline__ float mask_alpha(float coverage, uint32_t ctrl) {
+    if (ctrl & 1u) { // TILE_CTRL_MASK_WINDING
+        coverage = fabsf(coverage);
+    } else if (ctrl & 2u) { // TILE_CTRL_MASK_EVEN_ODD
+        float m = coverage - 2.0f * floorf(coverage * 0.5f);
+        coverage = 1.0f - fabsf(1.0f - m);
+    } else {
+        coverage = 1.0f;
+    }
+    return fminf(1.0f, coverage);
+}
+
+__device__ __forceinline__ uint32_t pack_rgba8(float r, float g, float b, float a) {
+    uint32_t R = __float2uint_rn(__saturatef(r) * 255.0f), G = __float2uint_rn(__saturatef(g) * 255.0f);
+    uint32_t B = __float2uint_rn(__saturatef(b) * 255.0f), A = __float2uint_rn(__saturatef(a) * 255.0f);
+    return R | (G << 8) | (B << 16) | (A << 24);
+}
+
+// One 64-thread group per framebuffer tile: thread (x, strip) owns column x, rows 4*strip..+3,
+// exactly the 16x4 workgroup of shaders/d3d11/tile.cs.glsl:22 — but the mask never leaves
+// registers: fill (coverage) and tile (composite) are one kernel.
+constexpr int COMPOSITE_TILES_PER_BLOCK = 4;
+
+__global__ void __launch_bounds__(64 * COMPOSITE_TILES_PER_BLOCK) k_composite(CompositeArgs a) {
+    const int group = threadIdx.x >> 6, tid = threadIdx.x & 63;
+    const int fb_w = a.fb.max_x - a.fb.min_x;
+    const int tiles_x_groups = (fb_w + COMPOSITE_TILES_PER_BLOCK - 1) / COMPOSITE_TILES_PER_BLOCK;
+    const int tile_col = (blockIdx.x % tiles_x_groups) * COMPOSITE_TILES_PER_BLOCK + group;
+    const int tile_row = a.tile_y0 + blockIdx.x / tiles_x_groups; // absolute tile y
+    if (tile_col >= fb_w) return;
+    const int tx = a.fb.min_x + tile_col, ty = tile_row;
+    const int x = tid & 15, strip = tid >> 4;
+    const int px = tx * 16 + x, py0 = ty * 16 + strip * 4;
+    if (px < 0 || px >= a.dest_w) return;
+
+    float4 dst[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int py = py0 + k;
+        if (a.load_dest && py >= 0 && py < a.dest_h) {
+            uint32_t v = *reinterpret_cast<const uint32_t *>(a.dest + (size_t)py * a.dest_pitch + (size_t)px * 4);
+            const float s = 1.0f / 255.0f;
+            dst[k] = make_float4((float)(v & 0xff) * s, (float)((v >> 8) & 0xff) * s, (float)((v >> 16) & 0xff) * s,
+                                 (float)(v >> 24) * s);
+        } else {
+            dst[k] = a.clear_color;
+        }
+    }
+
+    const int fy = ty - a.fb.min_y;
+    if (fy >= 0 && fy < a.fb.max_y - a.fb.min_y) {
+        const uint32_t fbi = (uint32_t)(fy * fb_w + tile_col);
+        const uint32_t e0 = __ldg(a.fb_start + fbi), e1 = __ldg(a.fb_end + fbi);
+        const float cx = (float)x + 0.5f, cy = (float)(strip * 4) + 0.5f;
+        for (uint32_t ei = e0; ei < e1; ei++) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + ei));
+            const uint32_t fill_end = raw.x, word = raw.y, paint_ctrl = raw.z;
+            const uint32_t count = word & 0x00ffffffu;
+            const float backdrop = (float)(int)(int8_t)(word >> 24);
+            const uint32_t ctrl = (paint_ctrl >> 16) & 0xffu;
+            const float4 base = __ldg(a.paints + (paint_ctrl & 0xffffu));
+            uint32_t acc[4] = {0, 0, 0, 0};
+            for (uint32_t fi = fill_end - count; fi < fill_end; fi++)
+                accumulate_fill(__ldg(a.fills + fi), cx, cy, a.area_lut, acc);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float coverage = finish_coverage(acc[k], count) + backdrop;
+                // calculateColor (tile_fragment.inc.glsl:560-614), solid colour, SrcOver;
+                // dest = dest * (1 - a) + src (tile.cs.glsl:155).
+                float alpha = base.w * mask_alpha(coverage, ctrl);
+                float ia = 1.0f - alpha;
+                dst[k].x = fmaf(dst[k].x, ia, base.x * alpha);
+                dst[k].y = fmaf(dst[k].y, ia, base.y * alpha);
+                dst[k].z = fmaf(dst[k].z, ia, base.z * alpha);
+                dst[k].w = fmaf(dst[k].w, ia, alpha);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int py = py0 + k;
+        if (py >= 0 && py < a.dest_h)
+            *reinterpret_cast<uint32_t *>(a.dest + (size_t)py * a.dest_pitch + (size_t)px * 4) =
+                pack_rgba8(dst[k].x, dst[k].y, dst[k].z, dst[k].w);
+    }
+}
+
+int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
+    int fb_w = a.fb.max_x - a.fb.min_x;
+    int rows = a.tile_y1 - a.tile_y0;
+    if (fb_w <= 0 || rows <= 0) return 0;
+    int groups_x = (fb_w + COMPOSITE_TILES_PER_BLOCK - 1) / COMPOSITE_TILES_PER_BLOCK;
+    k_composite<<<(unsigned)(groups_x * rows), 64 * COMPOSITE_TILES_PER_BLOCK, 0, stream>>>(a);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Parity-dump helpers: alpha tile numbering in SequentialExecutor order, D3D9-form lists.
+// ---------------------------------------------------------------------------------------------
+
+// A tile's alpha id is allocated by its first surviving fill (renderer/src/builder.rs:555-576), so
+// ids in first-fill order = exclusive scan, over emission order, of "this fill is its tile's first".
+__global__ void k_alpha_flags(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_first_fill,
+                              uint8_t *fill_is_first) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    if ((tile_word[t] & 0x00ffffffu) != 0) fill_is_first[tile_first_fill[t]] = 1;
+}
+int launch_alpha_flags(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_first_fill,
+                       uint8_t *fill_is_first, cudaStream_t stream) {
+    if (n_tiles == 0) return 0;
+    k_alpha_flags<<<div_up(n_tiles, 256), 256, 0, stream>>>(n_tiles, tile_word, tile_first_fill, fill_is_first);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+__global__ void k_alpha_assign(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_first_fill,
+                               const uint32_t *fill_first_scan, uint32_t *tile_alpha_id) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    tile_alpha_id[t] = (tile_word[t] & 0x00ffffffu) != 0 ? fill_first_scan[tile_first_fill[t]] : 0xffffffffu;
+}
+int launch_alpha_assign(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_first_fill,
+                        const uint32_t *fill_first_scan, uint32_t *tile_alpha_id, cudaStream_t stream) {
+    if (n_tiles == 0) return 0;
+    k_alpha_assign<<<div_up(n_tiles, 256), 256, 0, stream>>>(n_tiles, tile_word, tile_first_fill, fill_first_scan,
+                                                             tile_alpha_id);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+struct FillRecord { // gpu_data.rs:354-363
+    uint16_t from_x, from_y, to_x, to_y;
+    uint32_t link;
+};
+__global__ void k_dump_fills(uint32_t n, const EmitFill *fills_emit, const uint32_t *tile_alpha_id, FillRecord *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EmitFill f = fills_emit[i];
+    out[i] = FillRecord{(uint16_t)(f.from & 0xffff), (uint16_t)(f.from >> 16), (uint16_t)(f.to & 0xffff),
+                        (uint16_t)(f.to >> 16), tile_alpha_id[f.tile]};
+}
+int launch_dump_fills(uint32_t n_fills, const EmitFill *fills_emit, const uint32_t *tile_alpha_id, void *out,
+                      cudaStream_t stream) {
+    if (n_fills == 0) return 0;
+    k_dump_fills<<<div_up(n_fills, 256), 256, 0, stream>>>(n_fills, fills_emit, tile_alpha_id, (FillRecord *)out);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+__global__ void k_dump_tile_flags(uint32_t n_tiles, const uint32_t *tile_word, uint32_t *flags) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    uint32_t w = tile_word[t];
+    flags[t] = ((w & 0x00ffffffu) != 0 || (w >> 24) != 0) ? 1u : 0u;
+}
+int launch_dump_tile_flags(uint32_t n_tiles, const uint32_t *tile_word, uint32_t *flags, cudaStream_t stream) {
+    if (n_tiles == 0) return 0;
+    k_dump_tile_flags<<<div_up(n_tiles, 256), 256, 0, stream>>>(n_tiles, tile_word, flags);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+struct TileRecord { // TileObjectPrimitive, gpu_data.rs:264-275
+    int16_t tile_x, tile_y;
+    uint32_t alpha_tile_id;
+    uint32_t path_id;
+    uint16_t color;
+    uint8_t ctrl;
+    int8_t backdrop;
+};
+__global__ void k_dump_tiles(BatchDev b, const uint32_t *tile_word, const uint32_t *tile_alpha_id,
+                             const uint32_t *flags, const uint32_t *pos, TileRecord *out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= b.n_tiles || !flags[t]) return;
+    uint32_t p = search_le(b.path_tile_offset, b.n_paths, t);
+    const PathInfo path = load_path(b.paths, p);
+    int w = path.max_x - path.min_x;
+    uint32_t local = t - path.tile_offset;
+    TileRecord r;
+    r.tile_x = (int16_t)(path.min_x + (int)(local % (uint32_t)w));
+    r.tile_y = (int16_t)(path.min_y + (int)(local / (uint32_t)w));
+    r.alpha_tile_id = tile_alpha_id[t];
+    r.path_id = path.global_path_id;
+    r.color = (uint16_t)(path.paint_ctrl & 0xffff);
+    r.ctrl = (uint8_t)((path.paint_ctrl >> 16) & 0xff);
+    r.backdrop = (int8_t)(tile_word[t] >> 24);
+    out[pos[t]] = r;
+}
+int launch_dump_tiles(const BatchDev &b, const uint32_t *tile_word, const uint32_t *tile_alpha_id,
+                      const uint32_t *flags, const uint32_t *pos, void *out, cudaStream_t stream) {
+    if (b.n_tiles == 0) return 0;
+    k_dump_tiles<<<div_up(b.n_tiles, 256), 256, 0, stream>>>(b, tile_word, tile_alpha_id, flags, pos, (TileRecord *)out);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+// Coverage masks per alpha tile with the same device function the fused kernel uses.
+__global__ void __launch_bounds__(64)
+    k_alpha_masks(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_fill_pos,
+                  const uint32_t *tile_alpha_id, const PackedFill *fills, cudaTextureObject_t lut, float *out) {
+    const int x = threadIdx.x & 15, strip = threadIdx.x >> 4;
+    const float cx = (float)x + 0.5f, cy = (float)(strip * 4) + 0.5f;
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        uint32_t count = tile_word[t] & 0x00ffffffu;
+        if (count == 0) continue;
+        uint32_t end = tile_fill_pos[t];
+        uint32_t acc[4] = {0, 0, 0, 0};
+        for (uint32_t fi = end - count; fi < end; fi++) accumulate_fill(fills[fi], cx, cy, lut, acc);
+        float *mask = out + (size_t)tile_alpha_id[t] * 256;
+#pragma unroll
+        for (int k = 0; k < 4; k++) mask[(strip * 4 + k) * 16 + x] = finish_coverage(acc[k], count);
+    }
+}
+int launch_alpha_masks(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_fill_pos,
+                       const uint32_t *tile_alpha_id, const PackedFill *fills, cudaTextureObject_t area_lut,
+                       float *out, cudaStream_t stream) {
+    if (n_tiles == 0) return 0;
+    unsigned grid = n_tiles < 16384u ? n_tiles : 16384u;
+    k_alpha_masks<<<grid, 64, 0, stream>>>(n_tiles, tile_word, tile_fill_pos, tile_alpha_id, fills, area_lut, out);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+} // namespace pf

@@ -1,0 +1,137 @@
+// pathfinder_b200/csrc/kernels.cuh — device-side records and launch wrappers of the pipeline
+// stages (bound -> dice -> bin -> propagate -> sort -> fill+tile).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pf {
+
+// Per-path record of a batch, built on the host from PropagateMetadataD3D11 + DiceMetadataD3D11 +
+// TilePathInfoD3D11 (renderer/src/gpu_data.rs:297-334) with device-side offsets. 48 bytes,
+// 16-byte aligned so a thread loads it as three 128-bit words.
+struct __align__(16) PathInfo {
+    int32_t min_x, min_y, max_x, max_y; // tile rect, already restricted to this renderer's strip
+    uint32_t tile_offset;               // first dense tile of the path
+    uint32_t col_offset;                // first column backdrop of the path
+    uint32_t seg_batch_first;           // DiceMetadataD3D11.first_batch_segment_index
+    uint32_t seg_global_first;          // DiceMetadataD3D11.first_global_segment_index
+    uint32_t global_path_id;            // DiceMetadataD3D11.global_path_id (draw path id)
+    uint32_t paint_ctrl;                // color u16 | ctrl u8 << 16 | z_write << 24
+    uint32_t clip_path_index;           // PropagateMetadataD3D11.clip_path_index
+    uint32_t pad;
+};
+static_assert(sizeof(PathInfo) == 48, "PathInfo layout");
+
+struct Transform {
+    float m11, m21, m12, m22, tx, ty;
+    int identity;
+};
+
+struct ViewBox {
+    float min_x, min_y, max_x, max_y;
+};
+
+struct FbRect {
+    int32_t min_x, min_y, max_x, max_y; // framebuffer tile rect = round_out(view_box / 16)
+};
+
+// One entry of a framebuffer tile's painter's-order list (16 bytes, one 128-bit load).
+struct __align__(16) TileEntry {
+    uint32_t fill_end;    // end of the tile's run in the tile-grouped fill array
+    uint32_t word;        // fill count (low 24 bits) | backdrop i8 << 24
+    uint32_t paint_ctrl;  // color u16 | ctrl u8 << 16
+    uint32_t path_id;     // global draw path id
+};
+
+// Tile-grouped fill: the 4.8 fixed point segment (LineSegmentU16) as one 64-bit word.
+typedef uint2 PackedFill; // x = from_x | from_y << 16, y = to_x | to_y << 16
+
+struct EmitFill { // emission-ordered fill kept for parity dumps (12 bytes like gpu_data.rs Fill)
+    uint32_t from, to, tile;
+};
+
+// Everything the stage kernels read about one batch. Search arrays have n_paths + 1 entries (the
+// last one is the total) so a thread finds its path with one binary search over a dense array.
+struct BatchDev {
+    const float2 *points;
+    const uint2 *seg_indices;
+    const PathInfo *paths;
+    const uint32_t *path_seg_first;
+    const uint32_t *path_tile_offset;
+    const uint32_t *path_col_offset;
+    uint32_t n_paths, n_segments, n_tiles, n_columns;
+    Transform xf;
+    ViewBox view_box;
+    FbRect fb;
+};
+
+// ---- stage launchers (all asynchronous on `stream`; return the number of kernels launched) ----
+
+// dice: count pass writes seg_line_count[s]; emit pass reads seg_line_offset[s] and writes
+// lines/line_path.
+int launch_dice(bool emit, const BatchDev &b, uint32_t *seg_line_count, const uint32_t *seg_line_offset,
+                float4 *lines, uint32_t *line_path, uint32_t line_capacity, cudaStream_t stream);
+
+struct BinArgs {
+    const float4 *lines;
+    const uint32_t *line_path;
+    uint32_t n_lines;
+    uint32_t *tile_word;      // count (24) | backdrop delta (8)
+    int32_t *col_backdrop;
+    // count pass
+    uint32_t *line_fill_count;
+    // emit pass
+    const uint32_t *line_fill_offset;
+    uint32_t *tile_fill_pos;  // running cursor, initialised with the exclusive scan of counts
+    PackedFill *fills;        // tile-grouped
+    uint32_t fill_capacity;
+    uint32_t *tile_first_fill; // optional (parity dumps): min emission index per tile
+    EmitFill *fills_emit;      // optional (parity dumps): fills in emission order
+};
+int launch_bin(bool emit, const BatchDev &b, const BinArgs &args, cudaStream_t stream);
+
+int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_backdrop, int32_t *z_buffer,
+                     cudaStream_t stream);
+
+// tile_fb[t] = framebuffer tile index if the tile is non-empty, inside the framebuffer and not
+// z-culled, else 0xffffffff.
+int launch_list_flags(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
+                      cudaStream_t stream);
+int launch_list_emit(uint32_t n_tiles, const uint32_t *tile_fb, const uint32_t *tile_pos, uint32_t *keys,
+                     uint32_t *vals, uint32_t capacity, cudaStream_t stream);
+int launch_build_entries(const BatchDev &b, uint32_t n_entries, const uint32_t *keys, const uint32_t *vals,
+                         const uint32_t *tile_word, const uint32_t *tile_fill_pos, TileEntry *entries,
+                         uint32_t *fb_start, uint32_t *fb_end, cudaStream_t stream);
+
+struct CompositeArgs {
+    const TileEntry *entries;
+    const uint32_t *fb_start, *fb_end;
+    const PackedFill *fills;
+    const float4 *paints;      // base colour per paint id, already rounded through f16
+    cudaTextureObject_t area_lut;
+    FbRect fb;
+    int32_t tile_y0, tile_y1;  // tile rows composited by this renderer (strip)
+    uint8_t *dest;
+    size_t dest_pitch;
+    int32_t dest_w, dest_h;
+    float4 clear_color;
+    int load_dest;             // LOAD_ACTION_LOAD for batches after the first
+};
+int launch_composite(const CompositeArgs &args, cudaStream_t stream);
+
+// ---- parity-dump helpers ----
+int launch_alpha_flags(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_first_fill,
+                       uint8_t *fill_is_first, cudaStream_t stream);
+int launch_alpha_assign(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_first_fill,
+                        const uint32_t *fill_first_scan, uint32_t *tile_alpha_id, cudaStream_t stream);
+int launch_dump_fills(uint32_t n_fills, const EmitFill *fills_emit, const uint32_t *tile_alpha_id, void *out,
+                      cudaStream_t stream);
+int launch_dump_tile_flags(uint32_t n_tiles, const uint32_t *tile_word, uint32_t *flags, cudaStream_t stream);
+int launch_dump_tiles(const BatchDev &b, const uint32_t *tile_word, const uint32_t *tile_alpha_id,
+                      const uint32_t *flags, const uint32_t *pos, void *out, cudaStream_t stream);
+int launch_alpha_masks(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_fill_pos,
+                       const uint32_t *tile_alpha_id, const PackedFill *fills, cudaTextureObject_t area_lut,
+                       float *out, cudaStream_t stream);
+
+} // namespace pf

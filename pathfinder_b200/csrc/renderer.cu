@@ -1,0 +1,925 @@
+// pathfinder_b200/csrc/renderer.cu — host driver of the CUDA pipeline and the renderer half of the
+// C ABI (include/pf_cuda.h).
+//
+// Replaces RendererD3D11::{upload_scene, prepare_tiles, draw_tiles} (renderer/src/gpu/d3d11/
+// renderer.rs:236-241,427-542,711-782) and Renderer::{begin_scene, render_command, end_scene}
+// (renderer/src/gpu/renderer.rs:350-460). Differences by design:
+//   * every stage is count -> scan -> emit, so there is no overflow/retry loop and allocation is
+//     exact (the reference re-runs dice/bin with doubled buffers, d3d11/renderer.rs:463-499);
+//   * fill and tile are one kernel (the alpha mask never reaches HBM);
+//   * tile lists are sorted by a device radix sort instead of per-tile linked lists.
+#include <cuda_fp16.h>
+
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../include/pf_cuda.h"
+#include "common.cuh"
+#include "kernels.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace pf {
+
+thread_local std::string g_last_error;
+
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+
+template <typename T>
+struct PinnedBuffer {
+    T *ptr = nullptr;
+    size_t capacity = 0;
+    ~PinnedBuffer() {
+        if (ptr) cudaFreeHost(ptr);
+    }
+    void ensure(size_t n) {
+        if (n <= capacity) return;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        size_t want = n + n / 4 + 64;
+        PF_CUDA_CHECK(cudaMallocHost((void **)&ptr, want * sizeof(T)));
+        capacity = want;
+    }
+};
+
+struct SceneSegments {
+    DeviceBuffer<float2> points;
+    DeviceBuffer<uint2> indices;
+    size_t n_points = 0, n_indices = 0;
+};
+
+struct StageTimer {
+    cudaEvent_t ev[8];
+    bool created = false;
+    void create() {
+        if (created) return;
+        for (auto &e : ev) PF_CUDA_CHECK(cudaEventCreate(&e));
+        created = true;
+    }
+    void destroy() {
+        if (!created) return;
+        for (auto &e : ev) cudaEventDestroy(e);
+        created = false;
+    }
+};
+
+} // namespace pf
+
+using namespace pf;
+
+struct PFCudaDevice {
+    int ordinal;
+};
+
+struct PFCudaRenderer {
+    int ordinal = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    PFCudaRendererOptions options{};
+    size_t bytes_allocated = 0;
+
+    // Destination image.
+    DeviceBuffer<uint8_t> dest_owned;
+    uint8_t *dest = nullptr;
+    size_t dest_pitch = 0;
+    bool dest_external = false;
+
+    // Area LUT texture (textures/area-lut.png; renderer/src/gpu/renderer.rs:207-214).
+    cudaArray_t lut_array = nullptr;
+    cudaTextureObject_t lut_tex = 0;
+
+    // Scene-resident data (UploadSceneD3D11).
+    SceneSegments draw_segments, clip_segments;
+    bool has_scene = false;
+
+    // Paint table (UploadTextureMetadata), base colours rounded through f16.
+    DeviceBuffer<float4> paints;
+    size_t n_paints = 0;
+
+    // Strip partition.
+    int32_t strip_y0 = 0, strip_y1 = 0;
+
+    // Per-batch device buffers.
+    DeviceBuffer<uint8_t> batch_meta; // PathInfo[P] + 3 search arrays
+    PinnedBuffer<uint8_t> batch_meta_host;
+    cudaEvent_t meta_copied = nullptr;
+    DeviceBuffer<uint32_t> seg_line_offset;  // [S]
+    DeviceBuffer<float4> lines;
+    DeviceBuffer<uint32_t> line_path;
+    DeviceBuffer<uint32_t> line_fill_offset; // [L]
+    DeviceBuffer<uint32_t> tile_word, tile_fill_pos, tile_first_fill, tile_fb, tile_pos, tile_alpha_id;
+    DeviceBuffer<int32_t> col_backdrop;
+    DeviceBuffer<PackedFill> fills;
+    DeviceBuffer<EmitFill> fills_emit;
+    DeviceBuffer<int32_t> z_buffer;
+    DeviceBuffer<uint32_t> fb_start, fb_end;
+    DeviceBuffer<uint32_t> list_keys, list_vals;
+    DeviceBuffer<TileEntry> entries;
+    DeviceBuffer<uint32_t> counters; // device-side totals: [0]=lines [1]=fills [2]=entries [3]=alpha tiles [4]=dump tiles
+    PinnedBuffer<uint32_t> counters_host;
+    ScanScratch scan_scratch;
+    RadixSortScratch sort_scratch;
+    // debug / dump scratch
+    DeviceBuffer<uint8_t> fill_is_first;
+    DeviceBuffer<uint32_t> fill_first_scan;
+    DeviceBuffer<uint8_t> dump_out;
+
+    // State of the last batch (for dumps and stats).
+    BatchDev last_batch{};
+    uint32_t last_lines = 0, last_fills = 0, last_entries = 0, last_alpha_tiles = 0;
+    bool last_alpha_ids_valid = false;
+    FbRect last_fb{0, 0, 0, 0};
+
+    bool in_scene = false;
+    bool debug_lists = false;
+    bool timing = false;
+    int batches_drawn = 0;
+    PFCudaRenderStats stats{};
+    PFCudaRenderTime times{};
+    StageTimer timer;
+
+    // scene.view_box(): what process_line_segment clips to (renderer/src/tiler.rs:194). Defaults to
+    // the destination rect, which is what the demo sets (demo/common/src/lib.rs:910-914).
+    bool has_view_box = false;
+    ViewBox view_box{0, 0, 0, 0};
+    // SceneSink.last_scene for PFSceneBuildAndRenderCuda (renderer/src/scene.rs:384-396).
+    PFSceneSinkState sink_state{0, 0, 0};
+
+    void bind_device() { PF_CUDA_CHECK(cudaSetDevice(ordinal)); }
+};
+
+namespace {
+
+template <typename T>
+void track(PFCudaRenderer *r, DeviceBuffer<T> &b) {
+    b.bytes_allocated = &r->bytes_allocated;
+}
+
+void setup_tracking(PFCudaRenderer *r) {
+    track(r, r->dest_owned);
+    track(r, r->draw_segments.points);
+    track(r, r->draw_segments.indices);
+    track(r, r->clip_segments.points);
+    track(r, r->clip_segments.indices);
+    track(r, r->paints);
+    track(r, r->batch_meta);
+    track(r, r->seg_line_offset);
+    track(r, r->lines);
+    track(r, r->line_path);
+    track(r, r->line_fill_offset);
+    track(r, r->tile_word);
+    track(r, r->tile_fill_pos);
+    track(r, r->tile_first_fill);
+    track(r, r->tile_fb);
+    track(r, r->tile_pos);
+    track(r, r->tile_alpha_id);
+    track(r, r->col_backdrop);
+    track(r, r->fills);
+    track(r, r->fills_emit);
+    track(r, r->z_buffer);
+    track(r, r->fb_start);
+    track(r, r->fb_end);
+    track(r, r->list_keys);
+    track(r, r->list_vals);
+    track(r, r->entries);
+    track(r, r->counters);
+    track(r, r->scan_scratch.block_sums);
+    track(r, r->sort_scratch.hist);
+    track(r, r->sort_scratch.keys_tmp);
+    track(r, r->sort_scratch.vals_tmp);
+    track(r, r->sort_scratch.scan.block_sums);
+    track(r, r->fill_is_first);
+    track(r, r->fill_first_scan);
+    track(r, r->dump_out);
+}
+
+void allocate_dest(PFCudaRenderer *r) {
+    if (r->dest_external) return;
+    int w = r->options.dest_size.x, h = r->options.dest_size.y;
+    if (w <= 0 || h <= 0) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "dest_size must be positive");
+    r->dest_owned.ensure((size_t)w * h * 4);
+    r->dest = r->dest_owned.ptr;
+    r->dest_pitch = (size_t)w * 4;
+}
+
+// round_out(view_box / 16): the framebuffer tile rect (renderer/src/builder.rs:949-953).
+FbRect framebuffer_tile_rect(const PFCudaRenderer *r) {
+    FbRect fb;
+    fb.min_x = 0;
+    fb.min_y = 0;
+    fb.max_x = (r->options.dest_size.x + PF_TILE_WIDTH - 1) / PF_TILE_WIDTH;
+    fb.max_y = (r->options.dest_size.y + PF_TILE_HEIGHT - 1) / PF_TILE_HEIGHT;
+    return fb;
+}
+
+float4 clear_color(const PFCudaRenderer *r) {
+    // Renderer::clear_color_for_draw_operation (gpu/renderer.rs): background colour if set,
+    // otherwise transparent black.
+    if (r->options.flags & PF_RENDERER_OPTIONS_FLAGS_HAS_BACKGROUND_COLOR) {
+        const PFColorF &c = r->options.background_color;
+        return make_float4(c.r, c.g, c.b, c.a);
+    }
+    return make_float4(0, 0, 0, 0);
+}
+
+uint32_t read_counter(PFCudaRenderer *r, int index) {
+    r->counters_host.ensure(16);
+    PF_CUDA_CHECK(cudaMemcpyAsync(r->counters_host.ptr, r->counters.ptr + index, sizeof(uint32_t),
+                                  cudaMemcpyDeviceToHost, r->stream));
+    PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    r->stats.host_sync_count++;
+    return r->counters_host.ptr[0];
+}
+
+void upload_segments(PFCudaRenderer *r, SceneSegments &dst, const PFSegmentsD3D11 &src) {
+    dst.n_points = src.point_count;
+    dst.n_indices = src.index_count;
+    dst.points.ensure(src.point_count + 4);
+    dst.indices.ensure(src.index_count + 1);
+    if (src.point_count)
+        PF_CUDA_CHECK(cudaMemcpyAsync(dst.points.ptr, src.points, src.point_count * sizeof(float2),
+                                      cudaMemcpyHostToDevice, r->stream));
+    if (src.index_count)
+        PF_CUDA_CHECK(cudaMemcpyAsync(dst.indices.ptr, src.indices, src.index_count * sizeof(uint2),
+                                      cudaMemcpyHostToDevice, r->stream));
+    // The payload is borrowed for this call only and may be pageable: wait for the copies.
+    PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+}
+
+void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *entries, size_t n) {
+    std::vector<float4> table(n);
+    for (size_t i = 0; i < n; i++) {
+        const PFTextureMetadataEntry &e = entries[i];
+        if (e.color_0_combine_mode != 0 || e.filter != 0 || e.blend_mode != 0)
+            throw Error(PF_CUDA_ERROR_UNSUPPORTED,
+                        "only solid-colour SrcOver paints are on the hot path (SURVEY.md §2 row 7)");
+        // ColorU::to_f32 (color/src/lib.rs:70-73) then f16 (gpu/renderer.rs:726-729).
+        const float s = 1.0f / 255.0f;
+        float c[4] = {(float)e.base_color.r * s, (float)e.base_color.g * s, (float)e.base_color.b * s,
+                      (float)e.base_color.a * s};
+        for (float &v : c) v = __half2float(__float2half_rn(v));
+        table[i] = make_float4(c[0], c[1], c[2], c[3]);
+    }
+    r->n_paints = n;
+    r->paints.ensure(n + 1);
+    if (n) {
+        PF_CUDA_CHECK(cudaMemcpyAsync(r->paints.ptr, table.data(), n * sizeof(float4), cudaMemcpyHostToDevice,
+                                      r->stream));
+        PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    }
+}
+
+struct EventPair {
+    cudaEvent_t a, b;
+};
+
+// One DrawTilesD3D11 batch: prepare_tiles + draw_tiles (d3d11/renderer.rs:414-424).
+void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
+    if (!r->has_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "DrawTilesD3D11 before UploadSceneD3D11");
+    if (batch.path_source != PF_PATH_SOURCE_DRAW)
+        throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "draw batch with a clip path source");
+    if (batch.has_clipped_path_info && batch.clipped_path_info.clipped_path_count > 0)
+        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "clip paths are a 'next' row (SURVEY.md §8 f1)");
+    cudaStream_t st = r->stream;
+    const uint32_t P = batch.path_count;
+    const PFPrepareTilesInfoD3D11 &info = batch.prepare_info;
+    const SceneSegments &segs = r->draw_segments;
+    const FbRect fb = framebuffer_tile_rect(r);
+    const int32_t strip_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
+    const int32_t strip_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
+    int launches = 0;
+
+    if (r->timing) {
+        r->timer.create();
+        PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[0], st));
+    }
+
+    // ---- bound (host part): per-path records with strip-restricted rects and dense offsets.
+    // Replaces TileBatchDataD3D11 offsets (renderer/src/builder.rs:663-720) + bound.cs.glsl.
+    const size_t meta_bytes = (size_t)P * sizeof(PathInfo) + 3 * (size_t)(P + 1) * sizeof(uint32_t);
+    if (r->meta_copied) PF_CUDA_CHECK(cudaEventSynchronize(r->meta_copied));
+    r->batch_meta_host.ensure(meta_bytes + 64);
+    uint8_t *hbase = r->batch_meta_host.ptr;
+    PathInfo *h_paths = reinterpret_cast<PathInfo *>(hbase);
+    uint32_t *h_seg_first = reinterpret_cast<uint32_t *>(hbase + (size_t)P * sizeof(PathInfo));
+    uint32_t *h_tile_off = h_seg_first + (P + 1);
+    uint32_t *h_col_off = h_tile_off + (P + 1);
+    uint64_t n_tiles64 = 0, n_cols64 = 0;
+    uint32_t n_segments = batch.segment_count;
+    for (uint32_t i = 0; i < P; i++) {
+        const PFPropagateMetadataD3D11 &pm = info.propagate_metadata[i];
+        const PFDiceMetadataD3D11 &dm = info.dice_metadata[i];
+        const PFTilePathInfoD3D11 &tp = info.tile_path_info[i];
+        PathInfo &pi = h_paths[i];
+        pi.min_x = pm.tile_rect.origin.x;
+        pi.max_x = pm.tile_rect.lower_right.x;
+        pi.min_y = pm.tile_rect.origin.y;
+        pi.max_y = pm.tile_rect.lower_right.y;
+        if (pi.max_x < pi.min_x) pi.max_x = pi.min_x;
+        // Strip restriction: rows above the strip feed the column backdrops exactly like rows
+        // above the path rect do in the reference (builder.rs:609-612); rows below are ignored.
+        if (pi.min_y < strip_y0) pi.min_y = strip_y0;
+        if (pi.max_y > strip_y1) pi.max_y = strip_y1;
+        if (pi.max_y < pi.min_y) pi.max_y = pi.min_y;
+        if (pi.max_y == pi.min_y) pi.max_x = pi.min_x; // no tiles: no columns either
+        pi.tile_offset = (uint32_t)n_tiles64;
+        pi.col_offset = (uint32_t)n_cols64;
+        pi.seg_batch_first = dm.first_batch_segment_index;
+        pi.seg_global_first = dm.first_global_segment_index;
+        pi.global_path_id = dm.global_path_id;
+        pi.paint_ctrl = (uint32_t)tp.color | ((uint32_t)tp.ctrl << 16) | ((pm.z_write ? 1u : 0u) << 24);
+        pi.clip_path_index = pm.clip_path_index;
+        pi.pad = 0;
+        h_seg_first[i] = dm.first_batch_segment_index;
+        h_tile_off[i] = pi.tile_offset;
+        h_col_off[i] = pi.col_offset;
+        n_tiles64 += (uint64_t)(pi.max_x - pi.min_x) * (uint64_t)(pi.max_y - pi.min_y);
+        n_cols64 += (uint64_t)(pi.max_x - pi.min_x);
+        if (tp.color >= r->n_paints)
+            throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "paint id outside the uploaded texture metadata");
+    }
+    if (n_tiles64 >= 0xfffffff0ull) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "more than 2^32 bbox tiles in one batch");
+    const uint32_t n_tiles = (uint32_t)n_tiles64, n_cols = (uint32_t)n_cols64;
+    h_seg_first[P] = n_segments;
+    h_tile_off[P] = n_tiles;
+    h_col_off[P] = n_cols;
+
+    r->batch_meta.ensure(meta_bytes + 64, 1.25);
+    if (meta_bytes) {
+        PF_CUDA_CHECK(cudaMemcpyAsync(r->batch_meta.ptr, hbase, meta_bytes, cudaMemcpyHostToDevice, st));
+        if (!r->meta_copied) PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->meta_copied, cudaEventDisableTiming));
+        PF_CUDA_CHECK(cudaEventRecord(r->meta_copied, st));
+    }
+
+    BatchDev b{};
+    b.points = segs.points.ptr;
+    b.seg_indices = segs.indices.ptr;
+    b.paths = reinterpret_cast<const PathInfo *>(r->batch_meta.ptr);
+    b.path_seg_first = reinterpret_cast<const uint32_t *>(r->batch_meta.ptr + (size_t)P * sizeof(PathInfo));
+    b.path_tile_offset = b.path_seg_first + (P + 1);
+    b.path_col_offset = b.path_tile_offset + (P + 1);
+    b.n_paths = P;
+    b.n_segments = n_segments;
+    b.n_tiles = n_tiles;
+    b.n_columns = n_cols;
+    const PFTransform2F &t = info.transform;
+    b.xf.m11 = t.matrix.m00, b.xf.m12 = t.matrix.m01, b.xf.m21 = t.matrix.m10, b.xf.m22 = t.matrix.m11;
+    b.xf.tx = t.vector.x, b.xf.ty = t.vector.y;
+    b.xf.identity = (b.xf.m11 == 1.0f && b.xf.m12 == 0.0f && b.xf.m21 == 0.0f && b.xf.m22 == 1.0f &&
+                     b.xf.tx == 0.0f && b.xf.ty == 0.0f);
+    // process_line_segment clips to scene.view_box() (tiler.rs:194): the framebuffer rect.
+    b.view_box = r->has_view_box
+                     ? r->view_box
+                     : ViewBox{0.0f, 0.0f, (float)r->options.dest_size.x, (float)r->options.dest_size.y};
+    b.fb = fb;
+
+    r->counters.ensure(16);
+
+    // ---- bound (device part): clear the dense tile arrays. bound.cs.glsl:80-83 initialises
+    // {next=-1, first_fill=-1, backdrop=0}; here a tile is one word (count | backdrop delta).
+    r->tile_word.ensure(n_tiles + 1, 1.25);
+    r->tile_fill_pos.ensure(n_tiles + 1, 1.25);
+    r->col_backdrop.ensure(n_cols + 1, 1.25);
+    PF_CUDA_CHECK(cudaMemsetAsync(r->tile_word.ptr, 0, (size_t)n_tiles * 4, st));
+    PF_CUDA_CHECK(cudaMemsetAsync(r->col_backdrop.ptr, 0, (size_t)n_cols * 4, st));
+    if (info.backdrops && info.backdrop_count) {
+        // TransformCPUBinGPU-style non-zero initial backdrops (builder.rs:679-688).
+        std::vector<int32_t> init(n_cols, 0);
+        bool any = false;
+        for (size_t i = 0; i < info.backdrop_count; i++) {
+            const PFBackdropInfoD3D11 &bi = info.backdrops[i];
+            if (bi.initial_backdrop == 0 || bi.path_index >= P) continue;
+            const PathInfo &pi = h_paths[bi.path_index];
+            if (bi.tile_x_offset < 0 || bi.tile_x_offset >= pi.max_x - pi.min_x) continue;
+            init[pi.col_offset + (uint32_t)bi.tile_x_offset] = bi.initial_backdrop;
+            any = true;
+        }
+        if (any) {
+            PF_CUDA_CHECK(cudaMemcpyAsync(r->col_backdrop.ptr, init.data(), (size_t)n_cols * 4, cudaMemcpyHostToDevice, st));
+            PF_CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+    }
+    if (r->debug_lists) {
+        r->tile_first_fill.ensure(n_tiles + 1, 1.25);
+        PF_CUDA_CHECK(cudaMemsetAsync(r->tile_first_fill.ptr, 0xff, (size_t)n_tiles * 4, st));
+    }
+    const int fb_w = fb.max_x - fb.min_x, fb_h = fb.max_y - fb.min_y;
+    const uint32_t n_fb = (uint32_t)(fb_w * fb_h);
+    r->z_buffer.ensure(n_fb + 1);
+    r->fb_start.ensure(n_fb + 1);
+    r->fb_end.ensure(n_fb + 1);
+    PF_CUDA_CHECK(cudaMemsetAsync(r->z_buffer.ptr, 0, (size_t)n_fb * 4, st));
+    PF_CUDA_CHECK(cudaMemsetAsync(r->fb_start.ptr, 0, (size_t)n_fb * 4, st));
+    PF_CUDA_CHECK(cudaMemsetAsync(r->fb_end.ptr, 0, (size_t)n_fb * 4, st));
+    if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[1], st));
+
+    // ---- dice: count -> scan -> emit.
+    r->seg_line_offset.ensure(n_segments + 1, 1.25);
+    launches += launch_dice(false, b, r->seg_line_offset.ptr, nullptr, nullptr, nullptr, 0, st);
+    launches += exclusive_scan(LoadU32{r->seg_line_offset.ptr}, r->seg_line_offset.ptr, n_segments,
+                               r->counters.ptr + 0, r->scan_scratch, st);
+    const uint32_t n_lines = n_segments ? read_counter(r, 0) : 0;
+    r->lines.ensure(n_lines + 1, 1.25);
+    r->line_path.ensure(n_lines + 1, 1.25);
+    launches += launch_dice(true, b, nullptr, r->seg_line_offset.ptr, r->lines.ptr, r->line_path.ptr, n_lines, st);
+    if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[2], st));
+
+    // ---- bin: count (+ backdrop deltas) -> scans -> emit into tile-grouped runs.
+    r->line_fill_offset.ensure(n_lines + 1, 1.25);
+    BinArgs ba{};
+    ba.lines = r->lines.ptr;
+    ba.line_path = r->line_path.ptr;
+    ba.n_lines = n_lines;
+    ba.tile_word = r->tile_word.ptr;
+    ba.col_backdrop = r->col_backdrop.ptr;
+    ba.line_fill_count = r->line_fill_offset.ptr;
+    launches += launch_bin(false, b, ba, st);
+    launches += exclusive_scan(LoadU32{r->line_fill_offset.ptr}, r->line_fill_offset.ptr, n_lines,
+                               r->counters.ptr + 1, r->scan_scratch, st);
+    launches += exclusive_scan(LoadLow24{r->tile_word.ptr}, r->tile_fill_pos.ptr, n_tiles, nullptr,
+                               r->scan_scratch, st);
+    const uint32_t n_fills = n_lines ? read_counter(r, 1) : 0;
+    r->fills.ensure(n_fills + 1, 1.25);
+    if (r->debug_lists) r->fills_emit.ensure(n_fills + 1, 1.25);
+    ba.line_fill_offset = r->line_fill_offset.ptr;
+    ba.tile_fill_pos = r->tile_fill_pos.ptr;
+    ba.fills = r->fills.ptr;
+    ba.fill_capacity = n_fills;
+    ba.tile_first_fill = r->debug_lists ? r->tile_first_fill.ptr : nullptr;
+    ba.fills_emit = r->debug_lists ? r->fills_emit.ptr : nullptr;
+    launches += launch_bin(true, b, ba, st);
+    if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[3], st));
+
+    // ---- propagate: column backdrop prefix sums + occluder z-writes.
+    launches += launch_propagate(b, r->tile_word.ptr, r->col_backdrop.ptr, r->z_buffer.ptr, st);
+    if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[4], st));
+
+    // ---- sort: z-cull, compact surviving tiles, stable radix sort by framebuffer tile.
+    r->tile_fb.ensure(n_tiles + 1, 1.25);
+    r->tile_pos.ensure(n_tiles + 1, 1.25);
+    launches += launch_list_flags(b, r->tile_word.ptr, r->z_buffer.ptr, r->tile_fb.ptr, st);
+    launches += exclusive_scan(LoadNotInvalid{r->tile_fb.ptr}, r->tile_pos.ptr, n_tiles, r->counters.ptr + 2,
+                               r->scan_scratch, st);
+    const uint32_t n_entries = n_tiles ? read_counter(r, 2) : 0;
+    r->list_keys.ensure(n_entries + 1, 1.25);
+    r->list_vals.ensure(n_entries + 1, 1.25);
+    r->entries.ensure(n_entries + 1, 1.25);
+    launches += launch_list_emit(n_tiles, r->tile_fb.ptr, r->tile_pos.ptr, r->list_keys.ptr, r->list_vals.ptr,
+                                 n_entries, st);
+    int key_bits = 1;
+    while ((1u << key_bits) < n_fb && key_bits < 32) key_bits++;
+    launches += radix_sort_pairs(r->list_keys.ptr, r->list_vals.ptr, n_entries, key_bits, r->sort_scratch, st);
+    launches += launch_build_entries(b, n_entries, r->list_keys.ptr, r->list_vals.ptr, r->tile_word.ptr,
+                                     r->tile_fill_pos.ptr, r->entries.ptr, r->fb_start.ptr, r->fb_end.ptr, st);
+    if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[5], st));
+
+    // ---- fill + tile (fused).
+    CompositeArgs ca{};
+    ca.entries = r->entries.ptr;
+    ca.fb_start = r->fb_start.ptr;
+    ca.fb_end = r->fb_end.ptr;
+    ca.fills = r->fills.ptr;
+    ca.paints = r->paints.ptr;
+    ca.area_lut = r->lut_tex;
+    ca.fb = fb;
+    ca.tile_y0 = strip_y0;
+    ca.tile_y1 = strip_y1;
+    ca.dest = r->dest;
+    ca.dest_pitch = r->dest_pitch;
+    ca.dest_w = r->options.dest_size.x;
+    ca.dest_h = r->options.dest_size.y;
+    ca.clear_color = clear_color(r);
+    ca.load_dest = r->batches_drawn > 0;
+    launches += launch_composite(ca, st);
+    if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[6], st));
+
+    r->batches_drawn++;
+    r->last_batch = b;
+    r->last_lines = n_lines;
+    r->last_fills = n_fills;
+    r->last_entries = n_entries;
+    r->last_alpha_ids_valid = false;
+    r->last_fb = fb;
+    r->stats.path_count += P;
+    r->stats.fill_count += n_fills;
+    r->stats.total_tile_count += n_tiles;
+    r->stats.input_segment_count += n_segments;
+    r->stats.line_segment_count += n_lines;
+    r->stats.tile_list_entry_count += n_entries;
+    r->stats.column_count += n_cols;
+    r->stats.drawcall_count += (uint64_t)launches;
+
+    if (r->timing) {
+        PF_CUDA_CHECK(cudaEventSynchronize(r->timer.ev[6]));
+        float ms[6];
+        for (int i = 0; i < 6; i++) PF_CUDA_CHECK(cudaEventElapsedTime(&ms[i], r->timer.ev[i], r->timer.ev[i + 1]));
+        r->times.bound_ms += ms[0];
+        r->times.dice_ms += ms[1];
+        r->times.bin_ms += ms[2];
+        r->times.propagate_ms += ms[3];
+        r->times.sort_ms += ms[4];
+        r->times.fill_tile_ms += ms[5];
+        float total;
+        PF_CUDA_CHECK(cudaEventElapsedTime(&total, r->timer.ev[0], r->timer.ev[6]));
+        r->times.total_ms += total;
+    }
+}
+
+// Alpha tile ids in SequentialExecutor order for the last batch (needs debug lists).
+void ensure_alpha_ids(PFCudaRenderer *r) {
+    if (r->last_alpha_ids_valid) return;
+    if (!r->debug_lists) throw Error(PF_CUDA_ERROR_PROTOCOL, "enable debug lists before rendering to read alpha tile ids");
+    cudaStream_t st = r->stream;
+    const uint32_t n_tiles = r->last_batch.n_tiles, n_fills = r->last_fills;
+    r->fill_is_first.ensure(n_fills + 1, 1.25);
+    r->fill_first_scan.ensure(n_fills + 1, 1.25);
+    r->tile_alpha_id.ensure(n_tiles + 1, 1.25);
+    PF_CUDA_CHECK(cudaMemsetAsync(r->fill_is_first.ptr, 0, n_fills, st));
+    launch_alpha_flags(n_tiles, r->tile_word.ptr, r->tile_first_fill.ptr, r->fill_is_first.ptr, st);
+    exclusive_scan(LoadU8{r->fill_is_first.ptr}, r->fill_first_scan.ptr, n_fills, r->counters.ptr + 3,
+                   r->scan_scratch, st);
+    launch_alpha_assign(n_tiles, r->tile_word.ptr, r->tile_first_fill.ptr, r->fill_first_scan.ptr,
+                        r->tile_alpha_id.ptr, st);
+    r->last_alpha_tiles = n_fills ? read_counter(r, 3) : 0;
+    r->last_alpha_ids_valid = true;
+}
+
+template <typename F>
+PFCudaStatus guarded(PFCudaRenderer *r, F &&f) {
+    try {
+        if (!r) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null renderer");
+        r->bind_device();
+        f();
+        return PF_CUDA_OK;
+    } catch (const Error &e) {
+        set_last_error(e.what());
+        return e.status;
+    } catch (const std::exception &e) {
+        set_last_error(e.what());
+        return PF_CUDA_ERROR_CUDA;
+    }
+}
+
+template <typename F>
+int64_t guarded_count(PFCudaRenderer *r, F &&f) {
+    int64_t n = -1;
+    PFCudaStatus s = guarded(r, [&]() { n = f(); });
+    return s == PF_CUDA_OK ? n : -(int64_t)s;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *PFCudaGetLastError(void) { return g_last_error.c_str(); }
+
+PFCudaDeviceRef PFCudaDeviceCreate(int32_t ordinal) {
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        set_last_error(std::string("no CUDA device: ") + cudaGetErrorString(err));
+        return nullptr;
+    }
+    if (ordinal < 0 || ordinal >= count) {
+        set_last_error("CUDA device ordinal out of range");
+        return nullptr;
+    }
+    return new PFCudaDevice{ordinal};
+}
+
+void PFCudaDeviceDestroy(PFCudaDeviceRef device) { delete device; }
+
+uint8_t PFCudaDeviceGetFeatureLevel(PFCudaDeviceRef) { return PF_RENDERER_LEVEL_D3D11; }
+
+PFCudaRendererRef PFCudaRendererCreate(PFCudaDeviceRef device, const uint8_t *area_lut_rgba8, const uint8_t *,
+                                       const PFRendererMode *mode, const PFCudaRendererOptions *options) {
+    if (!device || !area_lut_rgba8 || !mode || !options) {
+        set_last_error("PFCudaRendererCreate: null argument");
+        return nullptr;
+    }
+    if (mode->level != PF_RENDERER_LEVEL_D3D11) {
+        set_last_error("the CUDA backend implements RendererLevel::D3D11 only");
+        return nullptr;
+    }
+    std::unique_ptr<PFCudaRenderer> r(new PFCudaRenderer());
+    r->ordinal = device->ordinal;
+    delete device; // ownership taken, as PFGLRendererCreate does (c/src/lib.rs:601-615)
+    try {
+        r->bind_device();
+        setup_tracking(r.get());
+        PF_CUDA_CHECK(cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking));
+        r->stream = r->own_stream;
+        r->options = *options;
+        allocate_dest(r.get());
+        // Area LUT: 256x256 RGBA8, LINEAR + CLAMP_TO_EDGE (gl/src/lib.rs:375,674-705).
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+        PF_CUDA_CHECK(cudaMallocArray(&r->lut_array, &desc, 256, 256));
+        PF_CUDA_CHECK(cudaMemcpy2DToArray(r->lut_array, 0, 0, area_lut_rgba8, 256 * 4, 256 * 4, 256, cudaMemcpyHostToDevice));
+        cudaResourceDesc res{};
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = r->lut_array;
+        cudaTextureDesc tex{};
+        tex.addressMode[0] = cudaAddressModeClamp;
+        tex.addressMode[1] = cudaAddressModeClamp;
+        tex.filterMode = cudaFilterModeLinear;
+        tex.readMode = cudaReadModeNormalizedFloat;
+        tex.normalizedCoords = 1;
+        PF_CUDA_CHECK(cudaCreateTextureObject(&r->lut_tex, &res, &tex, nullptr));
+    } catch (const std::exception &e) {
+        set_last_error(e.what());
+        return nullptr;
+    }
+    return r.release();
+}
+
+void PFCudaRendererDestroy(PFCudaRendererRef r) {
+    if (!r) return;
+    cudaSetDevice(r->ordinal);
+    cudaStreamSynchronize(r->stream);
+    if (r->lut_tex) cudaDestroyTextureObject(r->lut_tex);
+    if (r->lut_array) cudaFreeArray(r->lut_array);
+    if (r->meta_copied) cudaEventDestroy(r->meta_copied);
+    r->timer.destroy();
+    cudaStream_t own = r->own_stream;
+    delete r;
+    if (own) cudaStreamDestroy(own);
+}
+
+PFCudaStatus PFCudaRendererSetOptions(PFCudaRendererRef r, const PFCudaRendererOptions *options) {
+    return guarded(r, [&]() {
+        if (!options) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null options");
+        PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        r->options = *options;
+        allocate_dest(r);
+    });
+}
+
+PFCudaStatus PFCudaRendererBeginScene(PFCudaRendererRef r) {
+    return guarded(r, [&]() {
+        if (r->in_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "begin_scene called twice");
+        r->in_scene = true;
+        r->batches_drawn = 0;
+        r->stats = PFCudaRenderStats{};
+        r->times = PFCudaRenderTime{};
+    });
+}
+
+PFCudaStatus PFCudaRendererRenderCommand(PFCudaRendererRef r, const PFRenderCommand *cmd) {
+    return guarded(r, [&]() {
+        if (!cmd) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null command");
+        if (!r->in_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "render_command outside begin_scene/end_scene");
+        switch (cmd->kind) {
+        case PF_RENDER_COMMAND_START:
+            break;
+        case PF_RENDER_COMMAND_UPLOAD_TEXTURE_METADATA:
+            upload_texture_metadata(r, cmd->u.upload_texture_metadata.entries,
+                                    cmd->u.upload_texture_metadata.entry_count);
+            break;
+        case PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11:
+            upload_segments(r, r->draw_segments, cmd->u.upload_scene_d3d11.draw_segments);
+            upload_segments(r, r->clip_segments, cmd->u.upload_scene_d3d11.clip_segments);
+            r->has_scene = true;
+            break;
+        case PF_RENDER_COMMAND_PREPARE_CLIP_TILES_D3D11:
+            if (cmd->u.prepare_clip_tiles_d3d11.batch.path_count > 0)
+                throw Error(PF_CUDA_ERROR_UNSUPPORTED, "clip paths are a 'next' row (SURVEY.md §8 f1)");
+            break;
+        case PF_RENDER_COMMAND_DRAW_TILES_D3D11:
+            if (cmd->u.draw_tiles_d3d11.has_color_texture)
+                throw Error(PF_CUDA_ERROR_UNSUPPORTED, "colour textures (gradients/patterns) are out of scope");
+            draw_tile_batch(r, cmd->u.draw_tiles_d3d11.tile_batch_data);
+            break;
+        case PF_RENDER_COMMAND_FINISH:
+            r->stats.cpu_build_time_ns = cmd->u.finish.cpu_build_time_ns;
+            break;
+        case PF_RENDER_COMMAND_ADD_FILLS_D3D9:
+        case PF_RENDER_COMMAND_FLUSH_FILLS_D3D9:
+        case PF_RENDER_COMMAND_DRAW_TILES_D3D9:
+            // Renderer::require_d3d11 (gpu/renderer.rs:1349-1360) panics here.
+            throw Error(PF_CUDA_ERROR_WRONG_LEVEL, "D3D9-level command sent to the D3D11-level CUDA renderer");
+        case PF_RENDER_COMMAND_ALLOCATE_TEXTURE_PAGE:
+        case PF_RENDER_COMMAND_UPLOAD_TEXEL_DATA:
+        case PF_RENDER_COMMAND_DECLARE_RENDER_TARGET:
+        case PF_RENDER_COMMAND_PUSH_RENDER_TARGET:
+        case PF_RENDER_COMMAND_POP_RENDER_TARGET:
+            throw Error(PF_CUDA_ERROR_UNSUPPORTED, "texture pages / render targets are 'next' rows (SURVEY.md §8 f3, f4)");
+        default:
+            throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "unknown render command kind");
+        }
+    });
+}
+
+PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
+    return guarded(r, [&]() {
+        if (!r->in_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "end_scene without begin_scene");
+        r->in_scene = false;
+        if (r->batches_drawn == 0) {
+            // Nothing drawn: the frame is the clear colour (tile.cs.glsl LOAD_ACTION_CLEAR).
+            const FbRect fb = framebuffer_tile_rect(r);
+            const uint32_t n_fb = (uint32_t)((fb.max_x - fb.min_x) * (fb.max_y - fb.min_y));
+            r->fb_start.ensure(n_fb + 1);
+            r->fb_end.ensure(n_fb + 1);
+            PF_CUDA_CHECK(cudaMemsetAsync(r->fb_start.ptr, 0, (size_t)n_fb * 4, r->stream));
+            PF_CUDA_CHECK(cudaMemsetAsync(r->fb_end.ptr, 0, (size_t)n_fb * 4, r->stream));
+            CompositeArgs ca{};
+            ca.fb_start = r->fb_start.ptr;
+            ca.fb_end = r->fb_end.ptr;
+            ca.fb = fb;
+            ca.tile_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
+            ca.tile_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
+            ca.dest = r->dest;
+            ca.dest_pitch = r->dest_pitch;
+            ca.dest_w = r->options.dest_size.x;
+            ca.dest_h = r->options.dest_size.y;
+            ca.clear_color = clear_color(r);
+            r->stats.drawcall_count += (uint64_t)launch_composite(ca, r->stream);
+        }
+        r->stats.gpu_bytes_allocated = r->bytes_allocated;
+        r->stats.gpu_bytes_committed = r->bytes_allocated;
+    });
+}
+
+PFCudaStatus PFCudaRendererReadPixels(PFCudaRendererRef r, uint8_t *dst, size_t stride) {
+    return guarded(r, [&]() {
+        size_t row = (size_t)r->options.dest_size.x * 4;
+        if (!dst || stride < row) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "bad destination / stride");
+        PF_CUDA_CHECK(cudaMemcpy2DAsync(dst, stride, r->dest, r->dest_pitch, row, (size_t)r->options.dest_size.y,
+                                        cudaMemcpyDeviceToHost, r->stream));
+        PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    });
+}
+
+PFCudaStatus PFCudaRendererGetDestDevicePointer(PFCudaRendererRef r, uint64_t *device_ptr, size_t *pitch) {
+    return guarded(r, [&]() {
+        if (device_ptr) *device_ptr = (uint64_t)(uintptr_t)r->dest;
+        if (pitch) *pitch = r->dest_pitch;
+    });
+}
+
+PFCudaStatus PFCudaRendererSetDestDevicePointer(PFCudaRendererRef r, uint64_t device_ptr, size_t pitch) {
+    return guarded(r, [&]() {
+        PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        if (device_ptr == 0) {
+            r->dest_external = false;
+            allocate_dest(r);
+        } else {
+            if (pitch < (size_t)r->options.dest_size.x * 4) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "pitch too small");
+            r->dest_external = true;
+            r->dest = reinterpret_cast<uint8_t *>((uintptr_t)device_ptr);
+            r->dest_pitch = pitch;
+        }
+    });
+}
+
+PFCudaStatus PFCudaRendererSetStream(PFCudaRendererRef r, uint64_t cuda_stream) {
+    return guarded(r, [&]() {
+        PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        r->stream = cuda_stream ? reinterpret_cast<cudaStream_t>((uintptr_t)cuda_stream) : r->own_stream;
+    });
+}
+
+PFCudaStatus PFCudaRendererSynchronize(PFCudaRendererRef r) {
+    return guarded(r, [&]() { PF_CUDA_CHECK(cudaStreamSynchronize(r->stream)); });
+}
+
+PFCudaStatus PFCudaRendererSetStrip(PFCudaRendererRef r, int32_t tile_y0, int32_t tile_y1) {
+    return guarded(r, [&]() {
+        if (tile_y1 < tile_y0) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "strip rows out of order");
+        r->strip_y0 = tile_y0;
+        r->strip_y1 = tile_y1;
+    });
+}
+
+PFCudaStatus PFCudaRendererSetViewBox(PFCudaRendererRef r, const PFRectF *view_box) {
+    return guarded(r, [&]() {
+        if (!view_box) {
+            r->has_view_box = false;
+            return;
+        }
+        r->has_view_box = true;
+        r->view_box = ViewBox{view_box->origin.x, view_box->origin.y, view_box->lower_right.x, view_box->lower_right.y};
+    });
+}
+
+static PFCudaStatus forward_command(const PFRenderCommand *command, void *userdata) {
+    return PFCudaRendererRenderCommand(static_cast<PFCudaRendererRef>(userdata), command);
+}
+
+// Scene::build_and_render (renderer/src/scene.rs:369-378).
+PFCudaStatus PFSceneBuildAndRenderCuda(PFSceneRef scene, PFCudaRendererRef r, PFBuildOptionsRef options) {
+    if (!scene || !r || !options) {
+        set_last_error("PFSceneBuildAndRenderCuda: null argument");
+        return PF_CUDA_ERROR_INVALID_ARGUMENT;
+    }
+    PFRectF vb;
+    PFSceneGetViewBox(scene, &vb);
+    PFCudaStatus st = PFCudaRendererSetViewBox(r, &vb);
+    if (st != PF_CUDA_OK) return st;
+    st = PFCudaRendererBeginScene(r);
+    if (st != PF_CUDA_OK) return st;
+    st = PFSceneBuild(scene, options, &r->sink_state, forward_command, r);
+    PFCudaStatus end = PFCudaRendererEndScene(r);
+    return st != PF_CUDA_OK ? st : end;
+}
+
+PFCudaStatus PFCudaRendererGetStats(PFCudaRendererRef r, PFCudaRenderStats *stats) {
+    return guarded(r, [&]() {
+        if (!stats) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null stats");
+        *stats = r->stats;
+        if (r->debug_lists && r->batches_drawn > 0 && !r->in_scene) {
+            ensure_alpha_ids(r);
+            stats->alpha_tile_count = r->last_alpha_tiles;
+        }
+    });
+}
+
+PFCudaStatus PFCudaRendererSetTimingEnabled(PFCudaRendererRef r, int32_t enabled) {
+    return guarded(r, [&]() { r->timing = enabled != 0; });
+}
+
+PFCudaStatus PFCudaRendererGetTimes(PFCudaRendererRef r, PFCudaRenderTime *times) {
+    return guarded(r, [&]() {
+        if (!times) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null times");
+        *times = r->times;
+    });
+}
+
+PFCudaStatus PFCudaRendererSetDebugListsEnabled(PFCudaRendererRef r, int32_t enabled) {
+    return guarded(r, [&]() { r->debug_lists = enabled != 0; });
+}
+
+int64_t PFCudaRendererDebugCopyLines(PFCudaRendererRef r, float *out_lines, uint32_t *out_paths, size_t cap) {
+    return guarded_count(r, [&]() -> int64_t {
+        size_t n = r->last_lines, m = n < cap ? n : cap;
+        if (out_lines && m) PF_CUDA_CHECK(cudaMemcpyAsync(out_lines, r->lines.ptr, m * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
+        if (out_paths && m) PF_CUDA_CHECK(cudaMemcpyAsync(out_paths, r->line_path.ptr, m * 4, cudaMemcpyDeviceToHost, r->stream));
+        PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        return (int64_t)n;
+    });
+}
+
+int64_t PFCudaRendererDebugCopyFills(PFCudaRendererRef r, PFFill *out, size_t cap) {
+    return guarded_count(r, [&]() -> int64_t {
+        size_t n = r->last_fills, m = n < cap ? n : cap;
+        if (out && m) {
+            ensure_alpha_ids(r);
+            r->dump_out.ensure(n * sizeof(PFFill) + 16, 1.25);
+            launch_dump_fills((uint32_t)n, r->fills_emit.ptr, r->tile_alpha_id.ptr, r->dump_out.ptr, r->stream);
+            PF_CUDA_CHECK(cudaMemcpyAsync(out, r->dump_out.ptr, m * sizeof(PFFill), cudaMemcpyDeviceToHost, r->stream));
+            PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        }
+        return (int64_t)n;
+    });
+}
+
+int64_t PFCudaRendererDebugCopyTiles(PFCudaRendererRef r, PFTileObjectPrimitive *out, size_t cap) {
+    return guarded_count(r, [&]() -> int64_t {
+        ensure_alpha_ids(r);
+        const BatchDev &b = r->last_batch;
+        // tile_fb / tile_pos are free again after the sort stage: reuse them as flags / positions.
+        launch_dump_tile_flags(b.n_tiles, r->tile_word.ptr, r->tile_fb.ptr, r->stream);
+        exclusive_scan(LoadU32{r->tile_fb.ptr}, r->tile_pos.ptr, b.n_tiles, r->counters.ptr + 4, r->scan_scratch, r->stream);
+        size_t n = b.n_tiles ? read_counter(r, 4) : 0;
+        size_t m = n < cap ? n : cap;
+        if (out && m) {
+            r->dump_out.ensure(n * sizeof(PFTileObjectPrimitive) + 16, 1.25);
+            launch_dump_tiles(b, r->tile_word.ptr, r->tile_alpha_id.ptr, r->tile_fb.ptr, r->tile_pos.ptr, r->dump_out.ptr, r->stream);
+            PF_CUDA_CHECK(cudaMemcpyAsync(out, r->dump_out.ptr, m * sizeof(PFTileObjectPrimitive), cudaMemcpyDeviceToHost, r->stream));
+            PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        }
+        return (int64_t)n;
+    });
+}
+
+int64_t PFCudaRendererDebugCopyZBuffer(PFCudaRendererRef r, int32_t *out, size_t cap, int32_t rect_out[4]) {
+    return guarded_count(r, [&]() -> int64_t {
+        const FbRect &fb = r->last_fb;
+        if (rect_out) {
+            rect_out[0] = fb.min_x, rect_out[1] = fb.min_y, rect_out[2] = fb.max_x, rect_out[3] = fb.max_y;
+        }
+        size_t n = (size_t)(fb.max_x - fb.min_x) * (size_t)(fb.max_y - fb.min_y), m = n < cap ? n : cap;
+        if (out && m) {
+            PF_CUDA_CHECK(cudaMemcpyAsync(out, r->z_buffer.ptr, m * 4, cudaMemcpyDeviceToHost, r->stream));
+            PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        }
+        return (int64_t)n;
+    });
+}
+
+int64_t PFCudaRendererDebugCopyAlphaMasks(PFCudaRendererRef r, float *out, size_t cap_tiles) {
+    return guarded_count(r, [&]() -> int64_t {
+        ensure_alpha_ids(r);
+        size_t n = r->last_alpha_tiles;
+        if (out && n) {
+            if (cap_tiles < n) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "alpha mask buffer too small");
+            r->dump_out.ensure(n * 256 * sizeof(float) + 16, 1.25);
+            launch_alpha_masks(r->last_batch.n_tiles, r->tile_word.ptr, r->tile_fill_pos.ptr, r->tile_alpha_id.ptr,
+                               r->fills.ptr, r->lut_tex, reinterpret_cast<float *>(r->dump_out.ptr), r->stream);
+            PF_CUDA_CHECK(cudaMemcpyAsync(out, r->dump_out.ptr, n * 256 * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+            PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        }
+        return (int64_t)n;
+    });
+}
+
+} // extern "C"

@@ -1,0 +1,453 @@
+// pathfinder_b200/csrc/scene.cpp — host side above the C ABI: Scene, BuildOptions and the D3D11-level
+// SceneBuilder, mirrored in C++ because this image has no Rust toolchain (SURVEY.md §0 finding 2).
+//
+// Mirrors (paths relative to the reference checkout):
+//   Scene / DrawPath / ClipPath          renderer/src/scene.rs:36-226, 425-560
+//   BuildOptions / RenderTransform       renderer/src/options.rs:50-181
+//   SceneBuilder::build (D3D11 branch)   renderer/src/builder.rs:148-222
+//   BuiltSegments::from_scene, add_path  renderer/src/builder.rs:777-841
+//   prepare_draw_path_for_gpu_binning    renderer/src/builder.rs:1058-1095
+//   TileBatchDataD3D11::push             renderer/src/builder.rs:653-759
+//   Palette (solid colours only)         renderer/src/paint.rs:398-438, 641-659
+// Geometry helpers keep the reference's operator order so tile rects match
+// the CPU tiler's for scale + translate transforms; build without -ffast-math / FMA contraction.
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/pf_cuda.h"
+
+namespace pf {
+void set_last_error(const std::string &msg);
+}
+
+namespace {
+
+struct RectF {
+    float min_x, min_y, max_x, max_y;
+};
+
+inline float sse_min(float a, float b) { return a < b ? a : b; } // _mm_min_ps
+inline float sse_max(float a, float b) { return a > b ? a : b; } // _mm_max_ps
+
+inline RectF union_rect(RectF a, RectF b) { // geometry/src/rect.rs:114-120
+    return RectF{sse_min(a.min_x, b.min_x), sse_min(a.min_y, b.min_y), sse_max(a.max_x, b.max_x),
+                 sse_max(a.max_y, b.max_y)};
+}
+
+struct Transform {
+    float m11 = 1, m21 = 0, m12 = 0, m22 = 1, tx = 0, ty = 0;
+    bool is_identity() const { return m11 == 1 && m21 == 0 && m12 == 0 && m22 == 1 && tx == 0 && ty == 0; }
+    // Transform2F * Vector2F (geometry/src/transform2d.rs:123-130,312-318)
+    void apply(float x, float y, float &ox, float &oy) const {
+        float hx = m11 * x, hy = m21 * x, hz = m12 * y, hw = m22 * y;
+        ox = (hx + hz) + tx;
+        oy = (hy + hw) + ty;
+    }
+    // Transform2F * RectF (geometry/src/transform2d.rs:329-338)
+    RectF apply_rect(RectF r) const {
+        float ulx, uly, urx, ury, llx, lly, lrx, lry;
+        apply(r.min_x, r.min_y, ulx, uly);
+        apply(r.max_x, r.min_y, urx, ury);
+        apply(r.min_x, r.max_y, llx, lly);
+        apply(r.max_x, r.max_y, lrx, lry);
+        RectF o;
+        o.min_x = sse_min(sse_min(sse_min(ulx, urx), llx), lrx);
+        o.min_y = sse_min(sse_min(sse_min(uly, ury), lly), lry);
+        o.max_x = sse_max(sse_max(sse_max(ulx, urx), llx), lrx);
+        o.max_y = sse_max(sse_max(sse_max(uly, ury), lly), lry);
+        return o;
+    }
+};
+
+struct Path {
+    uint32_t first_contour, end_contour;
+    RectF bounds; // Outline::bounds(): min/max over all points of all non-empty contours
+    uint16_t paint;
+    uint8_t fill_rule, blend_mode;
+    uint32_t clip_path;
+};
+
+std::atomic<uint32_t> g_next_scene_id{0}; // NEXT_SCENE_ID, scene.rs:34
+
+} // namespace
+
+struct PFScene {
+    std::vector<PFVector2F> points;
+    std::vector<uint8_t> flags;
+    std::vector<uint32_t> contour_offsets{0};
+    std::vector<Path> draw_paths, clip_paths;
+    std::vector<PFColorU> paints;
+    std::unordered_map<uint32_t, uint16_t> paint_cache; // Palette::push_paint dedup (paint.rs:115-131)
+    RectF bounds{0, 0, 0, 0};
+    RectF view_box{0, 0, 0, 0};
+    uint32_t id;
+    uint32_t epoch = 0;
+
+    // Scratch reused across builds.
+    std::vector<PFVector2F> seg_points;
+    std::vector<PFSegmentIndicesD3D11> seg_indices;
+    std::vector<uint32_t> draw_segment_ranges; // [n_draw][2]
+    std::vector<PFPropagateMetadataD3D11> propagate_metadata;
+    std::vector<PFDiceMetadataD3D11> dice_metadata;
+    std::vector<PFTilePathInfoD3D11> tile_path_info;
+    std::vector<PFTextureMetadataEntry> texture_metadata;
+
+    PFScene() : id(g_next_scene_id.fetch_add(1)) {}
+};
+
+struct PFRenderTransform {
+    Transform t;
+};
+struct PFBuildOptions {
+    Transform transform; // RenderTransform::Transform2D; default identity (options.rs:80-85)
+    float dilation[2] = {0, 0};
+    bool subpixel_aa_enabled = false;
+};
+
+namespace {
+
+// Appends an outline's contours to the scene pools and returns its bounds
+// (Contour::push_point with update_bounds, content/src/outline.rs:560-573; Outline::push_contour
+// :180-192 drops empty contours).
+Path append_outline(PFScene *s, const PFVector2F *points, const uint8_t *point_flags,
+                    const uint32_t *contour_offsets, uint32_t contour_count) {
+    Path p{};
+    p.first_contour = (uint32_t)s->contour_offsets.size() - 1;
+    bool have_bounds = false;
+    RectF bounds{0, 0, 0, 0};
+    for (uint32_t c = 0; c < contour_count; c++) {
+        uint32_t p0 = contour_offsets[c], p1 = contour_offsets[c + 1];
+        if (p0 == p1) continue;
+        RectF cb{points[p0].x, points[p0].y, points[p0].x, points[p0].y};
+        for (uint32_t i = p0; i < p1; i++) {
+            s->points.push_back(points[i]);
+            s->flags.push_back(point_flags[i]);
+            cb.min_x = sse_min(cb.min_x, points[i].x);
+            cb.min_y = sse_min(cb.min_y, points[i].y);
+            cb.max_x = sse_max(cb.max_x, points[i].x);
+            cb.max_y = sse_max(cb.max_y, points[i].y);
+        }
+        s->contour_offsets.push_back((uint32_t)s->points.size());
+        bounds = have_bounds ? union_rect(bounds, cb) : cb;
+        have_bounds = true;
+    }
+    p.end_contour = (uint32_t)s->contour_offsets.size() - 1;
+    p.bounds = bounds;
+    return p;
+}
+
+// SegmentsD3D11::add_path (renderer/src/builder.rs:804-841).
+void add_path_segments(const PFScene *s, const Path &path, std::vector<PFVector2F> &points,
+                       std::vector<PFSegmentIndicesD3D11> &indices, uint32_t range[2]) {
+    range[0] = (uint32_t)indices.size();
+    for (uint32_t c = path.first_contour; c < path.end_contour; c++) {
+        const uint32_t p0 = s->contour_offsets[c], point_count = s->contour_offsets[c + 1] - p0;
+        const uint8_t *flags = s->flags.data() + p0;
+        const PFVector2F *pts = s->points.data() + p0;
+        for (uint32_t i = 0; i < point_count; i++) {
+            if (!(flags[i] & (PF_POINT_FLAGS_CONTROL_POINT_0 | PF_POINT_FLAGS_CONTROL_POINT_1))) {
+                uint32_t f = 0;
+                if (i + 1 < point_count && (flags[i + 1] & PF_POINT_FLAGS_CONTROL_POINT_0)) {
+                    if (i + 2 < point_count && (flags[i + 2] & PF_POINT_FLAGS_CONTROL_POINT_1))
+                        f = PF_CURVE_IS_CUBIC;
+                    else
+                        f = PF_CURVE_IS_QUADRATIC;
+                }
+                indices.push_back(PFSegmentIndicesD3D11{(uint32_t)points.size(), f});
+            }
+            points.push_back(pts[i]);
+        }
+        points.push_back(pts[0]); // implicit close: the first point again (builder.rs:835)
+    }
+    range[1] = (uint32_t)indices.size();
+}
+
+// RectF::intersection (geometry/src/rect.rs:122-137), strict comparisons.
+bool rect_intersection(RectF a, RectF b, RectF &out) {
+    if (!(a.min_x < b.max_x && a.min_y < b.max_y && b.min_x < a.max_x && b.min_y < a.max_y)) return false;
+    out = RectF{sse_max(a.min_x, b.min_x), sse_max(a.min_y, b.min_y), sse_min(a.max_x, b.max_x),
+                sse_min(a.max_y, b.max_y)};
+    return true;
+}
+
+PFRenderCommand make_command(uint32_t kind) {
+    PFRenderCommand c;
+    memset(&c, 0, sizeof(c));
+    c.kind = kind;
+    return c;
+}
+
+} // namespace
+
+extern "C" {
+
+PFSceneRef PFSceneCreate(void) { return new PFScene(); }
+void PFSceneDestroy(PFSceneRef scene) { delete scene; }
+
+void PFSceneSetViewBox(PFSceneRef s, const PFRectF *vb) {
+    s->view_box = RectF{vb->origin.x, vb->origin.y, vb->lower_right.x, vb->lower_right.y};
+    s->epoch++;
+}
+void PFSceneGetViewBox(PFSceneRef s, PFRectF *vb) {
+    vb->origin = PFVector2F{s->view_box.min_x, s->view_box.min_y};
+    vb->lower_right = PFVector2F{s->view_box.max_x, s->view_box.max_y};
+}
+void PFSceneGetBounds(PFSceneRef s, PFRectF *b) {
+    b->origin = PFVector2F{s->bounds.min_x, s->bounds.min_y};
+    b->lower_right = PFVector2F{s->bounds.max_x, s->bounds.max_y};
+}
+
+uint16_t PFScenePushPaint(PFSceneRef s, const PFColorU *color) {
+    uint32_t key = (uint32_t)color->r | ((uint32_t)color->g << 8) | ((uint32_t)color->b << 16) | ((uint32_t)color->a << 24);
+    auto it = s->paint_cache.find(key);
+    if (it != s->paint_cache.end()) return it->second;
+    uint16_t id = (uint16_t)s->paints.size(); // PaintId(u16), paint.rs:81
+    s->paints.push_back(*color);
+    s->paint_cache.emplace(key, id);
+    s->epoch++;
+    return id;
+}
+
+uint32_t PFScenePushDrawPath(PFSceneRef s, const PFVector2F *points, const uint8_t *point_flags,
+                             const uint32_t *contour_offsets, uint32_t contour_count, uint16_t paint_id,
+                             uint8_t fill_rule, uint8_t blend_mode, uint32_t clip_path_id) {
+    Path p = append_outline(s, points, point_flags, contour_offsets, contour_count);
+    p.paint = paint_id;
+    p.fill_rule = fill_rule;
+    p.blend_mode = blend_mode;
+    p.clip_path = clip_path_id;
+    s->bounds = union_rect(s->bounds, p.bounds); // scene.rs:84-86
+    s->draw_paths.push_back(p);
+    s->epoch++;
+    return (uint32_t)s->draw_paths.size() - 1;
+}
+
+uint32_t PFScenePushClipPath(PFSceneRef s, const PFVector2F *points, const uint8_t *point_flags,
+                             const uint32_t *contour_offsets, uint32_t contour_count, uint8_t fill_rule,
+                             uint32_t clip_path_id) {
+    Path p = append_outline(s, points, point_flags, contour_offsets, contour_count);
+    p.paint = 0;
+    p.fill_rule = fill_rule;
+    p.blend_mode = PF_BLEND_MODE_SRC_OVER;
+    p.clip_path = clip_path_id;
+    s->bounds = union_rect(s->bounds, p.bounds);
+    s->clip_paths.push_back(p);
+    s->epoch++;
+    return (uint32_t)s->clip_paths.size() - 1;
+}
+
+PFCudaStatus PFScenePushDrawPaths(PFSceneRef s, const PFVector2F *points, const uint8_t *point_flags,
+                                  size_t point_count, const uint32_t *contour_offsets, size_t contour_count,
+                                  const uint32_t *path_contour_offsets, size_t path_count,
+                                  const uint16_t *paint_ids, const uint8_t *fill_rules,
+                                  const uint32_t *clip_path_ids) {
+    if (contour_count && contour_offsets[contour_count] != point_count) {
+        pf::set_last_error("PFScenePushDrawPaths: contour_offsets do not cover the points");
+        return PF_CUDA_ERROR_INVALID_ARGUMENT;
+    }
+    s->points.reserve(s->points.size() + point_count);
+    s->flags.reserve(s->flags.size() + point_count);
+    s->contour_offsets.reserve(s->contour_offsets.size() + contour_count);
+    s->draw_paths.reserve(s->draw_paths.size() + path_count);
+    for (size_t i = 0; i < path_count; i++) {
+        uint32_t c0 = path_contour_offsets[i], c1 = path_contour_offsets[i + 1];
+        Path p = append_outline(s, points, point_flags, contour_offsets + c0, c1 - c0);
+        p.paint = paint_ids[i];
+        p.fill_rule = fill_rules[i];
+        p.blend_mode = PF_BLEND_MODE_SRC_OVER;
+        p.clip_path = clip_path_ids ? clip_path_ids[i] : PF_CLIP_PATH_NONE;
+        if (p.paint >= s->paints.size()) {
+            pf::set_last_error("PFScenePushDrawPaths: unknown paint id");
+            return PF_CUDA_ERROR_INVALID_ARGUMENT;
+        }
+        s->bounds = union_rect(s->bounds, p.bounds);
+        s->draw_paths.push_back(p);
+    }
+    s->epoch++;
+    return PF_CUDA_OK;
+}
+
+uint32_t PFSceneGetDrawPathCount(PFSceneRef s) { return (uint32_t)s->draw_paths.size(); }
+uint32_t PFSceneGetEpoch(PFSceneRef s) { return s->epoch; }
+
+PFRenderTransformRef PFRenderTransformCreate2D(const PFTransform2F *t) {
+    PFRenderTransform *r = new PFRenderTransform();
+    // Row-major C struct (c/src/lib.rs:151-163): m00 = m11(), m01 = m12(), m10 = m21(), m11 = m22().
+    r->t.m11 = t->matrix.m00, r->t.m12 = t->matrix.m01, r->t.m21 = t->matrix.m10, r->t.m22 = t->matrix.m11;
+    r->t.tx = t->vector.x, r->t.ty = t->vector.y;
+    return r;
+}
+void PFRenderTransformDestroy(PFRenderTransformRef t) { delete t; }
+PFBuildOptionsRef PFBuildOptionsCreate(void) { return new PFBuildOptions(); }
+void PFBuildOptionsDestroy(PFBuildOptionsRef o) { delete o; }
+void PFBuildOptionsSetTransform(PFBuildOptionsRef o, PFRenderTransformRef t) {
+    o->transform = t->t;
+    delete t; // consumed (c/src/lib.rs:768-772)
+}
+void PFBuildOptionsSetDilation(PFBuildOptionsRef o, const PFVector2F *d) {
+    o->dilation[0] = d->x;
+    o->dilation[1] = d->y;
+}
+void PFBuildOptionsSetSubpixelAAEnabled(PFBuildOptionsRef o, int32_t enabled) { o->subpixel_aa_enabled = enabled != 0; }
+
+PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState *sink,
+                          PFRenderCommandListenerFn listener, void *userdata) {
+    if (!s || !opts || !sink || !listener) {
+        pf::set_last_error("PFSceneBuild: null argument");
+        return PF_CUDA_ERROR_INVALID_ARGUMENT;
+    }
+    auto start_time = std::chrono::steady_clock::now();
+    PFCudaStatus st;
+#define SEND(cmd)                                  \
+    do {                                           \
+        st = listener(&(cmd), userdata);           \
+        if (st != PF_CUDA_OK) return st;           \
+    } while (0)
+
+    if (opts->dilation[0] != 0.0f || opts->dilation[1] != 0.0f || opts->subpixel_aa_enabled) {
+        // The reference's GPU prepare mode silently ignores both; the text
+        // configuration that needs them is a 'next' row (f3). Refuse rather than render differently
+        // from the CPU tiler.
+        pf::set_last_error("dilation / subpixel AA are not implemented on the D3D11-level path yet");
+        return PF_CUDA_ERROR_UNSUPPORTED;
+    }
+
+    // builder.rs:160-164
+    PFRenderCommand start = make_command(PF_RENDER_COMMAND_START);
+    start.u.start.path_count = s->clip_paths.size() + s->draw_paths.size();
+    start.u.start.needs_readable_framebuffer = 0; // only SrcOver is in scope (builder.rs:372-393)
+    SEND(start);
+
+    // Paint data (builder.rs:174-180): one TextureMetadataEntry per paint (paint.rs:641-659).
+    s->texture_metadata.resize(s->paints.size());
+    for (size_t i = 0; i < s->paints.size(); i++) {
+        PFTextureMetadataEntry &e = s->texture_metadata[i];
+        memset(&e, 0, sizeof(e));
+        e.color_0_transform.matrix = PFMatrix2x2F{1, 0, 0, 1};
+        e.base_color = s->paints[i];
+    }
+    PFRenderCommand meta = make_command(PF_RENDER_COMMAND_UPLOAD_TEXTURE_METADATA);
+    meta.u.upload_texture_metadata.entries = s->texture_metadata.data();
+    meta.u.upload_texture_metadata.entry_count = s->texture_metadata.size();
+    SEND(meta);
+
+    // Scene upload when dirty (builder.rs:190-216).
+    bool dirty = !sink->has_last_scene || sink->last_scene_id != s->id || sink->last_scene_epoch != s->epoch;
+    if (dirty || s->draw_segment_ranges.size() != 2 * s->draw_paths.size()) {
+        for (const Path &p : s->clip_paths)
+            if (p.first_contour != p.end_contour) {
+                pf::set_last_error("clip paths are a 'next' row (SURVEY.md §8 f1)");
+                return PF_CUDA_ERROR_UNSUPPORTED;
+            }
+        s->seg_points.clear();
+        s->seg_indices.clear();
+        s->draw_segment_ranges.resize(2 * s->draw_paths.size());
+        s->seg_points.reserve(s->points.size() + s->contour_offsets.size());
+        s->seg_indices.reserve(s->points.size());
+        for (size_t i = 0; i < s->draw_paths.size(); i++)
+            add_path_segments(s, s->draw_paths[i], s->seg_points, s->seg_indices, &s->draw_segment_ranges[2 * i]);
+        PFRenderCommand up = make_command(PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11);
+        up.u.upload_scene_d3d11.draw_segments = PFSegmentsD3D11{s->seg_points.data(), s->seg_points.size(),
+                                                                 s->seg_indices.data(), s->seg_indices.size()};
+        up.u.upload_scene_d3d11.clip_segments = PFSegmentsD3D11{nullptr, 0, nullptr, 0};
+        SEND(up);
+        sink->has_last_scene = 1;
+        sink->last_scene_id = s->id;
+        sink->last_scene_epoch = s->epoch;
+    }
+
+    // build_tile_batches at the D3D11 level (builder.rs:327-357, 886-1056): solid colours never
+    // break a batch (fixup_batch_for_new_path_if_possible, :1227-1243), so one DrawTilesD3D11.
+    const Transform &xf = opts->transform; // PrepareMode::GPU { transform } (options.rs:165-180)
+    const RectF effective_view_box = s->view_box; // subpixel AA refused above (scene.rs:276-282)
+    s->propagate_metadata.clear();
+    s->dice_metadata.clear();
+    s->tile_path_info.clear();
+    uint32_t tile_count = 0, segment_count = 0, column_count = 0;
+    for (uint32_t i = 0; i < s->draw_paths.size(); i++) {
+        const Path &p = s->draw_paths[i];
+        if (p.clip_path != PF_CLIP_PATH_NONE) {
+            pf::set_last_error("clip paths are a 'next' row (SURVEY.md §8 f1)");
+            return PF_CUDA_ERROR_UNSUPPORTED;
+        }
+        if (p.blend_mode != PF_BLEND_MODE_SRC_OVER) {
+            pf::set_last_error("only BlendMode::SrcOver is on the hot path");
+            return PF_CUDA_ERROR_UNSUPPORTED;
+        }
+        // prepare_draw_path_for_gpu_binning (builder.rs:1058-1095)
+        RectF path_bounds = xf.is_identity() ? p.bounds : xf.apply_rect(p.bounds);
+        RectF clipped;
+        if (!rect_intersection(path_bounds, effective_view_box, clipped)) continue;
+        // round_rect_out_to_tile_bounds (tiles.rs:64-66)
+        const float k = 1.0f / 16.0f;
+        PFRectI tile_rect;
+        tile_rect.origin.x = (int32_t)lrintf(floorf(clipped.min_x * k));
+        tile_rect.origin.y = (int32_t)lrintf(floorf(clipped.min_y * k));
+        tile_rect.lower_right.x = (int32_t)lrintf(ceilf(clipped.max_x * k));
+        tile_rect.lower_right.y = (int32_t)lrintf(ceilf(clipped.max_y * k));
+        const uint32_t w = (uint32_t)(tile_rect.lower_right.x - tile_rect.origin.x);
+        const uint32_t h = (uint32_t)(tile_rect.lower_right.y - tile_rect.origin.y);
+        // BuiltDrawPath::new (builder.rs:80-94): occludes = opaque paint && SrcOver.
+        const bool occludes = s->paints[p.paint].a == 255;
+        const uint8_t ctrl = p.fill_rule == PF_FILL_RULE_EVEN_ODD ? PF_TILE_CTRL_MASK_EVEN_ODD : PF_TILE_CTRL_MASK_WINDING;
+        const uint32_t batch_path_index = (uint32_t)s->propagate_metadata.size();
+        // TileBatchDataD3D11::push (builder.rs:653-721)
+        PFPropagateMetadataD3D11 pm;
+        memset(&pm, 0, sizeof(pm));
+        pm.tile_rect = tile_rect;
+        pm.tile_offset = tile_count;
+        pm.path_index = batch_path_index;
+        pm.z_write = occludes ? 1 : 0;
+        pm.clip_path_index = PF_PATH_INDEX_NONE;
+        pm.backdrop_offset = column_count;
+        s->propagate_metadata.push_back(pm);
+        const uint32_t *range = &s->draw_segment_ranges[2 * (size_t)i];
+        s->dice_metadata.push_back(PFDiceMetadataD3D11{i, range[0], segment_count, 0});
+        PFTilePathInfoD3D11 tp;
+        tp.tile_min_x = (int16_t)tile_rect.origin.x;
+        tp.tile_min_y = (int16_t)tile_rect.origin.y;
+        tp.tile_max_x = (int16_t)tile_rect.lower_right.x;
+        tp.tile_max_y = (int16_t)tile_rect.lower_right.y;
+        tp.first_tile_index = tile_count;
+        tp.color = p.paint;
+        tp.ctrl = ctrl;
+        tp.backdrop = 0;
+        s->tile_path_info.push_back(tp);
+        tile_count += w * h;
+        column_count += w;
+        segment_count += range[1] - range[0];
+    }
+    if (!s->propagate_metadata.empty()) {
+        PFRenderCommand draw = make_command(PF_RENDER_COMMAND_DRAW_TILES_D3D11);
+        PFTileBatchDataD3D11 &b = draw.u.draw_tiles_d3d11.tile_batch_data;
+        b.batch_id = 32; // MAX_CLIP_BATCHES: draw batch ids start there (builder.rs:50,864)
+        b.path_count = (uint32_t)s->propagate_metadata.size();
+        b.tile_count = tile_count;
+        b.segment_count = segment_count;
+        b.prepare_info.backdrops = nullptr; // all-zero initial backdrops (init_backdrops, builder.rs:762-768)
+        b.prepare_info.backdrop_count = 0;
+        b.prepare_info.propagate_metadata = s->propagate_metadata.data();
+        b.prepare_info.dice_metadata = s->dice_metadata.data();
+        b.prepare_info.tile_path_info = s->tile_path_info.data();
+        b.prepare_info.transform.matrix = PFMatrix2x2F{xf.m11, xf.m12, xf.m21, xf.m22};
+        b.prepare_info.transform.vector = PFVector2F{xf.tx, xf.ty};
+        b.path_source = PF_PATH_SOURCE_DRAW;
+        b.has_clipped_path_info = 0;
+        draw.u.draw_tiles_d3d11.has_color_texture = 0;
+        SEND(draw);
+    }
+
+    PFRenderCommand finish = make_command(PF_RENDER_COMMAND_FINISH);
+    finish.u.finish.cpu_build_time_ns =
+        (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - start_time).count();
+    SEND(finish);
+#undef SEND
+    return PF_CUDA_OK;
+}
+
+} // extern "C"

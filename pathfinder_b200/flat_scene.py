@@ -1,0 +1,139 @@
+"""Flat (numpy) scene container: the comparison origin for parity (SURVEY.md §8c — the Scene,
+i.e. post-loader outlines, is where the CUDA path and the oracle start from).
+
+Paths own contiguous contour ranges; contours own contiguous point ranges. Point flags follow
+`content/src/outline.rs` PointFlags (0 on-curve, 1 CONTROL_POINT_0, 2 CONTROL_POINT_1)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+FILL_RULE_WINDING = 0
+FILL_RULE_EVEN_ODD = 1
+NO_CLIP = 0xFFFFFFFF
+
+
+@dataclass
+class FlatScene:
+    points: np.ndarray            # (n_points, 2) float32
+    point_flags: np.ndarray       # (n_points,) uint8
+    contour_offsets: np.ndarray   # (n_contours + 1,) uint32 -> point index
+    path_contour_offsets: np.ndarray  # (n_paths + 1,) uint32 -> contour index (draw paths)
+    fill_rules: np.ndarray        # (n_paths,) uint8
+    paints: np.ndarray            # (n_paths,) uint16 paint id
+    paint_colors: np.ndarray      # (n_paints, 4) uint8 RGBA
+    view_box: tuple               # (min_x, min_y, max_x, max_y)
+    name: str = ""
+    meta: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        self.points = np.ascontiguousarray(self.points, dtype=np.float32).reshape(-1, 2)
+        self.point_flags = np.ascontiguousarray(self.point_flags, dtype=np.uint8)
+        self.contour_offsets = np.ascontiguousarray(self.contour_offsets, dtype=np.uint32)
+        self.path_contour_offsets = np.ascontiguousarray(self.path_contour_offsets, dtype=np.uint32)
+        self.fill_rules = np.ascontiguousarray(self.fill_rules, dtype=np.uint8)
+        self.paints = np.ascontiguousarray(self.paints, dtype=np.uint16)
+        self.paint_colors = np.ascontiguousarray(self.paint_colors, dtype=np.uint8).reshape(-1, 4)
+        self.view_box = tuple(float(v) for v in self.view_box)
+        assert len(self.points) == len(self.point_flags)
+        assert int(self.contour_offsets[-1]) == len(self.points)
+        assert int(self.path_contour_offsets[-1]) == len(self.contour_offsets) - 1
+        assert len(self.fill_rules) == self.n_paths and len(self.paints) == self.n_paths
+
+    @property
+    def n_paths(self) -> int:
+        return len(self.path_contour_offsets) - 1
+
+    @property
+    def n_contours(self) -> int:
+        return len(self.contour_offsets) - 1
+
+    def contour_ranges(self) -> np.ndarray:
+        return np.stack([self.path_contour_offsets[:-1], self.path_contour_offsets[1:]], axis=1).astype(np.uint32)
+
+    def with_view_box(self, view_box) -> "FlatScene":
+        return FlatScene(self.points, self.point_flags, self.contour_offsets, self.path_contour_offsets,
+                         self.fill_rules, self.paints, self.paint_colors, view_box, self.name, dict(self.meta))
+
+    def with_fill_rules(self, fill_rules) -> "FlatScene":
+        return FlatScene(self.points, self.point_flags, self.contour_offsets, self.path_contour_offsets,
+                         fill_rules, self.paints, self.paint_colors, self.view_box, self.name, dict(self.meta))
+
+    def save(self, path: str) -> None:
+        np.savez_compressed(path, points=self.points, point_flags=self.point_flags,
+                            contour_offsets=self.contour_offsets,
+                            path_contour_offsets=self.path_contour_offsets, fill_rules=self.fill_rules,
+                            paints=self.paints, paint_colors=self.paint_colors,
+                            view_box=np.asarray(self.view_box, dtype=np.float32),
+                            name=np.asarray(self.name))
+
+    @staticmethod
+    def load(path: str) -> "FlatScene":
+        z = np.load(path)
+        return FlatScene(z["points"], z["point_flags"], z["contour_offsets"], z["path_contour_offsets"],
+                         z["fill_rules"], z["paints"], z["paint_colors"], tuple(z["view_box"].tolist()),
+                         str(z["name"]))
+
+
+class SceneBuilderPy:
+    """Incremental builder of a FlatScene with a canvas-like path API (move_to / line_to / ...),
+    mirroring how `content/src/outline.rs` Contour::push_endpoint / push_quadratic / push_cubic lay
+    points out."""
+
+    def __init__(self, view_box):
+        self.view_box = tuple(view_box)
+        self._points: list = []
+        self._flags: list = []
+        self._contour_offsets = [0]
+        self._path_contour_offsets = [0]
+        self._fill_rules: list = []
+        self._paints: list = []
+        self._paint_colors: list = []
+        self._paint_cache: dict = {}
+        self._open = False
+
+    def paint(self, rgba) -> int:
+        key = tuple(int(v) for v in rgba)
+        if key not in self._paint_cache:
+            self._paint_cache[key] = len(self._paint_colors)
+            self._paint_colors.append(key)
+        return self._paint_cache[key]
+
+    def move_to(self, x, y):
+        self._end_contour()
+        self._points.append((x, y))
+        self._flags.append(0)
+        self._open = True
+
+    def line_to(self, x, y):
+        self._points.append((x, y))
+        self._flags.append(0)
+
+    def quad_to(self, cx, cy, x, y):
+        self._points += [(cx, cy), (x, y)]
+        self._flags += [1, 0]
+
+    def cubic_to(self, c0x, c0y, c1x, c1y, x, y):
+        self._points += [(c0x, c0y), (c1x, c1y), (x, y)]
+        self._flags += [1, 2, 0]
+
+    def close(self):
+        self._end_contour()
+
+    def _end_contour(self):
+        if self._open and len(self._points) > self._contour_offsets[-1]:
+            self._contour_offsets.append(len(self._points))
+        self._open = False
+
+    def end_path(self, rgba, fill_rule=FILL_RULE_WINDING):
+        self._end_contour()
+        self._path_contour_offsets.append(len(self._contour_offsets) - 1)
+        self._fill_rules.append(fill_rule)
+        self._paints.append(self.paint(rgba))
+
+    def finish(self, name="") -> FlatScene:
+        self._end_contour()
+        return FlatScene(np.asarray(self._points, dtype=np.float32).reshape(-1, 2), self._flags,
+                         self._contour_offsets, self._path_contour_offsets, self._fill_rules, self._paints,
+                         np.asarray(self._paint_colors, dtype=np.uint8).reshape(-1, 4), self.view_box, name)
