@@ -44,7 +44,7 @@ def check_scene(flat, xf, area_lut, size=None, background=(1.0, 1.0, 1.0, 1.0), 
     if masks.size:
         assert np.abs(masks - ref_masks).max() <= COVERAGE_TOL, np.abs(masks - ref_masks).max()
 
-    ref_img = built.render(area_lut, w, h, background=background)
+    ref_img = built.render(area_lut, w, h, background=background or (0.0, 0.0, 0.0, 0.0))
     diff = np.abs(img.astype(np.int32) - ref_img.astype(np.int32))
     assert diff.max() <= RGBA_TOL, f"max RGBA diff {diff.max()} at {np.unravel_index(diff.argmax(), diff.shape)}"
     return r, img, built
