@@ -1,0 +1,398 @@
+#!/usr/bin/env python3
+"""bench.py — the driver's benchmark contract for the CUDA backend.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N > 1: under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm = CPU tiler on host cores
+
+One "step" renders one frame of each scene of the headline workload (BASELINE.json metric:
+"ms/frame + Gsegments/s, tiger@4K & 100k-path@8K"): the Ghostscript tiger at 4096x4096 in its
+all-winding and odd-paths-even-odd variants (BASELINE.json configs[1]) and the synthetic 100k
+random cubic paths at 8192x8192 (configs[3]). A *segment* is one flattened line segment entering
+bin (one process_line_segment call, renderer/src/tiler.rs:177). `value` = segments of all frames of
+the step / device time with the scenes resident in HBM; `e2e` = the same through the public API
+with the scene re-uploaded from host memory and the frame read back to pinned host memory every
+frame. With N > 1 GPUs every frame is partitioned by horizontal tile strips (one rank per GPU) and
+assembled with one NCCL all-gather, so scaling is strong (fixed work per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Gsegments/s"
+UNIT = "Gsegments/s"
+
+
+def workload_scenes(which: str):
+    """Returns [(name, FlatScene, transform | None, size)]."""
+    from pathfinder_b200 import scenes
+    out = []
+    if which in ("headline", "tiger4k"):
+        flat, xf = scenes.tiger(4096)
+        out.append(("tiger@4096/winding", flat, xf, 4096))
+        flat, xf = scenes.tiger(4096, even_odd_odd_paths=True)
+        out.append(("tiger@4096/even-odd", flat, xf, 4096))
+    if which in ("headline", "random100k"):
+        out.append(("random100k@8192", scenes.random_paths(100000, 8192, 0x5EED0004), None, 8192))
+    if which == "random1m":
+        out.append(("random1m@16384", scenes.random_paths(1000000, 16384, 0x5EED0005), None, 16384))
+    if which == "smoke":
+        flat, xf = scenes.tiger(512)
+        out.append(("tiger@512", flat, xf, 512))
+    if not out:
+        raise SystemExit(f"unknown workload {which!r}")
+    return out
+
+
+WORKLOAD_NAMES = {
+    "headline": "tiger@4096 (winding + even-odd variants) + random100k@8192",
+    "tiger4k": "tiger@4096 (winding + even-odd variants)",
+    "random100k": "random100k@8192",
+    "random1m": "random1m@16384",
+    "smoke": "tiger@512",
+}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 9:
+                self.rows.append(parts)
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for p in self.rows:
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_scene_and_options(flat, xf):
+    from oracle import pf_oracle as O
+    sc = O.make_scene(points=flat.points, point_flags=flat.point_flags, contour_offsets=flat.contour_offsets,
+                      draw_contour_ranges=flat.contour_ranges(), draw_fill_rules=flat.fill_rules,
+                      draw_paints=flat.paints, paint_colors=flat.paint_colors, view_box=flat.view_box)
+    t = None if xf is None else (xf[0], xf[2], xf[1], xf[3], xf[4], xf[5])
+    return sc, O.make_options(transform=t)
+
+
+def cpu_tiler_step(prepared, n_threads: int):
+    """One step of the reference arm: the CPU tiler (oracle port of renderer/src/tiler.rs +
+    builder.rs, D3D9 level) over every scene of the workload. Returns (seconds, segments)."""
+    from oracle import pf_oracle as O
+    secs, segs = 0.0, 0
+    for sc, opt, n_segments in prepared:
+        secs += O.time_build(sc, opt, n_threads)
+        segs += n_segments
+    return secs, segs
+
+
+def prepare_cpu(scene_list):
+    from oracle import pf_oracle as O
+    prepared = []
+    for _name, flat, xf, _size in scene_list:
+        sc, opt = oracle_scene_and_options(flat, xf)
+        b = O.Built(sc, opt, n_threads=max(1, os.cpu_count() or 1))
+        prepared.append((sc, opt, b.line_segment_count))
+        b.close()
+    return prepared
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores. The
+    reference is Rust and cannot be built in this image (no rustc/cargo), so this times the oracle
+    port with all host threads; kind = "port"."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = max(1, os.cpu_count() or 1)
+    scene_list = workload_scenes(args.workload)
+    prepared = prepare_cpu(scene_list)
+    for _ in range(args.warmup):
+        cpu_tiler_step(prepared, cores)
+    t_total, seg_total = 0.0, 0
+    for _ in range(args.steps):
+        s, n = cpu_tiler_step(prepared, cores)
+        t_total += s
+        seg_total += n
+    value = seg_total / t_total / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[args.workload],
+                   "note": "CPU tiler only (scene build: flatten + tile + propagate + pack), as cpu_build_time"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full builds of every scene of the workload"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOAD_NAMES))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "cuda":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    from pathfinder_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the hot path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    scene_list = workload_scenes(args.workload)
+
+    # One renderer per scene size; every rank owns a strip of tile rows and renders straight into
+    # its slot of the gathered frame.
+    class Frame:
+        pass
+
+    frames = []
+    for name, flat, xf, size in scene_list:
+        f = Frame()
+        f.name, f.flat, f.size = name, flat, size
+        tile_rows = (size + 15) // 16
+        assert tile_rows % world == 0, "tile rows must divide evenly across ranks"
+        rows_per = tile_rows // world
+        f.y0, f.y1 = rank * rows_per, (rank + 1) * rows_per
+        f.full = torch.empty((size, size, 4), dtype=torch.uint8, device="cuda")
+        f.renderer = api.CudaRenderer((size, size), background_color=(1.0, 1.0, 1.0, 1.0), device_ordinal=local_rank)
+        f.renderer.set_stream(stream.cuda_stream)
+        f.renderer.set_dest_device_pointer(f.full.data_ptr(), size * 4)
+        if world > 1:
+            f.renderer.set_strip(f.y0, f.y1)
+            f.strip_view = f.full[f.y0 * 16:f.y1 * 16]
+        f.scene = api.Scene.from_flat(flat)
+        f.options = api.BuildOptions(transform=None if xf is None else api.Transform2F(*xf))
+        f.host = torch.empty((size, size, 4), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+        frames.append(f)
+
+    def render_frame(f, e2e: bool):
+        if e2e:
+            f.scene.set_view_box(f.flat.view_box)  # bumps the epoch: the scene is re-uploaded from host memory
+        f.scene.build_and_render(f.renderer, f.options)
+        if dist is not None:
+            dist.all_gather_into_tensor(f.full.view(-1), f.strip_view.reshape(-1))
+        if e2e and rank == 0:
+            f.host.copy_(f.full, non_blocking=True)
+
+    def step(e2e: bool):
+        for f in frames:
+            render_frame(f, e2e)
+
+    def timed(e2e: bool, steps: int):
+        barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        start.record(stream)
+        for _ in range(steps):
+            step(e2e)
+        end.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev = start.elapsed_time(end) / 1e3
+        # e2e includes host work (scene build, copies): wall clock around the synchronised region;
+        # device-resident value: CUDA events on the launching stream.
+        t = torch.tensor([wall if e2e else dev], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+
+    # Per-frame stats after warm-up.
+    seg_per_step, launches_per_step = 0, 0
+    per_scene = {}
+    for f in frames:
+        s = f.renderer.stats()
+        seg = s["line_segment_count"]
+        if dist is not None:  # strips flatten the same segments; count each once: take rank 0's view
+            pass
+        seg_per_step += seg
+        launches_per_step += s["drawcall_count"]
+        per_scene[f.name] = s
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for f in frames:
+        f.renderer.set_timing_enabled(True)
+    stage_acc = {f.name: {} for f in frames}
+
+    # Timed region: exactly K steps, device-resident scenes.
+    barrier()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(stream)
+    for _ in range(args.steps):
+        for f in frames:
+            render_frame(f, False)
+            for k, v in f.renderer.times().items():
+                stage_acc[f.name][k] = stage_acc[f.name].get(k, 0.0) + v
+    end.record(stream)
+    barrier()
+    dev_s = start.elapsed_time(end) / 1e3
+    t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    for f in frames:
+        f.renderer.set_timing_enabled(False)
+
+    # End to end: scene upload from host memory + render + read-back of the frame, every frame.
+    e2e_steps = max(3, min(args.steps, 10))
+    step(True)
+    e2e_s = timed(True, e2e_steps)
+    h2d = sum(int(f.flat.points.nbytes + f.flat.n_contours * 8 + len(f.flat.points) * 8) for f in frames)
+    d2h = sum(f.size * f.size * 4 for f in frames)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = seg_per_step * args.steps / dev_s / 1e9
+    e2e_value = seg_per_step * e2e_steps / e2e_s / 1e9
+
+    # Roofline of the dominant kernel (fused fill + tile) on the largest scene: algorithmic bytes
+    # = 8 B per fill read + 16 B per tile-list entry + 4 B per pixel written.
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    big = max(frames, key=lambda f: f.size)
+    bs = per_scene[big.name]
+    rows = (big.y1 - big.y0) * 16
+    algo_bytes = 8 * bs["fill_count"] + 16 * bs["tile_list_entry_count"] + 4 * big.size * rows
+    kernel_ms = stage_acc[big.name]["fill_tile_ms"] / args.steps
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "k_composite (fused fill + tile)", "scene": big.name,
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms, "peak_source": peak_src}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cores = max(1, os.cpu_count() or 1)
+        prepared = prepare_cpu(scene_list)
+        cpu_tiler_step(prepared, cores)
+        reps, t_cpu, seg_cpu = 0, 0.0, 0
+        t_begin = time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t_begin < 10.0 and reps < 50):
+            s, n = cpu_tiler_step(prepared, cores)
+            t_cpu += s
+            seg_cpu += n
+            reps += 1
+        s1, n1 = cpu_tiler_step(prepared, 1)
+        cpu_baseline = {"value": seg_cpu / t_cpu / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{reps} full CPU-tiler builds of every scene of the workload (scene build only: "
+                                  "flatten + tile + propagate + pack, the reference's cpu_build_time)",
+                        "single_thread_value": n1 / s1 / 1e9}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[args.workload], "frames_per_step": len(frames),
+                   "segments_per_step": seg_per_step,
+                   "parallelism": f"tile-strip x{world}" + (" + NCCL all-gather" if world > 1 else ""),
+                   "l2": "inputs larger than L2: a step touches > 1 GB of stage buffers and frames",
+                   "ms_per_frame": {f.name: stage_acc[f.name]["total_ms"] / args.steps for f in frames},
+                   "stage_ms": {f.name: {k: v / args.steps for k, v in stage_acc[f.name].items()} for f in frames}},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
