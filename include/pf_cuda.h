@@ -168,6 +168,11 @@ typedef struct PFTileBatchDataD3D11 {      /* gpu_data.rs:121-140 */
     uint32_t path_source;
     uint32_t has_clipped_path_info;
     PFClippedPathInfo clipped_path_info;
+    /* Extension (not in the reference): 0 = unknown. A non-zero key equal to the previous batch's
+     * promises byte-identical metadata arrays, so the renderer keeps its device copy — the
+     * reference's "scene not dirty" idea (builder.rs:193-215) applied to the batch data it
+     * otherwise rebuilds and re-uploads every frame. The Rust glue may always pass 0. */
+    uint64_t content_key;
 } PFTileBatchDataD3D11;
 
 /* RenderCommand (gpu_data.rs:37-105) as a tagged union. */
@@ -192,7 +197,8 @@ typedef struct PFRenderCommand {
     uint32_t kind; /* PFRenderCommandKind */
     union {
         struct { uint64_t path_count; uint32_t needs_readable_framebuffer; } start;
-        struct { const PFTextureMetadataEntry *entries; size_t entry_count; } upload_texture_metadata;
+        struct { const PFTextureMetadataEntry *entries; size_t entry_count; uint64_t content_key; /* as
+                 PFTileBatchDataD3D11.content_key */ } upload_texture_metadata;
         struct { PFSegmentsD3D11 draw_segments, clip_segments; } upload_scene_d3d11;
         struct { PFTileBatchDataD3D11 batch; } prepare_clip_tiles_d3d11;
         struct { PFTileBatchDataD3D11 tile_batch_data; uint32_t has_color_texture; } draw_tiles_d3d11;
@@ -286,7 +292,10 @@ typedef struct PFCudaRenderStats {
     uint64_t line_segment_count;   /* flattened segments entering bin ("segments") */
     uint64_t tile_list_entry_count;/* tiles surviving the z-cull, summed over framebuffer tiles */
     uint64_t column_count;
-    uint64_t host_sync_count;      /* blocking count read-backs this frame */
+    uint64_t host_sync_count;      /* blocking read-backs this frame (1 per batch in steady state) */
+    uint64_t visible_fill_count;   /* fills of tiles that survived the z-cull (read by fill+tile) */
+    uint64_t h2d_bytes;            /* host-to-device bytes copied this frame */
+    uint64_t batch_cache_hits;     /* batches rendered from the cached device-side metadata */
 } PFCudaRenderStats;
 PFCudaStatus PFCudaRendererGetStats(PFCudaRendererRef renderer, PFCudaRenderStats *stats);
 

@@ -94,7 +94,7 @@ class PFTileBatchDataD3D11(C.Structure):
     _fields_ = [("batch_id", C.c_uint32), ("path_count", C.c_uint32), ("tile_count", C.c_uint32),
                 ("segment_count", C.c_uint32), ("prepare_info", PFPrepareTilesInfoD3D11),
                 ("path_source", C.c_uint32), ("has_clipped_path_info", C.c_uint32),
-                ("clipped_path_info", PFClippedPathInfo)]
+                ("clipped_path_info", PFClippedPathInfo), ("content_key", C.c_uint64)]
 
 
 class _Start(C.Structure):
@@ -102,7 +102,7 @@ class _Start(C.Structure):
 
 
 class _UploadTextureMetadata(C.Structure):
-    _fields_ = [("entries", C.c_void_p), ("entry_count", C.c_size_t)]
+    _fields_ = [("entries", C.c_void_p), ("entry_count", C.c_size_t), ("content_key", C.c_uint64)]
 
 
 class _UploadSceneD3D11(C.Structure):
@@ -175,7 +175,8 @@ class PFCudaRenderStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "path_count", "fill_count", "alpha_tile_count", "total_tile_count", "cpu_build_time_ns",
         "drawcall_count", "gpu_bytes_allocated", "gpu_bytes_committed", "input_segment_count",
-        "line_segment_count", "tile_list_entry_count", "column_count", "host_sync_count")]
+        "line_segment_count", "tile_list_entry_count", "column_count", "host_sync_count",
+        "visible_fill_count", "h2d_bytes", "batch_cache_hits")]
 
 
 class PFCudaRenderTime(C.Structure):

@@ -214,7 +214,8 @@ __device__ __forceinline__ bool clip_line(float2 &from, float2 &to, const ViewBo
 template <bool EMIT>
 __global__ void __launch_bounds__(128) k_bin(BatchDev b, BinArgs a) {
     uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= a.n_lines) return;
+    const uint32_t n_lines = a.n_lines_dev ? min(a.n_lines, __ldg(a.n_lines_dev)) : a.n_lines;
+    if (l >= n_lines) return;
     float4 seg = __ldg(a.lines + l);
     uint32_t p = __ldg(a.line_path + l);
     const PathInfo path = load_path(b.paths, p);
@@ -434,30 +435,42 @@ int launch_list_emit(uint32_t n_tiles, const uint32_t *tile_fb, const uint32_t *
 }
 
 __global__ void __launch_bounds__(256)
-    k_build_entries(BatchDev b, uint32_t n_entries, const uint32_t *__restrict__ keys,
-                    const uint32_t *__restrict__ vals, const uint32_t *__restrict__ tile_word,
-                    const uint32_t *__restrict__ tile_fill_pos, TileEntry *__restrict__ entries,
-                    uint32_t *__restrict__ fb_start, uint32_t *__restrict__ fb_end) {
+    k_build_entries(BatchDev b, uint32_t n_entries, const uint32_t *__restrict__ n_entries_dev,
+                    const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                    const uint32_t *__restrict__ tile_word, const uint32_t *__restrict__ tile_fill_pos,
+                    TileEntry *__restrict__ entries, uint32_t *__restrict__ fb_start, uint32_t *__restrict__ fb_end,
+                    uint32_t *__restrict__ visible_fill_count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_entries) return;
-    uint32_t fbi = __ldg(keys + i), t = __ldg(vals + i);
-    uint32_t p = search_le(b.path_tile_offset, b.n_paths, t);
-    TileEntry e;
-    e.fill_end = __ldg(tile_fill_pos + t); // the emit pass left the cursor at the end of the run
-    e.word = __ldg(tile_word + t);
-    e.paint_ctrl = __ldg(&b.paths[p].paint_ctrl) & 0x00ffffffu;
-    e.path_id = __ldg(&b.paths[p].global_path_id);
-    *reinterpret_cast<uint4 *>(entries + i) = *reinterpret_cast<uint4 *>(&e);
-    if (i == 0 || __ldg(keys + i - 1) != fbi) fb_start[fbi] = i;
-    if (i + 1 == n_entries || __ldg(keys + i + 1) != fbi) fb_end[fbi] = i + 1;
+    if (n_entries_dev) n_entries = min(n_entries, __ldg(n_entries_dev));
+    uint32_t visible = 0;
+    if (i < n_entries) {
+        uint32_t fbi = __ldg(keys + i), t = __ldg(vals + i);
+        uint32_t p = search_le(b.path_tile_offset, b.n_paths, t);
+        TileEntry e;
+        e.fill_end = __ldg(tile_fill_pos + t); // the emit pass left the cursor at the end of the run
+        e.word = __ldg(tile_word + t);
+        e.paint_ctrl = __ldg(&b.paths[p].paint_ctrl) & 0x00ffffffu;
+        e.path_id = __ldg(&b.paths[p].global_path_id);
+        *reinterpret_cast<uint4 *>(entries + i) = *reinterpret_cast<uint4 *>(&e);
+        if (i == 0 || __ldg(keys + i - 1) != fbi) fb_start[fbi] = i;
+        if (i + 1 == n_entries || __ldg(keys + i + 1) != fbi) fb_end[fbi] = i + 1;
+        visible = e.word & 0x00ffffffu;
+    }
+    // Fills the fused kernel will actually read (statistics for the roofline's algorithmic bytes).
+    if (visible_fill_count) {
+        for (int d = 16; d > 0; d >>= 1) visible += __shfl_down_sync(0xffffffffu, visible, d);
+        if ((threadIdx.x & 31) == 0 && visible) atomicAdd(visible_fill_count, visible);
+    }
 }
 
-int launch_build_entries(const BatchDev &b, uint32_t n_entries, const uint32_t *keys, const uint32_t *vals,
-                         const uint32_t *tile_word, const uint32_t *tile_fill_pos, TileEntry *entries,
-                         uint32_t *fb_start, uint32_t *fb_end, cudaStream_t stream) {
+int launch_build_entries(const BatchDev &b, uint32_t n_entries, const uint32_t *n_entries_dev, const uint32_t *keys,
+                         const uint32_t *vals, const uint32_t *tile_word, const uint32_t *tile_fill_pos,
+                         TileEntry *entries, uint32_t *fb_start, uint32_t *fb_end, uint32_t *visible_fill_count,
+                         cudaStream_t stream) {
     if (n_entries == 0) return 0;
-    k_build_entries<<<div_up(n_entries, 256), 256, 0, stream>>>(b, n_entries, keys, vals, tile_word, tile_fill_pos,
-                                                                 entries, fb_start, fb_end);
+    k_build_entries<<<div_up(n_entries, 256), 256, 0, stream>>>(b, n_entries, n_entries_dev, keys, vals, tile_word,
+                                                                 tile_fill_pos, entries, fb_start, fb_end,
+                                                                 visible_fill_count);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

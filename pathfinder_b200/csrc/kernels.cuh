@@ -76,7 +76,8 @@ int launch_dice(bool emit, const BatchDev &b, uint32_t *seg_line_count, const ui
 struct BinArgs {
     const float4 *lines;
     const uint32_t *line_path;
-    uint32_t n_lines;
+    uint32_t n_lines;            // host-side bound (grid size)
+    const uint32_t *n_lines_dev; // optional: actual count on the device, min(*n_lines_dev, n_lines) is used
     uint32_t *tile_word;      // count (24) | backdrop delta (8)
     int32_t *col_backdrop;
     // count pass
@@ -100,9 +101,10 @@ int launch_list_flags(const BatchDev &b, const uint32_t *tile_word, const int32_
                       cudaStream_t stream);
 int launch_list_emit(uint32_t n_tiles, const uint32_t *tile_fb, const uint32_t *tile_pos, uint32_t *keys,
                      uint32_t *vals, uint32_t capacity, cudaStream_t stream);
-int launch_build_entries(const BatchDev &b, uint32_t n_entries, const uint32_t *keys, const uint32_t *vals,
-                         const uint32_t *tile_word, const uint32_t *tile_fill_pos, TileEntry *entries,
-                         uint32_t *fb_start, uint32_t *fb_end, cudaStream_t stream);
+int launch_build_entries(const BatchDev &b, uint32_t n_entries, const uint32_t *n_entries_dev, const uint32_t *keys,
+                         const uint32_t *vals, const uint32_t *tile_word, const uint32_t *tile_fill_pos,
+                         TileEntry *entries, uint32_t *fb_start, uint32_t *fb_end, uint32_t *visible_fill_count,
+                         cudaStream_t stream);
 
 struct CompositeArgs {
     const TileEntry *entries;

@@ -24,8 +24,10 @@ constexpr int RS_BINS = 256;
 
 // hist[bin * n_blocks + block] = number of keys in the block's tile with that digit.
 __global__ void __launch_bounds__(RS_THREADS)
-    k_rs_histogram(const uint32_t *keys, uint32_t n, int shift, uint32_t n_blocks, uint32_t *hist) {
+    k_rs_histogram(const uint32_t *keys, uint32_t n, const uint32_t *__restrict__ n_dev, int shift,
+                   uint32_t n_blocks, uint32_t *hist) {
     __shared__ uint32_t s_hist[RS_BINS];
+    if (n_dev) n = min(n, *n_dev);
     s_hist[threadIdx.x] = 0;
     __syncthreads();
     const size_t base = (size_t)blockIdx.x * RS_TILE;
@@ -40,9 +42,11 @@ __global__ void __launch_bounds__(RS_THREADS)
 
 __global__ void __launch_bounds__(RS_THREADS)
     k_rs_scatter(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
-                 uint32_t n, int shift, uint32_t n_blocks, const uint32_t *hist_scanned) {
+                 uint32_t n, const uint32_t *__restrict__ n_dev, int shift, uint32_t n_blocks,
+                 const uint32_t *hist_scanned) {
     // Per-warp digit counts, then turned into per-warp exclusive bases.
     __shared__ uint32_t s_warp_hist[RS_WARPS][RS_BINS];
+    if (n_dev) n = min(n, *n_dev);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
     __syncthreads();
@@ -99,8 +103,9 @@ struct RadixSortScratch {
 
 // Sorts n pairs by the low `key_bits` bits of the key, stably. The result is left in
 // (keys, vals) — an odd number of passes copies back through the temporaries. Returns launches.
+// With `n_dev` the pair count is read on the device (min(*n_dev, n)); n is the host bound.
 inline int radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t n, int key_bits, RadixSortScratch &s,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const uint32_t *n_dev = nullptr) {
     if (n == 0) return 0;
     int passes = (key_bits + 7) / 8;
     if (passes < 1) passes = 1;
@@ -112,10 +117,10 @@ inline int radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t n, int key_
     int launches = 0;
     for (int p = 0; p < passes; p++) {
         int shift = 8 * p;
-        k_rs_histogram<<<n_blocks, RS_THREADS, 0, stream>>>(k_in, n, shift, n_blocks, s.hist.ptr);
+        k_rs_histogram<<<n_blocks, RS_THREADS, 0, stream>>>(k_in, n, n_dev, shift, n_blocks, s.hist.ptr);
         launches += 1;
         launches += exclusive_scan(LoadU32{s.hist.ptr}, s.hist.ptr, RS_BINS * n_blocks, nullptr, s.scan, stream);
-        k_rs_scatter<<<n_blocks, RS_THREADS, 0, stream>>>(k_in, v_in, k_out, v_out, n, shift, n_blocks, s.hist.ptr);
+        k_rs_scatter<<<n_blocks, RS_THREADS, 0, stream>>>(k_in, v_in, k_out, v_out, n, n_dev, shift, n_blocks, s.hist.ptr);
         launches += 1;
         uint32_t *t;
         t = k_in, k_in = k_out, k_out = t;

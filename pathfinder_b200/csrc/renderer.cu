@@ -49,6 +49,19 @@ struct SceneSegments {
     size_t n_points = 0, n_indices = 0;
 };
 
+// What the renderer keeps about the batch it last uploaded, so that a batch with the same
+// content_key is rendered without any host-side rebuild or upload.
+struct BatchCache {
+    bool valid = false;
+    uint64_t key = 0;
+    uint64_t scene_generation = 0, paint_generation = 0;
+    int32_t strip_y0 = 0, strip_y1 = 0;
+    BatchDev batch{};
+    bool has_initial_backdrops = false;
+    bool counts_valid = false; // n_lines / n_fills / n_entries hold the last frame's totals
+    uint32_t n_lines = 0, n_fills = 0, n_entries = 0;
+};
+
 struct StageTimer {
     cudaEvent_t ev[8];
     bool created = false;
@@ -108,7 +121,7 @@ struct PFCudaRenderer {
     DeviceBuffer<uint32_t> line_path;
     DeviceBuffer<uint32_t> line_fill_offset; // [L]
     DeviceBuffer<uint32_t> tile_word, tile_fill_pos, tile_first_fill, tile_fb, tile_pos, tile_alpha_id;
-    DeviceBuffer<int32_t> col_backdrop;
+    DeviceBuffer<int32_t> col_backdrop, col_backdrop_init;
     DeviceBuffer<PackedFill> fills;
     DeviceBuffer<EmitFill> fills_emit;
     DeviceBuffer<int32_t> z_buffer;
@@ -123,6 +136,11 @@ struct PFCudaRenderer {
     DeviceBuffer<uint8_t> fill_is_first;
     DeviceBuffer<uint32_t> fill_first_scan;
     DeviceBuffer<uint8_t> dump_out;
+
+    BatchCache cache;
+    uint64_t scene_generation = 0, paint_generation = 0;
+    uint64_t paint_key = 0;
+    bool always_size = false; // debugging aid: read every count back (three syncs per batch)
 
     // State of the last batch (for dumps and stats).
     BatchDev last_batch{};
@@ -174,6 +192,7 @@ void setup_tracking(PFCudaRenderer *r) {
     track(r, r->tile_pos);
     track(r, r->tile_alpha_id);
     track(r, r->col_backdrop);
+    track(r, r->col_backdrop_init);
     track(r, r->fills);
     track(r, r->fills_emit);
     track(r, r->z_buffer);
@@ -244,6 +263,7 @@ void upload_segments(PFCudaRenderer *r, SceneSegments &dst, const PFSegmentsD3D1
                                       cudaMemcpyHostToDevice, r->stream));
     // The payload is borrowed for this call only and may be pageable: wait for the copies.
     PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    r->stats.h2d_bytes += src.point_count * sizeof(float2) + src.index_count * sizeof(uint2);
 }
 
 void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *entries, size_t n) {
@@ -266,36 +286,17 @@ void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *en
         PF_CUDA_CHECK(cudaMemcpyAsync(r->paints.ptr, table.data(), n * sizeof(float4), cudaMemcpyHostToDevice,
                                       r->stream));
         PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        r->stats.h2d_bytes += n * sizeof(float4);
     }
 }
 
-struct EventPair {
-    cudaEvent_t a, b;
-};
-
-// One DrawTilesD3D11 batch: prepare_tiles + draw_tiles (d3d11/renderer.rs:414-424).
-void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
-    if (!r->has_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "DrawTilesD3D11 before UploadSceneD3D11");
-    if (batch.path_source != PF_PATH_SOURCE_DRAW)
-        throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "draw batch with a clip path source");
-    if (batch.has_clipped_path_info && batch.clipped_path_info.clipped_path_count > 0)
-        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "clip paths are a 'next' row (SURVEY.md §8 f1)");
+// Builds the per-path device records of a batch (host part of "bound") and uploads them. Replaces
+// the offsets TileBatchDataD3D11::push assigns (renderer/src/builder.rs:663-720) + bound.cs.glsl.
+void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch, const FbRect &fb,
+                           int32_t strip_y0, int32_t strip_y1, BatchDev &b, bool &has_initial_backdrops) {
     cudaStream_t st = r->stream;
     const uint32_t P = batch.path_count;
     const PFPrepareTilesInfoD3D11 &info = batch.prepare_info;
-    const SceneSegments &segs = r->draw_segments;
-    const FbRect fb = framebuffer_tile_rect(r);
-    const int32_t strip_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
-    const int32_t strip_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
-    int launches = 0;
-
-    if (r->timing) {
-        r->timer.create();
-        PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[0], st));
-    }
-
-    // ---- bound (host part): per-path records with strip-restricted rects and dense offsets.
-    // Replaces TileBatchDataD3D11 offsets (renderer/src/builder.rs:663-720) + bound.cs.glsl.
     const size_t meta_bytes = (size_t)P * sizeof(PathInfo) + 3 * (size_t)(P + 1) * sizeof(uint32_t);
     if (r->meta_copied) PF_CUDA_CHECK(cudaEventSynchronize(r->meta_copied));
     r->batch_meta_host.ensure(meta_bytes + 64);
@@ -305,7 +306,9 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     uint32_t *h_tile_off = h_seg_first + (P + 1);
     uint32_t *h_col_off = h_tile_off + (P + 1);
     uint64_t n_tiles64 = 0, n_cols64 = 0;
-    uint32_t n_segments = batch.segment_count;
+    const uint32_t n_segments = batch.segment_count;
+    const uint32_t n_paints = (uint32_t)r->n_paints;
+    bool bad_paint = false;
     for (uint32_t i = 0; i < P; i++) {
         const PFPropagateMetadataD3D11 &pm = info.propagate_metadata[i];
         const PFDiceMetadataD3D11 &dm = info.dice_metadata[i];
@@ -335,9 +338,9 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
         h_col_off[i] = pi.col_offset;
         n_tiles64 += (uint64_t)(pi.max_x - pi.min_x) * (uint64_t)(pi.max_y - pi.min_y);
         n_cols64 += (uint64_t)(pi.max_x - pi.min_x);
-        if (tp.color >= r->n_paints)
-            throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "paint id outside the uploaded texture metadata");
+        bad_paint |= tp.color >= n_paints;
     }
+    if (bad_paint) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "paint id outside the uploaded texture metadata");
     if (n_tiles64 >= 0xfffffff0ull) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "more than 2^32 bbox tiles in one batch");
     const uint32_t n_tiles = (uint32_t)n_tiles64, n_cols = (uint32_t)n_cols64;
     h_seg_first[P] = n_segments;
@@ -350,10 +353,11 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
         if (!r->meta_copied) PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->meta_copied, cudaEventDisableTiming));
         PF_CUDA_CHECK(cudaEventRecord(r->meta_copied, st));
     }
+    r->stats.h2d_bytes += meta_bytes;
 
-    BatchDev b{};
-    b.points = segs.points.ptr;
-    b.seg_indices = segs.indices.ptr;
+    b = BatchDev{};
+    b.points = r->draw_segments.points.ptr;
+    b.seg_indices = r->draw_segments.indices.ptr;
     b.paths = reinterpret_cast<const PathInfo *>(r->batch_meta.ptr);
     b.path_seg_first = reinterpret_cast<const uint32_t *>(r->batch_meta.ptr + (size_t)P * sizeof(PathInfo));
     b.path_tile_offset = b.path_seg_first + (P + 1);
@@ -367,38 +371,68 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     b.xf.tx = t.vector.x, b.xf.ty = t.vector.y;
     b.xf.identity = (b.xf.m11 == 1.0f && b.xf.m12 == 0.0f && b.xf.m21 == 0.0f && b.xf.m22 == 1.0f &&
                      b.xf.tx == 0.0f && b.xf.ty == 0.0f);
-    // process_line_segment clips to scene.view_box() (tiler.rs:194): the framebuffer rect.
+    // process_line_segment clips to scene.view_box() (tiler.rs:194): by default the framebuffer rect.
     b.view_box = r->has_view_box
                      ? r->view_box
                      : ViewBox{0.0f, 0.0f, (float)r->options.dest_size.x, (float)r->options.dest_size.y};
     b.fb = fb;
 
-    r->counters.ensure(16);
-
-    // ---- bound (device part): clear the dense tile arrays. bound.cs.glsl:80-83 initialises
-    // {next=-1, first_fill=-1, backdrop=0}; here a tile is one word (count | backdrop delta).
-    r->tile_word.ensure(n_tiles + 1, 1.25);
-    r->tile_fill_pos.ensure(n_tiles + 1, 1.25);
-    r->col_backdrop.ensure(n_cols + 1, 1.25);
-    PF_CUDA_CHECK(cudaMemsetAsync(r->tile_word.ptr, 0, (size_t)n_tiles * 4, st));
-    PF_CUDA_CHECK(cudaMemsetAsync(r->col_backdrop.ptr, 0, (size_t)n_cols * 4, st));
+    // TransformCPUBinGPU-style non-zero initial backdrops (builder.rs:679-688).
+    has_initial_backdrops = false;
+    r->col_backdrop_init.ensure(n_cols + 1, 1.25);
     if (info.backdrops && info.backdrop_count) {
-        // TransformCPUBinGPU-style non-zero initial backdrops (builder.rs:679-688).
         std::vector<int32_t> init(n_cols, 0);
-        bool any = false;
         for (size_t i = 0; i < info.backdrop_count; i++) {
             const PFBackdropInfoD3D11 &bi = info.backdrops[i];
             if (bi.initial_backdrop == 0 || bi.path_index >= P) continue;
             const PathInfo &pi = h_paths[bi.path_index];
             if (bi.tile_x_offset < 0 || bi.tile_x_offset >= pi.max_x - pi.min_x) continue;
             init[pi.col_offset + (uint32_t)bi.tile_x_offset] = bi.initial_backdrop;
-            any = true;
+            has_initial_backdrops = true;
         }
-        if (any) {
-            PF_CUDA_CHECK(cudaMemcpyAsync(r->col_backdrop.ptr, init.data(), (size_t)n_cols * 4, cudaMemcpyHostToDevice, st));
+        if (has_initial_backdrops) {
+            PF_CUDA_CHECK(cudaMemcpyAsync(r->col_backdrop_init.ptr, init.data(), (size_t)n_cols * 4,
+                                          cudaMemcpyHostToDevice, st));
             PF_CUDA_CHECK(cudaStreamSynchronize(st));
         }
     }
+}
+
+// Runs bound(device) -> dice -> bin -> propagate -> sort -> fill+tile for the cached batch.
+// `sizing`: data-dependent counts (lines, fills, list entries) are read back as they become known
+// and buffers grown to fit — three host syncs, like the reference's three read-backs
+// (d3d11/renderer.rs:218-229,338-353,634-648). Otherwise the counts stay on the device, grids are
+// sized from the previous frame's counts plus slack, and the only sync is the verification at the end.
+// Returns false when a bound was exceeded (the caller re-runs in sizing mode).
+bool run_pipeline(PFCudaRenderer *r, bool sizing) {
+    cudaStream_t st = r->stream;
+    BatchCache &c = r->cache;
+    const BatchDev &b = c.batch;
+    const FbRect fb = b.fb;
+    const uint32_t n_segments = b.n_segments, n_tiles = b.n_tiles, n_cols = b.n_columns;
+    int launches = 0;
+    enum { C_LINES = 0, C_FILLS = 1, C_ENTRIES = 2, C_VISIBLE_FILLS = 5 };
+
+    if (r->timing) {
+        r->timer.create();
+        PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[0], st));
+    }
+    r->counters.ensure(16);
+    PF_CUDA_CHECK(cudaMemsetAsync(r->counters.ptr, 0, 16 * sizeof(uint32_t), st));
+
+    // ---- bound (device part): clear the dense tile arrays. bound.cs.glsl:80-83 initialises
+    // {next=-1, first_fill=-1, backdrop=0}; here a tile is one word (count | backdrop delta).
+    r->tile_word.ensure(n_tiles + 1, 1.25);
+    r->tile_fill_pos.ensure(n_tiles + 1, 1.25);
+    r->col_backdrop.ensure(n_cols + 1, 1.25);
+    r->tile_fb.ensure(n_tiles + 1, 1.25);
+    r->tile_pos.ensure(n_tiles + 1, 1.25);
+    PF_CUDA_CHECK(cudaMemsetAsync(r->tile_word.ptr, 0, (size_t)n_tiles * 4, st));
+    if (c.has_initial_backdrops)
+        PF_CUDA_CHECK(cudaMemcpyAsync(r->col_backdrop.ptr, r->col_backdrop_init.ptr, (size_t)n_cols * 4,
+                                      cudaMemcpyDeviceToDevice, st));
+    else
+        PF_CUDA_CHECK(cudaMemsetAsync(r->col_backdrop.ptr, 0, (size_t)n_cols * 4, st));
     if (r->debug_lists) {
         r->tile_first_fill.ensure(n_tiles + 1, 1.25);
         PF_CUDA_CHECK(cudaMemsetAsync(r->tile_first_fill.ptr, 0xff, (size_t)n_tiles * 4, st));
@@ -413,38 +447,57 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     PF_CUDA_CHECK(cudaMemsetAsync(r->fb_end.ptr, 0, (size_t)n_fb * 4, st));
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[1], st));
 
+    auto bound_of = [](uint32_t last, size_t capacity) -> uint32_t {
+        uint64_t want = (uint64_t)last + last / 8 + 4096;
+        return (uint32_t)(want < capacity ? want : capacity);
+    };
+
     // ---- dice: count -> scan -> emit.
     r->seg_line_offset.ensure(n_segments + 1, 1.25);
     launches += launch_dice(false, b, r->seg_line_offset.ptr, nullptr, nullptr, nullptr, 0, st);
     launches += exclusive_scan(LoadU32{r->seg_line_offset.ptr}, r->seg_line_offset.ptr, n_segments,
-                               r->counters.ptr + 0, r->scan_scratch, st);
-    const uint32_t n_lines = n_segments ? read_counter(r, 0) : 0;
-    r->lines.ensure(n_lines + 1, 1.25);
-    r->line_path.ensure(n_lines + 1, 1.25);
-    launches += launch_dice(true, b, nullptr, r->seg_line_offset.ptr, r->lines.ptr, r->line_path.ptr, n_lines, st);
+                               r->counters.ptr + C_LINES, r->scan_scratch, st);
+    uint32_t line_bound;
+    if (sizing) {
+        line_bound = n_segments ? read_counter(r, C_LINES) : 0;
+        r->lines.ensure(line_bound + 1, 1.25);
+        r->line_path.ensure(line_bound + 1, 1.25);
+        r->line_fill_offset.ensure(line_bound + 1, 1.25);
+    } else {
+        line_bound = bound_of(c.n_lines, std::min(r->lines.capacity, std::min(r->line_path.capacity, r->line_fill_offset.capacity)));
+    }
+    const uint32_t *n_lines_dev = r->counters.ptr + C_LINES;
+    launches += launch_dice(true, b, nullptr, r->seg_line_offset.ptr, r->lines.ptr, r->line_path.ptr, line_bound, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[2], st));
 
     // ---- bin: count (+ backdrop deltas) -> scans -> emit into tile-grouped runs.
-    r->line_fill_offset.ensure(n_lines + 1, 1.25);
     BinArgs ba{};
     ba.lines = r->lines.ptr;
     ba.line_path = r->line_path.ptr;
-    ba.n_lines = n_lines;
+    ba.n_lines = line_bound;
+    ba.n_lines_dev = n_lines_dev;
     ba.tile_word = r->tile_word.ptr;
     ba.col_backdrop = r->col_backdrop.ptr;
     ba.line_fill_count = r->line_fill_offset.ptr;
     launches += launch_bin(false, b, ba, st);
-    launches += exclusive_scan(LoadU32{r->line_fill_offset.ptr}, r->line_fill_offset.ptr, n_lines,
-                               r->counters.ptr + 1, r->scan_scratch, st);
+    launches += exclusive_scan(LoadU32{r->line_fill_offset.ptr}, r->line_fill_offset.ptr, line_bound,
+                               r->counters.ptr + C_FILLS, r->scan_scratch, st, n_lines_dev);
     launches += exclusive_scan(LoadLow24{r->tile_word.ptr}, r->tile_fill_pos.ptr, n_tiles, nullptr,
                                r->scan_scratch, st);
-    const uint32_t n_fills = n_lines ? read_counter(r, 1) : 0;
-    r->fills.ensure(n_fills + 1, 1.25);
-    if (r->debug_lists) r->fills_emit.ensure(n_fills + 1, 1.25);
+    uint32_t fill_bound;
+    if (sizing) {
+        fill_bound = line_bound ? read_counter(r, C_FILLS) : 0;
+        r->fills.ensure(fill_bound + 1, 1.25);
+        if (r->debug_lists) r->fills_emit.ensure(fill_bound + 1, 1.25);
+    } else {
+        size_t cap = r->fills.capacity;
+        if (r->debug_lists) cap = std::min(cap, r->fills_emit.capacity);
+        fill_bound = bound_of(c.n_fills, cap);
+    }
     ba.line_fill_offset = r->line_fill_offset.ptr;
     ba.tile_fill_pos = r->tile_fill_pos.ptr;
     ba.fills = r->fills.ptr;
-    ba.fill_capacity = n_fills;
+    ba.fill_capacity = fill_bound;
     ba.tile_first_fill = r->debug_lists ? r->tile_first_fill.ptr : nullptr;
     ba.fills_emit = r->debug_lists ? r->fills_emit.ptr : nullptr;
     launches += launch_bin(true, b, ba, st);
@@ -455,22 +508,33 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[4], st));
 
     // ---- sort: z-cull, compact surviving tiles, stable radix sort by framebuffer tile.
-    r->tile_fb.ensure(n_tiles + 1, 1.25);
-    r->tile_pos.ensure(n_tiles + 1, 1.25);
     launches += launch_list_flags(b, r->tile_word.ptr, r->z_buffer.ptr, r->tile_fb.ptr, st);
-    launches += exclusive_scan(LoadNotInvalid{r->tile_fb.ptr}, r->tile_pos.ptr, n_tiles, r->counters.ptr + 2,
+    launches += exclusive_scan(LoadNotInvalid{r->tile_fb.ptr}, r->tile_pos.ptr, n_tiles, r->counters.ptr + C_ENTRIES,
                                r->scan_scratch, st);
-    const uint32_t n_entries = n_tiles ? read_counter(r, 2) : 0;
-    r->list_keys.ensure(n_entries + 1, 1.25);
-    r->list_vals.ensure(n_entries + 1, 1.25);
-    r->entries.ensure(n_entries + 1, 1.25);
+    uint32_t entry_bound;
+    if (sizing) {
+        entry_bound = n_tiles ? read_counter(r, C_ENTRIES) : 0;
+        r->list_keys.ensure(entry_bound + 1, 1.25);
+        r->list_vals.ensure(entry_bound + 1, 1.25);
+        r->entries.ensure(entry_bound + 1, 1.25);
+        r->sort_scratch.keys_tmp.ensure(entry_bound + 1, 1.25);
+        r->sort_scratch.vals_tmp.ensure(entry_bound + 1, 1.25);
+    } else {
+        size_t cap = std::min(std::min(r->list_keys.capacity, r->list_vals.capacity),
+                              std::min(r->entries.capacity, std::min(r->sort_scratch.keys_tmp.capacity,
+                                                                     r->sort_scratch.vals_tmp.capacity)));
+        entry_bound = bound_of(c.n_entries, cap);
+    }
+    const uint32_t *n_entries_dev = r->counters.ptr + C_ENTRIES;
     launches += launch_list_emit(n_tiles, r->tile_fb.ptr, r->tile_pos.ptr, r->list_keys.ptr, r->list_vals.ptr,
-                                 n_entries, st);
+                                 entry_bound, st);
     int key_bits = 1;
     while ((1u << key_bits) < n_fb && key_bits < 32) key_bits++;
-    launches += radix_sort_pairs(r->list_keys.ptr, r->list_vals.ptr, n_entries, key_bits, r->sort_scratch, st);
-    launches += launch_build_entries(b, n_entries, r->list_keys.ptr, r->list_vals.ptr, r->tile_word.ptr,
-                                     r->tile_fill_pos.ptr, r->entries.ptr, r->fb_start.ptr, r->fb_end.ptr, st);
+    launches += radix_sort_pairs(r->list_keys.ptr, r->list_vals.ptr, entry_bound, key_bits, r->sort_scratch, st,
+                                 n_entries_dev);
+    launches += launch_build_entries(b, entry_bound, n_entries_dev, r->list_keys.ptr, r->list_vals.ptr,
+                                     r->tile_word.ptr, r->tile_fill_pos.ptr, r->entries.ptr, r->fb_start.ptr,
+                                     r->fb_end.ptr, r->counters.ptr + C_VISIBLE_FILLS, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[5], st));
 
     // ---- fill + tile (fused).
@@ -482,8 +546,8 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     ca.paints = r->paints.ptr;
     ca.area_lut = r->lut_tex;
     ca.fb = fb;
-    ca.tile_y0 = strip_y0;
-    ca.tile_y1 = strip_y1;
+    ca.tile_y0 = c.strip_y0;
+    ca.tile_y1 = c.strip_y1;
     ca.dest = r->dest;
     ca.dest_pitch = r->dest_pitch;
     ca.dest_w = r->options.dest_size.x;
@@ -493,24 +557,39 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     launches += launch_composite(ca, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[6], st));
 
-    r->batches_drawn++;
+    // ---- verification: one read-back of the totals at the end of the batch.
+    r->counters_host.ensure(16);
+    PF_CUDA_CHECK(cudaMemcpyAsync(r->counters_host.ptr, r->counters.ptr, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PF_CUDA_CHECK(cudaStreamSynchronize(st));
+    r->stats.host_sync_count++;
+    const uint32_t n_lines = r->counters_host.ptr[C_LINES], n_fills = r->counters_host.ptr[C_FILLS],
+                   n_entries = r->counters_host.ptr[C_ENTRIES];
+    r->stats.drawcall_count += (uint64_t)launches;
+    c.n_lines = n_lines;
+    c.n_fills = n_fills;
+    c.n_entries = n_entries;
+    if (n_lines > line_bound || n_fills > fill_bound || n_entries > entry_bound) {
+        c.counts_valid = false;
+        return false;
+    }
+    c.counts_valid = true;
+
     r->last_batch = b;
     r->last_lines = n_lines;
     r->last_fills = n_fills;
     r->last_entries = n_entries;
     r->last_alpha_ids_valid = false;
     r->last_fb = fb;
-    r->stats.path_count += P;
+    r->stats.path_count += b.n_paths;
     r->stats.fill_count += n_fills;
     r->stats.total_tile_count += n_tiles;
     r->stats.input_segment_count += n_segments;
     r->stats.line_segment_count += n_lines;
     r->stats.tile_list_entry_count += n_entries;
+    r->stats.visible_fill_count += r->counters_host.ptr[C_VISIBLE_FILLS];
     r->stats.column_count += n_cols;
-    r->stats.drawcall_count += (uint64_t)launches;
 
     if (r->timing) {
-        PF_CUDA_CHECK(cudaEventSynchronize(r->timer.ev[6]));
         float ms[6];
         for (int i = 0; i < 6; i++) PF_CUDA_CHECK(cudaEventElapsedTime(&ms[i], r->timer.ev[i], r->timer.ev[i + 1]));
         r->times.bound_ms += ms[0];
@@ -523,6 +602,51 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
         PF_CUDA_CHECK(cudaEventElapsedTime(&total, r->timer.ev[0], r->timer.ev[6]));
         r->times.total_ms += total;
     }
+    return true;
+}
+
+// One DrawTilesD3D11 batch: prepare_tiles + draw_tiles (d3d11/renderer.rs:414-424).
+void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
+    if (!r->has_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "DrawTilesD3D11 before UploadSceneD3D11");
+    if (batch.path_source != PF_PATH_SOURCE_DRAW)
+        throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "draw batch with a clip path source");
+    if (batch.has_clipped_path_info && batch.clipped_path_info.clipped_path_count > 0)
+        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "clip paths are a 'next' row (SURVEY.md §8 f1)");
+    const FbRect fb = framebuffer_tile_rect(r);
+    const int32_t strip_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
+    const int32_t strip_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
+    const ViewBox vb = r->has_view_box
+                           ? r->view_box
+                           : ViewBox{0.0f, 0.0f, (float)r->options.dest_size.x, (float)r->options.dest_size.y};
+
+    // Batch cache: a non-zero content_key promises that the metadata arrays are identical to the
+    // previous batch with the same key (the "scene not dirty" case extended to the per-frame batch
+    // data, which the reference rebuilds and re-uploads every frame, builder.rs:653-759).
+    BatchCache &c = r->cache;
+    const bool hit = c.valid && batch.content_key != 0 && batch.content_key == c.key &&
+                     c.scene_generation == r->scene_generation && c.paint_generation == r->paint_generation &&
+                     c.strip_y0 == strip_y0 && c.strip_y1 == strip_y1 &&
+                     memcmp(&c.batch.fb, &fb, sizeof(fb)) == 0 && memcmp(&c.batch.view_box, &vb, sizeof(vb)) == 0 &&
+                     c.batch.n_paths == batch.path_count && c.batch.n_segments == batch.segment_count;
+    if (!hit) {
+        c.valid = false;
+        upload_batch_metadata(r, batch, fb, strip_y0, strip_y1, c.batch, c.has_initial_backdrops);
+        c.key = batch.content_key;
+        c.scene_generation = r->scene_generation;
+        c.paint_generation = r->paint_generation;
+        c.strip_y0 = strip_y0;
+        c.strip_y1 = strip_y1;
+        c.counts_valid = false;
+        c.valid = true;
+    } else {
+        r->stats.batch_cache_hits++;
+    }
+    bool ok = run_pipeline(r, !c.counts_valid || r->always_size);
+    if (!ok) {
+        ok = run_pipeline(r, true);
+        if (!ok) throw Error(PF_CUDA_ERROR_CUDA, "stage buffer overflow after exact sizing (internal error)");
+    }
+    r->batches_drawn++;
 }
 
 // Alpha tile ids in SequentialExecutor order for the last batch (needs debug lists).
@@ -672,13 +796,20 @@ PFCudaStatus PFCudaRendererRenderCommand(PFCudaRendererRef r, const PFRenderComm
         case PF_RENDER_COMMAND_START:
             break;
         case PF_RENDER_COMMAND_UPLOAD_TEXTURE_METADATA:
-            upload_texture_metadata(r, cmd->u.upload_texture_metadata.entries,
-                                    cmd->u.upload_texture_metadata.entry_count);
+            // A non-zero content_key equal to the last upload's means "same table": skip it.
+            if (cmd->u.upload_texture_metadata.content_key == 0 ||
+                cmd->u.upload_texture_metadata.content_key != r->paint_key) {
+                upload_texture_metadata(r, cmd->u.upload_texture_metadata.entries,
+                                        cmd->u.upload_texture_metadata.entry_count);
+                r->paint_key = cmd->u.upload_texture_metadata.content_key;
+                r->paint_generation++;
+            }
             break;
         case PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11:
             upload_segments(r, r->draw_segments, cmd->u.upload_scene_d3d11.draw_segments);
             upload_segments(r, r->clip_segments, cmd->u.upload_scene_d3d11.clip_segments);
             r->has_scene = true;
+            r->scene_generation++;
             break;
         case PF_RENDER_COMMAND_PREPARE_CLIP_TILES_D3D11:
             if (cmd->u.prepare_clip_tiles_d3d11.batch.path_count > 0)

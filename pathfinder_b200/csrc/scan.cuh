@@ -47,9 +47,13 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
     return res;
 }
 
+// `n_dev` (optional): the element count lives in device memory (a previous stage's total); `n` is
+// then the host-side bound the grid was sized with, and the kernels use min(*n_dev, n).
 template <typename InFn>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(InFn in, uint32_t n, uint32_t *block_sums) {
+__global__ void __launch_bounds__(SCAN_THREADS)
+    k_scan_reduce(InFn in, uint32_t n, const uint32_t *__restrict__ n_dev, uint32_t *block_sums) {
     __shared__ uint32_t smem[SCAN_THREADS / 32 + 1];
+    if (n_dev) n = min(n, *n_dev);
     const size_t base = (size_t)blockIdx.x * SCAN_TILE;
     uint32_t sum = 0;
 #pragma unroll
@@ -96,8 +100,10 @@ __global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t *block_sums, 
 
 template <typename InFn>
 __global__ void __launch_bounds__(SCAN_THREADS)
-    k_scan_final(InFn in, uint32_t n, const uint32_t *block_offsets, uint32_t *out) {
+    k_scan_final(InFn in, uint32_t n, const uint32_t *__restrict__ n_dev, const uint32_t *block_offsets,
+                 uint32_t *out) {
     __shared__ uint32_t smem[SCAN_THREADS / 32 + 1];
+    if (n_dev) n = min(n, *n_dev);
     const size_t base = (size_t)blockIdx.x * SCAN_TILE;
     uint32_t carry = block_offsets[blockIdx.x];
 #pragma unroll
@@ -130,16 +136,16 @@ struct ScanScratch {
 // written by the same thread). Returns the number of kernels launched.
 template <typename InFn>
 inline int exclusive_scan(InFn in, uint32_t *out, uint32_t n, uint32_t *total_out, ScanScratch &scratch,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const uint32_t *n_dev = nullptr) {
     if (n == 0) {
         if (total_out) PF_CUDA_CHECK(cudaMemsetAsync(total_out, 0, sizeof(uint32_t), stream));
         return 0;
     }
     unsigned n_blocks = div_up(n, SCAN_TILE);
     scratch.block_sums.ensure(n_blocks, 1.5);
-    k_scan_reduce<<<n_blocks, SCAN_THREADS, 0, stream>>>(in, n, scratch.block_sums.ptr);
+    k_scan_reduce<<<n_blocks, SCAN_THREADS, 0, stream>>>(in, n, n_dev, scratch.block_sums.ptr);
     k_scan_block_sums<<<1, 1024, 0, stream>>>(scratch.block_sums.ptr, n_blocks, total_out);
-    k_scan_final<<<n_blocks, SCAN_THREADS, 0, stream>>>(in, n, scratch.block_sums.ptr, out);
+    k_scan_final<<<n_blocks, SCAN_THREADS, 0, stream>>>(in, n, n_dev, scratch.block_sums.ptr, out);
     PF_CUDA_CHECK(cudaGetLastError());
     return 3;
 }

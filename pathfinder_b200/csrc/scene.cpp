@@ -96,6 +96,10 @@ struct PFScene {
     std::vector<PFDiceMetadataD3D11> dice_metadata;
     std::vector<PFTilePathInfoD3D11> tile_path_info;
     std::vector<PFTextureMetadataEntry> texture_metadata;
+    // Key of the build whose batch arrays are still in the vectors above (0 = none).
+    uint64_t built_key = 0;
+    uint64_t built_paint_key = 0;
+    uint32_t built_tile_count = 0, built_segment_count = 0;
 
     PFScene() : id(g_next_scene_id.fetch_add(1)) {}
 };
@@ -173,6 +177,14 @@ bool rect_intersection(RectF a, RectF b, RectF &out) {
     out = RectF{sse_max(a.min_x, b.min_x), sse_max(a.min_y, b.min_y), sse_min(a.max_x, b.max_x),
                 sse_min(a.max_y, b.max_y)};
     return true;
+}
+
+// splitmix64-style mixing for content keys.
+uint64_t mix_key(uint64_t h, uint64_t v) {
+    uint64_t z = h ^ (v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
 }
 
 PFRenderCommand make_command(uint32_t kind) {
@@ -324,16 +336,22 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
     SEND(start);
 
     // Paint data (builder.rs:174-180): one TextureMetadataEntry per paint (paint.rs:641-659).
-    s->texture_metadata.resize(s->paints.size());
-    for (size_t i = 0; i < s->paints.size(); i++) {
-        PFTextureMetadataEntry &e = s->texture_metadata[i];
-        memset(&e, 0, sizeof(e));
-        e.color_0_transform.matrix = PFMatrix2x2F{1, 0, 0, 1};
-        e.base_color = s->paints[i];
+    // Paints are append-only, so (scene id, paint count) identifies the table.
+    const uint64_t paint_key = mix_key(mix_key(0x9a1f7u, s->id), s->paints.size());
+    if (s->built_paint_key != paint_key) {
+        s->texture_metadata.resize(s->paints.size());
+        for (size_t i = 0; i < s->paints.size(); i++) {
+            PFTextureMetadataEntry &e = s->texture_metadata[i];
+            memset(&e, 0, sizeof(e));
+            e.color_0_transform.matrix = PFMatrix2x2F{1, 0, 0, 1};
+            e.base_color = s->paints[i];
+        }
+        s->built_paint_key = paint_key;
     }
     PFRenderCommand meta = make_command(PF_RENDER_COMMAND_UPLOAD_TEXTURE_METADATA);
     meta.u.upload_texture_metadata.entries = s->texture_metadata.data();
     meta.u.upload_texture_metadata.entry_count = s->texture_metadata.size();
+    meta.u.upload_texture_metadata.content_key = paint_key;
     SEND(meta);
 
     // Scene upload when dirty (builder.rs:190-216).
@@ -365,11 +383,26 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
     // break a batch (fixup_batch_for_new_path_if_possible, :1227-1243), so one DrawTilesD3D11.
     const Transform &xf = opts->transform; // PrepareMode::GPU { transform } (options.rs:165-180)
     const RectF effective_view_box = s->view_box; // subpixel AA refused above (scene.rs:276-282)
-    s->propagate_metadata.clear();
-    s->dice_metadata.clear();
-    s->tile_path_info.clear();
-    uint32_t tile_count = 0, segment_count = 0, column_count = 0;
-    for (uint32_t i = 0; i < s->draw_paths.size(); i++) {
+    // The batch arrays depend only on (scene, epoch, transform, view box): keep them across frames
+    // and tell the renderer through content_key that nothing changed.
+    uint64_t batch_key = mix_key(mix_key(0xb47c4u, s->id), s->epoch);
+    {
+        uint32_t bits[10];
+        const float f[10] = {xf.m11, xf.m21, xf.m12, xf.m22, xf.tx, xf.ty, effective_view_box.min_x,
+                             effective_view_box.min_y, effective_view_box.max_x, effective_view_box.max_y};
+        memcpy(bits, f, sizeof(bits));
+        for (uint32_t v : bits) batch_key = mix_key(batch_key, v);
+        if (batch_key == 0) batch_key = 1;
+    }
+    uint32_t tile_count = s->built_tile_count, segment_count = s->built_segment_count, column_count = 0;
+    const bool rebuild = s->built_key != batch_key;
+    if (rebuild) {
+        tile_count = segment_count = 0;
+        s->propagate_metadata.clear();
+        s->dice_metadata.clear();
+        s->tile_path_info.clear();
+    }
+    for (uint32_t i = 0; rebuild && i < s->draw_paths.size(); i++) {
         const Path &p = s->draw_paths[i];
         if (p.clip_path != PF_CLIP_PATH_NONE) {
             pf::set_last_error("clip paths are a 'next' row (SURVEY.md §8 f1)");
@@ -422,6 +455,9 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         column_count += w;
         segment_count += range[1] - range[0];
     }
+    s->built_key = batch_key;
+    s->built_tile_count = tile_count;
+    s->built_segment_count = segment_count;
     if (!s->propagate_metadata.empty()) {
         PFRenderCommand draw = make_command(PF_RENDER_COMMAND_DRAW_TILES_D3D11);
         PFTileBatchDataD3D11 &b = draw.u.draw_tiles_d3d11.tile_batch_data;
@@ -438,6 +474,7 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         b.prepare_info.transform.vector = PFVector2F{xf.tx, xf.ty};
         b.path_source = PF_PATH_SOURCE_DRAW;
         b.has_clipped_path_info = 0;
+        b.content_key = batch_key;
         draw.u.draw_tiles_d3d11.has_color_texture = 0;
         SEND(draw);
     }
