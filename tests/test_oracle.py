@@ -1,0 +1,197 @@
+"""CPU oracle (oracle/pf_oracle.cpp) checks. The reference holds no golden vectors for this path
+(parity unpinned), so the oracle is pinned by (i) the reference's simd known answers
+(simd/src/test.rs:54-60,380-383: floor / ceil / round-to-nearest-even conversions) observed through
+the tiler, (ii) geometric properties, and (iii) committed golden lists that fix its output."""
+import os
+
+import numpy as np
+import pytest
+
+from pathfinder_b200 import scenes
+from pathfinder_b200.flat_scene import SceneBuilderPy
+from tests import helpers as H
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+INVALID = 0xFFFFFFFF
+
+
+def polygon_scene(points, size=64, rgba=(255, 255, 255, 255), fill_rule=0):
+    b = SceneBuilderPy((0, 0, size, size))
+    b.move_to(*points[0])
+    for p in points[1:]:
+        b.line_to(*p)
+    b.close()
+    b.end_path(rgba, fill_rule)
+    return b.finish("poly")
+
+
+def shoelace(points):
+    a = 0.0
+    for (x0, y0), (x1, y1) in zip(points, points[1:] + points[:1]):
+        a += x0 * y1 - x1 * y0
+    return abs(a) / 2.0
+
+
+def test_golden_lists_are_stable():
+    flat, xf = scenes.tiger(256)
+    b = H.oracle_build(flat, xf)
+    H.assert_records_equal(b.fills, np.load(os.path.join(GOLDEN, "tiger256_fills.npy")), "fills")
+    H.assert_records_equal(b.tiles, np.load(os.path.join(GOLDEN, "tiger256_tiles.npy")), "tiles")
+    assert np.array_equal(b.z_buffer, np.load(os.path.join(GOLDEN, "tiger256_zbuffer.npy")))
+
+
+def test_fill_quantisation_rounds_half_to_even():
+    """_mm_cvtps_epi32 semantics (simd/src/x86/mod.rs:318-320; KATs simd/src/test.rs:380-383):
+    x.5 rounds to the even integer. Vertices are placed at tile-relative k + 0.5 (in 1/256 px)."""
+    f = np.float32
+    rel = [(2.5, 10.5), (200.5, 77.5), (101.5, 3000.5)]  # 1/256 px inside tile (1, 1)
+    pts = [(16 + x / 256.0, 16 + y / 256.0) for x, y in rel]
+    b = H.oracle_build(polygon_scene(pts), None)
+    expect = []
+    for (x0, y0), (x1, y1) in zip(pts, pts[1:] + pts[:1]):
+        q = [int(np.rint((f(v) - f(16.0)) * f(256.0))) for v in (x0, y0, x1, y1)]
+        expect.append(tuple(q))
+    got = [(int(r["from_x"]), int(r["from_y"]), int(r["to_x"]), int(r["to_y"])) for r in b.fills]
+    assert got == expect
+    assert (2, 10, 200, 78) == expect[0]  # 2.5 -> 2, 10.5 -> 10, 200.5 -> 200, 77.5 -> 78
+    assert len(b.tiles) == 1 and b.tiles[0]["tile_x"] == 1 and b.tiles[0]["tile_y"] == 1
+    assert b.alpha_tile_count == 1 and (b.fills["link"] == 0).all()
+
+
+def test_tile_rect_floor_ceil():
+    """round_out uses floor/ceil (simd/src/test.rs:54-60): a bound exactly on a tile edge does not
+    spill into the next tile."""
+    b = H.oracle_build(polygon_scene([(17.0, 5.0), (48.0, 5.0), (48.0, 31.9), (17.0, 31.9)]), None)
+    assert b.bbox_tile_count == 2 * 2
+    b = H.oracle_build(polygon_scene([(17.0, 5.0), (48.1, 5.0), (48.1, 32.0), (17.0, 32.0)]), None)
+    assert b.bbox_tile_count == 3 * 2
+
+
+def test_rectangle_tiles_and_coverage(area_lut):
+    rect = [(8.0, 8.0), (56.0, 8.0), (56.0, 40.0), (8.0, 40.0)]
+    b = H.oracle_build(polygon_scene(rect), None)
+    tiles = {(int(t["tile_x"]), int(t["tile_y"])): t for t in b.tiles}
+    assert set(tiles) == {(x, y) for x in range(4) for y in range(3)}
+    for (x, y), t in tiles.items():
+        interior = x in (1, 2) and y == 1
+        assert (t["alpha_tile_id"] == INVALID) == interior
+        if interior:
+            assert abs(int(t["backdrop"])) == 1  # solid tile: winding number of the interior
+    img = b.render(area_lut, 64, 64)
+    alpha = img[:, :, 3].astype(np.int32)
+    ideal = np.zeros((64, 64), dtype=np.int32)
+    ideal[8:40, 8:56] = 255
+    # The LUT is sampled 1/32 px off-centre (utils/area-lut/src/main.rs:84-85), so edges aligned to
+    # pixel boundaries are reproduced within a few 1/255 steps, not exactly.
+    assert np.abs(alpha - ideal).max() <= 10
+    assert (alpha[12:36, 12:52] >= 253).all() and (alpha[44:, :] <= 2).all()  # 8-bit LUT: sums land within 2 steps
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_coverage_integrates_to_polygon_area(area_lut, seed):
+    """Sum of per-pixel coverage = polygon area (the point of exact-area coverage)."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(3, 9))
+    ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+    rad = rng.uniform(20, 58, n)
+    pts = [(64 + float(r * np.cos(a)), 64 + float(r * np.sin(a))) for a, r in zip(ang, rad)]
+    b = H.oracle_build(polygon_scene(pts, size=128), None)
+    img = b.render(area_lut, 128, 128)
+    area = img[:, :, 3].astype(np.float64).sum() / 255.0
+    assert abs(area - shoelace(pts)) <= 0.01 * shoelace(pts) + 2.0
+
+
+def test_even_odd_and_winding_differ_on_self_overlap(area_lut):
+    star = [(64, 8), (98, 112), (10, 44), (118, 44), (30, 112)]
+    w = H.oracle_build(polygon_scene(star, size=128, fill_rule=0), None).render(area_lut, 128, 128)
+    e = H.oracle_build(polygon_scene(star, size=128, fill_rule=1), None).render(area_lut, 128, 128)
+    assert w[60, 64, 3] == 255 and e[60, 64, 3] == 0  # centre pentagon has winding number 2
+    assert w[30, 64, 3] == 255 and e[30, 64, 3] == 255  # a point of the star
+
+
+def test_flattening_properties():
+    b = SceneBuilderPy((0, 0, 512, 512))
+    b.move_to(20, 20)
+    b.cubic_to(500, -100, 520, 600, 40, 480)
+    b.quad_to(-100, 250, 20, 20)
+    b.close()
+    b.end_path((0, 0, 0, 255))
+    built = H.oracle_build(b.finish(), None, keep_lines=True)
+    lines = built.path_lines(0)
+    assert built.line_segment_count == len(lines) > 20
+    # consecutive lines join up; the contour closes with a zero-length line
+    assert np.array_equal(lines[1:, :2], lines[:-1, 2:])
+    assert tuple(lines[0, :2]) == (20.0, 20.0) and tuple(lines[-1, 2:]) == (20.0, 20.0)
+    # every chord is short enough to satisfy the flatness tolerance scale (0.25 px deviation)
+    assert np.hypot(lines[:, 2] - lines[:, 0], lines[:, 3] - lines[:, 1]).max() < 80.0
+
+
+def test_off_screen_and_degenerate_inputs():
+    b = SceneBuilderPy((0, 0, 64, 64))
+    b.end_path((1, 2, 3, 255))           # empty path
+    b.move_to(5, 5)
+    b.close()
+    b.end_path((1, 2, 3, 255))           # single point
+    b.move_to(-50, -50)
+    b.line_to(-10, -50)
+    b.line_to(-30, -10)
+    b.close()
+    b.end_path((1, 2, 3, 255))           # entirely off screen
+    built = H.oracle_build(b.finish(), None)
+    assert len(built.fills) == 0 and len(built.tiles) == 0 and built.alpha_tile_count == 0
+
+
+def test_zero_area_path_has_fills_but_no_coverage(area_lut):
+    """add_fill culls only on from_x == to_x (renderer/src/builder.rs:532-536): a degenerate
+    horizontal path still emits fills, which cancel in the mask."""
+    built = H.oracle_build(polygon_scene([(5.0, 5.0), (50.0, 5.0)]), None)
+    assert len(built.fills) > 0 and built.alpha_tile_count > 0
+    assert built.render(area_lut, 64, 64)[:, :, 3].max() <= 1
+
+
+def test_threaded_build_matches_sequential_up_to_alpha_ids():
+    """RayonExecutor stand-in: alpha tile ids are racy (gpu_data.rs:449-454) but everything else
+    is identical after renumbering ids in first-use order."""
+    flat, xf = scenes.tiger(512)
+    seq = H.oracle_build(flat, xf)
+    par = H.oracle_build(flat, xf, n_threads=4)
+    assert len(seq.fills) == len(par.fills) and seq.alpha_tile_count == par.alpha_tile_count
+
+    def canon(fills, tiles):
+        remap = {}
+        links = np.empty(len(fills), dtype=np.uint32)
+        for i, l in enumerate(fills["link"].tolist()):
+            links[i] = remap.setdefault(l, len(remap))
+        f = fills.copy()
+        f["link"] = links
+        t = tiles.copy()
+        t["alpha_tile_id"] = [remap[a] if a != INVALID else INVALID for a in tiles["alpha_tile_id"].tolist()]
+        return f, t
+
+    fs, ts = canon(seq.fills, seq.tiles)
+    fp, tp = canon(par.fills, par.tiles)
+    H.assert_records_equal(fs, fp, "fills")
+    H.assert_records_equal(ts, tp, "tiles")
+    H.assert_records_equal(fs, seq.fills, "sequential ids are already canonical")
+
+
+def test_strip_restriction_partitions_the_tile_lists(area_lut):
+    """What each rank of the strip partition must produce: the union over strips of (tile coords,
+    backdrop, path, solid/alpha) equals the full build, and stitched strips equal the full frame."""
+    flat, xf = scenes.tiger(256)
+    full = H.oracle_build(flat, xf)
+    full_img = full.render(area_lut, 256, 256, background=(1, 1, 1, 1))
+    key = lambda t: (int(t["path_id"]), int(t["tile_y"]), int(t["tile_x"]), int(t["backdrop"]), int(t["alpha_tile_id"] == INVALID))
+    want = sorted(key(t) for t in full.tiles)
+    got, fills = [], 0
+    stitched = np.zeros_like(full_img)
+    for y0, y1 in [(0, 4), (4, 8), (8, 12), (12, 16)]:
+        part = H.oracle_build(flat, xf, strip=(y0, y1))
+        assert all(y0 <= int(t["tile_y"]) < y1 for t in part.tiles)
+        got += [key(t) for t in part.tiles]
+        fills += len(part.fills)
+        img = part.render(area_lut, 256, 256, background=(1, 1, 1, 1))
+        stitched[y0 * 16:y1 * 16] = img[y0 * 16:y1 * 16]
+    assert sorted(got) == want
+    assert fills == len(full.fills)
+    assert np.array_equal(stitched, full_img)

@@ -1,0 +1,134 @@
+"""Host side above the C ABI (csrc/scene.cpp): the D3D11-level SceneBuilder mirror, exercised
+without a GPU through the RenderCommandListener callback."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from pathfinder_b200 import _lib as L
+from pathfinder_b200 import api, scenes
+from pathfinder_b200.flat_scene import SceneBuilderPy
+from tests import helpers as H
+
+
+def collect(scene, options, sink=None):
+    out = []
+
+    def listener(cmd):
+        rec = {"kind": L.COMMAND_NAMES[cmd.kind]}
+        if cmd.kind == L.PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11:
+            ds = cmd.u.upload_scene_d3d11.draw_segments
+            rec["points"] = np.ctypeslib.as_array(C.cast(ds.points, C.POINTER(C.c_float)), (ds.point_count, 2)).copy()
+            rec["indices"] = np.ctypeslib.as_array(C.cast(ds.indices, C.POINTER(C.c_uint32)), (ds.index_count, 2)).copy()
+        elif cmd.kind == L.PF_RENDER_COMMAND_DRAW_TILES_D3D11:
+            b = cmd.u.draw_tiles_d3d11.tile_batch_data
+            rec.update(path_count=b.path_count, tile_count=b.tile_count, segment_count=b.segment_count,
+                       content_key=b.content_key, batch_id=b.batch_id)
+            pm = C.cast(b.prepare_info.propagate_metadata, C.POINTER(L.PFPropagateMetadataD3D11))
+            dm = C.cast(b.prepare_info.dice_metadata, C.POINTER(L.PFDiceMetadataD3D11))
+            tp = C.cast(b.prepare_info.tile_path_info, C.POINTER(L.PFTilePathInfoD3D11))
+            rec["rects"] = [(pm[i].tile_rect.origin.x, pm[i].tile_rect.origin.y, pm[i].tile_rect.lower_right.x,
+                             pm[i].tile_rect.lower_right.y) for i in range(b.path_count)]
+            rec["tile_offsets"] = [pm[i].tile_offset for i in range(b.path_count)]
+            rec["z_write"] = [pm[i].z_write for i in range(b.path_count)]
+            rec["global_path_ids"] = [dm[i].global_path_id for i in range(b.path_count)]
+            rec["first_batch_segment"] = [dm[i].first_batch_segment_index for i in range(b.path_count)]
+            rec["ctrl"] = [tp[i].ctrl for i in range(b.path_count)]
+            rec["color"] = [tp[i].color for i in range(b.path_count)]
+        elif cmd.kind == L.PF_RENDER_COMMAND_UPLOAD_TEXTURE_METADATA:
+            n = cmd.u.upload_texture_metadata.entry_count
+            e = C.cast(cmd.u.upload_texture_metadata.entries, C.POINTER(L.PFTextureMetadataEntry))
+            rec["colors"] = [(e[i].base_color.r, e[i].base_color.g, e[i].base_color.b, e[i].base_color.a) for i in range(n)]
+        out.append(rec)
+
+    scene.build(options, listener, sink)
+    return out
+
+
+def small_scene():
+    b = SceneBuilderPy((0, 0, 64, 64))
+    b.move_to(4, 4)
+    b.line_to(40, 8)
+    b.quad_to(50, 30, 30, 40)
+    b.cubic_to(20, 50, 10, 45, 6, 30)
+    b.close()
+    b.end_path((255, 0, 0, 255))
+    b.move_to(100, 100)  # outside the view box: skipped by prepare_draw_path_for_gpu_binning
+    b.line_to(120, 100)
+    b.line_to(110, 120)
+    b.close()
+    b.end_path((0, 255, 0, 128), fill_rule=1)
+    b.move_to(20, 20)
+    b.line_to(60, 20)
+    b.line_to(60, 60)
+    b.close()
+    b.end_path((0, 255, 0, 128), fill_rule=1)
+    return b.finish("small")
+
+
+def test_command_order_and_payloads():
+    flat = small_scene()
+    cmds = collect(api.Scene.from_flat(flat), api.BuildOptions())
+    # SceneBuilder::build order (renderer/src/builder.rs:160-221)
+    assert [c["kind"] for c in cmds] == ["Start", "UploadTextureMetadata", "UploadSceneD3D11", "DrawTilesD3D11", "Finish"]
+    assert cmds[1]["colors"] == [(255, 0, 0, 255), (0, 255, 0, 128)]  # Palette dedups equal paints
+    up = cmds[2]
+    # SegmentsD3D11::add_path (builder.rs:804-841): one index per on-curve point, first point re-appended.
+    idx = up["indices"]
+    assert idx[:4, 0].tolist() == [0, 1, 3, 6]
+    assert idx[:4, 1].tolist() == [0, 0x80000000, 0x40000000, 0]
+    pts = up["points"]
+    assert np.array_equal(pts[7], pts[0])  # implicit close
+    draw = cmds[3]
+    assert draw["batch_id"] == 32  # MAX_CLIP_BATCHES
+    assert draw["path_count"] == 2 and draw["global_path_ids"] == [0, 2]  # path 1 is off-screen
+    assert draw["rects"][0] == (0, 0, 4, 4)  # bounds include control points (outline.rs:884-896)
+    assert draw["rects"][1] == (1, 1, 4, 4)
+    assert draw["tile_offsets"] == [0, 16] and draw["tile_count"] == 25
+    assert draw["z_write"] == [1, 0]  # opaque paint occludes, translucent does not
+    assert draw["ctrl"] == [1, 2] and draw["color"] == [0, 1]
+    assert draw["first_batch_segment"] == [0, 4] and draw["segment_count"] == 7
+
+
+def test_scene_upload_only_when_dirty():
+    flat = small_scene()
+    scene = api.Scene.from_flat(flat)
+    sink = L.PFSceneSinkState()
+    first = collect(scene, api.BuildOptions(), sink)
+    second = collect(scene, api.BuildOptions(), sink)
+    assert "UploadSceneD3D11" in [c["kind"] for c in first]
+    assert "UploadSceneD3D11" not in [c["kind"] for c in second]  # builder.rs:193-215
+    assert first[3]["content_key"] == second[2]["content_key"] != 0
+    scene.set_view_box(flat.view_box)  # bumps the epoch
+    third = collect(scene, api.BuildOptions(), sink)
+    assert "UploadSceneD3D11" in [c["kind"] for c in third]
+    assert third[3]["content_key"] != first[3]["content_key"]
+    moved = collect(scene, api.BuildOptions(transform=api.Transform2F.from_scale(0.5)), sink)
+    assert moved[2]["content_key"] != third[3]["content_key"]
+
+
+@pytest.mark.parametrize("size", [256, 1024])
+def test_tile_rects_match_cpu_tiler(size):
+    """Sum of dense tile-map areas equals the CPU tiler's (renderer/src/builder.rs:430-436) for the
+    scale + translate transform of the tiger."""
+    flat, xf = scenes.tiger(size)
+    cmds = collect(api.Scene.from_flat(flat), api.BuildOptions(transform=api.Transform2F(*xf)))
+    draw = [c for c in cmds if c["kind"] == "DrawTilesD3D11"][0]
+    built = H.oracle_build(flat, xf)
+    assert draw["tile_count"] == built.bbox_tile_count
+    assert draw["segment_count"] == built.input_segment_count
+
+
+def test_random_scene_rects_match_cpu_tiler():
+    flat = scenes.random_paths(2000, 2048, 7)
+    cmds = collect(api.Scene.from_flat(flat), api.BuildOptions())
+    draw = [c for c in cmds if c["kind"] == "DrawTilesD3D11"][0]
+    built = H.oracle_build(flat, None)
+    assert draw["tile_count"] == built.bbox_tile_count
+
+
+def test_unsupported_options_are_refused():
+    flat = small_scene()
+    with pytest.raises(L.PathfinderCudaError) as e:
+        collect(api.Scene.from_flat(flat), api.BuildOptions(subpixel_aa_enabled=True))
+    assert e.value.status == L.PF_CUDA_ERROR_UNSUPPORTED

@@ -1,0 +1,60 @@
+"""N > 1 host logic on CPU: world_size-2 gloo run of the strip partition + all-gather plumbing that
+bench.py uses, with the oracle standing in for the per-rank renderer."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pathfinder_b200 import area_lut, partition, scenes
+from tests import helpers as H
+
+SIZE = 256
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        flat, xf = scenes.tiger(SIZE)
+        y0, y1 = partition.strip_rows(SIZE, world, rank)
+        built = H.oracle_build(flat, xf, strip=(y0, y1))
+        img = built.render(area_lut.generate(), SIZE, SIZE, background=(1, 1, 1, 1))
+        p0, p1 = partition.strip_pixel_rows(SIZE, world, rank)
+        strip = torch.from_numpy(np.ascontiguousarray(img[p0:p1]))
+        full = torch.empty((SIZE, SIZE, 4), dtype=torch.uint8)
+        dist.all_gather_into_tensor(full.view(-1), strip.reshape(-1))
+        counts = torch.tensor([len(built.fills), len(built.tiles)], dtype=torch.int64)
+        dist.all_reduce(counts)
+        if rank == 0:
+            np.savez(out_path, frame=full.numpy(), counts=counts.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_strip_render_and_gather(tmp_path):
+    out = str(tmp_path / "gathered.npz")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    z = np.load(out)
+    flat, xf = scenes.tiger(SIZE)
+    full = H.oracle_build(flat, xf)
+    ref = full.render(area_lut.generate(), SIZE, SIZE, background=(1, 1, 1, 1))
+    assert np.array_equal(z["frame"], ref)
+    assert z["counts"].tolist() == [len(full.fills), len(full.tiles)]
+
+
+def test_strip_rows():
+    assert partition.strip_rows(8192, 8, 3) == (192, 256)
+    assert partition.strip_pixel_rows(4096, 2, 1) == (2048, 4096)
+    import pytest
+    with pytest.raises(ValueError):
+        partition.strip_rows(100, 3, 0)
