@@ -42,6 +42,29 @@ __device__ __forceinline__ uint32_t search_le(const uint32_t *__restrict__ keys,
     return lo;
 }
 
+// search_le for a warp whose lanes hold consecutive (non-decreasing) x: lane 0 runs the binary
+// search once, the other lanes walk forward from its answer (paths are long runs of tiles /
+// columns / segments, so this is usually zero or one step), falling back to a bounded binary
+// search. Must be called by all 32 lanes; lanes with active == false only assist.
+__device__ __forceinline__ uint32_t search_le_warp(const uint32_t *__restrict__ keys, uint32_t n, uint32_t x,
+                                                   bool active) {
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t x0 = __shfl_sync(0xffffffffu, x, 0);
+    uint32_t p0 = 0;
+    if (lane == 0) p0 = search_le(keys, n, x0);
+    p0 = __shfl_sync(0xffffffffu, p0, 0);
+    if (!active) return p0;
+    uint32_t p = p0;
+#pragma unroll 1
+    for (int step = 0; step < 4; step++) {
+        if (p + 1 < n && __ldg(keys + p + 1) <= x)
+            p++;
+        else
+            return p;
+    }
+    return p + search_le(keys + p, n - p, x);
+}
+
 __device__ __forceinline__ PathInfo load_path(const PathInfo *__restrict__ paths, uint32_t p) {
     const int4 *q = reinterpret_cast<const int4 *>(paths + p);
     int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
@@ -377,18 +400,30 @@ int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_
 
 // ---------------------------------------------------------------------------------------------
 // sort — per-framebuffer-tile painter's-order lists with z-cull.
+//
+// Count -> scan -> emit again: every surviving tile bumps its framebuffer tile's counter, the scan
+// gives each framebuffer tile a contiguous run, and the emit pass appends 16-byte entries through
+// a per-framebuffer-tile cursor. The append order inside a run is arbitrary; the fused fill+tile
+// kernel sorts its (short) run by tile index — tiles are allocated path by path, so ascending
+// tile index is draw order — in shared memory. This replaces the linked-list insertion sort of
+// shaders/d3d11/sort.cs.glsl:60-95 and needs no global sort.
 // ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256)
-    k_list_flags(BatchDev b, const uint32_t *__restrict__ tile_word, const int32_t *__restrict__ z_buffer,
-                 uint32_t *__restrict__ tile_fb) {
+    k_list_count(BatchDev b, const uint32_t *__restrict__ tile_word, const int32_t *__restrict__ z_buffer,
+                 uint32_t *__restrict__ tile_fb, uint32_t *__restrict__ fb_count) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= b.n_tiles) return;
-    uint32_t word = __ldg(tile_word + t);
-    uint32_t result = 0xffffffffu;
+    const bool in_range = t < b.n_tiles;
+    uint32_t word = in_range ? __ldg(tile_word + t) : 0;
     // Empty tiles are never drawn (renderer/src/builder.rs:1014-1016).
-    if ((word & 0x00ffffffu) != 0 || (word >> 24) != 0) {
-        uint32_t p = search_le(b.path_tile_offset, b.n_paths, t);
+    const bool nonempty = (word & 0x00ffffffu) != 0 || (word >> 24) != 0;
+    if (!__any_sync(0xffffffffu, nonempty)) {
+        if (in_range) tile_fb[t] = 0xffffffffu;
+        return;
+    }
+    uint32_t p = search_le_warp(b.path_tile_offset, b.n_paths, in_range ? t : b.n_tiles - 1, nonempty);
+    uint32_t result = 0xffffffffu;
+    if (nonempty) {
         const PathInfo path = load_path(b.paths, p);
         int w = path.max_x - path.min_x;
         uint32_t local = t - path.tile_offset;
@@ -398,62 +433,43 @@ __global__ void __launch_bounds__(256)
         if (fx >= 0 && fy >= 0 && fx < fb_w && fy < fb_h) {
             uint32_t fbi = (uint32_t)(fy * fb_w + fx);
             // z-cull: dropped iff path_id < z (shaders/d3d11/sort.cs.glsl:74, d3d9/tile.vs.glsl:52-56)
-            if ((int32_t)path.global_path_id >= __ldg(z_buffer + fbi)) result = fbi;
+            if ((int32_t)path.global_path_id >= __ldg(z_buffer + fbi)) {
+                result = fbi;
+                atomicAdd(fb_count + fbi, 1u);
+            }
         }
     }
-    tile_fb[t] = result;
+    if (in_range) tile_fb[t] = result;
 }
 
-int launch_list_flags(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
-                      cudaStream_t stream) {
+int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
+                      uint32_t *fb_count, cudaStream_t stream) {
     if (b.n_tiles == 0) return 0;
-    k_list_flags<<<div_up(b.n_tiles, 256), 256, 0, stream>>>(b, tile_word, z_buffer, tile_fb);
+    k_list_count<<<div_up(b.n_tiles, 256), 256, 0, stream>>>(b, tile_word, z_buffer, tile_fb, fb_count);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
 
 __global__ void __launch_bounds__(256)
-    k_list_emit(uint32_t n_tiles, const uint32_t *__restrict__ tile_fb, const uint32_t *__restrict__ tile_pos,
-                uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t capacity) {
+    k_list_emit(BatchDev b, const uint32_t *__restrict__ tile_fb, const uint32_t *__restrict__ tile_word,
+                const uint32_t *__restrict__ tile_fill_pos, const uint32_t *__restrict__ fb_start,
+                uint32_t *__restrict__ fb_cursor, TileEntry *__restrict__ entries, uint32_t capacity,
+                uint32_t *__restrict__ visible_fill_count) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tiles) return;
-    uint32_t fbi = __ldg(tile_fb + t);
-    if (fbi == 0xffffffffu) return;
-    uint32_t pos = __ldg(tile_pos + t);
-    if (pos < capacity) {
-        keys[pos] = fbi;
-        vals[pos] = t;
-    }
-}
-
-int launch_list_emit(uint32_t n_tiles, const uint32_t *tile_fb, const uint32_t *tile_pos, uint32_t *keys,
-                     uint32_t *vals, uint32_t capacity, cudaStream_t stream) {
-    if (n_tiles == 0) return 0;
-    k_list_emit<<<div_up(n_tiles, 256), 256, 0, stream>>>(n_tiles, tile_fb, tile_pos, keys, vals, capacity);
-    PF_CUDA_CHECK(cudaGetLastError());
-    return 1;
-}
-
-__global__ void __launch_bounds__(256)
-    k_build_entries(BatchDev b, uint32_t n_entries, const uint32_t *__restrict__ n_entries_dev,
-                    const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                    const uint32_t *__restrict__ tile_word, const uint32_t *__restrict__ tile_fill_pos,
-                    TileEntry *__restrict__ entries, uint32_t *__restrict__ fb_start, uint32_t *__restrict__ fb_end,
-                    uint32_t *__restrict__ visible_fill_count) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n_entries_dev) n_entries = min(n_entries, __ldg(n_entries_dev));
+    const bool in_range = t < b.n_tiles;
+    uint32_t fbi = in_range ? __ldg(tile_fb + t) : 0xffffffffu;
+    const bool live = fbi != 0xffffffffu;
+    if (!__any_sync(0xffffffffu, live)) return;
+    uint32_t p = search_le_warp(b.path_tile_offset, b.n_paths, in_range ? t : b.n_tiles - 1, live);
     uint32_t visible = 0;
-    if (i < n_entries) {
-        uint32_t fbi = __ldg(keys + i), t = __ldg(vals + i);
-        uint32_t p = search_le(b.path_tile_offset, b.n_paths, t);
+    if (live) {
         TileEntry e;
-        e.fill_end = __ldg(tile_fill_pos + t); // the emit pass left the cursor at the end of the run
+        e.fill_end = __ldg(tile_fill_pos + t); // the bin emit pass left the cursor at the end of the run
         e.word = __ldg(tile_word + t);
         e.paint_ctrl = __ldg(&b.paths[p].paint_ctrl) & 0x00ffffffu;
-        e.path_id = __ldg(&b.paths[p].global_path_id);
-        *reinterpret_cast<uint4 *>(entries + i) = *reinterpret_cast<uint4 *>(&e);
-        if (i == 0 || __ldg(keys + i - 1) != fbi) fb_start[fbi] = i;
-        if (i + 1 == n_entries || __ldg(keys + i + 1) != fbi) fb_end[fbi] = i + 1;
+        e.tile_index = t;
+        uint32_t slot = __ldg(fb_start + fbi) + atomicAdd(fb_cursor + fbi, 1u);
+        if (slot < capacity) *reinterpret_cast<uint4 *>(entries + slot) = *reinterpret_cast<uint4 *>(&e);
         visible = e.word & 0x00ffffffu;
     }
     // Fills the fused kernel will actually read (statistics for the roofline's algorithmic bytes).
@@ -463,14 +479,12 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-int launch_build_entries(const BatchDev &b, uint32_t n_entries, const uint32_t *n_entries_dev, const uint32_t *keys,
-                         const uint32_t *vals, const uint32_t *tile_word, const uint32_t *tile_fill_pos,
-                         TileEntry *entries, uint32_t *fb_start, uint32_t *fb_end, uint32_t *visible_fill_count,
-                         cudaStream_t stream) {
-    if (n_entries == 0) return 0;
-    k_build_entries<<<div_up(n_entries, 256), 256, 0, stream>>>(b, n_entries, n_entries_dev, keys, vals, tile_word,
-                                                                 tile_fill_pos, entries, fb_start, fb_end,
-                                                                 visible_fill_count);
+int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t *tile_word,
+                     const uint32_t *tile_fill_pos, const uint32_t *fb_start, uint32_t *fb_cursor,
+                     TileEntry *entries, uint32_t capacity, uint32_t *visible_fill_count, cudaStream_t stream) {
+    if (b.n_tiles == 0) return 0;
+    k_list_emit<<<div_up(b.n_tiles, 256), 256, 0, stream>>>(b, tile_fb, tile_word, tile_fill_pos, fb_start, fb_cursor,
+                                                             entries, capacity, visible_fill_count);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -491,8 +505,7 @@ constexpr float COV_SCALE = 1.0f / 32768.0f;
 __device__ __forceinline__ void accumulate_fill(PackedFill f, float cx, float cy, cudaTextureObject_t lut,
                                                 uint32_t acc[4]) {
     const float s = 1.0f / 256.0f;
-    float from_x = fmaf((float)(f.x & 0xffffu), s, -cx), from_y = fmaf((float)(f.x >> 16), s, -cy);
-    float to_x = fmaf((float)(f.y & 0xffffu), s, -cx), to_y = fmaf((float)(f.y >> 16), s, -cy);
+    float from_x = fmaf((float)(f.x & 0xffffu), s, -cx), to_x = fmaf((float)(f.y & 0xffffu), s, -cx);
     float wx = fminf(fmaxf(from_x, -0.5f), 0.5f), wy = fminf(fmaxf(to_x, -0.5f), 0.5f);
     float dX = wx - wy;
     if (dX == 0.0f) { // the pixel column is outside the segment's x range: LUT * 0
@@ -500,10 +513,11 @@ __device__ __forceinline__ void accumulate_fill(PackedFill f, float cx, float cy
         for (int k = 0; k < 4; k++) acc[k] += COV_MAGIC_BITS;
         return;
     }
+    float from_y = fmaf((float)(f.x >> 16), s, -cy), to_y = fmaf((float)(f.y >> 16), s, -cy);
     bool from_left = from_x < to_x;
     float lx = from_left ? from_x : to_x, ly = from_left ? from_y : to_y;
     float rx = from_left ? to_x : from_x, ry = from_left ? to_y : from_y;
-    float inv = __frcp_rn(rx - lx);
+    float inv = __fdividef(1.0f, rx - lx);
     float offset = 0.5f * (wx + wy) - lx;
     float t = offset * inv;
     float y = fmaf(ry - ly, t, ly);
@@ -532,34 +546,52 @@ __device__ __forceinline__ float mask_alpha(float coverage, uint32_t ctrl) {
     return fminf(1.0f, coverage);
 }
 
-__device__ __forceinline__ uint32_t pack_rgba8(float r, float g, float b, float a) {
-    uint32_t R = __float2uint_rn(__saturatef(r) * 255.0f), G = __float2uint_rn(__saturatef(g) * 255.0f);
-    uint32_t B = __float2uint_rn(__saturatef(b) * 255.0f), A = __float2uint_rn(__saturatef(a) * 255.0f);
+__device__ __forceinline__ uint32_t pack_rgba8(float4 c) {
+    uint32_t R = __float2uint_rn(__saturatef(c.x) * 255.0f), G = __float2uint_rn(__saturatef(c.y) * 255.0f);
+    uint32_t B = __float2uint_rn(__saturatef(c.z) * 255.0f), A = __float2uint_rn(__saturatef(c.w) * 255.0f);
     return R | (G << 8) | (B << 16) | (A << 24);
+}
+
+__device__ __forceinline__ void group_barrier(int group) {
+    // named barrier per 64-thread tile group (barrier 0 is __syncthreads)
+    asm volatile("bar.sync %0, 64;" ::"r"(group + 1) : "memory");
 }
 
 // One 64-thread group per framebuffer tile: thread (x, strip) owns column x, rows 4*strip..+3,
 // exactly the 16x4 workgroup of shaders/d3d11/tile.cs.glsl:22 — but the mask never leaves
 // registers: fill (coverage) and tile (composite) are one kernel.
 constexpr int COMPOSITE_TILES_PER_BLOCK = 4;
+constexpr int COMPOSITE_SORT_CAP = 256; // entries sorted in shared memory; longer lists use the slow path
 
 __global__ void __launch_bounds__(64 * COMPOSITE_TILES_PER_BLOCK) k_composite(CompositeArgs a) {
+    __shared__ uint4 s_entries[COMPOSITE_TILES_PER_BLOCK][COMPOSITE_SORT_CAP];
+    __shared__ uint32_t s_keys[COMPOSITE_TILES_PER_BLOCK][COMPOSITE_SORT_CAP];
+    __shared__ uint32_t s_min[COMPOSITE_TILES_PER_BLOCK][2];
+
     const int group = threadIdx.x >> 6, tid = threadIdx.x & 63;
     const int fb_w = a.fb.max_x - a.fb.min_x;
     const int tiles_x_groups = (fb_w + COMPOSITE_TILES_PER_BLOCK - 1) / COMPOSITE_TILES_PER_BLOCK;
     const int tile_col = (blockIdx.x % tiles_x_groups) * COMPOSITE_TILES_PER_BLOCK + group;
     const int tile_row = a.tile_y0 + blockIdx.x / tiles_x_groups; // absolute tile y
-    if (tile_col >= fb_w) return;
+    if (tile_col >= fb_w) return; // whole group exits together
     const int tx = a.fb.min_x + tile_col, ty = tile_row;
     const int x = tid & 15, strip = tid >> 4;
     const int px = tx * 16 + x, py0 = ty * 16 + strip * 4;
-    if (px < 0 || px >= a.dest_w) return;
+    const bool px_ok = px >= 0 && px < a.dest_w;
+
+    const int fy = ty - a.fb.min_y;
+    uint32_t e0 = 0, n = 0;
+    if (fy >= 0 && fy < a.fb.max_y - a.fb.min_y) {
+        const uint32_t fbi = (uint32_t)(fy * fb_w + tile_col);
+        n = __ldg(a.fb_count + fbi);
+        e0 = __ldg(a.fb_start + fbi);
+    }
 
     float4 dst[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         int py = py0 + k;
-        if (a.load_dest && py >= 0 && py < a.dest_h) {
+        if (a.load_dest && px_ok && py >= 0 && py < a.dest_h) {
             uint32_t v = *reinterpret_cast<const uint32_t *>(a.dest + (size_t)py * a.dest_pitch + (size_t)px * 4);
             const float s = 1.0f / 255.0f;
             dst[k] = make_float4((float)(v & 0xff) * s, (float)((v >> 8) & 0xff) * s, (float)((v >> 16) & 0xff) * s,
@@ -569,41 +601,88 @@ __global__ void __launch_bounds__(64 * COMPOSITE_TILES_PER_BLOCK) k_composite(Co
         }
     }
 
-    const int fy = ty - a.fb.min_y;
-    if (fy >= 0 && fy < a.fb.max_y - a.fb.min_y) {
-        const uint32_t fbi = (uint32_t)(fy * fb_w + tile_col);
-        const uint32_t e0 = __ldg(a.fb_start + fbi), e1 = __ldg(a.fb_end + fbi);
-        const float cx = (float)x + 0.5f, cy = (float)(strip * 4) + 0.5f;
-        for (uint32_t ei = e0; ei < e1; ei++) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + ei));
-            const uint32_t fill_end = raw.x, word = raw.y, paint_ctrl = raw.z;
-            const uint32_t count = word & 0x00ffffffu;
-            const float backdrop = (float)(int)(int8_t)(word >> 24);
-            const uint32_t ctrl = (paint_ctrl >> 16) & 0xffu;
-            const float4 base = __ldg(a.paints + (paint_ctrl & 0xffffu));
-            uint32_t acc[4] = {0, 0, 0, 0};
-            for (uint32_t fi = fill_end - count; fi < fill_end; fi++)
-                accumulate_fill(__ldg(a.fills + fi), cx, cy, a.area_lut, acc);
+    // ---- sort the run by tile index (painter's order) ----
+    const bool in_smem = n > 1 && n <= COMPOSITE_SORT_CAP;
+    if (in_smem) {
+        for (uint32_t i = tid; i < n; i += 64) s_keys[group][i] = __ldg(&a.entries[e0 + i].tile_index);
+        group_barrier(group);
+        for (uint32_t i = tid; i < n; i += 64) {
+            const uint32_t key = s_keys[group][i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n; j++) rank += s_keys[group][j] < key ? 1u : 0u;
+            s_entries[group][rank] = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + i));
+        }
+        group_barrier(group);
+    }
+
+    const float cx = (float)x + 0.5f, cy = (float)(strip * 4) + 0.5f;
+    uint32_t last_key = 0; // slow path cursor: smallest tile index not yet drawn
+    for (uint32_t ei = 0; ei < n; ei++) {
+        uint4 raw;
+        if (in_smem) {
+            raw = s_entries[group][ei];
+        } else if (n == 1) {
+            raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0));
+        } else {
+            // Slow path for very deep lists: select the next entry in draw order by a min-scan.
+            uint32_t best = 0xffffffffu, best_i = 0;
+            for (uint32_t i = tid; i < n; i += 64) {
+                uint32_t key = __ldg(&a.entries[e0 + i].tile_index);
+                if (key >= last_key && key < best) best = key, best_i = i;
+            }
+            for (int d = 16; d > 0; d >>= 1) {
+                uint32_t ob = __shfl_xor_sync(0xffffffffu, best, d), oi = __shfl_xor_sync(0xffffffffu, best_i, d);
+                if (ob < best) best = ob, best_i = oi;
+            }
+            if ((tid & 31) == 0) s_min[group][tid >> 5] = best, s_keys[group][tid >> 5] = best_i;
+            group_barrier(group);
+            uint32_t b0 = s_min[group][0], b1 = s_min[group][1];
+            best_i = b0 <= b1 ? s_keys[group][0] : s_keys[group][1];
+            last_key = (b0 <= b1 ? b0 : b1) + 1;
+            group_barrier(group);
+            raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + best_i));
+        }
+        const uint32_t fill_end = raw.x, word = raw.y, paint_ctrl = raw.z;
+        const uint32_t count = word & 0x00ffffffu;
+        const float backdrop = (float)(int)(int8_t)(word >> 24);
+        const uint32_t ctrl = (paint_ctrl >> 16) & 0xffu;
+        const float4 base = __ldg(a.paints + (paint_ctrl & 0xffffu));
+        if (count == 0) {
+            // Solid tile: coverage = backdrop for every pixel (tile_fragment.inc.glsl:548).
+            const float alpha = base.w * mask_alpha(backdrop, ctrl);
+            const float ia = 1.0f - alpha;
+            const float sr = base.x * alpha, sg = base.y * alpha, sb = base.z * alpha;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                float coverage = finish_coverage(acc[k], count) + backdrop;
-                // calculateColor (tile_fragment.inc.glsl:560-614), solid colour, SrcOver;
-                // dest = dest * (1 - a) + src (tile.cs.glsl:155).
-                float alpha = base.w * mask_alpha(coverage, ctrl);
-                float ia = 1.0f - alpha;
-                dst[k].x = fmaf(dst[k].x, ia, base.x * alpha);
-                dst[k].y = fmaf(dst[k].y, ia, base.y * alpha);
-                dst[k].z = fmaf(dst[k].z, ia, base.z * alpha);
+                dst[k].x = fmaf(dst[k].x, ia, sr);
+                dst[k].y = fmaf(dst[k].y, ia, sg);
+                dst[k].z = fmaf(dst[k].z, ia, sb);
                 dst[k].w = fmaf(dst[k].w, ia, alpha);
             }
+            continue;
+        }
+        uint32_t acc[4] = {0, 0, 0, 0};
+        for (uint32_t fi = fill_end - count; fi < fill_end; fi++)
+            accumulate_fill(__ldg(a.fills + fi), cx, cy, a.area_lut, acc);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float coverage = finish_coverage(acc[k], count) + backdrop;
+            // calculateColor (tile_fragment.inc.glsl:560-614), solid colour, SrcOver;
+            // dest = dest * (1 - a) + src (tile.cs.glsl:155).
+            float alpha = base.w * mask_alpha(coverage, ctrl);
+            float ia = 1.0f - alpha;
+            dst[k].x = fmaf(dst[k].x, ia, base.x * alpha);
+            dst[k].y = fmaf(dst[k].y, ia, base.y * alpha);
+            dst[k].z = fmaf(dst[k].z, ia, base.z * alpha);
+            dst[k].w = fmaf(dst[k].w, ia, alpha);
         }
     }
+    if (!px_ok) return;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         int py = py0 + k;
         if (py >= 0 && py < a.dest_h)
-            *reinterpret_cast<uint32_t *>(a.dest + (size_t)py * a.dest_pitch + (size_t)px * 4) =
-                pack_rgba8(dst[k].x, dst[k].y, dst[k].z, dst[k].w);
+            *reinterpret_cast<uint32_t *>(a.dest + (size_t)py * a.dest_pitch + (size_t)px * 4) = pack_rgba8(dst[k]);
     }
 }
 

@@ -41,7 +41,7 @@ struct __align__(16) TileEntry {
     uint32_t fill_end;    // end of the tile's run in the tile-grouped fill array
     uint32_t word;        // fill count (low 24 bits) | backdrop i8 << 24
     uint32_t paint_ctrl;  // color u16 | ctrl u8 << 16
-    uint32_t path_id;     // global draw path id
+    uint32_t tile_index;  // dense tile index: ascending = draw order (sort key inside a list)
 };
 
 // Tile-grouped fill: the 4.8 fixed point segment (LineSegmentU16) as one 64-bit word.
@@ -96,19 +96,17 @@ int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_
                      cudaStream_t stream);
 
 // tile_fb[t] = framebuffer tile index if the tile is non-empty, inside the framebuffer and not
-// z-culled, else 0xffffffff.
-int launch_list_flags(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
-                      cudaStream_t stream);
-int launch_list_emit(uint32_t n_tiles, const uint32_t *tile_fb, const uint32_t *tile_pos, uint32_t *keys,
-                     uint32_t *vals, uint32_t capacity, cudaStream_t stream);
-int launch_build_entries(const BatchDev &b, uint32_t n_entries, const uint32_t *n_entries_dev, const uint32_t *keys,
-                         const uint32_t *vals, const uint32_t *tile_word, const uint32_t *tile_fill_pos,
-                         TileEntry *entries, uint32_t *fb_start, uint32_t *fb_end, uint32_t *visible_fill_count,
-                         cudaStream_t stream);
+// z-culled, else 0xffffffff; fb_count[fb] += 1 for every survivor.
+int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
+                      uint32_t *fb_count, cudaStream_t stream);
+// Appends one TileEntry per surviving tile to its framebuffer tile's run [fb_start, fb_start + count).
+int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t *tile_word,
+                     const uint32_t *tile_fill_pos, const uint32_t *fb_start, uint32_t *fb_cursor,
+                     TileEntry *entries, uint32_t capacity, uint32_t *visible_fill_count, cudaStream_t stream);
 
 struct CompositeArgs {
-    const TileEntry *entries;
-    const uint32_t *fb_start, *fb_end;
+    const TileEntry *entries;   // runs in arbitrary order; the kernel sorts each by tile_index
+    const uint32_t *fb_start, *fb_count;
     const PackedFill *fills;
     const float4 *paints;      // base colour per paint id, already rounded through f16
     cudaTextureObject_t area_lut;

@@ -17,7 +17,6 @@
 #include "../../include/pf_cuda.h"
 #include "common.cuh"
 #include "kernels.cuh"
-#include "radix_sort.cuh"
 #include "scan.cuh"
 
 namespace pf {
@@ -125,13 +124,11 @@ struct PFCudaRenderer {
     DeviceBuffer<PackedFill> fills;
     DeviceBuffer<EmitFill> fills_emit;
     DeviceBuffer<int32_t> z_buffer;
-    DeviceBuffer<uint32_t> fb_start, fb_end;
-    DeviceBuffer<uint32_t> list_keys, list_vals;
+    DeviceBuffer<uint32_t> fb_start, fb_count, fb_cursor;
     DeviceBuffer<TileEntry> entries;
     DeviceBuffer<uint32_t> counters; // device-side totals: [0]=lines [1]=fills [2]=entries [3]=alpha tiles [4]=dump tiles
     PinnedBuffer<uint32_t> counters_host;
     ScanScratch scan_scratch;
-    RadixSortScratch sort_scratch;
     // debug / dump scratch
     DeviceBuffer<uint8_t> fill_is_first;
     DeviceBuffer<uint32_t> fill_first_scan;
@@ -197,16 +194,11 @@ void setup_tracking(PFCudaRenderer *r) {
     track(r, r->fills_emit);
     track(r, r->z_buffer);
     track(r, r->fb_start);
-    track(r, r->fb_end);
-    track(r, r->list_keys);
-    track(r, r->list_vals);
+    track(r, r->fb_count);
+    track(r, r->fb_cursor);
     track(r, r->entries);
     track(r, r->counters);
     track(r, r->scan_scratch.block_sums);
-    track(r, r->sort_scratch.hist);
-    track(r, r->sort_scratch.keys_tmp);
-    track(r, r->sort_scratch.vals_tmp);
-    track(r, r->sort_scratch.scan.block_sums);
     track(r, r->fill_is_first);
     track(r, r->fill_first_scan);
     track(r, r->dump_out);
@@ -426,7 +418,6 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     r->tile_fill_pos.ensure(n_tiles + 1, 1.25);
     r->col_backdrop.ensure(n_cols + 1, 1.25);
     r->tile_fb.ensure(n_tiles + 1, 1.25);
-    r->tile_pos.ensure(n_tiles + 1, 1.25);
     PF_CUDA_CHECK(cudaMemsetAsync(r->tile_word.ptr, 0, (size_t)n_tiles * 4, st));
     if (c.has_initial_backdrops)
         PF_CUDA_CHECK(cudaMemcpyAsync(r->col_backdrop.ptr, r->col_backdrop_init.ptr, (size_t)n_cols * 4,
@@ -441,10 +432,11 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     const uint32_t n_fb = (uint32_t)(fb_w * fb_h);
     r->z_buffer.ensure(n_fb + 1);
     r->fb_start.ensure(n_fb + 1);
-    r->fb_end.ensure(n_fb + 1);
+    r->fb_count.ensure(n_fb + 1);
+    r->fb_cursor.ensure(n_fb + 1);
     PF_CUDA_CHECK(cudaMemsetAsync(r->z_buffer.ptr, 0, (size_t)n_fb * 4, st));
-    PF_CUDA_CHECK(cudaMemsetAsync(r->fb_start.ptr, 0, (size_t)n_fb * 4, st));
-    PF_CUDA_CHECK(cudaMemsetAsync(r->fb_end.ptr, 0, (size_t)n_fb * 4, st));
+    PF_CUDA_CHECK(cudaMemsetAsync(r->fb_count.ptr, 0, (size_t)n_fb * 4, st));
+    PF_CUDA_CHECK(cudaMemsetAsync(r->fb_cursor.ptr, 0, (size_t)n_fb * 4, st));
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[1], st));
 
     auto bound_of = [](uint32_t last, size_t capacity) -> uint32_t {
@@ -507,41 +499,27 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     launches += launch_propagate(b, r->tile_word.ptr, r->col_backdrop.ptr, r->z_buffer.ptr, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[4], st));
 
-    // ---- sort: z-cull, compact surviving tiles, stable radix sort by framebuffer tile.
-    launches += launch_list_flags(b, r->tile_word.ptr, r->z_buffer.ptr, r->tile_fb.ptr, st);
-    launches += exclusive_scan(LoadNotInvalid{r->tile_fb.ptr}, r->tile_pos.ptr, n_tiles, r->counters.ptr + C_ENTRIES,
+    // ---- sort: z-cull + per-framebuffer-tile runs (count -> scan -> append); the run itself is
+    // sorted into draw order inside the fused kernel.
+    launches += launch_list_count(b, r->tile_word.ptr, r->z_buffer.ptr, r->tile_fb.ptr, r->fb_count.ptr, st);
+    launches += exclusive_scan(LoadU32{r->fb_count.ptr}, r->fb_start.ptr, n_fb, r->counters.ptr + C_ENTRIES,
                                r->scan_scratch, st);
     uint32_t entry_bound;
     if (sizing) {
         entry_bound = n_tiles ? read_counter(r, C_ENTRIES) : 0;
-        r->list_keys.ensure(entry_bound + 1, 1.25);
-        r->list_vals.ensure(entry_bound + 1, 1.25);
         r->entries.ensure(entry_bound + 1, 1.25);
-        r->sort_scratch.keys_tmp.ensure(entry_bound + 1, 1.25);
-        r->sort_scratch.vals_tmp.ensure(entry_bound + 1, 1.25);
     } else {
-        size_t cap = std::min(std::min(r->list_keys.capacity, r->list_vals.capacity),
-                              std::min(r->entries.capacity, std::min(r->sort_scratch.keys_tmp.capacity,
-                                                                     r->sort_scratch.vals_tmp.capacity)));
-        entry_bound = bound_of(c.n_entries, cap);
+        entry_bound = bound_of(c.n_entries, r->entries.capacity);
     }
-    const uint32_t *n_entries_dev = r->counters.ptr + C_ENTRIES;
-    launches += launch_list_emit(n_tiles, r->tile_fb.ptr, r->tile_pos.ptr, r->list_keys.ptr, r->list_vals.ptr,
-                                 entry_bound, st);
-    int key_bits = 1;
-    while ((1u << key_bits) < n_fb && key_bits < 32) key_bits++;
-    launches += radix_sort_pairs(r->list_keys.ptr, r->list_vals.ptr, entry_bound, key_bits, r->sort_scratch, st,
-                                 n_entries_dev);
-    launches += launch_build_entries(b, entry_bound, n_entries_dev, r->list_keys.ptr, r->list_vals.ptr,
-                                     r->tile_word.ptr, r->tile_fill_pos.ptr, r->entries.ptr, r->fb_start.ptr,
-                                     r->fb_end.ptr, r->counters.ptr + C_VISIBLE_FILLS, st);
+    launches += launch_list_emit(b, r->tile_fb.ptr, r->tile_word.ptr, r->tile_fill_pos.ptr, r->fb_start.ptr,
+                                 r->fb_cursor.ptr, r->entries.ptr, entry_bound, r->counters.ptr + C_VISIBLE_FILLS, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[5], st));
 
     // ---- fill + tile (fused).
     CompositeArgs ca{};
     ca.entries = r->entries.ptr;
     ca.fb_start = r->fb_start.ptr;
-    ca.fb_end = r->fb_end.ptr;
+    ca.fb_count = r->fb_count.ptr;
     ca.fills = r->fills.ptr;
     ca.paints = r->paints.ptr;
     ca.area_lut = r->lut_tex;
@@ -849,12 +827,12 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
             const FbRect fb = framebuffer_tile_rect(r);
             const uint32_t n_fb = (uint32_t)((fb.max_x - fb.min_x) * (fb.max_y - fb.min_y));
             r->fb_start.ensure(n_fb + 1);
-            r->fb_end.ensure(n_fb + 1);
+            r->fb_count.ensure(n_fb + 1);
             PF_CUDA_CHECK(cudaMemsetAsync(r->fb_start.ptr, 0, (size_t)n_fb * 4, r->stream));
-            PF_CUDA_CHECK(cudaMemsetAsync(r->fb_end.ptr, 0, (size_t)n_fb * 4, r->stream));
+            PF_CUDA_CHECK(cudaMemsetAsync(r->fb_count.ptr, 0, (size_t)n_fb * 4, r->stream));
             CompositeArgs ca{};
             ca.fb_start = r->fb_start.ptr;
-            ca.fb_end = r->fb_end.ptr;
+            ca.fb_count = r->fb_count.ptr;
             ca.fb = fb;
             ca.tile_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
             ca.tile_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
@@ -1007,7 +985,8 @@ int64_t PFCudaRendererDebugCopyTiles(PFCudaRendererRef r, PFTileObjectPrimitive 
     return guarded_count(r, [&]() -> int64_t {
         ensure_alpha_ids(r);
         const BatchDev &b = r->last_batch;
-        // tile_fb / tile_pos are free again after the sort stage: reuse them as flags / positions.
+        // tile_fb is free again after the sort stage: reuse it for the non-empty flags.
+        r->tile_pos.ensure(b.n_tiles + 1, 1.25);
         launch_dump_tile_flags(b.n_tiles, r->tile_word.ptr, r->tile_fb.ptr, r->stream);
         exclusive_scan(LoadU32{r->tile_fb.ptr}, r->tile_pos.ptr, b.n_tiles, r->counters.ptr + 4, r->scan_scratch, r->stream);
         size_t n = b.n_tiles ? read_counter(r, 4) : 0;
