@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(128) k_bin(BatchDev b, BinArgs a) {
     const int rect_w = path.max_x - path.min_x, rect_h = path.max_y - path.min_y;
 
     uint32_t emitted = 0;
-    const uint32_t out_base = EMIT ? __ldg(a.line_fill_offset + l) : 0;
+    const uint32_t out_base = (EMIT && a.line_fill_offset) ? __ldg(a.line_fill_offset + l) : 0;
 
     // ObjectBuilder::add_fill (renderer/src/builder.rs:509-553)
     auto add_fill = [&](float2 from, float2 to, int tx, int ty) {
@@ -261,12 +261,18 @@ __global__ void __launch_bounds__(128) k_bin(BatchDev b, BinArgs a) {
         if (!EMIT) {
             atomicAdd(a.tile_word + t, 1u);
         } else {
-            uint32_t e = out_base + emitted;
-            uint32_t pos = atomicAdd(a.tile_fill_pos + t, 1u);
             uint32_t from_w = (uint32_t)fx | ((uint32_t)fy << 16), to_w = (uint32_t)tx8 | ((uint32_t)ty8 << 16);
-            if (pos < a.fill_capacity) a.fills[pos] = make_uint2(from_w, to_w);
-            if (a.tile_first_fill) atomicMin(a.tile_first_fill + t, e);
-            if (a.fills_emit && e < a.fill_capacity) a.fills_emit[e] = EmitFill{from_w, to_w, t};
+            // Occlusion culling before fill emission: tiles that lost the z-test (or lie outside
+            // the framebuffer) get no space in the tile-grouped array.
+            if (!a.tile_fb || __ldg(a.tile_fb + t) != 0xffffffffu) {
+                uint32_t pos = atomicAdd(a.tile_fill_pos + t, 1u);
+                if (pos < a.fill_capacity) a.fills[pos] = make_uint2(from_w, to_w);
+            }
+            if (a.fills_emit) { // parity dumps: every fill, in emission order
+                uint32_t e = out_base + emitted;
+                atomicMin(a.tile_first_fill + t, e);
+                if (e < a.emit_capacity) a.fills_emit[e] = EmitFill{from_w, to_w, t};
+            }
         }
         emitted++;
     };
@@ -340,7 +346,7 @@ __global__ void __launch_bounds__(128) k_bin(BatchDev b, BinArgs a) {
             last_step = next_step;
         }
     }
-    if (!EMIT) a.line_fill_count[l] = emitted;
+    if (!EMIT && a.line_fill_count) a.line_fill_count[l] = emitted;
 }
 
 int launch_bin(bool emit, const BatchDev &b, const BinArgs &args, cudaStream_t stream) {
@@ -350,6 +356,23 @@ int launch_bin(bool emit, const BatchDev &b, const BinArgs &args, cudaStream_t s
         k_bin<true><<<grid, 128, 0, stream>>>(b, args);
     else
         k_bin<false><<<grid, 128, 0, stream>>>(b, args);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+// Sum of the per-tile fill counts (RenderStats.fill_count), computed on demand.
+__global__ void __launch_bounds__(256) k_sum_fill_counts(const uint32_t *__restrict__ tile_word, uint32_t n_tiles,
+                                                         unsigned long long *__restrict__ total) {
+    unsigned long long sum = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_tiles; i += (size_t)gridDim.x * blockDim.x)
+        sum += tile_word[i] & 0x00ffffffu;
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(total, sum);
+}
+int launch_sum_fill_counts(const uint32_t *tile_word, uint32_t n_tiles, unsigned long long *total, cudaStream_t stream) {
+    if (n_tiles == 0) return 0;
+    unsigned grid = div_up(n_tiles, 256 * 8);
+    k_sum_fill_counts<<<grid < 1184 ? grid : 1184, 256, 0, stream>>>(tile_word, n_tiles, total);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

@@ -78,19 +78,24 @@ struct BinArgs {
     const uint32_t *line_path;
     uint32_t n_lines;            // host-side bound (grid size)
     const uint32_t *n_lines_dev; // optional: actual count on the device, min(*n_lines_dev, n_lines) is used
-    uint32_t *tile_word;      // count (24) | backdrop delta (8)
+    uint32_t *tile_word;         // count (24) | backdrop delta (8)
     int32_t *col_backdrop;
     // count pass
-    uint32_t *line_fill_count;
-    // emit pass
-    const uint32_t *line_fill_offset;
-    uint32_t *tile_fill_pos;  // running cursor, initialised with the exclusive scan of counts
-    PackedFill *fills;        // tile-grouped
+    uint32_t *line_fill_count;   // optional (parity dumps): fills per line, for emission-order offsets
+    // emit pass (runs after propagate + z-cull)
+    const uint32_t *tile_fb;     // 0xffffffff = tile culled: its fills are not stored (NULL: store all)
+    uint32_t *tile_fill_pos;     // running cursor, initialised with the exclusive scan of live counts
+    PackedFill *fills;           // tile-grouped, surviving tiles only
     uint32_t fill_capacity;
-    uint32_t *tile_first_fill; // optional (parity dumps): min emission index per tile
-    EmitFill *fills_emit;      // optional (parity dumps): fills in emission order
+    // parity dumps only (all three or none)
+    const uint32_t *line_fill_offset;
+    uint32_t *tile_first_fill;   // min emission index per tile
+    EmitFill *fills_emit;        // every fill in emission order
+    uint32_t emit_capacity;
 };
 int launch_bin(bool emit, const BatchDev &b, const BinArgs &args, cudaStream_t stream);
+
+int launch_sum_fill_counts(const uint32_t *tile_word, uint32_t n_tiles, unsigned long long *total, cudaStream_t stream);
 
 int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_backdrop, int32_t *z_buffer,
                      cudaStream_t stream);

@@ -58,7 +58,7 @@ struct BatchCache {
     BatchDev batch{};
     bool has_initial_backdrops = false;
     bool counts_valid = false; // n_lines / n_fills / n_entries hold the last frame's totals
-    uint32_t n_lines = 0, n_fills = 0, n_entries = 0;
+    uint32_t n_lines = 0, n_fills = 0, n_entries = 0, n_visible_fills = 0;
 };
 
 struct StageTimer {
@@ -235,11 +235,11 @@ float4 clear_color(const PFCudaRenderer *r) {
 
 uint32_t read_counter(PFCudaRenderer *r, int index) {
     r->counters_host.ensure(16);
-    PF_CUDA_CHECK(cudaMemcpyAsync(r->counters_host.ptr, r->counters.ptr + index, sizeof(uint32_t),
+    PF_CUDA_CHECK(cudaMemcpyAsync(r->counters_host.ptr, r->counters.ptr, 8 * sizeof(uint32_t),
                                   cudaMemcpyDeviceToHost, r->stream));
     PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
     r->stats.host_sync_count++;
-    return r->counters_host.ptr[0];
+    return r->counters_host.ptr[index];
 }
 
 void upload_segments(PFCudaRenderer *r, SceneSegments &dst, const PFSegmentsD3D11 &src) {
@@ -454,15 +454,17 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
         line_bound = n_segments ? read_counter(r, C_LINES) : 0;
         r->lines.ensure(line_bound + 1, 1.25);
         r->line_path.ensure(line_bound + 1, 1.25);
-        r->line_fill_offset.ensure(line_bound + 1, 1.25);
+        if (r->debug_lists) r->line_fill_offset.ensure(line_bound + 1, 1.25);
     } else {
-        line_bound = bound_of(c.n_lines, std::min(r->lines.capacity, std::min(r->line_path.capacity, r->line_fill_offset.capacity)));
+        size_t cap = std::min(r->lines.capacity, r->line_path.capacity);
+        if (r->debug_lists) cap = std::min(cap, r->line_fill_offset.capacity);
+        line_bound = bound_of(c.n_lines, cap);
     }
     const uint32_t *n_lines_dev = r->counters.ptr + C_LINES;
     launches += launch_dice(true, b, nullptr, r->seg_line_offset.ptr, r->lines.ptr, r->line_path.ptr, line_bound, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[2], st));
 
-    // ---- bin: count (+ backdrop deltas) -> scans -> emit into tile-grouped runs.
+    // ---- bin, count pass: per-tile fill counts + backdrop deltas.
     BinArgs ba{};
     ba.lines = r->lines.ptr;
     ba.line_path = r->line_path.ptr;
@@ -470,29 +472,11 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     ba.n_lines_dev = n_lines_dev;
     ba.tile_word = r->tile_word.ptr;
     ba.col_backdrop = r->col_backdrop.ptr;
-    ba.line_fill_count = r->line_fill_offset.ptr;
+    ba.line_fill_count = r->debug_lists ? r->line_fill_offset.ptr : nullptr;
     launches += launch_bin(false, b, ba, st);
-    launches += exclusive_scan(LoadU32{r->line_fill_offset.ptr}, r->line_fill_offset.ptr, line_bound,
-                               r->counters.ptr + C_FILLS, r->scan_scratch, st, n_lines_dev);
-    launches += exclusive_scan(LoadLow24{r->tile_word.ptr}, r->tile_fill_pos.ptr, n_tiles, nullptr,
-                               r->scan_scratch, st);
-    uint32_t fill_bound;
-    if (sizing) {
-        fill_bound = line_bound ? read_counter(r, C_FILLS) : 0;
-        r->fills.ensure(fill_bound + 1, 1.25);
-        if (r->debug_lists) r->fills_emit.ensure(fill_bound + 1, 1.25);
-    } else {
-        size_t cap = r->fills.capacity;
-        if (r->debug_lists) cap = std::min(cap, r->fills_emit.capacity);
-        fill_bound = bound_of(c.n_fills, cap);
-    }
-    ba.line_fill_offset = r->line_fill_offset.ptr;
-    ba.tile_fill_pos = r->tile_fill_pos.ptr;
-    ba.fills = r->fills.ptr;
-    ba.fill_capacity = fill_bound;
-    ba.tile_first_fill = r->debug_lists ? r->tile_first_fill.ptr : nullptr;
-    ba.fills_emit = r->debug_lists ? r->fills_emit.ptr : nullptr;
-    launches += launch_bin(true, b, ba, st);
+    if (r->debug_lists) // emission-order offsets (and the total fill count), only needed for the parity dumps
+        launches += exclusive_scan(LoadU32{r->line_fill_offset.ptr}, r->line_fill_offset.ptr, line_bound,
+                                   r->counters.ptr + C_FILLS, r->scan_scratch, st, n_lines_dev);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[3], st));
 
     // ---- propagate: column backdrop prefix sums + occluder z-writes.
@@ -504,16 +488,48 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     launches += launch_list_count(b, r->tile_word.ptr, r->z_buffer.ptr, r->tile_fb.ptr, r->fb_count.ptr, st);
     launches += exclusive_scan(LoadU32{r->fb_count.ptr}, r->fb_start.ptr, n_fb, r->counters.ptr + C_ENTRIES,
                                r->scan_scratch, st);
-    uint32_t entry_bound;
+    // Fill runs only for tiles that survived the cull (occlusion culling before fill emission).
+    // With the parity dumps on, every alpha tile keeps its fills so its mask can be read back.
+    if (r->debug_lists)
+        launches += exclusive_scan(LoadLow24{r->tile_word.ptr}, r->tile_fill_pos.ptr, n_tiles,
+                                   r->counters.ptr + C_VISIBLE_FILLS, r->scan_scratch, st);
+    else
+        launches += exclusive_scan(LoadLiveCount{r->tile_word.ptr, r->tile_fb.ptr}, r->tile_fill_pos.ptr, n_tiles,
+                                   r->counters.ptr + C_VISIBLE_FILLS, r->scan_scratch, st);
+    uint32_t entry_bound, fill_bound, emit_bound = 0;
     if (sizing) {
-        entry_bound = n_tiles ? read_counter(r, C_ENTRIES) : 0;
+        if (n_tiles) read_counter(r, 0); // one read-back of all three totals
+        entry_bound = n_tiles ? r->counters_host.ptr[C_ENTRIES] : 0;
+        fill_bound = n_tiles ? r->counters_host.ptr[C_VISIBLE_FILLS] : 0;
         r->entries.ensure(entry_bound + 1, 1.25);
+        r->fills.ensure(fill_bound + 1, 1.25);
+        if (r->debug_lists) {
+            emit_bound = n_tiles ? r->counters_host.ptr[C_FILLS] : 0;
+            r->fills_emit.ensure(emit_bound + 1, 1.25);
+        }
     } else {
         entry_bound = bound_of(c.n_entries, r->entries.capacity);
+        fill_bound = bound_of(c.n_visible_fills, r->fills.capacity);
+        if (r->debug_lists) emit_bound = bound_of(c.n_fills, r->fills_emit.capacity);
     }
-    launches += launch_list_emit(b, r->tile_fb.ptr, r->tile_word.ptr, r->tile_fill_pos.ptr, r->fb_start.ptr,
-                                 r->fb_cursor.ptr, r->entries.ptr, entry_bound, r->counters.ptr + C_VISIBLE_FILLS, st);
+
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[5], st));
+
+    // ---- bin, emit pass: fills of surviving tiles into their tile-grouped runs.
+    ba.tile_fb = r->debug_lists ? nullptr : r->tile_fb.ptr;
+    ba.tile_fill_pos = r->tile_fill_pos.ptr;
+    ba.fills = r->fills.ptr;
+    ba.fill_capacity = fill_bound;
+    if (r->debug_lists) {
+        ba.line_fill_offset = r->line_fill_offset.ptr;
+        ba.tile_first_fill = r->tile_first_fill.ptr;
+        ba.fills_emit = r->fills_emit.ptr;
+        ba.emit_capacity = emit_bound;
+    }
+    launches += launch_bin(true, b, ba, st);
+    launches += launch_list_emit(b, r->tile_fb.ptr, r->tile_word.ptr, r->tile_fill_pos.ptr, r->fb_start.ptr,
+                                 r->fb_cursor.ptr, r->entries.ptr, entry_bound, nullptr, st);
+    if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[6], st));
 
     // ---- fill + tile (fused).
     CompositeArgs ca{};
@@ -533,7 +549,7 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     ca.clear_color = clear_color(r);
     ca.load_dest = r->batches_drawn > 0;
     launches += launch_composite(ca, st);
-    if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[6], st));
+    if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[7], st));
 
     // ---- verification: one read-back of the totals at the end of the batch.
     r->counters_host.ensure(16);
@@ -541,12 +557,14 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     PF_CUDA_CHECK(cudaStreamSynchronize(st));
     r->stats.host_sync_count++;
     const uint32_t n_lines = r->counters_host.ptr[C_LINES], n_fills = r->counters_host.ptr[C_FILLS],
-                   n_entries = r->counters_host.ptr[C_ENTRIES];
+                   n_entries = r->counters_host.ptr[C_ENTRIES], n_visible = r->counters_host.ptr[C_VISIBLE_FILLS];
     r->stats.drawcall_count += (uint64_t)launches;
     c.n_lines = n_lines;
     c.n_fills = n_fills;
     c.n_entries = n_entries;
-    if (n_lines > line_bound || n_fills > fill_bound || n_entries > entry_bound) {
+    c.n_visible_fills = n_visible;
+    if (n_lines > line_bound || n_visible > fill_bound || n_entries > entry_bound ||
+        (r->debug_lists && n_fills > emit_bound)) {
         c.counts_valid = false;
         return false;
     }
@@ -559,25 +577,25 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     r->last_alpha_ids_valid = false;
     r->last_fb = fb;
     r->stats.path_count += b.n_paths;
-    r->stats.fill_count += n_fills;
+    r->stats.fill_count += n_fills; // 0 unless debug lists are on; PFCudaRendererGetStats fills it in lazily
     r->stats.total_tile_count += n_tiles;
     r->stats.input_segment_count += n_segments;
     r->stats.line_segment_count += n_lines;
     r->stats.tile_list_entry_count += n_entries;
-    r->stats.visible_fill_count += r->counters_host.ptr[C_VISIBLE_FILLS];
+    r->stats.visible_fill_count += n_visible;
     r->stats.column_count += n_cols;
 
     if (r->timing) {
-        float ms[6];
-        for (int i = 0; i < 6; i++) PF_CUDA_CHECK(cudaEventElapsedTime(&ms[i], r->timer.ev[i], r->timer.ev[i + 1]));
+        float ms[7];
+        for (int i = 0; i < 7; i++) PF_CUDA_CHECK(cudaEventElapsedTime(&ms[i], r->timer.ev[i], r->timer.ev[i + 1]));
         r->times.bound_ms += ms[0];
         r->times.dice_ms += ms[1];
-        r->times.bin_ms += ms[2];
+        r->times.bin_ms += ms[2] + ms[5]; // count pass + emit pass (the emit pass runs after the z-cull)
         r->times.propagate_ms += ms[3];
         r->times.sort_ms += ms[4];
-        r->times.fill_tile_ms += ms[5];
+        r->times.fill_tile_ms += ms[6];
         float total;
-        PF_CUDA_CHECK(cudaEventElapsedTime(&total, r->timer.ev[0], r->timer.ev[6]));
+        PF_CUDA_CHECK(cudaEventElapsedTime(&total, r->timer.ev[0], r->timer.ev[7]));
         r->times.total_ms += total;
     }
     return true;
@@ -934,6 +952,16 @@ PFCudaStatus PFSceneBuildAndRenderCuda(PFSceneRef scene, PFCudaRendererRef r, PF
 PFCudaStatus PFCudaRendererGetStats(PFCudaRendererRef r, PFCudaRenderStats *stats) {
     return guarded(r, [&]() {
         if (!stats) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null stats");
+        if (r->stats.fill_count == 0 && r->batches_drawn == 1 && !r->in_scene && r->last_batch.n_tiles) {
+            // RenderStats.fill_count (all fills, before occlusion culling): summed on demand.
+            unsigned long long *total = reinterpret_cast<unsigned long long *>(r->counters.ptr + 8);
+            PF_CUDA_CHECK(cudaMemsetAsync(total, 0, sizeof(*total), r->stream));
+            launch_sum_fill_counts(r->tile_word.ptr, r->last_batch.n_tiles, total, r->stream);
+            unsigned long long host_total = 0;
+            PF_CUDA_CHECK(cudaMemcpyAsync(&host_total, total, sizeof(host_total), cudaMemcpyDeviceToHost, r->stream));
+            PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+            r->stats.fill_count = host_total;
+        }
         *stats = r->stats;
         if (r->debug_lists && r->batches_drawn > 0 && !r->in_scene) {
             ensure_alpha_ids(r);
@@ -954,7 +982,10 @@ PFCudaStatus PFCudaRendererGetTimes(PFCudaRendererRef r, PFCudaRenderTime *times
 }
 
 PFCudaStatus PFCudaRendererSetDebugListsEnabled(PFCudaRendererRef r, int32_t enabled) {
-    return guarded(r, [&]() { r->debug_lists = enabled != 0; });
+    return guarded(r, [&]() {
+        r->debug_lists = enabled != 0;
+        r->cache.counts_valid = false; // the dump buffers must be sized on the next frame
+    });
 }
 
 int64_t PFCudaRendererDebugCopyLines(PFCudaRendererRef r, float *out_lines, uint32_t *out_paths, size_t cap) {

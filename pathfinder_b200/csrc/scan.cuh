@@ -158,6 +158,13 @@ struct LoadLow24 {
     const uint32_t *p;
     __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return p[i] & 0x00ffffffu; }
 };
+// Fill count of tiles that survived the z-cull (tile_fb != invalid), else 0.
+struct LoadLiveCount {
+    const uint32_t *word, *tile_fb;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+        return tile_fb[i] != 0xffffffffu ? (word[i] & 0x00ffffffu) : 0u;
+    }
+};
 struct LoadNotInvalid {
     const uint32_t *p;
     __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return p[i] != 0xffffffffu ? 1u : 0u; }

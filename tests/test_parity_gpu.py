@@ -47,7 +47,16 @@ def check_scene(flat, xf, area_lut, size=None, background=(1.0, 1.0, 1.0, 1.0), 
     ref_img = built.render(area_lut, w, h, background=background or (0.0, 0.0, 0.0, 0.0))
     diff = np.abs(img.astype(np.int32) - ref_img.astype(np.int32))
     assert diff.max() <= RGBA_TOL, f"max RGBA diff {diff.max()} at {np.unravel_index(diff.argmax(), diff.shape)}"
-    return r, img, built
+
+    # The production configuration (no stage lists kept, fills of z-culled tiles never stored) must
+    # give the same frame byte for byte, first in sizing mode and again from the cached batch.
+    r2, img2 = H.cuda_render(flat, xf, size=size, background=background, debug=False)
+    assert np.array_equal(img2, img), "production path differs from the instrumented path"
+    scene_stats = r2.stats()
+    assert scene_stats["fill_count"] == len(built.fills)
+    r.close()
+    r2.close()
+    return img, built
 
 
 def test_single_triangle(area_lut):
@@ -138,3 +147,62 @@ def test_matches_golden_tiles(area_lut):
     tiles = np.load(os.path.join(g, "tiger256_tiles.npy"))
     H.assert_records_equal(r.debug_fills(), fills, "fills vs golden")
     H.assert_records_equal(r.debug_tiles(), tiles, "tiles vs golden")
+
+
+def test_cached_batch_and_strips_are_byte_identical(area_lut):
+    """Steady state (batch cache hit, device-side counts) and the 4-strip partition reproduce the
+    full single-pass frame exactly; the union of the strips' tile lists equals the full list."""
+    from pathfinder_b200 import api
+    flat = scenes.random_paths(1500, 512, 11, r_min=8.0, r_max=80.0)
+    r = api.CudaRenderer((512, 512), background_color=(1, 1, 1, 1))
+    scene = api.Scene.from_flat(flat)
+    opts = api.BuildOptions()
+    scene.build_and_render(r, opts)
+    first = r.read_pixels()
+    assert r.stats()["batch_cache_hits"] == 0 and r.stats()["host_sync_count"] >= 2
+    scene.build_and_render(r, opts)
+    second = r.read_pixels()
+    s = r.stats()
+    assert s["batch_cache_hits"] == 1 and s["host_sync_count"] == 1 and s["h2d_bytes"] == 0
+    assert np.array_equal(first, second)
+
+    full_tiles = None
+    r.set_debug_lists_enabled(True)
+    scene.build_and_render(r, opts)
+    full_tiles = r.debug_tiles()
+    stitched = np.zeros_like(first)
+    parts = []
+    for y0, y1 in [(0, 8), (8, 16), (16, 24), (24, 32)]:
+        rs = api.CudaRenderer((512, 512), background_color=(1, 1, 1, 1))
+        rs.set_debug_lists_enabled(True)
+        rs.set_strip(y0, y1)
+        scene.build_and_render(rs, opts)
+        img = rs.read_pixels()
+        stitched[y0 * 16:y1 * 16] = img[y0 * 16:y1 * 16]
+        parts.append(rs.debug_tiles())
+        rs.close()
+    assert np.array_equal(stitched, first)
+    key = lambda t: (int(t["path_id"]), int(t["tile_y"]), int(t["tile_x"]), int(t["backdrop"]), int(t["alpha_tile_id"] == 0xFFFFFFFF))
+    assert sorted(key(t) for p in parts for t in p) == sorted(key(t) for t in full_tiles)
+    r.close()
+
+
+def test_wrong_level_commands_are_rejected():
+    """Renderer::require_d3d11 (gpu/renderer.rs:1349-1360): D3D9 commands panic at the D3D11 level."""
+    from pathfinder_b200 import _lib as L
+    from pathfinder_b200 import api
+    r = api.CudaRenderer((64, 64))
+    r.begin_scene()
+    for kind in (L.PF_RENDER_COMMAND_ADD_FILLS_D3D9, L.PF_RENDER_COMMAND_FLUSH_FILLS_D3D9, L.PF_RENDER_COMMAND_DRAW_TILES_D3D9):
+        cmd = L.PFRenderCommand()
+        cmd.kind = kind
+        with pytest.raises(L.PathfinderCudaError) as e:
+            r.render_command(cmd)
+        assert e.value.status == L.PF_CUDA_ERROR_WRONG_LEVEL
+    r.end_scene()
+    with pytest.raises(L.PathfinderCudaError) as e:
+        r.end_scene()
+    assert e.value.status == L.PF_CUDA_ERROR_PROTOCOL
+    with pytest.raises(L.PathfinderCudaError):
+        api.CudaRenderer((64, 64), level=api.RendererLevel.D3D9)
+    r.close()
