@@ -523,37 +523,41 @@ constexpr float COV_MAGIC = 384.0f;
 constexpr uint32_t COV_MAGIC_BITS = 0x43c00000u;
 constexpr float COV_SCALE = 1.0f / 32768.0f;
 
-// computeCoverage (shaders/fill_area.inc.glsl:11-27) for the 4-row strip whose first pixel centre
-// is (cx, cy) in tile space; acc[k] accumulates row k.
-__device__ __forceinline__ void accumulate_fill(PackedFill f, float cx, float cy, cudaTextureObject_t lut,
-                                                uint32_t acc[4]) {
+// computeCoverage (shaders/fill_area.inc.glsl:11-27) for one pixel column and NS vertically
+// adjacent 4-row strips: (cx, cy) is the centre of the first pixel of the first strip in tile
+// space. Everything that depends only on x (window, dX, t) is computed once per column; each strip
+// costs one LUT fetch (4 rows per texel) and four multiply-adds. Returns false when the column is
+// outside the segment's x range (the LUT term is multiplied by dX = 0 in the reference).
+template <int NS>
+__device__ __forceinline__ bool accumulate_fill(uint32_t from_w, uint32_t to_w, float cx, float cy,
+                                                cudaTextureObject_t lut, uint32_t (&acc)[NS][4]) {
     const float s = 1.0f / 256.0f;
-    float from_x = fmaf((float)(f.x & 0xffffu), s, -cx), to_x = fmaf((float)(f.y & 0xffffu), s, -cx);
+    float from_x = fmaf((float)(from_w & 0xffffu), s, -cx), to_x = fmaf((float)(to_w & 0xffffu), s, -cx);
     float wx = fminf(fmaxf(from_x, -0.5f), 0.5f), wy = fminf(fmaxf(to_x, -0.5f), 0.5f);
     float dX = wx - wy;
-    if (dX == 0.0f) { // the pixel column is outside the segment's x range: LUT * 0
-#pragma unroll
-        for (int k = 0; k < 4; k++) acc[k] += COV_MAGIC_BITS;
-        return;
-    }
-    float from_y = fmaf((float)(f.x >> 16), s, -cy), to_y = fmaf((float)(f.y >> 16), s, -cy);
+    if (dX == 0.0f) return false;
+    float from_y = fmaf((float)(from_w >> 16), s, -cy), to_y = fmaf((float)(to_w >> 16), s, -cy);
     bool from_left = from_x < to_x;
     float lx = from_left ? from_x : to_x, ly = from_left ? from_y : to_y;
     float rx = from_left ? to_x : from_x, ry = from_left ? to_y : from_y;
     float inv = __fdividef(1.0f, rx - lx);
-    float offset = 0.5f * (wx + wy) - lx;
-    float t = offset * inv;
+    float t = (0.5f * (wx + wy) - lx) * inv;
     float y = fmaf(ry - ly, t, ly);
-    float d = (ry - ly) * inv;
-    float4 tex = tex2D<float4>(lut, (y + 8.0f) * (1.0f / 16.0f), fabsf(d * dX) * (1.0f / 16.0f));
-    acc[0] += __float_as_uint(fmaf(tex.x, dX, COV_MAGIC));
-    acc[1] += __float_as_uint(fmaf(tex.y, dX, COV_MAGIC));
-    acc[2] += __float_as_uint(fmaf(tex.z, dX, COV_MAGIC));
-    acc[3] += __float_as_uint(fmaf(tex.w, dX, COV_MAGIC));
+    float v = fabsf((ry - ly) * inv * dX) * (1.0f / 16.0f);
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        // the strip k rows lower sees the segment 4k px higher: y - 4k
+        float4 tex = tex2D<float4>(lut, (y + (8.0f - 4.0f * (float)k)) * (1.0f / 16.0f), v);
+        acc[k][0] += __float_as_uint(fmaf(tex.x, dX, COV_MAGIC));
+        acc[k][1] += __float_as_uint(fmaf(tex.y, dX, COV_MAGIC));
+        acc[k][2] += __float_as_uint(fmaf(tex.z, dX, COV_MAGIC));
+        acc[k][3] += __float_as_uint(fmaf(tex.w, dX, COV_MAGIC));
+    }
+    return true;
 }
 
-__device__ __forceinline__ float finish_coverage(uint32_t acc, uint32_t count) {
-    return (float)(int32_t)(acc - count * COV_MAGIC_BITS) * COV_SCALE;
+__device__ __forceinline__ float finish_coverage(uint32_t acc, uint32_t contributions) {
+    return (float)(int32_t)(acc - contributions * COV_MAGIC_BITS) * COV_SCALE;
 }
 
 // sampleMask (shaders/tile_fragment.inc.glsl:539-556) on coverage = mask + backdrop.
@@ -569,38 +573,65 @@ __device__ __forceinline__ float mask_alpha(float coverage, uint32_t ctrl) {
     return fminf(1.0f, coverage);
 }
 
+// clamp to [0,1], scale by 255, round to nearest even: the integer lands in the low mantissa bits
+// of x * 255 + 2^23 (no F2I on the slow pipe), then the four bytes are packed with PRMT.
 __device__ __forceinline__ uint32_t pack_rgba8(float4 c) {
-    uint32_t R = __float2uint_rn(__saturatef(c.x) * 255.0f), G = __float2uint_rn(__saturatef(c.y) * 255.0f);
-    uint32_t B = __float2uint_rn(__saturatef(c.z) * 255.0f), A = __float2uint_rn(__saturatef(c.w) * 255.0f);
-    return R | (G << 8) | (B << 16) | (A << 24);
+    const float magic = 8388608.0f;
+    uint32_t r = __float_as_uint(fmaf(__saturatef(c.x), 255.0f, magic));
+    uint32_t g = __float_as_uint(fmaf(__saturatef(c.y), 255.0f, magic));
+    uint32_t b = __float_as_uint(fmaf(__saturatef(c.z), 255.0f, magic));
+    uint32_t a = __float_as_uint(fmaf(__saturatef(c.w), 255.0f, magic));
+    uint32_t rg = __byte_perm(r, g, 0x0040); // bytes: r0, g0, 0, 0
+    uint32_t ba = __byte_perm(b, a, 0x0040);
+    return __byte_perm(rg, ba, 0x5410);
 }
 
-__device__ __forceinline__ void group_barrier(int group) {
-    // named barrier per 64-thread tile group (barrier 0 is __syncthreads)
-    asm volatile("bar.sync %0, 64;" ::"r"(group + 1) : "memory");
+// dest = dest * (1 - a) + src with premultiplied src (shaders/d3d11/tile.cs.glsl:155).
+__device__ __forceinline__ void blend(float4 &d, float4 base, float alpha) {
+    float ia = 1.0f - alpha;
+    d.x = fmaf(d.x, ia, base.x * alpha);
+    d.y = fmaf(d.y, ia, base.y * alpha);
+    d.z = fmaf(d.z, ia, base.z * alpha);
+    d.w = fmaf(d.w, ia, alpha);
 }
 
-// One 64-thread group per framebuffer tile: thread (x, strip) owns column x, rows 4*strip..+3,
-// exactly the 16x4 workgroup of shaders/d3d11/tile.cs.glsl:22 — but the mask never leaves
-// registers: fill (coverage) and tile (composite) are one kernel.
-constexpr int COMPOSITE_TILES_PER_BLOCK = 4;
-constexpr int COMPOSITE_SORT_CAP = 256; // entries sorted in shared memory; longer lists use the slow path
+// One warp per framebuffer tile: lane (x, half) owns column x, rows 8*half .. 8*half+7 (two of the
+// 4-row strips of shaders/d3d11/tile.cs.glsl:22). Fill (coverage) and tile (composite) are one
+// kernel — the mask never leaves registers. Entries and fills are loaded cooperatively (lane i
+// loads element i) and broadcast with shuffles / shared memory. While every entry drawn so far is a
+// solid tile the whole tile has one colour, so a single pixel is blended per lane ("uniform"
+// prefix); per-pixel state is only expanded at the first tile that has fills.
+constexpr int COMPOSITE_WARPS = 2;       // tiles per block, horizontally adjacent
+constexpr int COMPOSITE_SORT_CAP = 128;  // entries sorted in shared memory; longer lists use the slow path
 
-__global__ void __launch_bounds__(64 * COMPOSITE_TILES_PER_BLOCK) k_composite(CompositeArgs a) {
-    __shared__ uint4 s_entries[COMPOSITE_TILES_PER_BLOCK][COMPOSITE_SORT_CAP];
-    __shared__ uint32_t s_keys[COMPOSITE_TILES_PER_BLOCK][COMPOSITE_SORT_CAP];
-    __shared__ uint32_t s_min[COMPOSITE_TILES_PER_BLOCK][2];
+template <bool LOAD_DEST>
+__global__ void __launch_bounds__(32 * COMPOSITE_WARPS) k_composite(CompositeArgs a) {
+    __shared__ uint4 s_entries[COMPOSITE_WARPS][COMPOSITE_SORT_CAP];
+    __shared__ float4 s_paints[COMPOSITE_WARPS][COMPOSITE_SORT_CAP];
+    __shared__ uint32_t s_keys[COMPOSITE_WARPS][COMPOSITE_SORT_CAP];
 
-    const int group = threadIdx.x >> 6, tid = threadIdx.x & 63;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fb_w = a.fb.max_x - a.fb.min_x;
-    const int tiles_x_groups = (fb_w + COMPOSITE_TILES_PER_BLOCK - 1) / COMPOSITE_TILES_PER_BLOCK;
-    const int tile_col = (blockIdx.x % tiles_x_groups) * COMPOSITE_TILES_PER_BLOCK + group;
-    const int tile_row = a.tile_y0 + blockIdx.x / tiles_x_groups; // absolute tile y
-    if (tile_col >= fb_w) return; // whole group exits together
-    const int tx = a.fb.min_x + tile_col, ty = tile_row;
-    const int x = tid & 15, strip = tid >> 4;
-    const int px = tx * 16 + x, py0 = ty * 16 + strip * 4;
-    const bool px_ok = px >= 0 && px < a.dest_w;
+    const uint32_t n_work = (uint32_t)fb_w * (uint32_t)(a.tile_y1 - a.tile_y0);
+    // Persistent warps: tiles differ wildly in depth, so every warp pulls its next tile from a
+    // global counter instead of owning a fixed one (row-major, so neighbours stay neighbours).
+    for (;;) {
+    uint32_t work = 0;
+    if (lane == 0) work = atomicAdd(a.work_counter, 1u);
+    work = __shfl_sync(0xffffffffu, work, 0);
+    if (work >= n_work) return;
+    const int tile_col = (int)(work % (uint32_t)fb_w);
+    const int ty = a.tile_y0 + (int)(work / (uint32_t)fb_w); // absolute tile y
+    const int tx = a.fb.min_x + tile_col;
+    const int x = lane & 15, half = lane >> 4;
+    const int px = tx * 16 + x, py0 = ty * 16 + half * 8;
+    // Rows of this lane that exist in the destination image (bit k = row py0 + k).
+    uint32_t row_mask = 0;
+    if (px >= 0 && px < a.dest_w) {
+        int lo = max(0, -py0), hi = min(8, a.dest_h - py0);
+        row_mask = hi > lo ? ((0xffu >> (8 - hi)) & (0xffu << lo)) : 0u;
+    }
+    uint8_t *out = a.dest + (ptrdiff_t)py0 * (ptrdiff_t)a.dest_pitch + (ptrdiff_t)px * 4;
 
     const int fy = ty - a.fb.min_y;
     uint32_t e0 = 0, n = 0;
@@ -610,102 +641,126 @@ __global__ void __launch_bounds__(64 * COMPOSITE_TILES_PER_BLOCK) k_composite(Co
         e0 = __ldg(a.fb_start + fbi);
     }
 
-    float4 dst[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int py = py0 + k;
-        if (a.load_dest && px_ok && py >= 0 && py < a.dest_h) {
-            uint32_t v = *reinterpret_cast<const uint32_t *>(a.dest + (size_t)py * a.dest_pitch + (size_t)px * 4);
-            const float s = 1.0f / 255.0f;
-            dst[k] = make_float4((float)(v & 0xff) * s, (float)((v >> 8) & 0xff) * s, (float)((v >> 16) & 0xff) * s,
-                                 (float)(v >> 24) * s);
+    // ---- bring the run into draw order: rank sort by tile index in shared memory ----
+    const bool in_smem = n <= COMPOSITE_SORT_CAP;
+    if (in_smem && n > 0) {
+        if (n == 1) {
+            if (lane == 0) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0));
+                s_entries[warp][0] = raw;
+                s_paints[warp][0] = __ldg(a.paints + (raw.z & 0xffffu));
+            }
         } else {
+            for (uint32_t i = lane; i < n; i += 32) s_keys[warp][i] = __ldg(&a.entries[e0 + i].tile_index);
+            __syncwarp();
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint32_t key = s_keys[warp][i];
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < n; j++) rank += s_keys[warp][j] < key ? 1u : 0u;
+                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + i));
+                s_entries[warp][rank] = raw;
+                s_paints[warp][rank] = __ldg(a.paints + (raw.z & 0xffffu));
+            }
+        }
+        __syncwarp();
+    }
+
+    float4 dst[8];
+    float4 uni = a.clear_color; // the tile's single colour while `uniform`
+    bool uniform = !LOAD_DEST;
+    if (LOAD_DEST) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
             dst[k] = a.clear_color;
+            if (row_mask & (1u << k)) {
+                uint32_t v = *reinterpret_cast<const uint32_t *>(out + (size_t)k * a.dest_pitch);
+                const float s = 1.0f / 255.0f;
+                dst[k] = make_float4((float)(v & 0xff) * s, (float)((v >> 8) & 0xff) * s,
+                                     (float)((v >> 16) & 0xff) * s, (float)(v >> 24) * s);
+            }
         }
     }
 
-    // ---- sort the run by tile index (painter's order) ----
-    const bool in_smem = n > 1 && n <= COMPOSITE_SORT_CAP;
-    if (in_smem) {
-        for (uint32_t i = tid; i < n; i += 64) s_keys[group][i] = __ldg(&a.entries[e0 + i].tile_index);
-        group_barrier(group);
-        for (uint32_t i = tid; i < n; i += 64) {
-            const uint32_t key = s_keys[group][i];
-            uint32_t rank = 0;
-            for (uint32_t j = 0; j < n; j++) rank += s_keys[group][j] < key ? 1u : 0u;
-            s_entries[group][rank] = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + i));
-        }
-        group_barrier(group);
-    }
-
-    const float cx = (float)x + 0.5f, cy = (float)(strip * 4) + 0.5f;
-    uint32_t last_key = 0; // slow path cursor: smallest tile index not yet drawn
+    const float cx = (float)x + 0.5f, cy = (float)(half * 8) + 0.5f;
+    uint32_t next_key = 0; // slow path cursor: smallest tile index not yet drawn
     for (uint32_t ei = 0; ei < n; ei++) {
         uint4 raw;
+        float4 base;
         if (in_smem) {
-            raw = s_entries[group][ei];
-        } else if (n == 1) {
-            raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0));
+            raw = s_entries[warp][ei];
+            base = s_paints[warp][ei];
         } else {
             // Slow path for very deep lists: select the next entry in draw order by a min-scan.
             uint32_t best = 0xffffffffu, best_i = 0;
-            for (uint32_t i = tid; i < n; i += 64) {
+            for (uint32_t i = lane; i < n; i += 32) {
                 uint32_t key = __ldg(&a.entries[e0 + i].tile_index);
-                if (key >= last_key && key < best) best = key, best_i = i;
+                if (key >= next_key && key < best) best = key, best_i = i;
             }
             for (int d = 16; d > 0; d >>= 1) {
                 uint32_t ob = __shfl_xor_sync(0xffffffffu, best, d), oi = __shfl_xor_sync(0xffffffffu, best_i, d);
                 if (ob < best) best = ob, best_i = oi;
             }
-            if ((tid & 31) == 0) s_min[group][tid >> 5] = best, s_keys[group][tid >> 5] = best_i;
-            group_barrier(group);
-            uint32_t b0 = s_min[group][0], b1 = s_min[group][1];
-            best_i = b0 <= b1 ? s_keys[group][0] : s_keys[group][1];
-            last_key = (b0 <= b1 ? b0 : b1) + 1;
-            group_barrier(group);
+            next_key = best + 1;
             raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + best_i));
+            base = __ldg(a.paints + (raw.z & 0xffffu));
         }
-        const uint32_t fill_end = raw.x, word = raw.y, paint_ctrl = raw.z;
+        const uint32_t fill_end = raw.x, word = raw.y;
         const uint32_t count = word & 0x00ffffffu;
         const float backdrop = (float)(int)(int8_t)(word >> 24);
-        const uint32_t ctrl = (paint_ctrl >> 16) & 0xffu;
-        const float4 base = __ldg(a.paints + (paint_ctrl & 0xffffu));
+        const uint32_t ctrl = (raw.z >> 16) & 0xffu;
         if (count == 0) {
             // Solid tile: coverage = backdrop for every pixel (tile_fragment.inc.glsl:548).
             const float alpha = base.w * mask_alpha(backdrop, ctrl);
-            const float ia = 1.0f - alpha;
-            const float sr = base.x * alpha, sg = base.y * alpha, sb = base.z * alpha;
+            if (uniform) {
+                blend(uni, base, alpha);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                dst[k].x = fmaf(dst[k].x, ia, sr);
-                dst[k].y = fmaf(dst[k].y, ia, sg);
-                dst[k].z = fmaf(dst[k].z, ia, sb);
-                dst[k].w = fmaf(dst[k].w, ia, alpha);
+                for (int k = 0; k < 8; k++) blend(dst[k], base, alpha);
             }
             continue;
         }
-        uint32_t acc[4] = {0, 0, 0, 0};
-        for (uint32_t fi = fill_end - count; fi < fill_end; fi++)
-            accumulate_fill(__ldg(a.fills + fi), cx, cy, a.area_lut, acc);
+        if (uniform) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float coverage = finish_coverage(acc[k], count) + backdrop;
-            // calculateColor (tile_fragment.inc.glsl:560-614), solid colour, SrcOver;
-            // dest = dest * (1 - a) + src (tile.cs.glsl:155).
-            float alpha = base.w * mask_alpha(coverage, ctrl);
-            float ia = 1.0f - alpha;
-            dst[k].x = fmaf(dst[k].x, ia, base.x * alpha);
-            dst[k].y = fmaf(dst[k].y, ia, base.y * alpha);
-            dst[k].z = fmaf(dst[k].z, ia, base.z * alpha);
-            dst[k].w = fmaf(dst[k].w, ia, alpha);
+            for (int k = 0; k < 8; k++) dst[k] = uni;
+            uniform = false;
+        }
+        uint32_t acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+        uint32_t contributions = 0;
+        for (uint32_t f0 = fill_end - count; f0 < fill_end; f0 += 32) {
+            const uint32_t m = min(32u, fill_end - f0);
+            uint2 mine = make_uint2(0, 0);
+            if ((uint32_t)lane < m) mine = __ldg(a.fills + f0 + lane);
+            for (uint32_t j = 0; j < m; j++) {
+                uint32_t from_w = __shfl_sync(0xffffffffu, mine.x, j), to_w = __shfl_sync(0xffffffffu, mine.y, j);
+                contributions += accumulate_fill<2>(from_w, to_w, cx, cy, a.area_lut, acc) ? 1u : 0u;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            float coverage = finish_coverage(acc[k >> 2][k & 3], contributions) + backdrop;
+            // calculateColor (tile_fragment.inc.glsl:560-614), solid colour, SrcOver.
+            blend(dst[k], base, base.w * mask_alpha(coverage, ctrl));
         }
     }
-    if (!px_ok) return;
+    if (uniform) {
+        const uint32_t packed = pack_rgba8(uni);
+        if (row_mask == 0xffu) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int py = py0 + k;
-        if (py >= 0 && py < a.dest_h)
-            *reinterpret_cast<uint32_t *>(a.dest + (size_t)py * a.dest_pitch + (size_t)px * 4) = pack_rgba8(dst[k]);
+            for (int k = 0; k < 8; k++, out += a.dest_pitch) *reinterpret_cast<uint32_t *>(out) = packed;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++, out += a.dest_pitch)
+                if (row_mask & (1u << k)) *reinterpret_cast<uint32_t *>(out) = packed;
+        }
+    } else if (row_mask == 0xffu) {
+#pragma unroll
+        for (int k = 0; k < 8; k++, out += a.dest_pitch) *reinterpret_cast<uint32_t *>(out) = pack_rgba8(dst[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++, out += a.dest_pitch)
+            if (row_mask & (1u << k)) *reinterpret_cast<uint32_t *>(out) = pack_rgba8(dst[k]);
+    }
+    __syncwarp(); // the next tile reuses this warp's shared-memory slots
     }
 }
 
@@ -713,8 +768,24 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     int fb_w = a.fb.max_x - a.fb.min_x;
     int rows = a.tile_y1 - a.tile_y0;
     if (fb_w <= 0 || rows <= 0) return 0;
-    int groups_x = (fb_w + COMPOSITE_TILES_PER_BLOCK - 1) / COMPOSITE_TILES_PER_BLOCK;
-    k_composite<<<(unsigned)(groups_x * rows), 64 * COMPOSITE_TILES_PER_BLOCK, 0, stream>>>(a);
+    // One resident wave of persistent warps: SM count x resident blocks per SM.
+    static int blocks_per_sm[2] = {0, 0}, sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        PF_CUDA_CHECK(cudaGetDevice(&dev));
+        PF_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], k_composite<false>, 32 * COMPOSITE_WARPS, 0));
+        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], k_composite<true>, 32 * COMPOSITE_WARPS, 0));
+    }
+    const uint64_t n_work = (uint64_t)fb_w * (uint64_t)rows;
+    uint64_t want = (n_work + COMPOSITE_WARPS - 1) / COMPOSITE_WARPS;
+    uint64_t resident = (uint64_t)sm_count * (uint64_t)blocks_per_sm[a.load_dest ? 1 : 0];
+    unsigned grid = (unsigned)(want < resident ? want : resident);
+    PF_CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), stream));
+    if (a.load_dest)
+        k_composite<true><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(a);
+    else
+        k_composite<false><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(a);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -821,20 +892,24 @@ int launch_dump_tiles(const BatchDev &b, const uint32_t *tile_word, const uint32
 }
 
 // Coverage masks per alpha tile with the same device function the fused kernel uses.
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(32)
     k_alpha_masks(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_fill_pos,
                   const uint32_t *tile_alpha_id, const PackedFill *fills, cudaTextureObject_t lut, float *out) {
-    const int x = threadIdx.x & 15, strip = threadIdx.x >> 4;
-    const float cx = (float)x + 0.5f, cy = (float)(strip * 4) + 0.5f;
+    const int x = threadIdx.x & 15, half = threadIdx.x >> 4;
+    const float cx = (float)x + 0.5f, cy = (float)(half * 8) + 0.5f;
     for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         uint32_t count = tile_word[t] & 0x00ffffffu;
         if (count == 0) continue;
         uint32_t end = tile_fill_pos[t];
-        uint32_t acc[4] = {0, 0, 0, 0};
-        for (uint32_t fi = end - count; fi < end; fi++) accumulate_fill(fills[fi], cx, cy, lut, acc);
+        uint32_t acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+        uint32_t contributions = 0;
+        for (uint32_t fi = end - count; fi < end; fi++) {
+            PackedFill f = fills[fi];
+            contributions += accumulate_fill<2>(f.x, f.y, cx, cy, lut, acc) ? 1u : 0u;
+        }
         float *mask = out + (size_t)tile_alpha_id[t] * 256;
 #pragma unroll
-        for (int k = 0; k < 4; k++) mask[(strip * 4 + k) * 16 + x] = finish_coverage(acc[k], count);
+        for (int k = 0; k < 8; k++) mask[(half * 8 + k) * 16 + x] = finish_coverage(acc[k >> 2][k & 3], contributions);
     }
 }
 int launch_alpha_masks(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_fill_pos,
@@ -842,7 +917,7 @@ int launch_alpha_masks(uint32_t n_tiles, const uint32_t *tile_word, const uint32
                        float *out, cudaStream_t stream) {
     if (n_tiles == 0) return 0;
     unsigned grid = n_tiles < 16384u ? n_tiles : 16384u;
-    k_alpha_masks<<<grid, 64, 0, stream>>>(n_tiles, tile_word, tile_fill_pos, tile_alpha_id, fills, area_lut, out);
+    k_alpha_masks<<<grid, 32, 0, stream>>>(n_tiles, tile_word, tile_fill_pos, tile_alpha_id, fills, area_lut, out);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

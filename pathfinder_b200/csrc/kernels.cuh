@@ -122,6 +122,7 @@ struct CompositeArgs {
     int32_t dest_w, dest_h;
     float4 clear_color;
     int load_dest;             // LOAD_ACTION_LOAD for batches after the first
+    uint32_t *work_counter;    // device word used by the persistent warps to pull tiles
 };
 int launch_composite(const CompositeArgs &args, cudaStream_t stream);
 

@@ -548,6 +548,7 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     ca.dest_h = r->options.dest_size.y;
     ca.clear_color = clear_color(r);
     ca.load_dest = r->batches_drawn > 0;
+    ca.work_counter = r->counters.ptr + 12;
     launches += launch_composite(ca, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[7], st));
 
@@ -859,6 +860,8 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
             ca.dest_w = r->options.dest_size.x;
             ca.dest_h = r->options.dest_size.y;
             ca.clear_color = clear_color(r);
+            r->counters.ensure(16);
+            ca.work_counter = r->counters.ptr + 12;
             r->stats.drawcall_count += (uint64_t)launch_composite(ca, r->stream);
         }
         r->stats.gpu_bytes_allocated = r->bytes_allocated;
