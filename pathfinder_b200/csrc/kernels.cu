@@ -42,27 +42,20 @@ __device__ __forceinline__ uint32_t search_le(const uint32_t *__restrict__ keys,
     return lo;
 }
 
-// search_le for a warp whose lanes hold consecutive (non-decreasing) x: lane 0 runs the binary
-// search once, the other lanes walk forward from its answer (paths are long runs of tiles /
-// columns / segments, so this is usually zero or one step), falling back to a bounded binary
-// search. Must be called by all 32 lanes; lanes with active == false only assist.
-__device__ __forceinline__ uint32_t search_le_warp(const uint32_t *__restrict__ keys, uint32_t n, uint32_t x,
-                                                   bool active) {
-    const unsigned lane = threadIdx.x & 31;
-    uint32_t x0 = __shfl_sync(0xffffffffu, x, 0);
-    uint32_t p0 = 0;
-    if (lane == 0) p0 = search_le(keys, n, x0);
-    p0 = __shfl_sync(0xffffffffu, p0, 0);
-    if (!active) return p0;
-    uint32_t p = p0;
-#pragma unroll 1
-    for (int step = 0; step < 4; step++) {
-        if (p + 1 < n && __ldg(keys + p + 1) <= x)
-            p++;
+// search_le through a coarse index: table[k] is the answer for x = k << shift, so the answer for
+// any x lies in [table[x >> shift], table[(x >> shift) + 1]] — one or two probes instead of a
+// 17-step dependent binary search over 100k+ paths.
+__device__ __forceinline__ uint32_t search_coarse(const uint32_t *__restrict__ keys, const CoarseIndex ci, uint32_t x) {
+    const uint32_t k = x >> ci.shift;
+    uint32_t lo = __ldg(ci.table + k), hi = __ldg(ci.table + k + 1) + 1;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(keys + mid) <= x)
+            lo = mid;
         else
-            return p;
+            hi = mid;
     }
-    return p + search_le(keys + p, n - p, x);
+    return lo;
 }
 
 __device__ __forceinline__ PathInfo load_path(const PathInfo *__restrict__ paths, uint32_t p) {
@@ -113,7 +106,7 @@ __global__ void __launch_bounds__(128)
            float4 *__restrict__ lines, uint32_t *__restrict__ line_path, uint32_t line_capacity) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.n_segments) return;
-    uint32_t p = search_le(b.path_seg_first, b.n_paths, s);
+    uint32_t p = search_coarse(b.path_seg_first, b.seg_index, s);
     const PathInfo *pi = b.paths + p;
     uint32_t gseg = __ldg(&pi->seg_global_first) + (s - __ldg(&pi->seg_batch_first));
     uint2 si = __ldg(b.seg_indices + gseg);
@@ -386,7 +379,7 @@ __global__ void __launch_bounds__(128)
                 int32_t *__restrict__ z_buffer) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= b.n_columns) return;
-    uint32_t p = search_le(b.path_col_offset, b.n_paths, c);
+    uint32_t p = search_coarse(b.path_col_offset, b.col_index, c);
     const PathInfo path = load_path(b.paths, p);
     const int w = path.max_x - path.min_x, h = path.max_y - path.min_y;
     const int x = (int)(c - path.col_offset);
@@ -444,7 +437,7 @@ __global__ void __launch_bounds__(256)
         if (in_range) tile_fb[t] = 0xffffffffu;
         return;
     }
-    uint32_t p = search_le_warp(b.path_tile_offset, b.n_paths, in_range ? t : b.n_tiles - 1, nonempty);
+    uint32_t p = nonempty ? search_coarse(b.path_tile_offset, b.tile_index, t) : 0;
     uint32_t result = 0xffffffffu;
     if (nonempty) {
         const PathInfo path = load_path(b.paths, p);
@@ -483,7 +476,7 @@ __global__ void __launch_bounds__(256)
     uint32_t fbi = in_range ? __ldg(tile_fb + t) : 0xffffffffu;
     const bool live = fbi != 0xffffffffu;
     if (!__any_sync(0xffffffffu, live)) return;
-    uint32_t p = search_le_warp(b.path_tile_offset, b.n_paths, in_range ? t : b.n_tiles - 1, live);
+    uint32_t p = live ? search_coarse(b.path_tile_offset, b.tile_index, t) : 0;
     uint32_t visible = 0;
     if (live) {
         TileEntry e;
@@ -869,7 +862,7 @@ __global__ void k_dump_tiles(BatchDev b, const uint32_t *tile_word, const uint32
                              const uint32_t *flags, const uint32_t *pos, TileRecord *out) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= b.n_tiles || !flags[t]) return;
-    uint32_t p = search_le(b.path_tile_offset, b.n_paths, t);
+    uint32_t p = search_coarse(b.path_tile_offset, b.tile_index, t);
     const PathInfo path = load_path(b.paths, p);
     int w = path.max_x - path.min_x;
     uint32_t local = t - path.tile_offset;

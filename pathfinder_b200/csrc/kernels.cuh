@@ -51,6 +51,13 @@ struct EmitFill { // emission-ordered fill kept for parity dumps (12 bytes like 
     uint32_t from, to, tile;
 };
 
+// Coarse index over one of the per-path offset arrays: table[k] = largest path p with
+// offsets[p] <= (k << shift); (count >> shift) + 2 entries. Built on the host with the batch.
+struct CoarseIndex {
+    const uint32_t *table;
+    int shift;
+};
+
 // Everything the stage kernels read about one batch. Search arrays have n_paths + 1 entries (the
 // last one is the total) so a thread finds its path with one binary search over a dense array.
 struct BatchDev {
@@ -60,6 +67,7 @@ struct BatchDev {
     const uint32_t *path_seg_first;
     const uint32_t *path_tile_offset;
     const uint32_t *path_col_offset;
+    CoarseIndex seg_index, tile_index, col_index;
     uint32_t n_paths, n_segments, n_tiles, n_columns;
     Transform xf;
     ViewBox view_box;

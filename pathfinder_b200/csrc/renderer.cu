@@ -289,7 +289,21 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
     cudaStream_t st = r->stream;
     const uint32_t P = batch.path_count;
     const PFPrepareTilesInfoD3D11 &info = batch.prepare_info;
-    const size_t meta_bytes = (size_t)P * sizeof(PathInfo) + 3 * (size_t)(P + 1) * sizeof(uint32_t);
+    // Coarse search tables (see CoarseIndex): sized from upper bounds known before the loop.
+    constexpr int SEG_SHIFT = 5, TILE_SHIFT = 7, COL_SHIFT = 5;
+    uint64_t tile_bound = 0, col_bound = 0;
+    for (uint32_t i = 0; i < P; i++) {
+        const PFRectI &tr = info.propagate_metadata[i].tile_rect;
+        int64_t w = std::max<int64_t>(0, (int64_t)tr.lower_right.x - tr.origin.x);
+        int64_t h = std::max<int64_t>(0, (int64_t)tr.lower_right.y - tr.origin.y);
+        tile_bound += (uint64_t)(w * h);
+        col_bound += (uint64_t)w;
+    }
+    if (tile_bound >= 0xfffffff0ull) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "more than 2^32 bbox tiles in one batch");
+    const size_t seg_table_n = ((size_t)batch.segment_count >> SEG_SHIFT) + 2;
+    const size_t tile_table_cap = ((size_t)tile_bound >> TILE_SHIFT) + 2, col_table_cap = ((size_t)col_bound >> COL_SHIFT) + 2;
+    const size_t base_bytes = (size_t)P * sizeof(PathInfo) + 3 * (size_t)(P + 1) * sizeof(uint32_t);
+    const size_t meta_bytes = base_bytes + (seg_table_n + tile_table_cap + col_table_cap) * sizeof(uint32_t);
     if (r->meta_copied) PF_CUDA_CHECK(cudaEventSynchronize(r->meta_copied));
     r->batch_meta_host.ensure(meta_bytes + 64);
     uint8_t *hbase = r->batch_meta_host.ptr;
@@ -338,6 +352,24 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
     h_seg_first[P] = n_segments;
     h_tile_off[P] = n_tiles;
     h_col_off[P] = n_cols;
+    uint32_t *h_seg_table = h_col_off + (P + 1);
+    uint32_t *h_tile_table = h_seg_table + seg_table_n;
+    uint32_t *h_col_table = h_tile_table + tile_table_cap;
+    auto build_table = [P](const uint32_t *offsets, uint32_t count, int shift, uint32_t *table) {
+        // table[k] = largest p < P with offsets[p] <= k << shift (offsets[0] == 0)
+        const size_t n = ((size_t)count >> shift) + 2;
+        uint32_t p = 0;
+        for (size_t k = 0; k < n; k++) {
+            const uint64_t x = (uint64_t)k << shift;
+            while (p + 1 < P && offsets[p + 1] <= x) p++;
+            table[k] = p;
+        }
+    };
+    if (P) {
+        build_table(h_seg_first, n_segments, SEG_SHIFT, h_seg_table);
+        build_table(h_tile_off, n_tiles, TILE_SHIFT, h_tile_table);
+        build_table(h_col_off, n_cols, COL_SHIFT, h_col_table);
+    }
 
     r->batch_meta.ensure(meta_bytes + 64, 1.25);
     if (meta_bytes) {
@@ -354,6 +386,9 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
     b.path_seg_first = reinterpret_cast<const uint32_t *>(r->batch_meta.ptr + (size_t)P * sizeof(PathInfo));
     b.path_tile_offset = b.path_seg_first + (P + 1);
     b.path_col_offset = b.path_tile_offset + (P + 1);
+    b.seg_index = CoarseIndex{b.path_col_offset + (P + 1), SEG_SHIFT};
+    b.tile_index = CoarseIndex{b.seg_index.table + seg_table_n, TILE_SHIFT};
+    b.col_index = CoarseIndex{b.tile_index.table + tile_table_cap, COL_SHIFT};
     b.n_paths = P;
     b.n_segments = n_segments;
     b.n_tiles = n_tiles;
