@@ -99,11 +99,15 @@ __device__ __forceinline__ float2 lerp_half(float2 a, float2 b) { // a + t * (b 
 }
 
 constexpr int DICE_MAX_DEPTH = 40; // f32 halving collapses long before; the oracle uses the same cap
+constexpr int DICE_SMEM_LEVELS = 8; // pending right halves kept in shared memory per thread
+constexpr int DICE_THREADS = 128;
 
 template <bool EMIT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(DICE_THREADS)
     k_dice(BatchDev b, uint32_t *__restrict__ seg_line_count, const uint32_t *__restrict__ seg_line_offset,
            float4 *__restrict__ lines, uint32_t *__restrict__ line_path, uint32_t line_capacity) {
+    __shared__ float s_stack[DICE_SMEM_LEVELS][6][DICE_THREADS];
+    __shared__ unsigned char s_depth[DICE_SMEM_LEVELS][DICE_THREADS];
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= b.n_segments) return;
     uint32_t p = search_coarse(b.path_seg_first, b.seg_index, s);
@@ -145,28 +149,49 @@ __global__ void __launch_bounds__(128)
             cur.p2 = make_float2((c2.x + cur.p3.x) * third, (c2.y + cur.p3.y) * third);
         }
         // process_segment (renderer/src/tiler.rs:166-184) with an explicit stack: left half first.
-        Cubic stack[DICE_MAX_DEPTH];
-        unsigned char depth_stack[DICE_MAX_DEPTH];
+        // A pending right half is stored as (p1, p2, p3, depth): its p0 is the end point of the
+        // leaf emitted just before it is popped (splits keep end points bit-exact). The first
+        // DICE_SMEM_LEVELS levels live in shared memory ([level][field][thread]: conflict-free);
+        // deeper recursion, which f32 curves of sane size never reach, spills to local memory.
+        float deep[DICE_MAX_DEPTH - DICE_SMEM_LEVELS][7];
         int sp = 0;
         int depth = 0;
+        const int tid = threadIdx.x;
         for (;;) {
             if (cubic_is_flat(cur) || depth >= DICE_MAX_DEPTH) {
                 emit_line(cur.p0, cur.p3);
                 if (sp == 0) break;
                 sp--;
-                cur = stack[sp];
-                depth = depth_stack[sp];
+                cur.p0 = cur.p3;
+                if (sp < DICE_SMEM_LEVELS) {
+                    cur.p1 = make_float2(s_stack[sp][0][tid], s_stack[sp][1][tid]);
+                    cur.p2 = make_float2(s_stack[sp][2][tid], s_stack[sp][3][tid]);
+                    cur.p3 = make_float2(s_stack[sp][4][tid], s_stack[sp][5][tid]);
+                    depth = s_depth[sp][tid];
+                } else {
+                    const float *d = deep[sp - DICE_SMEM_LEVELS];
+                    cur.p1 = make_float2(d[0], d[1]);
+                    cur.p2 = make_float2(d[2], d[3]);
+                    cur.p3 = make_float2(d[4], d[5]);
+                    depth = (int)d[6];
+                }
             } else {
                 // CubicSegment::split(0.5) (content/src/segment.rs:307-360)
                 float2 p01 = lerp_half(cur.p0, cur.p1), p12 = lerp_half(cur.p1, cur.p2),
                        p23 = lerp_half(cur.p2, cur.p3);
                 float2 p012 = lerp_half(p01, p12), p123 = lerp_half(p12, p23);
                 float2 p0123 = lerp_half(p012, p123);
-                Cubic right;
-                right.p0 = p0123, right.p1 = p123, right.p2 = p23, right.p3 = cur.p3;
                 depth++;
-                stack[sp] = right;
-                depth_stack[sp] = (unsigned char)depth;
+                if (sp < DICE_SMEM_LEVELS) {
+                    s_stack[sp][0][tid] = p123.x, s_stack[sp][1][tid] = p123.y;
+                    s_stack[sp][2][tid] = p23.x, s_stack[sp][3][tid] = p23.y;
+                    s_stack[sp][4][tid] = cur.p3.x, s_stack[sp][5][tid] = cur.p3.y;
+                    s_depth[sp][tid] = (unsigned char)depth;
+                } else {
+                    float *d = deep[sp - DICE_SMEM_LEVELS];
+                    d[0] = p123.x, d[1] = p123.y, d[2] = p23.x, d[3] = p23.y, d[4] = cur.p3.x, d[5] = cur.p3.y;
+                    d[6] = (float)depth;
+                }
                 sp++;
                 cur.p1 = p01, cur.p2 = p012, cur.p3 = p0123;
             }
@@ -178,11 +203,11 @@ __global__ void __launch_bounds__(128)
 int launch_dice(bool emit, const BatchDev &b, uint32_t *seg_line_count, const uint32_t *seg_line_offset,
                 float4 *lines, uint32_t *line_path, uint32_t line_capacity, cudaStream_t stream) {
     if (b.n_segments == 0) return 0;
-    unsigned grid = div_up(b.n_segments, 128);
+    unsigned grid = div_up(b.n_segments, DICE_THREADS);
     if (emit)
-        k_dice<true><<<grid, 128, 0, stream>>>(b, seg_line_count, seg_line_offset, lines, line_path, line_capacity);
+        k_dice<true><<<grid, DICE_THREADS, 0, stream>>>(b, seg_line_count, seg_line_offset, lines, line_path, line_capacity);
     else
-        k_dice<false><<<grid, 128, 0, stream>>>(b, seg_line_count, seg_line_offset, lines, line_path, line_capacity);
+        k_dice<false><<<grid, DICE_THREADS, 0, stream>>>(b, seg_line_count, seg_line_offset, lines, line_path, line_capacity);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
