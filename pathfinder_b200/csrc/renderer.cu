@@ -198,7 +198,8 @@ void setup_tracking(PFCudaRenderer *r) {
     track(r, r->fb_cursor);
     track(r, r->entries);
     track(r, r->counters);
-    track(r, r->scan_scratch.block_sums);
+    track(r, r->scan_scratch.control);
+    track(r, r->scan_scratch.status);
     track(r, r->fill_is_first);
     track(r, r->fill_first_scan);
     track(r, r->dump_out);

@@ -5,8 +5,13 @@
 // :218-229,338-353,463-499): every stage first counts its outputs, the scan turns counts into
 // deterministic offsets, and the stage then writes in place.
 //
-// Three launches: per-block reduce, one-block scan of the block sums, per-block scan + offset.
-// The input is a functor so that producers can be fused (e.g. "low 24 bits of the tile word").
+// One launch, one pass over the input ("decoupled look-back"): every block takes a ticket, reduces
+// its 4096-element tile, publishes the tile aggregate, looks back over its predecessors' published
+// aggregates / inclusive prefixes until it knows its own exclusive prefix, publishes its inclusive
+// prefix and writes the scanned tile. Status words carry an epoch so they never need clearing; the
+// epoch and the ticket counter live in device memory and are advanced by the last tile, which keeps
+// the launch replayable from a CUDA graph. The input is a functor so producers can be fused
+// (e.g. "low 24 bits of the tile word").
 #pragma once
 
 #include "common.cuh"
@@ -47,93 +52,126 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
     return res;
 }
 
+// Device-resident state shared by all scans on one stream (they run back to back, never
+// concurrently): control[0] = ticket counter, control[1] = epoch; one status word per tile.
+struct ScanState {
+    uint32_t *control;
+    unsigned long long *status; // epoch << 34 | flag << 32 | value
+};
+
+constexpr unsigned long long SCAN_FLAG_AGGREGATE = 1ull, SCAN_FLAG_PREFIX = 2ull;
+
+__device__ __forceinline__ unsigned long long scan_pack(uint32_t epoch, unsigned long long flag, uint32_t value) {
+    return ((unsigned long long)(epoch & 0x3fffffffu) << 34) | (flag << 32) | (unsigned long long)value;
+}
+
 // `n_dev` (optional): the element count lives in device memory (a previous stage's total); `n` is
-// then the host-side bound the grid was sized with, and the kernels use min(*n_dev, n).
+// then the host-side bound the grid was sized with, and the kernel uses min(*n_dev, n).
 template <typename InFn>
 __global__ void __launch_bounds__(SCAN_THREADS)
-    k_scan_reduce(InFn in, uint32_t n, const uint32_t *__restrict__ n_dev, uint32_t *block_sums) {
+    k_scan(InFn in, uint32_t n, const uint32_t *__restrict__ n_dev, uint32_t *__restrict__ out,
+           uint32_t *__restrict__ total_out, ScanState st) {
     __shared__ uint32_t smem[SCAN_THREADS / 32 + 1];
+    __shared__ uint32_t s_tile, s_epoch, s_prefix;
     if (n_dev) n = min(n, *n_dev);
-    const size_t base = (size_t)blockIdx.x * SCAN_TILE;
+    if (threadIdx.x == 0) {
+        s_epoch = *reinterpret_cast<volatile uint32_t *>(st.control + 1) + 1; // read before the ticket
+        s_tile = atomicAdd(st.control, 1u);
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile, epoch = s_epoch;
+    const uint32_t n_tiles = gridDim.x;
+
+    // Load and reduce the tile (items stay in registers).
+    const size_t base = (size_t)tile * SCAN_TILE;
+    uint32_t v[4][4];
+    uint32_t round_sum[4];
     uint32_t sum = 0;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         size_t i0 = base + (size_t)r * (SCAN_THREADS * 4) + (size_t)threadIdx.x * 4;
+        round_sum[r] = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (i0 + k < n) sum += in((uint32_t)(i0 + k));
-    }
-    uint32_t total;
-    block_exclusive_scan(sum, smem, &total);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
-
-// One block: exclusive scan of the block sums in place, total to *total_out (+ optional copy).
-__global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t *block_sums, uint32_t n_blocks,
-                                                          uint32_t *total_out) {
-    __shared__ uint32_t warp_sums[33];
-    __shared__ uint32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < n_blocks; base += 1024) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = i < n_blocks ? block_sums[i] : 0;
-        uint32_t inc = warp_inclusive_scan(v);
-        if (lane == 31) warp_sums[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_sums[lane];
-            uint32_t winc = warp_inclusive_scan(w);
-            warp_sums[lane] = winc - w;
-            if (lane == 31) warp_sums[32] = winc;
+        for (int k = 0; k < 4; k++) {
+            v[r][k] = (i0 + k < n) ? in((uint32_t)(i0 + k)) : 0;
+            round_sum[r] += v[r][k];
         }
-        __syncthreads();
-        uint32_t carry = carry_s;
-        if (i < n_blocks) block_sums[i] = carry + warp_sums[warp] + inc - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + warp_sums[32];
-        __syncthreads();
+        sum += round_sum[r];
     }
-    if (threadIdx.x == 0 && total_out) *total_out = carry_s;
-}
+    uint32_t aggregate;
+    block_exclusive_scan(sum, smem, &aggregate);
 
-template <typename InFn>
-__global__ void __launch_bounds__(SCAN_THREADS)
-    k_scan_final(InFn in, uint32_t n, const uint32_t *__restrict__ n_dev, const uint32_t *block_offsets,
-                 uint32_t *out) {
-    __shared__ uint32_t smem[SCAN_THREADS / 32 + 1];
-    if (n_dev) n = min(n, *n_dev);
-    const size_t base = (size_t)blockIdx.x * SCAN_TILE;
-    uint32_t carry = block_offsets[blockIdx.x];
+    // Publish, look back, publish again.
+    if (threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x;
+        volatile unsigned long long *status = st.status;
+        if (tile == 0) {
+            if (lane == 0) {
+                status[0] = scan_pack(epoch, SCAN_FLAG_PREFIX, aggregate);
+                s_prefix = 0;
+            }
+        } else {
+            if (lane == 0) status[tile] = scan_pack(epoch, SCAN_FLAG_AGGREGATE, aggregate);
+            uint32_t exclusive = 0;
+            int look = (int)tile - 1;
+            for (;;) {
+                int idx = look - (int)lane;
+                unsigned long long w;
+                unsigned long long flag;
+                do {
+                    w = idx >= 0 ? status[idx] : scan_pack(epoch, SCAN_FLAG_PREFIX, 0);
+                    flag = ((w >> 34) == (unsigned long long)(epoch & 0x3fffffffu)) ? ((w >> 32) & 3ull) : 0ull;
+                } while (__any_sync(0xffffffffu, flag == 0ull));
+                unsigned prefix_lanes = __ballot_sync(0xffffffffu, flag == SCAN_FLAG_PREFIX);
+                uint32_t val = (uint32_t)w;
+                if (prefix_lanes) {
+                    unsigned first = __ffs(prefix_lanes) - 1; // nearest predecessor with an inclusive prefix
+                    val = lane <= first ? val : 0;
+                }
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                exclusive += val;
+                if (prefix_lanes) break;
+                look -= 32;
+            }
+            if (lane == 0) {
+                status[tile] = scan_pack(epoch, SCAN_FLAG_PREFIX, exclusive + aggregate);
+                s_prefix = exclusive;
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t carry = s_prefix;
+    if (tile == n_tiles - 1 && threadIdx.x == 0) {
+        if (total_out) *total_out = carry + aggregate;
+        // Every other tile already holds its ticket and epoch: advance both for the next scan.
+        st.control[1] = epoch;
+        st.control[0] = 0;
+    }
+
+    // Scan the tile and write it out.
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         size_t i0 = base + (size_t)r * (SCAN_THREADS * 4) + (size_t)threadIdx.x * 4;
-        uint32_t v[4];
-        uint32_t sum = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            v[k] = (i0 + k < n) ? in((uint32_t)(i0 + k)) : 0;
-            sum += v[k];
-        }
         uint32_t total;
-        uint32_t excl = block_exclusive_scan(sum, smem, &total) + carry;
+        uint32_t excl = block_exclusive_scan(round_sum[r], smem, &total) + carry;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (i0 + k < n) out[i0 + k] = excl;
-            excl += v[k];
+            excl += v[r][k];
         }
         carry += total;
     }
 }
 
 struct ScanScratch {
-    DeviceBuffer<uint32_t> block_sums;
+    DeviceBuffer<uint32_t> control;
+    DeviceBuffer<unsigned long long> status;
+    bool initialised = false;
 };
 
 // out[i] = sum_{j<i} in(j) for i in [0, n); *total_out (device) = sum of all. `out` may alias
-// the array `in` reads only if in(i) reads element i alone (each element is read before it is
-// written by the same thread). Returns the number of kernels launched.
+// the array `in` reads if in(i) reads element i alone (a tile is read completely before it is
+// written, and tiles are disjoint). Returns the number of kernels launched.
 template <typename InFn>
 inline int exclusive_scan(InFn in, uint32_t *out, uint32_t n, uint32_t *total_out, ScanScratch &scratch,
                           cudaStream_t stream, const uint32_t *n_dev = nullptr) {
@@ -142,12 +180,21 @@ inline int exclusive_scan(InFn in, uint32_t *out, uint32_t n, uint32_t *total_ou
         return 0;
     }
     unsigned n_blocks = div_up(n, SCAN_TILE);
-    scratch.block_sums.ensure(n_blocks, 1.5);
-    k_scan_reduce<<<n_blocks, SCAN_THREADS, 0, stream>>>(in, n, n_dev, scratch.block_sums.ptr);
-    k_scan_block_sums<<<1, 1024, 0, stream>>>(scratch.block_sums.ptr, n_blocks, total_out);
-    k_scan_final<<<n_blocks, SCAN_THREADS, 0, stream>>>(in, n, n_dev, scratch.block_sums.ptr, out);
+    if (!scratch.initialised) {
+        scratch.control.ensure(2);
+        PF_CUDA_CHECK(cudaMemsetAsync(scratch.control.ptr, 0, 2 * sizeof(uint32_t), stream));
+        scratch.initialised = true;
+    }
+    if (n_blocks > scratch.status.capacity) {
+        // The old buffer may still be in use by an earlier scan on this stream.
+        PF_CUDA_CHECK(cudaStreamSynchronize(stream));
+        scratch.status.ensure(n_blocks, 1.5);
+        PF_CUDA_CHECK(cudaMemsetAsync(scratch.status.ptr, 0, scratch.status.capacity * sizeof(unsigned long long), stream));
+    }
+    ScanState st{scratch.control.ptr, scratch.status.ptr};
+    k_scan<<<n_blocks, SCAN_THREADS, 0, stream>>>(in, n, n_dev, out, total_out, st);
     PF_CUDA_CHECK(cudaGetLastError());
-    return 3;
+    return 1;
 }
 
 struct LoadU32 {
