@@ -214,6 +214,15 @@ int launch_dice(bool emit, const BatchDev &b, uint32_t *seg_line_count, const ui
 
 // ---------------------------------------------------------------------------------------------
 // bin — segment-to-tile lattice clipping, one thread per flattened line.
+//
+// Three modes of one walk:
+//   BIN_COUNT      per-tile fill counts + backdrop deltas (+ fills per line for the parity dumps)
+//   BIN_EMIT_LIVE  production emit, run after propagate + z-cull: only the fills of tiles that
+//                  survived are stored, straight into their tile-grouped runs
+//   BIN_EMIT       parity dumps: every fill, tile-grouped and at its emission-order slot (what
+//                  AddFillsD3D9 carries)
+// Lines that stay inside one tile (the majority after flattening) take a division-free fast path;
+// the others are compacted through shared memory so the long walks run on dense warps.
 // ---------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return a + (b - a) * t; } // util.rs:25-27
@@ -252,21 +261,20 @@ __device__ __forceinline__ bool clip_line(float2 &from, float2 &to, const ViewBo
     }
 }
 
-template <bool EMIT>
-__global__ void __launch_bounds__(128) k_bin(BatchDev b, BinArgs a) {
-    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_lines = a.n_lines_dev ? min(a.n_lines, __ldg(a.n_lines_dev)) : a.n_lines;
-    if (l >= n_lines) return;
-    float4 seg = __ldg(a.lines + l);
-    uint32_t p = __ldg(a.line_path + l);
-    const PathInfo path = load_path(b.paths, p);
-    const int rect_w = path.max_x - path.min_x, rect_h = path.max_y - path.min_y;
+enum BinMode { BIN_EMIT_LIVE = 0, BIN_COUNT = 1, BIN_EMIT = 2 };
+constexpr int BIN_THREADS = 128;
 
-    uint32_t emitted = 0;
-    const uint32_t out_base = (EMIT && a.line_fill_offset) ? __ldg(a.line_fill_offset + l) : 0;
+// Receives the fills and backdrop adjustments of one line.
+template <int MODE>
+struct BinSink {
+    const BinArgs &a;
+    const PathInfo &path;
+    int rect_w, rect_h;
+    uint32_t out_base;
+    uint32_t emitted;
 
     // ObjectBuilder::add_fill (renderer/src/builder.rs:509-553)
-    auto add_fill = [&](float2 from, float2 to, int tx, int ty) {
+    __device__ __forceinline__ void add_fill(float2 from, float2 to, int tx, int ty) {
         int ox = tx - path.min_x, oy = ty - path.min_y;
         if (ox < 0 || oy < 0 || ox >= rect_w || oy >= rect_h) return; // tile_coords_to_local_index
         float ulx = (float)tx * 16.0f, uly = (float)ty * 16.0f;
@@ -275,28 +283,32 @@ __global__ void __launch_bounds__(128) k_bin(BatchDev b, BinArgs a) {
         int tx8 = cvtps(sse_min(sse_max((to.x - ulx) * 256.0f, 0.0f), 4095.0f));
         int ty8 = cvtps(sse_min(sse_max((to.y - uly) * 256.0f, 0.0f), 4095.0f));
         if (fx == tx8) return; // cull degenerate fills
-        uint32_t t = path.tile_offset + (uint32_t)(ox + rect_w * oy);
-        if (!EMIT) {
-            atomicAdd(a.tile_word + t, 1u);
-        } else {
-            uint32_t from_w = (uint32_t)fx | ((uint32_t)fy << 16), to_w = (uint32_t)tx8 | ((uint32_t)ty8 << 16);
-            // Occlusion culling before fill emission: tiles that lost the z-test (or lie outside
-            // the framebuffer) get no space in the tile-grouped array.
-            if (!a.tile_fb || __ldg(a.tile_fb + t) != 0xffffffffu) {
+        const uint32_t t = path.tile_offset + (uint32_t)(ox + rect_w * oy);
+        const uint32_t from_w = (uint32_t)fx | ((uint32_t)fy << 16), to_w = (uint32_t)tx8 | ((uint32_t)ty8 << 16);
+        if (MODE == BIN_EMIT_LIVE) {
+            // Production emit, after the z-cull: tiles that lost the z-test (or lie outside the
+            // framebuffer) get no space in the tile-grouped array — occlusion culling before fill
+            // emission.
+            if (__ldg(a.tile_fb + t) != 0xffffffffu) {
                 uint32_t pos = atomicAdd(a.tile_fill_pos + t, 1u);
                 if (pos < a.fill_capacity) a.fills[pos] = make_uint2(from_w, to_w);
             }
-            if (a.fills_emit) { // parity dumps: every fill, in emission order
-                uint32_t e = out_base + emitted;
-                atomicMin(a.tile_first_fill + t, e);
-                if (e < a.emit_capacity) a.fills_emit[e] = EmitFill{from_w, to_w, t};
-            }
+        } else if (MODE == BIN_COUNT) {
+            atomicAdd(a.tile_word + t, 1u);
+        } else {
+            // Parity dumps: every fill tile-grouped (no culling) and at its emission-order slot.
+            uint32_t pos = atomicAdd(a.tile_fill_pos + t, 1u);
+            if (pos < a.fill_capacity) a.fills[pos] = make_uint2(from_w, to_w);
+            uint32_t e = out_base + emitted;
+            atomicMin(a.tile_first_fill + t, e);
+            if (e < a.emit_capacity) a.fills_emit[e] = EmitFill{from_w, to_w, t};
         }
         emitted++;
-    };
-    // ObjectBuilder::adjust_alpha_tile_backdrop (renderer/src/builder.rs:595-616); count pass only.
-    auto adjust_backdrop = [&](int tx, int ty, int delta) {
-        if (EMIT) return;
+    }
+
+    // ObjectBuilder::adjust_alpha_tile_backdrop (renderer/src/builder.rs:595-616); once per frame.
+    __device__ __forceinline__ void adjust_backdrop(int tx, int ty, int delta) {
+        if (MODE != BIN_COUNT) return;
         int ox = tx - path.min_x, oy = ty - path.min_y;
         if (ox < 0 || ox >= rect_w || oy >= rect_h) return;
         if (oy < 0) {
@@ -305,75 +317,131 @@ __global__ void __launch_bounds__(128) k_bin(BatchDev b, BinArgs a) {
         }
         // i8 wrapping add in the top byte of the tile word (no carry reaches the count bits).
         atomicAdd(a.tile_word + path.tile_offset + (uint32_t)(ox + rect_w * oy), (uint32_t)delta << 24);
-    };
-
-    float2 from = make_float2(seg.x, seg.y), to = make_float2(seg.z, seg.w);
-    if (rect_w > 0 && clip_line(from, to, b.view_box)) {
-        // process_line_segment (renderer/src/tiler.rs:202-308)
-        const float tile_size = 16.0f, recip = 1.0f / 16.0f;
-        int from_tx = cvtps(floorf(from.x * recip)), from_ty = cvtps(floorf(from.y * recip));
-        int to_tx = cvtps(floorf(to.x * recip)), to_ty = cvtps(floorf(to.y * recip));
-        float vx = to.x - from.x, vy = to.y - from.y;
-        bool neg_x = vx < 0.0f, neg_y = vy < 0.0f;
-        int step_x = neg_x ? -1 : 1, step_y = neg_y ? -1 : 1;
-        float first_cross_x = (float)(from_tx + (neg_x ? 0 : 1)) * tile_size;
-        float first_cross_y = (float)(from_ty + (neg_y ? 0 : 1)) * tile_size;
-        float t_max_x = (first_cross_x - from.x) / vx;
-        float t_max_y = (first_cross_y - from.y) / vy;
-        float t_delta_x = fabsf(tile_size / vx);
-        float t_delta_y = fabsf(tile_size / vy);
-
-        float2 cur = from;
-        int tx = from_tx, ty = from_ty;
-        int last_step = 0; // 0 none, 1 X, 2 Y
-        for (;;) {
-            int next_step;
-            if (t_max_x < t_max_y)
-                next_step = 1;
-            else if (t_max_x > t_max_y)
-                next_step = 2;
-            else
-                next_step = step_x > 0 ? 1 : 2;
-            float next_t = fminf(next_step == 1 ? t_max_x : t_max_y, 1.0f);
-            if (tx == to_tx && ty == to_ty) next_step = 0;
-            float2 next = make_float2(from.x + vx * next_t, from.y + vy * next_t);
-            add_fill(cur, next, tx, ty);
-            if (step_y < 0 && next_step == 2) {
-                add_fill(next, make_float2((float)tx * tile_size, (float)ty * tile_size), tx, ty);
-            } else if (step_y > 0 && last_step == 2) {
-                add_fill(make_float2((float)tx * tile_size, (float)ty * tile_size), cur, tx, ty);
-            }
-            if (step_x < 0 && last_step == 1) {
-                adjust_backdrop(tx, ty, 1);
-            } else if (step_x > 0 && next_step == 1) {
-                adjust_backdrop(tx, ty, -1);
-            }
-            if (next_step == 0) break;
-            if (next_step == 1) {
-                if (tx == to_tx) break;
-                t_max_x += t_delta_x;
-                t_max_y += 0.0f;
-                tx += step_x;
-            } else {
-                if (ty == to_ty) break;
-                t_max_x += 0.0f;
-                t_max_y += t_delta_y;
-                ty += step_y;
-            }
-            cur = next;
-            last_step = next_step;
-        }
     }
-    if (!EMIT && a.line_fill_count) a.line_fill_count[l] = emitted;
+};
+
+// process_line_segment (renderer/src/tiler.rs:202-308) after clipping, for a line that crosses
+// at least one tile boundary.
+template <typename Sink>
+__device__ __forceinline__ void walk_line(float2 from, float2 to, int from_tx, int from_ty, int to_tx, int to_ty,
+                                          Sink &sink) {
+    const float tile_size = 16.0f;
+    float vx = to.x - from.x, vy = to.y - from.y;
+    bool neg_x = vx < 0.0f, neg_y = vy < 0.0f;
+    int step_x = neg_x ? -1 : 1, step_y = neg_y ? -1 : 1;
+    float first_cross_x = (float)(from_tx + (neg_x ? 0 : 1)) * tile_size;
+    float first_cross_y = (float)(from_ty + (neg_y ? 0 : 1)) * tile_size;
+    float t_max_x = (first_cross_x - from.x) / vx;
+    float t_max_y = (first_cross_y - from.y) / vy;
+    float t_delta_x = fabsf(tile_size / vx);
+    float t_delta_y = fabsf(tile_size / vy);
+
+    float2 cur = from;
+    int tx = from_tx, ty = from_ty;
+    int last_step = 0; // 0 none, 1 X, 2 Y
+    for (;;) {
+        int next_step;
+        if (t_max_x < t_max_y)
+            next_step = 1;
+        else if (t_max_x > t_max_y)
+            next_step = 2;
+        else
+            next_step = step_x > 0 ? 1 : 2;
+        float next_t = fminf(next_step == 1 ? t_max_x : t_max_y, 1.0f);
+        if (tx == to_tx && ty == to_ty) next_step = 0;
+        float2 next = make_float2(from.x + vx * next_t, from.y + vy * next_t);
+        sink.add_fill(cur, next, tx, ty);
+        if (step_y < 0 && next_step == 2) {
+            sink.add_fill(next, make_float2((float)tx * tile_size, (float)ty * tile_size), tx, ty);
+        } else if (step_y > 0 && last_step == 2) {
+            sink.add_fill(make_float2((float)tx * tile_size, (float)ty * tile_size), cur, tx, ty);
+        }
+        if (step_x < 0 && last_step == 1) {
+            sink.adjust_backdrop(tx, ty, 1);
+        } else if (step_x > 0 && next_step == 1) {
+            sink.adjust_backdrop(tx, ty, -1);
+        }
+        if (next_step == 0) break;
+        if (next_step == 1) {
+            if (tx == to_tx) break;
+            t_max_x += t_delta_x;
+            t_max_y += 0.0f;
+            tx += step_x;
+        } else {
+            if (ty == to_ty) break;
+            t_max_x += 0.0f;
+            t_max_y += t_delta_y;
+            ty += step_y;
+        }
+        cur = next;
+        last_step = next_step;
+    }
 }
 
-int launch_bin(bool emit, const BatchDev &b, const BinArgs &args, cudaStream_t stream) {
+template <int MODE>
+__global__ void __launch_bounds__(BIN_THREADS) k_bin(BatchDev b, BinArgs a) {
+    __shared__ float4 s_line[BIN_THREADS];
+    __shared__ uint32_t s_index[BIN_THREADS];
+    __shared__ uint32_t s_queued;
+    if (threadIdx.x == 0) s_queued = 0;
+    __syncthreads();
+
+    const uint32_t n_lines = a.n_lines_dev ? min(a.n_lines, __ldg(a.n_lines_dev)) : a.n_lines;
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    const float recip = 1.0f / 16.0f;
+    if (l < n_lines) {
+        float4 seg = __ldg(a.lines + l);
+        const PathInfo path = load_path(b.paths, __ldg(a.line_path + l));
+        const int rect_w = path.max_x - path.min_x, rect_h = path.max_y - path.min_y;
+        float2 from = make_float2(seg.x, seg.y), to = make_float2(seg.z, seg.w);
+        uint32_t emitted = 0;
+        if (rect_w > 0 && clip_line(from, to, b.view_box)) {
+            int from_tx = cvtps(floorf(from.x * recip)), from_ty = cvtps(floorf(from.y * recip));
+            int to_tx = cvtps(floorf(to.x * recip)), to_ty = cvtps(floorf(to.y * recip));
+            if (from_tx == to_tx && from_ty == to_ty) {
+                // The line stays inside one tile: both t_max are >= 1 (the first crossing lies
+                // beyond `to`), so next_t = min(t_max, 1) = 1, there is no step, no auxiliary fill
+                // and no backdrop change — one fill from `from` to from + v * 1.
+                float vx = to.x - from.x, vy = to.y - from.y;
+                BinSink<MODE> sink{a, path, rect_w, rect_h,
+                                   (MODE == BIN_EMIT) ? __ldg(a.line_fill_offset + l) : 0u, 0u};
+                sink.add_fill(from, make_float2(from.x + vx * 1.0f, from.y + vy * 1.0f), from_tx, from_ty);
+                emitted = sink.emitted;
+            } else {
+                uint32_t q = atomicAdd(&s_queued, 1u);
+                s_line[q] = make_float4(from.x, from.y, to.x, to.y);
+                s_index[q] = l;
+                emitted = 0xffffffffu; // counted by whichever thread walks it
+            }
+        }
+        if (MODE == BIN_COUNT && a.line_fill_count && emitted != 0xffffffffu) a.line_fill_count[l] = emitted;
+    }
+    __syncthreads();
+    // Long walks, compacted: thread q takes the q-th queued line.
+    const uint32_t queued = s_queued;
+    for (uint32_t q = threadIdx.x; q < queued; q += BIN_THREADS) {
+        const float4 seg = s_line[q];
+        const uint32_t li = s_index[q];
+        const PathInfo path = load_path(b.paths, __ldg(a.line_path + li));
+        const int rect_w = path.max_x - path.min_x, rect_h = path.max_y - path.min_y;
+        float2 from = make_float2(seg.x, seg.y), to = make_float2(seg.z, seg.w);
+        int from_tx = cvtps(floorf(from.x * recip)), from_ty = cvtps(floorf(from.y * recip));
+        int to_tx = cvtps(floorf(to.x * recip)), to_ty = cvtps(floorf(to.y * recip));
+        BinSink<MODE> sink{a, path, rect_w, rect_h, (MODE == BIN_EMIT) ? __ldg(a.line_fill_offset + li) : 0u, 0u};
+        walk_line(from, to, from_tx, from_ty, to_tx, to_ty, sink);
+        if (MODE == BIN_COUNT && a.line_fill_count) a.line_fill_count[li] = sink.emitted;
+    }
+}
+
+int launch_bin(int mode, const BatchDev &b, const BinArgs &args, cudaStream_t stream) {
     if (args.n_lines == 0) return 0;
-    unsigned grid = div_up(args.n_lines, 128);
-    if (emit)
-        k_bin<true><<<grid, 128, 0, stream>>>(b, args);
+    unsigned grid = div_up(args.n_lines, BIN_THREADS);
+    if (mode == BIN_EMIT_LIVE)
+        k_bin<BIN_EMIT_LIVE><<<grid, BIN_THREADS, 0, stream>>>(b, args);
+    else if (mode == BIN_COUNT)
+        k_bin<BIN_COUNT><<<grid, BIN_THREADS, 0, stream>>>(b, args);
     else
-        k_bin<false><<<grid, 128, 0, stream>>>(b, args);
+        k_bin<BIN_EMIT><<<grid, BIN_THREADS, 0, stream>>>(b, args);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

@@ -88,20 +88,21 @@ struct BinArgs {
     const uint32_t *n_lines_dev; // optional: actual count on the device, min(*n_lines_dev, n_lines) is used
     uint32_t *tile_word;         // count (24) | backdrop delta (8)
     int32_t *col_backdrop;
-    // count pass
-    uint32_t *line_fill_count;   // optional (parity dumps): fills per line, for emission-order offsets
-    // emit pass (runs after propagate + z-cull)
-    const uint32_t *tile_fb;     // 0xffffffff = tile culled: its fills are not stored (NULL: store all)
-    uint32_t *tile_fill_pos;     // running cursor, initialised with the exclusive scan of live counts
-    PackedFill *fills;           // tile-grouped, surviving tiles only
+    // BIN_COUNT: optional fills per line (parity dumps), for emission-order offsets
+    uint32_t *line_fill_count;
+    // BIN_EMIT_LIVE / BIN_EMIT
+    const uint32_t *tile_fb;     // BIN_EMIT_LIVE: 0xffffffff = tile culled, its fills are not stored
+    uint32_t *tile_fill_pos;     // running cursor, initialised with the exclusive scan of the (live) counts
+    PackedFill *fills;           // tile-grouped
     uint32_t fill_capacity;
-    // parity dumps only (all three or none)
+    // BIN_EMIT only (parity dumps)
     const uint32_t *line_fill_offset;
     uint32_t *tile_first_fill;   // min emission index per tile
     EmitFill *fills_emit;        // every fill in emission order
     uint32_t emit_capacity;
 };
-int launch_bin(bool emit, const BatchDev &b, const BinArgs &args, cudaStream_t stream);
+// mode: 0 = BIN_EMIT_LIVE (production emit), 1 = BIN_COUNT, 2 = BIN_EMIT (parity dumps).
+int launch_bin(int mode, const BatchDev &b, const BinArgs &args, cudaStream_t stream);
 
 int launch_sum_fill_counts(const uint32_t *tile_word, uint32_t n_tiles, unsigned long long *total, cudaStream_t stream);
 

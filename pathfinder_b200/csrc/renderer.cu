@@ -455,11 +455,14 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     r->col_backdrop.ensure(n_cols + 1, 1.25);
     r->tile_fb.ensure(n_tiles + 1, 1.25);
     PF_CUDA_CHECK(cudaMemsetAsync(r->tile_word.ptr, 0, (size_t)n_tiles * 4, st));
-    if (c.has_initial_backdrops)
-        PF_CUDA_CHECK(cudaMemcpyAsync(r->col_backdrop.ptr, r->col_backdrop_init.ptr, (size_t)n_cols * 4,
-                                      cudaMemcpyDeviceToDevice, st));
-    else
-        PF_CUDA_CHECK(cudaMemsetAsync(r->col_backdrop.ptr, 0, (size_t)n_cols * 4, st));
+    auto reset_col_backdrops = [&]() {
+        if (c.has_initial_backdrops)
+            PF_CUDA_CHECK(cudaMemcpyAsync(r->col_backdrop.ptr, r->col_backdrop_init.ptr, (size_t)n_cols * 4,
+                                          cudaMemcpyDeviceToDevice, st));
+        else
+            PF_CUDA_CHECK(cudaMemsetAsync(r->col_backdrop.ptr, 0, (size_t)n_cols * 4, st));
+    };
+    reset_col_backdrops();
     if (r->debug_lists) {
         r->tile_first_fill.ensure(n_tiles + 1, 1.25);
         PF_CUDA_CHECK(cudaMemsetAsync(r->tile_first_fill.ptr, 0xff, (size_t)n_tiles * 4, st));
@@ -509,8 +512,9 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     ba.tile_word = r->tile_word.ptr;
     ba.col_backdrop = r->col_backdrop.ptr;
     ba.line_fill_count = r->debug_lists ? r->line_fill_offset.ptr : nullptr;
-    launches += launch_bin(false, b, ba, st);
-    if (r->debug_lists) // emission-order offsets (and the total fill count), only needed for the parity dumps
+    launches += launch_bin(1 /* BIN_COUNT */, b, ba, st);
+    uint32_t emit_bound = 0;
+    if (r->debug_lists) // emission-order offsets and the total fill count, for the parity dumps
         launches += exclusive_scan(LoadU32{r->line_fill_offset.ptr}, r->line_fill_offset.ptr, line_bound,
                                    r->counters.ptr + C_FILLS, r->scan_scratch, st, n_lines_dev);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[3], st));
@@ -532,9 +536,9 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     else
         launches += exclusive_scan(LoadLiveCount{r->tile_word.ptr, r->tile_fb.ptr}, r->tile_fill_pos.ptr, n_tiles,
                                    r->counters.ptr + C_VISIBLE_FILLS, r->scan_scratch, st);
-    uint32_t entry_bound, fill_bound, emit_bound = 0;
+    uint32_t entry_bound, fill_bound;
     if (sizing) {
-        if (n_tiles) read_counter(r, 0); // one read-back of all three totals
+        if (n_tiles) read_counter(r, 0); // one read-back of all totals
         entry_bound = n_tiles ? r->counters_host.ptr[C_ENTRIES] : 0;
         fill_bound = n_tiles ? r->counters_host.ptr[C_VISIBLE_FILLS] : 0;
         r->entries.ensure(entry_bound + 1, 1.25);
@@ -548,11 +552,10 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
         fill_bound = bound_of(c.n_visible_fills, r->fills.capacity);
         if (r->debug_lists) emit_bound = bound_of(c.n_fills, r->fills_emit.capacity);
     }
-
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[5], st));
 
     // ---- bin, emit pass: fills of surviving tiles into their tile-grouped runs.
-    ba.tile_fb = r->debug_lists ? nullptr : r->tile_fb.ptr;
+    ba.tile_fb = r->tile_fb.ptr;
     ba.tile_fill_pos = r->tile_fill_pos.ptr;
     ba.fills = r->fills.ptr;
     ba.fill_capacity = fill_bound;
@@ -561,8 +564,10 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
         ba.tile_first_fill = r->tile_first_fill.ptr;
         ba.fills_emit = r->fills_emit.ptr;
         ba.emit_capacity = emit_bound;
+        launches += launch_bin(2 /* BIN_EMIT */, b, ba, st);
+    } else {
+        launches += launch_bin(0 /* BIN_EMIT_LIVE */, b, ba, st);
     }
-    launches += launch_bin(true, b, ba, st);
     launches += launch_list_emit(b, r->tile_fb.ptr, r->tile_word.ptr, r->tile_fill_pos.ptr, r->fb_start.ptr,
                                  r->fb_cursor.ptr, r->entries.ptr, entry_bound, nullptr, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[6], st));
@@ -614,7 +619,7 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     r->last_alpha_ids_valid = false;
     r->last_fb = fb;
     r->stats.path_count += b.n_paths;
-    r->stats.fill_count += n_fills; // 0 unless debug lists are on; PFCudaRendererGetStats fills it in lazily
+    r->stats.fill_count += n_fills;
     r->stats.total_tile_count += n_tiles;
     r->stats.input_segment_count += n_segments;
     r->stats.line_segment_count += n_lines;
@@ -992,7 +997,8 @@ PFCudaStatus PFCudaRendererGetStats(PFCudaRendererRef r, PFCudaRenderStats *stat
     return guarded(r, [&]() {
         if (!stats) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null stats");
         if (r->stats.fill_count == 0 && r->batches_drawn == 1 && !r->in_scene && r->last_batch.n_tiles) {
-            // RenderStats.fill_count (all fills, before occlusion culling): summed on demand.
+            // RenderStats.fill_count (all fills, before occlusion culling) is not needed to render:
+            // summed on demand from the per-tile counts.
             unsigned long long *total = reinterpret_cast<unsigned long long *>(r->counters.ptr + 8);
             PF_CUDA_CHECK(cudaMemsetAsync(total, 0, sizeof(*total), r->stream));
             launch_sum_fill_counts(r->tile_word.ptr, r->last_batch.n_tiles, total, r->stream);
