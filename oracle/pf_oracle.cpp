@@ -659,7 +659,8 @@ struct PFOBuilt {
     RectI z_rect{0, 0, 0, 0};
     uint32_t alpha_tile_count = 0;
     uint64_t n_lines = 0, n_input_segments = 0, n_bbox_tiles = 0;
-    double seconds = 0;
+    double seconds = 0;       // build_paths_on_cpu + build_tile_batches (the reference's cpu_build_time)
+    double seconds_paths = 0; // the per-path (parallel) part alone
 };
 
 extern "C" {
@@ -705,6 +706,7 @@ PFOBuilt *pfo_build(const PFOScene *scene, const PFOBuildOptions *options, int n
     };
     run(true, s.n_clip_paths, b->clip_paths);
     run(false, s.n_draw_paths, b->draw_paths);
+    b->seconds_paths = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
     // build_tile_batches, D3D9 level (builder.rs:886-1056): one batch (solid colours only).
     RectI zr = round_rect_out_to_tile_bounds(ctx.view_box); // builder.rs:949-953 uses scene.view_box()
@@ -730,6 +732,10 @@ PFOBuilt *pfo_build(const PFOScene *scene, const PFOBuildOptions *options, int n
             if (cl.dest_tile_id != INVALID_ALPHA && cl.src_tile_id != INVALID_ALPHA) b->clips.push_back(cl);
     }
 
+    // cpu_build_time stops here: the reference hands each path's Vec<Fill> to the listener by move
+    // (builder.rs:320-325); concatenating them below is only this oracle's output format.
+    b->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
     // AddFillsD3D9 payloads, in path order (builder.rs:320-325).
     size_t nf = 0;
     for (const BuiltPath &bp : b->clip_paths) nf += bp.fills.size();
@@ -749,7 +755,6 @@ PFOBuilt *pfo_build(const PFOScene *scene, const PFOBuildOptions *options, int n
     gather(b->draw_paths);
     b->fill_path_offsets.push_back((uint32_t)b->fills.size());
     b->alpha_tile_count = ctx.next_alpha_tile.load();
-    b->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return b;
 }
 
@@ -775,6 +780,7 @@ uint64_t pfo_line_segment_count(const PFOBuilt *b) { return b->n_lines; }
 uint64_t pfo_input_segment_count(const PFOBuilt *b) { return b->n_input_segments; }
 uint64_t pfo_bbox_tile_count(const PFOBuilt *b) { return b->n_bbox_tiles; }
 double pfo_build_seconds(const PFOBuilt *b) { return b->seconds; }
+double pfo_build_seconds_paths(const PFOBuilt *b) { return b->seconds_paths; }
 
 size_t pfo_path_lines(const PFOBuilt *b, uint32_t path, float *out, size_t cap) {
     const BuiltPath &bp = path < b->clip_paths.size() ? b->clip_paths[path] : b->draw_paths[path - b->clip_paths.size()];

@@ -114,6 +114,7 @@ uint64_t pfo_line_segment_count(const PFOBuilt *b);  /* process_line_segment cal
 uint64_t pfo_input_segment_count(const PFOBuilt *b); /* contour iterator items */
 uint64_t pfo_bbox_tile_count(const PFOBuilt *b);     /* sum of dense tile map areas */
 double pfo_build_seconds(const PFOBuilt *b);         /* wall time of the build (cpu_build_time) */
+double pfo_build_seconds_paths(const PFOBuilt *b);   /* its per-path (parallel) part */
 
 /* Flattened line segments of one path in emission order (for dice parity). Returns count;
  * copies up to cap segments (4 floats each) into out. path index is in [0, n_clip + n_draw). */

@@ -76,7 +76,8 @@ def lib():
                           ("pfo_clips", C.c_void_p), ("pfo_alpha_tile_count", C.c_uint32),
                           ("pfo_line_segment_count", C.c_uint64),
                           ("pfo_input_segment_count", C.c_uint64),
-                          ("pfo_bbox_tile_count", C.c_uint64), ("pfo_build_seconds", C.c_double)]:
+                          ("pfo_bbox_tile_count", C.c_uint64), ("pfo_build_seconds", C.c_double),
+                          ("pfo_build_seconds_paths", C.c_double)]:
             f = getattr(l, name)
             f.restype = res
             f.argtypes = [C.c_void_p]
