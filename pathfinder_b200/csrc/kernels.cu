@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace pf {
 
@@ -532,43 +533,74 @@ int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_
 // shaders/d3d11/sort.cs.glsl:60-95 and needs no global sort.
 // ---------------------------------------------------------------------------------------------
 
+// Also allocates the tile-grouped fill runs: a block sums the fill counts of its surviving tiles,
+// reserves that many slots from a global cursor with ONE atomic, and hands each tile its run start
+// from a block-local scan. Runs of different blocks land in arbitrary order, which nothing depends
+// on (every reader goes through tile_fill_pos / TileEntry.fill_end) — and the device-wide scan over
+// all bbox tiles that used to do this is gone.
+constexpr int LIST_ITEMS = 8; // tiles per thread
+constexpr int LIST_TILE = 256 * LIST_ITEMS;
+
 __global__ void __launch_bounds__(256)
     k_list_count(BatchDev b, const uint32_t *__restrict__ tile_word, const int32_t *__restrict__ z_buffer,
-                 uint32_t *__restrict__ tile_fb, uint32_t *__restrict__ fb_count) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in_range = t < b.n_tiles;
-    uint32_t word = in_range ? __ldg(tile_word + t) : 0;
-    // Empty tiles are never drawn (renderer/src/builder.rs:1014-1016).
-    const bool nonempty = (word & 0x00ffffffu) != 0 || (word >> 24) != 0;
-    if (!__any_sync(0xffffffffu, nonempty)) {
-        if (in_range) tile_fb[t] = 0xffffffffu;
-        return;
-    }
-    uint32_t p = nonempty ? search_coarse(b.path_tile_offset, b.tile_index, t) : 0;
-    uint32_t result = 0xffffffffu;
-    if (nonempty) {
-        const PathInfo path = load_path(b.paths, p);
-        int w = path.max_x - path.min_x;
-        uint32_t local = t - path.tile_offset;
-        int x = (int)(local % (uint32_t)w), y = (int)(local / (uint32_t)w);
-        int fx = path.min_x + x - b.fb.min_x, fy = path.min_y + y - b.fb.min_y;
-        int fb_w = b.fb.max_x - b.fb.min_x, fb_h = b.fb.max_y - b.fb.min_y;
-        if (fx >= 0 && fy >= 0 && fx < fb_w && fy < fb_h) {
-            uint32_t fbi = (uint32_t)(fy * fb_w + fx);
-            // z-cull: dropped iff path_id < z (shaders/d3d11/sort.cs.glsl:74, d3d9/tile.vs.glsl:52-56)
-            if ((int32_t)path.global_path_id >= __ldg(z_buffer + fbi)) {
-                result = fbi;
-                atomicAdd(fb_count + fbi, 1u);
+                 uint32_t *__restrict__ tile_fb, uint32_t *__restrict__ fb_count,
+                 uint32_t *__restrict__ tile_fill_pos, uint32_t *__restrict__ fill_cursor, int keep_all_fills) {
+    __shared__ uint32_t smem[256 / 32 + 1];
+    __shared__ uint32_t s_base;
+    const uint32_t base = blockIdx.x * LIST_TILE + threadIdx.x;
+    const int fb_w = b.fb.max_x - b.fb.min_x, fb_h = b.fb.max_y - b.fb.min_y;
+    uint32_t run[LIST_ITEMS];
+    uint32_t total = 0;
+#pragma unroll
+    for (int r = 0; r < LIST_ITEMS; r++) {
+        const uint32_t t = base + (uint32_t)r * 256u;
+        run[r] = 0;
+        if (t >= b.n_tiles) continue;
+        const uint32_t word = __ldg(tile_word + t);
+        const uint32_t count = word & 0x00ffffffu;
+        uint32_t result = 0xffffffffu;
+        // Empty tiles are never drawn (renderer/src/builder.rs:1014-1016).
+        if (count != 0 || (word >> 24) != 0) {
+            const uint32_t p = search_coarse(b.path_tile_offset, b.tile_index, t);
+            const PathInfo path = load_path(b.paths, p);
+            const int w = path.max_x - path.min_x;
+            const uint32_t local = t - path.tile_offset;
+            const int x = (int)(local % (uint32_t)w), y = (int)(local / (uint32_t)w);
+            const int fx = path.min_x + x - b.fb.min_x, fy = path.min_y + y - b.fb.min_y;
+            if (fx >= 0 && fy >= 0 && fx < fb_w && fy < fb_h) {
+                const uint32_t fbi = (uint32_t)(fy * fb_w + fx);
+                // z-cull: dropped iff path_id < z (shaders/d3d11/sort.cs.glsl:74, d3d9/tile.vs.glsl:52-56)
+                if ((int32_t)path.global_path_id >= __ldg(z_buffer + fbi)) {
+                    result = fbi;
+                    atomicAdd(fb_count + fbi, 1u);
+                }
             }
         }
+        tile_fb[t] = result;
+        // Occlusion culling before fill emission: culled tiles get no run (parity dumps keep all).
+        run[r] = (keep_all_fills || result != 0xffffffffu) ? count : 0u;
+        total += run[r];
     }
-    if (in_range) tile_fb[t] = result;
+    uint32_t block_total;
+    uint32_t pos = block_exclusive_scan(total, smem, &block_total);
+    if (threadIdx.x == 0) s_base = block_total ? atomicAdd(fill_cursor, block_total) : 0u;
+    __syncthreads();
+    pos += s_base;
+#pragma unroll
+    for (int r = 0; r < LIST_ITEMS; r++) {
+        if (run[r]) {
+            tile_fill_pos[base + (uint32_t)r * 256u] = pos;
+            pos += run[r];
+        }
+    }
 }
 
 int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
-                      uint32_t *fb_count, cudaStream_t stream) {
+                      uint32_t *fb_count, uint32_t *tile_fill_pos, uint32_t *fill_cursor, bool keep_all_fills,
+                      cudaStream_t stream) {
     if (b.n_tiles == 0) return 0;
-    k_list_count<<<div_up(b.n_tiles, 256), 256, 0, stream>>>(b, tile_word, z_buffer, tile_fb, fb_count);
+    k_list_count<<<div_up(b.n_tiles, LIST_TILE), 256, 0, stream>>>(b, tile_word, z_buffer, tile_fb, fb_count,
+                                                                    tile_fill_pos, fill_cursor, keep_all_fills ? 1 : 0);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

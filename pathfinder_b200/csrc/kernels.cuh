@@ -111,8 +111,11 @@ int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_
 
 // tile_fb[t] = framebuffer tile index if the tile is non-empty, inside the framebuffer and not
 // z-culled, else 0xffffffff; fb_count[fb] += 1 for every survivor.
+// It also reserves each surviving tile's run in the tile-grouped fill array: tile_fill_pos[t] = run
+// start, *fill_cursor += total (keep_all_fills: culled tiles keep their runs, for the parity dumps).
 int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
-                      uint32_t *fb_count, cudaStream_t stream);
+                      uint32_t *fb_count, uint32_t *tile_fill_pos, uint32_t *fill_cursor, bool keep_all_fills,
+                      cudaStream_t stream);
 // Appends one TileEntry per surviving tile to its framebuffer tile's run [fb_start, fb_start + count).
 int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t *tile_word,
                      const uint32_t *tile_fill_pos, const uint32_t *fb_start, uint32_t *fb_cursor,

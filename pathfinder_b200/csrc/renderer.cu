@@ -525,17 +525,12 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
 
     // ---- sort: z-cull + per-framebuffer-tile runs (count -> scan -> append); the run itself is
     // sorted into draw order inside the fused kernel.
-    launches += launch_list_count(b, r->tile_word.ptr, r->z_buffer.ptr, r->tile_fb.ptr, r->fb_count.ptr, st);
+    // (the same kernel reserves the fill runs of the surviving tiles: occlusion culling before fill
+    // emission; with the parity dumps on, every alpha tile keeps its fills so its mask can be read back)
+    launches += launch_list_count(b, r->tile_word.ptr, r->z_buffer.ptr, r->tile_fb.ptr, r->fb_count.ptr,
+                                  r->tile_fill_pos.ptr, r->counters.ptr + C_VISIBLE_FILLS, r->debug_lists, st);
     launches += exclusive_scan(LoadU32{r->fb_count.ptr}, r->fb_start.ptr, n_fb, r->counters.ptr + C_ENTRIES,
                                r->scan_scratch, st);
-    // Fill runs only for tiles that survived the cull (occlusion culling before fill emission).
-    // With the parity dumps on, every alpha tile keeps its fills so its mask can be read back.
-    if (r->debug_lists)
-        launches += exclusive_scan(LoadLow24{r->tile_word.ptr}, r->tile_fill_pos.ptr, n_tiles,
-                                   r->counters.ptr + C_VISIBLE_FILLS, r->scan_scratch, st);
-    else
-        launches += exclusive_scan(LoadLiveCount{r->tile_word.ptr, r->tile_fb.ptr}, r->tile_fill_pos.ptr, n_tiles,
-                                   r->counters.ptr + C_VISIBLE_FILLS, r->scan_scratch, st);
     uint32_t entry_bound, fill_bound;
     if (sizing) {
         if (n_tiles) read_counter(r, 0); // one read-back of all totals
