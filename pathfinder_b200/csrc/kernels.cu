@@ -735,6 +735,7 @@ __device__ __forceinline__ void blend(float4 &d, float4 base, float alpha) {
 // prefix); per-pixel state is only expanded at the first tile that has fills.
 constexpr int COMPOSITE_WARPS = 2;       // tiles per block, horizontally adjacent
 constexpr int COMPOSITE_SORT_CAP = 128;  // entries sorted in shared memory; longer lists use the slow path
+constexpr int COMPOSITE_BATCH = 1;       // consecutive tiles a warp reserves per atomic
 
 template <bool LOAD_DEST>
 __global__ void __launch_bounds__(32 * COMPOSITE_WARPS) k_composite(CompositeArgs a) {
@@ -747,11 +748,14 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS) k_composite(CompositeArg
     const uint32_t n_work = (uint32_t)fb_w * (uint32_t)(a.tile_y1 - a.tile_y0);
     // Persistent warps: tiles differ wildly in depth, so every warp pulls its next tile from a
     // global counter instead of owning a fixed one (row-major, so neighbours stay neighbours).
-    for (;;) {
-    uint32_t work = 0;
-    if (lane == 0) work = atomicAdd(a.work_counter, 1u);
-    work = __shfl_sync(0xffffffffu, work, 0);
-    if (work >= n_work) return;
+    uint32_t work = 0, work_end = 0; // [work, work_end): tiles this warp has reserved
+    for (;; work++) {
+    if (work >= work_end) {
+        if (lane == 0) work = atomicAdd(a.work_counter, (uint32_t)COMPOSITE_BATCH);
+        work = __shfl_sync(0xffffffffu, work, 0);
+        work_end = min(work + (uint32_t)COMPOSITE_BATCH, n_work);
+        if (work >= n_work) return;
+    }
     const int tile_col = (int)(work % (uint32_t)fb_w);
     const int ty = a.tile_y0 + (int)(work / (uint32_t)fb_w); // absolute tile y
     const int tx = a.fb.min_x + tile_col;
