@@ -239,11 +239,15 @@ def main():
         f.renderer = api.CudaRenderer((size, size), background_color=(1.0, 1.0, 1.0, 1.0), device_ordinal=local_rank)
         f.renderer.set_stream(stream.cuda_stream)
         f.renderer.set_dest_device_pointer(f.full.data_ptr(), size * 4)
+        f.scene = api.Scene.from_flat(flat)
+        f.options = api.BuildOptions(transform=None if xf is None else api.Transform2F(*xf))
+        # The metric counts the flattened segments of the WHOLE frame (fixed work, independent of
+        # N): one untimed full-frame render gives the count before the strip is set.
+        f.scene.build_and_render(f.renderer, f.options)
+        f.full_stats = f.renderer.stats()
         if world > 1:
             f.renderer.set_strip(f.y0, f.y1)
             f.strip_view = f.full[f.y0 * 16:f.y1 * 16]
-        f.scene = api.Scene.from_flat(flat)
-        f.options = api.BuildOptions(transform=None if xf is None else api.Transform2F(*xf))
         f.host = torch.empty((size, size, 4), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
         frames.append(f)
 
@@ -287,10 +291,7 @@ def main():
     per_scene = {}
     for f in frames:
         s = f.renderer.stats()
-        seg = s["line_segment_count"]
-        if dist is not None:  # strips flatten the same segments; count each once: take rank 0's view
-            pass
-        seg_per_step += seg
+        seg_per_step += f.full_stats["line_segment_count"]
         launches_per_step += s["drawcall_count"]
         per_scene[f.name] = s
 

@@ -59,6 +59,7 @@ struct BatchCache {
     bool has_initial_backdrops = false;
     bool counts_valid = false; // n_lines / n_fills / n_entries hold the last frame's totals
     uint32_t n_lines = 0, n_fills = 0, n_entries = 0, n_visible_fills = 0;
+    uint32_t command_paths = 0, command_segments = 0; // as sent (before strip culling)
 };
 
 struct StageTimer {
@@ -313,60 +314,65 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
     uint32_t *h_tile_off = h_seg_first + (P + 1);
     uint32_t *h_col_off = h_tile_off + (P + 1);
     uint64_t n_tiles64 = 0, n_cols64 = 0;
-    const uint32_t n_segments = batch.segment_count;
     const uint32_t n_paints = (uint32_t)r->n_paints;
     bool bad_paint = false;
+    uint32_t kept = 0, n_segments = 0;
     for (uint32_t i = 0; i < P; i++) {
         const PFPropagateMetadataD3D11 &pm = info.propagate_metadata[i];
         const PFDiceMetadataD3D11 &dm = info.dice_metadata[i];
         const PFTilePathInfoD3D11 &tp = info.tile_path_info[i];
-        PathInfo &pi = h_paths[i];
+        bad_paint |= tp.color >= n_paints;
+        PathInfo pi;
         pi.min_x = pm.tile_rect.origin.x;
         pi.max_x = pm.tile_rect.lower_right.x;
         pi.min_y = pm.tile_rect.origin.y;
         pi.max_y = pm.tile_rect.lower_right.y;
-        if (pi.max_x < pi.min_x) pi.max_x = pi.min_x;
         // Strip restriction: rows above the strip feed the column backdrops exactly like rows
         // above the path rect do in the reference (builder.rs:609-612); rows below are ignored.
         if (pi.min_y < strip_y0) pi.min_y = strip_y0;
         if (pi.max_y > strip_y1) pi.max_y = strip_y1;
-        if (pi.max_y < pi.min_y) pi.max_y = pi.min_y;
-        if (pi.max_y == pi.min_y) pi.max_x = pi.min_x; // no tiles: no columns either
+        // A path without a tile in this strip contributes nothing (every fill is culled by
+        // add_fill, every backdrop adjustment by the rect test): drop it, segments included, so
+        // dice / bin / propagate only see the paths that reach the strip.
+        if (pi.max_x <= pi.min_x || pi.max_y <= pi.min_y) continue;
+        const uint32_t seg_end = i + 1 < P ? info.dice_metadata[i + 1].first_batch_segment_index : batch.segment_count;
         pi.tile_offset = (uint32_t)n_tiles64;
         pi.col_offset = (uint32_t)n_cols64;
-        pi.seg_batch_first = dm.first_batch_segment_index;
+        pi.seg_batch_first = n_segments;
         pi.seg_global_first = dm.first_global_segment_index;
         pi.global_path_id = dm.global_path_id;
         pi.paint_ctrl = (uint32_t)tp.color | ((uint32_t)tp.ctrl << 16) | ((pm.z_write ? 1u : 0u) << 24);
         pi.clip_path_index = pm.clip_path_index;
-        pi.pad = 0;
-        h_seg_first[i] = dm.first_batch_segment_index;
-        h_tile_off[i] = pi.tile_offset;
-        h_col_off[i] = pi.col_offset;
+        pi.pad = i; // index in the command's arrays (initial backdrops are keyed by it)
+        h_paths[kept] = pi;
+        h_seg_first[kept] = pi.seg_batch_first;
+        h_tile_off[kept] = pi.tile_offset;
+        h_col_off[kept] = pi.col_offset;
+        kept++;
+        n_segments += seg_end - dm.first_batch_segment_index;
         n_tiles64 += (uint64_t)(pi.max_x - pi.min_x) * (uint64_t)(pi.max_y - pi.min_y);
         n_cols64 += (uint64_t)(pi.max_x - pi.min_x);
-        bad_paint |= tp.color >= n_paints;
     }
     if (bad_paint) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "paint id outside the uploaded texture metadata");
     if (n_tiles64 >= 0xfffffff0ull) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "more than 2^32 bbox tiles in one batch");
     const uint32_t n_tiles = (uint32_t)n_tiles64, n_cols = (uint32_t)n_cols64;
-    h_seg_first[P] = n_segments;
-    h_tile_off[P] = n_tiles;
-    h_col_off[P] = n_cols;
+    h_seg_first[kept] = n_segments;
+    h_tile_off[kept] = n_tiles;
+    h_col_off[kept] = n_cols;
     uint32_t *h_seg_table = h_col_off + (P + 1);
     uint32_t *h_tile_table = h_seg_table + seg_table_n;
     uint32_t *h_col_table = h_tile_table + tile_table_cap;
-    auto build_table = [P](const uint32_t *offsets, uint32_t count, int shift, uint32_t *table) {
-        // table[k] = largest p < P with offsets[p] <= k << shift (offsets[0] == 0)
+    auto build_table = [kept](const uint32_t *offsets, uint32_t count, int shift, uint32_t *table) {
+        // table[k] = largest p < kept with offsets[p] <= k << shift (offsets[0] == 0)
         const size_t n = ((size_t)count >> shift) + 2;
         uint32_t p = 0;
         for (size_t k = 0; k < n; k++) {
             const uint64_t x = (uint64_t)k << shift;
-            while (p + 1 < P && offsets[p + 1] <= x) p++;
+            while (p + 1 < kept && offsets[p + 1] <= x) p++;
             table[k] = p;
         }
     };
-    if (P) {
+    if (kept) {
         build_table(h_seg_first, n_segments, SEG_SHIFT, h_seg_table);
         build_table(h_tile_off, n_tiles, TILE_SHIFT, h_tile_table);
         build_table(h_col_off, n_cols, COL_SHIFT, h_col_table);
@@ -390,7 +396,7 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
     b.seg_index = CoarseIndex{b.path_col_offset + (P + 1), SEG_SHIFT};
     b.tile_index = CoarseIndex{b.seg_index.table + seg_table_n, TILE_SHIFT};
     b.col_index = CoarseIndex{b.tile_index.table + tile_table_cap, COL_SHIFT};
-    b.n_paths = P;
+    b.n_paths = kept;
     b.n_segments = n_segments;
     b.n_tiles = n_tiles;
     b.n_columns = n_cols;
@@ -410,10 +416,12 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
     r->col_backdrop_init.ensure(n_cols + 1, 1.25);
     if (info.backdrops && info.backdrop_count) {
         std::vector<int32_t> init(n_cols, 0);
+        std::vector<uint32_t> kept_index(P, 0xffffffffu);
+        for (uint32_t k = 0; k < kept; k++) kept_index[h_paths[k].pad] = k;
         for (size_t i = 0; i < info.backdrop_count; i++) {
             const PFBackdropInfoD3D11 &bi = info.backdrops[i];
-            if (bi.initial_backdrop == 0 || bi.path_index >= P) continue;
-            const PathInfo &pi = h_paths[bi.path_index];
+            if (bi.initial_backdrop == 0 || bi.path_index >= P || kept_index[bi.path_index] == 0xffffffffu) continue;
+            const PathInfo &pi = h_paths[kept_index[bi.path_index]];
             if (bi.tile_x_offset < 0 || bi.tile_x_offset >= pi.max_x - pi.min_x) continue;
             init[pi.col_offset + (uint32_t)bi.tile_x_offset] = bi.initial_backdrop;
             has_initial_backdrops = true;
@@ -660,11 +668,13 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
                      c.scene_generation == r->scene_generation && c.paint_generation == r->paint_generation &&
                      c.strip_y0 == strip_y0 && c.strip_y1 == strip_y1 &&
                      memcmp(&c.batch.fb, &fb, sizeof(fb)) == 0 && memcmp(&c.batch.view_box, &vb, sizeof(vb)) == 0 &&
-                     c.batch.n_paths == batch.path_count && c.batch.n_segments == batch.segment_count;
+                     c.command_paths == batch.path_count && c.command_segments == batch.segment_count;
     if (!hit) {
         c.valid = false;
         upload_batch_metadata(r, batch, fb, strip_y0, strip_y1, c.batch, c.has_initial_backdrops);
         c.key = batch.content_key;
+        c.command_paths = batch.path_count;
+        c.command_segments = batch.segment_count;
         c.scene_generation = r->scene_generation;
         c.paint_generation = r->paint_generation;
         c.strip_y0 = strip_y0;
