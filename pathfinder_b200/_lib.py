@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpf_cuda.so")
+# PF_CUDA_LIB selects another build of the same library (A/B measurements); default: the in-tree build.
+LIB_PATH = os.environ.get("PF_CUDA_LIB") or os.path.join(_HERE, "libpf_cuda.so")
 
 
 class PFColorF(C.Structure):

@@ -321,8 +321,86 @@ struct BinSink {
     }
 };
 
-// process_line_segment (renderer/src/tiler.rs:202-308) after clipping, for a line that crosses
-// at least one tile boundary.
+// process_line_segment (renderer/src/tiler.rs:202-308) after clipping, for a line that crosses at
+// least one tile boundary, split into "advance the Amanatides-Woo state by one tile" (cheap, strictly
+// serial: t_max is accumulated) and "emit the fills / backdrop change of that tile" (the expensive
+// part, independent per tile).
+struct WalkState {
+    float2 from;
+    float vx, vy, t_max_x, t_max_y, t_delta_x, t_delta_y;
+    float2 cur;
+    int step_x, step_y, tx, ty, to_tx, to_ty, last_step; // step codes: 0 none, 1 X, 2 Y
+};
+struct WalkStep {
+    float2 cur, next;
+    int tx, ty, last_step, next_step;
+};
+
+__device__ __forceinline__ void walk_init(WalkState &w, float2 from, float2 to, int from_tx, int from_ty, int to_tx,
+                                          int to_ty) {
+    const float tile_size = 16.0f;
+    w.from = from;
+    w.vx = to.x - from.x, w.vy = to.y - from.y;
+    const bool neg_x = w.vx < 0.0f, neg_y = w.vy < 0.0f;
+    w.step_x = neg_x ? -1 : 1, w.step_y = neg_y ? -1 : 1;
+    const float first_cross_x = (float)(from_tx + (neg_x ? 0 : 1)) * tile_size;
+    const float first_cross_y = (float)(from_ty + (neg_y ? 0 : 1)) * tile_size;
+    w.t_max_x = (first_cross_x - from.x) / w.vx;
+    w.t_max_y = (first_cross_y - from.y) / w.vy;
+    w.t_delta_x = fabsf(tile_size / w.vx);
+    w.t_delta_y = fabsf(tile_size / w.vy);
+    w.cur = from;
+    w.tx = from_tx, w.ty = from_ty, w.to_tx = to_tx, w.to_ty = to_ty;
+    w.last_step = 0;
+}
+
+// Fills `st` with the current tile's step and moves to the next tile. Returns false after the last tile.
+__device__ __forceinline__ bool walk_advance(WalkState &w, WalkStep &st) {
+    int next_step;
+    if (w.t_max_x < w.t_max_y)
+        next_step = 1;
+    else if (w.t_max_x > w.t_max_y)
+        next_step = 2;
+    else
+        next_step = w.step_x > 0 ? 1 : 2;
+    const float next_t = fminf(next_step == 1 ? w.t_max_x : w.t_max_y, 1.0f);
+    if (w.tx == w.to_tx && w.ty == w.to_ty) next_step = 0;
+    const float2 next = make_float2(w.from.x + w.vx * next_t, w.from.y + w.vy * next_t);
+    st.cur = w.cur, st.next = next, st.tx = w.tx, st.ty = w.ty, st.last_step = w.last_step, st.next_step = next_step;
+    if (next_step == 0) return false;
+    if (next_step == 1) {
+        if (w.tx == w.to_tx) return false;
+        w.t_max_x += w.t_delta_x;
+        w.t_max_y += 0.0f;
+        w.tx += w.step_x;
+    } else {
+        if (w.ty == w.to_ty) return false;
+        w.t_max_x += 0.0f;
+        w.t_max_y += w.t_delta_y;
+        w.ty += w.step_y;
+    }
+    w.cur = next;
+    w.last_step = next_step;
+    return true;
+}
+
+template <typename Sink>
+__device__ __forceinline__ void walk_emit(const WalkStep &st, int step_x, int step_y, Sink &sink) {
+    const float tile_size = 16.0f;
+    sink.add_fill(st.cur, st.next, st.tx, st.ty);
+    if (step_y < 0 && st.next_step == 2) { // leaves through the top boundary
+        sink.add_fill(st.next, make_float2((float)st.tx * tile_size, (float)st.ty * tile_size), st.tx, st.ty);
+    } else if (step_y > 0 && st.last_step == 2) { // entered through the top boundary
+        sink.add_fill(make_float2((float)st.tx * tile_size, (float)st.ty * tile_size), st.cur, st.tx, st.ty);
+    }
+    if (step_x < 0 && st.last_step == 1) {
+        sink.adjust_backdrop(st.tx, st.ty, 1); // entered through the right boundary
+    } else if (step_x > 0 && st.next_step == 1) {
+        sink.adjust_backdrop(st.tx, st.ty, -1); // leaving through the right boundary
+    }
+}
+
+// The walk by one thread (the common case), written out so the state stays in registers.
 template <typename Sink>
 __device__ __forceinline__ void walk_line(float2 from, float2 to, int from_tx, int from_ty, int to_tx, int to_ty,
                                           Sink &sink) {
@@ -379,6 +457,32 @@ __device__ __forceinline__ void walk_line(float2 from, float2 to, int from_tx, i
     }
 }
 
+// The same walk by a whole warp, for lines that cross many tiles (long straight edges): every lane
+// advances the (cheap, serial) state in lock step and keeps the step whose index equals its lane;
+// after 32 steps the lanes emit their tiles' fills in parallel. Must be called by all 32 lanes with
+// identical arguments. Fill order within the line is not preserved (only BIN_EMIT needs it).
+template <typename Sink>
+__device__ __forceinline__ void walk_line_warp(float2 from, float2 to, int from_tx, int from_ty, int to_tx, int to_ty,
+                                               Sink &sink) {
+    const int lane = threadIdx.x & 31;
+    WalkState w;
+    walk_init(w, from, to, from_tx, from_ty, to_tx, to_ty);
+    bool more = true;
+    while (more) {
+        WalkStep mine;
+        bool have = false;
+        for (int k = 0; k < 32 && more; k++) {
+            WalkStep st;
+            more = walk_advance(w, st);
+            if (k == lane) mine = st, have = true;
+        }
+        if (have) walk_emit(mine, w.step_x, w.step_y, sink);
+        __syncwarp();
+    }
+}
+
+constexpr int BIN_LONG_STEPS = 12; // tile crossings from which a line is walked by a whole warp
+
 template <int MODE>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin(BatchDev b, BinArgs a) {
     __shared__ float4 s_line[BIN_THREADS];
@@ -418,33 +522,82 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(BatchDev b, BinArgs a) {
         if (MODE == BIN_COUNT && a.line_fill_count && emitted != 0xffffffffu) a.line_fill_count[l] = emitted;
     }
     __syncthreads();
-    // Long walks, compacted: thread q takes the q-th queued line.
+    // Long walks, compacted: thread q takes the q-th queued line. Lines that cross many tiles go to
+    // a global queue and are walked by whole warps in k_bin_long (kept out of this kernel so its
+    // register count, and with it the occupancy of the common path, stays low).
     const uint32_t queued = s_queued;
     for (uint32_t q = threadIdx.x; q < queued; q += BIN_THREADS) {
         const float4 seg = s_line[q];
         const uint32_t li = s_index[q];
-        const PathInfo path = load_path(b.paths, __ldg(a.line_path + li));
-        const int rect_w = path.max_x - path.min_x, rect_h = path.max_y - path.min_y;
         float2 from = make_float2(seg.x, seg.y), to = make_float2(seg.z, seg.w);
         int from_tx = cvtps(floorf(from.x * recip)), from_ty = cvtps(floorf(from.y * recip));
         int to_tx = cvtps(floorf(to.x * recip)), to_ty = cvtps(floorf(to.y * recip));
+        if (MODE != BIN_EMIT && a.long_queue && abs(to_tx - from_tx) + abs(to_ty - from_ty) >= BIN_LONG_STEPS) {
+            const uint32_t slot = atomicAdd(a.long_count, 1u);
+            if (slot < a.long_capacity) {
+                a.long_queue[slot] = li;
+                continue;
+            }
+        }
+        const PathInfo path = load_path(b.paths, __ldg(a.line_path + li));
+        const int rect_w = path.max_x - path.min_x, rect_h = path.max_y - path.min_y;
         BinSink<MODE> sink{a, path, rect_w, rect_h, (MODE == BIN_EMIT) ? __ldg(a.line_fill_offset + li) : 0u, 0u};
         walk_line(from, to, from_tx, from_ty, to_tx, to_ty, sink);
         if (MODE == BIN_COUNT && a.line_fill_count) a.line_fill_count[li] = sink.emitted;
     }
 }
 
+// Lines that cross >= BIN_LONG_STEPS tiles (long straight edges: the tiger at 4K has edges spanning
+// hundreds of tiles), one warp per line, warps pull from the queue the main kernel filled.
+template <int MODE>
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_long(BatchDev b, BinArgs a) {
+    const uint32_t n_long = min(*a.long_count, a.long_capacity);
+    const float recip = 1.0f / 16.0f;
+    for (;;) {
+        uint32_t k = 0;
+        if ((threadIdx.x & 31) == 0) k = atomicAdd(a.long_cursor, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_long) return;
+        const uint32_t li = a.long_queue[k];
+        const float4 seg = __ldg(a.lines + li);
+        const PathInfo path = load_path(b.paths, __ldg(a.line_path + li));
+        const int rect_w = path.max_x - path.min_x, rect_h = path.max_y - path.min_y;
+        float2 from = make_float2(seg.x, seg.y), to = make_float2(seg.z, seg.w);
+        clip_line(from, to, b.view_box); // it was accepted by the main kernel: same result
+        int from_tx = cvtps(floorf(from.x * recip)), from_ty = cvtps(floorf(from.y * recip));
+        int to_tx = cvtps(floorf(to.x * recip)), to_ty = cvtps(floorf(to.y * recip));
+        BinSink<MODE> sink{a, path, rect_w, rect_h, 0u, 0u};
+        walk_line_warp(from, to, from_tx, from_ty, to_tx, to_ty, sink);
+        if (MODE == BIN_COUNT && a.line_fill_count) {
+            uint32_t total = sink.emitted;
+            for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+            if ((threadIdx.x & 31) == 0) a.line_fill_count[li] = total;
+        }
+    }
+}
+
 int launch_bin(int mode, const BatchDev &b, const BinArgs &args, cudaStream_t stream) {
     if (args.n_lines == 0) return 0;
     unsigned grid = div_up(args.n_lines, BIN_THREADS);
+    int launches = 1;
+    if (mode != BIN_EMIT && args.long_queue) // reset the long-line queue of this pass
+        PF_CUDA_CHECK(cudaMemsetAsync(args.long_count, 0, 2 * sizeof(uint32_t), stream));
     if (mode == BIN_EMIT_LIVE)
         k_bin<BIN_EMIT_LIVE><<<grid, BIN_THREADS, 0, stream>>>(b, args);
     else if (mode == BIN_COUNT)
         k_bin<BIN_COUNT><<<grid, BIN_THREADS, 0, stream>>>(b, args);
     else
         k_bin<BIN_EMIT><<<grid, BIN_THREADS, 0, stream>>>(b, args);
+    if (mode != BIN_EMIT && args.long_queue) {
+        const unsigned long_grid = 148 * 2; // persistent warps; exits at once when the queue is empty
+        if (mode == BIN_EMIT_LIVE)
+            k_bin_long<BIN_EMIT_LIVE><<<long_grid, BIN_THREADS, 0, stream>>>(b, args);
+        else
+            k_bin_long<BIN_COUNT><<<long_grid, BIN_THREADS, 0, stream>>>(b, args);
+        launches++;
+    }
     PF_CUDA_CHECK(cudaGetLastError());
-    return 1;
+    return launches;
 }
 
 // Sum of the per-tile fill counts (RenderStats.fill_count), computed on demand.

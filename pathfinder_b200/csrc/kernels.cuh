@@ -100,6 +100,11 @@ struct BinArgs {
     uint32_t *tile_first_fill;   // min emission index per tile
     EmitFill *fills_emit;        // every fill in emission order
     uint32_t emit_capacity;
+    // Lines crossing many tiles are queued here by k_bin and walked by whole warps in k_bin_long.
+    uint32_t *long_queue;        // line indices (NULL: walk everything in k_bin)
+    uint32_t long_capacity;
+    uint32_t *long_count;        // two consecutive words: queue length, consumer cursor
+    uint32_t *long_cursor;
 };
 // mode: 0 = BIN_EMIT_LIVE (production emit), 1 = BIN_COUNT, 2 = BIN_EMIT (parity dumps).
 int launch_bin(int mode, const BatchDev &b, const BinArgs &args, cudaStream_t stream);

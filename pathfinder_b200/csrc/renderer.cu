@@ -62,6 +62,8 @@ struct BatchCache {
     uint32_t command_paths = 0, command_segments = 0; // as sent (before strip culling)
 };
 
+constexpr uint32_t LONG_QUEUE_CAPACITY = 1u << 18; // more long lines than this fall back to the per-thread walk
+
 struct StageTimer {
     cudaEvent_t ev[8];
     bool created = false;
@@ -122,6 +124,7 @@ struct PFCudaRenderer {
     DeviceBuffer<uint32_t> line_fill_offset; // [L]
     DeviceBuffer<uint32_t> tile_word, tile_fill_pos, tile_first_fill, tile_fb, tile_pos, tile_alpha_id;
     DeviceBuffer<int32_t> col_backdrop, col_backdrop_init;
+    DeviceBuffer<uint32_t> long_queue; // lines walked by whole warps (k_bin_long)
     DeviceBuffer<PackedFill> fills;
     DeviceBuffer<EmitFill> fills_emit;
     DeviceBuffer<int32_t> z_buffer;
@@ -191,6 +194,7 @@ void setup_tracking(PFCudaRenderer *r) {
     track(r, r->tile_alpha_id);
     track(r, r->col_backdrop);
     track(r, r->col_backdrop_init);
+    track(r, r->long_queue);
     track(r, r->fills);
     track(r, r->fills_emit);
     track(r, r->z_buffer);
@@ -520,6 +524,11 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     ba.tile_word = r->tile_word.ptr;
     ba.col_backdrop = r->col_backdrop.ptr;
     ba.line_fill_count = r->debug_lists ? r->line_fill_offset.ptr : nullptr;
+    r->long_queue.ensure(LONG_QUEUE_CAPACITY);
+    ba.long_queue = r->long_queue.ptr;
+    ba.long_capacity = LONG_QUEUE_CAPACITY;
+    ba.long_count = r->counters.ptr + 6;
+    ba.long_cursor = r->counters.ptr + 7;
     launches += launch_bin(1 /* BIN_COUNT */, b, ba, st);
     uint32_t emit_bound = 0;
     if (r->debug_lists) // emission-order offsets and the total fill count, for the parity dumps
