@@ -249,16 +249,29 @@ def main():
             f.renderer.set_strip(f.y0, f.y1)
             f.strip_view = f.full[f.y0 * 16:f.y1 * 16]
         f.host = torch.empty((size, size, 4), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+        f.copied = None
         frames.append(f)
+
+    copy_stream = torch.cuda.Stream()
 
     def render_frame(f, e2e: bool):
         if e2e:
             f.scene.set_view_box(f.flat.view_box)  # bumps the epoch: the scene is re-uploaded from host memory
+            if f.copied is not None:
+                stream.wait_event(f.copied)  # the previous read-back of this frame buffer must be done
         f.scene.build_and_render(f.renderer, f.options)
         if dist is not None:
             dist.all_gather_into_tensor(f.full.view(-1), f.strip_view.reshape(-1))
         if e2e and rank == 0:
-            f.host.copy_(f.full, non_blocking=True)
+            # Device -> pinned host read-back of the assembled frame on a copy stream, so it overlaps
+            # the host-side build and the rendering of the next frame.
+            done = torch.cuda.Event()
+            done.record(stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                f.host.copy_(f.full, non_blocking=True)
+                f.copied = torch.cuda.Event()
+                f.copied.record(copy_stream)
 
     def step(e2e: bool):
         for f in frames:

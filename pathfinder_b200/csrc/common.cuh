@@ -5,8 +5,11 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <vector>
 
 namespace pf {
 
@@ -60,5 +63,27 @@ struct DeviceBuffer {
 };
 
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// Runs f(begin, end) over [0, n) split across host threads (the reference parallelises its CPU-side
+// scene work with Rayon, renderer/src/concurrent/rayon.rs:17-24). Small inputs run inline.
+template <typename F>
+inline void parallel_ranges(size_t n, size_t grain, F &&f) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t threads = std::min<size_t>(hw ? hw : 1, 16);
+    threads = std::min(threads, n / (grain ? grain : 1));
+    if (threads <= 1) {
+        f((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> workers;
+    workers.reserve(threads);
+    const size_t per = (n + threads - 1) / threads;
+    for (size_t t = 0; t < threads; t++) {
+        const size_t b0 = t * per, e0 = std::min(n, b0 + per);
+        if (b0 >= e0) break;
+        workers.emplace_back([&f, b0, e0]() { f(b0, e0); });
+    }
+    for (auto &w : workers) w.join();
+}
 
 } // namespace pf

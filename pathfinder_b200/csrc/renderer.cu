@@ -10,6 +10,9 @@
 //   * tile lists are sorted by a device radix sort instead of per-tile linked lists.
 #include <cuda_fp16.h>
 
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -125,6 +128,7 @@ struct PFCudaRenderer {
     DeviceBuffer<uint32_t> tile_word, tile_fill_pos, tile_first_fill, tile_fb, tile_pos, tile_alpha_id;
     DeviceBuffer<int32_t> col_backdrop, col_backdrop_init;
     DeviceBuffer<uint32_t> long_queue; // lines walked by whole warps (k_bin_long)
+    std::vector<uint32_t> meta_slot;   // host scratch: command path index -> kept index
     DeviceBuffer<PackedFill> fills;
     DeviceBuffer<EmitFill> fills_emit;
     DeviceBuffer<int32_t> z_buffer;
@@ -248,7 +252,20 @@ uint32_t read_counter(PFCudaRenderer *r, int index) {
     return r->counters_host.ptr[index];
 }
 
+struct HostTimer {
+    const char *what;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit HostTimer(const char *w) : what(w) {}
+    ~HostTimer() {
+        static const bool on = getenv("PF_HOST_TIMING") != nullptr;
+        if (on)
+            fprintf(stderr, "%s: %.3f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
 void upload_segments(PFCudaRenderer *r, SceneSegments &dst, const PFSegmentsD3D11 &src) {
+    HostTimer timer("upload_segments");
     dst.n_points = src.point_count;
     dst.n_indices = src.index_count;
     dst.points.ensure(src.point_count + 4);
@@ -292,6 +309,7 @@ void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *en
 // the offsets TileBatchDataD3D11::push assigns (renderer/src/builder.rs:663-720) + bound.cs.glsl.
 void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch, const FbRect &fb,
                            int32_t strip_y0, int32_t strip_y1, BatchDev &b, bool &has_initial_backdrops) {
+    HostTimer timer("upload_batch_metadata");
     cudaStream_t st = r->stream;
     const uint32_t P = batch.path_count;
     const PFPrepareTilesInfoD3D11 &info = batch.prepare_info;
@@ -321,42 +339,62 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
     const uint32_t n_paints = (uint32_t)r->n_paints;
     bool bad_paint = false;
     uint32_t kept = 0, n_segments = 0;
+    // Pass 1 (sequential, integer only): which paths reach the strip, and their running offsets.
+    // A path without a tile in this strip contributes nothing (every fill is culled by add_fill,
+    // every backdrop adjustment by the rect test): it is dropped, segments included, so dice / bin
+    // / propagate only see the paths that reach the strip.
+    std::vector<uint32_t> &slot = r->meta_slot;
+    slot.resize(P);
     for (uint32_t i = 0; i < P; i++) {
-        const PFPropagateMetadataD3D11 &pm = info.propagate_metadata[i];
-        const PFDiceMetadataD3D11 &dm = info.dice_metadata[i];
-        const PFTilePathInfoD3D11 &tp = info.tile_path_info[i];
-        bad_paint |= tp.color >= n_paints;
-        PathInfo pi;
-        pi.min_x = pm.tile_rect.origin.x;
-        pi.max_x = pm.tile_rect.lower_right.x;
-        pi.min_y = pm.tile_rect.origin.y;
-        pi.max_y = pm.tile_rect.lower_right.y;
+        const PFRectI &tr = info.propagate_metadata[i].tile_rect;
         // Strip restriction: rows above the strip feed the column backdrops exactly like rows
         // above the path rect do in the reference (builder.rs:609-612); rows below are ignored.
-        if (pi.min_y < strip_y0) pi.min_y = strip_y0;
-        if (pi.max_y > strip_y1) pi.max_y = strip_y1;
-        // A path without a tile in this strip contributes nothing (every fill is culled by
-        // add_fill, every backdrop adjustment by the rect test): drop it, segments included, so
-        // dice / bin / propagate only see the paths that reach the strip.
-        if (pi.max_x <= pi.min_x || pi.max_y <= pi.min_y) continue;
-        const uint32_t seg_end = i + 1 < P ? info.dice_metadata[i + 1].first_batch_segment_index : batch.segment_count;
-        pi.tile_offset = (uint32_t)n_tiles64;
-        pi.col_offset = (uint32_t)n_cols64;
-        pi.seg_batch_first = n_segments;
-        pi.seg_global_first = dm.first_global_segment_index;
-        pi.global_path_id = dm.global_path_id;
-        pi.paint_ctrl = (uint32_t)tp.color | ((uint32_t)tp.ctrl << 16) | ((pm.z_write ? 1u : 0u) << 24);
-        pi.clip_path_index = pm.clip_path_index;
-        pi.pad = i; // index in the command's arrays (initial backdrops are keyed by it)
-        h_paths[kept] = pi;
-        h_seg_first[kept] = pi.seg_batch_first;
-        h_tile_off[kept] = pi.tile_offset;
-        h_col_off[kept] = pi.col_offset;
+        const int32_t min_y = std::max(tr.origin.y, strip_y0), max_y = std::min(tr.lower_right.y, strip_y1);
+        const int32_t w = tr.lower_right.x - tr.origin.x, h = max_y - min_y;
+        if (w <= 0 || h <= 0) {
+            slot[i] = 0xffffffffu;
+            continue;
+        }
+        slot[i] = kept;
+        h_seg_first[kept] = n_segments;
+        h_tile_off[kept] = (uint32_t)n_tiles64;
+        h_col_off[kept] = (uint32_t)n_cols64;
         kept++;
-        n_segments += seg_end - dm.first_batch_segment_index;
-        n_tiles64 += (uint64_t)(pi.max_x - pi.min_x) * (uint64_t)(pi.max_y - pi.min_y);
-        n_cols64 += (uint64_t)(pi.max_x - pi.min_x);
+        const uint32_t seg_begin = info.dice_metadata[i].first_batch_segment_index;
+        const uint32_t seg_end = i + 1 < P ? info.dice_metadata[i + 1].first_batch_segment_index : batch.segment_count;
+        n_segments += seg_end - seg_begin;
+        n_tiles64 += (uint64_t)w * (uint64_t)h;
+        n_cols64 += (uint64_t)w;
     }
+    // Pass 2 (parallel): the 48-byte records.
+    std::atomic<bool> bad_paint_flag{false};
+    parallel_ranges(P, 16384, [&](size_t begin, size_t end) {
+        bool bad = false;
+        for (size_t i = begin; i < end; i++) {
+            const uint32_t k = slot[i];
+            const PFTilePathInfoD3D11 &tp = info.tile_path_info[i];
+            bad |= tp.color >= n_paints;
+            if (k == 0xffffffffu) continue;
+            const PFPropagateMetadataD3D11 &pm = info.propagate_metadata[i];
+            const PFDiceMetadataD3D11 &dm = info.dice_metadata[i];
+            PathInfo pi;
+            pi.min_x = pm.tile_rect.origin.x;
+            pi.max_x = pm.tile_rect.lower_right.x;
+            pi.min_y = std::max(pm.tile_rect.origin.y, strip_y0);
+            pi.max_y = std::min(pm.tile_rect.lower_right.y, strip_y1);
+            pi.tile_offset = h_tile_off[k];
+            pi.col_offset = h_col_off[k];
+            pi.seg_batch_first = h_seg_first[k];
+            pi.seg_global_first = dm.first_global_segment_index;
+            pi.global_path_id = dm.global_path_id;
+            pi.paint_ctrl = (uint32_t)tp.color | ((uint32_t)tp.ctrl << 16) | ((pm.z_write ? 1u : 0u) << 24);
+            pi.clip_path_index = pm.clip_path_index;
+            pi.pad = (uint32_t)i; // index in the command's arrays (initial backdrops are keyed by it)
+            h_paths[k] = pi;
+        }
+        if (bad) bad_paint_flag.store(true);
+    });
+    bad_paint = bad_paint_flag.load();
     if (bad_paint) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "paint id outside the uploaded texture metadata");
     if (n_tiles64 >= 0xfffffff0ull) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "more than 2^32 bbox tiles in one batch");
     const uint32_t n_tiles = (uint32_t)n_tiles64, n_cols = (uint32_t)n_cols64;
@@ -679,6 +717,12 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
                      memcmp(&c.batch.fb, &fb, sizeof(fb)) == 0 && memcmp(&c.batch.view_box, &vb, sizeof(vb)) == 0 &&
                      c.command_paths == batch.path_count && c.command_segments == batch.segment_count;
     if (!hit) {
+        // A batch of the same shape as the previous one (same path / segment counts, same strip)
+        // is most likely the same scene re-sent: keep the previous totals as bounds so the frame
+        // runs without count read-backs; the end-of-batch verification falls back to exact sizing.
+        const bool same_shape = c.valid && c.counts_valid && c.command_paths == batch.path_count &&
+                                c.command_segments == batch.segment_count && c.strip_y0 == strip_y0 &&
+                                c.strip_y1 == strip_y1 && memcmp(&c.batch.fb, &fb, sizeof(fb)) == 0;
         c.valid = false;
         upload_batch_metadata(r, batch, fb, strip_y0, strip_y1, c.batch, c.has_initial_backdrops);
         c.key = batch.content_key;
@@ -688,7 +732,7 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
         c.paint_generation = r->paint_generation;
         c.strip_y0 = strip_y0;
         c.strip_y1 = strip_y1;
-        c.counts_valid = false;
+        c.counts_valid = same_shape;
         c.valid = true;
     } else {
         r->stats.batch_cache_hits++;

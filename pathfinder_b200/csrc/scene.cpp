@@ -14,16 +14,61 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
 #include "../../include/pf_cuda.h"
+#include "common.cuh"
+
+#include <cuda_runtime.h>
 
 namespace pf {
 void set_last_error(const std::string &msg);
 }
+
+namespace {
+// Host array that lives in pinned memory when a CUDA driver is present (so UploadSceneD3D11 payloads
+// are copied at PCIe speed without a staging pass) and in ordinary memory otherwise (CPU-only tests).
+template <typename T>
+struct HostBuffer {
+    T *ptr = nullptr;
+    size_t capacity = 0;
+    bool pinned = false;
+    HostBuffer() = default;
+    HostBuffer(const HostBuffer &) = delete;
+    HostBuffer &operator=(const HostBuffer &) = delete;
+    ~HostBuffer() { release(); }
+    void release() {
+        if (!ptr) return;
+        if (pinned)
+            cudaFreeHost(ptr);
+        else
+            free(ptr);
+        ptr = nullptr;
+        capacity = 0;
+    }
+    void ensure(size_t n) {
+        if (n <= capacity) return;
+        release();
+        size_t want = n + n / 8 + 64;
+        void *p = nullptr;
+        if (cudaMallocHost(&p, want * sizeof(T)) == cudaSuccess) {
+            pinned = true;
+        } else {
+            (void)cudaGetLastError();
+            p = malloc(want * sizeof(T));
+            pinned = false;
+        }
+        ptr = static_cast<T *>(p);
+        capacity = want;
+    }
+};
+} // namespace
 
 namespace {
 
@@ -70,6 +115,8 @@ struct Path {
     uint16_t paint;
     uint8_t fill_rule, blend_mode;
     uint32_t clip_path;
+    uint32_t segment_points;  // points SegmentsD3D11::add_path emits: all points + one closing copy per contour
+    uint32_t segment_indices; // on-curve points = segments
 };
 
 std::atomic<uint32_t> g_next_scene_id{0}; // NEXT_SCENE_ID, scene.rs:34
@@ -89,8 +136,12 @@ struct PFScene {
     uint32_t epoch = 0;
 
     // Scratch reused across builds.
-    std::vector<PFVector2F> seg_points;
-    std::vector<PFSegmentIndicesD3D11> seg_indices;
+    HostBuffer<PFVector2F> seg_points;
+    HostBuffer<PFSegmentIndicesD3D11> seg_indices;
+    size_t seg_point_count = 0, seg_index_count = 0;
+    std::vector<uint32_t> seg_path_offsets; // per-path output offsets of build_segments
+    std::vector<PFRectI> path_tile_rects;   // scratch of the batch build (kept == rect non-empty)
+    std::vector<uint32_t> path_batch_offsets;
     std::vector<uint32_t> draw_segment_ranges; // [n_draw][2]
     std::vector<PFPropagateMetadataD3D11> propagate_metadata;
     std::vector<PFDiceMetadataD3D11> dice_metadata;
@@ -128,9 +179,11 @@ Path append_outline(PFScene *s, const PFVector2F *points, const uint8_t *point_f
         uint32_t p0 = contour_offsets[c], p1 = contour_offsets[c + 1];
         if (p0 == p1) continue;
         RectF cb{points[p0].x, points[p0].y, points[p0].x, points[p0].y};
+        p.segment_points += p1 - p0 + 1;
         for (uint32_t i = p0; i < p1; i++) {
             s->points.push_back(points[i]);
             s->flags.push_back(point_flags[i]);
+            p.segment_indices += (point_flags[i] & (PF_POINT_FLAGS_CONTROL_POINT_0 | PF_POINT_FLAGS_CONTROL_POINT_1)) ? 0u : 1u;
             cb.min_x = sse_min(cb.min_x, points[i].x);
             cb.min_y = sse_min(cb.min_y, points[i].y);
             cb.max_x = sse_max(cb.max_x, points[i].x);
@@ -145,30 +198,56 @@ Path append_outline(PFScene *s, const PFVector2F *points, const uint8_t *point_f
     return p;
 }
 
-// SegmentsD3D11::add_path (renderer/src/builder.rs:804-841).
-void add_path_segments(const PFScene *s, const Path &path, std::vector<PFVector2F> &points,
-                       std::vector<PFSegmentIndicesD3D11> &indices, uint32_t range[2]) {
-    range[0] = (uint32_t)indices.size();
-    for (uint32_t c = path.first_contour; c < path.end_contour; c++) {
-        const uint32_t p0 = s->contour_offsets[c], point_count = s->contour_offsets[c + 1] - p0;
-        const uint8_t *flags = s->flags.data() + p0;
-        const PFVector2F *pts = s->points.data() + p0;
-        for (uint32_t i = 0; i < point_count; i++) {
-            if (!(flags[i] & (PF_POINT_FLAGS_CONTROL_POINT_0 | PF_POINT_FLAGS_CONTROL_POINT_1))) {
-                uint32_t f = 0;
-                if (i + 1 < point_count && (flags[i + 1] & PF_POINT_FLAGS_CONTROL_POINT_0)) {
-                    if (i + 2 < point_count && (flags[i + 2] & PF_POINT_FLAGS_CONTROL_POINT_1))
-                        f = PF_CURVE_IS_CUBIC;
-                    else
-                        f = PF_CURVE_IS_QUADRATIC;
-                }
-                indices.push_back(PFSegmentIndicesD3D11{(uint32_t)points.size(), f});
-            }
-            points.push_back(pts[i]);
-        }
-        points.push_back(pts[0]); // implicit close: the first point again (builder.rs:835)
+using pf::parallel_ranges;
+
+// BuiltSegments::from_scene + SegmentsD3D11::add_path (renderer/src/builder.rs:777-841) for the draw
+// paths: every contour's points followed by its first point again (implicit close), one index entry
+// per on-curve point, flagged quadratic / cubic by the control points that follow it. Output
+// positions are prefix sums of per-path counts, so paths are filled in parallel.
+void build_segments(PFScene *s) {
+    const size_t n_paths = s->draw_paths.size();
+    s->seg_path_offsets.resize(2 * (n_paths + 1));
+    uint32_t *point_off = s->seg_path_offsets.data(), *index_off = point_off + (n_paths + 1);
+    uint32_t np = 0, ni = 0;
+    for (size_t pi = 0; pi < n_paths; pi++) {
+        point_off[pi] = np, index_off[pi] = ni;
+        np += s->draw_paths[pi].segment_points;
+        ni += s->draw_paths[pi].segment_indices;
     }
-    range[1] = (uint32_t)indices.size();
+    point_off[n_paths] = np, index_off[n_paths] = ni;
+    s->seg_points.ensure((size_t)np + 1);
+    s->seg_indices.ensure((size_t)ni + 1);
+    s->draw_segment_ranges.resize(2 * n_paths);
+    PFVector2F *out_points = s->seg_points.ptr;
+    PFSegmentIndicesD3D11 *out_indices = s->seg_indices.ptr;
+    const uint8_t ctrl_mask = PF_POINT_FLAGS_CONTROL_POINT_0 | PF_POINT_FLAGS_CONTROL_POINT_1;
+    parallel_ranges(n_paths, 4096, [&](size_t begin, size_t end) {
+        for (size_t pi = begin; pi < end; pi++) {
+            const Path &path = s->draw_paths[pi];
+            size_t wp = point_off[pi], wi = index_off[pi];
+            s->draw_segment_ranges[2 * pi] = (uint32_t)wi;
+            for (uint32_t c = path.first_contour; c < path.end_contour; c++) {
+                const uint32_t p0 = s->contour_offsets[c], point_count = s->contour_offsets[c + 1] - p0;
+                const uint8_t *flags = s->flags.data() + p0;
+                const PFVector2F *pts = s->points.data() + p0;
+                memcpy(out_points + wp, pts, (size_t)point_count * sizeof(PFVector2F));
+                for (uint32_t i = 0; i < point_count; i++) {
+                    if (flags[i] & ctrl_mask) continue;
+                    uint32_t f = 0;
+                    if (i + 1 < point_count && (flags[i + 1] & PF_POINT_FLAGS_CONTROL_POINT_0))
+                        f = (i + 2 < point_count && (flags[i + 2] & PF_POINT_FLAGS_CONTROL_POINT_1))
+                                ? PF_CURVE_IS_CUBIC
+                                : PF_CURVE_IS_QUADRATIC;
+                    out_indices[wi++] = PFSegmentIndicesD3D11{(uint32_t)(wp + i), f};
+                }
+                wp += point_count;
+                out_points[wp++] = pts[0]; // implicit close: the first point again (builder.rs:835)
+            }
+            s->draw_segment_ranges[2 * pi + 1] = (uint32_t)wi;
+        }
+    });
+    s->seg_point_count = np;
+    s->seg_index_count = ni;
 }
 
 // RectF::intersection (geometry/src/rect.rs:122-137), strict comparisons.
@@ -362,16 +441,10 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                 pf::set_last_error("clip paths are a 'next' row (SURVEY.md §8 f1)");
                 return PF_CUDA_ERROR_UNSUPPORTED;
             }
-        s->seg_points.clear();
-        s->seg_indices.clear();
-        s->draw_segment_ranges.resize(2 * s->draw_paths.size());
-        s->seg_points.reserve(s->points.size() + s->contour_offsets.size());
-        s->seg_indices.reserve(s->points.size());
-        for (size_t i = 0; i < s->draw_paths.size(); i++)
-            add_path_segments(s, s->draw_paths[i], s->seg_points, s->seg_indices, &s->draw_segment_ranges[2 * i]);
+        build_segments(s);
         PFRenderCommand up = make_command(PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11);
-        up.u.upload_scene_d3d11.draw_segments = PFSegmentsD3D11{s->seg_points.data(), s->seg_points.size(),
-                                                                 s->seg_indices.data(), s->seg_indices.size()};
+        up.u.upload_scene_d3d11.draw_segments =
+            PFSegmentsD3D11{s->seg_points.ptr, s->seg_point_count, s->seg_indices.ptr, s->seg_index_count};
         up.u.upload_scene_d3d11.clip_segments = PFSegmentsD3D11{nullptr, 0, nullptr, 0};
         SEND(up);
         sink->has_last_scene = 1;
@@ -398,63 +471,99 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
     const bool rebuild = s->built_key != batch_key;
     if (rebuild) {
         tile_count = segment_count = 0;
-        s->propagate_metadata.clear();
-        s->dice_metadata.clear();
-        s->tile_path_info.clear();
     }
-    for (uint32_t i = 0; rebuild && i < s->draw_paths.size(); i++) {
-        const Path &p = s->draw_paths[i];
-        if (p.clip_path != PF_CLIP_PATH_NONE) {
-            pf::set_last_error("clip paths are a 'next' row (SURVEY.md §8 f1)");
-            return PF_CUDA_ERROR_UNSUPPORTED;
+    auto t_loop0 = std::chrono::steady_clock::now();
+    if (rebuild) {
+        const size_t n_paths = s->draw_paths.size();
+        for (const Path &p : s->draw_paths) {
+            if (p.clip_path != PF_CLIP_PATH_NONE) {
+                pf::set_last_error("clip paths are a 'next' row (SURVEY.md §8 f1)");
+                return PF_CUDA_ERROR_UNSUPPORTED;
+            }
+            if (p.blend_mode != PF_BLEND_MODE_SRC_OVER) {
+                pf::set_last_error("only BlendMode::SrcOver is on the hot path");
+                return PF_CUDA_ERROR_UNSUPPORTED;
+            }
         }
-        if (p.blend_mode != PF_BLEND_MODE_SRC_OVER) {
-            pf::set_last_error("only BlendMode::SrcOver is on the hot path");
-            return PF_CUDA_ERROR_UNSUPPORTED;
+        // Pass 1 (parallel): prepare_draw_path_for_gpu_binning (builder.rs:1058-1095) — the tile rect
+        // of every path; an empty rect marks a path outside the view box (skipped by the builder).
+        s->path_tile_rects.resize(n_paths);
+        parallel_ranges(n_paths, 8192, [&](size_t begin, size_t end) {
+            for (size_t i = begin; i < end; i++) {
+                const Path &p = s->draw_paths[i];
+                PFRectI tile_rect{{0, 0}, {0, 0}};
+                RectF path_bounds = xf.is_identity() ? p.bounds : xf.apply_rect(p.bounds);
+                RectF clipped;
+                if (rect_intersection(path_bounds, effective_view_box, clipped)) {
+                    // round_rect_out_to_tile_bounds (tiles.rs:64-66); floor/ceil results are integral,
+                    // so the float -> int conversion is exact in any rounding mode.
+                    const float k = 1.0f / 16.0f;
+                    tile_rect.origin.x = (int32_t)floorf(clipped.min_x * k);
+                    tile_rect.origin.y = (int32_t)floorf(clipped.min_y * k);
+                    tile_rect.lower_right.x = (int32_t)ceilf(clipped.max_x * k);
+                    tile_rect.lower_right.y = (int32_t)ceilf(clipped.max_y * k);
+                } else {
+                    tile_rect.origin.x = 1, tile_rect.lower_right.x = 0; // "skipped" marker (a kept rect has max >= min)
+                }
+                s->path_tile_rects[i] = tile_rect;
+            }
+        });
+        // Pass 2 (sequential, integer adds only): batch index and running offsets
+        // (TileBatchDataD3D11::push, builder.rs:660-721).
+        s->path_batch_offsets.resize(4 * (n_paths + 1));
+        uint32_t *batch_index = s->path_batch_offsets.data(), *tile_off = batch_index + (n_paths + 1),
+                 *col_off = tile_off + (n_paths + 1), *seg_off = col_off + (n_paths + 1);
+        uint32_t kept = 0;
+        for (size_t i = 0; i < n_paths; i++) {
+            const PFRectI &tr = s->path_tile_rects[i];
+            batch_index[i] = kept, tile_off[i] = tile_count, col_off[i] = column_count, seg_off[i] = segment_count;
+            if (tr.origin.x > tr.lower_right.x) continue; // skipped
+            const uint32_t w = (uint32_t)(tr.lower_right.x - tr.origin.x), h = (uint32_t)(tr.lower_right.y - tr.origin.y);
+            kept++;
+            tile_count += w * h;
+            column_count += w;
+            segment_count += s->draw_segment_ranges[2 * i + 1] - s->draw_segment_ranges[2 * i];
         }
-        // prepare_draw_path_for_gpu_binning (builder.rs:1058-1095)
-        RectF path_bounds = xf.is_identity() ? p.bounds : xf.apply_rect(p.bounds);
-        RectF clipped;
-        if (!rect_intersection(path_bounds, effective_view_box, clipped)) continue;
-        // round_rect_out_to_tile_bounds (tiles.rs:64-66)
-        const float k = 1.0f / 16.0f;
-        PFRectI tile_rect;
-        tile_rect.origin.x = (int32_t)lrintf(floorf(clipped.min_x * k));
-        tile_rect.origin.y = (int32_t)lrintf(floorf(clipped.min_y * k));
-        tile_rect.lower_right.x = (int32_t)lrintf(ceilf(clipped.max_x * k));
-        tile_rect.lower_right.y = (int32_t)lrintf(ceilf(clipped.max_y * k));
-        const uint32_t w = (uint32_t)(tile_rect.lower_right.x - tile_rect.origin.x);
-        const uint32_t h = (uint32_t)(tile_rect.lower_right.y - tile_rect.origin.y);
-        // BuiltDrawPath::new (builder.rs:80-94): occludes = opaque paint && SrcOver.
-        const bool occludes = s->paints[p.paint].a == 255;
-        const uint8_t ctrl = p.fill_rule == PF_FILL_RULE_EVEN_ODD ? PF_TILE_CTRL_MASK_EVEN_ODD : PF_TILE_CTRL_MASK_WINDING;
-        const uint32_t batch_path_index = (uint32_t)s->propagate_metadata.size();
-        // TileBatchDataD3D11::push (builder.rs:653-721)
-        PFPropagateMetadataD3D11 pm;
-        memset(&pm, 0, sizeof(pm));
-        pm.tile_rect = tile_rect;
-        pm.tile_offset = tile_count;
-        pm.path_index = batch_path_index;
-        pm.z_write = occludes ? 1 : 0;
-        pm.clip_path_index = PF_PATH_INDEX_NONE;
-        pm.backdrop_offset = column_count;
-        s->propagate_metadata.push_back(pm);
-        const uint32_t *range = &s->draw_segment_ranges[2 * (size_t)i];
-        s->dice_metadata.push_back(PFDiceMetadataD3D11{i, range[0], segment_count, 0});
-        PFTilePathInfoD3D11 tp;
-        tp.tile_min_x = (int16_t)tile_rect.origin.x;
-        tp.tile_min_y = (int16_t)tile_rect.origin.y;
-        tp.tile_max_x = (int16_t)tile_rect.lower_right.x;
-        tp.tile_max_y = (int16_t)tile_rect.lower_right.y;
-        tp.first_tile_index = tile_count;
-        tp.color = p.paint;
-        tp.ctrl = ctrl;
-        tp.backdrop = 0;
-        s->tile_path_info.push_back(tp);
-        tile_count += w * h;
-        column_count += w;
-        segment_count += range[1] - range[0];
+        s->propagate_metadata.resize(kept);
+        s->dice_metadata.resize(kept);
+        s->tile_path_info.resize(kept);
+        // Pass 3 (parallel): the records.
+        parallel_ranges(n_paths, 8192, [&](size_t begin, size_t end) {
+            for (size_t i = begin; i < end; i++) {
+                const PFRectI &tile_rect = s->path_tile_rects[i];
+                if (tile_rect.origin.x > tile_rect.lower_right.x) continue;
+                const Path &p = s->draw_paths[i];
+                const uint32_t bi = batch_index[i];
+                // BuiltDrawPath::new (builder.rs:80-94): occludes = opaque paint && SrcOver.
+                const bool occludes = s->paints[p.paint].a == 255;
+                const uint8_t ctrl = p.fill_rule == PF_FILL_RULE_EVEN_ODD ? PF_TILE_CTRL_MASK_EVEN_ODD : PF_TILE_CTRL_MASK_WINDING;
+                PFPropagateMetadataD3D11 pm;
+                memset(&pm, 0, sizeof(pm));
+                pm.tile_rect = tile_rect;
+                pm.tile_offset = tile_off[i];
+                pm.path_index = bi;
+                pm.z_write = occludes ? 1 : 0;
+                pm.clip_path_index = PF_PATH_INDEX_NONE;
+                pm.backdrop_offset = col_off[i];
+                s->propagate_metadata[bi] = pm;
+                s->dice_metadata[bi] = PFDiceMetadataD3D11{(uint32_t)i, s->draw_segment_ranges[2 * i], seg_off[i], 0};
+                PFTilePathInfoD3D11 tp;
+                tp.tile_min_x = (int16_t)tile_rect.origin.x;
+                tp.tile_min_y = (int16_t)tile_rect.origin.y;
+                tp.tile_max_x = (int16_t)tile_rect.lower_right.x;
+                tp.tile_max_y = (int16_t)tile_rect.lower_right.y;
+                tp.first_tile_index = tile_off[i];
+                tp.color = p.paint;
+                tp.ctrl = ctrl;
+                tp.backdrop = 0;
+                s->tile_path_info[bi] = tp;
+            }
+        });
     }
+    if (getenv("PF_HOST_TIMING"))
+        fprintf(stderr, "PFSceneBuild: %.3f ms before the path loop, %.3f ms in it\n",
+                std::chrono::duration<double, std::milli>(t_loop0 - start_time).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop0).count());
     s->built_key = batch_key;
     s->built_tile_count = tile_count;
     s->built_segment_count = segment_count;
