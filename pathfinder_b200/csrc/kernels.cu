@@ -494,7 +494,8 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin(BatchDev b, BinArgs a) {
     const uint32_t n_lines = a.n_lines_dev ? min(a.n_lines, __ldg(a.n_lines_dev)) : a.n_lines;
     const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     const float recip = 1.0f / 16.0f;
-    if (l < n_lines) {
+    if (l < n_lines && (MODE != BIN_EMIT_LIVE || __ldg(a.path_live + __ldg(a.line_path + l)) != 0u)) {
+        // (BIN_EMIT_LIVE: a path whose tiles were all culled has nothing left to emit)
         float4 seg = __ldg(a.lines + l);
         const PathInfo path = load_path(b.paths, __ldg(a.line_path + l));
         const int rect_w = path.max_x - path.min_x, rect_h = path.max_y - path.min_y;
@@ -697,7 +698,8 @@ constexpr int LIST_TILE = 256 * LIST_ITEMS;
 __global__ void __launch_bounds__(256)
     k_list_count(BatchDev b, const uint32_t *__restrict__ tile_word, const int32_t *__restrict__ z_buffer,
                  uint32_t *__restrict__ tile_fb, uint32_t *__restrict__ fb_count,
-                 uint32_t *__restrict__ tile_fill_pos, uint32_t *__restrict__ fill_cursor, int keep_all_fills) {
+                 uint32_t *__restrict__ tile_fill_pos, uint32_t *__restrict__ fill_cursor,
+                 uint32_t *__restrict__ path_live, int keep_all_fills) {
     __shared__ uint32_t smem[256 / 32 + 1];
     __shared__ uint32_t s_base;
     const uint32_t base = blockIdx.x * LIST_TILE + threadIdx.x;
@@ -726,6 +728,7 @@ __global__ void __launch_bounds__(256)
                 if ((int32_t)path.global_path_id >= __ldg(z_buffer + fbi)) {
                     result = fbi;
                     atomicAdd(fb_count + fbi, 1u);
+                    if (count != 0) path_live[p] = 1u; // some fills of this path will be read: its lines must be walked again
                 }
             }
         }
@@ -749,11 +752,12 @@ __global__ void __launch_bounds__(256)
 }
 
 int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
-                      uint32_t *fb_count, uint32_t *tile_fill_pos, uint32_t *fill_cursor, bool keep_all_fills,
-                      cudaStream_t stream) {
+                      uint32_t *fb_count, uint32_t *tile_fill_pos, uint32_t *fill_cursor, uint32_t *path_live,
+                      bool keep_all_fills, cudaStream_t stream) {
     if (b.n_tiles == 0) return 0;
     k_list_count<<<div_up(b.n_tiles, LIST_TILE), 256, 0, stream>>>(b, tile_word, z_buffer, tile_fb, fb_count,
-                                                                    tile_fill_pos, fill_cursor, keep_all_fills ? 1 : 0);
+                                                                    tile_fill_pos, fill_cursor, path_live,
+                                                                    keep_all_fills ? 1 : 0);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

@@ -92,6 +92,7 @@ struct BinArgs {
     uint32_t *line_fill_count;
     // BIN_EMIT_LIVE / BIN_EMIT
     const uint32_t *tile_fb;     // BIN_EMIT_LIVE: 0xffffffff = tile culled, its fills are not stored
+    const uint32_t *path_live;   // BIN_EMIT_LIVE: 0 = every tile of the path was culled, skip its lines
     uint32_t *tile_fill_pos;     // running cursor, initialised with the exclusive scan of the (live) counts
     PackedFill *fills;           // tile-grouped
     uint32_t fill_capacity;
@@ -119,8 +120,8 @@ int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_
 // It also reserves each surviving tile's run in the tile-grouped fill array: tile_fill_pos[t] = run
 // start, *fill_cursor += total (keep_all_fills: culled tiles keep their runs, for the parity dumps).
 int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
-                      uint32_t *fb_count, uint32_t *tile_fill_pos, uint32_t *fill_cursor, bool keep_all_fills,
-                      cudaStream_t stream);
+                      uint32_t *fb_count, uint32_t *tile_fill_pos, uint32_t *fill_cursor, uint32_t *path_live,
+                      bool keep_all_fills, cudaStream_t stream);
 // Appends one TileEntry per surviving tile to its framebuffer tile's run [fb_start, fb_start + count).
 int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t *tile_word,
                      const uint32_t *tile_fill_pos, const uint32_t *fb_start, uint32_t *fb_cursor,

@@ -128,6 +128,7 @@ struct PFCudaRenderer {
     DeviceBuffer<uint32_t> tile_word, tile_fill_pos, tile_first_fill, tile_fb, tile_pos, tile_alpha_id;
     DeviceBuffer<int32_t> col_backdrop, col_backdrop_init;
     DeviceBuffer<uint32_t> long_queue; // lines walked by whole warps (k_bin_long)
+    DeviceBuffer<uint32_t> path_live;  // per path: some tile with fills survived the z-cull
     std::vector<uint32_t> meta_slot;   // host scratch: command path index -> kept index
     DeviceBuffer<PackedFill> fills;
     DeviceBuffer<EmitFill> fills_emit;
@@ -199,6 +200,7 @@ void setup_tracking(PFCudaRenderer *r) {
     track(r, r->col_backdrop);
     track(r, r->col_backdrop_init);
     track(r, r->long_queue);
+    track(r, r->path_live);
     track(r, r->fills);
     track(r, r->fills_emit);
     track(r, r->z_buffer);
@@ -504,6 +506,8 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     r->tile_fill_pos.ensure(n_tiles + 1, 1.25);
     r->col_backdrop.ensure(n_cols + 1, 1.25);
     r->tile_fb.ensure(n_tiles + 1, 1.25);
+    r->path_live.ensure(b.n_paths + 1, 1.25);
+    PF_CUDA_CHECK(cudaMemsetAsync(r->path_live.ptr, 0, (size_t)b.n_paths * 4, st));
     PF_CUDA_CHECK(cudaMemsetAsync(r->tile_word.ptr, 0, (size_t)n_tiles * 4, st));
     auto reset_col_backdrops = [&]() {
         if (c.has_initial_backdrops)
@@ -583,7 +587,8 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     // (the same kernel reserves the fill runs of the surviving tiles: occlusion culling before fill
     // emission; with the parity dumps on, every alpha tile keeps its fills so its mask can be read back)
     launches += launch_list_count(b, r->tile_word.ptr, r->z_buffer.ptr, r->tile_fb.ptr, r->fb_count.ptr,
-                                  r->tile_fill_pos.ptr, r->counters.ptr + C_VISIBLE_FILLS, r->debug_lists, st);
+                                  r->tile_fill_pos.ptr, r->counters.ptr + C_VISIBLE_FILLS, r->path_live.ptr,
+                                  r->debug_lists, st);
     launches += exclusive_scan(LoadU32{r->fb_count.ptr}, r->fb_start.ptr, n_fb, r->counters.ptr + C_ENTRIES,
                                r->scan_scratch, st);
     uint32_t entry_bound, fill_bound;
@@ -606,6 +611,7 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
 
     // ---- bin, emit pass: fills of surviving tiles into their tile-grouped runs.
     ba.tile_fb = r->tile_fb.ptr;
+    ba.path_live = r->path_live.ptr;
     ba.tile_fill_pos = r->tile_fill_pos.ptr;
     ba.fills = r->fills.ptr;
     ba.fill_capacity = fill_bound;
