@@ -1037,7 +1037,15 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS) k_composite(CompositeArg
     }
     if (uniform) {
         const uint32_t packed = pack_rgba8(uni);
-        if (row_mask == 0xffu) {
+        // One colour for the whole tile: when the tile lies inside the image and rows are 16-byte
+        // aligned, lane l writes half of row l/2 with two 128-bit stores instead of eight 32-bit ones.
+        const bool inside = tx >= 0 && ty >= 0 && tx * 16 + 16 <= a.dest_w && ty * 16 + 16 <= a.dest_h;
+        if (inside && (((uintptr_t)a.dest | a.dest_pitch) & 15) == 0) {
+            uint8_t *row = a.dest + (size_t)(ty * 16 + (lane >> 1)) * a.dest_pitch + (size_t)tx * 64 + (size_t)(lane & 1) * 32;
+            const uint4 v = make_uint4(packed, packed, packed, packed);
+            reinterpret_cast<uint4 *>(row)[0] = v;
+            reinterpret_cast<uint4 *>(row)[1] = v;
+        } else if (row_mask == 0xffu) {
 #pragma unroll
             for (int k = 0; k < 8; k++, out += a.dest_pitch) *reinterpret_cast<uint32_t *>(out) = packed;
         } else {
