@@ -206,3 +206,95 @@ def test_wrong_level_commands_are_rejected():
     with pytest.raises(L.PathfinderCudaError):
         api.CudaRenderer((64, 64), level=api.RendererLevel.D3D9)
     r.close()
+
+
+# ---- BASELINE.json configurations at full size -------------------------------------------------
+
+@pytest.mark.parametrize("even_odd", [False, True])
+def test_full_size_tiger_4096(area_lut, even_odd):
+    """configs[1]: tiger at 4096x4096, all-winding and odd-paths-even-odd. Lists bit-exact, RGBA
+    within 1/255 of the oracle's evaluation of the reference fill math."""
+    flat, xf = scenes.tiger(4096, even_odd_odd_paths=even_odd)
+    built = H.oracle_build(flat, xf)
+    r, img = H.cuda_render(flat, xf, background=(1.0, 1.0, 1.0, 1.0))
+    H.assert_records_equal(r.debug_fills(), built.fills, "fills")
+    H.assert_records_equal(r.debug_tiles(), built.tiles, "tiles")
+    z, _ = r.debug_z_buffer()
+    assert np.array_equal(z, built.z_buffer)
+    ref = built.render(area_lut, 4096, 4096, background=(1.0, 1.0, 1.0, 1.0))
+    assert np.abs(img.astype(np.int32) - ref.astype(np.int32)).max() <= RGBA_TOL
+    r2, img2 = H.cuda_render(flat, xf, background=(1.0, 1.0, 1.0, 1.0), debug=False)
+    assert np.array_equal(img, img2)
+    r.close()
+    r2.close()
+
+
+def test_full_size_random100k_8192():
+    """configs[3]: 100k random cubic paths at 8192x8192. Fills, tiles and z-buffer bit-exact against
+    the CPU tiler; the frame is checked through size-independent properties (strips stitched =
+    full frame, production path = instrumented path, deterministic across runs)."""
+    from pathfinder_b200 import api
+    flat = scenes.random_paths(100000, 8192, 0x5EED0004)
+    built = H.oracle_build(flat, None)
+    r, img = H.cuda_render(flat, None, background=(1.0, 1.0, 1.0, 1.0))
+    s = r.stats()
+    assert s["line_segment_count"] == built.line_segment_count
+    assert s["input_segment_count"] == built.input_segment_count
+    H.assert_records_equal(r.debug_fills(), built.fills, "fills")
+    H.assert_records_equal(r.debug_tiles(), built.tiles, "tiles")
+    z, _ = r.debug_z_buffer()
+    assert np.array_equal(z, built.z_buffer)
+    assert s["alpha_tile_count"] == built.alpha_tile_count
+    r.close()
+    # production path, twice (sizing frame, then cached batch), and two strips
+    rp = api.CudaRenderer((8192, 8192), background_color=(1.0, 1.0, 1.0, 1.0))
+    scene = api.Scene.from_flat(flat)
+    opts = api.BuildOptions()
+    scene.build_and_render(rp, opts)
+    a = rp.read_pixels()
+    scene.build_and_render(rp, opts)
+    b = rp.read_pixels()
+    assert np.array_equal(a, img) and np.array_equal(b, img)
+    for y0, y1 in [(0, 256), (256, 512)]:
+        rp.set_strip(y0, y1)
+        scene.build_and_render(rp, opts)
+        part = rp.read_pixels()
+        assert np.array_equal(part[y0 * 16:y1 * 16], img[y0 * 16:y1 * 16])
+    rp.close()
+
+
+def test_edge_inputs(area_lut):
+    """Empty and ragged inputs, degenerate geometry, extreme coordinates, maximum winding depth."""
+    b = SceneBuilderPy((0, 0, 160, 96))
+    b.end_path((9, 9, 9, 255))                      # empty path
+    b.move_to(30, 30)
+    b.close()
+    b.end_path((9, 9, 9, 255))                      # one point
+    b.move_to(5, 5)
+    b.line_to(150, 5)
+    b.close()
+    b.end_path((9, 9, 9, 255))                      # zero area: fills that cancel
+    b.move_to(-1.0e6, -2.0e6)
+    b.line_to(3.0e6, 40)
+    b.line_to(80, 4.0e6)
+    b.close()
+    b.end_path((30, 60, 200, 180))                  # huge triangle clipped on every side
+    b.move_to(16, 16)
+    b.line_to(48, 16)
+    b.line_to(48, 48)
+    b.line_to(16, 48)
+    b.close()
+    b.end_path((200, 10, 10, 255))                  # edges exactly on tile boundaries
+    for _ in range(140):                            # > 127 nested windings: i8 backdrop wraps (quirk 7)
+        b.move_to(100, 20)
+        b.line_to(150, 20)
+        b.line_to(150, 80)
+        b.line_to(100, 80)
+        b.close()
+    b.end_path((10, 200, 10, 200))
+    b.move_to(60, 60)
+    b.cubic_to(60, 60, 60, 60, 60, 60)              # degenerate cubic
+    b.quad_to(90, 90, 60, 90)
+    b.close()
+    b.end_path((0, 0, 0, 128), FILL_RULE_EVEN_ODD)
+    check_scene(b.finish("edges"), None, area_lut)
