@@ -1,0 +1,98 @@
+#!/usr/bin/env python3
+"""Turns the ncu outputs gathered on the GPU box (gpurun_out/) into the committed summaries under
+profiles/. Usage: python tools/summarise_profiles.py r01"""
+import csv, os, subprocess, sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out_dir = os.path.join(ROOT, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+
+
+def launch_table(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+    by = OrderedDict()
+    for r in rows:
+        by.setdefault((r[0], r[4].split("(")[0].strip()), {})[r[-3]] = float(r[-1].replace(",", ""))
+    ids = list(by.keys())
+    starts = [i for i, k in enumerate(ids) if "k_dice<0>" in k[1]]
+    s, e = starts[0], (starts[1] if len(starts) > 1 else len(ids))
+    return [(k[1], by[k]) for k in ids[s:e]]
+
+
+lines = [f"# {tag} — ncu launch lists, one frame per scene", "",
+         "`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum "
+         "--clock-control none python tools/stage_times.py <scene>` on a B200. Per-launch times are cold-cache and "
+         "serialised: compare shares, not absolutes (the CUDA-event stage times of the same build are in the bench line).", ""]
+for scene in ("random100k", "tiger4k"):
+    path = os.path.join(ROOT, "gpurun_out", f"{tag}_launches_{scene}.csv")
+    if not os.path.exists(path):
+        continue
+    table = launch_table(path)
+    tot = sum(m.get("gpu__time_duration.sum", 0) for _, m in table) / 1000
+    lines += [f"## {scene}", "", "| kernel | us | share | DRAM read MB | DRAM write MB | warp instr (M) |", "|---|---:|---:|---:|---:|---:|"]
+    for name, m in table:
+        t = m.get("gpu__time_duration.sum", 0) / 1000
+        lines.append(f"| `{name}` | {t:.1f} | {100 * t / tot:.1f}% | {m.get('dram__bytes_read.sum', 0) / 1e6:.1f} | "
+                     f"{m.get('dram__bytes_write.sum', 0) / 1e6:.1f} | {m.get('smsp__inst_executed.sum', 0) / 1e6:.1f} |")
+    lines += [f"| **total** | {tot:.1f} | | | | |", ""]
+open(os.path.join(out_dir, f"{tag}_launches.md"), "w").write("\n".join(lines))
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio"]
+lines = [f"# {tag} — `ncu --set full` of the dominant kernel: k_composite (fused fill + tile)", ""]
+for scene in ("random100k", "tiger4k"):
+    rep = os.path.join(ROOT, "gpurun_out", f"{tag}_composite_{scene}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    lines += [f"## {scene}", "", "| metric | unit | value |", "|---|---|---:|"]
+    for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            lines.append(f"| `{k}` | {units[i]} | {vals[i]} |")
+    lines.append("")
+open(os.path.join(out_dir, f"{tag}_composite_ncu.md"), "w").write("\n".join(lines))
+
+# SASS evidence: memory / texture / atomic / shuffle mnemonics per kernel.
+so = os.path.join(ROOT, "pathfinder_b200", "libpf_cuda.so")
+sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+kernels, cur = OrderedDict(), None
+for ln in sass.splitlines():
+    if "Function :" in ln:
+        cur = ln.split("Function :")[1].strip()
+        kernels[cur] = {}
+    elif cur and "/*" in ln and ";" in ln:
+        body = ln.split("*/")[1].strip() if "*/" in ln else ""
+        op = body.split()[0] if body else ""
+        if op.startswith("@"):
+            op = body.split()[1] if len(body.split()) > 1 else ""
+        for pat in ("LDG.E.128", "LDG.E.64", "LDG", "STG.E.128", "STG.E.64", "STG", "TEX", "ATOMG", "RED", "ATOMS", "SHFL", "VOTE", "MATCH",
+                    "LDS", "STS", "LDL", "STL", "BAR", "FFMA", "MUFU", "HMMA", "UTC", "UTMA"):
+            if op.startswith(pat):
+                kernels[cur][pat] = kernels[cur].get(pat, 0) + 1
+                break
+lines = [f"# {tag} — SASS mnemonic counts per kernel (`cuobjdump -sass libpf_cuda.so`, sm_100a)", "",
+         "No tensor-core (`HMMA`/`UTC*MMA`) or TMA (`UTMA*`) instructions are expected: nothing on this path is a dense "
+         "contraction or a bulk tile copy (BASELINE.json north_star). `LDL`/`STL` = local memory (the dice deep-recursion fallback, a small composite spill).", "",
+         "| kernel | " + " | ".join(["LDG.E.128", "LDG.E.64", "LDG", "STG.E.128", "STG", "TEX", "ATOMG", "RED", "ATOMS", "SHFL", "VOTE", "LDS", "STS", "LDL", "STL", "BAR", "FFMA", "HMMA", "UTC", "UTMA"]) + " |",
+         "|---|" + "---:|" * 20]
+import re
+for name, c in kernels.items():
+    short = re.sub(r"^_ZN2pf\d+", "", name)[:40]
+    lines.append(f"| `{short}` | " + " | ".join(str(c.get(k, 0)) for k in ["LDG.E.128", "LDG.E.64", "LDG", "STG.E.128", "STG", "TEX", "ATOMG", "RED", "ATOMS", "SHFL", "VOTE", "LDS", "STS", "LDL", "STL", "BAR", "FFMA", "HMMA", "UTC", "UTMA"]) + " |")
+open(os.path.join(out_dir, f"{tag}_sass.md"), "w").write("\n".join(lines) + "\n")
+print("wrote", [f for f in os.listdir(out_dir) if f.startswith(tag)])
