@@ -188,6 +188,10 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOAD_NAMES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="nccl", choices=["peer", "nccl"],
+                    help="N > 1: 'nccl' = all_gather_into_tensor on NCCL's stream, overlapped with the next frame; "
+                         "'peer' = the fused fill+tile kernel stores every tile into all peers' frames over NVLink "
+                         "(IPC-mapped buffers) + one barrier (measured slower at 8 GPUs: 64-byte remote stores)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3
@@ -245,23 +249,47 @@ def main():
         # N): one untimed full-frame render gives the count before the strip is set.
         f.scene.build_and_render(f.renderer, f.options)
         f.full_stats = f.renderer.stats()
+        # Frames are enqueued back to back: the check that no stage overflowed its bound happens at
+        # the next use of the renderer instead of stalling the host at the end of every batch.
+        f.renderer.set_deferred_verification(True)
         if world > 1:
             f.renderer.set_strip(f.y0, f.y1)
             f.strip_view = f.full[f.y0 * 16:f.y1 * 16]
         f.host = torch.empty((size, size, 4), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
         f.copied = None
+        f.gather = None
+        f.peer = False
+        if world > 1 and args.gather == "peer":
+            # Exchange CUDA IPC handles of the frame buffers; every rank then writes its strip into all copies.
+            mine = api.ipc_export(f.full.data_ptr())
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine)
+            peers = [everyone[i] for i in range(world) if i != rank]
+            f.renderer.set_peer_dests([h for h, _ in peers], [o for _, o in peers])
+            f.peer = True
         frames.append(f)
 
     copy_stream = torch.cuda.Stream()
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
 
     def render_frame(f, e2e: bool):
         if e2e:
             f.scene.set_view_box(f.flat.view_box)  # bumps the epoch: the scene is re-uploaded from host memory
             if f.copied is not None:
                 stream.wait_event(f.copied)  # the previous read-back of this frame buffer must be done
+        if f.gather is not None:
+            f.gather.wait()  # the previous all-gather of this frame buffer must be done before it is redrawn
+            f.gather = None
         f.scene.build_and_render(f.renderer, f.options)
         if dist is not None:
-            dist.all_gather_into_tensor(f.full.view(-1), f.strip_view.reshape(-1))
+            if f.peer:
+                dist.all_reduce(flag)  # barrier on the stream: every rank's strip has landed in every frame copy
+            else:
+                # Asynchronous: runs on NCCL's stream after this frame's kernels, while the next frame renders.
+                f.gather = dist.all_gather_into_tensor(f.full.view(-1), f.strip_view.reshape(-1), async_op=True)
+                if e2e and rank == 0:
+                    f.gather.wait()
+                    f.gather = None
         if e2e and rank == 0:
             # Device -> pinned host read-back of the assembled frame on a copy stream, so it overlaps
             # the host-side build and the rendering of the next frame.
@@ -393,7 +421,8 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAMES[args.workload], "frames_per_step": len(frames),
                    "segments_per_step": seg_per_step,
-                   "parallelism": f"tile-strip x{world}" + (" + NCCL all-gather" if world > 1 else ""),
+                   "parallelism": f"tile-strip x{world}" + ((" + fused peer-store gather (NVLink P2P) + barrier" if args.gather == "peer"
+                                                             else " + NCCL all-gather overlapped with the next frame") if world > 1 else ""),
                    "l2": "inputs larger than L2: a step touches > 1 GB of stage buffers and frames",
                    "ms_per_frame": {f.name: stage_acc[f.name]["total_ms"] / args.steps for f in frames},
                    "stage_ms": {f.name: {k: v / args.steps for k, v in stage_acc[f.name].items()} for f in frames}},

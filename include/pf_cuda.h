@@ -262,9 +262,25 @@ PFCudaStatus PFCudaRendererGetDestDevicePointer(PFCudaRendererRef renderer, uint
  * all-gather buffer); pass 0 to return to the renderer-owned image. */
 PFCudaStatus PFCudaRendererSetDestDevicePointer(PFCudaRendererRef renderer, uint64_t device_ptr,
                                                 size_t pitch_bytes);
+/* Fused all-gather for the strip partition: every rank exports its frame buffer with PFCudaIpcExport
+ * (a 64-byte CUDA IPC handle + the pointer's offset inside its allocation), the handles are exchanged
+ * out of band (e.g. torch.distributed.all_gather_object), and each rank registers its peers' buffers
+ * here. From then on the fused fill+tile kernel stores every finished tile into the local image and
+ * into all peers' images over NVLink, so no separate collective is needed — only a barrier before the
+ * assembled frame is read. count = 0 removes the peers. At most 7 peers (8 GPUs). */
+PFCudaStatus PFCudaIpcExport(uint64_t device_ptr, uint8_t handle_out[64], uint64_t *offset_out);
+PFCudaStatus PFCudaRendererSetPeerDests(PFCudaRendererRef renderer, const uint8_t *handles,
+                                        const uint64_t *offsets, int32_t count);
 /* Uses the given cudaStream_t (as an integer handle) for all work; 0 = the renderer's own. */
 PFCudaStatus PFCudaRendererSetStream(PFCudaRendererRef renderer, uint64_t cuda_stream);
-/* Blocks until all submitted work is complete. */
+/* In steady state (cached batch, bounds from the previous frame) the only host wait of a frame is the
+ * check that no stage overflowed its bound. With deferred verification that check moves to the next
+ * call on this renderer (begin_scene, ReadPixels, Synchronize, GetStats, ...), so consecutive frames
+ * are enqueued without any host wait; a frame that did overflow is re-rendered then. Callers that hand
+ * the destination to an external consumer (peer copy, collective) on the stream should call
+ * PFCudaRendererSynchronize first if they cannot tolerate a frame being repaired late. Default: off. */
+PFCudaStatus PFCudaRendererSetDeferredVerification(PFCudaRendererRef renderer, int32_t enabled);
+/* Blocks until all submitted work is complete (and verified). */
 PFCudaStatus PFCudaRendererSynchronize(PFCudaRendererRef renderer);
 
 /* Multi-GPU strip partition (not in the reference): this renderer owns tile rows
@@ -296,6 +312,7 @@ typedef struct PFCudaRenderStats {
     uint64_t visible_fill_count;   /* fills of tiles that survived the z-cull (read by fill+tile) */
     uint64_t h2d_bytes;            /* host-to-device bytes copied this frame */
     uint64_t batch_cache_hits;     /* batches rendered from the cached device-side metadata */
+    uint64_t reruns;               /* batches re-rendered because a stage overflowed its bound */
 } PFCudaRenderStats;
 PFCudaStatus PFCudaRendererGetStats(PFCudaRendererRef renderer, PFCudaRenderStats *stats);
 

@@ -177,7 +177,7 @@ class PFCudaRenderStats(C.Structure):
         "path_count", "fill_count", "alpha_tile_count", "total_tile_count", "cpu_build_time_ns",
         "drawcall_count", "gpu_bytes_allocated", "gpu_bytes_committed", "input_segment_count",
         "line_segment_count", "tile_list_entry_count", "column_count", "host_sync_count",
-        "visible_fill_count", "h2d_bytes", "batch_cache_hits")]
+        "visible_fill_count", "h2d_bytes", "batch_cache_hits", "reruns")]
 
 
 class PFCudaRenderTime(C.Structure):
@@ -208,8 +208,11 @@ SIGNATURES = {
     "PFCudaRendererReadPixels": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "PFCudaRendererGetDestDevicePointer": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_size_t)]),
     "PFCudaRendererSetDestDevicePointer": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_size_t]),
+    "PFCudaIpcExport": (C.c_int32, [C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "PFCudaRendererSetPeerDests": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "PFCudaRendererSetStream": (C.c_int32, [C.c_void_p, C.c_uint64]),
     "PFCudaRendererSynchronize": (C.c_int32, [C.c_void_p]),
+    "PFCudaRendererSetDeferredVerification": (C.c_int32, [C.c_void_p, C.c_int32]),
     "PFCudaRendererSetStrip": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
     "PFCudaRendererSetViewBox": (C.c_int32, [C.c_void_p, C.POINTER(PFRectF)]),
     "PFCudaRendererGetStats": (C.c_int32, [C.c_void_p, C.POINTER(PFCudaRenderStats)]),

@@ -154,6 +154,14 @@ class Scene:
             pass
 
 
+def ipc_export(device_ptr: int):
+    """(handle bytes, offset) of a device allocation, to be opened by peer processes."""
+    h = (C.c_uint8 * 64)()
+    off = C.c_uint64()
+    L.check(L.lib().PFCudaIpcExport(device_ptr, h, C.byref(off)))
+    return bytes(h), int(off.value)
+
+
 class CudaRenderer:
     """Renderer<CudaDevice> at RendererLevel::D3D11."""
 
@@ -212,8 +220,20 @@ class CudaRenderer:
         L.check(L.lib().PFCudaRendererGetDestDevicePointer(self._h, C.byref(p), C.byref(pitch)))
         return int(p.value), int(pitch.value)
 
+    def set_peer_dests(self, handles: list, offsets: list):
+        """Registers the peers' frame buffers (IPC handles from ipc_export) for the fused gather."""
+        n = len(handles)
+        buf = (C.c_uint8 * (64 * max(n, 1)))()
+        for i, h in enumerate(handles):
+            C.memmove(C.addressof(buf) + 64 * i, bytes(h), 64)
+        offs = (C.c_uint64 * max(n, 1))(*[int(o) for o in offsets])
+        L.check(L.lib().PFCudaRendererSetPeerDests(self._h, buf, offs, n))
+
     def set_debug_lists_enabled(self, enabled: bool):
         L.check(L.lib().PFCudaRendererSetDebugListsEnabled(self._h, int(enabled)))
+
+    def set_deferred_verification(self, enabled: bool):
+        L.check(L.lib().PFCudaRendererSetDeferredVerification(self._h, int(enabled)))
 
     def set_timing_enabled(self, enabled: bool):
         L.check(L.lib().PFCudaRendererSetTimingEnabled(self._h, int(enabled)))

@@ -766,14 +766,19 @@ __global__ void __launch_bounds__(256)
     k_list_emit(BatchDev b, const uint32_t *__restrict__ tile_fb, const uint32_t *__restrict__ tile_word,
                 const uint32_t *__restrict__ tile_fill_pos, const uint32_t *__restrict__ fb_start,
                 uint32_t *__restrict__ fb_cursor, TileEntry *__restrict__ entries, uint32_t capacity,
-                uint32_t *__restrict__ visible_fill_count) {
+                OverflowGuard guard) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    // All totals are final by now. A batch that overflowed a stage buffer must leave the destination
+    // untouched (the exact-sized re-run may have to load it): park the fused kernel's work counter
+    // past the end so its warps find nothing to do.
+    if (t == 0 && (guard.totals[0] > guard.line_bound || guard.totals[2] > guard.entry_bound ||
+                   guard.totals[5] > guard.fill_bound))
+        *guard.work_counter = 0xf0000000u;
     const bool in_range = t < b.n_tiles;
     uint32_t fbi = in_range ? __ldg(tile_fb + t) : 0xffffffffu;
     const bool live = fbi != 0xffffffffu;
     if (!__any_sync(0xffffffffu, live)) return;
     uint32_t p = live ? search_coarse(b.path_tile_offset, b.tile_index, t) : 0;
-    uint32_t visible = 0;
     if (live) {
         TileEntry e;
         e.fill_end = __ldg(tile_fill_pos + t); // the bin emit pass left the cursor at the end of the run
@@ -782,21 +787,15 @@ __global__ void __launch_bounds__(256)
         e.tile_index = t;
         uint32_t slot = __ldg(fb_start + fbi) + atomicAdd(fb_cursor + fbi, 1u);
         if (slot < capacity) *reinterpret_cast<uint4 *>(entries + slot) = *reinterpret_cast<uint4 *>(&e);
-        visible = e.word & 0x00ffffffu;
-    }
-    // Fills the fused kernel will actually read (statistics for the roofline's algorithmic bytes).
-    if (visible_fill_count) {
-        for (int d = 16; d > 0; d >>= 1) visible += __shfl_down_sync(0xffffffffu, visible, d);
-        if ((threadIdx.x & 31) == 0 && visible) atomicAdd(visible_fill_count, visible);
     }
 }
 
 int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t *tile_word,
                      const uint32_t *tile_fill_pos, const uint32_t *fb_start, uint32_t *fb_cursor,
-                     TileEntry *entries, uint32_t capacity, uint32_t *visible_fill_count, cudaStream_t stream) {
+                     TileEntry *entries, uint32_t capacity, const OverflowGuard &guard, cudaStream_t stream) {
     if (b.n_tiles == 0) return 0;
     k_list_emit<<<div_up(b.n_tiles, 256), 256, 0, stream>>>(b, tile_fb, tile_word, tile_fill_pos, fb_start, fb_cursor,
-                                                             entries, capacity, visible_fill_count);
+                                                             entries, capacity, guard);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -1035,31 +1034,41 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS) k_composite(CompositeArg
             blend(dst[k], base, base.w * mask_alpha(coverage, ctrl));
         }
     }
+    // ---- store: into the local image and, when the frame is strip-partitioned over several GPUs,
+    // straight into every peer's copy of the frame over NVLink (P2P stores to IPC-mapped buffers) —
+    // the all-gather that assembles the frame is fused into this kernel's epilogue, so it overlaps
+    // the compositing of the other tiles instead of running as a separate collective afterwards.
+    uint32_t pk[8];
     if (uniform) {
         const uint32_t packed = pack_rgba8(uni);
-        // One colour for the whole tile: when the tile lies inside the image and rows are 16-byte
-        // aligned, lane l writes half of row l/2 with two 128-bit stores instead of eight 32-bit ones.
-        const bool inside = tx >= 0 && ty >= 0 && tx * 16 + 16 <= a.dest_w && ty * 16 + 16 <= a.dest_h;
-        if (inside && (((uintptr_t)a.dest | a.dest_pitch) & 15) == 0) {
-            uint8_t *row = a.dest + (size_t)(ty * 16 + (lane >> 1)) * a.dest_pitch + (size_t)tx * 64 + (size_t)(lane & 1) * 32;
-            const uint4 v = make_uint4(packed, packed, packed, packed);
-            reinterpret_cast<uint4 *>(row)[0] = v;
-            reinterpret_cast<uint4 *>(row)[1] = v;
-        } else if (row_mask == 0xffu) {
 #pragma unroll
-            for (int k = 0; k < 8; k++, out += a.dest_pitch) *reinterpret_cast<uint32_t *>(out) = packed;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; k++, out += a.dest_pitch)
-                if (row_mask & (1u << k)) *reinterpret_cast<uint32_t *>(out) = packed;
-        }
-    } else if (row_mask == 0xffu) {
-#pragma unroll
-        for (int k = 0; k < 8; k++, out += a.dest_pitch) *reinterpret_cast<uint32_t *>(out) = pack_rgba8(dst[k]);
+        for (int k = 0; k < 8; k++) pk[k] = packed;
     } else {
 #pragma unroll
-        for (int k = 0; k < 8; k++, out += a.dest_pitch)
-            if (row_mask & (1u << k)) *reinterpret_cast<uint32_t *>(out) = pack_rgba8(dst[k]);
+        for (int k = 0; k < 8; k++) pk[k] = pack_rgba8(dst[k]);
+    }
+    // One colour for the whole tile: when the tile lies inside the image and rows are 16-byte
+    // aligned, lane l writes half of row l/2 with two 128-bit stores instead of eight 32-bit ones.
+    const bool vec = uniform && tx >= 0 && ty >= 0 && tx * 16 + 16 <= a.dest_w && ty * 16 + 16 <= a.dest_h &&
+                     (a.dest_align_mask & 15) == 0;
+    const size_t vec_off = (size_t)(ty * 16 + (lane >> 1)) * a.dest_pitch + (size_t)tx * 64 + (size_t)(lane & 1) * 32;
+    const ptrdiff_t px_off = (ptrdiff_t)py0 * (ptrdiff_t)a.dest_pitch + (ptrdiff_t)px * 4;
+    for (int d = 0; d < a.n_dest; d++) {
+        uint8_t *base = a.dests[d];
+        if (vec) {
+            const uint4 v = make_uint4(pk[0], pk[0], pk[0], pk[0]);
+            reinterpret_cast<uint4 *>(base + vec_off)[0] = v;
+            reinterpret_cast<uint4 *>(base + vec_off)[1] = v;
+        } else if (row_mask == 0xffu) {
+            uint8_t *o = base + px_off;
+#pragma unroll
+            for (int k = 0; k < 8; k++, o += a.dest_pitch) *reinterpret_cast<uint32_t *>(o) = pk[k];
+        } else {
+            uint8_t *o = base + px_off;
+#pragma unroll
+            for (int k = 0; k < 8; k++, o += a.dest_pitch)
+                if (row_mask & (1u << k)) *reinterpret_cast<uint32_t *>(o) = pk[k];
+        }
     }
     __syncwarp(); // the next tile reuses this warp's shared-memory slots
     }

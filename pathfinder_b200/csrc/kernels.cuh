@@ -122,10 +122,16 @@ int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_
 int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
                       uint32_t *fb_count, uint32_t *tile_fill_pos, uint32_t *fill_cursor, uint32_t *path_live,
                       bool keep_all_fills, cudaStream_t stream);
+// Device-side totals ([0] lines, [2] entries, [5] visible fills) and the capacities they must fit.
+struct OverflowGuard {
+    const uint32_t *totals;
+    uint32_t line_bound, entry_bound, fill_bound;
+    uint32_t *work_counter; // the fused kernel's tile counter; parked past the end on overflow
+};
 // Appends one TileEntry per surviving tile to its framebuffer tile's run [fb_start, fb_start + count).
 int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t *tile_word,
                      const uint32_t *tile_fill_pos, const uint32_t *fb_start, uint32_t *fb_cursor,
-                     TileEntry *entries, uint32_t capacity, uint32_t *visible_fill_count, cudaStream_t stream);
+                     TileEntry *entries, uint32_t capacity, const OverflowGuard &guard, cudaStream_t stream);
 
 struct CompositeArgs {
     const TileEntry *entries;   // runs in arbitrary order; the kernel sorts each by tile_index
@@ -135,7 +141,10 @@ struct CompositeArgs {
     cudaTextureObject_t area_lut;
     FbRect fb;
     int32_t tile_y0, tile_y1;  // tile rows composited by this renderer (strip)
-    uint8_t *dest;
+    uint8_t *dest;             // local image (also dests[0])
+    uint8_t *dests[8];         // local image first, then the peers' images (same layout) for the fused gather
+    int n_dest;
+    uint32_t dest_align_mask;  // OR of all destination addresses and the pitch (low bits: alignment)
     size_t dest_pitch;
     int32_t dest_w, dest_h;
     float4 clear_color;

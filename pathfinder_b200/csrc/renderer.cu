@@ -8,6 +8,7 @@
 //     exact (the reference re-runs dice/bin with doubled buffers, d3d11/renderer.rs:463-499);
 //   * fill and tile are one kernel (the alpha mask never reaches HBM);
 //   * tile lists are sorted by a device radix sort instead of per-tile linked lists.
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <atomic>
@@ -67,6 +68,14 @@ struct BatchCache {
 
 constexpr uint32_t LONG_QUEUE_CAPACITY = 1u << 18; // more long lines than this fall back to the per-thread walk
 
+// Bounds of the batch whose totals have not been checked yet (deferred verification).
+struct PendingVerify {
+    bool active = false;
+    uint32_t line_bound = 0, fill_bound = 0, entry_bound = 0, emit_bound = 0;
+    int launches = 0;
+    int batches_drawn_before = 0;
+};
+
 struct StageTimer {
     cudaEvent_t ev[8];
     bool created = false;
@@ -116,6 +125,10 @@ struct PFCudaRenderer {
 
     // Strip partition.
     int32_t strip_y0 = 0, strip_y1 = 0;
+    // Peers' copies of the frame (IPC-mapped), written by the fused gather in k_composite.
+    uint8_t *peer_dest[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *peer_base[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n_peers = 0;
 
     // Per-batch device buffers.
     DeviceBuffer<uint8_t> batch_meta; // PathInfo[P] + 3 search arrays
@@ -144,6 +157,9 @@ struct PFCudaRenderer {
     DeviceBuffer<uint8_t> dump_out;
 
     BatchCache cache;
+    PendingVerify pending;
+    cudaEvent_t verify_event = nullptr;
+    bool deferred_verify = false;
     uint64_t scene_generation = 0, paint_generation = 0;
     uint64_t paint_key = 0;
     bool always_size = false; // debugging aid: read every count back (three syncs per batch)
@@ -233,6 +249,18 @@ FbRect framebuffer_tile_rect(const PFCudaRenderer *r) {
     fb.max_x = (r->options.dest_size.x + PF_TILE_WIDTH - 1) / PF_TILE_WIDTH;
     fb.max_y = (r->options.dest_size.y + PF_TILE_HEIGHT - 1) / PF_TILE_HEIGHT;
     return fb;
+}
+
+// Local image first, then the peers' images (fused all-gather, see k_composite).
+void fill_destinations(const PFCudaRenderer *r, CompositeArgs &ca) {
+    ca.dests[0] = r->dest;
+    ca.n_dest = 1;
+    uintptr_t bits = (uintptr_t)r->dest | (uintptr_t)r->dest_pitch;
+    for (int i = 0; i < r->n_peers && ca.n_dest < 8; i++) {
+        ca.dests[ca.n_dest++] = r->peer_dest[i];
+        bits |= (uintptr_t)r->peer_dest[i];
+    }
+    ca.dest_align_mask = (uint32_t)(bits & 0xffffffffu);
 }
 
 float4 clear_color(const PFCudaRenderer *r) {
@@ -484,6 +512,8 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
 // (d3d11/renderer.rs:218-229,338-353,634-648). Otherwise the counts stay on the device, grids are
 // sized from the previous frame's counts plus slack, and the only sync is the verification at the end.
 // Returns false when a bound was exceeded (the caller re-runs in sizing mode).
+bool finalize_batch(PFCudaRenderer *r);
+
 bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     cudaStream_t st = r->stream;
     BatchCache &c = r->cache;
@@ -624,8 +654,9 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     } else {
         launches += launch_bin(0 /* BIN_EMIT_LIVE */, b, ba, st);
     }
+    const OverflowGuard guard{r->counters.ptr, line_bound, entry_bound, fill_bound, r->counters.ptr + 12};
     launches += launch_list_emit(b, r->tile_fb.ptr, r->tile_word.ptr, r->tile_fill_pos.ptr, r->fb_start.ptr,
-                                 r->fb_cursor.ptr, r->entries.ptr, entry_bound, nullptr, st);
+                                 r->fb_cursor.ptr, r->entries.ptr, entry_bound, guard, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[6], st));
 
     // ---- fill + tile (fused).
@@ -640,6 +671,7 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     ca.tile_y0 = c.strip_y0;
     ca.tile_y1 = c.strip_y1;
     ca.dest = r->dest;
+    fill_destinations(r, ca);
     ca.dest_pitch = r->dest_pitch;
     ca.dest_w = r->options.dest_size.x;
     ca.dest_h = r->options.dest_size.y;
@@ -649,20 +681,42 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     launches += launch_composite(ca, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[7], st));
 
-    // ---- verification: one read-back of the totals at the end of the batch.
+    // ---- verification: one read-back of the totals at the end of the batch. With deferred
+    // verification the host does not wait for it here: the totals are checked the next time the
+    // renderer is used (verify_pending), so consecutive frames are enqueued back to back.
     r->counters_host.ensure(16);
     PF_CUDA_CHECK(cudaMemcpyAsync(r->counters_host.ptr, r->counters.ptr, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PendingVerify &pv = r->pending;
+    pv.line_bound = line_bound, pv.fill_bound = fill_bound, pv.entry_bound = entry_bound, pv.emit_bound = emit_bound;
+    pv.launches = launches;
+    pv.batches_drawn_before = r->batches_drawn;
+    if (r->deferred_verify && !sizing) {
+        if (!r->verify_event) PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->verify_event, cudaEventDisableTiming));
+        PF_CUDA_CHECK(cudaEventRecord(r->verify_event, st));
+        pv.active = true;
+        return true; // optimistic; verify_pending() repairs the frame if a bound was exceeded
+    }
     PF_CUDA_CHECK(cudaStreamSynchronize(st));
     r->stats.host_sync_count++;
+    return finalize_batch(r);
+}
+
+// Reads the totals of the batch whose counters have arrived in pinned memory, updates caches / stats /
+// stage times, and reports whether every stage stayed inside its bound.
+bool finalize_batch(PFCudaRenderer *r) {
+    enum { C_LINES = 0, C_FILLS = 1, C_ENTRIES = 2, C_VISIBLE_FILLS = 5 };
+    BatchCache &c = r->cache;
+    const BatchDev &b = c.batch;
+    const PendingVerify &pv = r->pending;
     const uint32_t n_lines = r->counters_host.ptr[C_LINES], n_fills = r->counters_host.ptr[C_FILLS],
                    n_entries = r->counters_host.ptr[C_ENTRIES], n_visible = r->counters_host.ptr[C_VISIBLE_FILLS];
-    r->stats.drawcall_count += (uint64_t)launches;
+    r->stats.drawcall_count += (uint64_t)pv.launches;
     c.n_lines = n_lines;
     c.n_fills = n_fills;
     c.n_entries = n_entries;
     c.n_visible_fills = n_visible;
-    if (n_lines > line_bound || n_visible > fill_bound || n_entries > entry_bound ||
-        (r->debug_lists && n_fills > emit_bound)) {
+    if (n_lines > pv.line_bound || n_visible > pv.fill_bound || n_entries > pv.entry_bound ||
+        (r->debug_lists && n_fills > pv.emit_bound)) {
         c.counts_valid = false;
         return false;
     }
@@ -673,15 +727,15 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     r->last_fills = n_fills;
     r->last_entries = n_entries;
     r->last_alpha_ids_valid = false;
-    r->last_fb = fb;
+    r->last_fb = b.fb;
     r->stats.path_count += b.n_paths;
     r->stats.fill_count += n_fills;
-    r->stats.total_tile_count += n_tiles;
-    r->stats.input_segment_count += n_segments;
+    r->stats.total_tile_count += b.n_tiles;
+    r->stats.input_segment_count += b.n_segments;
     r->stats.line_segment_count += n_lines;
     r->stats.tile_list_entry_count += n_entries;
     r->stats.visible_fill_count += n_visible;
-    r->stats.column_count += n_cols;
+    r->stats.column_count += b.n_columns;
 
     if (r->timing) {
         float ms[7];
@@ -699,8 +753,27 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     return true;
 }
 
+// Deferred verification: waits for the totals of the last batch (normally long finished), and if a
+// stage overflowed its bound re-renders that batch with exact sizing.
+void verify_pending(PFCudaRenderer *r) {
+    if (!r->pending.active) return;
+    r->pending.active = false;
+    PF_CUDA_CHECK(cudaEventSynchronize(r->verify_event));
+    r->stats.host_sync_count++;
+    if (finalize_batch(r)) return;
+    const int drawn_now = r->batches_drawn;
+    r->batches_drawn = r->pending.batches_drawn_before; // same load action as the failed attempt
+    const bool ok = run_pipeline(r, true);
+    r->batches_drawn = drawn_now;
+    r->stats.reruns++;
+    if (!ok) throw Error(PF_CUDA_ERROR_CUDA, "stage buffer overflow after exact sizing (internal error)");
+}
+
 // One DrawTilesD3D11 batch: prepare_tiles + draw_tiles (d3d11/renderer.rs:414-424).
+void verify_pending(PFCudaRenderer *r);
+
 void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
+    verify_pending(r);
     if (!r->has_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "DrawTilesD3D11 before UploadSceneD3D11");
     if (batch.path_source != PF_PATH_SOURCE_DRAW)
         throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "draw batch with a clip path source");
@@ -746,6 +819,7 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     bool ok = run_pipeline(r, !c.counts_valid || r->always_size);
     if (!ok) {
         ok = run_pipeline(r, true);
+        r->stats.reruns++;
         if (!ok) throw Error(PF_CUDA_ERROR_CUDA, "stage buffer overflow after exact sizing (internal error)");
     }
     r->batches_drawn++;
@@ -768,6 +842,12 @@ void ensure_alpha_ids(PFCudaRenderer *r) {
                         r->tile_alpha_id.ptr, st);
     r->last_alpha_tiles = n_fills ? read_counter(r, 3) : 0;
     r->last_alpha_ids_valid = true;
+}
+
+void close_peers(PFCudaRenderer *r) {
+    for (int i = 0; i < r->n_peers; i++)
+        if (r->peer_base[i]) cudaIpcCloseMemHandle(r->peer_base[i]);
+    r->n_peers = 0;
 }
 
 template <typename F>
@@ -862,6 +942,8 @@ void PFCudaRendererDestroy(PFCudaRendererRef r) {
     if (!r) return;
     cudaSetDevice(r->ordinal);
     cudaStreamSynchronize(r->stream);
+    close_peers(r);
+    if (r->verify_event) cudaEventDestroy(r->verify_event);
     if (r->lut_tex) cudaDestroyTextureObject(r->lut_tex);
     if (r->lut_array) cudaFreeArray(r->lut_array);
     if (r->meta_copied) cudaEventDestroy(r->meta_copied);
@@ -873,6 +955,7 @@ void PFCudaRendererDestroy(PFCudaRendererRef r) {
 
 PFCudaStatus PFCudaRendererSetOptions(PFCudaRendererRef r, const PFCudaRendererOptions *options) {
     return guarded(r, [&]() {
+        verify_pending(r);
         if (!options) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null options");
         PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
         r->options = *options;
@@ -883,6 +966,7 @@ PFCudaStatus PFCudaRendererSetOptions(PFCudaRendererRef r, const PFCudaRendererO
 PFCudaStatus PFCudaRendererBeginScene(PFCudaRendererRef r) {
     return guarded(r, [&]() {
         if (r->in_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "begin_scene called twice");
+        verify_pending(r); // the previous frame's totals (deferred verification)
         r->in_scene = true;
         r->batches_drawn = 0;
         r->stats = PFCudaRenderStats{};
@@ -961,6 +1045,7 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
             ca.tile_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
             ca.tile_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
             ca.dest = r->dest;
+            fill_destinations(r, ca);
             ca.dest_pitch = r->dest_pitch;
             ca.dest_w = r->options.dest_size.x;
             ca.dest_h = r->options.dest_size.y;
@@ -976,6 +1061,7 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
 
 PFCudaStatus PFCudaRendererReadPixels(PFCudaRendererRef r, uint8_t *dst, size_t stride) {
     return guarded(r, [&]() {
+        verify_pending(r);
         size_t row = (size_t)r->options.dest_size.x * 4;
         if (!dst || stride < row) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "bad destination / stride");
         PF_CUDA_CHECK(cudaMemcpy2DAsync(dst, stride, r->dest, r->dest_pitch, row, (size_t)r->options.dest_size.y,
@@ -993,6 +1079,7 @@ PFCudaStatus PFCudaRendererGetDestDevicePointer(PFCudaRendererRef r, uint64_t *d
 
 PFCudaStatus PFCudaRendererSetDestDevicePointer(PFCudaRendererRef r, uint64_t device_ptr, size_t pitch) {
     return guarded(r, [&]() {
+        verify_pending(r);
         PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
         if (device_ptr == 0) {
             r->dest_external = false;
@@ -1006,19 +1093,66 @@ PFCudaStatus PFCudaRendererSetDestDevicePointer(PFCudaRendererRef r, uint64_t de
     });
 }
 
+PFCudaStatus PFCudaIpcExport(uint64_t device_ptr, uint8_t handle_out[64], uint64_t *offset_out) {
+    try {
+        if (!device_ptr || !handle_out || !offset_out) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null argument");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        PF_CUDA_CHECK(cudaIpcGetMemHandle(&h, reinterpret_cast<void *>((uintptr_t)device_ptr)));
+        memcpy(handle_out, &h, 64);
+        // The handle names the whole allocation: report where the pointer sits inside it.
+        // (driver entry point fetched at run time: the library must load on machines without libcuda)
+        typedef CUresult (*GetAddressRangeFn)(CUdeviceptr *, size_t *, CUdeviceptr);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult query;
+        PF_CUDA_CHECK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &query));
+        CUdeviceptr base = 0;
+        size_t size = 0;
+        if (!fn || reinterpret_cast<GetAddressRangeFn>(fn)(&base, &size, (CUdeviceptr)device_ptr) != CUDA_SUCCESS)
+            throw Error(PF_CUDA_ERROR_CUDA, "cuMemGetAddressRange failed");
+        *offset_out = (uint64_t)device_ptr - (uint64_t)base;
+        return PF_CUDA_OK;
+    } catch (const Error &e) {
+        set_last_error(e.what());
+        return e.status;
+    }
+}
+
+PFCudaStatus PFCudaRendererSetPeerDests(PFCudaRendererRef r, const uint8_t *handles, const uint64_t *offsets,
+                                        int32_t count) {
+    return guarded(r, [&]() {
+        verify_pending(r);
+        PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        close_peers(r);
+        if (count < 0 || count > 7) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "at most 7 peers");
+        for (int i = 0; i < count; i++) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + (size_t)i * 64, 64);
+            void *base = nullptr;
+            PF_CUDA_CHECK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            r->peer_base[i] = base;
+            r->peer_dest[i] = static_cast<uint8_t *>(base) + offsets[i];
+            r->n_peers = i + 1;
+        }
+    });
+}
+
 PFCudaStatus PFCudaRendererSetStream(PFCudaRendererRef r, uint64_t cuda_stream) {
     return guarded(r, [&]() {
+        verify_pending(r);
         PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
         r->stream = cuda_stream ? reinterpret_cast<cudaStream_t>((uintptr_t)cuda_stream) : r->own_stream;
     });
 }
 
 PFCudaStatus PFCudaRendererSynchronize(PFCudaRendererRef r) {
-    return guarded(r, [&]() { PF_CUDA_CHECK(cudaStreamSynchronize(r->stream)); });
+    return guarded(r, [&]() {
+        verify_pending(r); PF_CUDA_CHECK(cudaStreamSynchronize(r->stream)); });
 }
 
 PFCudaStatus PFCudaRendererSetStrip(PFCudaRendererRef r, int32_t tile_y0, int32_t tile_y1) {
     return guarded(r, [&]() {
+        verify_pending(r);
         if (tile_y1 < tile_y0) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "strip rows out of order");
         r->strip_y0 = tile_y0;
         r->strip_y1 = tile_y1;
@@ -1059,6 +1193,7 @@ PFCudaStatus PFSceneBuildAndRenderCuda(PFSceneRef scene, PFCudaRendererRef r, PF
 
 PFCudaStatus PFCudaRendererGetStats(PFCudaRendererRef r, PFCudaRenderStats *stats) {
     return guarded(r, [&]() {
+        verify_pending(r);
         if (!stats) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null stats");
         if (r->stats.fill_count == 0 && r->batches_drawn == 1 && !r->in_scene && r->last_batch.n_tiles) {
             // RenderStats.fill_count (all fills, before occlusion culling) is not needed to render:
@@ -1079,12 +1214,20 @@ PFCudaStatus PFCudaRendererGetStats(PFCudaRendererRef r, PFCudaRenderStats *stat
     });
 }
 
+PFCudaStatus PFCudaRendererSetDeferredVerification(PFCudaRendererRef r, int32_t enabled) {
+    return guarded(r, [&]() {
+        verify_pending(r);
+        r->deferred_verify = enabled != 0;
+    });
+}
+
 PFCudaStatus PFCudaRendererSetTimingEnabled(PFCudaRendererRef r, int32_t enabled) {
     return guarded(r, [&]() { r->timing = enabled != 0; });
 }
 
 PFCudaStatus PFCudaRendererGetTimes(PFCudaRendererRef r, PFCudaRenderTime *times) {
     return guarded(r, [&]() {
+        verify_pending(r);
         if (!times) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null times");
         *times = r->times;
     });
@@ -1092,6 +1235,7 @@ PFCudaStatus PFCudaRendererGetTimes(PFCudaRendererRef r, PFCudaRenderTime *times
 
 PFCudaStatus PFCudaRendererSetDebugListsEnabled(PFCudaRendererRef r, int32_t enabled) {
     return guarded(r, [&]() {
+        verify_pending(r);
         r->debug_lists = enabled != 0;
         r->cache.counts_valid = false; // the dump buffers must be sized on the next frame
     });
@@ -1099,6 +1243,7 @@ PFCudaStatus PFCudaRendererSetDebugListsEnabled(PFCudaRendererRef r, int32_t ena
 
 int64_t PFCudaRendererDebugCopyLines(PFCudaRendererRef r, float *out_lines, uint32_t *out_paths, size_t cap) {
     return guarded_count(r, [&]() -> int64_t {
+        verify_pending(r);
         size_t n = r->last_lines, m = n < cap ? n : cap;
         if (out_lines && m) PF_CUDA_CHECK(cudaMemcpyAsync(out_lines, r->lines.ptr, m * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
         if (out_paths && m) PF_CUDA_CHECK(cudaMemcpyAsync(out_paths, r->line_path.ptr, m * 4, cudaMemcpyDeviceToHost, r->stream));
@@ -1109,6 +1254,7 @@ int64_t PFCudaRendererDebugCopyLines(PFCudaRendererRef r, float *out_lines, uint
 
 int64_t PFCudaRendererDebugCopyFills(PFCudaRendererRef r, PFFill *out, size_t cap) {
     return guarded_count(r, [&]() -> int64_t {
+        verify_pending(r);
         size_t n = r->last_fills, m = n < cap ? n : cap;
         if (out && m) {
             ensure_alpha_ids(r);
@@ -1123,6 +1269,7 @@ int64_t PFCudaRendererDebugCopyFills(PFCudaRendererRef r, PFFill *out, size_t ca
 
 int64_t PFCudaRendererDebugCopyTiles(PFCudaRendererRef r, PFTileObjectPrimitive *out, size_t cap) {
     return guarded_count(r, [&]() -> int64_t {
+        verify_pending(r);
         ensure_alpha_ids(r);
         const BatchDev &b = r->last_batch;
         // tile_fb is free again after the sort stage: reuse it for the non-empty flags.
@@ -1143,6 +1290,7 @@ int64_t PFCudaRendererDebugCopyTiles(PFCudaRendererRef r, PFTileObjectPrimitive 
 
 int64_t PFCudaRendererDebugCopyZBuffer(PFCudaRendererRef r, int32_t *out, size_t cap, int32_t rect_out[4]) {
     return guarded_count(r, [&]() -> int64_t {
+        verify_pending(r);
         const FbRect &fb = r->last_fb;
         if (rect_out) {
             rect_out[0] = fb.min_x, rect_out[1] = fb.min_y, rect_out[2] = fb.max_x, rect_out[3] = fb.max_y;
@@ -1158,6 +1306,7 @@ int64_t PFCudaRendererDebugCopyZBuffer(PFCudaRendererRef r, int32_t *out, size_t
 
 int64_t PFCudaRendererDebugCopyAlphaMasks(PFCudaRendererRef r, float *out, size_t cap_tiles) {
     return guarded_count(r, [&]() -> int64_t {
+        verify_pending(r);
         ensure_alpha_ids(r);
         size_t n = r->last_alpha_tiles;
         if (out && n) {

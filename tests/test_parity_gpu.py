@@ -187,6 +187,36 @@ def test_cached_batch_and_strips_are_byte_identical(area_lut):
     r.close()
 
 
+@pytest.mark.parametrize("deferred", [False, True])
+def test_bound_overflow_is_repaired(area_lut, deferred):
+    """A batch of the same shape as the previous one runs with the previous totals as buffer bounds. When
+    the scene grew past them (same paths, larger transform) the frame must be re-rendered with exact
+    sizes — at the end of the batch, or with deferred verification at the next use of the renderer — and
+    the result must equal a fresh renderer's."""
+    from pathfinder_b200 import api
+    flat = scenes.random_paths(3000, 1024, 21, r_min=10.0, r_max=40.0)
+    scene = api.Scene.from_flat(flat)
+    small = api.BuildOptions(transform=api.Transform2F(0.1, 0.0, 0.0, 0.1, 100.0, 100.0))
+    large = api.BuildOptions()
+    r = api.CudaRenderer((1024, 1024), background_color=(1, 1, 1, 1))
+    r.set_deferred_verification(deferred)
+    scene.build_and_render(r, small)
+    small_stats = r.stats()
+    scene.build_and_render(r, large)
+    img = r.read_pixels()
+    s = r.stats()
+    assert s["reruns"] == 1 and s["fill_count"] > 2 * small_stats["fill_count"]
+    fresh = api.CudaRenderer((1024, 1024), background_color=(1, 1, 1, 1))
+    scene.build_and_render(fresh, large)
+    assert np.array_equal(img, fresh.read_pixels())
+    assert fresh.stats()["fill_count"] == s["fill_count"] and fresh.stats()["reruns"] == 0
+    # and the steady state afterwards needs neither a re-run nor, when deferred, a wait inside the frame
+    scene.build_and_render(r, large)
+    assert np.array_equal(r.read_pixels(), img) and r.stats()["reruns"] == 0
+    fresh.close()
+    r.close()
+
+
 def test_wrong_level_commands_are_rejected():
     """Renderer::require_d3d11 (gpu/renderer.rs:1349-1360): D3D9 commands panic at the D3D11 level."""
     from pathfinder_b200 import _lib as L
