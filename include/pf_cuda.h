@@ -199,7 +199,13 @@ typedef struct PFRenderCommand {
         struct { uint64_t path_count; uint32_t needs_readable_framebuffer; } start;
         struct { const PFTextureMetadataEntry *entries; size_t entry_count; uint64_t content_key; /* as
                  PFTileBatchDataD3D11.content_key */ } upload_texture_metadata;
-        struct { PFSegmentsD3D11 draw_segments, clip_segments; } upload_scene_d3d11;
+        struct { PFSegmentsD3D11 draw_segments, clip_segments;
+                 /* Extension (0 = the reference's semantics: the arrays are borrowed for the call, the
+                  * renderer waits for its copies). Non-zero: the caller keeps the arrays valid and
+                  * unmodified until the frame has been verified — PFCudaRendererEndScene by default,
+                  * with deferred verification the next BeginScene / Synchronize / ReadPixels / GetStats
+                  * on this renderer — so the host-to-device copies are enqueued without a wait. */
+                 uint32_t payload_persists; } upload_scene_d3d11;
         struct { PFTileBatchDataD3D11 batch; } prepare_clip_tiles_d3d11;
         struct { PFTileBatchDataD3D11 tile_batch_data; uint32_t has_color_texture; } draw_tiles_d3d11;
         struct { uint32_t render_target_id; } push_render_target;

@@ -107,7 +107,8 @@ class _UploadTextureMetadata(C.Structure):
 
 
 class _UploadSceneD3D11(C.Structure):
-    _fields_ = [("draw_segments", PFSegmentsD3D11), ("clip_segments", PFSegmentsD3D11)]
+    _fields_ = [("draw_segments", PFSegmentsD3D11), ("clip_segments", PFSegmentsD3D11),
+                ("payload_persists", C.c_uint32)]
 
 
 class _PrepareClipTiles(C.Structure):

@@ -1091,7 +1091,7 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     uint64_t want = (n_work + COMPOSITE_WARPS - 1) / COMPOSITE_WARPS;
     uint64_t resident = (uint64_t)sm_count * (uint64_t)blocks_per_sm[a.load_dest ? 1 : 0];
     unsigned grid = (unsigned)(want < resident ? want : resident);
-    PF_CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(uint32_t), stream));
+    // The caller has zeroed a.work_counter (the tile-list kernel may since have parked it past the end).
     if (a.load_dest)
         k_composite<true><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(a);
     else

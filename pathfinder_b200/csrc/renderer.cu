@@ -142,7 +142,6 @@ struct PFCudaRenderer {
     DeviceBuffer<int32_t> col_backdrop, col_backdrop_init;
     DeviceBuffer<uint32_t> long_queue; // lines walked by whole warps (k_bin_long)
     DeviceBuffer<uint32_t> path_live;  // per path: some tile with fills survived the z-cull
-    std::vector<uint32_t> meta_slot;   // host scratch: command path index -> kept index
     DeviceBuffer<PackedFill> fills;
     DeviceBuffer<EmitFill> fills_emit;
     DeviceBuffer<int32_t> z_buffer;
@@ -160,6 +159,9 @@ struct PFCudaRenderer {
     PendingVerify pending;
     cudaEvent_t verify_event = nullptr;
     bool deferred_verify = false;
+    // Host-to-device copies from caller-owned arrays (payload_persists) that no host wait has covered yet.
+    bool borrowed_copies_pending = false;
+    bool uploaded_scene_this_frame = false;
     uint64_t scene_generation = 0, paint_generation = 0;
     uint64_t paint_key = 0;
     bool always_size = false; // debugging aid: read every count back (three syncs per batch)
@@ -294,20 +296,29 @@ struct HostTimer {
     }
 };
 
-void upload_segments(PFCudaRenderer *r, SceneSegments &dst, const PFSegmentsD3D11 &src) {
+void upload_segments(PFCudaRenderer *r, SceneSegments &dst, const PFSegmentsD3D11 &src, bool payload_persists) {
     HostTimer timer("upload_segments");
+    LapTimer laps;
     dst.n_points = src.point_count;
     dst.n_indices = src.index_count;
     dst.points.ensure(src.point_count + 4);
     dst.indices.ensure(src.index_count + 1);
+    laps.lap("segments: ensure");
     if (src.point_count)
         PF_CUDA_CHECK(cudaMemcpyAsync(dst.points.ptr, src.points, src.point_count * sizeof(float2),
                                       cudaMemcpyHostToDevice, r->stream));
+    laps.lap("segments: enqueue points");
     if (src.index_count)
         PF_CUDA_CHECK(cudaMemcpyAsync(dst.indices.ptr, src.indices, src.index_count * sizeof(uint2),
                                       cudaMemcpyHostToDevice, r->stream));
-    // The payload is borrowed for this call only and may be pageable: wait for the copies.
-    PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    laps.lap("segments: enqueue indices");
+    if (src.point_count == 0 && src.index_count == 0) return;
+    if (payload_persists) {
+        r->borrowed_copies_pending = true; // covered by the frame's verification wait (or EndScene)
+    } else {
+        // The payload is borrowed for this call only and may be pageable: wait for the copies.
+        PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    }
     r->stats.h2d_bytes += src.point_count * sizeof(float2) + src.index_count * sizeof(uint2);
 }
 
@@ -340,24 +351,65 @@ void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *en
 void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch, const FbRect &fb,
                            int32_t strip_y0, int32_t strip_y1, BatchDev &b, bool &has_initial_backdrops) {
     HostTimer timer("upload_batch_metadata");
+    LapTimer laps;
     cudaStream_t st = r->stream;
     const uint32_t P = batch.path_count;
     const PFPrepareTilesInfoD3D11 &info = batch.prepare_info;
-    // Coarse search tables (see CoarseIndex): sized from upper bounds known before the loop.
+    // Coarse search tables (see CoarseIndex); sized once pass 1 has counted the kept tiles / columns.
     constexpr int SEG_SHIFT = 5, TILE_SHIFT = 7, COL_SHIFT = 5;
-    uint64_t tile_bound = 0, col_bound = 0;
-    for (uint32_t i = 0; i < P; i++) {
+    const uint32_t n_paints = (uint32_t)r->n_paints;
+    // A path without a tile in this strip contributes nothing (every fill is culled by add_fill,
+    // every backdrop adjustment by the rect test): it is dropped, segments included, so dice / bin
+    // / propagate only see the paths that reach the strip.
+    // Strip restriction: rows above the strip feed the column backdrops exactly like rows above the
+    // path rect do in the reference (builder.rs:609-612); rows below are ignored.
+    auto strip_rect = [&](uint32_t i, int32_t &w, int32_t &h) {
         const PFRectI &tr = info.propagate_metadata[i].tile_rect;
-        int64_t w = std::max<int64_t>(0, (int64_t)tr.lower_right.x - tr.origin.x);
-        int64_t h = std::max<int64_t>(0, (int64_t)tr.lower_right.y - tr.origin.y);
-        tile_bound += (uint64_t)(w * h);
-        col_bound += (uint64_t)w;
+        const int32_t min_y = std::max(tr.origin.y, strip_y0), max_y = std::min(tr.lower_right.y, strip_y1);
+        w = tr.lower_right.x - tr.origin.x, h = max_y - min_y;
+        return w > 0 && h > 0;
+    };
+    auto segments_of = [&](uint32_t i) {
+        const uint32_t seg_begin = info.dice_metadata[i].first_batch_segment_index;
+        const uint32_t seg_end = i + 1 < P ? info.dice_metadata[i + 1].first_batch_segment_index : batch.segment_count;
+        return seg_end - seg_begin;
+    };
+    // Pass 1 (parallel): what the kept paths of each chunk add to the running offsets (integer only);
+    // pass 2 (same chunks) starts from the prefix over chunks — a two-level scan.
+    struct ChunkSums {
+        uint64_t kept = 0, segments = 0, tiles = 0, columns = 0;
+        uint64_t pad[4]; // one cache line per chunk
+    };
+    const size_t chunks = chunk_count(P, 8192);
+    std::vector<ChunkSums> sums(chunks + 1);
+    parallel_chunks(P, chunks, [&](size_t chunk, size_t begin, size_t end) {
+        ChunkSums sum;
+        for (size_t i = begin; i < end; i++) {
+            int32_t w, h;
+            if (!strip_rect((uint32_t)i, w, h)) continue;
+            sum.kept++;
+            sum.segments += segments_of((uint32_t)i);
+            sum.tiles += (uint64_t)w * (uint64_t)h;
+            sum.columns += (uint64_t)w;
+        }
+        sums[chunk + 1] = sum;
+    });
+    for (size_t c = 1; c <= chunks; c++) { // exclusive prefix: sums[c] = totals of the chunks before c
+        sums[c].kept += sums[c - 1].kept;
+        sums[c].segments += sums[c - 1].segments;
+        sums[c].tiles += sums[c - 1].tiles;
+        sums[c].columns += sums[c - 1].columns;
     }
-    if (tile_bound >= 0xfffffff0ull) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "more than 2^32 bbox tiles in one batch");
-    const size_t seg_table_n = ((size_t)batch.segment_count >> SEG_SHIFT) + 2;
-    const size_t tile_table_cap = ((size_t)tile_bound >> TILE_SHIFT) + 2, col_table_cap = ((size_t)col_bound >> COL_SHIFT) + 2;
+    if (sums[chunks].tiles >= 0xfffffff0ull) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "more than 2^32 bbox tiles in one batch");
+    const uint32_t kept = (uint32_t)sums[chunks].kept, n_segments = (uint32_t)sums[chunks].segments,
+                   n_tiles = (uint32_t)sums[chunks].tiles, n_cols = (uint32_t)sums[chunks].columns;
+    laps.lap("meta pass 1");
+
+    // Host staging / device layout: [P records][3 x (P + 1) offsets][segment table][tile table][column table].
+    const size_t seg_table_n = ((size_t)n_segments >> SEG_SHIFT) + 2, tile_table_n = ((size_t)n_tiles >> TILE_SHIFT) + 2,
+                 col_table_n = ((size_t)n_cols >> COL_SHIFT) + 2;
     const size_t base_bytes = (size_t)P * sizeof(PathInfo) + 3 * (size_t)(P + 1) * sizeof(uint32_t);
-    const size_t meta_bytes = base_bytes + (seg_table_n + tile_table_cap + col_table_cap) * sizeof(uint32_t);
+    const size_t meta_bytes = base_bytes + (seg_table_n + tile_table_n + col_table_n) * sizeof(uint32_t);
     if (r->meta_copied) PF_CUDA_CHECK(cudaEventSynchronize(r->meta_copied));
     r->batch_meta_host.ensure(meta_bytes + 64);
     uint8_t *hbase = r->batch_meta_host.ptr;
@@ -365,46 +417,20 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
     uint32_t *h_seg_first = reinterpret_cast<uint32_t *>(hbase + (size_t)P * sizeof(PathInfo));
     uint32_t *h_tile_off = h_seg_first + (P + 1);
     uint32_t *h_col_off = h_tile_off + (P + 1);
-    uint64_t n_tiles64 = 0, n_cols64 = 0;
-    const uint32_t n_paints = (uint32_t)r->n_paints;
-    bool bad_paint = false;
-    uint32_t kept = 0, n_segments = 0;
-    // Pass 1 (sequential, integer only): which paths reach the strip, and their running offsets.
-    // A path without a tile in this strip contributes nothing (every fill is culled by add_fill,
-    // every backdrop adjustment by the rect test): it is dropped, segments included, so dice / bin
-    // / propagate only see the paths that reach the strip.
-    std::vector<uint32_t> &slot = r->meta_slot;
-    slot.resize(P);
-    for (uint32_t i = 0; i < P; i++) {
-        const PFRectI &tr = info.propagate_metadata[i].tile_rect;
-        // Strip restriction: rows above the strip feed the column backdrops exactly like rows
-        // above the path rect do in the reference (builder.rs:609-612); rows below are ignored.
-        const int32_t min_y = std::max(tr.origin.y, strip_y0), max_y = std::min(tr.lower_right.y, strip_y1);
-        const int32_t w = tr.lower_right.x - tr.origin.x, h = max_y - min_y;
-        if (w <= 0 || h <= 0) {
-            slot[i] = 0xffffffffu;
-            continue;
-        }
-        slot[i] = kept;
-        h_seg_first[kept] = n_segments;
-        h_tile_off[kept] = (uint32_t)n_tiles64;
-        h_col_off[kept] = (uint32_t)n_cols64;
-        kept++;
-        const uint32_t seg_begin = info.dice_metadata[i].first_batch_segment_index;
-        const uint32_t seg_end = i + 1 < P ? info.dice_metadata[i + 1].first_batch_segment_index : batch.segment_count;
-        n_segments += seg_end - seg_begin;
-        n_tiles64 += (uint64_t)w * (uint64_t)h;
-        n_cols64 += (uint64_t)w;
-    }
-    // Pass 2 (parallel): the 48-byte records.
+    h_seg_first[kept] = n_segments;
+    h_tile_off[kept] = n_tiles;
+    h_col_off[kept] = n_cols;
+    // Pass 2 (parallel): running offsets and the 48-byte records of the kept paths.
     std::atomic<bool> bad_paint_flag{false};
-    parallel_ranges(P, 16384, [&](size_t begin, size_t end) {
+    parallel_chunks(P, chunks, [&](size_t chunk, size_t begin, size_t end) {
         bool bad = false;
+        uint32_t k = (uint32_t)sums[chunk].kept, seg_first = (uint32_t)sums[chunk].segments,
+                 tile_off = (uint32_t)sums[chunk].tiles, col_off = (uint32_t)sums[chunk].columns;
         for (size_t i = begin; i < end; i++) {
-            const uint32_t k = slot[i];
             const PFTilePathInfoD3D11 &tp = info.tile_path_info[i];
             bad |= tp.color >= n_paints;
-            if (k == 0xffffffffu) continue;
+            int32_t w, h;
+            if (!strip_rect((uint32_t)i, w, h)) continue;
             const PFPropagateMetadataD3D11 &pm = info.propagate_metadata[i];
             const PFDiceMetadataD3D11 &dm = info.dice_metadata[i];
             PathInfo pi;
@@ -412,44 +438,51 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
             pi.max_x = pm.tile_rect.lower_right.x;
             pi.min_y = std::max(pm.tile_rect.origin.y, strip_y0);
             pi.max_y = std::min(pm.tile_rect.lower_right.y, strip_y1);
-            pi.tile_offset = h_tile_off[k];
-            pi.col_offset = h_col_off[k];
-            pi.seg_batch_first = h_seg_first[k];
+            pi.tile_offset = tile_off;
+            pi.col_offset = col_off;
+            pi.seg_batch_first = seg_first;
             pi.seg_global_first = dm.first_global_segment_index;
             pi.global_path_id = dm.global_path_id;
             pi.paint_ctrl = (uint32_t)tp.color | ((uint32_t)tp.ctrl << 16) | ((pm.z_write ? 1u : 0u) << 24);
             pi.clip_path_index = pm.clip_path_index;
             pi.pad = (uint32_t)i; // index in the command's arrays (initial backdrops are keyed by it)
             h_paths[k] = pi;
+            h_seg_first[k] = seg_first;
+            h_tile_off[k] = tile_off;
+            h_col_off[k] = col_off;
+            k++;
+            seg_first += segments_of((uint32_t)i);
+            tile_off += (uint32_t)((uint64_t)w * (uint64_t)h);
+            col_off += (uint32_t)w;
         }
         if (bad) bad_paint_flag.store(true);
     });
-    bad_paint = bad_paint_flag.load();
-    if (bad_paint) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "paint id outside the uploaded texture metadata");
-    if (n_tiles64 >= 0xfffffff0ull) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "more than 2^32 bbox tiles in one batch");
-    const uint32_t n_tiles = (uint32_t)n_tiles64, n_cols = (uint32_t)n_cols64;
-    h_seg_first[kept] = n_segments;
-    h_tile_off[kept] = n_tiles;
-    h_col_off[kept] = n_cols;
+    laps.lap("meta pass 2");
+    if (bad_paint_flag.load()) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "paint id outside the uploaded texture metadata");
     uint32_t *h_seg_table = h_col_off + (P + 1);
     uint32_t *h_tile_table = h_seg_table + seg_table_n;
-    uint32_t *h_col_table = h_tile_table + tile_table_cap;
-    auto build_table = [kept](const uint32_t *offsets, uint32_t count, int shift, uint32_t *table) {
-        // table[k] = largest p < kept with offsets[p] <= k << shift (offsets[0] == 0)
-        const size_t n = ((size_t)count >> shift) + 2;
-        uint32_t p = 0;
-        for (size_t k = 0; k < n; k++) {
-            const uint64_t x = (uint64_t)k << shift;
-            while (p + 1 < kept && offsets[p + 1] <= x) p++;
-            table[k] = p;
-        }
+    uint32_t *h_col_table = h_tile_table + tile_table_n;
+    // table[k] = largest p < kept with offsets[p] <= k << shift (offsets[0] == 0); chunks of the table
+    // are independent: each starts from a binary search and sweeps forward.
+    auto build_table = [kept](const uint32_t *offsets, size_t n, int shift, uint32_t *table) {
+        parallel_ranges(n, 8192, [&](size_t begin, size_t end) {
+            const uint64_t x0 = (uint64_t)begin << shift;
+            uint32_t p = (uint32_t)(std::upper_bound(offsets, offsets + kept, x0,
+                                                     [](uint64_t x, uint32_t o) { return x < (uint64_t)o; }) - offsets);
+            p = p ? p - 1 : 0;
+            for (size_t k = begin; k < end; k++) {
+                const uint64_t x = (uint64_t)k << shift;
+                while (p + 1 < kept && offsets[p + 1] <= x) p++;
+                table[k] = p;
+            }
+        });
     };
     if (kept) {
-        build_table(h_seg_first, n_segments, SEG_SHIFT, h_seg_table);
-        build_table(h_tile_off, n_tiles, TILE_SHIFT, h_tile_table);
-        build_table(h_col_off, n_cols, COL_SHIFT, h_col_table);
+        build_table(h_seg_first, seg_table_n, SEG_SHIFT, h_seg_table);
+        build_table(h_tile_off, tile_table_n, TILE_SHIFT, h_tile_table);
+        build_table(h_col_off, col_table_n, COL_SHIFT, h_col_table);
     }
-
+    laps.lap("meta tables");
     r->batch_meta.ensure(meta_bytes + 64, 1.25);
     if (meta_bytes) {
         PF_CUDA_CHECK(cudaMemcpyAsync(r->batch_meta.ptr, hbase, meta_bytes, cudaMemcpyHostToDevice, st));
@@ -457,6 +490,7 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
         PF_CUDA_CHECK(cudaEventRecord(r->meta_copied, st));
     }
     r->stats.h2d_bytes += meta_bytes;
+    laps.lap("meta enqueue copy");
 
     b = BatchDev{};
     b.points = r->draw_segments.points.ptr;
@@ -467,7 +501,7 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
     b.path_col_offset = b.path_tile_offset + (P + 1);
     b.seg_index = CoarseIndex{b.path_col_offset + (P + 1), SEG_SHIFT};
     b.tile_index = CoarseIndex{b.seg_index.table + seg_table_n, TILE_SHIFT};
-    b.col_index = CoarseIndex{b.tile_index.table + tile_table_cap, COL_SHIFT};
+    b.col_index = CoarseIndex{b.tile_index.table + tile_table_n, COL_SHIFT};
     b.n_paths = kept;
     b.n_segments = n_segments;
     b.n_tiles = n_tiles;
@@ -697,6 +731,7 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
         return true; // optimistic; verify_pending() repairs the frame if a bound was exceeded
     }
     PF_CUDA_CHECK(cudaStreamSynchronize(st));
+    r->borrowed_copies_pending = false;
     r->stats.host_sync_count++;
     return finalize_batch(r);
 }
@@ -759,6 +794,7 @@ void verify_pending(PFCudaRenderer *r) {
     if (!r->pending.active) return;
     r->pending.active = false;
     PF_CUDA_CHECK(cudaEventSynchronize(r->verify_event));
+    r->borrowed_copies_pending = false; // the event was recorded after every copy of that frame
     r->stats.host_sync_count++;
     if (finalize_batch(r)) return;
     const int drawn_now = r->batches_drawn;
@@ -992,10 +1028,13 @@ PFCudaStatus PFCudaRendererRenderCommand(PFCudaRendererRef r, const PFRenderComm
             }
             break;
         case PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11:
-            upload_segments(r, r->draw_segments, cmd->u.upload_scene_d3d11.draw_segments);
-            upload_segments(r, r->clip_segments, cmd->u.upload_scene_d3d11.clip_segments);
+            upload_segments(r, r->draw_segments, cmd->u.upload_scene_d3d11.draw_segments,
+                            cmd->u.upload_scene_d3d11.payload_persists != 0);
+            upload_segments(r, r->clip_segments, cmd->u.upload_scene_d3d11.clip_segments,
+                            cmd->u.upload_scene_d3d11.payload_persists != 0);
             r->has_scene = true;
             r->scene_generation++;
+            r->uploaded_scene_this_frame = true;
             break;
         case PF_RENDER_COMMAND_PREPARE_CLIP_TILES_D3D11:
             if (cmd->u.prepare_clip_tiles_d3d11.batch.path_count > 0)
@@ -1052,7 +1091,13 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
             ca.clear_color = clear_color(r);
             r->counters.ensure(16);
             ca.work_counter = r->counters.ptr + 12;
+            PF_CUDA_CHECK(cudaMemsetAsync(ca.work_counter, 0, sizeof(uint32_t), r->stream));
             r->stats.drawcall_count += (uint64_t)launch_composite(ca, r->stream);
+        }
+        if (r->borrowed_copies_pending && !r->pending.active) {
+            // payload_persists uploads of a frame that ended without a verification wait
+            PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+            r->borrowed_copies_pending = false;
         }
         r->stats.gpu_bytes_allocated = r->bytes_allocated;
         r->stats.gpu_bytes_committed = r->bytes_allocated;
@@ -1186,7 +1231,20 @@ PFCudaStatus PFSceneBuildAndRenderCuda(PFSceneRef scene, PFCudaRendererRef r, PF
     if (st != PF_CUDA_OK) return st;
     st = PFCudaRendererBeginScene(r);
     if (st != PF_CUDA_OK) return st;
+    // The scene's segment arrays outlive the frame, so their upload does not have to be waited for
+    // here: the scene itself waits (scene_note_borrowed) before it rewrites them.
+    r->uploaded_scene_this_frame = false;
+    pf::g_scene_payload_persists = true;
     st = PFSceneBuild(scene, options, &r->sink_state, forward_command, r);
+    pf::g_scene_payload_persists = false;
+    if (r->uploaded_scene_this_frame) {
+        try {
+            pf::scene_note_borrowed(scene, r->stream, r->ordinal);
+        } catch (const Error &e) {
+            set_last_error(e.what());
+            if (st == PF_CUDA_OK) st = (PFCudaStatus)e.status;
+        }
+    }
     PFCudaStatus end = PFCudaRendererEndScene(r);
     return st != PF_CUDA_OK ? st : end;
 }

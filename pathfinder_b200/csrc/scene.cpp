@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 namespace pf {
+thread_local bool g_scene_payload_persists = false;
 void set_last_error(const std::string &msg);
 }
 
@@ -135,6 +136,11 @@ struct PFScene {
     uint32_t id;
     uint32_t epoch = 0;
 
+    // Set while a renderer may still be copying seg_points / seg_indices (payload_persists uploads).
+    cudaEvent_t borrowed_event = nullptr;
+    int borrowed_device = -1;
+    bool borrowed = false;
+
     // Scratch reused across builds.
     HostBuffer<PFVector2F> seg_points;
     HostBuffer<PFSegmentIndicesD3D11> seg_indices;
@@ -163,6 +169,23 @@ struct PFBuildOptions {
     float dilation[2] = {0, 0};
     bool subpixel_aa_enabled = false;
 };
+
+namespace pf {
+void scene_note_borrowed(PFScene *s, cudaStream_t stream, int device) {
+    if (s->borrowed_event && s->borrowed_device != device) {
+        // the scene moved to a renderer on another GPU: events belong to the device they were created on
+        if (s->borrowed) cudaEventSynchronize(s->borrowed_event);
+        cudaEventDestroy(s->borrowed_event);
+        s->borrowed_event = nullptr;
+    }
+    if (!s->borrowed_event) {
+        PF_CUDA_CHECK(cudaEventCreateWithFlags(&s->borrowed_event, cudaEventDisableTiming));
+        s->borrowed_device = device;
+    }
+    PF_CUDA_CHECK(cudaEventRecord(s->borrowed_event, stream));
+    s->borrowed = true;
+}
+} // namespace pf
 
 namespace {
 
@@ -204,7 +227,15 @@ using pf::parallel_ranges;
 // paths: every contour's points followed by its first point again (implicit close), one index entry
 // per on-curve point, flagged quadratic / cubic by the control points that follow it. Output
 // positions are prefix sums of per-path counts, so paths are filled in parallel.
+// The previous upload of the segment arrays may still be in flight on a renderer's stream.
+void wait_for_borrowers(PFScene *s) {
+    if (!s->borrowed) return;
+    s->borrowed = false;
+    if (cudaEventSynchronize(s->borrowed_event) != cudaSuccess) (void)cudaGetLastError();
+}
+
 void build_segments(PFScene *s) {
+    wait_for_borrowers(s);
     const size_t n_paths = s->draw_paths.size();
     s->seg_path_offsets.resize(2 * (n_paths + 1));
     uint32_t *point_off = s->seg_path_offsets.data(), *index_off = point_off + (n_paths + 1);
@@ -278,7 +309,12 @@ PFRenderCommand make_command(uint32_t kind) {
 extern "C" {
 
 PFSceneRef PFSceneCreate(void) { return new PFScene(); }
-void PFSceneDestroy(PFSceneRef scene) { delete scene; }
+void PFSceneDestroy(PFSceneRef scene) {
+    if (!scene) return;
+    wait_for_borrowers(scene);
+    if (scene->borrowed_event) cudaEventDestroy(scene->borrowed_event);
+    delete scene;
+}
 
 void PFSceneSetViewBox(PFSceneRef s, const PFRectF *vb) {
     s->view_box = RectF{vb->origin.x, vb->origin.y, vb->lower_right.x, vb->lower_right.y};
@@ -446,6 +482,7 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         up.u.upload_scene_d3d11.draw_segments =
             PFSegmentsD3D11{s->seg_points.ptr, s->seg_point_count, s->seg_indices.ptr, s->seg_index_count};
         up.u.upload_scene_d3d11.clip_segments = PFSegmentsD3D11{nullptr, 0, nullptr, 0};
+        up.u.upload_scene_d3d11.payload_persists = pf::g_scene_payload_persists ? 1 : 0;
         SEND(up);
         sink->has_last_scene = 1;
         sink->last_scene_id = s->id;
@@ -473,24 +510,28 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         tile_count = segment_count = 0;
     }
     auto t_loop0 = std::chrono::steady_clock::now();
+    pf::LapTimer laps;
     if (rebuild) {
         const size_t n_paths = s->draw_paths.size();
-        for (const Path &p : s->draw_paths) {
-            if (p.clip_path != PF_CLIP_PATH_NONE) {
-                pf::set_last_error("clip paths are a 'next' row (SURVEY.md §8 f1)");
-                return PF_CUDA_ERROR_UNSUPPORTED;
-            }
-            if (p.blend_mode != PF_BLEND_MODE_SRC_OVER) {
-                pf::set_last_error("only BlendMode::SrcOver is on the hot path");
-                return PF_CUDA_ERROR_UNSUPPORTED;
-            }
-        }
+        std::atomic<int> unsupported{0}; // 1: a path has a clip path, 2: a blend mode other than SrcOver
         // Pass 1 (parallel): prepare_draw_path_for_gpu_binning (builder.rs:1058-1095) — the tile rect
         // of every path; an empty rect marks a path outside the view box (skipped by the builder).
+        // Each chunk also sums what its kept paths add to the batch's running offsets, so that pass 2
+        // (same chunks) can assign the offsets of TileBatchDataD3D11::push (builder.rs:660-721) in
+        // parallel: a two-level scan, integer adds only.
+        struct ChunkSums {
+            uint32_t kept = 0, tiles = 0, columns = 0, segments = 0;
+            uint32_t pad[12]; // one cache line per chunk
+        };
         s->path_tile_rects.resize(n_paths);
-        parallel_ranges(n_paths, 8192, [&](size_t begin, size_t end) {
+        const size_t chunks = pf::chunk_count(n_paths, 4096);
+        std::vector<ChunkSums> sums(chunks + 1);
+        pf::parallel_chunks(n_paths, chunks, [&](size_t chunk, size_t begin, size_t end) {
+            ChunkSums sum;
             for (size_t i = begin; i < end; i++) {
                 const Path &p = s->draw_paths[i];
+                if (p.clip_path != PF_CLIP_PATH_NONE) unsupported.store(1, std::memory_order_relaxed);
+                if (p.blend_mode != PF_BLEND_MODE_SRC_OVER) unsupported.store(2, std::memory_order_relaxed);
                 PFRectI tile_rect{{0, 0}, {0, 0}};
                 RectF path_bounds = xf.is_identity() ? p.bounds : xf.apply_rect(p.bounds);
                 RectF clipped;
@@ -502,66 +543,82 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                     tile_rect.origin.y = (int32_t)floorf(clipped.min_y * k);
                     tile_rect.lower_right.x = (int32_t)ceilf(clipped.max_x * k);
                     tile_rect.lower_right.y = (int32_t)ceilf(clipped.max_y * k);
+                    const uint32_t w = (uint32_t)(tile_rect.lower_right.x - tile_rect.origin.x),
+                                   h = (uint32_t)(tile_rect.lower_right.y - tile_rect.origin.y);
+                    sum.kept++;
+                    sum.tiles += w * h;
+                    sum.columns += w;
+                    sum.segments += s->draw_segment_ranges[2 * i + 1] - s->draw_segment_ranges[2 * i];
                 } else {
                     tile_rect.origin.x = 1, tile_rect.lower_right.x = 0; // "skipped" marker (a kept rect has max >= min)
                 }
                 s->path_tile_rects[i] = tile_rect;
             }
+            sums[chunk + 1] = sum;
         });
-        // Pass 2 (sequential, integer adds only): batch index and running offsets
-        // (TileBatchDataD3D11::push, builder.rs:660-721).
-        s->path_batch_offsets.resize(4 * (n_paths + 1));
-        uint32_t *batch_index = s->path_batch_offsets.data(), *tile_off = batch_index + (n_paths + 1),
-                 *col_off = tile_off + (n_paths + 1), *seg_off = col_off + (n_paths + 1);
-        uint32_t kept = 0;
-        for (size_t i = 0; i < n_paths; i++) {
-            const PFRectI &tr = s->path_tile_rects[i];
-            batch_index[i] = kept, tile_off[i] = tile_count, col_off[i] = column_count, seg_off[i] = segment_count;
-            if (tr.origin.x > tr.lower_right.x) continue; // skipped
-            const uint32_t w = (uint32_t)(tr.lower_right.x - tr.origin.x), h = (uint32_t)(tr.lower_right.y - tr.origin.y);
-            kept++;
-            tile_count += w * h;
-            column_count += w;
-            segment_count += s->draw_segment_ranges[2 * i + 1] - s->draw_segment_ranges[2 * i];
+        laps.lap("scene pass 1");
+        if (unsupported.load() != 0) {
+            pf::set_last_error(unsupported.load() == 1 ? "clip paths are a 'next' row (SURVEY.md §8 f1)"
+                                                       : "only BlendMode::SrcOver is on the hot path");
+            return PF_CUDA_ERROR_UNSUPPORTED;
         }
+        for (size_t c = 1; c <= chunks; c++) { // exclusive prefix: sums[c] = totals of chunks before c
+            sums[c].kept += sums[c - 1].kept;
+            sums[c].tiles += sums[c - 1].tiles;
+            sums[c].columns += sums[c - 1].columns;
+            sums[c].segments += sums[c - 1].segments;
+        }
+        const uint32_t kept = sums[chunks].kept;
+        tile_count = sums[chunks].tiles;
+        column_count = sums[chunks].columns;
+        segment_count = sums[chunks].segments;
         s->propagate_metadata.resize(kept);
         s->dice_metadata.resize(kept);
         s->tile_path_info.resize(kept);
-        // Pass 3 (parallel): the records.
-        parallel_ranges(n_paths, 8192, [&](size_t begin, size_t end) {
+        // Pass 2 (parallel, same chunks): the records.
+        pf::parallel_chunks(n_paths, chunks, [&](size_t chunk, size_t begin, size_t end) {
+            uint32_t bi = sums[chunk].kept, tile_off = sums[chunk].tiles, col_off = sums[chunk].columns,
+                     seg_off = sums[chunk].segments;
             for (size_t i = begin; i < end; i++) {
                 const PFRectI &tile_rect = s->path_tile_rects[i];
                 if (tile_rect.origin.x > tile_rect.lower_right.x) continue;
                 const Path &p = s->draw_paths[i];
-                const uint32_t bi = batch_index[i];
                 // BuiltDrawPath::new (builder.rs:80-94): occludes = opaque paint && SrcOver.
                 const bool occludes = s->paints[p.paint].a == 255;
                 const uint8_t ctrl = p.fill_rule == PF_FILL_RULE_EVEN_ODD ? PF_TILE_CTRL_MASK_EVEN_ODD : PF_TILE_CTRL_MASK_WINDING;
                 PFPropagateMetadataD3D11 pm;
                 memset(&pm, 0, sizeof(pm));
                 pm.tile_rect = tile_rect;
-                pm.tile_offset = tile_off[i];
+                pm.tile_offset = tile_off;
                 pm.path_index = bi;
                 pm.z_write = occludes ? 1 : 0;
                 pm.clip_path_index = PF_PATH_INDEX_NONE;
-                pm.backdrop_offset = col_off[i];
+                pm.backdrop_offset = col_off;
                 s->propagate_metadata[bi] = pm;
-                s->dice_metadata[bi] = PFDiceMetadataD3D11{(uint32_t)i, s->draw_segment_ranges[2 * i], seg_off[i], 0};
+                s->dice_metadata[bi] = PFDiceMetadataD3D11{(uint32_t)i, s->draw_segment_ranges[2 * i], seg_off, 0};
                 PFTilePathInfoD3D11 tp;
                 tp.tile_min_x = (int16_t)tile_rect.origin.x;
                 tp.tile_min_y = (int16_t)tile_rect.origin.y;
                 tp.tile_max_x = (int16_t)tile_rect.lower_right.x;
                 tp.tile_max_y = (int16_t)tile_rect.lower_right.y;
-                tp.first_tile_index = tile_off[i];
+                tp.first_tile_index = tile_off;
                 tp.color = p.paint;
                 tp.ctrl = ctrl;
                 tp.backdrop = 0;
                 s->tile_path_info[bi] = tp;
+                const uint32_t w = (uint32_t)(tile_rect.lower_right.x - tile_rect.origin.x),
+                               h = (uint32_t)(tile_rect.lower_right.y - tile_rect.origin.y);
+                bi++;
+                tile_off += w * h;
+                col_off += w;
+                seg_off += s->draw_segment_ranges[2 * i + 1] - s->draw_segment_ranges[2 * i];
             }
         });
     }
+    laps.lap("scene pass 2");
     if (getenv("PF_HOST_TIMING"))
-        fprintf(stderr, "PFSceneBuild: %.3f ms before the path loop, %.3f ms in it\n",
+        fprintf(stderr, "PFSceneBuild (segment arrays %s): %.3f ms before the path loop, %.3f ms in it\n",
+                s->seg_points.pinned ? "pinned" : "pageable",
                 std::chrono::duration<double, std::milli>(t_loop0 - start_time).count(),
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop0).count());
     s->built_key = batch_key;

@@ -22,4 +22,8 @@ for name, (flat, xf), size in [("tiger4k", scenes.tiger(4096), 4096), ("random10
     def readback(): r.read_pixels_into(host.data_ptr(), size * 4)
     print(name, "clean frame ms (min, mean):", timeit(clean), "dirty frame:", timeit(dirty), "readback:", timeit(readback),
           "GB/s:", size * size * 4 / timeit(readback)[0] / 1e6)
+    r.set_deferred_verification(True)
+    def dirty_host():  # host time of a dirty frame when nothing waits for the GPU
+        scene.set_view_box(flat.view_box); scene.build_and_render(r, opts)
+    print("   deferred verification, dirty frame: host-only ms (min, mean):", timeit(dirty_host, 8))
     print("   stats", {k: v for k, v in r.stats().items() if k in ("host_sync_count", "h2d_bytes", "batch_cache_hits", "cpu_build_time_ns")})
