@@ -765,8 +765,8 @@ int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_
 __global__ void __launch_bounds__(256)
     k_list_emit(BatchDev b, const uint32_t *__restrict__ tile_fb, const uint32_t *__restrict__ tile_word,
                 const uint32_t *__restrict__ tile_fill_pos, const uint32_t *__restrict__ fb_start,
-                uint32_t *__restrict__ fb_cursor, TileEntry *__restrict__ entries, uint32_t capacity,
-                OverflowGuard guard) {
+                uint32_t *__restrict__ fb_cursor, const float4 *__restrict__ paints,
+                TileEntry *__restrict__ entries, uint32_t capacity, OverflowGuard guard) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     // All totals are final by now. A batch that overflowed a stage buffer must leave the destination
     // untouched (the exact-sized re-run may have to load it): park the fused kernel's work counter
@@ -786,16 +786,21 @@ __global__ void __launch_bounds__(256)
         e.paint_ctrl = __ldg(&b.paths[p].paint_ctrl) & 0x00ffffffu;
         e.tile_index = t;
         uint32_t slot = __ldg(fb_start + fbi) + atomicAdd(fb_cursor + fbi, 1u);
-        if (slot < capacity) *reinterpret_cast<uint4 *>(entries + slot) = *reinterpret_cast<uint4 *>(&e);
+        const float4 color = __ldg(paints + (e.paint_ctrl & 0xffffu));
+        if (slot < capacity) {
+            *reinterpret_cast<uint4 *>(entries + slot) = *reinterpret_cast<uint4 *>(&e);
+            entries[slot].color = color;
+        }
     }
 }
 
 int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t *tile_word,
                      const uint32_t *tile_fill_pos, const uint32_t *fb_start, uint32_t *fb_cursor,
-                     TileEntry *entries, uint32_t capacity, const OverflowGuard &guard, cudaStream_t stream) {
+                     const float4 *paints, TileEntry *entries, uint32_t capacity, const OverflowGuard &guard,
+                     cudaStream_t stream) {
     if (b.n_tiles == 0) return 0;
     k_list_emit<<<div_up(b.n_tiles, 256), 256, 0, stream>>>(b, tile_fb, tile_word, tile_fill_pos, fb_start, fb_cursor,
-                                                             entries, capacity, guard);
+                                                             paints, entries, capacity, guard);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -874,13 +879,37 @@ __device__ __forceinline__ uint32_t pack_rgba8(float4 c) {
     return __byte_perm(rg, ba, 0x5410);
 }
 
-// dest = dest * (1 - a) + src with premultiplied src (shaders/d3d11/tile.cs.glsl:155).
+// Packed f32x2 arithmetic (sm_100: FFMA2 / FMUL2 issue two fp32 operations per lane per instruction;
+// the compositing loop is issue-bound, not FP32-pipe-bound). Same roundings as the scalar forms.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// dest = dest * (1 - a) + src with premultiplied src (shaders/d3d11/tile.cs.glsl:155):
+// d = fma(d, 1 - a, (base.rgb * a, a)), two channels per instruction.
 __device__ __forceinline__ void blend(float4 &d, float4 base, float alpha) {
-    float ia = 1.0f - alpha;
-    d.x = fmaf(d.x, ia, base.x * alpha);
-    d.y = fmaf(d.y, ia, base.y * alpha);
-    d.z = fmaf(d.z, ia, base.z * alpha);
-    d.w = fmaf(d.w, ia, alpha);
+    const float ia = 1.0f - alpha;
+    const unsigned long long ii = pack2(ia, ia);
+    const unsigned long long src_xy = mul2(pack2(base.x, base.y), pack2(alpha, alpha));
+    const unsigned long long xy = fma2(pack2(d.x, d.y), ii, src_xy);
+    const unsigned long long zw = fma2(pack2(d.z, d.w), ii, pack2(base.z * alpha, alpha));
+    unpack2(xy, d.x, d.y);
+    unpack2(zw, d.z, d.w);
 }
 
 // One warp per framebuffer tile: lane (x, half) owns column x, rows 8*half .. 8*half+7 (two of the
@@ -891,10 +920,9 @@ __device__ __forceinline__ void blend(float4 &d, float4 base, float alpha) {
 // prefix); per-pixel state is only expanded at the first tile that has fills.
 constexpr int COMPOSITE_WARPS = 2;       // tiles per block, horizontally adjacent
 constexpr int COMPOSITE_SORT_CAP = 128;  // entries sorted in shared memory; longer lists use the slow path
-constexpr int COMPOSITE_BATCH = 1;       // consecutive tiles a warp reserves per atomic
 
 template <bool LOAD_DEST>
-__global__ void __launch_bounds__(32 * COMPOSITE_WARPS) k_composite(CompositeArgs a) {
+__global__ void __launch_bounds__(32 * COMPOSITE_WARPS, 10) k_composite(CompositeArgs a) {
     __shared__ uint4 s_entries[COMPOSITE_WARPS][COMPOSITE_SORT_CAP];
     __shared__ float4 s_paints[COMPOSITE_WARPS][COMPOSITE_SORT_CAP];
     __shared__ uint32_t s_keys[COMPOSITE_WARPS][COMPOSITE_SORT_CAP];
@@ -904,16 +932,43 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS) k_composite(CompositeArg
     const uint32_t n_work = (uint32_t)fb_w * (uint32_t)(a.tile_y1 - a.tile_y0);
     // Persistent warps: tiles differ wildly in depth, so every warp pulls its next tile from a
     // global counter instead of owning a fixed one (row-major, so neighbours stay neighbours).
-    uint32_t work = 0, work_end = 0; // [work, work_end): tiles this warp has reserved
-    for (;; work++) {
-    if (work >= work_end) {
-        if (lane == 0) work = atomicAdd(a.work_counter, (uint32_t)COMPOSITE_BATCH);
-        work = __shfl_sync(0xffffffffu, work, 0);
-        work_end = min(work + (uint32_t)COMPOSITE_BATCH, n_work);
-        if (work >= n_work) return;
-    }
-    const int tile_col = (int)(work % (uint32_t)fb_w);
-    const int ty = a.tile_y0 + (int)(work / (uint32_t)fb_w); // absolute tile y
+    // The pull is software-pipelined two deep: while tile i is composited, the counter increment for
+    // tile i + 2 and the list header (start, count) of tile i + 1 are in flight, so neither the atomic's
+    // nor the header's latency sits on a tile's critical path. (Claiming several consecutive tiles per
+    // atomic was measured: no gain on the 100k-path scene, and the tiger's clustered deep tiles
+    // unbalance the tail.)
+    const int64_t fb_base = (int64_t)(a.tile_y0 - a.fb.min_y) * fb_w; // list index of work item 0
+    const int64_t n_fb = (int64_t)fb_w * (a.fb.max_y - a.fb.min_y);
+    auto claim = [&]() -> uint32_t {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(a.work_counter, 1u);
+        return c; // lane 0 only; broadcast when it is needed, not before
+    };
+    auto load_header = [&](uint32_t w, uint32_t &count, uint32_t &start) {
+        count = start = 0;
+        const int64_t index = (int64_t)w + fb_base;
+        if (w < n_work && index >= 0 && index < n_fb) {
+            count = __ldg(a.fb_count + index);
+            start = __ldg(a.fb_start + index);
+        }
+    };
+    uint32_t pending = claim();
+    uint32_t work = __shfl_sync(0xffffffffu, pending, 0);
+    pending = claim();
+    uint32_t n, e0;
+    load_header(work, n, e0);
+    for (;;) {
+    if (work >= n_work) return;
+    const uint32_t work_next = __shfl_sync(0xffffffffu, pending, 0);
+    pending = claim();
+    uint32_t n_next, e0_next;
+    load_header(work_next, n_next, e0_next);
+
+    // work / fb_w by multiplication: fb_w_recip = floor(2^32 / fb_w) under-estimates the quotient by at most one.
+    uint32_t tile_row = __umulhi(work, a.fb_w_recip), tile_col_u = work - tile_row * (uint32_t)fb_w;
+    if (tile_col_u >= (uint32_t)fb_w) tile_row++, tile_col_u -= (uint32_t)fb_w;
+    const int tile_col = (int)tile_col_u;
+    const int ty = a.tile_y0 + (int)tile_row; // absolute tile y
     const int tx = a.fb.min_x + tile_col;
     const int x = lane & 15, half = lane >> 4;
     const int px = tx * 16 + x, py0 = ty * 16 + half * 8;
@@ -925,22 +980,29 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS) k_composite(CompositeArg
     }
     uint8_t *out = a.dest + (ptrdiff_t)py0 * (ptrdiff_t)a.dest_pitch + (ptrdiff_t)px * 4;
 
-    const int fy = ty - a.fb.min_y;
-    uint32_t e0 = 0, n = 0;
-    if (fy >= 0 && fy < a.fb.max_y - a.fb.min_y) {
-        const uint32_t fbi = (uint32_t)(fy * fb_w + tile_col);
-        n = __ldg(a.fb_count + fbi);
-        e0 = __ldg(a.fb_start + fbi);
-    }
-
     // ---- bring the run into draw order: rank sort by tile index in shared memory ----
     const bool in_smem = n <= COMPOSITE_SORT_CAP;
     if (in_smem && n > 0) {
         if (n == 1) {
             if (lane == 0) {
-                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0));
-                s_entries[warp][0] = raw;
-                s_paints[warp][0] = __ldg(a.paints + (raw.z & 0xffffu));
+                s_entries[warp][0] = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0));
+                s_paints[warp][0] = __ldg(&a.entries[e0].color);
+            }
+        } else if (n <= 32) {
+            // One entry per lane: loaded once, ranked against the keys in shared memory.
+            uint4 raw = make_uint4(0, 0, 0, 0);
+            float4 color = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if ((uint32_t)lane < n) {
+                raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + lane));
+                color = __ldg(&a.entries[e0 + lane].color);
+                s_keys[warp][lane] = raw.w;
+            }
+            __syncwarp();
+            if ((uint32_t)lane < n) {
+                uint32_t rank = 0;
+                for (uint32_t j = 0; j < n; j++) rank += s_keys[warp][j] < raw.w ? 1u : 0u;
+                s_entries[warp][rank] = raw;
+                s_paints[warp][rank] = color;
             }
         } else {
             for (uint32_t i = lane; i < n; i += 32) s_keys[warp][i] = __ldg(&a.entries[e0 + i].tile_index);
@@ -949,9 +1011,8 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS) k_composite(CompositeArg
                 const uint32_t key = s_keys[warp][i];
                 uint32_t rank = 0;
                 for (uint32_t j = 0; j < n; j++) rank += s_keys[warp][j] < key ? 1u : 0u;
-                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + i));
-                s_entries[warp][rank] = raw;
-                s_paints[warp][rank] = __ldg(a.paints + (raw.z & 0xffffu));
+                s_entries[warp][rank] = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + i));
+                s_paints[warp][rank] = __ldg(&a.entries[e0 + i].color);
             }
         }
         __syncwarp();
@@ -994,7 +1055,7 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS) k_composite(CompositeArg
             }
             next_key = best + 1;
             raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + best_i));
-            base = __ldg(a.paints + (raw.z & 0xffffu));
+            base = __ldg(&a.entries[e0 + best_i].color);
         }
         const uint32_t fill_end = raw.x, word = raw.y;
         const uint32_t count = word & 0x00ffffffu;
@@ -1027,11 +1088,41 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS) k_composite(CompositeArg
                 contributions += accumulate_fill<2>(from_w, to_w, cx, cy, a.area_lut, acc) ? 1u : 0u;
             }
         }
+        // calculateColor (tile_fragment.inc.glsl:560-614), solid colour, SrcOver.
+        if (count <= 127u) {
+            // At most 127 contributions of magnitude <= 2^15 units: |sum| < 2^22, so the signed sum
+            // can be read off the mantissa of 1.5 * 2^23 + sum (no I2F on the quarter-rate pipe) and
+            // scaled, un-biased (12582912 * 2^-15 = 384) and offset by the backdrop in one FFMA —
+            // the same single rounding as float(sum) * 2^-15 + backdrop.
+            const uint32_t bias = 0x4b400000u - contributions * COV_MAGIC_BITS;
+            const float offset = backdrop - 384.0f;
+            if (ctrl & 1u) { // TILE_CTRL_MASK_WINDING
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            float coverage = finish_coverage(acc[k >> 2][k & 3], contributions) + backdrop;
-            // calculateColor (tile_fragment.inc.glsl:560-614), solid colour, SrcOver.
-            blend(dst[k], base, base.w * mask_alpha(coverage, ctrl));
+                for (int k = 0; k < 8; k++) {
+                    const float coverage = fmaf(__uint_as_float(acc[k >> 2][k & 3] + bias), COV_SCALE, offset);
+                    blend(dst[k], base, base.w * fminf(fabsf(coverage), 1.0f));
+                }
+            } else if (ctrl & 2u) { // TILE_CTRL_MASK_EVEN_ODD
+                // 1 - |1 - (c mod 2)| is the distance from c to the nearest even integer:
+                // 2 * |c/2 - rint(c/2)|, with rint from the 1.5 * 2^23 trick (|c/2| < 2^22 here).
+                const float twice_alpha = 2.0f * base.w;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float coverage = fmaf(__uint_as_float(acc[k >> 2][k & 3] + bias), COV_SCALE, offset);
+                    const float t = coverage * 0.5f;
+                    const float nearest = (t + 12582912.0f) - 12582912.0f;
+                    blend(dst[k], base, twice_alpha * fabsf(t - nearest));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) blend(dst[k], base, base.w);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float coverage = finish_coverage(acc[k >> 2][k & 3], contributions) + backdrop;
+                blend(dst[k], base, base.w * mask_alpha(coverage, ctrl));
+            }
         }
     }
     // ---- store: into the local image and, when the frame is strip-partitioned over several GPUs,
@@ -1071,6 +1162,7 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS) k_composite(CompositeArg
         }
     }
     __syncwarp(); // the next tile reuses this warp's shared-memory slots
+    work = work_next, n = n_next, e0 = e0_next;
     }
 }
 
@@ -1088,14 +1180,16 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
         PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], k_composite<true>, 32 * COMPOSITE_WARPS, 0));
     }
     const uint64_t n_work = (uint64_t)fb_w * (uint64_t)rows;
+    CompositeArgs args = a;
+    args.fb_w_recip = (uint32_t)std::min<uint64_t>(0xffffffffull, (1ull << 32) / (uint64_t)fb_w);
     uint64_t want = (n_work + COMPOSITE_WARPS - 1) / COMPOSITE_WARPS;
     uint64_t resident = (uint64_t)sm_count * (uint64_t)blocks_per_sm[a.load_dest ? 1 : 0];
     unsigned grid = (unsigned)(want < resident ? want : resident);
     // The caller has zeroed a.work_counter (the tile-list kernel may since have parked it past the end).
     if (a.load_dest)
-        k_composite<true><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(a);
+        k_composite<true><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(args);
     else
-        k_composite<false><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(a);
+        k_composite<false><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(args);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

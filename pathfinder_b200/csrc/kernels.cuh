@@ -36,12 +36,14 @@ struct FbRect {
     int32_t min_x, min_y, max_x, max_y; // framebuffer tile rect = round_out(view_box / 16)
 };
 
-// One entry of a framebuffer tile's painter's-order list (16 bytes, one 128-bit load).
-struct __align__(16) TileEntry {
+// One entry of a framebuffer tile's painter's-order list (32 bytes, two 128-bit loads). The paint's
+// colour is stored inline so that the fused kernel has no dependent entry -> paint-table load.
+struct __align__(32) TileEntry {
     uint32_t fill_end;    // end of the tile's run in the tile-grouped fill array
     uint32_t word;        // fill count (low 24 bits) | backdrop i8 << 24
     uint32_t paint_ctrl;  // color u16 | ctrl u8 << 16
     uint32_t tile_index;  // dense tile index: ascending = draw order (sort key inside a list)
+    float4 color;         // base colour of the paint, already rounded through f16
 };
 
 // Tile-grouped fill: the 4.8 fixed point segment (LineSegmentU16) as one 64-bit word.
@@ -131,13 +133,13 @@ struct OverflowGuard {
 // Appends one TileEntry per surviving tile to its framebuffer tile's run [fb_start, fb_start + count).
 int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t *tile_word,
                      const uint32_t *tile_fill_pos, const uint32_t *fb_start, uint32_t *fb_cursor,
-                     TileEntry *entries, uint32_t capacity, const OverflowGuard &guard, cudaStream_t stream);
+                     const float4 *paints, TileEntry *entries, uint32_t capacity, const OverflowGuard &guard,
+                     cudaStream_t stream);
 
 struct CompositeArgs {
     const TileEntry *entries;   // runs in arbitrary order; the kernel sorts each by tile_index
     const uint32_t *fb_start, *fb_count;
     const PackedFill *fills;
-    const float4 *paints;      // base colour per paint id, already rounded through f16
     cudaTextureObject_t area_lut;
     FbRect fb;
     int32_t tile_y0, tile_y1;  // tile rows composited by this renderer (strip)
@@ -150,6 +152,7 @@ struct CompositeArgs {
     float4 clear_color;
     int load_dest;             // LOAD_ACTION_LOAD for batches after the first
     uint32_t *work_counter;    // device word used by the persistent warps to pull tiles
+    uint32_t fb_w_recip;       // floor(2^32 / framebuffer width in tiles); set by launch_composite
 };
 int launch_composite(const CompositeArgs &args, cudaStream_t stream);
 

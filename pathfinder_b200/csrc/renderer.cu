@@ -690,7 +690,7 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     }
     const OverflowGuard guard{r->counters.ptr, line_bound, entry_bound, fill_bound, r->counters.ptr + 12};
     launches += launch_list_emit(b, r->tile_fb.ptr, r->tile_word.ptr, r->tile_fill_pos.ptr, r->fb_start.ptr,
-                                 r->fb_cursor.ptr, r->entries.ptr, entry_bound, guard, st);
+                                 r->fb_cursor.ptr, r->paints.ptr, r->entries.ptr, entry_bound, guard, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[6], st));
 
     // ---- fill + tile (fused).
@@ -699,7 +699,6 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     ca.fb_start = r->fb_start.ptr;
     ca.fb_count = r->fb_count.ptr;
     ca.fills = r->fills.ptr;
-    ca.paints = r->paints.ptr;
     ca.area_lut = r->lut_tex;
     ca.fb = fb;
     ca.tile_y0 = c.strip_y0;
