@@ -581,8 +581,7 @@ int launch_bin(int mode, const BatchDev &b, const BinArgs &args, cudaStream_t st
     if (args.n_lines == 0) return 0;
     unsigned grid = div_up(args.n_lines, BIN_THREADS);
     int launches = 1;
-    if (mode != BIN_EMIT && args.long_queue) // reset the long-line queue of this pass
-        PF_CUDA_CHECK(cudaMemsetAsync(args.long_count, 0, 2 * sizeof(uint32_t), stream));
+    // (the caller hands every pass its own zeroed long_count / long_cursor words)
     if (mode == BIN_EMIT_LIVE)
         k_bin<BIN_EMIT_LIVE><<<grid, BIN_THREADS, 0, stream>>>(b, args);
     else if (mode == BIN_COUNT)

@@ -46,6 +46,12 @@ struct PinnedBuffer {
     }
 };
 
+// A typed window into PFCudaRenderer::zeroed.
+template <typename T>
+struct ZeroedView {
+    T *ptr = nullptr;
+};
+
 struct SceneSegments {
     DeviceBuffer<float2> points;
     DeviceBuffer<uint2> indices;
@@ -138,16 +144,22 @@ struct PFCudaRenderer {
     DeviceBuffer<float4> lines;
     DeviceBuffer<uint32_t> line_path;
     DeviceBuffer<uint32_t> line_fill_offset; // [L]
-    DeviceBuffer<uint32_t> tile_word, tile_fill_pos, tile_first_fill, tile_fb, tile_pos, tile_alpha_id;
-    DeviceBuffer<int32_t> col_backdrop, col_backdrop_init;
+    // Everything a frame needs zeroed lives in one allocation and is cleared by one memset (carve_zeroed).
+    DeviceBuffer<uint32_t> zeroed;
+    ZeroedView<uint32_t> counters;  // device-side totals: [0]=lines [1]=fills [2]=entries [3]=alpha tiles [4]=dump tiles
+                                    // [5]=visible fills [6,7]/[13,14]=long-line queues [8,9]=u64 scratch [12]=tile counter
+    ZeroedView<uint32_t> path_live; // per path: some tile with fills survived the z-cull
+    ZeroedView<uint32_t> tile_word;
+    ZeroedView<int32_t> col_backdrop;
+    ZeroedView<int32_t> z_buffer;
+    ZeroedView<uint32_t> fb_count, fb_cursor;
+    DeviceBuffer<uint32_t> tile_fill_pos, tile_first_fill, tile_fb, tile_pos, tile_alpha_id;
+    DeviceBuffer<int32_t> col_backdrop_init;
     DeviceBuffer<uint32_t> long_queue; // lines walked by whole warps (k_bin_long)
-    DeviceBuffer<uint32_t> path_live;  // per path: some tile with fills survived the z-cull
     DeviceBuffer<PackedFill> fills;
     DeviceBuffer<EmitFill> fills_emit;
-    DeviceBuffer<int32_t> z_buffer;
-    DeviceBuffer<uint32_t> fb_start, fb_count, fb_cursor;
+    DeviceBuffer<uint32_t> fb_start;
     DeviceBuffer<TileEntry> entries;
-    DeviceBuffer<uint32_t> counters; // device-side totals: [0]=lines [1]=fills [2]=entries [3]=alpha tiles [4]=dump tiles
     PinnedBuffer<uint32_t> counters_host;
     ScanScratch scan_scratch;
     // debug / dump scratch
@@ -209,24 +221,18 @@ void setup_tracking(PFCudaRenderer *r) {
     track(r, r->lines);
     track(r, r->line_path);
     track(r, r->line_fill_offset);
-    track(r, r->tile_word);
+    track(r, r->zeroed);
     track(r, r->tile_fill_pos);
     track(r, r->tile_first_fill);
     track(r, r->tile_fb);
     track(r, r->tile_pos);
     track(r, r->tile_alpha_id);
-    track(r, r->col_backdrop);
     track(r, r->col_backdrop_init);
     track(r, r->long_queue);
-    track(r, r->path_live);
     track(r, r->fills);
     track(r, r->fills_emit);
-    track(r, r->z_buffer);
     track(r, r->fb_start);
-    track(r, r->fb_count);
-    track(r, r->fb_cursor);
     track(r, r->entries);
-    track(r, r->counters);
     track(r, r->scan_scratch.control);
     track(r, r->scan_scratch.status);
     track(r, r->fill_is_first);
@@ -548,6 +554,23 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
 // Returns false when a bound was exceeded (the caller re-runs in sizing mode).
 bool finalize_batch(PFCudaRenderer *r);
 
+// Lays the frame's zero-initialised arrays out in r->zeroed and clears all of them with one memset
+// (eight separate clears cost more in launch gaps than in bandwidth on the small scenes).
+void carve_zeroed(PFCudaRenderer *r, size_t n_paths, size_t n_tiles, size_t n_cols, size_t n_fb) {
+    auto padded = [](size_t n) { return (n + 4) & ~(size_t)3; }; // >= n + 1, keeps every array 16-byte aligned
+    const size_t total = 16 + padded(n_paths) + padded(n_tiles) + padded(n_cols) + 3 * padded(n_fb);
+    r->zeroed.ensure(total, 1.25);
+    uint32_t *p = r->zeroed.ptr;
+    r->counters.ptr = p, p += 16;
+    r->path_live.ptr = p, p += padded(n_paths);
+    r->tile_word.ptr = p, p += padded(n_tiles);
+    r->col_backdrop.ptr = reinterpret_cast<int32_t *>(p), p += padded(n_cols);
+    r->z_buffer.ptr = reinterpret_cast<int32_t *>(p), p += padded(n_fb);
+    r->fb_count.ptr = p, p += padded(n_fb);
+    r->fb_cursor.ptr = p;
+    PF_CUDA_CHECK(cudaMemsetAsync(r->zeroed.ptr, 0, total * sizeof(uint32_t), r->stream));
+}
+
 bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     cudaStream_t st = r->stream;
     BatchCache &c = r->cache;
@@ -561,39 +584,23 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
         r->timer.create();
         PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[0], st));
     }
-    r->counters.ensure(16);
-    PF_CUDA_CHECK(cudaMemsetAsync(r->counters.ptr, 0, 16 * sizeof(uint32_t), st));
-
     // ---- bound (device part): clear the dense tile arrays. bound.cs.glsl:80-83 initialises
-    // {next=-1, first_fill=-1, backdrop=0}; here a tile is one word (count | backdrop delta).
-    r->tile_word.ensure(n_tiles + 1, 1.25);
+    // {next=-1, first_fill=-1, backdrop=0}; here a tile is one word (count | backdrop delta). The
+    // counters, per-path flags, tile words, column backdrops, z-buffer and list counts share one
+    // allocation and one memset.
+    const int fb_w = fb.max_x - fb.min_x, fb_h = fb.max_y - fb.min_y;
+    const uint32_t n_fb = (uint32_t)(fb_w * fb_h);
+    carve_zeroed(r, b.n_paths, n_tiles, n_cols, n_fb);
     r->tile_fill_pos.ensure(n_tiles + 1, 1.25);
-    r->col_backdrop.ensure(n_cols + 1, 1.25);
     r->tile_fb.ensure(n_tiles + 1, 1.25);
-    r->path_live.ensure(b.n_paths + 1, 1.25);
-    PF_CUDA_CHECK(cudaMemsetAsync(r->path_live.ptr, 0, (size_t)b.n_paths * 4, st));
-    PF_CUDA_CHECK(cudaMemsetAsync(r->tile_word.ptr, 0, (size_t)n_tiles * 4, st));
-    auto reset_col_backdrops = [&]() {
-        if (c.has_initial_backdrops)
-            PF_CUDA_CHECK(cudaMemcpyAsync(r->col_backdrop.ptr, r->col_backdrop_init.ptr, (size_t)n_cols * 4,
-                                          cudaMemcpyDeviceToDevice, st));
-        else
-            PF_CUDA_CHECK(cudaMemsetAsync(r->col_backdrop.ptr, 0, (size_t)n_cols * 4, st));
-    };
-    reset_col_backdrops();
+    r->fb_start.ensure(n_fb + 1);
+    if (c.has_initial_backdrops)
+        PF_CUDA_CHECK(cudaMemcpyAsync(r->col_backdrop.ptr, r->col_backdrop_init.ptr, (size_t)n_cols * 4,
+                                      cudaMemcpyDeviceToDevice, st));
     if (r->debug_lists) {
         r->tile_first_fill.ensure(n_tiles + 1, 1.25);
         PF_CUDA_CHECK(cudaMemsetAsync(r->tile_first_fill.ptr, 0xff, (size_t)n_tiles * 4, st));
     }
-    const int fb_w = fb.max_x - fb.min_x, fb_h = fb.max_y - fb.min_y;
-    const uint32_t n_fb = (uint32_t)(fb_w * fb_h);
-    r->z_buffer.ensure(n_fb + 1);
-    r->fb_start.ensure(n_fb + 1);
-    r->fb_count.ensure(n_fb + 1);
-    r->fb_cursor.ensure(n_fb + 1);
-    PF_CUDA_CHECK(cudaMemsetAsync(r->z_buffer.ptr, 0, (size_t)n_fb * 4, st));
-    PF_CUDA_CHECK(cudaMemsetAsync(r->fb_count.ptr, 0, (size_t)n_fb * 4, st));
-    PF_CUDA_CHECK(cudaMemsetAsync(r->fb_cursor.ptr, 0, (size_t)n_fb * 4, st));
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[1], st));
 
     auto bound_of = [](uint32_t last, size_t capacity) -> uint32_t {
@@ -636,6 +643,8 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     ba.long_count = r->counters.ptr + 6;
     ba.long_cursor = r->counters.ptr + 7;
     launches += launch_bin(1 /* BIN_COUNT */, b, ba, st);
+    ba.long_count = r->counters.ptr + 13; // the emit pass queues its long lines afresh
+    ba.long_cursor = r->counters.ptr + 14;
     uint32_t emit_bound = 0;
     if (r->debug_lists) // emission-order offsets and the total fill count, for the parity dumps
         launches += exclusive_scan(LoadU32{r->line_fill_offset.ptr}, r->line_fill_offset.ptr, line_bound,
@@ -1073,9 +1082,7 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
             const FbRect fb = framebuffer_tile_rect(r);
             const uint32_t n_fb = (uint32_t)((fb.max_x - fb.min_x) * (fb.max_y - fb.min_y));
             r->fb_start.ensure(n_fb + 1);
-            r->fb_count.ensure(n_fb + 1);
-            PF_CUDA_CHECK(cudaMemsetAsync(r->fb_start.ptr, 0, (size_t)n_fb * 4, r->stream));
-            PF_CUDA_CHECK(cudaMemsetAsync(r->fb_count.ptr, 0, (size_t)n_fb * 4, r->stream));
+            carve_zeroed(r, 0, 0, 0, n_fb); // every list empty, tile counter zero
             CompositeArgs ca{};
             ca.fb_start = r->fb_start.ptr;
             ca.fb_count = r->fb_count.ptr;
@@ -1088,9 +1095,7 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
             ca.dest_w = r->options.dest_size.x;
             ca.dest_h = r->options.dest_size.y;
             ca.clear_color = clear_color(r);
-            r->counters.ensure(16);
             ca.work_counter = r->counters.ptr + 12;
-            PF_CUDA_CHECK(cudaMemsetAsync(ca.work_counter, 0, sizeof(uint32_t), r->stream));
             r->stats.drawcall_count += (uint64_t)launch_composite(ca, r->stream);
         }
         if (r->borrowed_copies_pending && !r->pending.active) {
