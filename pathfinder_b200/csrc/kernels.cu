@@ -201,6 +201,140 @@ __global__ void __launch_bounds__(DICE_THREADS)
     if (!EMIT) seg_line_count[s] = n;
 }
 
+// Single-pass dice for the steady state: lines are appended in arbitrary order, so no count pass and
+// no scan are needed. Nothing downstream depends on the order of the lines — tile counts, backdrops
+// and z values are accumulated with commutative atomics and coverage is summed as integers — only
+// the parity dumps do, and they keep the ordered two-pass path above. The 32 lanes of a warp step
+// their segments' subdivision trees in lock-step; leaves produced in a step are compacted into a
+// per-warp staging buffer in shared memory and written out 32 at a time (one counter increment and
+// one coalesced 512-byte store per 32 lines).
+__global__ void __launch_bounds__(DICE_THREADS)
+    k_dice_stream(BatchDev b, float4 *__restrict__ lines, uint32_t *__restrict__ line_path, uint32_t line_capacity,
+                  uint32_t *__restrict__ line_count) {
+    __shared__ float s_stack[DICE_SMEM_LEVELS][6][DICE_THREADS];
+    __shared__ unsigned char s_depth[DICE_SMEM_LEVELS][DICE_THREADS];
+    __shared__ float4 s_line[DICE_THREADS / 32][64];
+    __shared__ uint32_t s_path[DICE_THREADS / 32][64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = s < b.n_segments;
+    bool is_line = false;
+    uint32_t p = 0;
+    Cubic cur;
+    cur.p0 = cur.p1 = cur.p2 = cur.p3 = make_float2(0.0f, 0.0f);
+    if (active) {
+        p = search_coarse(b.path_seg_first, b.seg_index, s);
+        const PathInfo *pi = b.paths + p;
+        const uint32_t gseg = __ldg(&pi->seg_global_first) + (s - __ldg(&pi->seg_batch_first));
+        const uint2 si = __ldg(b.seg_indices + gseg);
+        const float2 *pts = b.points + si.x;
+        const bool is_cubic = (si.y & 0x40000000u) != 0, is_quad = (si.y & 0x80000000u) != 0;
+        cur.p0 = xf_apply(b.xf, __ldg(pts));
+        if (is_cubic) {
+            cur.p1 = xf_apply(b.xf, __ldg(pts + 1));
+            cur.p2 = xf_apply(b.xf, __ldg(pts + 2));
+            cur.p3 = xf_apply(b.xf, __ldg(pts + 3));
+        } else if (is_quad) {
+            // Segment::to_cubic (content/src/segment.rs:171-183)
+            float2 c = xf_apply(b.xf, __ldg(pts + 1));
+            cur.p3 = xf_apply(b.xf, __ldg(pts + 2));
+            float2 c2 = make_float2(c.x + c.x, c.y + c.y);
+            const float third = 1.0f / 3.0f;
+            cur.p1 = make_float2((cur.p0.x + c2.x) * third, (cur.p0.y + c2.y) * third);
+            cur.p2 = make_float2((c2.x + cur.p3.x) * third, (c2.y + cur.p3.y) * third);
+        } else {
+            is_line = true;
+            cur.p3 = xf_apply(b.xf, __ldg(pts + 1));
+        }
+    }
+    float deep[DICE_MAX_DEPTH - DICE_SMEM_LEVELS][7];
+    int sp = 0, depth = 0;
+    // Staging ring of 64 lines per warp: [head, head + staged) mod 64 (both warp-uniform).
+    uint32_t head = 0, staged = 0;
+    auto flush = [&](uint32_t count) { // writes the oldest `count` (<= 32) staged lines
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(line_count, count);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t slot = (head + lane) & 63u;
+        if ((uint32_t)lane < count && base + lane < line_capacity) {
+            lines[base + lane] = s_line[warp][slot];
+            line_path[base + lane] = s_path[warp][slot];
+        }
+        head = (head + count) & 63u;
+        staged -= count;
+    };
+    while (__any_sync(0xffffffffu, active)) {
+        bool leaf = false;
+        float2 leaf_from = cur.p0, leaf_to = cur.p3;
+        if (active) {
+            // process_segment (renderer/src/tiler.rs:166-184), one node of the subdivision tree per step
+            if (is_line || cubic_is_flat(cur) || depth >= DICE_MAX_DEPTH) {
+                leaf = true;
+                if (sp == 0) {
+                    active = false;
+                } else {
+                    sp--;
+                    cur.p0 = cur.p3;
+                    if (sp < DICE_SMEM_LEVELS) {
+                        cur.p1 = make_float2(s_stack[sp][0][tid], s_stack[sp][1][tid]);
+                        cur.p2 = make_float2(s_stack[sp][2][tid], s_stack[sp][3][tid]);
+                        cur.p3 = make_float2(s_stack[sp][4][tid], s_stack[sp][5][tid]);
+                        depth = s_depth[sp][tid];
+                    } else {
+                        const float *d = deep[sp - DICE_SMEM_LEVELS];
+                        cur.p1 = make_float2(d[0], d[1]);
+                        cur.p2 = make_float2(d[2], d[3]);
+                        cur.p3 = make_float2(d[4], d[5]);
+                        depth = (int)d[6];
+                    }
+                }
+            } else {
+                // CubicSegment::split(0.5) (content/src/segment.rs:307-360)
+                float2 p01 = lerp_half(cur.p0, cur.p1), p12 = lerp_half(cur.p1, cur.p2),
+                       p23 = lerp_half(cur.p2, cur.p3);
+                float2 p012 = lerp_half(p01, p12), p123 = lerp_half(p12, p23);
+                float2 p0123 = lerp_half(p012, p123);
+                depth++;
+                if (sp < DICE_SMEM_LEVELS) {
+                    s_stack[sp][0][tid] = p123.x, s_stack[sp][1][tid] = p123.y;
+                    s_stack[sp][2][tid] = p23.x, s_stack[sp][3][tid] = p23.y;
+                    s_stack[sp][4][tid] = cur.p3.x, s_stack[sp][5][tid] = cur.p3.y;
+                    s_depth[sp][tid] = (unsigned char)depth;
+                } else {
+                    float *d = deep[sp - DICE_SMEM_LEVELS];
+                    d[0] = p123.x, d[1] = p123.y, d[2] = p23.x, d[3] = p23.y, d[4] = cur.p3.x, d[5] = cur.p3.y;
+                    d[6] = (float)depth;
+                }
+                sp++;
+                cur.p1 = p01, cur.p2 = p012, cur.p3 = p0123;
+            }
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, leaf);
+        if (leaf) {
+            const uint32_t slot = (head + staged + __popc(ballot & ((1u << lane) - 1u))) & 63u;
+            s_line[warp][slot] = make_float4(leaf_from.x, leaf_from.y, leaf_to.x, leaf_to.y);
+            s_path[warp][slot] = p;
+        }
+        staged += __popc(ballot);
+        if (staged >= 32) {
+            __syncwarp();
+            flush(32);
+            __syncwarp(); // the flushed slots may be rewritten by the next step
+        }
+    }
+    __syncwarp();
+    if (staged) flush(staged);
+}
+
+int launch_dice_stream(const BatchDev &b, float4 *lines, uint32_t *line_path, uint32_t line_capacity,
+                       uint32_t *line_count, cudaStream_t stream) {
+    if (b.n_segments == 0) return 0;
+    k_dice_stream<<<div_up(b.n_segments, DICE_THREADS), DICE_THREADS, 0, stream>>>(b, lines, line_path, line_capacity,
+                                                                                  line_count);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
 int launch_dice(bool emit, const BatchDev &b, uint32_t *seg_line_count, const uint32_t *seg_line_offset,
                 float4 *lines, uint32_t *line_path, uint32_t line_capacity, cudaStream_t stream) {
     if (b.n_segments == 0) return 0;

@@ -82,6 +82,9 @@ struct BatchDev {
 // lines/line_path.
 int launch_dice(bool emit, const BatchDev &b, uint32_t *seg_line_count, const uint32_t *seg_line_offset,
                 float4 *lines, uint32_t *line_path, uint32_t line_capacity, cudaStream_t stream);
+// Steady state: one pass, lines appended in arbitrary order; *line_count (zeroed by the caller) ends as the total.
+int launch_dice_stream(const BatchDev &b, float4 *lines, uint32_t *line_path, uint32_t line_capacity,
+                       uint32_t *line_count, cudaStream_t stream);
 
 struct BinArgs {
     const float4 *lines;

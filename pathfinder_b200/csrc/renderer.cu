@@ -608,24 +608,31 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
         return (uint32_t)(want < capacity ? want : capacity);
     };
 
-    // ---- dice: count -> scan -> emit.
-    r->seg_line_offset.ensure(n_segments + 1, 1.25);
-    launches += launch_dice(false, b, r->seg_line_offset.ptr, nullptr, nullptr, nullptr, 0, st);
-    launches += exclusive_scan(LoadU32{r->seg_line_offset.ptr}, r->seg_line_offset.ptr, n_segments,
-                               r->counters.ptr + C_LINES, r->scan_scratch, st);
+    // ---- dice. Steady state: one pass that appends lines in arbitrary order (nothing but the parity
+    // dumps depends on it). Sizing / parity dumps: count -> scan -> emit in segment order.
+    const bool stream_dice = !sizing && !r->debug_lists;
     uint32_t line_bound;
-    if (sizing) {
-        line_bound = n_segments ? read_counter(r, C_LINES) : 0;
-        r->lines.ensure(line_bound + 1, 1.25);
-        r->line_path.ensure(line_bound + 1, 1.25);
-        if (r->debug_lists) r->line_fill_offset.ensure(line_bound + 1, 1.25);
-    } else {
-        size_t cap = std::min(r->lines.capacity, r->line_path.capacity);
-        if (r->debug_lists) cap = std::min(cap, r->line_fill_offset.capacity);
-        line_bound = bound_of(c.n_lines, cap);
-    }
     const uint32_t *n_lines_dev = r->counters.ptr + C_LINES;
-    launches += launch_dice(true, b, nullptr, r->seg_line_offset.ptr, r->lines.ptr, r->line_path.ptr, line_bound, st);
+    if (stream_dice) {
+        line_bound = bound_of(c.n_lines, std::min(r->lines.capacity, r->line_path.capacity));
+        launches += launch_dice_stream(b, r->lines.ptr, r->line_path.ptr, line_bound, r->counters.ptr + C_LINES, st);
+    } else {
+        r->seg_line_offset.ensure(n_segments + 1, 1.25);
+        launches += launch_dice(false, b, r->seg_line_offset.ptr, nullptr, nullptr, nullptr, 0, st);
+        launches += exclusive_scan(LoadU32{r->seg_line_offset.ptr}, r->seg_line_offset.ptr, n_segments,
+                                   r->counters.ptr + C_LINES, r->scan_scratch, st);
+        if (sizing) {
+            line_bound = n_segments ? read_counter(r, C_LINES) : 0;
+            r->lines.ensure(line_bound + 1, 1.25);
+            r->line_path.ensure(line_bound + 1, 1.25);
+            if (r->debug_lists) r->line_fill_offset.ensure(line_bound + 1, 1.25);
+        } else {
+            size_t cap = std::min(r->lines.capacity, r->line_path.capacity);
+            if (r->debug_lists) cap = std::min(cap, r->line_fill_offset.capacity);
+            line_bound = bound_of(c.n_lines, cap);
+        }
+        launches += launch_dice(true, b, nullptr, r->seg_line_offset.ptr, r->lines.ptr, r->line_path.ptr, line_bound, st);
+    }
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[2], st));
 
     // ---- bin, count pass: per-tile fill counts + backdrop deltas.

@@ -165,6 +165,22 @@ def test_cached_batch_and_strips_are_byte_identical(area_lut):
     s = r.stats()
     assert s["batch_cache_hits"] == 1 and s["host_sync_count"] == 1 and s["h2d_bytes"] == 0
     assert np.array_equal(first, second)
+    # The steady state dices in one pass and appends lines in arbitrary order; the first frame of a
+    # renderer (exact sizing) uses the ordered count -> scan -> emit path. Curves at a large scale
+    # exercise deep subdivision: both paths must give the same pixels and the same totals.
+    tflat, txf = scenes.tiger(1024)
+    tr = api.CudaRenderer((1024, 1024), background_color=(1, 1, 1, 1))
+    tscene = api.Scene.from_flat(tflat)
+    topts = api.BuildOptions(transform=api.Transform2F(*txf))
+    tscene.build_and_render(tr, topts)
+    ordered, ordered_stats = tr.read_pixels(), tr.stats()
+    for _ in range(2):
+        tscene.build_and_render(tr, topts)
+        streamed, streamed_stats = tr.read_pixels(), tr.stats()
+        assert np.array_equal(ordered, streamed)
+        for k in ("line_segment_count", "tile_list_entry_count", "visible_fill_count"):
+            assert ordered_stats[k] == streamed_stats[k], k
+    tr.close()
 
     full_tiles = None
     r.set_debug_lists_enabled(True)
