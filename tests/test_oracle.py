@@ -195,3 +195,27 @@ def test_strip_restriction_partitions_the_tile_lists(area_lut):
     assert sorted(got) == want
     assert fills == len(full.fills)
     assert np.array_equal(stitched, full_img)
+
+
+def test_golden_tools_round_trip(tmp_path):
+    """tools/make_golden_lists.py regenerates the committed golden lists exactly, and the text dump used
+    to pin the oracle against the Rust tiler (tools/dump_lists.py + tools/diff_lists.py) round-trips."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    run = lambda *a: subprocess.run([sys.executable, *a], cwd=root, capture_output=True, text=True)
+    r = run("tools/make_golden_lists.py", "--check")
+    assert r.returncode == 0, r.stdout + r.stderr
+    a, b, scene = str(tmp_path / "a.lists"), str(tmp_path / "b.lists"), str(tmp_path / "a.scene")
+    assert run("tools/dump_lists.py", "tiger", "256", "--out", a, "--scene-out", scene).returncode == 0
+    assert run("tools/dump_lists.py", "tiger", "256", "--out", b).returncode == 0
+    r = run("tools/diff_lists.py", a, b)
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout
+    # a corrupted record must be reported
+    lines = open(b).read().splitlines()
+    w = lines[0].split()
+    w[1] = str(int(w[1]) ^ 1)
+    lines[0] = " ".join(w)
+    open(b, "w").write("\n".join(lines) + "\n")
+    assert run("tools/diff_lists.py", a, b).returncode == 1
+    assert open(scene).readline().startswith("viewbox ")
