@@ -16,8 +16,10 @@ def launch_table(path):
     for r in rows:
         by.setdefault((r[0], r[4].split("(")[0].strip()), {})[r[-3]] = float(r[-1].replace(",", ""))
     ids = list(by.keys())
-    starts = [i for i, k in enumerate(ids) if "k_dice<0>" in k[1]]
-    s, e = starts[0], (starts[1] if len(starts) > 1 else len(ids))
+    # one steady-state frame: from one single-pass dice launch to the next (the first frame of a renderer
+    # sizes its buffers with the ordered two-pass dice and is skipped)
+    starts = [i for i, k in enumerate(ids) if "k_dice_stream" in k[1]] or [i for i, k in enumerate(ids) if "k_dice<0>" in k[1]]
+    s, e = (starts[-2], starts[-1]) if len(starts) > 1 else (starts[0], len(ids))
     return [(k[1], by[k]) for k in ids[s:e]]
 
 
@@ -81,18 +83,18 @@ for ln in sass.splitlines():
         if op.startswith("@"):
             op = body.split()[1] if len(body.split()) > 1 else ""
         for pat in ("LDG.E.128", "LDG.E.64", "LDG", "STG.E.128", "STG.E.64", "STG", "TEX", "ATOMG", "RED", "ATOMS", "SHFL", "VOTE", "MATCH",
-                    "LDS", "STS", "LDL", "STL", "BAR", "FFMA", "MUFU", "HMMA", "UTC", "UTMA"):
+                    "LDS", "STS", "LDL", "STL", "BAR", "FFMA2", "FMUL2", "FFMA", "MUFU", "HMMA", "UTC", "UTMA"):
             if op.startswith(pat):
                 kernels[cur][pat] = kernels[cur].get(pat, 0) + 1
                 break
 lines = [f"# {tag} — SASS mnemonic counts per kernel (`cuobjdump -sass libpf_cuda.so`, sm_100a)", "",
          "No tensor-core (`HMMA`/`UTC*MMA`) or TMA (`UTMA*`) instructions are expected: nothing on this path is a dense "
-         "contraction or a bulk tile copy (BASELINE.json north_star). `LDL`/`STL` = local memory (the dice deep-recursion fallback, a small composite spill).", "",
-         "| kernel | " + " | ".join(["LDG.E.128", "LDG.E.64", "LDG", "STG.E.128", "STG", "TEX", "ATOMG", "RED", "ATOMS", "SHFL", "VOTE", "LDS", "STS", "LDL", "STL", "BAR", "FFMA", "HMMA", "UTC", "UTMA"]) + " |",
-         "|---|" + "---:|" * 20]
+         "contraction or a bulk tile copy (BASELINE.json north_star). `FFMA2`/`FMUL2` are sm_100's packed f32x2 operations (the compositing blend). `LDL`/`STL` = local memory (the dice deep-recursion fallback).", "",
+         "| kernel | " + " | ".join(["LDG.E.128", "LDG.E.64", "LDG", "STG.E.128", "STG", "TEX", "ATOMG", "RED", "ATOMS", "SHFL", "VOTE", "LDS", "STS", "LDL", "STL", "BAR", "FFMA2", "FMUL2", "FFMA", "HMMA", "UTC", "UTMA"]) + " |",
+         "|---|" + "---:|" * 22]
 import re
 for name, c in kernels.items():
     short = re.sub(r"^_ZN2pf\d+", "", name)[:40]
-    lines.append(f"| `{short}` | " + " | ".join(str(c.get(k, 0)) for k in ["LDG.E.128", "LDG.E.64", "LDG", "STG.E.128", "STG", "TEX", "ATOMG", "RED", "ATOMS", "SHFL", "VOTE", "LDS", "STS", "LDL", "STL", "BAR", "FFMA", "HMMA", "UTC", "UTMA"]) + " |")
+    lines.append(f"| `{short}` | " + " | ".join(str(c.get(k, 0)) for k in ["LDG.E.128", "LDG.E.64", "LDG", "STG.E.128", "STG", "TEX", "ATOMG", "RED", "ATOMS", "SHFL", "VOTE", "LDS", "STS", "LDL", "STL", "BAR", "FFMA2", "FMUL2", "FFMA", "HMMA", "UTC", "UTMA"]) + " |")
 open(os.path.join(out_dir, f"{tag}_sass.md"), "w").write("\n".join(lines) + "\n")
 print("wrote", [f for f in os.listdir(out_dir) if f.startswith(tag)])
