@@ -84,16 +84,17 @@ __device__ __forceinline__ float2 xf_apply(const Transform &t, float2 p) {
     return make_float2((hx + hz) + t.tx, (hy + hw) + t.ty);
 }
 
-// CubicSegment::is_flat(0.25) (content/src/segment.rs:292-300).
-__device__ __forceinline__ bool cubic_is_flat(const Cubic &c) {
+// CubicSegment::is_flat(0.25) (content/src/segment.rs:292-300): flat iff the measure is <= 1.
+__device__ __forceinline__ float cubic_flat_measure(const Cubic &c) {
     float u0x = ((3.0f * c.p1.x - c.p0.x) - c.p0.x) - c.p3.x;
     float u0y = ((3.0f * c.p1.y - c.p0.y) - c.p0.y) - c.p3.y;
     float u1x = ((3.0f * c.p2.x - c.p3.x) - c.p3.x) - c.p0.x;
     float u1y = ((3.0f * c.p2.y - c.p3.y) - c.p3.y) - c.p0.y;
     u0x = u0x * u0x, u0y = u0y * u0y, u1x = u1x * u1x, u1y = u1y * u1y;
     float mx = sse_max(u0x, u1x), my = sse_max(u0y, u1y);
-    return mx + my <= 1.0f; // 16 * 0.25 * 0.25
+    return mx + my; // compared with 16 * 0.25 * 0.25
 }
+__device__ __forceinline__ bool cubic_is_flat(const Cubic &c) { return cubic_flat_measure(c) <= 1.0f; }
 
 __device__ __forceinline__ float2 lerp_half(float2 a, float2 b) { // a + t * (b - a), t = 0.5
     return make_float2(a.x + 0.5f * (b.x - a.x), a.y + 0.5f * (b.y - a.y));
@@ -205,50 +206,59 @@ __global__ void __launch_bounds__(DICE_THREADS)
 // no scan are needed. Nothing downstream depends on the order of the lines — tile counts, backdrops
 // and z values are accumulated with commutative atomics and coverage is summed as integers — only
 // the parity dumps do, and they keep the ordered two-pass path above. The 32 lanes of a warp step
-// their segments' subdivision trees in lock-step; leaves produced in a step are compacted into a
-// per-warp staging buffer in shared memory and written out 32 at a time (one counter increment and
-// one coalesced 512-byte store per 32 lines).
-__global__ void __launch_bounds__(DICE_THREADS)
-    k_dice_stream(BatchDev b, float4 *__restrict__ lines, uint32_t *__restrict__ line_path, uint32_t line_capacity,
-                  uint32_t *__restrict__ line_count) {
-    __shared__ float s_stack[DICE_SMEM_LEVELS][6][DICE_THREADS];
-    __shared__ unsigned char s_depth[DICE_SMEM_LEVELS][DICE_THREADS];
-    __shared__ float4 s_line[DICE_THREADS / 32][64];
-    __shared__ uint32_t s_path[DICE_THREADS / 32][64];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = s < b.n_segments;
-    bool is_line = false;
-    uint32_t p = 0;
-    Cubic cur;
-    cur.p0 = cur.p1 = cur.p2 = cur.p3 = make_float2(0.0f, 0.0f);
-    if (active) {
-        p = search_coarse(b.path_seg_first, b.seg_index, s);
-        const PathInfo *pi = b.paths + p;
-        const uint32_t gseg = __ldg(&pi->seg_global_first) + (s - __ldg(&pi->seg_batch_first));
-        const uint2 si = __ldg(b.seg_indices + gseg);
-        const float2 *pts = b.points + si.x;
-        const bool is_cubic = (si.y & 0x40000000u) != 0, is_quad = (si.y & 0x80000000u) != 0;
-        cur.p0 = xf_apply(b.xf, __ldg(pts));
-        if (is_cubic) {
-            cur.p1 = xf_apply(b.xf, __ldg(pts + 1));
-            cur.p2 = xf_apply(b.xf, __ldg(pts + 2));
-            cur.p3 = xf_apply(b.xf, __ldg(pts + 3));
-        } else if (is_quad) {
-            // Segment::to_cubic (content/src/segment.rs:171-183)
-            float2 c = xf_apply(b.xf, __ldg(pts + 1));
-            cur.p3 = xf_apply(b.xf, __ldg(pts + 2));
-            float2 c2 = make_float2(c.x + c.x, c.y + c.y);
-            const float third = 1.0f / 3.0f;
-            cur.p1 = make_float2((cur.p0.x + c2.x) * third, (cur.p0.y + c2.y) * third);
-            cur.p2 = make_float2((c2.x + cur.p3.x) * third, (c2.y + cur.p3.y) * third);
-        } else {
-            is_line = true;
-            cur.p3 = xf_apply(b.xf, __ldg(pts + 1));
-        }
+// their subdivision trees in lock-step; leaves produced in a step are compacted into a per-warp
+// staging ring in shared memory and written out 32 at a time (one counter increment and one
+// coalesced 512-byte store per 32 lines).
+struct DiceShared {
+    float stack[DICE_SMEM_LEVELS][8][DICE_THREADS]; // pending right halves, all four points (stealable)
+    unsigned char depth[DICE_SMEM_LEVELS][DICE_THREADS];
+    float4 line[DICE_THREADS / 32][64];
+    uint32_t path[DICE_THREADS / 32][64];
+};
+
+// Loads and transforms segment s of the batch as a cubic; returns true for a straight line (p0 -> p3).
+__device__ __forceinline__ bool load_segment(const BatchDev &b, uint32_t s, uint32_t &p, Cubic &cur) {
+    p = search_coarse(b.path_seg_first, b.seg_index, s);
+    const PathInfo *pi = b.paths + p;
+    const uint32_t gseg = __ldg(&pi->seg_global_first) + (s - __ldg(&pi->seg_batch_first));
+    const uint2 si = __ldg(b.seg_indices + gseg);
+    const float2 *pts = b.points + si.x;
+    const bool is_cubic = (si.y & 0x40000000u) != 0, is_quad = (si.y & 0x80000000u) != 0;
+    cur.p0 = xf_apply(b.xf, __ldg(pts));
+    if (is_cubic) {
+        cur.p1 = xf_apply(b.xf, __ldg(pts + 1));
+        cur.p2 = xf_apply(b.xf, __ldg(pts + 2));
+        cur.p3 = xf_apply(b.xf, __ldg(pts + 3));
+        return false;
     }
+    if (is_quad) {
+        // Segment::to_cubic (content/src/segment.rs:171-183)
+        float2 c = xf_apply(b.xf, __ldg(pts + 1));
+        cur.p3 = xf_apply(b.xf, __ldg(pts + 2));
+        float2 c2 = make_float2(c.x + c.x, c.y + c.y);
+        const float third = 1.0f / 3.0f;
+        cur.p1 = make_float2((cur.p0.x + c2.x) * third, (cur.p0.y + c2.y) * third);
+        cur.p2 = make_float2((c2.x + cur.p3.x) * third, (c2.y + cur.p3.y) * third);
+        return false;
+    }
+    cur.p1 = cur.p2 = cur.p0;
+    cur.p3 = xf_apply(b.xf, __ldg(pts + 1));
+    return true;
+}
+
+// The lock-step subdivision of one (sub)curve per lane; must be called by all 32 lanes of the warp.
+// Lanes whose curve is finished steal work: a lane's pending right halves form a deque in shared
+// memory ([level][field][thread]); the owner pops from the top, an idle lane takes the bottom entry
+// (the largest pending subtree) of a busy lane. Pairing is computed by every lane from two ballots,
+// so no locks are needed, and a warp's step count approaches (nodes of its 32 curves) / 32 instead of
+// the node count of its deepest curve.
+__device__ __forceinline__ void dice_lockstep(DiceShared &sh, Cubic cur, int depth, bool active, bool is_line, uint32_t p,
+                                              float4 *__restrict__ lines, uint32_t *__restrict__ line_path,
+                                              uint32_t line_capacity, uint32_t *__restrict__ line_count) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t lanes_below = (1u << lane) - 1u;
     float deep[DICE_MAX_DEPTH - DICE_SMEM_LEVELS][7];
-    int sp = 0, depth = 0;
+    int sp = 0, bottom = 0; // this lane's pending right halves are levels [bottom, sp)
     // Staging ring of 64 lines per warp: [head, head + staged) mod 64 (both warp-uniform).
     uint32_t head = 0, staged = 0;
     auto flush = [&](uint32_t count) { // writes the oldest `count` (<= 32) staged lines
@@ -257,8 +267,8 @@ __global__ void __launch_bounds__(DICE_THREADS)
         base = __shfl_sync(0xffffffffu, base, 0);
         const uint32_t slot = (head + lane) & 63u;
         if ((uint32_t)lane < count && base + lane < line_capacity) {
-            lines[base + lane] = s_line[warp][slot];
-            line_path[base + lane] = s_path[warp][slot];
+            lines[base + lane] = sh.line[warp][slot];
+            line_path[base + lane] = sh.path[warp][slot];
         }
         head = (head + count) & 63u;
         staged -= count;
@@ -270,16 +280,16 @@ __global__ void __launch_bounds__(DICE_THREADS)
             // process_segment (renderer/src/tiler.rs:166-184), one node of the subdivision tree per step
             if (is_line || cubic_is_flat(cur) || depth >= DICE_MAX_DEPTH) {
                 leaf = true;
-                if (sp == 0) {
+                if (sp == bottom) {
                     active = false;
                 } else {
                     sp--;
-                    cur.p0 = cur.p3;
+                    cur.p0 = cur.p3; // = the stored p0: splits keep end points bit-exact
                     if (sp < DICE_SMEM_LEVELS) {
-                        cur.p1 = make_float2(s_stack[sp][0][tid], s_stack[sp][1][tid]);
-                        cur.p2 = make_float2(s_stack[sp][2][tid], s_stack[sp][3][tid]);
-                        cur.p3 = make_float2(s_stack[sp][4][tid], s_stack[sp][5][tid]);
-                        depth = s_depth[sp][tid];
+                        cur.p1 = make_float2(sh.stack[sp][2][tid], sh.stack[sp][3][tid]);
+                        cur.p2 = make_float2(sh.stack[sp][4][tid], sh.stack[sp][5][tid]);
+                        cur.p3 = make_float2(sh.stack[sp][6][tid], sh.stack[sp][7][tid]);
+                        depth = sh.depth[sp][tid];
                     } else {
                         const float *d = deep[sp - DICE_SMEM_LEVELS];
                         cur.p1 = make_float2(d[0], d[1]);
@@ -296,10 +306,11 @@ __global__ void __launch_bounds__(DICE_THREADS)
                 float2 p0123 = lerp_half(p012, p123);
                 depth++;
                 if (sp < DICE_SMEM_LEVELS) {
-                    s_stack[sp][0][tid] = p123.x, s_stack[sp][1][tid] = p123.y;
-                    s_stack[sp][2][tid] = p23.x, s_stack[sp][3][tid] = p23.y;
-                    s_stack[sp][4][tid] = cur.p3.x, s_stack[sp][5][tid] = cur.p3.y;
-                    s_depth[sp][tid] = (unsigned char)depth;
+                    sh.stack[sp][0][tid] = p0123.x, sh.stack[sp][1][tid] = p0123.y;
+                    sh.stack[sp][2][tid] = p123.x, sh.stack[sp][3][tid] = p123.y;
+                    sh.stack[sp][4][tid] = p23.x, sh.stack[sp][5][tid] = p23.y;
+                    sh.stack[sp][6][tid] = cur.p3.x, sh.stack[sp][7][tid] = cur.p3.y;
+                    sh.depth[sp][tid] = (unsigned char)depth;
                 } else {
                     float *d = deep[sp - DICE_SMEM_LEVELS];
                     d[0] = p123.x, d[1] = p123.y, d[2] = p23.x, d[3] = p23.y, d[4] = cur.p3.x, d[5] = cur.p3.y;
@@ -311,9 +322,9 @@ __global__ void __launch_bounds__(DICE_THREADS)
         }
         const uint32_t ballot = __ballot_sync(0xffffffffu, leaf);
         if (leaf) {
-            const uint32_t slot = (head + staged + __popc(ballot & ((1u << lane) - 1u))) & 63u;
-            s_line[warp][slot] = make_float4(leaf_from.x, leaf_from.y, leaf_to.x, leaf_to.y);
-            s_path[warp][slot] = p;
+            const uint32_t slot = (head + staged + __popc(ballot & lanes_below)) & 63u;
+            sh.line[warp][slot] = make_float4(leaf_from.x, leaf_from.y, leaf_to.x, leaf_to.y);
+            sh.path[warp][slot] = p;
         }
         staged += __popc(ballot);
         if (staged >= 32) {
@@ -321,16 +332,72 @@ __global__ void __launch_bounds__(DICE_THREADS)
             flush(32);
             __syncwarp(); // the flushed slots may be rewritten by the next step
         }
+        // ---- work stealing: the k-th idle lane takes the bottom entry of the k-th lane that can give one
+        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (idle == 0) continue;
+        const bool can_give = active && bottom < sp && bottom < DICE_SMEM_LEVELS;
+        const uint32_t givers = __ballot_sync(0xffffffffu, can_give);
+        if (givers == 0) continue;
+        __syncwarp(); // the givers' pushes of this step are visible
+        const int pairs = min(__popc(idle), __popc(givers));
+        int victim = -1;
+        if (!active && __popc(idle & lanes_below) < pairs) victim = (int)__fns(givers, 0, __popc(idle & lanes_below) + 1);
+        const int victim_bottom = __shfl_sync(0xffffffffu, bottom, victim < 0 ? 0 : victim);
+        const uint32_t victim_path = __shfl_sync(0xffffffffu, p, victim < 0 ? 0 : victim);
+        if (victim >= 0) {
+            const int vt = (tid & ~31) + victim;
+            cur.p0 = make_float2(sh.stack[victim_bottom][0][vt], sh.stack[victim_bottom][1][vt]);
+            cur.p1 = make_float2(sh.stack[victim_bottom][2][vt], sh.stack[victim_bottom][3][vt]);
+            cur.p2 = make_float2(sh.stack[victim_bottom][4][vt], sh.stack[victim_bottom][5][vt]);
+            cur.p3 = make_float2(sh.stack[victim_bottom][6][vt], sh.stack[victim_bottom][7][vt]);
+            depth = sh.depth[victim_bottom][vt];
+            p = victim_path;
+            is_line = false;
+            active = true;
+            sp = bottom = 0;
+        } else if (can_give && __popc(givers & lanes_below) < pairs) {
+            bottom++;
+        }
+        __syncwarp(); // stolen entries are read before their owners can overwrite anything
     }
     __syncwarp();
     if (staged) flush(staged);
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(DICE_THREADS)
+    k_dice_stream(BatchDev b, uint32_t segments_per_warp, float4 *__restrict__ lines, uint32_t *__restrict__ line_path,
+                  uint32_t line_capacity, uint32_t *__restrict__ line_count) {
+    __shared__ DiceShared sh;
+    // A warp starts with segments_per_warp (<= 32) curves, one per low lane: on small scenes the other
+    // lanes start idle and take the first right halves that appear, so even a few thousand curves
+    // spread over every SM and the deepest curve is shared by a whole warp.
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t s = warp_global * segments_per_warp + lane;
+    bool active = lane < segments_per_warp && s < b.n_segments;
+    bool is_line = false;
+    uint32_t p = 0;
+    Cubic cur;
+    cur.p0 = cur.p1 = cur.p2 = cur.p3 = make_float2(0.0f, 0.0f);
+    if (active) is_line = load_segment(b, s, p, cur);
+    dice_lockstep(sh, cur, 0, active, is_line, p, lines, line_path, line_capacity, line_count);
 }
 
 int launch_dice_stream(const BatchDev &b, float4 *lines, uint32_t *line_path, uint32_t line_capacity,
                        uint32_t *line_count, cudaStream_t stream) {
     if (b.n_segments == 0) return 0;
-    k_dice_stream<<<div_up(b.n_segments, DICE_THREADS), DICE_THREADS, 0, stream>>>(b, lines, line_path, line_capacity,
-                                                                                  line_count);
+    // Enough warps to give every scheduler of the GPU a few (148 SMs x 4 schedulers x 2), at most 32 curves each.
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        PF_CUDA_CHECK(cudaGetDevice(&dev));
+        PF_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const uint32_t target_warps = (uint32_t)sm_count * 8u;
+    const uint32_t per_warp = std::min(32u, std::max(1u, div_up(b.n_segments, target_warps)));
+    const uint32_t warps = div_up(b.n_segments, per_warp);
+    k_dice_stream<<<div_up(warps, DICE_THREADS / 32), DICE_THREADS, 0, stream>>>(b, per_warp, lines, line_path,
+                                                                                  line_capacity, line_count);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
