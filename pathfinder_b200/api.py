@@ -89,10 +89,17 @@ class Scene:
         for i, c in enumerate(flat.paint_colors):
             remap[i] = s.push_paint(c)
         paints = np.ascontiguousarray(remap[flat.paints], dtype=np.uint16)
+        for (c0, c1), rule in zip(flat.clip_contour_ranges, flat.clip_fill_rules):
+            p0, p1 = int(flat.contour_offsets[c0]), int(flat.contour_offsets[c1])
+            s.push_clip_path(flat.points[p0:p1], flat.point_flags[p0:p1], flat.contour_offsets[c0:c1 + 1] - p0, int(rule))
+        n_draw_contours = int(flat.path_contour_offsets[-1])
+        n_draw_points = int(flat.contour_offsets[n_draw_contours])
+        clip_ids = flat.draw_clip_paths if flat.n_clip_paths else None
         L.check(lib.PFScenePushDrawPaths(
-            s._h, flat.points.ctypes.data, flat.point_flags.ctypes.data, len(flat.points),
-            flat.contour_offsets.ctypes.data, flat.n_contours, flat.path_contour_offsets.ctypes.data,
-            flat.n_paths, paints.ctypes.data, flat.fill_rules.ctypes.data, None))
+            s._h, flat.points.ctypes.data, flat.point_flags.ctypes.data, n_draw_points,
+            flat.contour_offsets.ctypes.data, n_draw_contours, flat.path_contour_offsets.ctypes.data,
+            flat.n_paths, paints.ctypes.data, flat.fill_rules.ctypes.data,
+            clip_ids.ctypes.data if clip_ids is not None else None))
         return s
 
     def set_view_box(self, view_box):
@@ -115,6 +122,14 @@ class Scene:
         co = np.ascontiguousarray(contour_offsets, dtype=np.uint32)
         return int(L.lib().PFScenePushDrawPath(self._h, pts.ctypes.data, fl.ctypes.data, co.ctypes.data,
                                                len(co) - 1, paint_id, fill_rule, blend_mode, clip_path_id))
+
+    def push_clip_path(self, points, point_flags, contour_offsets, fill_rule=0, clip_path_id=0xFFFFFFFF) -> int:
+        """Scene::push_clip_path (scene.rs:99-106); returns the ClipPathId."""
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
+        fl = np.ascontiguousarray(point_flags, dtype=np.uint8)
+        co = np.ascontiguousarray(contour_offsets, dtype=np.uint32)
+        return int(L.lib().PFScenePushClipPath(self._h, pts.ctypes.data, fl.ctypes.data, co.ctypes.data,
+                                               len(co) - 1, fill_rule, clip_path_id))
 
     def draw_path_count(self) -> int:
         return int(L.lib().PFSceneGetDrawPathCount(self._h))

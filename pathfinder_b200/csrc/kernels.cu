@@ -822,9 +822,10 @@ int launch_sum_fill_counts(const uint32_t *tile_word, uint32_t n_tiles, unsigned
 // propagate — backdrop prefix sums down tile columns + occluder z-writes, one thread per column.
 // ---------------------------------------------------------------------------------------------
 
+template <bool HAS_CLIP>
 __global__ void __launch_bounds__(128)
     k_propagate(BatchDev b, uint32_t *__restrict__ tile_word, const int32_t *__restrict__ col_backdrop,
-                int32_t *__restrict__ z_buffer) {
+                int32_t *__restrict__ z_buffer, ClipDev clip, uint32_t *__restrict__ tile_clip) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= b.n_columns) return;
     uint32_t p = search_coarse(b.path_col_offset, b.col_index, c);
@@ -838,6 +839,18 @@ __global__ void __launch_bounds__(128)
     int32_t backdrop = col_backdrop[c];
     uint32_t t = path.tile_offset + (uint32_t)x;
     const int fb_h = b.fb.max_y - b.fb.min_y;
+    // The clip path of this draw path, if any: the column's clip tiles are at clip_t0 + row * clip_w.
+    bool clipped = false, clip_column = false;
+    int clip_w = 0, clip_min_y = 0, clip_max_y = 0;
+    uint32_t clip_t0 = 0;
+    if (HAS_CLIP && path.clip_path_index < clip.n_paths) {
+        clipped = true;
+        const PathInfo cp = load_path(clip.paths, path.clip_path_index);
+        const int cx = path.min_x + x - cp.min_x;
+        clip_w = cp.max_x - cp.min_x, clip_min_y = cp.min_y, clip_max_y = cp.max_y;
+        clip_column = cx >= 0 && cx < clip_w;
+        clip_t0 = cp.tile_offset + (uint32_t)cx;
+    }
     // The prefix sum is serial down the column, but the loads are not: fetch 8 rows ahead so the
     // chain waits for memory once per 8 tiles instead of once per tile.
     constexpr int AHEAD = 8;
@@ -852,12 +865,34 @@ __global__ void __launch_bounds__(128)
             if (y < h) {
                 const uint32_t word = words[k];
                 const int delta = (int)(int8_t)(word >> 24);
-                const uint32_t count = word & 0x00ffffffu;
-                const int8_t b8 = (int8_t)backdrop; // backdrops[column] as i8   (renderer/src/tiler.rs:112)
+                uint32_t count = word & 0x00ffffffu;
+                int8_t b8 = (int8_t)backdrop; // backdrops[column] as i8   (renderer/src/tiler.rs:112)
+                uint32_t clip_ref = 0;
+                if (HAS_CLIP && clipped) {
+                    // Tiler::prepare_tiles, the four clip cases (renderer/src/tiler.rs:114-156;
+                    // twin: shaders/d3d11/propagate.cs.glsl:142-189).
+                    const int ty = path.min_y + y;
+                    bool drop = true;
+                    if (clip_column && ty >= clip_min_y && ty < clip_max_y) {
+                        const uint32_t ct = clip_t0 + (uint32_t)(ty - clip_min_y) * (uint32_t)clip_w;
+                        const uint32_t cw = __ldg(clip.tile_word + ct);
+                        const bool clip_alpha = (cw & 0x00ffffffu) != 0;
+                        drop = false;
+                        if (clip_alpha && count != 0) {
+                            clip_ref = ct + 1u; // both are masks: min-combined in the fused kernel
+                        } else if (clip_alpha && count == 0 && b8 != 0) {
+                            clip_ref = (ct + 1u) | TILE_CLIP_REPLACE; // the solid draw tile takes the clip tile's mask
+                        } else if (!clip_alpha && (cw >> 24) == 0) {
+                            drop = true; // the clip path does not cover this tile
+                        }
+                    }
+                    if (drop) count = 0, b8 = 0;
+                    tile_clip[t + (uint32_t)(k * w)] = clip_ref;
+                }
                 tile_word[t + (uint32_t)(k * w)] = count | ((uint32_t)(uint8_t)b8 << 24);
                 // Occluder z-write for solid tiles (renderer/src/builder.rs:1014-1028; twin:
                 // shaders/d3d11/propagate.cs.glsl:204-208). The fill rule is ignored, as in the reference.
-                if (z_write && count == 0 && b8 != 0 && fx_ok) {
+                if (z_write && count == 0 && b8 != 0 && clip_ref == 0 && fx_ok) {
                     const int fy = path.min_y + y - b.fb.min_y;
                     if (fy >= 0 && fy < fb_h) atomicMax(z_buffer + (size_t)fy * fb_w + fx, (int32_t)path.global_path_id);
                 }
@@ -869,9 +904,12 @@ __global__ void __launch_bounds__(128)
 }
 
 int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_backdrop, int32_t *z_buffer,
-                     cudaStream_t stream) {
+                     const ClipDev *clip, uint32_t *tile_clip, cudaStream_t stream) {
     if (b.n_columns == 0) return 0;
-    k_propagate<<<div_up(b.n_columns, 128), 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer);
+    if (clip && tile_clip)
+        k_propagate<true><<<div_up(b.n_columns, 128), 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, *clip, tile_clip);
+    else
+        k_propagate<false><<<div_up(b.n_columns, 128), 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, ClipDev{}, nullptr);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -966,7 +1004,8 @@ __global__ void __launch_bounds__(256)
     k_list_emit(BatchDev b, const uint32_t *__restrict__ tile_fb, const uint32_t *__restrict__ tile_word,
                 const uint32_t *__restrict__ tile_fill_pos, const uint32_t *__restrict__ fb_start,
                 uint32_t *__restrict__ fb_cursor, const float4 *__restrict__ paints,
-                TileEntry *__restrict__ entries, uint32_t capacity, OverflowGuard guard) {
+                TileEntry *__restrict__ entries, uint32_t capacity, OverflowGuard guard, ClipDev clip,
+                const uint32_t *__restrict__ tile_clip, uint2 *__restrict__ entry_clip) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     // All totals are final by now. A batch that overflowed a stage buffer must leave the destination
     // untouched (the exact-sized re-run may have to load it): park the fused kernel's work counter
@@ -987,9 +1026,19 @@ __global__ void __launch_bounds__(256)
         e.tile_index = t;
         uint32_t slot = __ldg(fb_start + fbi) + atomicAdd(fb_cursor + fbi, 1u);
         const float4 color = __ldg(paints + (e.paint_ctrl & 0xffffu));
+        uint2 clip_entry = make_uint2(0, 0);
+        if (tile_clip) { // the batch has clipped paths
+            const uint32_t ref = __ldg(tile_clip + t);
+            if (ref != 0) {
+                const uint32_t ct = (ref & ~TILE_CLIP_REPLACE) - 1u;
+                clip_entry = make_uint2(__ldg(clip.tile_fill_end + ct), __ldg(clip.tile_word + ct));
+                e.paint_ctrl |= ENTRY_HAS_CLIP | ((ref & TILE_CLIP_REPLACE) ? ENTRY_CLIP_REPLACE : 0u);
+            }
+        }
         if (slot < capacity) {
             *reinterpret_cast<uint4 *>(entries + slot) = *reinterpret_cast<uint4 *>(&e);
             entries[slot].color = color;
+            if (tile_clip) entry_clip[slot] = clip_entry;
         }
     }
 }
@@ -997,10 +1046,12 @@ __global__ void __launch_bounds__(256)
 int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t *tile_word,
                      const uint32_t *tile_fill_pos, const uint32_t *fb_start, uint32_t *fb_cursor,
                      const float4 *paints, TileEntry *entries, uint32_t capacity, const OverflowGuard &guard,
-                     cudaStream_t stream) {
+                     const ClipDev *clip, const uint32_t *tile_clip, uint2 *entry_clip, cudaStream_t stream) {
     if (b.n_tiles == 0) return 0;
     k_list_emit<<<div_up(b.n_tiles, 256), 256, 0, stream>>>(b, tile_fb, tile_word, tile_fill_pos, fb_start, fb_cursor,
-                                                             paints, entries, capacity, guard);
+                                                             paints, entries, capacity, guard,
+                                                             clip && tile_clip ? *clip : ClipDev{},
+                                                             clip ? tile_clip : nullptr, entry_clip);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -1121,11 +1172,12 @@ __device__ __forceinline__ void blend(float4 &d, float4 base, float alpha) {
 constexpr int COMPOSITE_WARPS = 2;       // tiles per block, horizontally adjacent
 constexpr int COMPOSITE_SORT_CAP = 128;  // entries sorted in shared memory; longer lists use the slow path
 
-template <bool LOAD_DEST>
+template <bool LOAD_DEST, bool HAS_CLIP>
 __global__ void __launch_bounds__(32 * COMPOSITE_WARPS, 10) k_composite(CompositeArgs a) {
     __shared__ uint4 s_entries[COMPOSITE_WARPS][COMPOSITE_SORT_CAP];
     __shared__ float4 s_paints[COMPOSITE_WARPS][COMPOSITE_SORT_CAP];
     __shared__ uint32_t s_keys[COMPOSITE_WARPS][COMPOSITE_SORT_CAP];
+    __shared__ uint2 s_clip[COMPOSITE_WARPS][HAS_CLIP ? COMPOSITE_SORT_CAP : 1]; // {clip fill end, clip tile word}
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fb_w = a.fb.max_x - a.fb.min_x;
@@ -1187,6 +1239,7 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS, 10) k_composite(Composit
             if (lane == 0) {
                 s_entries[warp][0] = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0));
                 s_paints[warp][0] = __ldg(&a.entries[e0].color);
+                if (HAS_CLIP) s_clip[warp][0] = __ldg(a.entry_clip + e0);
             }
         } else if (n <= 32) {
             // One entry per lane: loaded once, ranked against the keys in shared memory.
@@ -1203,6 +1256,7 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS, 10) k_composite(Composit
                 for (uint32_t j = 0; j < n; j++) rank += s_keys[warp][j] < raw.w ? 1u : 0u;
                 s_entries[warp][rank] = raw;
                 s_paints[warp][rank] = color;
+                if (HAS_CLIP) s_clip[warp][rank] = __ldg(a.entry_clip + e0 + lane);
             }
         } else {
             for (uint32_t i = lane; i < n; i += 32) s_keys[warp][i] = __ldg(&a.entries[e0 + i].tile_index);
@@ -1213,6 +1267,7 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS, 10) k_composite(Composit
                 for (uint32_t j = 0; j < n; j++) rank += s_keys[warp][j] < key ? 1u : 0u;
                 s_entries[warp][rank] = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + i));
                 s_paints[warp][rank] = __ldg(&a.entries[e0 + i].color);
+                if (HAS_CLIP) s_clip[warp][rank] = __ldg(a.entry_clip + e0 + i);
             }
         }
         __syncwarp();
@@ -1239,9 +1294,11 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS, 10) k_composite(Composit
     for (uint32_t ei = 0; ei < n; ei++) {
         uint4 raw;
         float4 base;
+        uint2 clip_entry = make_uint2(0, 0);
         if (in_smem) {
             raw = s_entries[warp][ei];
             base = s_paints[warp][ei];
+            if (HAS_CLIP) clip_entry = s_clip[warp][ei];
         } else {
             // Slow path for very deep lists: select the next entry in draw order by a min-scan.
             uint32_t best = 0xffffffffu, best_i = 0;
@@ -1256,11 +1313,46 @@ __global__ void __launch_bounds__(32 * COMPOSITE_WARPS, 10) k_composite(Composit
             next_key = best + 1;
             raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + best_i));
             base = __ldg(&a.entries[e0 + best_i].color);
+            if (HAS_CLIP) clip_entry = __ldg(a.entry_clip + e0 + best_i);
         }
         const uint32_t fill_end = raw.x, word = raw.y;
         const uint32_t count = word & 0x00ffffffu;
         const float backdrop = (float)(int)(int8_t)(word >> 24);
         const uint32_t ctrl = (raw.z >> 16) & 0xffu;
+        if (HAS_CLIP && (raw.z & ENTRY_HAS_CLIP)) {
+            // A tile of a clipped path that meets an alpha tile of its clip path (tiler.rs:114-156). Both
+            // masks are evaluated here; D3D9 combines them as min(|draw + backdrop|, |clip + backdrop|)
+            // with the draw tile's backdrop then zeroed (tile_clip_combine.fs.glsl:28-31); a solid
+            // draw tile simply takes over the clip tile's mask and backdrop.
+            if (uniform) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) dst[k] = uni;
+                uniform = false;
+            }
+            const bool replace = (raw.z & ENTRY_CLIP_REPLACE) != 0;
+            const uint32_t clip_count = clip_entry.y & 0x00ffffffu;
+            const float clip_backdrop = (float)(int)(int8_t)(clip_entry.y >> 24);
+            uint32_t acc_draw[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, acc_clip[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+            uint32_t n_draw = 0, n_clip = 0;
+            if (!replace)
+                for (uint32_t f = fill_end - count; f < fill_end; f++) {
+                    const uint2 fill = __ldg(a.fills + f);
+                    n_draw += accumulate_fill<2>(fill.x, fill.y, cx, cy, a.area_lut, acc_draw) ? 1u : 0u;
+                }
+            for (uint32_t f = clip_entry.x - clip_count; f < clip_entry.x; f++) {
+                const uint2 fill = __ldg(a.clip_fills + f);
+                n_clip += accumulate_fill<2>(fill.x, fill.y, cx, cy, a.area_lut, acc_clip) ? 1u : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float clip_cov = finish_coverage(acc_clip[k >> 2][k & 3], n_clip) + clip_backdrop;
+                float coverage = clip_cov;
+                if (!replace)
+                    coverage = fminf(fabsf(finish_coverage(acc_draw[k >> 2][k & 3], n_draw) + backdrop), fabsf(clip_cov));
+                blend(dst[k], base, base.w * mask_alpha(coverage, ctrl));
+            }
+            continue;
+        }
         if (count == 0) {
             // Solid tile: coverage = backdrop for every pixel (tile_fragment.inc.glsl:548).
             const float alpha = base.w * mask_alpha(backdrop, ctrl);
@@ -1371,25 +1463,37 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     int rows = a.tile_y1 - a.tile_y0;
     if (fb_w <= 0 || rows <= 0) return 0;
     // One resident wave of persistent warps: SM count x resident blocks per SM.
-    static int blocks_per_sm[2] = {0, 0}, sm_count = 0;
+    static int blocks_per_sm[2] = {0, 0}, clip_blocks_per_sm[2] = {0, 0}, sm_count = 0;
     if (sm_count == 0) {
         int dev = 0;
         PF_CUDA_CHECK(cudaGetDevice(&dev));
         PF_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], k_composite<false>, 32 * COMPOSITE_WARPS, 0));
-        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], k_composite<true>, 32 * COMPOSITE_WARPS, 0));
+        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], k_composite<false, false>, 32 * COMPOSITE_WARPS, 0));
+        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], k_composite<true, false>, 32 * COMPOSITE_WARPS, 0));
+        // the clip variants keep one more shared array per warp; never more resident blocks than the plain ones
+        int with_clip[2];
+        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_clip[0], k_composite<false, true>, 32 * COMPOSITE_WARPS, 0));
+        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_clip[1], k_composite<true, true>, 32 * COMPOSITE_WARPS, 0));
+        clip_blocks_per_sm[0] = with_clip[0], clip_blocks_per_sm[1] = with_clip[1];
     }
     const uint64_t n_work = (uint64_t)fb_w * (uint64_t)rows;
     CompositeArgs args = a;
     args.fb_w_recip = (uint32_t)std::min<uint64_t>(0xffffffffull, (1ull << 32) / (uint64_t)fb_w);
     uint64_t want = (n_work + COMPOSITE_WARPS - 1) / COMPOSITE_WARPS;
-    uint64_t resident = (uint64_t)sm_count * (uint64_t)blocks_per_sm[a.load_dest ? 1 : 0];
+    const bool has_clip = a.entry_clip != nullptr;
+    uint64_t resident = (uint64_t)sm_count * (uint64_t)(has_clip ? clip_blocks_per_sm : blocks_per_sm)[a.load_dest ? 1 : 0];
     unsigned grid = (unsigned)(want < resident ? want : resident);
     // The caller has zeroed a.work_counter (the tile-list kernel may since have parked it past the end).
-    if (a.load_dest)
-        k_composite<true><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(args);
-    else
-        k_composite<false><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(args);
+    if (has_clip) {
+        if (a.load_dest)
+            k_composite<true, true><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(args);
+        else
+            k_composite<false, true><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(args);
+    } else if (a.load_dest) {
+        k_composite<true, false><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(args);
+    } else {
+        k_composite<false, false><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(args);
+    }
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

@@ -117,8 +117,25 @@ int launch_bin(int mode, const BatchDev &b, const BinArgs &args, cudaStream_t st
 
 int launch_sum_fill_counts(const uint32_t *tile_word, uint32_t n_tiles, unsigned long long *total, cudaStream_t stream);
 
+// Results of the clip batch (PrepareClipTilesD3D11), read while a draw batch with clipped paths is
+// resolved (reference: tiler.rs:114-156, propagate.cs.glsl:142-189).
+struct ClipDev {
+    const PathInfo *paths;         // the clip batch's path records (tile rects, dense tile offsets)
+    uint32_t n_paths;
+    const uint32_t *tile_word;     // fill count | backdrop of every clip tile, after its own propagate
+    const uint32_t *tile_fill_end; // end of each clip tile's run in `fills`
+    const PackedFill *fills;
+};
+// Per draw tile, written by propagate when the batch has clipped paths: 0 = not clipped by an alpha
+// tile; else (dense clip tile index + 1), with TILE_CLIP_REPLACE when the (solid) draw tile takes over
+// the clip tile's mask and backdrop instead of min-combining its own mask with it.
+constexpr uint32_t TILE_CLIP_REPLACE = 0x80000000u;
+// TileEntry.paint_ctrl flag bits (the low 24 bits are colour | ctrl).
+constexpr uint32_t ENTRY_HAS_CLIP = 1u << 24, ENTRY_CLIP_REPLACE = 1u << 25;
+
+// clip / tile_clip: NULL unless the batch has clipped paths.
 int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_backdrop, int32_t *z_buffer,
-                     cudaStream_t stream);
+                     const ClipDev *clip, uint32_t *tile_clip, cudaStream_t stream);
 
 // tile_fb[t] = framebuffer tile index if the tile is non-empty, inside the framebuffer and not
 // z-culled, else 0xffffffff; fb_count[fb] += 1 for every survivor.
@@ -137,10 +154,12 @@ struct OverflowGuard {
 int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t *tile_word,
                      const uint32_t *tile_fill_pos, const uint32_t *fb_start, uint32_t *fb_cursor,
                      const float4 *paints, TileEntry *entries, uint32_t capacity, const OverflowGuard &guard,
-                     cudaStream_t stream);
+                     const ClipDev *clip, const uint32_t *tile_clip, uint2 *entry_clip, cudaStream_t stream);
 
 struct CompositeArgs {
     const TileEntry *entries;   // runs in arbitrary order; the kernel sorts each by tile_index
+    const uint2 *entry_clip;    // per entry {clip fill end, clip tile word}, for entries with ENTRY_HAS_CLIP (else NULL)
+    const PackedFill *clip_fills;
     const uint32_t *fb_start, *fb_count;
     const PackedFill *fills;
     cudaTextureObject_t area_lut;

@@ -67,6 +67,7 @@ struct BatchCache {
     int32_t strip_y0 = 0, strip_y1 = 0;
     BatchDev batch{};
     bool has_initial_backdrops = false;
+    bool has_clips = false; // the batch has clipped paths (resolved against r->clip)
     bool counts_valid = false; // n_lines / n_fills / n_entries hold the last frame's totals
     uint32_t n_lines = 0, n_fills = 0, n_entries = 0, n_visible_fills = 0;
     uint32_t command_paths = 0, command_segments = 0; // as sent (before strip culling)
@@ -156,6 +157,16 @@ struct PFCudaRenderer {
     DeviceBuffer<uint32_t> tile_fill_pos, tile_first_fill, tile_fb, tile_pos, tile_alpha_id;
     DeviceBuffer<int32_t> col_backdrop_init;
     DeviceBuffer<uint32_t> long_queue; // lines walked by whole warps (k_bin_long)
+    // Clip batch results (PrepareClipTilesD3D11), kept until the draw batch of the same frame has used them.
+    struct ClipStage {
+        bool valid = false;
+        uint32_t n_paths = 0;
+        DeviceBuffer<uint8_t> meta;              // PathInfo[n_paths]
+        DeviceBuffer<uint32_t> tile_word, tile_fill_end;
+        DeviceBuffer<PackedFill> fills;
+    } clip;
+    DeviceBuffer<uint32_t> tile_clip;  // per draw tile: clip tile reference (batches with clipped paths)
+    DeviceBuffer<uint2> entry_clip;    // per list entry: {clip fill end, clip tile word}
     DeviceBuffer<PackedFill> fills;
     DeviceBuffer<EmitFill> fills_emit;
     DeviceBuffer<uint32_t> fb_start;
@@ -229,6 +240,12 @@ void setup_tracking(PFCudaRenderer *r) {
     track(r, r->tile_alpha_id);
     track(r, r->col_backdrop_init);
     track(r, r->long_queue);
+    track(r, r->clip.meta);
+    track(r, r->clip.tile_word);
+    track(r, r->clip.tile_fill_end);
+    track(r, r->clip.fills);
+    track(r, r->tile_clip);
+    track(r, r->entry_clip);
     track(r, r->fills);
     track(r, r->fills_emit);
     track(r, r->fb_start);
@@ -355,7 +372,8 @@ void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *en
 // Builds the per-path device records of a batch (host part of "bound") and uploads them. Replaces
 // the offsets TileBatchDataD3D11::push assigns (renderer/src/builder.rs:663-720) + bound.cs.glsl.
 void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch, const FbRect &fb,
-                           int32_t strip_y0, int32_t strip_y1, BatchDev &b, bool &has_initial_backdrops) {
+                           int32_t strip_y0, int32_t strip_y1, BatchDev &b, bool &has_initial_backdrops,
+                           const SceneSegments &segments, bool is_clip_batch) {
     HostTimer timer("upload_batch_metadata");
     LapTimer laps;
     cudaStream_t st = r->stream;
@@ -434,7 +452,7 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
                  tile_off = (uint32_t)sums[chunk].tiles, col_off = (uint32_t)sums[chunk].columns;
         for (size_t i = begin; i < end; i++) {
             const PFTilePathInfoD3D11 &tp = info.tile_path_info[i];
-            bad |= tp.color >= n_paints;
+            bad |= !is_clip_batch && tp.color >= n_paints; // clip paths have no paint
             int32_t w, h;
             if (!strip_rect((uint32_t)i, w, h)) continue;
             const PFPropagateMetadataD3D11 &pm = info.propagate_metadata[i];
@@ -499,8 +517,8 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
     laps.lap("meta enqueue copy");
 
     b = BatchDev{};
-    b.points = r->draw_segments.points.ptr;
-    b.seg_indices = r->draw_segments.indices.ptr;
+    b.points = segments.points.ptr;
+    b.seg_indices = segments.indices.ptr;
     b.paths = reinterpret_cast<const PathInfo *>(r->batch_meta.ptr);
     b.path_seg_first = reinterpret_cast<const uint32_t *>(r->batch_meta.ptr + (size_t)P * sizeof(PathInfo));
     b.path_tile_offset = b.path_seg_first + (P + 1);
@@ -571,7 +589,7 @@ void carve_zeroed(PFCudaRenderer *r, size_t n_paths, size_t n_tiles, size_t n_co
     PF_CUDA_CHECK(cudaMemsetAsync(r->zeroed.ptr, 0, total * sizeof(uint32_t), r->stream));
 }
 
-bool run_pipeline(PFCudaRenderer *r, bool sizing) {
+bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
     cudaStream_t st = r->stream;
     BatchCache &c = r->cache;
     const BatchDev &b = c.batch;
@@ -659,7 +677,20 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[3], st));
 
     // ---- propagate: column backdrop prefix sums + occluder z-writes.
-    launches += launch_propagate(b, r->tile_word.ptr, r->col_backdrop.ptr, r->z_buffer.ptr, st);
+    // A batch with clipped paths resolves its tiles against the clip batch here (the four cases of
+    // Tiler::prepare_tiles) and leaves a reference to the clip tile wherever a mask has to be combined.
+    ClipDev clip_dev{};
+    const bool use_clip = !clip_pass && c.has_clips;
+    if (use_clip) {
+        clip_dev.paths = reinterpret_cast<const PathInfo *>(r->clip.meta.ptr);
+        clip_dev.n_paths = r->clip.n_paths;
+        clip_dev.tile_word = r->clip.tile_word.ptr;
+        clip_dev.tile_fill_end = r->clip.tile_fill_end.ptr;
+        clip_dev.fills = r->clip.fills.ptr;
+        r->tile_clip.ensure(n_tiles + 1, 1.25);
+    }
+    launches += launch_propagate(b, r->tile_word.ptr, r->col_backdrop.ptr, r->z_buffer.ptr,
+                                 use_clip ? &clip_dev : nullptr, use_clip ? r->tile_clip.ptr : nullptr, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[4], st));
 
     // ---- sort: z-cull + per-framebuffer-tile runs (count -> scan -> append); the run itself is
@@ -704,14 +735,40 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing) {
     } else {
         launches += launch_bin(0 /* BIN_EMIT_LIVE */, b, ba, st);
     }
+    if (clip_pass) {
+        // The clip batch ends here: keep what the draw batch will read — the stage buffers themselves are
+        // reused by the draw batch.
+        r->clip.n_paths = b.n_paths;
+        r->clip.meta.ensure((size_t)b.n_paths * sizeof(PathInfo) + 64);
+        r->clip.tile_word.ensure(n_tiles + 1);
+        r->clip.tile_fill_end.ensure(n_tiles + 1);
+        r->clip.fills.ensure(fill_bound + 1);
+        auto keep = [&](void *dst, const void *src, size_t bytes) {
+            if (bytes) PF_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+        };
+        keep(r->clip.meta.ptr, b.paths, (size_t)b.n_paths * sizeof(PathInfo));
+        keep(r->clip.tile_word.ptr, r->tile_word.ptr, (size_t)n_tiles * 4);
+        keep(r->clip.tile_fill_end.ptr, r->tile_fill_pos.ptr, (size_t)n_tiles * 4);
+        keep(r->clip.fills.ptr, r->fills.ptr, (size_t)fill_bound * sizeof(PackedFill));
+        PF_CUDA_CHECK(cudaStreamSynchronize(st)); // (the clip pass always runs with exact sizes, synchronously)
+        r->stats.host_sync_count++;
+        r->stats.drawcall_count += (uint64_t)launches;
+        r->clip.valid = true;
+        return true;
+    }
+    if (use_clip) r->entry_clip.ensure(entry_bound + 1, 1.25);
     const OverflowGuard guard{r->counters.ptr, line_bound, entry_bound, fill_bound, r->counters.ptr + 12};
     launches += launch_list_emit(b, r->tile_fb.ptr, r->tile_word.ptr, r->tile_fill_pos.ptr, r->fb_start.ptr,
-                                 r->fb_cursor.ptr, r->paints.ptr, r->entries.ptr, entry_bound, guard, st);
+                                 r->fb_cursor.ptr, r->paints.ptr, r->entries.ptr, entry_bound, guard,
+                                 use_clip ? &clip_dev : nullptr, use_clip ? r->tile_clip.ptr : nullptr,
+                                 use_clip ? r->entry_clip.ptr : nullptr, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[6], st));
 
     // ---- fill + tile (fused).
     CompositeArgs ca{};
     ca.entries = r->entries.ptr;
+    ca.entry_clip = use_clip ? r->entry_clip.ptr : nullptr;
+    ca.clip_fills = use_clip ? r->clip.fills.ptr : nullptr;
     ca.fb_start = r->fb_start.ptr;
     ca.fb_count = r->fb_count.ptr;
     ca.fills = r->fills.ptr;
@@ -823,13 +880,41 @@ void verify_pending(PFCudaRenderer *r) {
 // One DrawTilesD3D11 batch: prepare_tiles + draw_tiles (d3d11/renderer.rs:414-424).
 void verify_pending(PFCudaRenderer *r);
 
+// PrepareClipTilesD3D11: dice, bin and propagate the clip paths and keep their tiles and fills for the
+// draw batch that references them (d3d11/renderer.rs prepare_tiles on a clip batch).
+// One level of clipping: a clip path that is itself clipped is refused.
+void prepare_clip_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
+    verify_pending(r);
+    if (!r->has_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "PrepareClipTilesD3D11 before UploadSceneD3D11");
+    if (batch.path_source != PF_PATH_SOURCE_CLIP)
+        throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "clip batch with a draw path source");
+    if (batch.has_clipped_path_info && batch.clipped_path_info.clipped_path_count > 0)
+        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "nested clip paths are not implemented");
+    if (r->clip.valid) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "more than one clip batch per frame (nested clip levels)");
+    if (r->debug_lists)
+        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "the parity dumps do not cover clipped paths yet (SURVEY.md §8 f1)");
+    const FbRect fb = framebuffer_tile_rect(r);
+    const int32_t strip_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
+    const int32_t strip_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
+    BatchCache &c = r->cache;
+    c.valid = false; // the stage buffers and the batch slot are borrowed; the draw batch re-uploads
+    c.has_clips = false;
+    upload_batch_metadata(r, batch, fb, strip_y0, strip_y1, c.batch, c.has_initial_backdrops, r->clip_segments, true);
+    c.strip_y0 = strip_y0;
+    c.strip_y1 = strip_y1;
+    run_pipeline(r, true, true);
+}
+
 void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     verify_pending(r);
     if (!r->has_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "DrawTilesD3D11 before UploadSceneD3D11");
     if (batch.path_source != PF_PATH_SOURCE_DRAW)
         throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "draw batch with a clip path source");
-    if (batch.has_clipped_path_info && batch.clipped_path_info.clipped_path_count > 0)
-        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "clip paths are a 'next' row (SURVEY.md §8 f1)");
+    const bool has_clips = batch.has_clipped_path_info && batch.clipped_path_info.clipped_path_count > 0;
+    if (has_clips && !r->clip.valid)
+        throw Error(PF_CUDA_ERROR_PROTOCOL, "draw batch with clipped paths before PrepareClipTilesD3D11");
+    if (has_clips && r->debug_lists)
+        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "the parity dumps do not cover clipped paths yet (SURVEY.md §8 f1)");
     const FbRect fb = framebuffer_tile_rect(r);
     const int32_t strip_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
     const int32_t strip_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
@@ -854,7 +939,7 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
                                 c.command_segments == batch.segment_count && c.strip_y0 == strip_y0 &&
                                 c.strip_y1 == strip_y1 && memcmp(&c.batch.fb, &fb, sizeof(fb)) == 0;
         c.valid = false;
-        upload_batch_metadata(r, batch, fb, strip_y0, strip_y1, c.batch, c.has_initial_backdrops);
+        upload_batch_metadata(r, batch, fb, strip_y0, strip_y1, c.batch, c.has_initial_backdrops, r->draw_segments, false);
         c.key = batch.content_key;
         c.command_paths = batch.path_count;
         c.command_segments = batch.segment_count;
@@ -862,7 +947,8 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
         c.paint_generation = r->paint_generation;
         c.strip_y0 = strip_y0;
         c.strip_y1 = strip_y1;
-        c.counts_valid = same_shape;
+        c.counts_valid = same_shape && !has_clips; // batches with clips are sized exactly every frame
+        c.has_clips = has_clips;
         c.valid = true;
     } else {
         r->stats.batch_cache_hits++;
@@ -1019,6 +1105,7 @@ PFCudaStatus PFCudaRendererBeginScene(PFCudaRendererRef r) {
         if (r->in_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "begin_scene called twice");
         verify_pending(r); // the previous frame's totals (deferred verification)
         r->in_scene = true;
+        r->clip.valid = false;
         r->batches_drawn = 0;
         r->stats = PFCudaRenderStats{};
         r->times = PFCudaRenderTime{};
@@ -1053,7 +1140,7 @@ PFCudaStatus PFCudaRendererRenderCommand(PFCudaRendererRef r, const PFRenderComm
             break;
         case PF_RENDER_COMMAND_PREPARE_CLIP_TILES_D3D11:
             if (cmd->u.prepare_clip_tiles_d3d11.batch.path_count > 0)
-                throw Error(PF_CUDA_ERROR_UNSUPPORTED, "clip paths are a 'next' row (SURVEY.md §8 f1)");
+                prepare_clip_batch(r, cmd->u.prepare_clip_tiles_d3d11.batch);
             break;
         case PF_RENDER_COMMAND_DRAW_TILES_D3D11:
             if (cmd->u.draw_tiles_d3d11.has_color_texture)

@@ -145,6 +145,18 @@ struct PFScene {
     HostBuffer<PFVector2F> seg_points;
     HostBuffer<PFSegmentIndicesD3D11> seg_indices;
     size_t seg_point_count = 0, seg_index_count = 0;
+    // The same for the clip paths (BuiltSegments::from_scene builds both, builder.rs:801-815).
+    HostBuffer<PFVector2F> clip_seg_points;
+    HostBuffer<PFSegmentIndicesD3D11> clip_seg_indices;
+    size_t clip_seg_point_count = 0, clip_seg_index_count = 0;
+    std::vector<uint32_t> clip_seg_path_offsets, clip_segment_ranges;
+    // Clip batch arrays (PrepareClipTilesD3D11) and the clip path -> batch index map of the last build.
+    std::vector<PFPropagateMetadataD3D11> clip_propagate_metadata;
+    std::vector<PFDiceMetadataD3D11> clip_dice_metadata;
+    std::vector<PFTilePathInfoD3D11> clip_tile_path_info;
+    std::vector<uint32_t> clip_batch_index;
+    uint32_t built_clip_tile_count = 0, built_clip_segment_count = 0, built_clipped_path_count = 0,
+             built_clipped_tile_count = 0;
     std::vector<uint32_t> seg_path_offsets; // per-path output offsets of build_segments
     std::vector<PFRectI> path_tile_rects;   // scratch of the batch build (kept == rect non-empty)
     std::vector<uint32_t> path_batch_offsets;
@@ -234,29 +246,31 @@ void wait_for_borrowers(PFScene *s) {
     if (cudaEventSynchronize(s->borrowed_event) != cudaSuccess) (void)cudaGetLastError();
 }
 
-void build_segments(PFScene *s) {
-    wait_for_borrowers(s);
-    const size_t n_paths = s->draw_paths.size();
-    s->seg_path_offsets.resize(2 * (n_paths + 1));
-    uint32_t *point_off = s->seg_path_offsets.data(), *index_off = point_off + (n_paths + 1);
+// SegmentsD3D11::add_path for every path of one kind (builder.rs:817-857).
+void build_path_segments(PFScene *s, const std::vector<Path> &paths, HostBuffer<PFVector2F> &seg_points,
+                         HostBuffer<PFSegmentIndicesD3D11> &seg_indices, size_t &seg_point_count, size_t &seg_index_count,
+                         std::vector<uint32_t> &path_offsets, std::vector<uint32_t> &segment_ranges) {
+    const size_t n_paths = paths.size();
+    path_offsets.resize(2 * (n_paths + 1));
+    uint32_t *point_off = path_offsets.data(), *index_off = point_off + (n_paths + 1);
     uint32_t np = 0, ni = 0;
     for (size_t pi = 0; pi < n_paths; pi++) {
         point_off[pi] = np, index_off[pi] = ni;
-        np += s->draw_paths[pi].segment_points;
-        ni += s->draw_paths[pi].segment_indices;
+        np += paths[pi].segment_points;
+        ni += paths[pi].segment_indices;
     }
     point_off[n_paths] = np, index_off[n_paths] = ni;
-    s->seg_points.ensure((size_t)np + 1);
-    s->seg_indices.ensure((size_t)ni + 1);
-    s->draw_segment_ranges.resize(2 * n_paths);
-    PFVector2F *out_points = s->seg_points.ptr;
-    PFSegmentIndicesD3D11 *out_indices = s->seg_indices.ptr;
+    seg_points.ensure((size_t)np + 1);
+    seg_indices.ensure((size_t)ni + 1);
+    segment_ranges.resize(2 * n_paths);
+    PFVector2F *out_points = seg_points.ptr;
+    PFSegmentIndicesD3D11 *out_indices = seg_indices.ptr;
     const uint8_t ctrl_mask = PF_POINT_FLAGS_CONTROL_POINT_0 | PF_POINT_FLAGS_CONTROL_POINT_1;
     parallel_ranges(n_paths, 4096, [&](size_t begin, size_t end) {
         for (size_t pi = begin; pi < end; pi++) {
-            const Path &path = s->draw_paths[pi];
+            const Path &path = paths[pi];
             size_t wp = point_off[pi], wi = index_off[pi];
-            s->draw_segment_ranges[2 * pi] = (uint32_t)wi;
+            segment_ranges[2 * pi] = (uint32_t)wi;
             for (uint32_t c = path.first_contour; c < path.end_contour; c++) {
                 const uint32_t p0 = s->contour_offsets[c], point_count = s->contour_offsets[c + 1] - p0;
                 const uint8_t *flags = s->flags.data() + p0;
@@ -274,11 +288,19 @@ void build_segments(PFScene *s) {
                 wp += point_count;
                 out_points[wp++] = pts[0]; // implicit close: the first point again (builder.rs:835)
             }
-            s->draw_segment_ranges[2 * pi + 1] = (uint32_t)wi;
+            segment_ranges[2 * pi + 1] = (uint32_t)wi;
         }
     });
-    s->seg_point_count = np;
-    s->seg_index_count = ni;
+    seg_point_count = np;
+    seg_index_count = ni;
+}
+
+void build_segments(PFScene *s) {
+    wait_for_borrowers(s);
+    build_path_segments(s, s->draw_paths, s->seg_points, s->seg_indices, s->seg_point_count, s->seg_index_count,
+                        s->seg_path_offsets, s->draw_segment_ranges);
+    build_path_segments(s, s->clip_paths, s->clip_seg_points, s->clip_seg_indices, s->clip_seg_point_count,
+                        s->clip_seg_index_count, s->clip_seg_path_offsets, s->clip_segment_ranges);
 }
 
 // RectF::intersection (geometry/src/rect.rs:122-137), strict comparisons.
@@ -472,16 +494,12 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
     // Scene upload when dirty (builder.rs:190-216).
     bool dirty = !sink->has_last_scene || sink->last_scene_id != s->id || sink->last_scene_epoch != s->epoch;
     if (dirty || s->draw_segment_ranges.size() != 2 * s->draw_paths.size()) {
-        for (const Path &p : s->clip_paths)
-            if (p.first_contour != p.end_contour) {
-                pf::set_last_error("clip paths are a 'next' row (SURVEY.md §8 f1)");
-                return PF_CUDA_ERROR_UNSUPPORTED;
-            }
         build_segments(s);
         PFRenderCommand up = make_command(PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11);
         up.u.upload_scene_d3d11.draw_segments =
             PFSegmentsD3D11{s->seg_points.ptr, s->seg_point_count, s->seg_indices.ptr, s->seg_index_count};
-        up.u.upload_scene_d3d11.clip_segments = PFSegmentsD3D11{nullptr, 0, nullptr, 0};
+        up.u.upload_scene_d3d11.clip_segments = PFSegmentsD3D11{s->clip_seg_points.ptr, s->clip_seg_point_count,
+                                                                s->clip_seg_indices.ptr, s->clip_seg_index_count};
         up.u.upload_scene_d3d11.payload_persists = pf::g_scene_payload_persists ? 1 : 0;
         SEND(up);
         sink->has_last_scene = 1;
@@ -513,7 +531,67 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
     pf::LapTimer laps;
     if (rebuild) {
         const size_t n_paths = s->draw_paths.size();
-        std::atomic<int> unsupported{0}; // 1: a path has a clip path, 2: a blend mode other than SrcOver
+        std::atomic<int> unsupported{0}; // 2: a blend mode other than SrcOver
+        // Clip batch (add_clip_path_to_batch, builder.rs:1124-1175): the clip paths some draw path uses, in
+        // order of first use, one level deep. The tile rect follows the CPU tiler, which is the parity
+        // target: outline bounds ∩ view box (Tiler::new, tiler.rs:47-50), an empty rect when they miss.
+        s->clip_batch_index.assign(s->clip_paths.size(), PF_PATH_INDEX_NONE);
+        s->clip_propagate_metadata.clear();
+        s->clip_dice_metadata.clear();
+        s->clip_tile_path_info.clear();
+        uint32_t clip_tiles = 0, clip_columns = 0, clip_segments = 0;
+        for (const Path &p : s->draw_paths) {
+            if (p.clip_path == PF_CLIP_PATH_NONE) continue;
+            if (p.clip_path >= s->clip_paths.size()) {
+                pf::set_last_error("draw path refers to a clip path that does not exist");
+                return PF_CUDA_ERROR_INVALID_ARGUMENT;
+            }
+            if (s->clip_batch_index[p.clip_path] != PF_PATH_INDEX_NONE) continue;
+            const Path &cp = s->clip_paths[p.clip_path];
+            if (cp.clip_path != PF_CLIP_PATH_NONE) {
+                pf::set_last_error("nested clip paths are not implemented");
+                return PF_CUDA_ERROR_UNSUPPORTED;
+            }
+            PFRectI tile_rect{{0, 0}, {0, 0}};
+            RectF bounds = xf.is_identity() ? cp.bounds : xf.apply_rect(cp.bounds), clipped;
+            if (cp.first_contour != cp.end_contour && rect_intersection(bounds, effective_view_box, clipped)) {
+                const float k = 1.0f / 16.0f;
+                tile_rect.origin.x = (int32_t)floorf(clipped.min_x * k);
+                tile_rect.origin.y = (int32_t)floorf(clipped.min_y * k);
+                tile_rect.lower_right.x = (int32_t)ceilf(clipped.max_x * k);
+                tile_rect.lower_right.y = (int32_t)ceilf(clipped.max_y * k);
+            }
+            const uint32_t bi = (uint32_t)s->clip_propagate_metadata.size();
+            s->clip_batch_index[p.clip_path] = bi;
+            const uint32_t w = (uint32_t)(tile_rect.lower_right.x - tile_rect.origin.x),
+                           h = (uint32_t)(tile_rect.lower_right.y - tile_rect.origin.y);
+            PFPropagateMetadataD3D11 pm;
+            memset(&pm, 0, sizeof(pm));
+            pm.tile_rect = tile_rect;
+            pm.tile_offset = clip_tiles;
+            pm.path_index = bi;
+            pm.z_write = 0;
+            pm.clip_path_index = PF_PATH_INDEX_NONE;
+            pm.backdrop_offset = clip_columns;
+            s->clip_propagate_metadata.push_back(pm);
+            s->clip_dice_metadata.push_back(
+                PFDiceMetadataD3D11{p.clip_path, s->clip_segment_ranges[2 * p.clip_path], clip_segments, 0});
+            PFTilePathInfoD3D11 tp;
+            tp.tile_min_x = (int16_t)tile_rect.origin.x;
+            tp.tile_min_y = (int16_t)tile_rect.origin.y;
+            tp.tile_max_x = (int16_t)tile_rect.lower_right.x;
+            tp.tile_max_y = (int16_t)tile_rect.lower_right.y;
+            tp.first_tile_index = clip_tiles;
+            tp.color = 0; // TilingPathInfo::Clip: paint 0, ctrl 0 (builder.rs:423-428, tiles.rs:45-61)
+            tp.ctrl = 0;
+            tp.backdrop = 0;
+            s->clip_tile_path_info.push_back(tp);
+            clip_tiles += w * h;
+            clip_columns += w;
+            clip_segments += s->clip_segment_ranges[2 * p.clip_path + 1] - s->clip_segment_ranges[2 * p.clip_path];
+        }
+        s->built_clip_tile_count = clip_tiles;
+        s->built_clip_segment_count = clip_segments;
         // Pass 1 (parallel): prepare_draw_path_for_gpu_binning (builder.rs:1058-1095) — the tile rect
         // of every path; an empty rect marks a path outside the view box (skipped by the builder).
         // Each chunk also sums what its kept paths add to the batch's running offsets, so that pass 2
@@ -521,7 +599,8 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         // parallel: a two-level scan, integer adds only.
         struct ChunkSums {
             uint32_t kept = 0, tiles = 0, columns = 0, segments = 0;
-            uint32_t pad[12]; // one cache line per chunk
+            uint32_t clipped = 0, clipped_tiles = 0; // kept paths with a clip path, and their tiles
+            uint32_t pad[10]; // one cache line per chunk
         };
         s->path_tile_rects.resize(n_paths);
         const size_t chunks = pf::chunk_count(n_paths, 4096);
@@ -530,7 +609,6 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
             ChunkSums sum;
             for (size_t i = begin; i < end; i++) {
                 const Path &p = s->draw_paths[i];
-                if (p.clip_path != PF_CLIP_PATH_NONE) unsupported.store(1, std::memory_order_relaxed);
                 if (p.blend_mode != PF_BLEND_MODE_SRC_OVER) unsupported.store(2, std::memory_order_relaxed);
                 PFRectI tile_rect{{0, 0}, {0, 0}};
                 RectF path_bounds = xf.is_identity() ? p.bounds : xf.apply_rect(p.bounds);
@@ -546,6 +624,7 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                     const uint32_t w = (uint32_t)(tile_rect.lower_right.x - tile_rect.origin.x),
                                    h = (uint32_t)(tile_rect.lower_right.y - tile_rect.origin.y);
                     sum.kept++;
+                    if (p.clip_path != PF_CLIP_PATH_NONE) sum.clipped++, sum.clipped_tiles += w * h;
                     sum.tiles += w * h;
                     sum.columns += w;
                     sum.segments += s->draw_segment_ranges[2 * i + 1] - s->draw_segment_ranges[2 * i];
@@ -558,8 +637,7 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         });
         laps.lap("scene pass 1");
         if (unsupported.load() != 0) {
-            pf::set_last_error(unsupported.load() == 1 ? "clip paths are a 'next' row (SURVEY.md §8 f1)"
-                                                       : "only BlendMode::SrcOver is on the hot path");
+            pf::set_last_error("only BlendMode::SrcOver is on the hot path");
             return PF_CUDA_ERROR_UNSUPPORTED;
         }
         for (size_t c = 1; c <= chunks; c++) { // exclusive prefix: sums[c] = totals of chunks before c
@@ -567,7 +645,11 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
             sums[c].tiles += sums[c - 1].tiles;
             sums[c].columns += sums[c - 1].columns;
             sums[c].segments += sums[c - 1].segments;
+            sums[c].clipped += sums[c - 1].clipped;
+            sums[c].clipped_tiles += sums[c - 1].clipped_tiles;
         }
+        s->built_clipped_path_count = sums[chunks].clipped;
+        s->built_clipped_tile_count = sums[chunks].clipped_tiles;
         const uint32_t kept = sums[chunks].kept;
         tile_count = sums[chunks].tiles;
         column_count = sums[chunks].columns;
@@ -592,7 +674,7 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                 pm.tile_offset = tile_off;
                 pm.path_index = bi;
                 pm.z_write = occludes ? 1 : 0;
-                pm.clip_path_index = PF_PATH_INDEX_NONE;
+                pm.clip_path_index = p.clip_path == PF_CLIP_PATH_NONE ? PF_PATH_INDEX_NONE : s->clip_batch_index[p.clip_path];
                 pm.backdrop_offset = col_off;
                 s->propagate_metadata[bi] = pm;
                 s->dice_metadata[bi] = PFDiceMetadataD3D11{(uint32_t)i, s->draw_segment_ranges[2 * i], seg_off, 0};
@@ -624,6 +706,27 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
     s->built_key = batch_key;
     s->built_tile_count = tile_count;
     s->built_segment_count = segment_count;
+    const bool has_clips = !s->propagate_metadata.empty() && s->built_clipped_path_count > 0;
+    if (has_clips) {
+        // Clip batches are prepared before the draw batches that use them (builder.rs:1098-1104).
+        PFRenderCommand prepare = make_command(PF_RENDER_COMMAND_PREPARE_CLIP_TILES_D3D11);
+        PFTileBatchDataD3D11 &b = prepare.u.prepare_clip_tiles_d3d11.batch;
+        b.batch_id = 0; // clip level 0
+        b.path_count = (uint32_t)s->clip_propagate_metadata.size();
+        b.tile_count = s->built_clip_tile_count;
+        b.segment_count = s->built_clip_segment_count;
+        b.prepare_info.backdrops = nullptr;
+        b.prepare_info.backdrop_count = 0;
+        b.prepare_info.propagate_metadata = s->clip_propagate_metadata.data();
+        b.prepare_info.dice_metadata = s->clip_dice_metadata.data();
+        b.prepare_info.tile_path_info = s->clip_tile_path_info.data();
+        b.prepare_info.transform.matrix = PFMatrix2x2F{xf.m11, xf.m12, xf.m21, xf.m22};
+        b.prepare_info.transform.vector = PFVector2F{xf.tx, xf.ty};
+        b.path_source = PF_PATH_SOURCE_CLIP;
+        b.has_clipped_path_info = 0;
+        b.content_key = 0;
+        SEND(prepare);
+    }
     if (!s->propagate_metadata.empty()) {
         PFRenderCommand draw = make_command(PF_RENDER_COMMAND_DRAW_TILES_D3D11);
         PFTileBatchDataD3D11 &b = draw.u.draw_tiles_d3d11.tile_batch_data;
@@ -639,7 +742,8 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         b.prepare_info.transform.matrix = PFMatrix2x2F{xf.m11, xf.m12, xf.m21, xf.m22};
         b.prepare_info.transform.vector = PFVector2F{xf.tx, xf.ty};
         b.path_source = PF_PATH_SOURCE_DRAW;
-        b.has_clipped_path_info = 0;
+        b.has_clipped_path_info = has_clips ? 1 : 0;
+        b.clipped_path_info = PFClippedPathInfo{0, s->built_clipped_path_count, s->built_clipped_tile_count};
         b.content_key = batch_key;
         draw.u.draw_tiles_d3d11.has_color_texture = 0;
         SEND(draw);

@@ -26,6 +26,10 @@ class FlatScene:
     view_box: tuple               # (min_x, min_y, max_x, max_y)
     name: str = ""
     meta: dict = field(default_factory=dict)
+    # Clip paths (optional): their contours follow the draw paths' contours in the same pools.
+    clip_contour_ranges: np.ndarray | None = None  # (n_clip_paths, 2) uint32 contour ranges
+    clip_fill_rules: np.ndarray | None = None      # (n_clip_paths,) uint8
+    draw_clip_paths: np.ndarray | None = None      # (n_paths,) uint32 clip path id, NO_CLIP = none
 
     def __post_init__(self):
         self.points = np.ascontiguousarray(self.points, dtype=np.float32).reshape(-1, 2)
@@ -38,12 +42,25 @@ class FlatScene:
         self.view_box = tuple(float(v) for v in self.view_box)
         assert len(self.points) == len(self.point_flags)
         assert int(self.contour_offsets[-1]) == len(self.points)
-        assert int(self.path_contour_offsets[-1]) == len(self.contour_offsets) - 1
         assert len(self.fill_rules) == self.n_paths and len(self.paints) == self.n_paths
+        if self.clip_contour_ranges is None:
+            assert int(self.path_contour_offsets[-1]) == len(self.contour_offsets) - 1
+            self.clip_contour_ranges = np.zeros((0, 2), dtype=np.uint32)
+            self.clip_fill_rules = np.zeros(0, dtype=np.uint8)
+        self.clip_contour_ranges = np.ascontiguousarray(self.clip_contour_ranges, dtype=np.uint32).reshape(-1, 2)
+        self.clip_fill_rules = np.ascontiguousarray(self.clip_fill_rules, dtype=np.uint8)
+        if self.draw_clip_paths is None:
+            self.draw_clip_paths = np.full(self.n_paths, NO_CLIP, dtype=np.uint32)
+        self.draw_clip_paths = np.ascontiguousarray(self.draw_clip_paths, dtype=np.uint32)
+        assert len(self.draw_clip_paths) == self.n_paths and len(self.clip_fill_rules) == self.n_clip_paths
 
     @property
     def n_paths(self) -> int:
         return len(self.path_contour_offsets) - 1
+
+    @property
+    def n_clip_paths(self) -> int:
+        return len(self.clip_contour_ranges)
 
     @property
     def n_contours(self) -> int:
@@ -92,6 +109,8 @@ class SceneBuilderPy:
         self._paint_colors: list = []
         self._paint_cache: dict = {}
         self._open = False
+        self._clip_paths: list = []   # (points, flags, local contour offsets, fill rule)
+        self._draw_clip: list = []
 
     def paint(self, rgba) -> int:
         key = tuple(int(v) for v in rgba)
@@ -126,14 +145,38 @@ class SceneBuilderPy:
             self._contour_offsets.append(len(self._points))
         self._open = False
 
-    def end_path(self, rgba, fill_rule=FILL_RULE_WINDING):
+    def end_path(self, rgba, fill_rule=FILL_RULE_WINDING, clip=NO_CLIP):
         self._end_contour()
         self._path_contour_offsets.append(len(self._contour_offsets) - 1)
         self._fill_rules.append(fill_rule)
         self._paints.append(self.paint(rgba))
+        self._draw_clip.append(clip)
+
+    def end_clip_path(self, fill_rule=FILL_RULE_WINDING) -> int:
+        """Turns the contours drawn since the last end_path / end_clip_path into a clip path
+        (Scene::push_clip_path) and returns its id, to be passed as end_path(..., clip=id)."""
+        self._end_contour()
+        c0 = self._path_contour_offsets[-1]
+        p0 = self._contour_offsets[c0]
+        local = [o - p0 for o in self._contour_offsets[c0:]]
+        self._clip_paths.append((self._points[p0:], self._flags[p0:], local, fill_rule))
+        del self._points[p0:], self._flags[p0:], self._contour_offsets[c0 + 1:]
+        return len(self._clip_paths) - 1
 
     def finish(self, name="") -> FlatScene:
         self._end_contour()
-        return FlatScene(np.asarray(self._points, dtype=np.float32).reshape(-1, 2), self._flags,
-                         self._contour_offsets, self._path_contour_offsets, self._fill_rules, self._paints,
-                         np.asarray(self._paint_colors, dtype=np.uint8).reshape(-1, 4), self.view_box, name)
+        points, flags, contour_offsets = list(self._points), list(self._flags), list(self._contour_offsets)
+        clip_ranges, clip_rules = [], []
+        for cp_points, cp_flags, local, rule in self._clip_paths:  # clip contours follow the draw contours
+            base, c0 = len(points), len(contour_offsets) - 1
+            points += cp_points
+            flags += cp_flags
+            contour_offsets += [base + o for o in local[1:]]
+            clip_ranges.append((c0, len(contour_offsets) - 1))
+            clip_rules.append(rule)
+        return FlatScene(np.asarray(points, dtype=np.float32).reshape(-1, 2), flags,
+                         contour_offsets, self._path_contour_offsets, self._fill_rules, self._paints,
+                         np.asarray(self._paint_colors, dtype=np.uint8).reshape(-1, 4), self.view_box, name,
+                         clip_contour_ranges=np.asarray(clip_ranges, dtype=np.uint32).reshape(-1, 2) if clip_ranges else None,
+                         clip_fill_rules=np.asarray(clip_rules, dtype=np.uint8) if clip_ranges else None,
+                         draw_clip_paths=np.asarray(self._draw_clip, dtype=np.uint32) if clip_ranges else None)

@@ -132,3 +132,50 @@ def test_unsupported_options_are_refused():
     with pytest.raises(L.PathfinderCudaError) as e:
         collect(api.Scene.from_flat(flat), api.BuildOptions(subpixel_aa_enabled=True))
     assert e.value.status == L.PF_CUDA_ERROR_UNSUPPORTED
+
+
+def test_clip_batch_commands():
+    """A scene with clipped draw paths emits PrepareClipTilesD3D11 before DrawTilesD3D11 (builder.rs:1098-1104);
+    the draw batch's propagate metadata points into the clip batch and carries clipped_path_info."""
+    from pathfinder_b200 import _lib as L
+    from pathfinder_b200 import api
+    from pathfinder_b200.flat_scene import SceneBuilderPy
+    b = SceneBuilderPy((0, 0, 128, 128))
+    b.move_to(10, 10); b.line_to(100, 20); b.line_to(50, 110); b.close()
+    unused = b.end_clip_path()
+    b.move_to(20, 20); b.line_to(120, 20); b.line_to(120, 120); b.line_to(20, 120); b.close()
+    used = b.end_clip_path()
+    b.move_to(0, 0); b.line_to(64, 0); b.line_to(64, 64); b.close()
+    b.end_path((255, 0, 0, 255))
+    b.move_to(0, 0); b.line_to(128, 0); b.line_to(128, 128); b.line_to(0, 128); b.close()
+    b.end_path((0, 255, 0, 255), clip=used)
+    flat = b.finish()
+    assert unused == 0 and used == 1
+    scene = api.Scene.from_flat(flat)
+    seen = []
+
+    def listener(cmd):
+        kind = int(cmd.kind)
+        seen.append(kind)
+        if kind == L.PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11:
+            u = cmd.u.upload_scene_d3d11
+            assert u.clip_segments.index_count == 3 + 4 and u.draw_segments.index_count == 3 + 4
+        if kind == L.PF_RENDER_COMMAND_PREPARE_CLIP_TILES_D3D11:
+            batch = cmd.u.prepare_clip_tiles_d3d11.batch
+            assert batch.path_count == 1 and batch.path_source == 1
+            pm = C.cast(batch.prepare_info.propagate_metadata, C.POINTER(L.PFPropagateMetadataD3D11))[0]
+            dm = C.cast(batch.prepare_info.dice_metadata, C.POINTER(L.PFDiceMetadataD3D11))
+            assert (pm.tile_rect.origin.x, pm.tile_rect.origin.y, pm.tile_rect.lower_right.x, pm.tile_rect.lower_right.y) == (1, 1, 8, 8)
+            assert batch.tile_count == 49 and batch.segment_count == 4
+            assert dm[0].global_path_id == used
+            assert dm[0].first_global_segment_index == 3  # after the unused clip path
+        if kind == L.PF_RENDER_COMMAND_DRAW_TILES_D3D11:
+            batch = cmd.u.draw_tiles_d3d11.tile_batch_data
+            assert batch.has_clipped_path_info == 1
+            assert batch.clipped_path_info.clipped_path_count == 1 and batch.clipped_path_info.max_clipped_tile_count == 64
+            pms = C.cast(batch.prepare_info.propagate_metadata, C.POINTER(L.PFPropagateMetadataD3D11))
+            assert pms[0].clip_path_index == 0xFFFFFFFF and pms[1].clip_path_index == 0
+
+    scene.build(api.BuildOptions(), listener)
+    i_clip = seen.index(L.PF_RENDER_COMMAND_PREPARE_CLIP_TILES_D3D11)
+    assert seen.index(L.PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11) < i_clip < seen.index(L.PF_RENDER_COMMAND_DRAW_TILES_D3D11)
