@@ -347,6 +347,11 @@ int64_t PFCudaRendererDebugCopyFills(PFCudaRendererRef renderer, PFFill *out, si
 /* Non-empty tiles in path order, row-major inside a path (DrawTileBatchD3D9.tiles,
  * renderer/src/builder.rs:1013-1019), path_id = global draw path id. */
 int64_t PFCudaRendererDebugCopyTiles(PFCudaRendererRef renderer, PFTileObjectPrimitive *out, size_t cap);
+/* Clip records of the batch (DrawTileBatchD3D9.clips, renderer/src/builder.rs:1031-1040): one per draw tile
+ * whose mask is min-combined with a clip tile's mask, in tile order. With clipped paths the fill list starts
+ * with the clip paths' fills and alpha tile ids count the clip tiles first (SequentialExecutor order; the clip
+ * batch holds the clip paths that are used, in order of first use). */
+int64_t PFCudaRendererDebugCopyClips(PFCudaRendererRef renderer, PFClip *out, size_t cap);
 /* Z-buffer over the framebuffer tile rect (DrawTileBatchD3D9.z_buffer_data). rect_out = min_x,
  * min_y, max_x, max_y in tiles. */
 int64_t PFCudaRendererDebugCopyZBuffer(PFCudaRendererRef renderer, int32_t *out, size_t cap,

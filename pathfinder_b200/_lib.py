@@ -223,6 +223,7 @@ SIGNATURES = {
     "PFCudaRendererDebugCopyLines": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "PFCudaRendererDebugCopyFills": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "PFCudaRendererDebugCopyTiles": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "PFCudaRendererDebugCopyClips": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "PFCudaRendererDebugCopyZBuffer": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32 * 4)]),
     "PFCudaRendererDebugCopyAlphaMasks": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "PFSceneCreate": (C.c_void_p, []),

@@ -19,6 +19,7 @@ from .flat_scene import FlatScene
 FILL_DTYPE = np.dtype([("from_x", "<u2"), ("from_y", "<u2"), ("to_x", "<u2"), ("to_y", "<u2"), ("link", "<u4")])
 TILE_DTYPE = np.dtype([("tile_x", "<i2"), ("tile_y", "<i2"), ("alpha_tile_id", "<u4"), ("path_id", "<u4"),
                        ("color", "<u2"), ("ctrl", "u1"), ("backdrop", "i1")])
+CLIP_DTYPE = np.dtype([("dest_tile_id", "<u4"), ("dest_backdrop", "<i4"), ("src_tile_id", "<u4"), ("src_backdrop", "<i4")])
 
 
 class RendererLevel:
@@ -307,6 +308,14 @@ class CudaRenderer:
         out = np.zeros(n, dtype=TILE_DTYPE)
         if n:
             self._count(lib.PFCudaRendererDebugCopyTiles(self._h, out.ctypes.data, n))
+        return out
+
+    def debug_clips(self) -> np.ndarray:
+        lib = L.lib()
+        n = self._count(lib.PFCudaRendererDebugCopyClips(self._h, None, 0))
+        out = np.zeros(n, dtype=CLIP_DTYPE)
+        if n:
+            self._count(lib.PFCudaRendererDebugCopyClips(self._h, out.ctypes.data, n))
         return out
 
     def debug_z_buffer(self):

@@ -825,7 +825,8 @@ int launch_sum_fill_counts(const uint32_t *tile_word, uint32_t n_tiles, unsigned
 template <bool HAS_CLIP>
 __global__ void __launch_bounds__(128)
     k_propagate(BatchDev b, uint32_t *__restrict__ tile_word, const int32_t *__restrict__ col_backdrop,
-                int32_t *__restrict__ z_buffer, ClipDev clip, uint32_t *__restrict__ tile_clip) {
+                int32_t *__restrict__ z_buffer, ClipDev clip, uint32_t *__restrict__ tile_clip,
+                uint32_t *__restrict__ tile_orig_count) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= b.n_columns) return;
     uint32_t p = search_coarse(b.path_col_offset, b.col_index, c);
@@ -868,6 +869,9 @@ __global__ void __launch_bounds__(128)
                 uint32_t count = word & 0x00ffffffu;
                 int8_t b8 = (int8_t)backdrop; // backdrops[column] as i8   (renderer/src/tiler.rs:112)
                 uint32_t clip_ref = 0;
+                // (parity dumps: the fills of a tile the clip drops stay in the fill list with their alpha tile id)
+                if (HAS_CLIP && tile_orig_count) tile_orig_count[t + (uint32_t)(k * w)] = count;
+                if (HAS_CLIP && !clipped) tile_clip[t + (uint32_t)(k * w)] = 0;
                 if (HAS_CLIP && clipped) {
                     // Tiler::prepare_tiles, the four clip cases (renderer/src/tiler.rs:114-156;
                     // twin: shaders/d3d11/propagate.cs.glsl:142-189).
@@ -904,12 +908,14 @@ __global__ void __launch_bounds__(128)
 }
 
 int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_backdrop, int32_t *z_buffer,
-                     const ClipDev *clip, uint32_t *tile_clip, cudaStream_t stream) {
+                     const ClipDev *clip, uint32_t *tile_clip, uint32_t *tile_orig_count, cudaStream_t stream) {
     if (b.n_columns == 0) return 0;
     if (clip && tile_clip)
-        k_propagate<true><<<div_up(b.n_columns, 128), 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, *clip, tile_clip);
+        k_propagate<true><<<div_up(b.n_columns, 128), 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, *clip,
+                                                                         tile_clip, tile_orig_count);
     else
-        k_propagate<false><<<div_up(b.n_columns, 128), 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, ClipDev{}, nullptr);
+        k_propagate<false><<<div_up(b.n_columns, 128), 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, ClipDev{},
+                                                                          nullptr, nullptr);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -937,7 +943,7 @@ __global__ void __launch_bounds__(256)
     k_list_count(BatchDev b, const uint32_t *__restrict__ tile_word, const int32_t *__restrict__ z_buffer,
                  uint32_t *__restrict__ tile_fb, uint32_t *__restrict__ fb_count,
                  uint32_t *__restrict__ tile_fill_pos, uint32_t *__restrict__ fill_cursor,
-                 uint32_t *__restrict__ path_live, int keep_all_fills) {
+                 uint32_t *__restrict__ path_live, int keep_all_fills, const uint32_t *__restrict__ run_counts) {
     __shared__ uint32_t smem[256 / 32 + 1];
     __shared__ uint32_t s_base;
     const uint32_t base = blockIdx.x * LIST_TILE + threadIdx.x;
@@ -972,7 +978,8 @@ __global__ void __launch_bounds__(256)
         }
         tile_fb[t] = result;
         // Occlusion culling before fill emission: culled tiles get no run (parity dumps keep all).
-        run[r] = (keep_all_fills || result != 0xffffffffu) ? count : 0u;
+        // (parity dumps with clipped paths: tiles dropped by the clip keep the run of their original fills)
+        run[r] = (keep_all_fills || result != 0xffffffffu) ? (run_counts ? __ldg(run_counts + t) & 0x00ffffffu : count) : 0u;
         total += run[r];
     }
     uint32_t block_total;
@@ -991,11 +998,11 @@ __global__ void __launch_bounds__(256)
 
 int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
                       uint32_t *fb_count, uint32_t *tile_fill_pos, uint32_t *fill_cursor, uint32_t *path_live,
-                      bool keep_all_fills, cudaStream_t stream) {
+                      bool keep_all_fills, const uint32_t *run_counts, cudaStream_t stream) {
     if (b.n_tiles == 0) return 0;
     k_list_count<<<div_up(b.n_tiles, LIST_TILE), 256, 0, stream>>>(b, tile_word, z_buffer, tile_fb, fb_count,
                                                                     tile_fill_pos, fill_cursor, path_live,
-                                                                    keep_all_fills ? 1 : 0);
+                                                                    keep_all_fills ? 1 : 0, run_counts);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -1519,16 +1526,17 @@ int launch_alpha_flags(uint32_t n_tiles, const uint32_t *tile_word, const uint32
 }
 
 __global__ void k_alpha_assign(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_first_fill,
-                               const uint32_t *fill_first_scan, uint32_t *tile_alpha_id) {
+                               const uint32_t *fill_first_scan, uint32_t *tile_alpha_id, uint32_t alpha_base) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    tile_alpha_id[t] = (tile_word[t] & 0x00ffffffu) != 0 ? fill_first_scan[tile_first_fill[t]] : 0xffffffffu;
+    tile_alpha_id[t] = (tile_word[t] & 0x00ffffffu) != 0 ? alpha_base + fill_first_scan[tile_first_fill[t]] : 0xffffffffu;
 }
 int launch_alpha_assign(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_first_fill,
-                        const uint32_t *fill_first_scan, uint32_t *tile_alpha_id, cudaStream_t stream) {
+                        const uint32_t *fill_first_scan, uint32_t *tile_alpha_id, uint32_t alpha_base,
+                        cudaStream_t stream) {
     if (n_tiles == 0) return 0;
     k_alpha_assign<<<div_up(n_tiles, 256), 256, 0, stream>>>(n_tiles, tile_word, tile_first_fill, fill_first_scan,
-                                                             tile_alpha_id);
+                                                             tile_alpha_id, alpha_base);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -1574,7 +1582,8 @@ struct TileRecord { // TileObjectPrimitive, gpu_data.rs:264-275
     int8_t backdrop;
 };
 __global__ void k_dump_tiles(BatchDev b, const uint32_t *tile_word, const uint32_t *tile_alpha_id,
-                             const uint32_t *flags, const uint32_t *pos, TileRecord *out) {
+                             const uint32_t *flags, const uint32_t *pos, TileRecord *out, const uint32_t *tile_clip,
+                             const uint32_t *clip_tile_word, const uint32_t *clip_alpha_id) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= b.n_tiles || !flags[t]) return;
     uint32_t p = search_coarse(b.path_tile_offset, b.tile_index, t);
@@ -1589,12 +1598,61 @@ __global__ void k_dump_tiles(BatchDev b, const uint32_t *tile_word, const uint32
     r.color = (uint16_t)(path.paint_ctrl & 0xffff);
     r.ctrl = (uint8_t)((path.paint_ctrl >> 16) & 0xff);
     r.backdrop = (int8_t)(tile_word[t] >> 24);
+    if (tile_clip && tile_clip[t] != 0) { // Tiler::prepare_tiles, renderer/src/tiler.rs:124-141
+        const uint32_t ref = tile_clip[t], ct = (ref & ~TILE_CLIP_REPLACE) - 1u;
+        if (ref & TILE_CLIP_REPLACE) {
+            r.alpha_tile_id = clip_alpha_id[ct];
+            r.backdrop = (int8_t)(clip_tile_word[ct] >> 24);
+        } else {
+            r.backdrop = 0; // moved into the Clip record's dest_backdrop
+        }
+    }
     out[pos[t]] = r;
 }
+
+// Clip records of the D3D9 batch (gpu_data.rs Clip; builder.rs:1031-1040): one per draw tile whose mask is
+// combined with a clip tile's mask, in tile order.
+struct ClipRecord {
+    uint32_t dest_tile_id;
+    int32_t dest_backdrop;
+    uint32_t src_tile_id;
+    int32_t src_backdrop;
+};
+__global__ void k_dump_clip_flags(uint32_t n_tiles, const uint32_t *tile_clip, uint32_t *flags) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    flags[t] = (tile_clip[t] != 0 && !(tile_clip[t] & TILE_CLIP_REPLACE)) ? 1u : 0u;
+}
+__global__ void k_dump_clips(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_alpha_id,
+                             const uint32_t *tile_clip, const uint32_t *clip_tile_word, const uint32_t *clip_alpha_id,
+                             const uint32_t *flags, const uint32_t *pos, ClipRecord *out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles || !flags[t]) return;
+    const uint32_t ct = tile_clip[t] - 1u;
+    out[pos[t]] = ClipRecord{tile_alpha_id[t], (int32_t)(int8_t)(tile_word[t] >> 24), clip_alpha_id[ct],
+                             (int32_t)(int8_t)(clip_tile_word[ct] >> 24)};
+}
+int launch_dump_clip_flags(uint32_t n_tiles, const uint32_t *tile_clip, uint32_t *flags, cudaStream_t stream) {
+    if (n_tiles == 0) return 0;
+    k_dump_clip_flags<<<div_up(n_tiles, 256), 256, 0, stream>>>(n_tiles, tile_clip, flags);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+int launch_dump_clips(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_alpha_id, const uint32_t *tile_clip,
+                      const uint32_t *clip_tile_word, const uint32_t *clip_alpha_id, const uint32_t *flags,
+                      const uint32_t *pos, void *out, cudaStream_t stream) {
+    if (n_tiles == 0) return 0;
+    k_dump_clips<<<div_up(n_tiles, 256), 256, 0, stream>>>(n_tiles, tile_word, tile_alpha_id, tile_clip, clip_tile_word,
+                                                           clip_alpha_id, flags, pos, (ClipRecord *)out);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
 int launch_dump_tiles(const BatchDev &b, const uint32_t *tile_word, const uint32_t *tile_alpha_id,
-                      const uint32_t *flags, const uint32_t *pos, void *out, cudaStream_t stream) {
+                      const uint32_t *flags, const uint32_t *pos, void *out, const uint32_t *tile_clip,
+                      const uint32_t *clip_tile_word, const uint32_t *clip_alpha_id, cudaStream_t stream) {
     if (b.n_tiles == 0) return 0;
-    k_dump_tiles<<<div_up(b.n_tiles, 256), 256, 0, stream>>>(b, tile_word, tile_alpha_id, flags, pos, (TileRecord *)out);
+    k_dump_tiles<<<div_up(b.n_tiles, 256), 256, 0, stream>>>(b, tile_word, tile_alpha_id, flags, pos, (TileRecord *)out,
+                                                             tile_clip, clip_tile_word, clip_alpha_id);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

@@ -135,7 +135,8 @@ constexpr uint32_t ENTRY_HAS_CLIP = 1u << 24, ENTRY_CLIP_REPLACE = 1u << 25;
 
 // clip / tile_clip: NULL unless the batch has clipped paths.
 int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_backdrop, int32_t *z_buffer,
-                     const ClipDev *clip, uint32_t *tile_clip, cudaStream_t stream);
+                     const ClipDev *clip, uint32_t *tile_clip, uint32_t *tile_orig_count, cudaStream_t stream);
+// (tile_orig_count, optional: the fill count of every tile before the clip was applied, for the parity dumps)
 
 // tile_fb[t] = framebuffer tile index if the tile is non-empty, inside the framebuffer and not
 // z-culled, else 0xffffffff; fb_count[fb] += 1 for every survivor.
@@ -143,7 +144,7 @@ int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_
 // start, *fill_cursor += total (keep_all_fills: culled tiles keep their runs, for the parity dumps).
 int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
                       uint32_t *fb_count, uint32_t *tile_fill_pos, uint32_t *fill_cursor, uint32_t *path_live,
-                      bool keep_all_fills, cudaStream_t stream);
+                      bool keep_all_fills, const uint32_t *run_counts, cudaStream_t stream);
 // Device-side totals ([0] lines, [2] entries, [5] visible fills) and the capacities they must fit.
 struct OverflowGuard {
     const uint32_t *totals;
@@ -182,12 +183,19 @@ int launch_composite(const CompositeArgs &args, cudaStream_t stream);
 int launch_alpha_flags(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_first_fill,
                        uint8_t *fill_is_first, cudaStream_t stream);
 int launch_alpha_assign(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_first_fill,
-                        const uint32_t *fill_first_scan, uint32_t *tile_alpha_id, cudaStream_t stream);
+                        const uint32_t *fill_first_scan, uint32_t *tile_alpha_id, uint32_t alpha_base,
+                        cudaStream_t stream);
 int launch_dump_fills(uint32_t n_fills, const EmitFill *fills_emit, const uint32_t *tile_alpha_id, void *out,
                       cudaStream_t stream);
 int launch_dump_tile_flags(uint32_t n_tiles, const uint32_t *tile_word, uint32_t *flags, cudaStream_t stream);
+// tile_clip / clip_tile_word / clip_alpha_id: NULL unless the batch has clipped paths.
 int launch_dump_tiles(const BatchDev &b, const uint32_t *tile_word, const uint32_t *tile_alpha_id,
-                      const uint32_t *flags, const uint32_t *pos, void *out, cudaStream_t stream);
+                      const uint32_t *flags, const uint32_t *pos, void *out, const uint32_t *tile_clip,
+                      const uint32_t *clip_tile_word, const uint32_t *clip_alpha_id, cudaStream_t stream);
+int launch_dump_clip_flags(uint32_t n_tiles, const uint32_t *tile_clip, uint32_t *flags, cudaStream_t stream);
+int launch_dump_clips(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_alpha_id, const uint32_t *tile_clip,
+                      const uint32_t *clip_tile_word, const uint32_t *clip_alpha_id, const uint32_t *flags,
+                      const uint32_t *pos, void *out, cudaStream_t stream);
 int launch_alpha_masks(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_fill_pos,
                        const uint32_t *tile_alpha_id, const PackedFill *fills, cudaTextureObject_t area_lut,
                        float *out, cudaStream_t stream);

@@ -164,7 +164,13 @@ struct PFCudaRenderer {
         DeviceBuffer<uint8_t> meta;              // PathInfo[n_paths]
         DeviceBuffer<uint32_t> tile_word, tile_fill_end;
         DeviceBuffer<PackedFill> fills;
+        // parity dumps: alpha tile ids of the clip tiles (they come first in SequentialExecutor order)
+        // and the clip paths' fills as records
+        DeviceBuffer<uint32_t> tile_alpha_id;
+        DeviceBuffer<uint8_t> fill_records;
+        uint32_t n_fills = 0, n_alpha = 0;
     } clip;
+    DeviceBuffer<uint32_t> tile_orig;  // parity dumps with clips: fill count of every draw tile before the clip
     DeviceBuffer<uint32_t> tile_clip;  // per draw tile: clip tile reference (batches with clipped paths)
     DeviceBuffer<uint2> entry_clip;    // per list entry: {clip fill end, clip tile word}
     DeviceBuffer<PackedFill> fills;
@@ -244,6 +250,9 @@ void setup_tracking(PFCudaRenderer *r) {
     track(r, r->clip.tile_word);
     track(r, r->clip.tile_fill_end);
     track(r, r->clip.fills);
+    track(r, r->clip.tile_alpha_id);
+    track(r, r->clip.fill_records);
+    track(r, r->tile_orig);
     track(r, r->tile_clip);
     track(r, r->entry_clip);
     track(r, r->fills);
@@ -571,6 +580,7 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
 // sized from the previous frame's counts plus slack, and the only sync is the verification at the end.
 // Returns false when a bound was exceeded (the caller re-runs in sizing mode).
 bool finalize_batch(PFCudaRenderer *r);
+void ensure_alpha_ids(PFCudaRenderer *r, const uint32_t *counts = nullptr, uint32_t alpha_base = 0);
 
 // Lays the frame's zero-initialised arrays out in r->zeroed and clears all of them with one memset
 // (eight separate clears cost more in launch gaps than in bandwidth on the small scenes).
@@ -688,9 +698,12 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
         clip_dev.tile_fill_end = r->clip.tile_fill_end.ptr;
         clip_dev.fills = r->clip.fills.ptr;
         r->tile_clip.ensure(n_tiles + 1, 1.25);
+        if (r->debug_lists) r->tile_orig.ensure(n_tiles + 1, 1.25);
     }
+    const bool clip_dumps = use_clip && r->debug_lists;
     launches += launch_propagate(b, r->tile_word.ptr, r->col_backdrop.ptr, r->z_buffer.ptr,
-                                 use_clip ? &clip_dev : nullptr, use_clip ? r->tile_clip.ptr : nullptr, st);
+                                 use_clip ? &clip_dev : nullptr, use_clip ? r->tile_clip.ptr : nullptr,
+                                 clip_dumps ? r->tile_orig.ptr : nullptr, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[4], st));
 
     // ---- sort: z-cull + per-framebuffer-tile runs (count -> scan -> append); the run itself is
@@ -699,7 +712,7 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
     // emission; with the parity dumps on, every alpha tile keeps its fills so its mask can be read back)
     launches += launch_list_count(b, r->tile_word.ptr, r->z_buffer.ptr, r->tile_fb.ptr, r->fb_count.ptr,
                                   r->tile_fill_pos.ptr, r->counters.ptr + C_VISIBLE_FILLS, r->path_live.ptr,
-                                  r->debug_lists, st);
+                                  r->debug_lists, clip_dumps ? r->tile_orig.ptr : nullptr, st);
     launches += exclusive_scan(LoadU32{r->fb_count.ptr}, r->fb_start.ptr, n_fb, r->counters.ptr + C_ENTRIES,
                                r->scan_scratch, st);
     uint32_t entry_bound, fill_bound;
@@ -750,6 +763,23 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
         keep(r->clip.tile_word.ptr, r->tile_word.ptr, (size_t)n_tiles * 4);
         keep(r->clip.tile_fill_end.ptr, r->tile_fill_pos.ptr, (size_t)n_tiles * 4);
         keep(r->clip.fills.ptr, r->fills.ptr, (size_t)fill_bound * sizeof(PackedFill));
+        r->clip.n_fills = r->clip.n_alpha = 0;
+        if (r->debug_lists) {
+            // Parity dumps: number the clip tiles' alpha ids now (clip paths precede draw paths in
+            // SequentialExecutor order) and keep their fills as records.
+            r->last_batch = b;
+            r->last_fills = emit_bound;
+            r->last_alpha_ids_valid = false;
+            ensure_alpha_ids(r, r->tile_word.ptr, 0);
+            r->clip.n_fills = emit_bound;
+            r->clip.n_alpha = r->last_alpha_tiles;
+            r->clip.tile_alpha_id.ensure(n_tiles + 1);
+            r->clip.fill_records.ensure((size_t)emit_bound * sizeof(PFFill) + 16);
+            keep(r->clip.tile_alpha_id.ptr, r->tile_alpha_id.ptr, (size_t)n_tiles * 4);
+            launch_dump_fills(emit_bound, r->fills_emit.ptr, r->tile_alpha_id.ptr, r->clip.fill_records.ptr, st);
+            r->last_alpha_ids_valid = false;
+            r->stats.fill_count += emit_bound;
+        }
         PF_CUDA_CHECK(cudaStreamSynchronize(st)); // (the clip pass always runs with exact sizes, synchronously)
         r->stats.host_sync_count++;
         r->stats.drawcall_count += (uint64_t)launches;
@@ -891,8 +921,6 @@ void prepare_clip_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     if (batch.has_clipped_path_info && batch.clipped_path_info.clipped_path_count > 0)
         throw Error(PF_CUDA_ERROR_UNSUPPORTED, "nested clip paths are not implemented");
     if (r->clip.valid) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "more than one clip batch per frame (nested clip levels)");
-    if (r->debug_lists)
-        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "the parity dumps do not cover clipped paths yet (SURVEY.md §8 f1)");
     const FbRect fb = framebuffer_tile_rect(r);
     const int32_t strip_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
     const int32_t strip_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
@@ -913,8 +941,6 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     const bool has_clips = batch.has_clipped_path_info && batch.clipped_path_info.clipped_path_count > 0;
     if (has_clips && !r->clip.valid)
         throw Error(PF_CUDA_ERROR_PROTOCOL, "draw batch with clipped paths before PrepareClipTilesD3D11");
-    if (has_clips && r->debug_lists)
-        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "the parity dumps do not cover clipped paths yet (SURVEY.md §8 f1)");
     const FbRect fb = framebuffer_tile_rect(r);
     const int32_t strip_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
     const int32_t strip_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
@@ -963,8 +989,15 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
 }
 
 // Alpha tile ids in SequentialExecutor order for the last batch (needs debug lists).
-void ensure_alpha_ids(PFCudaRenderer *r) {
+// `counts`: where the tiles' fill counts are read from (NULL: the tile words, or with clipped paths the
+// counts before the clip was applied); `alpha_base`: ids already taken by the clip batch.
+void ensure_alpha_ids(PFCudaRenderer *r, const uint32_t *counts, uint32_t alpha_base) {
     if (r->last_alpha_ids_valid) return;
+    if (!counts) {
+        const bool clipped = r->cache.has_clips && r->clip.valid;
+        counts = clipped ? r->tile_orig.ptr : r->tile_word.ptr;
+        alpha_base = clipped ? r->clip.n_alpha : 0;
+    }
     if (!r->debug_lists) throw Error(PF_CUDA_ERROR_PROTOCOL, "enable debug lists before rendering to read alpha tile ids");
     cudaStream_t st = r->stream;
     const uint32_t n_tiles = r->last_batch.n_tiles, n_fills = r->last_fills;
@@ -972,11 +1005,11 @@ void ensure_alpha_ids(PFCudaRenderer *r) {
     r->fill_first_scan.ensure(n_fills + 1, 1.25);
     r->tile_alpha_id.ensure(n_tiles + 1, 1.25);
     PF_CUDA_CHECK(cudaMemsetAsync(r->fill_is_first.ptr, 0, n_fills, st));
-    launch_alpha_flags(n_tiles, r->tile_word.ptr, r->tile_first_fill.ptr, r->fill_is_first.ptr, st);
+    launch_alpha_flags(n_tiles, counts, r->tile_first_fill.ptr, r->fill_is_first.ptr, st);
     exclusive_scan(LoadU8{r->fill_is_first.ptr}, r->fill_first_scan.ptr, n_fills, r->counters.ptr + 3,
                    r->scan_scratch, st);
-    launch_alpha_assign(n_tiles, r->tile_word.ptr, r->tile_first_fill.ptr, r->fill_first_scan.ptr,
-                        r->tile_alpha_id.ptr, st);
+    launch_alpha_assign(n_tiles, counts, r->tile_first_fill.ptr, r->fill_first_scan.ptr, r->tile_alpha_id.ptr,
+                        alpha_base, st);
     r->last_alpha_tiles = n_fills ? read_counter(r, 3) : 0;
     r->last_alpha_ids_valid = true;
 }
@@ -1365,7 +1398,7 @@ PFCudaStatus PFCudaRendererGetStats(PFCudaRendererRef r, PFCudaRenderStats *stat
         *stats = r->stats;
         if (r->debug_lists && r->batches_drawn > 0 && !r->in_scene) {
             ensure_alpha_ids(r);
-            stats->alpha_tile_count = r->last_alpha_tiles;
+            stats->alpha_tile_count = r->last_alpha_tiles + ((r->cache.has_clips && r->clip.valid) ? r->clip.n_alpha : 0);
         }
     });
 }
@@ -1411,11 +1444,17 @@ int64_t PFCudaRendererDebugCopyLines(PFCudaRendererRef r, float *out_lines, uint
 int64_t PFCudaRendererDebugCopyFills(PFCudaRendererRef r, PFFill *out, size_t cap) {
     return guarded_count(r, [&]() -> int64_t {
         verify_pending(r);
-        size_t n = r->last_fills, m = n < cap ? n : cap;
+        // With clipped paths the clip paths' fills come first (SequentialExecutor order: clip paths, then draw paths).
+        const size_t n_clip = (r->cache.has_clips && r->clip.valid) ? r->clip.n_fills : 0;
+        size_t n = n_clip + r->last_fills, m = n < cap ? n : cap;
         if (out && m) {
             ensure_alpha_ids(r);
             r->dump_out.ensure(n * sizeof(PFFill) + 16, 1.25);
-            launch_dump_fills((uint32_t)n, r->fills_emit.ptr, r->tile_alpha_id.ptr, r->dump_out.ptr, r->stream);
+            if (n_clip)
+                PF_CUDA_CHECK(cudaMemcpyAsync(r->dump_out.ptr, r->clip.fill_records.ptr, n_clip * sizeof(PFFill),
+                                              cudaMemcpyDeviceToDevice, r->stream));
+            launch_dump_fills(r->last_fills, r->fills_emit.ptr, r->tile_alpha_id.ptr,
+                              r->dump_out.ptr + n_clip * sizeof(PFFill), r->stream);
             PF_CUDA_CHECK(cudaMemcpyAsync(out, r->dump_out.ptr, m * sizeof(PFFill), cudaMemcpyDeviceToHost, r->stream));
             PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
         }
@@ -1428,6 +1467,7 @@ int64_t PFCudaRendererDebugCopyTiles(PFCudaRendererRef r, PFTileObjectPrimitive 
         verify_pending(r);
         ensure_alpha_ids(r);
         const BatchDev &b = r->last_batch;
+        const bool clipped = r->cache.has_clips && r->clip.valid;
         // tile_fb is free again after the sort stage: reuse it for the non-empty flags.
         r->tile_pos.ensure(b.n_tiles + 1, 1.25);
         launch_dump_tile_flags(b.n_tiles, r->tile_word.ptr, r->tile_fb.ptr, r->stream);
@@ -1436,8 +1476,33 @@ int64_t PFCudaRendererDebugCopyTiles(PFCudaRendererRef r, PFTileObjectPrimitive 
         size_t m = n < cap ? n : cap;
         if (out && m) {
             r->dump_out.ensure(n * sizeof(PFTileObjectPrimitive) + 16, 1.25);
-            launch_dump_tiles(b, r->tile_word.ptr, r->tile_alpha_id.ptr, r->tile_fb.ptr, r->tile_pos.ptr, r->dump_out.ptr, r->stream);
+            launch_dump_tiles(b, r->tile_word.ptr, r->tile_alpha_id.ptr, r->tile_fb.ptr, r->tile_pos.ptr, r->dump_out.ptr,
+                              clipped ? r->tile_clip.ptr : nullptr, clipped ? r->clip.tile_word.ptr : nullptr,
+                              clipped ? r->clip.tile_alpha_id.ptr : nullptr, r->stream);
             PF_CUDA_CHECK(cudaMemcpyAsync(out, r->dump_out.ptr, m * sizeof(PFTileObjectPrimitive), cudaMemcpyDeviceToHost, r->stream));
+            PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        }
+        return (int64_t)n;
+    });
+}
+
+// The Clip records of the D3D9 batch (gpu_data.rs Clip, builder.rs:1031-1040), in tile order.
+int64_t PFCudaRendererDebugCopyClips(PFCudaRendererRef r, PFClip *out, size_t cap) {
+    return guarded_count(r, [&]() -> int64_t {
+        verify_pending(r);
+        if (!(r->cache.has_clips && r->clip.valid)) return 0;
+        ensure_alpha_ids(r);
+        const BatchDev &b = r->last_batch;
+        r->tile_pos.ensure(b.n_tiles + 1, 1.25);
+        launch_dump_clip_flags(b.n_tiles, r->tile_clip.ptr, r->tile_fb.ptr, r->stream);
+        exclusive_scan(LoadU32{r->tile_fb.ptr}, r->tile_pos.ptr, b.n_tiles, r->counters.ptr + 4, r->scan_scratch, r->stream);
+        size_t n = b.n_tiles ? read_counter(r, 4) : 0;
+        size_t m = n < cap ? n : cap;
+        if (out && m) {
+            r->dump_out.ensure(n * sizeof(PFClip) + 16, 1.25);
+            launch_dump_clips(b.n_tiles, r->tile_word.ptr, r->tile_alpha_id.ptr, r->tile_clip.ptr, r->clip.tile_word.ptr,
+                              r->clip.tile_alpha_id.ptr, r->tile_fb.ptr, r->tile_pos.ptr, r->dump_out.ptr, r->stream);
+            PF_CUDA_CHECK(cudaMemcpyAsync(out, r->dump_out.ptr, m * sizeof(PFClip), cudaMemcpyDeviceToHost, r->stream));
             PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
         }
         return (int64_t)n;
@@ -1463,6 +1528,8 @@ int64_t PFCudaRendererDebugCopyZBuffer(PFCudaRendererRef r, int32_t *out, size_t
 int64_t PFCudaRendererDebugCopyAlphaMasks(PFCudaRendererRef r, float *out, size_t cap_tiles) {
     return guarded_count(r, [&]() -> int64_t {
         verify_pending(r);
+        if (r->cache.has_clips && r->clip.valid)
+            throw Error(PF_CUDA_ERROR_UNSUPPORTED, "alpha mask dumps do not cover clipped paths");
         ensure_alpha_ids(r);
         size_t n = r->last_alpha_tiles;
         if (out && n) {

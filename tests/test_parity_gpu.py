@@ -401,16 +401,28 @@ def clip_scene(size=256, n_draw=40, seed=5):
 
 @pytest.mark.parametrize("size", [256, 1024])
 def test_clip_paths(area_lut, size):
-    """Pixels of a clipped scene against the oracle's CPU tiler + D3D9 clip combine (tiler.rs:114-156,
-    tile_clip_combine.fs.glsl:28-31). (The emission-ordered list dumps do not cover clips yet.)"""
+    """A clipped scene against the oracle's CPU tiler + D3D9 clip combine (tiler.rs:114-156,
+    tile_clip_combine.fs.glsl:28-31): fills (clip paths first), tiles, Clip records and z-buffer bit-exact,
+    pixels within 1/255. Both clip paths are used, in scene order, so the D3D11 clip batch (used clip paths in
+    order of first use) numbers alpha tiles like the CPU tiler (all clip paths in scene order)."""
     from pathfinder_b200 import api
     flat = clip_scene(size)
     built = H.oracle_build(flat, None)
     assert len(built.clips) > 0
     ref = built.render(area_lut, size, size, background=(1.0, 1.0, 1.0, 1.0))
+    rd, img_debug = H.cuda_render(flat, None, size=(size, size), background=(1.0, 1.0, 1.0, 1.0), debug=True)
+    H.assert_records_equal(rd.debug_fills(), built.fills, "fills")
+    H.assert_records_equal(rd.debug_tiles(), built.tiles, "tiles")
+    H.assert_records_equal(rd.debug_clips(), built.clips, "clips")
+    z, rect = rd.debug_z_buffer()
+    assert rect == built.z_rect and np.array_equal(z, built.z_buffer)
+    st = rd.stats()
+    assert st["alpha_tile_count"] == built.alpha_tile_count and st["fill_count"] == len(built.fills)
     r, img = H.cuda_render(flat, None, size=(size, size), background=(1.0, 1.0, 1.0, 1.0), debug=False)
     diff = np.abs(img.astype(np.int32) - ref.astype(np.int32))
     assert diff.max() <= RGBA_TOL, f"max RGBA diff {diff.max()} at {np.unravel_index(diff.argmax(), diff.shape)}"
+    assert np.array_equal(img_debug, img), "production path differs from the instrumented path"
+    rd.close()
     # the clip really matters: the same draw paths without their clip paths render differently
     import dataclasses
     unclipped = dataclasses.replace(flat, draw_clip_paths=np.full(flat.n_paths, 0xFFFFFFFF, np.uint32))
