@@ -219,3 +219,50 @@ def test_golden_tools_round_trip(tmp_path):
     open(b, "w").write("\n".join(lines) + "\n")
     assert run("tools/diff_lists.py", a, b).returncode == 1
     assert open(scene).readline().startswith("viewbox ")
+
+
+def _clip_scene(clip_kind):
+    b = SceneBuilderPy((0, 0, 128, 128))
+    if clip_kind == "cover":      # covers the whole view box: clipping changes nothing
+        b.move_to(-10, -10); b.line_to(138, -10); b.line_to(138, 138); b.line_to(-10, 138); b.close()
+    elif clip_kind == "miss":     # lies outside every draw tile: everything is clipped away
+        b.move_to(100, 100); b.line_to(126, 100); b.line_to(126, 126); b.line_to(100, 126); b.close()
+    else:                         # a diamond through the middle of the draw paths
+        b.move_to(64, 6); b.line_to(122, 64); b.line_to(64, 122); b.line_to(6, 64); b.close()
+    clip = b.end_clip_path()
+    b.move_to(8, 8); b.line_to(90, 12); b.line_to(80, 88); b.line_to(12, 70); b.close()
+    b.end_path((200, 30, 30, 255), clip=clip)
+    b.move_to(20, 20); b.cubic_to(90, 0, 100, 90, 30, 80); b.close()
+    b.end_path((30, 30, 200, 160), clip=clip)
+    return b.finish(clip_kind)
+
+
+def test_clip_path_cases(area_lut):
+    """Tiler::prepare_tiles clip cases (renderer/src/tiler.rs:114-156) + D3D9 clip combine, through properties:
+    a clip path covering everything leaves the frame unchanged, one that misses every draw tile erases it, and
+    a partial clip equals the unclipped frame inside the clip path and the background outside, away from its edge."""
+    import dataclasses
+    bg = (1.0, 1.0, 1.0, 1.0)
+    flat = _clip_scene("cover")
+    unclipped = dataclasses.replace(flat, draw_clip_paths=np.full(flat.n_paths, 0xFFFFFFFF, np.uint32))
+    ref = H.oracle_build(unclipped).render(area_lut, 128, 128, background=bg)
+    covered = H.oracle_build(flat)
+    assert np.array_equal(covered.render(area_lut, 128, 128, background=bg), ref)
+    assert len(covered.clips) == 0  # the clip path has no alpha tile under the draw paths
+
+    missed = H.oracle_build(_clip_scene("miss"))
+    assert len(missed.tiles) == 0
+    assert (missed.render(area_lut, 128, 128, background=bg) == 255).all()
+
+    part = H.oracle_build(_clip_scene("diamond"))
+    assert len(part.clips) > 0
+    img = part.render(area_lut, 128, 128, background=bg).astype(np.int32)
+    yy, xx = np.mgrid[0:128, 0:128]
+    d = np.abs(xx + 0.5 - 64) + np.abs(yy + 0.5 - 64)   # L1 distance from the diamond's centre (radius 58)
+    inside, outside = d < 55, d > 61
+    assert np.abs(img[inside] - ref.astype(np.int32)[inside]).max() <= 1
+    assert (img[outside] >= 254).all()  # (the LUT's 1/32 px bias leaves 1 LSB at a few tile-edge columns)
+    # every Clip record joins two alpha tiles that exist, and the combined tiles carry a zero backdrop
+    assert part.clips["dest_tile_id"].max() < part.alpha_tile_count and part.clips["src_tile_id"].max() < part.alpha_tile_count
+    combined = part.tiles[np.isin(part.tiles["alpha_tile_id"], part.clips["dest_tile_id"])]
+    assert (combined["backdrop"] == 0).all()
