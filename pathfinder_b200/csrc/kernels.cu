@@ -11,10 +11,11 @@
 //              geometry/src/transform2d.rs:123-130,312-318
 //   bin        renderer/src/tiler.rs:191-308, content/src/clip.rs:494-565,
 //              renderer/src/builder.rs:509-616
-//   propagate  renderer/src/tiler.rs:93-163 (backdrop prefix), builder.rs:1013-1029 (z-buffer)
+//   propagate  renderer/src/tiler.rs:93-163 (backdrop prefix, clip cases), builder.rs:1013-1029 (z-buffer)
 //   sort       shaders/d3d11/sort.cs.glsl:60-95 (painter's order + z-cull)
 //   fill       shaders/fill_area.inc.glsl:11-27, shaders/d3d11/fill_compute.inc.glsl:11-25
-//   tile       shaders/d3d11/tile.cs.glsl:71-163, shaders/tile_fragment.inc.glsl:539-614
+//   tile       shaders/d3d11/tile.cs.glsl:71-163, shaders/tile_fragment.inc.glsl:539-614,
+//              shaders/d3d9/tile_clip_combine.fs.glsl:28-31 (clip mask combine)
 #include "kernels.cuh"
 
 #include "common.cuh"

@@ -4,10 +4,15 @@
 // Replaces RendererD3D11::{upload_scene, prepare_tiles, draw_tiles} (renderer/src/gpu/d3d11/
 // renderer.rs:236-241,427-542,711-782) and Renderer::{begin_scene, render_command, end_scene}
 // (renderer/src/gpu/renderer.rs:350-460). Differences by design:
-//   * every stage is count -> scan -> emit, so there is no overflow/retry loop and allocation is
-//     exact (the reference re-runs dice/bin with doubled buffers, d3d11/renderer.rs:463-499);
-//   * fill and tile are one kernel (the alpha mask never reaches HBM);
-//   * tile lists are sorted by a device radix sort instead of per-tile linked lists.
+//   * the first frame of a batch is count -> scan -> emit with exact allocation; later frames keep the
+//     counts on the device, size grids from the previous frame and verify once at the end, so there
+//     is no overflow/retry loop per stage (the reference re-runs dice/bin with doubled buffers,
+//     d3d11/renderer.rs:463-499) and at most one host wait per frame (none with deferred verification);
+//   * occlusion culling happens before fill emission; fill and tile are one kernel (the alpha mask
+//     never reaches HBM);
+//   * per-framebuffer-tile lists are runs from a count + scan, rank-sorted inside the fused kernel,
+//     instead of per-tile linked lists with an insertion sort;
+//   * clip paths (one level) are a second batch through the same stages, resolved in propagate.
 #include <cuda.h>
 #include <cuda_fp16.h>
 

@@ -66,6 +66,18 @@ class FlatScene:
     def n_contours(self) -> int:
         return len(self.contour_offsets) - 1
 
+    def palette(self):
+        """(paint id per path, colour table) as Scene::push_paint assigns them: equal colours share one id,
+        ids in order of first appearance in the table (Palette::push_paint, renderer/src/paint.rs:115-131)."""
+        colors = np.ascontiguousarray(self.paint_colors, dtype=np.uint8).reshape(-1, 4)
+        keys = colors.view(np.uint32).reshape(-1)
+        _, first, inverse = np.unique(keys, return_index=True, return_inverse=True)
+        order = np.argsort(first)                 # unique colours in order of first appearance
+        rank = np.empty_like(order)
+        rank[order] = np.arange(len(order))
+        remap = rank[inverse].astype(np.uint16)   # table index -> deduplicated paint id
+        return remap[self.paints], colors[np.sort(first)]
+
     def contour_ranges(self) -> np.ndarray:
         return np.stack([self.path_contour_offsets[:-1], self.path_contour_offsets[1:]], axis=1).astype(np.uint32)
 

@@ -8,9 +8,11 @@ from pathfinder_b200.flat_scene import FlatScene
 
 
 def oracle_scene(flat: FlatScene) -> O.OracleScene:
+    # Paint ids as Scene::push_paint assigns them (equal colours share an id), like the CUDA-side Scene.
+    paints, paint_colors = flat.palette()
     return O.make_scene(points=flat.points, point_flags=flat.point_flags, contour_offsets=flat.contour_offsets,
                         draw_contour_ranges=flat.contour_ranges(), draw_fill_rules=flat.fill_rules,
-                        draw_paints=flat.paints, paint_colors=flat.paint_colors, view_box=flat.view_box,
+                        draw_paints=paints, paint_colors=paint_colors, view_box=flat.view_box,
                         clip_contour_ranges=flat.clip_contour_ranges if flat.n_clip_paths else None,
                         clip_fill_rules=flat.clip_fill_rules if flat.n_clip_paths else None,
                         draw_clip_paths=flat.draw_clip_paths if flat.n_clip_paths else None)

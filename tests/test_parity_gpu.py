@@ -309,6 +309,40 @@ def test_full_size_random100k_8192():
     rp.close()
 
 
+def test_full_size_random1m_16384():
+    """configs[4]: 1M random cubic paths at 16384x16384 (the multi-GPU configuration), on one GPU. Tiles, z-buffer
+    and the fill / alpha-tile / line totals bit-exact against the CPU tiler (the 120M-record fill list itself is
+    compared at 100k paths above); the 1 GiB frame through size-independent properties: production path =
+    instrumented path, cached batch = first frame, two of the eight strips = the same rows of the full frame."""
+    from pathfinder_b200 import api
+    size = 16384
+    flat = scenes.random_paths(1000000, size, 0x5EED0005)
+    built = H.oracle_build(flat, None)
+    r, img = H.cuda_render(flat, None, background=(1.0, 1.0, 1.0, 1.0))
+    s = r.stats()
+    assert s["line_segment_count"] == built.line_segment_count
+    assert s["input_segment_count"] == built.input_segment_count
+    assert s["fill_count"] == len(built.fills) and s["alpha_tile_count"] == built.alpha_tile_count
+    H.assert_records_equal(r.debug_tiles(), built.tiles, "tiles")
+    z, _ = r.debug_z_buffer()
+    assert np.array_equal(z, built.z_buffer)
+    r.close()
+    del built
+    rp = api.CudaRenderer((size, size), background_color=(1.0, 1.0, 1.0, 1.0))
+    scene = api.Scene.from_flat(flat)
+    opts = api.BuildOptions()
+    for _ in range(2):
+        scene.build_and_render(rp, opts)
+        assert np.array_equal(rp.read_pixels(), img)
+    rows = size // 16 // 8
+    for g in (0, 5):
+        rp.set_strip(g * rows, (g + 1) * rows)
+        scene.build_and_render(rp, opts)
+        part = rp.read_pixels()
+        assert np.array_equal(part[g * rows * 16:(g + 1) * rows * 16], img[g * rows * 16:(g + 1) * rows * 16])
+    rp.close()
+
+
 def test_edge_inputs(area_lut):
     """Empty and ragged inputs, degenerate geometry, extreme coordinates, maximum winding depth."""
     b = SceneBuilderPy((0, 0, 160, 96))
