@@ -329,6 +329,9 @@ typedef struct PFCudaRenderTime {
 } PFCudaRenderTime;
 PFCudaStatus PFCudaRendererSetTimingEnabled(PFCudaRendererRef renderer, int32_t enabled);
 PFCudaStatus PFCudaRendererGetTimes(PFCudaRendererRef renderer, PFCudaRenderTime *times);
+/* Sums over every batch since timing was switched on (per-frame times are reset by begin_scene; with deferred
+ * verification a caller that never waits inside its loop reads the totals once at the end). */
+PFCudaStatus PFCudaRendererGetAccumulatedTimes(PFCudaRendererRef renderer, PFCudaRenderTime *times, uint32_t *batches);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Stage-level read-backs for parity tests (SURVEY.md §8b "stage-level test hooks"). They copy   */

@@ -219,6 +219,7 @@ SIGNATURES = {
     "PFCudaRendererGetStats": (C.c_int32, [C.c_void_p, C.POINTER(PFCudaRenderStats)]),
     "PFCudaRendererSetTimingEnabled": (C.c_int32, [C.c_void_p, C.c_int32]),
     "PFCudaRendererGetTimes": (C.c_int32, [C.c_void_p, C.POINTER(PFCudaRenderTime)]),
+    "PFCudaRendererGetAccumulatedTimes": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "PFCudaRendererSetDebugListsEnabled": (C.c_int32, [C.c_void_p, C.c_int32]),
     "PFCudaRendererDebugCopyLines": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "PFCudaRendererDebugCopyFills": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t]),

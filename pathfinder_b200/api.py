@@ -278,6 +278,12 @@ class CudaRenderer:
         L.check(L.lib().PFCudaRendererGetTimes(self._h, C.byref(t)))
         return {n: float(getattr(t, n)) for n, _ in t._fields_}
 
+    def accumulated_times(self):
+        """(stage times summed over every batch since timing was switched on, number of batches)."""
+        t, n = L.PFCudaRenderTime(), C.c_uint32()
+        L.check(L.lib().PFCudaRendererGetAccumulatedTimes(self._h, C.byref(t), C.byref(n)))
+        return {k: float(getattr(t, k)) for k, _ in t._fields_}, int(n.value)
+
     # -- stage-level read-backs (parity tests) --------------------------------------------------
     @staticmethod
     def _count(n: int) -> int:

@@ -211,7 +211,9 @@ struct PFCudaRenderer {
     bool timing = false;
     int batches_drawn = 0;
     PFCudaRenderStats stats{};
-    PFCudaRenderTime times{};
+    PFCudaRenderTime times{};       // the current frame
+    PFCudaRenderTime times_total{}; // every batch since timing was switched on
+    uint32_t times_batches = 0;
     StageTimer timer;
 
     // scene.view_box(): what process_line_segment clips to (renderer/src/tiler.rs:194). Defaults to
@@ -891,6 +893,15 @@ bool finalize_batch(PFCudaRenderer *r) {
         float total;
         PF_CUDA_CHECK(cudaEventElapsedTime(&total, r->timer.ev[0], r->timer.ev[7]));
         r->times.total_ms += total;
+        // since timing was switched on (not reset per frame: frames verified late still count)
+        r->times_total.bound_ms += ms[0];
+        r->times_total.dice_ms += ms[1];
+        r->times_total.bin_ms += ms[2] + ms[5];
+        r->times_total.propagate_ms += ms[3];
+        r->times_total.sort_ms += ms[4];
+        r->times_total.fill_tile_ms += ms[6];
+        r->times_total.total_ms += total;
+        r->times_batches++;
     }
     return true;
 }
@@ -1416,7 +1427,20 @@ PFCudaStatus PFCudaRendererSetDeferredVerification(PFCudaRendererRef r, int32_t 
 }
 
 PFCudaStatus PFCudaRendererSetTimingEnabled(PFCudaRendererRef r, int32_t enabled) {
-    return guarded(r, [&]() { r->timing = enabled != 0; });
+    return guarded(r, [&]() {
+        verify_pending(r);
+        if (enabled && !r->timing) r->times_total = PFCudaRenderTime{}, r->times_batches = 0;
+        r->timing = enabled != 0;
+    });
+}
+
+PFCudaStatus PFCudaRendererGetAccumulatedTimes(PFCudaRendererRef r, PFCudaRenderTime *times, uint32_t *batches) {
+    return guarded(r, [&]() {
+        verify_pending(r);
+        if (!times || !batches) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null argument");
+        *times = r->times_total;
+        *batches = r->times_batches;
+    });
 }
 
 PFCudaStatus PFCudaRendererGetTimes(PFCudaRendererRef r, PFCudaRenderTime *times) {
