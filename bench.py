@@ -199,6 +199,9 @@ def main():
         run_reference(args)
         return
 
+    # One process per GPU: the ranks share the host's cores for their scene / batch builds.
+    os.environ.setdefault("PF_HOST_THREADS", str(max(2, (os.cpu_count() or 16) // max(1, int(os.environ.get("WORLD_SIZE", "1"))))))
+
     import torch
     from pathfinder_b200 import api
 

@@ -136,8 +136,10 @@ class WorkerPool {
     static constexpr size_t MAX_CHUNKS = INDEX_MASK;
 
     WorkerPool() {
+        // PF_HOST_THREADS caps the pool (several renderer processes on one host should share its cores).
         unsigned hw = std::thread::hardware_concurrency();
         size_t n = std::min<size_t>(hw ? hw : 1, 16);
+        if (const char *env = getenv("PF_HOST_THREADS")) n = std::max<size_t>(1, std::min<size_t>(n, (size_t)atoi(env)));
         for (size_t i = 1; i < n; i++) workers_.emplace_back([this]() { loop(); });
     }
     ~WorkerPool() {
