@@ -475,3 +475,33 @@ def test_clip_paths(area_lut, size):
     assert np.array_equal(stitched, img)
     r.close()
     r0.close()
+
+
+def test_deferred_verification_and_accumulated_times(area_lut):
+    """Two renderers sharing one stream with deferred verification: frames are enqueued without a host wait,
+    the accumulated stage times cover every batch, and the pixels equal the synchronous frames."""
+    import torch
+    from pathfinder_b200 import api
+    stream = torch.cuda.Stream()
+    items = []
+    for flat, xf, size in [(scenes.tiger(512)[0], scenes.tiger(512)[1], 512), (scenes.random_paths(2000, 1024, 3), None, 1024)]:
+        r = api.CudaRenderer((size, size), background_color=(1, 1, 1, 1))
+        r.set_stream(stream.cuda_stream)
+        scene = api.Scene.from_flat(flat)
+        opts = api.BuildOptions(transform=None if xf is None else api.Transform2F(*xf))
+        scene.build_and_render(r, opts)
+        items.append((r, scene, opts, r.read_pixels()))
+    for r, *_ in items:
+        r.set_deferred_verification(True)
+        r.set_timing_enabled(True)
+    for _ in range(5):
+        for r, scene, opts, _ in items:
+            scene.build_and_render(r, opts)
+    for r, scene, opts, ref in items:
+        totals, batches = r.accumulated_times()
+        assert batches == 5 and totals["total_ms"] > 0 and totals["fill_tile_ms"] > 0
+        assert abs(sum(totals[k] for k in ("bound_ms", "dice_ms", "bin_ms", "propagate_ms", "sort_ms", "fill_tile_ms")) - totals["total_ms"]) < 0.05 * totals["total_ms"]
+        s = r.stats()
+        assert s["reruns"] == 0 and s["host_sync_count"] <= 1
+        assert np.array_equal(r.read_pixels(), ref)
+        r.close()
