@@ -180,6 +180,24 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ncu_dram_bytes(world: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_composite launch on random100k@8192 from the committed
+    `ncu --set full` summary (profiles/r*_composite_ncu.md, newest round); only meaningful for the whole frame (N = 1)."""
+    import glob
+    import re
+    if world != 1:
+        return None
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_composite_ncu.md")))
+    if not files:
+        return None
+    text = open(files[-1]).read().split("## tiger4k")[0]
+    got = {k: re.search(r"`%s` \| (\w+) \| ([0-9.]+)" % re.escape(k), text) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")}
+    if not all(got.values()):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    return int(sum(float(m.group(2)) * scale.get(m.group(1), 1.0) for m in got.values()))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -464,7 +482,7 @@ def main():
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
     roofline = {"bound": "hbm", "kernel": "k_composite (fused fill + tile)", "scene": big.name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": ncu_dram_bytes(world),
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms, "peak_source": peak_src}
 
     cpu_baseline = None
