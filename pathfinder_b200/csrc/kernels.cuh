@@ -144,7 +144,9 @@ int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_
 // start, *fill_cursor += total (keep_all_fills: culled tiles keep their runs, for the parity dumps).
 int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
                       uint32_t *fb_count, uint32_t *tile_fill_pos, uint32_t *fill_cursor, uint32_t *path_live,
-                      bool keep_all_fills, const uint32_t *run_counts, cudaStream_t stream);
+                      bool keep_all_fills, const uint32_t *run_counts, uint32_t *live_tiles, uint32_t live_capacity,
+                      uint32_t *live_count, cudaStream_t stream);
+// (live_tiles, optional: the surviving tiles as a compact list, *live_count of them, for launch_list_emit)
 // Device-side totals ([0] lines, [2] entries, [5] visible fills) and the capacities they must fit.
 struct OverflowGuard {
     const uint32_t *totals;
@@ -155,7 +157,8 @@ struct OverflowGuard {
 int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t *tile_word,
                      const uint32_t *tile_fill_pos, const uint32_t *fb_start, uint32_t *fb_cursor,
                      const float4 *paints, TileEntry *entries, uint32_t capacity, const OverflowGuard &guard,
-                     const ClipDev *clip, const uint32_t *tile_clip, uint2 *entry_clip, cudaStream_t stream);
+                     const ClipDev *clip, const uint32_t *tile_clip, uint2 *entry_clip, const uint32_t *live_tiles,
+                     uint32_t live_capacity, const uint32_t *live_count, cudaStream_t stream);
 
 struct CompositeArgs {
     const TileEntry *entries;   // runs in arbitrary order; the kernel sorts each by tile_index

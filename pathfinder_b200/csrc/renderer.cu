@@ -153,7 +153,7 @@ struct PFCudaRenderer {
     // Everything a frame needs zeroed lives in one allocation and is cleared by one memset (carve_zeroed).
     DeviceBuffer<uint32_t> zeroed;
     ZeroedView<uint32_t> counters;  // device-side totals: [0]=lines [1]=fills [2]=entries [3]=alpha tiles [4]=dump tiles
-                                    // [5]=visible fills [6,7]/[13,14]=long-line queues [8,9]=u64 scratch [12]=tile counter
+                                    // [5]=visible fills [6,7]/[13,14]=long-line queues [8,9]=u64 scratch [12]=tile counter [15]=surviving tiles
     ZeroedView<uint32_t> path_live; // per path: some tile with fills survived the z-cull
     ZeroedView<uint32_t> tile_word;
     ZeroedView<int32_t> col_backdrop;
@@ -176,6 +176,7 @@ struct PFCudaRenderer {
         uint32_t n_fills = 0, n_alpha = 0;
     } clip;
     DeviceBuffer<uint32_t> tile_orig;  // parity dumps with clips: fill count of every draw tile before the clip
+    DeviceBuffer<uint32_t> live_tiles; // steady state: the tiles that survived the z-cull, compacted
     DeviceBuffer<uint32_t> tile_clip;  // per draw tile: clip tile reference (batches with clipped paths)
     DeviceBuffer<uint2> entry_clip;    // per list entry: {clip fill end, clip tile word}
     DeviceBuffer<PackedFill> fills;
@@ -260,6 +261,7 @@ void setup_tracking(PFCudaRenderer *r) {
     track(r, r->clip.tile_alpha_id);
     track(r, r->clip.fill_records);
     track(r, r->tile_orig);
+    track(r, r->live_tiles);
     track(r, r->tile_clip);
     track(r, r->entry_clip);
     track(r, r->fills);
@@ -717,9 +719,18 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
     // sorted into draw order inside the fused kernel.
     // (the same kernel reserves the fill runs of the surviving tiles: occlusion culling before fill
     // emission; with the parity dumps on, every alpha tile keeps its fills so its mask can be read back)
+    // Steady state: the survivors are also compacted into a list sized like the entries (same bound, same
+    // overflow condition), so the entry pass does not have to visit every bbox tile.
+    const bool compact_lists = !sizing && !r->debug_lists;
+    uint32_t live_capacity = 0;
+    if (compact_lists) {
+        live_capacity = bound_of(c.n_entries, r->entries.capacity);
+        r->live_tiles.ensure(live_capacity + 1, 1.25);
+    }
     launches += launch_list_count(b, r->tile_word.ptr, r->z_buffer.ptr, r->tile_fb.ptr, r->fb_count.ptr,
                                   r->tile_fill_pos.ptr, r->counters.ptr + C_VISIBLE_FILLS, r->path_live.ptr,
-                                  r->debug_lists, clip_dumps ? r->tile_orig.ptr : nullptr, st);
+                                  r->debug_lists, clip_dumps ? r->tile_orig.ptr : nullptr,
+                                  compact_lists ? r->live_tiles.ptr : nullptr, live_capacity, r->counters.ptr + 15, st);
     launches += exclusive_scan(LoadU32{r->fb_count.ptr}, r->fb_start.ptr, n_fb, r->counters.ptr + C_ENTRIES,
                                r->scan_scratch, st);
     uint32_t entry_bound, fill_bound;
@@ -798,7 +809,8 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
     launches += launch_list_emit(b, r->tile_fb.ptr, r->tile_word.ptr, r->tile_fill_pos.ptr, r->fb_start.ptr,
                                  r->fb_cursor.ptr, r->paints.ptr, r->entries.ptr, entry_bound, guard,
                                  use_clip ? &clip_dev : nullptr, use_clip ? r->tile_clip.ptr : nullptr,
-                                 use_clip ? r->entry_clip.ptr : nullptr, st);
+                                 use_clip ? r->entry_clip.ptr : nullptr, compact_lists ? r->live_tiles.ptr : nullptr,
+                                 live_capacity, r->counters.ptr + 15, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[6], st));
 
     // ---- fill + tile (fused).
