@@ -1238,6 +1238,10 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
             const uint32_t n_fb = (uint32_t)((fb.max_x - fb.min_x) * (fb.max_y - fb.min_y));
             r->fb_start.ensure(n_fb + 1);
             carve_zeroed(r, 0, 0, 0, n_fb); // every list empty, tile counter zero
+            r->last_fb = fb;                // (the z-buffer of an empty frame is all zero over the same rect)
+            r->last_batch = BatchDev{};
+            r->last_lines = r->last_fills = r->last_entries = 0;
+            r->last_alpha_ids_valid = false;
             CompositeArgs ca{};
             ca.fb_start = r->fb_start.ptr;
             ca.fb_count = r->fb_count.ptr;

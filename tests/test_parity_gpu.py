@@ -505,3 +505,54 @@ def test_deferred_verification_and_accumulated_times(area_lut):
         assert s["reruns"] == 0 and s["host_sync_count"] <= 1
         assert np.array_equal(r.read_pixels(), ref)
         r.close()
+
+
+# ---- seeded fuzz: many small scenes of mixed geometry against the oracle --------------------------
+
+def fuzz_scene(seed):
+    """A small random scene: lines, quadratics and cubics mixed inside each contour, several contours per path,
+    coordinates that stray outside the view box, points exactly on tile and pixel boundaries, tiny and huge
+    shapes, opaque and translucent paints, both fill rules; view boxes that are not a multiple of the tile size."""
+    rng = np.random.RandomState(seed)
+    w, h = int(rng.choice([37, 64, 100, 160, 250])), int(rng.choice([33, 64, 96, 130, 200]))
+    ox, oy = 0.0, 0.0  # the destination image starts at the origin, like the reference's viewport
+    b = SceneBuilderPy((ox, oy, ox + w, oy + h))
+    snap = lambda v: float(np.round(v * rng.choice([1.0, 1.0, 1.0 / 16.0, 4.0])) / rng.choice([1.0, 16.0, 4.0])) if rng.rand() < 0.15 else float(v)
+
+    def point(cx, cy, r):
+        return snap(cx + rng.uniform(-r, r)), snap(cy + rng.uniform(-r, r))
+
+    for _ in range(int(rng.randint(1, 14))):
+        cx, cy = ox + rng.uniform(-0.3, 1.3) * w, oy + rng.uniform(-0.3, 1.3) * h
+        r = float(np.exp(rng.uniform(np.log(0.3), np.log(1.5 * max(w, h)))))
+        for _ in range(int(rng.randint(1, 4))):
+            b.move_to(*point(cx, cy, r))
+            for _ in range(int(rng.randint(1, 7))):
+                kind = rng.randint(0, 3)
+                if kind == 0:
+                    b.line_to(*point(cx, cy, r))
+                elif kind == 1:
+                    b.quad_to(*point(cx, cy, 2 * r), *point(cx, cy, r))
+                else:
+                    b.cubic_to(*point(cx, cy, 2 * r), *point(cx, cy, 2 * r), *point(cx, cy, r))
+            b.close()
+        alpha = 255 if rng.rand() < 0.5 else int(rng.randint(1, 255))
+        b.end_path(tuple(int(v) for v in rng.randint(0, 256, 3)) + (alpha,),
+                   FILL_RULE_EVEN_ODD if rng.rand() < 0.5 else FILL_RULE_WINDING)
+    xf = None
+    if seed % 2:
+        s = float(np.exp(rng.uniform(np.log(0.25), np.log(6.0))))
+        xf = (s, 0.0, 0.0, s, float(rng.uniform(-0.5, 0.5) * w), float(rng.uniform(-0.5, 0.5) * h))
+    return b.finish(f"fuzz{seed}"), xf, (w, h)
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_fuzz_small_scenes(area_lut, block):
+    """25 seeded random scenes per block: lines, fills (with alpha tile ids), tiles, z-buffer bit-exact, masks and
+    pixels within 1/255, production path identical to the instrumented one (check_scene)."""
+    for seed in range(block * 25, block * 25 + 25):
+        flat, xf, (w, h) = fuzz_scene(seed)
+        try:
+            check_scene(flat, xf, area_lut, size=(w, h), background=(0.9, 0.95, 1.0, 1.0) if seed % 4 else None)
+        except AssertionError as e:
+            raise AssertionError(f"fuzz seed {seed}: {e}") from e
