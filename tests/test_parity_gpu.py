@@ -556,3 +556,64 @@ def test_fuzz_small_scenes(area_lut, block):
             check_scene(flat, xf, area_lut, size=(w, h), background=(0.9, 0.95, 1.0, 1.0) if seed % 4 else None)
         except AssertionError as e:
             raise AssertionError(f"fuzz seed {seed}: {e}") from e
+
+
+def fuzz_clip_scene(seed):
+    """Like fuzz_scene, with one or two clip paths (used in scene order, see test_clip_paths) and draw paths that
+    are clipped by them or not."""
+    rng = np.random.RandomState(1000 + seed)
+    w, h = int(rng.choice([64, 100, 160, 250])), int(rng.choice([64, 96, 130, 200]))
+    b = SceneBuilderPy((0.0, 0.0, w, h))
+
+    def blob(cx, cy, r, curvy):
+        k = int(rng.randint(3, 8))
+        for m in range(k):
+            a = 2 * np.pi * m / k + rng.uniform(-0.3, 0.3)
+            x, y = cx + r * np.cos(a) * rng.uniform(0.5, 1.0), cy + r * np.sin(a) * rng.uniform(0.5, 1.0)
+            if m == 0:
+                b.move_to(x, y)
+            elif curvy and m % 2:
+                b.quad_to(cx + 1.4 * r * np.cos(a - 0.4), cy + 1.4 * r * np.sin(a - 0.4), x, y)
+            else:
+                b.line_to(x, y)
+        b.close()
+
+    clips = []
+    for _ in range(int(rng.randint(1, 3))):
+        for _ in range(int(rng.randint(1, 3))):  # one or two contours (holes / islands with even-odd)
+            blob(rng.uniform(0.2, 0.8) * w, rng.uniform(0.2, 0.8) * h, rng.uniform(0.15, 0.6) * max(w, h), True)
+        clips.append(b.end_clip_path(FILL_RULE_EVEN_ODD if rng.rand() < 0.5 else FILL_RULE_WINDING))
+    n_draw = int(rng.randint(len(clips), 12))
+    for i in range(n_draw):
+        big = rng.rand() < 0.3
+        r = (rng.uniform(0.5, 1.2) if big else rng.uniform(0.05, 0.4)) * max(w, h)
+        blob(rng.uniform(-0.1, 1.1) * w, rng.uniform(-0.1, 1.1) * h, r, rng.rand() < 0.6)
+        alpha = 255 if rng.rand() < 0.5 else int(rng.randint(1, 255))
+        clip = clips[i] if i < len(clips) else (int(rng.choice(clips)) if rng.rand() < 0.6 else 0xFFFFFFFF)
+        b.end_path(tuple(int(v) for v in rng.randint(0, 256, 3)) + (alpha,),
+                   FILL_RULE_EVEN_ODD if rng.rand() < 0.4 else FILL_RULE_WINDING, clip=clip)
+    return b.finish(f"clipfuzz{seed}"), (w, h)
+
+
+def test_fuzz_clipped_scenes(area_lut):
+    """40 seeded random clipped scenes: fills (clip paths first), tiles, Clip records and z-buffer bit-exact,
+    pixels within 1/255, production frame identical to the instrumented one."""
+    for seed in range(40):
+        flat, (w, h) = fuzz_clip_scene(seed)
+        built = H.oracle_build(flat, None)
+        try:
+            rd, img = H.cuda_render(flat, None, size=(w, h), background=(1.0, 1.0, 1.0, 1.0), debug=True)
+            H.assert_records_equal(rd.debug_fills(), built.fills, "fills")
+            H.assert_records_equal(rd.debug_tiles(), built.tiles, "tiles")
+            H.assert_records_equal(rd.debug_clips(), built.clips, "clips")
+            z, rect = rd.debug_z_buffer()
+            assert rect == built.z_rect and np.array_equal(z, built.z_buffer), "z-buffer"
+            ref = built.render(area_lut, w, h, background=(1.0, 1.0, 1.0, 1.0))
+            diff = np.abs(img.astype(np.int32) - ref.astype(np.int32))
+            assert diff.max() <= RGBA_TOL, f"max RGBA diff {diff.max()} at {np.unravel_index(diff.argmax(), diff.shape)}"
+            rp, img2 = H.cuda_render(flat, None, size=(w, h), background=(1.0, 1.0, 1.0, 1.0), debug=False)
+            assert np.array_equal(img2, img), "production path differs from the instrumented path"
+            rd.close()
+            rp.close()
+        except AssertionError as e:
+            raise AssertionError(f"clip fuzz seed {seed}: {e}") from e
