@@ -509,7 +509,7 @@ def test_deferred_verification_and_accumulated_times(area_lut):
 
 # ---- seeded fuzz: many small scenes of mixed geometry against the oracle --------------------------
 
-def fuzz_scene(seed):
+def fuzz_scene(seed, rotate=False):
     """A small random scene: lines, quadratics and cubics mixed inside each contour, several contours per path,
     coordinates that stray outside the view box, points exactly on tile and pixel boundaries, tiny and huge
     shapes, opaque and translucent paints, both fill rules; view boxes that are not a multiple of the tile size."""
@@ -543,6 +543,14 @@ def fuzz_scene(seed):
     if seed % 2:
         s = float(np.exp(rng.uniform(np.log(0.25), np.log(6.0))))
         xf = (s, 0.0, 0.0, s, float(rng.uniform(-0.5, 0.5) * w), float(rng.uniform(-0.5, 0.5) * h))
+    if rotate:
+        # a general affine map (rotation, anisotropic scale, shear) about the middle of the view box
+        a = float(rng.uniform(0, 2 * np.pi))
+        sx, sy, k = float(rng.uniform(0.5, 2.0)), float(rng.uniform(0.5, 2.0)), float(rng.uniform(-0.5, 0.5))
+        m11, m12 = sx * np.cos(a), -sy * np.sin(a) + k * sx * np.cos(a)
+        m21, m22 = sx * np.sin(a), sy * np.cos(a) + k * sx * np.sin(a)
+        cx, cy = 0.5 * w, 0.5 * h
+        xf = tuple(float(np.float32(v)) for v in (m11, m12, m21, m22, cx - (m11 * cx + m12 * cy), cy - (m21 * cx + m22 * cy)))
     return b.finish(f"fuzz{seed}"), xf, (w, h)
 
 
@@ -556,6 +564,19 @@ def test_fuzz_small_scenes(area_lut, block):
             check_scene(flat, xf, area_lut, size=(w, h), background=(0.9, 0.95, 1.0, 1.0) if seed % 4 else None)
         except AssertionError as e:
             raise AssertionError(f"fuzz seed {seed}: {e}") from e
+
+
+def test_fuzz_general_affine_transforms(area_lut):
+    """BuildOptions transforms with rotation and shear: the D3D11 builder's tile rects (transformed bounding box)
+    are then a superset of the CPU tiler's (bounds of the transformed outline); the extra tiles are empty, so
+    fills, non-empty tiles, z-buffer and pixels still match. Flattened lines are compared too: both sides
+    transform the control points before dicing."""
+    for seed in range(200, 230):
+        flat, xf, (w, h) = fuzz_scene(seed, rotate=True)
+        try:
+            check_scene(flat, xf, area_lut, size=(w, h), background=(1.0, 1.0, 1.0, 1.0))
+        except AssertionError as e:
+            raise AssertionError(f"affine fuzz seed {seed}: {e}") from e
 
 
 def fuzz_clip_scene(seed):
