@@ -561,7 +561,17 @@ def test_fuzz_small_scenes(area_lut, block):
     for seed in range(block * 25, block * 25 + 25):
         flat, xf, (w, h) = fuzz_scene(seed)
         try:
-            check_scene(flat, xf, area_lut, size=(w, h), background=(0.9, 0.95, 1.0, 1.0) if seed % 4 else None)
+            background = (0.9, 0.95, 1.0, 1.0) if seed % 4 else None
+            img, _ = check_scene(flat, xf, area_lut, size=(w, h), background=background)
+            if seed % 5 == 0:  # three uneven strips of tile rows reproduce the frame
+                rows = (h + 15) // 16
+                cuts = sorted({0, rows // 3, (2 * rows + 2) // 3, rows})
+                stitched = np.zeros_like(img)
+                for y0, y1 in zip(cuts[:-1], cuts[1:]):
+                    rs, part = H.cuda_render(flat, xf, size=(w, h), background=background, debug=False, strip=(y0, y1))
+                    stitched[y0 * 16:y1 * 16] = part[y0 * 16:y1 * 16]
+                    rs.close()
+                assert np.array_equal(stitched, img), "strips differ from the full frame"
         except AssertionError as e:
             raise AssertionError(f"fuzz seed {seed}: {e}") from e
 
