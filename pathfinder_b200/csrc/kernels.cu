@@ -925,7 +925,7 @@ int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_
 // sort — per-framebuffer-tile painter's-order lists with z-cull.
 //
 // Count -> scan -> emit again: every surviving tile bumps its framebuffer tile's counter, the scan
-// gives each framebuffer tile a contiguous run, and the emit pass appends 16-byte entries through
+// gives each framebuffer tile a contiguous run, and the emit pass appends 32-byte entries through
 // a per-framebuffer-tile cursor. The append order inside a run is arbitrary; the fused fill+tile
 // kernel sorts its (short) run by tile index — tiles are allocated path by path, so ascending
 // tile index is draw order — in shared memory. This replaces the linked-list insertion sort of
