@@ -10,7 +10,7 @@ from collections import OrderedDict
 
 
 def read(path):
-    fills, tiles, z = OrderedDict(), {}, None
+    fills, tiles, z, clips = OrderedDict(), {}, None, []
     for line in open(path):
         w = line.split()
         if not w:
@@ -22,23 +22,26 @@ def read(path):
             tiles[(pid, ty, tx)] = (alpha, color, ctrl, backdrop)
         elif w[0] == "z":
             z = tuple(int(v) for v in w[1:])
-    return fills, tiles, z
+        elif w[0] == "clip":
+            clips.append(tuple(int(v) for v in w[1:5]))
+    return fills, tiles, z, clips
 
 
-def canonical(fills, tiles):
+def canonical(fills, tiles, clips=()):
     rename = {old: new for new, old in enumerate(fills.keys())}
     cf = {rename[k]: v for k, v in fills.items()}
     ct = {}
     for key, (alpha, color, ctrl, backdrop) in tiles.items():
         solid = alpha == 0xFFFFFFFF or alpha not in rename
         ct[key] = (None if solid else rename[alpha], color, ctrl, backdrop)
-    return cf, ct
+    cc = sorted((rename.get(d, d), db, rename.get(s, s), sb) for d, db, s, sb in clips)
+    return cf, ct, cc
 
 
 def main():
     a, b = read(sys.argv[1]), read(sys.argv[2])
-    fa, ta = canonical(a[0], a[1])
-    fb, tb = canonical(b[0], b[1])
+    fa, ta, ca = canonical(a[0], a[1], a[3])
+    fb, tb, cb = canonical(b[0], b[1], b[3])
     problems = 0
     if len(fa) != len(fb):
         print(f"alpha tile count differs: {len(fa)} vs {len(fb)}")
@@ -53,6 +56,9 @@ def main():
             problems += 1
             if problems < 20:
                 print(f"tile (path, y, x) = {k} differs: {ta.get(k)} vs {tb.get(k)}")
+    if ca != cb:
+        print(f"clip records differ: {len(ca)} vs {len(cb)} records")
+        problems += 1
     if a[2] != b[2]:
         print("z-buffers differ")
         problems += 1

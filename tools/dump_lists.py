@@ -13,11 +13,13 @@ List format, one record per line:
   fill <from_x> <from_y> <to_x> <to_y> <alpha_tile_id>      (LineSegmentU16 in 8.8 fixed point, gpu_data.rs Fill)
   tile <tile_x> <tile_y> <alpha_tile_id> <path_id> <color> <ctrl> <backdrop>   (TileObjectPrimitive)
   z <width> <height> <v0> <v1> ...                          (DrawTilesD3D9 z-buffer texels, row-major)
+  clip <dest_tile_id> <dest_backdrop> <src_tile_id> <src_backdrop>             (Clip, DrawTileBatchD3D9.clips)
 Scene format:
   viewbox <min_x> <min_y> <max_x> <max_y>
   transform <m11> <m12> <m21> <m22> <tx> <ty>               (BuildOptions transform, Transform2F row-major)
   paint <r> <g> <b> <a>
-  path <fill_rule: 0 winding | 1 even-odd> <paint index> <contour count>
+  clippath <fill_rule> <contour count>                       (clip paths first, ids in file order)
+  path <fill_rule: 0 winding | 1 even-odd> <paint index> <contour count> [<clip path id> | -1]
   contour <point count>
   p <x> <y> <flags>                                          (f32 as hex bits; flags: 1 = control 0, 2 = control 1)
 """
@@ -36,10 +38,13 @@ from pathfinder_b200 import scenes  # noqa: E402
 def load(spec, size):
     if spec == "tiger":
         return scenes.tiger(size)
+    if spec == "clips":
+        from tests.test_parity_gpu import clip_scene
+        return clip_scene(size), None
     if spec.startswith("random:"):
         _, n, seed = spec.split(":")
         return scenes.random_paths(int(n), size, int(seed)), None
-    raise SystemExit(f"unknown scene {spec!r} (tiger | random:<paths>:<seed>)")
+    raise SystemExit(f"unknown scene {spec!r} (tiger | clips | random:<paths>:<seed>)")
 
 
 def bits(v):
@@ -53,17 +58,24 @@ def write_scene(flat, xf, path):
         f.write("transform " + " ".join(bits(v) for v in t) + "\n")
         for c in np.asarray(flat.paint_colors).reshape(-1, 4):
             f.write("paint %d %d %d %d\n" % tuple(int(v) for v in c))
-        ranges = flat.contour_ranges()
-        for i, (c0, c1) in enumerate(ranges):
-            f.write("path %d %d %d\n" % (int(flat.fill_rules[i]), int(flat.paints[i]), int(c1 - c0)))
+        def contours(c0, c1):
             for c in range(int(c0), int(c1)):
                 p0, p1 = int(flat.contour_offsets[c]), int(flat.contour_offsets[c + 1])
                 f.write("contour %d\n" % (p1 - p0))
                 for k in range(p0, p1):
                     f.write("p %s %s %d\n" % (bits(flat.points[k][0]), bits(flat.points[k][1]), int(flat.point_flags[k])))
 
+        for (c0, c1), rule in zip(flat.clip_contour_ranges, flat.clip_fill_rules):
+            f.write("clippath %d %d\n" % (int(rule), int(c1 - c0)))
+            contours(c0, c1)
+        paints = flat.paints  # table indices: the reader pushes the table in order
+        for i, (c0, c1) in enumerate(flat.contour_ranges()):
+            clip = int(flat.draw_clip_paths[i])
+            f.write("path %d %d %d %d\n" % (int(flat.fill_rules[i]), int(paints[i]), int(c1 - c0), -1 if clip == 0xFFFFFFFF else clip))
+            contours(c0, c1)
 
-def write_lists(fills, tiles, z, path):
+
+def write_lists(fills, tiles, z, path, clips=()):
     with open(path, "w") as f:
         for r in fills:
             f.write("fill %d %d %d %d %d\n" % (r["from_x"], r["from_y"], r["to_x"], r["to_y"], r["link"]))
@@ -72,6 +84,8 @@ def write_lists(fills, tiles, z, path):
                                                    r["color"], r["ctrl"], r["backdrop"]))
         z = np.asarray(z)
         f.write("z %d %d %s\n" % (z.shape[1], z.shape[0], " ".join(str(int(v)) for v in z.reshape(-1))))
+        for r in clips:
+            f.write("clip %d %d %d %d\n" % (r["dest_tile_id"], r["dest_backdrop"], r["src_tile_id"], r["src_backdrop"]))
 
 
 def main():
@@ -88,11 +102,12 @@ def main():
     if args.source == "oracle":
         from tests import helpers as H
         b = H.oracle_build(flat, xf)
-        write_lists(b.fills, b.tiles, b.z_buffer, args.out)
+        write_lists(b.fills, b.tiles, b.z_buffer, args.out, b.clips)
     else:
         from tests import helpers as H
         r, _ = H.cuda_render(flat, xf, size=(args.size, args.size), debug=True)
-        write_lists(r.debug_fills(), r.debug_tiles(), r.debug_z_buffer(), args.out)
+        z, _rect = r.debug_z_buffer()
+        write_lists(r.debug_fills(), r.debug_tiles(), z, args.out, r.debug_clips())
 
 
 if __name__ == "__main__":

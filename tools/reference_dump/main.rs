@@ -14,8 +14,8 @@
 //
 // It builds the Scene from the outlines in the file (the comparison origin: post-loader outlines), runs
 // `Scene::build` at RendererLevel::D3D9 with SequentialExecutor (the canonical order of SURVEY.md §8c)
-// and prints every AddFillsD3D9 / DrawTilesD3D9 payload (renderer/src/gpu_data.rs:69,97,227-237,266-275,
-// 356-363).
+// and prints every AddFillsD3D9 / DrawTilesD3D9 payload, Clip records included (renderer/src/gpu_data.rs:69,97,
+// 227-237,266-275,356-363,378-383). Clip paths are read too (`clippath` records, `path ... <clip id>`).
 
 use pathfinder_color::ColorU;
 use pathfinder_content::fill::FillRule;
@@ -28,7 +28,7 @@ use pathfinder_renderer::gpu::options::RendererLevel;
 use pathfinder_renderer::gpu_data::RenderCommand;
 use pathfinder_renderer::options::{BuildOptions, RenderCommandListener, RenderTransform};
 use pathfinder_renderer::paint::Paint;
-use pathfinder_renderer::scene::{DrawPath, Scene, SceneSink};
+use pathfinder_renderer::scene::{ClipPath, ClipPathId, DrawPath, Scene, SceneSink};
 use std::env;
 use std::fs;
 use std::sync::{Arc, Mutex};
@@ -43,8 +43,9 @@ fn main() {
     let mut scene = Scene::new();
     let mut transform = Transform2F::default();
     let mut paints = vec![];
-    // (fill rule, paint, contours still to read, outline)
-    let mut current: Option<(FillRule, usize, usize, Outline)> = None;
+    // (fill rule, paint (None: a clip path), clip path of a draw path, outline)
+    let mut current: Option<(FillRule, Option<usize>, Option<ClipPathId>, Outline)> = None;
+    let mut clip_ids: Vec<ClipPathId> = vec![];
     let mut contour: Option<(Contour, Vec<(Vector2F, u8)>, usize)> = None;
 
     fn finish_contour(points: &[(Vector2F, u8)]) -> Contour {
@@ -69,10 +70,21 @@ fn main() {
         c
     }
 
-    let mut flush_path = |scene: &mut Scene, paints: &Vec<_>, cur: (FillRule, usize, usize, Outline)| {
-        let mut draw_path = DrawPath::new(cur.3, paints[cur.1]);
-        draw_path.set_fill_rule(cur.0);
-        scene.push_draw_path(draw_path);
+    let mut flush_path = |scene: &mut Scene, paints: &Vec<_>, clip_ids: &mut Vec<ClipPathId>,
+                          cur: (FillRule, Option<usize>, Option<ClipPathId>, Outline)| {
+        match cur.1 {
+            Some(paint) => {
+                let mut draw_path = DrawPath::new(cur.3, paints[paint]);
+                draw_path.set_fill_rule(cur.0);
+                draw_path.set_clip_path(cur.2);
+                scene.push_draw_path(draw_path);
+            }
+            None => {
+                let mut clip_path = ClipPath::new(cur.3);
+                clip_path.set_fill_rule(cur.0);
+                clip_ids.push(scene.push_clip_path(clip_path));
+            }
+        }
     };
 
     for line in text.lines() {
@@ -89,12 +101,21 @@ fn main() {
                 let c: Vec<u8> = w[1..5].iter().map(|v| v.parse().unwrap()).collect();
                 paints.push(scene.push_paint(&Paint::from_color(ColorU::new(c[0], c[1], c[2], c[3]))));
             }
-            Some("path") => {
+            Some("clippath") => {
                 if let Some(cur) = current.take() {
-                    flush_path(&mut scene, &paints, cur);
+                    flush_path(&mut scene, &paints, &mut clip_ids, cur);
                 }
                 let rule = if w[1] == "1" { FillRule::EvenOdd } else { FillRule::Winding };
-                current = Some((rule, w[2].parse().unwrap(), w[3].parse().unwrap(), Outline::new()));
+                current = Some((rule, None, None, Outline::new()));
+            }
+            Some("path") => {
+                if let Some(cur) = current.take() {
+                    flush_path(&mut scene, &paints, &mut clip_ids, cur);
+                }
+                let rule = if w[1] == "1" { FillRule::EvenOdd } else { FillRule::Winding };
+                let clip: i64 = w.get(4).map_or(-1, |v| v.parse().unwrap());
+                let clip = if clip < 0 { None } else { Some(clip_ids[clip as usize]) };
+                current = Some((rule, Some(w[2].parse().unwrap()), clip, Outline::new()));
             }
             Some("contour") => contour = Some((Contour::new(), vec![], w[1].parse().unwrap())),
             Some("p") => {
@@ -112,7 +133,7 @@ fn main() {
         }
     }
     if let Some(cur) = current.take() {
-        flush_path(&mut scene, &paints, cur);
+        flush_path(&mut scene, &paints, &mut clip_ids, cur);
     }
 
     let commands = Arc::new(Mutex::new(vec![]));
@@ -141,6 +162,9 @@ fn main() {
                 let z = &batch.z_buffer_data;
                 let texels: Vec<String> = z.data.iter().map(|v| v.to_string()).collect();
                 println!("z {} {} {}", z.rect.width(), z.rect.height(), texels.join(" "));
+                for c in &batch.clips {
+                    println!("clip {} {} {} {}", c.dest_tile_id.0, c.dest_backdrop, c.src_tile_id.0, c.src_backdrop);
+                }
             }
             _ => {}
         }
