@@ -219,6 +219,15 @@ def test_golden_tools_round_trip(tmp_path):
     open(b, "w").write("\n".join(lines) + "\n")
     assert run("tools/diff_lists.py", a, b).returncode == 1
     assert open(scene).readline().startswith("viewbox ")
+    # clipped scenes: clip paths in the scene file, Clip records in the lists
+    c, cs = str(tmp_path / "c.lists"), str(tmp_path / "c.scene")
+    assert run("tools/dump_lists.py", "clips", "256", "--out", c, "--scene-out", cs).returncode == 0
+    text = open(c).read()
+    assert "\nclip " in text and "clippath " in open(cs).read()
+    assert run("tools/diff_lists.py", c, c).returncode == 0
+    broken = str(tmp_path / "c2.lists")
+    open(broken, "w").write(text.replace("\nclip ", "\nclip 1", 1))
+    assert run("tools/diff_lists.py", c, broken).returncode == 1
 
 
 def _clip_scene(clip_kind):
