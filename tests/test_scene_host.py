@@ -179,3 +179,51 @@ def test_clip_batch_commands():
     scene.build(api.BuildOptions(), listener)
     i_clip = seen.index(L.PF_RENDER_COMMAND_PREPARE_CLIP_TILES_D3D11)
     assert seen.index(L.PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11) < i_clip < seen.index(L.PF_RENDER_COMMAND_DRAW_TILES_D3D11)
+
+
+def test_concurrent_scene_builds_share_the_worker_pool():
+    """Scene::build from several host threads at once (ctypes releases the GIL): the builds share one worker pool,
+    which runs one parallel region at a time, and every build must produce the arrays a lone build produces."""
+    import threading
+    flat = scenes.random_paths(30000, 2048, 77)
+
+    def build_once():
+        scene = api.Scene.from_flat(flat)
+        out = {}
+
+        def listener(cmd):
+            if int(cmd.kind) == L.PF_RENDER_COMMAND_DRAW_TILES_D3D11:
+                b = cmd.u.draw_tiles_d3d11.tile_batch_data
+                n = int(b.path_count)
+                pm = np.ctypeslib.as_array(C.cast(b.prepare_info.propagate_metadata, C.POINTER(C.c_uint8)),
+                                           shape=(n * C.sizeof(L.PFPropagateMetadataD3D11),)).copy()
+                dm = np.ctypeslib.as_array(C.cast(b.prepare_info.dice_metadata, C.POINTER(C.c_uint8)),
+                                           shape=(n * C.sizeof(L.PFDiceMetadataD3D11),)).copy()
+                out["batch"] = (n, int(b.tile_count), int(b.segment_count), pm.tobytes(), dm.tobytes())
+            if int(cmd.kind) == L.PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11:
+                s = cmd.u.upload_scene_d3d11.draw_segments
+                pts = np.ctypeslib.as_array(C.cast(s.points, C.POINTER(C.c_float)), shape=(int(s.point_count) * 2,)).copy()
+                out["segments"] = (int(s.point_count), int(s.index_count), pts.tobytes())
+
+        for _ in range(3):
+            scene.set_view_box(flat.view_box)  # dirty: segments and batch are rebuilt
+            scene.build(api.BuildOptions(), listener)
+        return out
+
+    expected = build_once()
+    results, errors = [None] * 6, []
+
+    def worker(i):
+        try:
+            results[i] = build_once()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(results))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for r in results:
+        assert r == expected
