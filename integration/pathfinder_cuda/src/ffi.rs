@@ -1,0 +1,146 @@
+//! Raw bindings to include/pf_cuda.h (the renderer half). The `#[repr(C)]` payload records
+//! (`SegmentIndicesD3D11`, `PropagateMetadataD3D11`, `DiceMetadataD3D11`, `TilePathInfoD3D11`,
+//! `BackdropInfoD3D11`, `TextureMetadataEntry`) are the reference's own, so the `Vec`s inside a
+//! `RenderCommand` are passed by pointer without conversion.
+
+use pathfinder_geometry::rect::RectF;
+use pathfinder_geometry::vector::Vector2F;
+use pathfinder_renderer::gpu_data::{BackdropInfoD3D11, DiceMetadataD3D11, PropagateMetadataD3D11};
+use pathfinder_renderer::gpu_data::{SegmentIndicesD3D11, TextureMetadataEntry, TilePathInfoD3D11};
+use std::os::raw::{c_char, c_void};
+
+pub const PF_CUDA_OK: i32 = 0;
+
+// PFRenderCommandKind
+pub const START: u32 = 0;
+pub const ALLOCATE_TEXTURE_PAGE: u32 = 1;
+pub const UPLOAD_TEXEL_DATA: u32 = 2;
+pub const DECLARE_RENDER_TARGET: u32 = 3;
+pub const UPLOAD_TEXTURE_METADATA: u32 = 4;
+pub const ADD_FILLS_D3D9: u32 = 5;
+pub const FLUSH_FILLS_D3D9: u32 = 6;
+pub const UPLOAD_SCENE_D3D11: u32 = 7;
+pub const PUSH_RENDER_TARGET: u32 = 8;
+pub const POP_RENDER_TARGET: u32 = 9;
+pub const PREPARE_CLIP_TILES_D3D11: u32 = 10;
+pub const DRAW_TILES_D3D9: u32 = 11;
+pub const DRAW_TILES_D3D11: u32 = 12;
+pub const FINISH: u32 = 13;
+
+#[repr(C)]
+pub struct PFRendererMode {
+    pub level: u32, // 1 = D3D9, 2 = D3D11
+}
+
+#[repr(C)]
+pub struct PFCudaRendererOptions {
+    pub dest_size: [i32; 2],
+    pub background_color: [f32; 4],
+    pub flags: u8, // bit 0: has a background colour
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFSegmentsD3D11 {
+    pub points: *const Vector2F,
+    pub point_count: usize,
+    pub indices: *const SegmentIndicesD3D11,
+    pub index_count: usize,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFPrepareTilesInfoD3D11 {
+    pub backdrops: *const BackdropInfoD3D11,
+    pub backdrop_count: usize,
+    pub propagate_metadata: *const PropagateMetadataD3D11,
+    pub dice_metadata: *const DiceMetadataD3D11,
+    pub tile_path_info: *const TilePathInfoD3D11,
+    pub transform: [f32; 6], // m00 m01 m10 m11 tx ty
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFClippedPathInfo {
+    pub clip_batch_id: u32,
+    pub clipped_path_count: u32,
+    pub max_clipped_tile_count: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFTileBatchDataD3D11 {
+    pub batch_id: u32,
+    pub path_count: u32,
+    pub tile_count: u32,
+    pub segment_count: u32,
+    pub prepare_info: PFPrepareTilesInfoD3D11,
+    pub path_source: u32, // 0 draw, 1 clip
+    pub has_clipped_path_info: u32,
+    pub clipped_path_info: PFClippedPathInfo,
+    pub content_key: u64, // 0: no promise about the batch being unchanged
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFStart {
+    pub path_count: u64,
+    pub needs_readable_framebuffer: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFUploadTextureMetadata {
+    pub entries: *const TextureMetadataEntry,
+    pub entry_count: usize,
+    pub content_key: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFUploadSceneD3D11 {
+    pub draw_segments: PFSegmentsD3D11,
+    pub clip_segments: PFSegmentsD3D11,
+    pub payload_persists: u32, // 0: borrowed for the call (the reference's semantics)
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFDrawTilesD3D11 {
+    pub tile_batch_data: PFTileBatchDataD3D11,
+    pub has_color_texture: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub union PFRenderCommandPayload {
+    pub start: PFStart,
+    pub upload_texture_metadata: PFUploadTextureMetadata,
+    pub upload_scene_d3d11: PFUploadSceneD3D11,
+    pub prepare_clip_tiles_d3d11: PFTileBatchDataD3D11,
+    pub draw_tiles_d3d11: PFDrawTilesD3D11,
+    pub push_render_target: u32,
+    pub finish_cpu_build_time_ns: u64,
+}
+
+#[repr(C)]
+pub struct PFRenderCommand {
+    pub kind: u32,
+    pub u: PFRenderCommandPayload,
+}
+
+extern "C" {
+    pub fn PFCudaGetLastError() -> *const c_char;
+    pub fn PFCudaDeviceCreate(ordinal: i32) -> *mut c_void;
+    pub fn PFCudaRendererCreate(device: *mut c_void, area_lut_rgba8: *const u8, gamma_lut_l8: *const u8,
+                                mode: *const PFRendererMode, options: *const PFCudaRendererOptions)
+                                -> *mut c_void;
+    pub fn PFCudaRendererDestroy(renderer: *mut c_void);
+    pub fn PFCudaRendererSetViewBox(renderer: *mut c_void, view_box: *const RectF) -> i32;
+    pub fn PFCudaRendererSetDeferredVerification(renderer: *mut c_void, enabled: i32) -> i32;
+    pub fn PFCudaRendererBeginScene(renderer: *mut c_void) -> i32;
+    pub fn PFCudaRendererRenderCommand(renderer: *mut c_void, command: *const PFRenderCommand) -> i32;
+    pub fn PFCudaRendererEndScene(renderer: *mut c_void) -> i32;
+    pub fn PFCudaRendererReadPixels(renderer: *mut c_void, dst: *mut u8, stride: usize) -> i32;
+    pub fn PFCudaRendererSynchronize(renderer: *mut c_void) -> i32;
+}

@@ -8,7 +8,8 @@
 //     mkdir -p examples/reference_dump/src && cp main.rs examples/reference_dump/src/
 //     # Cargo.toml of the example: dependencies pathfinder_renderer (features = ["d3d9"]),
 //     #   pathfinder_content, pathfinder_geometry, pathfinder_color (path = "../../<crate>"); add the
-//     #   example to the workspace members.
+//     #   example to the workspace members. `gpu_data` is a private module of pathfinder_renderer
+//     #   (renderer/src/lib.rs:28): make it `pub mod gpu_data;` for this build.
 //     cargo run --release -p reference_dump -- tiger1024.scene > reference.lists
 //     python tools/diff_lists.py ours.lists reference.lists
 //
