@@ -55,3 +55,22 @@ def test_record_layouts():
     assert ctypes.sizeof(_lib.PFBackdropInfoD3D11) == 12
     from pathfinder_b200 import api
     assert api.FILL_DTYPE.itemsize == 12 and api.TILE_DTYPE.itemsize == 16
+
+
+def test_rust_bindings_agree_with_the_header():
+    """integration/pathfinder_cuda/src/ffi.rs (source only) uses the header's command kinds and declares only
+    entry points the header declares."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "pf_cuda.h")).read()
+    ffi = open(os.path.join(root, "integration", "pathfinder_cuda", "src", "ffi.rs")).read()
+    kinds = {m.group(1): int(m.group(2)) for m in re.finditer(r"PF_RENDER_COMMAND_(\w+) = (\d+)", header)}
+    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"pub const (\w+): u32 = (\d+);", ffi)}
+    assert len(kinds) == 14 and consts == kinds
+    declared = set(re.findall(r"\b(PF[A-Z]\w+)\s*\(", header))
+    for fn in re.findall(r"pub fn (PF\w+)\(", ffi):
+        assert fn in declared, fn
+    # the extension fields are present on both sides
+    for field in ("content_key", "payload_persists", "has_clipped_path_info"):
+        assert field in header and field in ffi
