@@ -522,7 +522,7 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         for (uint32_t v : bits) batch_key = mix_key(batch_key, v);
         if (batch_key == 0) batch_key = 1;
     }
-    uint32_t tile_count = s->built_tile_count, segment_count = s->built_segment_count, column_count = 0;
+    uint32_t tile_count = s->built_tile_count, segment_count = s->built_segment_count;
     const bool rebuild = s->built_key != batch_key;
     if (rebuild) {
         tile_count = segment_count = 0;
@@ -652,7 +652,6 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         s->built_clipped_tile_count = sums[chunks].clipped_tiles;
         const uint32_t kept = sums[chunks].kept;
         tile_count = sums[chunks].tiles;
-        column_count = sums[chunks].columns;
         segment_count = sums[chunks].segments;
         s->propagate_metadata.resize(kept);
         s->dice_metadata.resize(kept);
