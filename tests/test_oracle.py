@@ -275,3 +275,15 @@ def test_clip_path_cases(area_lut):
     assert part.clips["dest_tile_id"].max() < part.alpha_tile_count and part.clips["src_tile_id"].max() < part.alpha_tile_count
     combined = part.tiles[np.isin(part.tiles["alpha_tile_id"], part.clips["dest_tile_id"])]
     assert (combined["backdrop"] == 0).all()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/resources/svg/Ghostscript_Tiger.svg"),
+                    reason="the reference checkout (and its tiger SVG) is only present in the build container")
+def test_tiger_fixture_is_reproducible():
+    """tests/golden/tiger.npz is exactly what tools/make_tiger_scene.py derives from the reference's
+    resources/svg/Ghostscript_Tiger.svg (path-data parser + stroke-to-fill restatement)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "tools/make_tiger_scene.py", "--check"], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -491,6 +491,13 @@ def main():
                 n_stroke += 1
     scene = builder.finish("tiger")
     out = os.path.join(ROOT, "tests", "golden", "tiger.npz")
+    if "--check" in sys.argv[1:]:  # compare with the committed fixture, write nothing
+        from pathfinder_b200.flat_scene import FlatScene
+        have = FlatScene.load(out)
+        same = all(np.array_equal(getattr(have, k), getattr(scene, k)) for k in
+                   ("points", "point_flags", "contour_offsets", "path_contour_offsets", "fill_rules", "paints", "paint_colors"))
+        print("tiger.npz:", "identical" if same else "DIFFERENT")
+        sys.exit(0 if same else 1)
     scene.save(out)
     print(f"{n_fill} fills + {n_stroke} strokes = {scene.n_paths} paths, {scene.n_contours} contours, "
           f"{len(scene.points)} points -> {out} ({os.path.getsize(out)} bytes)")
