@@ -428,6 +428,38 @@ typedef struct PFSceneSinkState { uint32_t has_last_scene, last_scene_id, last_s
 PFCudaStatus PFSceneBuild(PFSceneRef scene, PFBuildOptionsRef options, PFSceneSinkState *sink_state,
                           PFRenderCommandListenerFn listener, void *userdata);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Stroke-to-fill on the host: OutlineStrokeToFill, content/src/stroke.rs:88-448. */
+/* ------------------------------------------------------------------------------------------- */
+
+#define PF_LINE_CAP_BUTT 0    /* stroke.rs LineCap */
+#define PF_LINE_CAP_SQUARE 1
+#define PF_LINE_CAP_ROUND 2   /* not implemented */
+#define PF_LINE_JOIN_MITER 0  /* stroke.rs LineJoin::Miter(miter_limit) */
+#define PF_LINE_JOIN_BEVEL 1
+#define PF_LINE_JOIN_ROUND 2  /* not implemented */
+
+typedef struct PFStrokeStyle {            /* stroke.rs:45-53 */
+    float line_width;
+    uint32_t line_cap;
+    uint32_t line_join;
+    float miter_limit;                    /* LineJoin::Miter's ratio; the reference's default is 10 */
+} PFStrokeStyle;
+
+typedef struct PFOutline *PFOutlineRef;
+
+/* OutlineStrokeToFill::new + offset + into_outline on an outline given as flat arrays (points, PointFlags,
+ * contour_offsets[contour_count + 1], closed flag per contour). Returns NULL (see PFCudaGetLastError) for round
+ * caps or joins. The stroked outline's contours are all closed; fill it with the winding rule. */
+PFOutlineRef PFOutlineStrokeToFill(const PFVector2F *points, const uint8_t *point_flags,
+                                   const uint32_t *contour_offsets, const uint8_t *contour_closed,
+                                   uint32_t contour_count, const PFStrokeStyle *style);
+uint32_t PFOutlineGetContourCount(PFOutlineRef outline);
+size_t PFOutlineGetPointCount(PFOutlineRef outline);
+/* points / point_flags: PFOutlineGetPointCount entries; contour_offsets: PFOutlineGetContourCount + 1. */
+void PFOutlineCopy(PFOutlineRef outline, PFVector2F *points, uint8_t *point_flags, uint32_t *contour_offsets);
+void PFOutlineDestroy(PFOutlineRef outline);
+
 /* Scene::build_and_render (scene.rs:369-378) against the CUDA renderer: begin_scene, build with a
  * listener forwarding to PFCudaRendererRenderCommand, end_scene. Borrows everything
  * (as PFSceneProxyBuildAndRenderGL, c/src/lib.rs:672-681). */

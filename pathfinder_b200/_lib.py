@@ -86,6 +86,10 @@ class PFPrepareTilesInfoD3D11(C.Structure):
                 ("tile_path_info", C.c_void_p), ("transform", PFTransform2F)]
 
 
+class PFStrokeStyle(C.Structure):
+    _fields_ = [("line_width", C.c_float), ("line_cap", C.c_uint32), ("line_join", C.c_uint32), ("miter_limit", C.c_float)]
+
+
 class PFClippedPathInfo(C.Structure):
     _fields_ = [("clip_batch_id", C.c_uint32), ("clipped_path_count", C.c_uint32),
                 ("max_clipped_tile_count", C.c_uint32)]
@@ -235,6 +239,11 @@ SIGNATURES = {
     "PFScenePushPaint": (C.c_uint16, [C.c_void_p, C.POINTER(PFColorU)]),
     "PFScenePushDrawPath": (C.c_uint32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint32]),
+    "PFOutlineStrokeToFill": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "PFOutlineGetContourCount": (C.c_uint32, [C.c_void_p]),
+    "PFOutlineGetPointCount": (C.c_size_t, [C.c_void_p]),
+    "PFOutlineCopy": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "PFOutlineDestroy": (None, [C.c_void_p]),
     "PFScenePushClipPath": (C.c_uint32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_uint8, C.c_uint32]),
     "PFScenePushDrawPaths": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,

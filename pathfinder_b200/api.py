@@ -124,6 +124,14 @@ class Scene:
         return int(L.lib().PFScenePushDrawPath(self._h, pts.ctypes.data, fl.ctypes.data, co.ctypes.data,
                                                len(co) - 1, paint_id, fill_rule, blend_mode, clip_path_id))
 
+    def push_stroked_path(self, points, point_flags, contour_offsets, contour_closed, paint_id, line_width,
+                          line_join="miter", miter_limit=10.0, line_cap="butt", clip_path_id=0xFFFFFFFF) -> int:
+        """What the reference's front ends do with a stroked path (svg/src/lib.rs:204-231, canvas stroke_path):
+        OutlineStrokeToFill, then a draw path with the winding rule."""
+        pts, flags, offsets = stroke_to_fill(points, point_flags, contour_offsets, contour_closed, line_width,
+                                             line_join, miter_limit, line_cap)
+        return self.push_draw_path(pts, flags, offsets, paint_id, fill_rule=0, clip_path_id=clip_path_id)
+
     def push_clip_path(self, points, point_flags, contour_offsets, fill_rule=0, clip_path_id=0xFFFFFFFF) -> int:
         """Scene::push_clip_path (scene.rs:99-106); returns the ClipPathId."""
         pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
@@ -168,6 +176,32 @@ class Scene:
                 self._h = None
         except Exception:
             pass
+
+
+LINE_CAP = {"butt": 0, "square": 1, "round": 2}
+LINE_JOIN = {"miter": 0, "bevel": 1, "round": 2}
+
+
+def stroke_to_fill(points, point_flags, contour_offsets, contour_closed, line_width, line_join="miter",
+                   miter_limit=10.0, line_cap="butt"):
+    """OutlineStrokeToFill (content/src/stroke.rs:88-131) on flat arrays; returns (points, point_flags,
+    contour_offsets) of the stroked outline, whose contours are all closed."""
+    pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
+    fl = np.ascontiguousarray(point_flags, dtype=np.uint8)
+    co = np.ascontiguousarray(contour_offsets, dtype=np.uint32)
+    cl = np.ascontiguousarray(contour_closed, dtype=np.uint8)
+    style = L.PFStrokeStyle(float(line_width), LINE_CAP[line_cap], LINE_JOIN[line_join], float(miter_limit))
+    lib = L.lib()
+    h = lib.PFOutlineStrokeToFill(pts.ctypes.data, fl.ctypes.data, co.ctypes.data, cl.ctypes.data, len(co) - 1, C.byref(style))
+    if not h:
+        raise L.PathfinderCudaError(L.PF_CUDA_ERROR_UNSUPPORTED, lib.PFCudaGetLastError().decode("utf-8", "replace"))
+    try:
+        n, k = int(lib.PFOutlineGetPointCount(h)), int(lib.PFOutlineGetContourCount(h))
+        out_p, out_f, out_c = np.zeros((n, 2), np.float32), np.zeros(n, np.uint8), np.zeros(k + 1, np.uint32)
+        lib.PFOutlineCopy(h, out_p.ctypes.data, out_f.ctypes.data, out_c.ctypes.data)
+    finally:
+        lib.PFOutlineDestroy(h)
+    return out_p, out_f, out_c
 
 
 def ipc_export(device_ptr: int):
