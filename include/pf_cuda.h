@@ -434,10 +434,10 @@ PFCudaStatus PFSceneBuild(PFSceneRef scene, PFBuildOptionsRef options, PFSceneSi
 
 #define PF_LINE_CAP_BUTT 0    /* stroke.rs LineCap */
 #define PF_LINE_CAP_SQUARE 1
-#define PF_LINE_CAP_ROUND 2   /* not implemented */
+#define PF_LINE_CAP_ROUND 2
 #define PF_LINE_JOIN_MITER 0  /* stroke.rs LineJoin::Miter(miter_limit) */
 #define PF_LINE_JOIN_BEVEL 1
-#define PF_LINE_JOIN_ROUND 2  /* not implemented */
+#define PF_LINE_JOIN_ROUND 2
 
 typedef struct PFStrokeStyle {            /* stroke.rs:45-53 */
     float line_width;
@@ -449,8 +449,8 @@ typedef struct PFStrokeStyle {            /* stroke.rs:45-53 */
 typedef struct PFOutline *PFOutlineRef;
 
 /* OutlineStrokeToFill::new + offset + into_outline on an outline given as flat arrays (points, PointFlags,
- * contour_offsets[contour_count + 1], closed flag per contour). Returns NULL (see PFCudaGetLastError) for round
- * caps or joins. The stroked outline's contours are all closed; fill it with the winding rule. */
+ * contour_offsets[contour_count + 1], closed flag per contour). Returns NULL (see PFCudaGetLastError) on invalid
+ * arguments. The stroked outline's contours are all closed; fill it with the winding rule. */
 PFOutlineRef PFOutlineStrokeToFill(const PFVector2F *points, const uint8_t *point_flags,
                                    const uint32_t *contour_offsets, const uint8_t *contour_closed,
                                    uint32_t contour_count, const PFStrokeStyle *style);

@@ -1,7 +1,8 @@
 // pathfinder_b200/csrc/stroke.cpp — stroke-to-fill on the host: a C++ restatement of
 // OutlineStrokeToFill (content/src/stroke.rs:88-448) in the reference's f32 arithmetic, one rounding per
-// operation (compiled with -ffp-contract=off). Miter and bevel joins, butt and square caps; round joins and
-// caps (arc approximation, outline.rs push_arc_from_unit_chord) are refused.
+// operation (compiled with -ffp-contract=off). Miter, bevel and round joins; butt, square and round caps (round
+// shapes through Contour::push_arc_from_unit_chord, content/src/outline.rs:632-680: at most four cubic arcs of at
+// most a quarter circle each, content/src/segment.rs:94-122).
 //
 // Geometry helpers follow geometry/src/vector.rs:118-126 (length, normalize = v * (1 / length)),
 // geometry/src/line_segment.rs:219-247 (intersection_t, sample, offset), geometry/src/transform2d.rs:60-72,
@@ -131,6 +132,36 @@ Segment reversed(const Segment &s) {
     return r;
 }
 
+// Matrix2x2F (m11, m21, m12, m22) and Transform2F, with the SIMD formulas of geometry/src/transform2d.rs:45-47,
+// 115-130,301-317 written out lane by lane.
+struct Mat {
+    float m[4];
+};
+struct Xf {
+    Mat matrix;
+    V2 vector;
+};
+inline Mat mat_mul(const Mat &a, const Mat &b) {
+    return Mat{{a.m[0] * b.m[0] + a.m[2] * b.m[1], a.m[1] * b.m[0] + a.m[3] * b.m[1], a.m[0] * b.m[2] + a.m[2] * b.m[3],
+                a.m[1] * b.m[2] + a.m[3] * b.m[3]}};
+}
+inline V2 mat_apply(const Mat &a, V2 v) { return V2{a.m[0] * v.x + a.m[2] * v.y, a.m[1] * v.x + a.m[3] * v.y}; }
+inline V2 xf_apply(const Xf &t, V2 v) { return mat_apply(t.matrix, v) + t.vector; }
+inline Xf xf_mul(const Xf &a, const Xf &b) { return Xf{mat_mul(a.matrix, b.matrix), xf_apply(a, b.vector)}; }
+// Transform2F::from_scale(scale).translate(v) = from_translation(v) * from_scale(scale)
+inline Xf scale_then_translate(float scale, V2 v) {
+    const Xf translation{Mat{{1.0f, 0.0f, 0.0f, 1.0f}}, v}, scaling{Mat{{scale, 0.0f, 0.0f, scale}}, V2{0.0f, 0.0f}};
+    return xf_mul(translation, scaling);
+}
+
+// UnitVector (geometry/src/unit_vector.rs:25-46)
+inline V2 rotate_by(V2 a, V2 b) { return V2{a.x * b.x - a.y * b.y, a.y * b.x + a.x * b.y}; }
+inline V2 rev_rotate_by(V2 a, V2 b) { return V2{a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }
+inline V2 halve_angle(V2 a) {
+    const float px = 0.5f * (1.0f + a.x), py = 0.5f * (1.0f + -a.x);
+    return V2{std::sqrt(px > 0.0f ? px : 0.0f), std::sqrt(py > 0.0f ? py : 0.0f)};
+}
+
 struct Contour {
     std::vector<V2> points;
     std::vector<uint8_t> flags;
@@ -149,12 +180,19 @@ struct Contour {
         }
         push_point(s.baseline.to, 0);
     }
+    // Contour::push_arc_from_unit_chord (outline.rs:632-680), ArcDirection::CW.
+    void push_arc_from_unit_chord(const Xf &transform, V2 chord_from, V2 chord_to);
     // stroke.rs:383-392
     bool might_need_join(uint32_t join) const { return len() >= 2 && join != PF_LINE_JOIN_BEVEL; }
     // stroke.rs:394-431
     void add_join(float distance, uint32_t join, float miter_limit, V2 join_point, Line next_tangent) {
         const Line prev_tangent{points[len() - 2], points[len() - 1]};
         if (prev_tangent.square_length() < EPSILON || next_tangent.square_length() < EPSILON) return;
+        if (join == PF_LINE_JOIN_ROUND) {
+            const Xf transform = scale_then_translate(std::fabs(distance), join_point);
+            push_arc_from_unit_chord(transform, normalize(prev_tangent.to - join_point), normalize(next_tangent.to - join_point));
+            return;
+        }
         if (join != PF_LINE_JOIN_MITER) return;
         float t;
         if (!intersection_t(prev_tangent, next_tangent, t)) return;
@@ -165,6 +203,47 @@ struct Contour {
         push_endpoint(miter_endpoint);
     }
 };
+
+// Segment::arc_from_cos (segment.rs:94-111): a unit arc centred on the +x axis, from below it to above it.
+Segment arc_from_cos(float c) {
+    if (c >= 1.0f - EPSILON) return Segment{LINE, Line{V2{1.0f, 0.0f}, V2{1.0f, 0.0f}}, Line{}};
+    const float p0x = std::sqrt((1.0f + c) * 0.5f), p0y = std::sqrt((1.0f + -c) * 0.5f);
+    const float p1x = 4.0f - p0x, p1y = (1.0f - p0x) * (3.0f - p0x) / p0y;
+    const float third = 1.0f / 3.0f;
+    return Segment{CUBIC, Line{V2{p0x, -p0y}, V2{p0x, p0y}}, Line{V2{p1x * third, -p1y * third}, V2{p1x * third, p1y * third}}};
+}
+// Segment::quarter_circle_arc (segment.rs:116-122)
+Segment quarter_circle_arc() {
+    const float sqrt2 = 1.41421356237309504880168872420969808f;
+    const V2 p0{sqrt2 * 0.5f, sqrt2 * 0.5f};
+    const V2 p1{-sqrt2 / 6.0f + 4.0f / 3.0f, 7.0f * sqrt2 / 6.0f - 4.0f / 3.0f};
+    return Segment{CUBIC, Line{V2{p0.x, -p0.y}, p0}, Line{V2{p1.x, -p1.y}, p1}};
+}
+
+void Contour::push_arc_from_unit_chord(const Xf &transform, V2 chord_from, V2 chord_to) {
+    V2 vector = chord_from;
+    const V2 end_vector = chord_to;
+    for (int segment_index = 0; segment_index < 4; segment_index++) {
+        V2 sweep = rev_rotate_by(end_vector, vector);
+        const bool last = sweep.x >= -EPSILON && sweep.y >= -EPSILON;
+        Segment segment;
+        if (!last) {
+            sweep = V2{0.0f, 1.0f};
+            segment = quarter_circle_arc();
+        } else {
+            segment = arc_from_cos(sweep.x);
+        }
+        const V2 r = rotate_by(halve_angle(sweep), vector);
+        const Xf rotation{Mat{{r.x, r.y, -r.y, r.x}}, V2{0.0f, 0.0f}}; // Matrix2x2F::from_rotation_vector
+        const Xf identity{Mat{{1.0f, 0.0f, 0.0f, 1.0f}}, V2{0.0f, 0.0f}};
+        const Xf t = xf_mul(xf_mul(transform, identity), rotation); // transform * direction_transform * rotation
+        segment.baseline = Line{xf_apply(t, segment.baseline.from), xf_apply(t, segment.baseline.to)};
+        if (segment.kind != LINE) segment.ctrl = Line{xf_apply(t, segment.ctrl.from), xf_apply(t, segment.ctrl.to)};
+        push_segment(segment);
+        if (last) break;
+        vector = rotate_by(vector, sweep);
+    }
+}
 
 struct Stroker {
     uint32_t join;
@@ -272,7 +351,7 @@ std::vector<Segment> contour_segments(const V2 *pts, const uint8_t *flags, uint3
     return out;
 }
 
-// OutlineStrokeToFill::add_cap (stroke.rs:151-199), square caps.
+// OutlineStrokeToFill::add_cap (stroke.rs:151-199).
 void add_cap(Contour &c, uint32_t cap, float width) {
     if (cap == PF_LINE_CAP_BUTT || c.len() < 2) return;
     const V2 p1 = c.points[c.len() - 1];
@@ -285,6 +364,12 @@ void add_cap(Contour &c, uint32_t cap, float width) {
         i--;
     }
     const V2 gradient = normalize(p1 - p0);
+    if (cap == PF_LINE_CAP_ROUND) {
+        const V2 offset = V2{gradient.y, gradient.x} * V2{-1.0f, 1.0f};
+        const Xf transform = scale_then_translate(width * 0.5f, p1 + offset * (width * 0.5f));
+        c.push_arc_from_unit_chord(transform, V2{-offset.x, -offset.y}, offset);
+        return;
+    }
     const V2 offset = gradient * (width * 0.5f);
     const V2 p2 = p1 + offset;
     const V2 p3 = p2 + V2{gradient.y, gradient.x} * V2{-width, width};
@@ -311,9 +396,8 @@ PFOutlineRef PFOutlineStrokeToFill(const PFVector2F *points, const uint8_t *poin
         pf::set_last_error("PFOutlineStrokeToFill: null argument");
         return nullptr;
     }
-    if (style->line_cap == PF_LINE_CAP_ROUND || style->line_join == PF_LINE_JOIN_ROUND || style->line_cap > 2 ||
-        style->line_join > 2) {
-        pf::set_last_error("round caps and joins are not implemented (SURVEY.md §8 f2)");
+    if (style->line_cap > PF_LINE_CAP_ROUND || style->line_join > PF_LINE_JOIN_ROUND) {
+        pf::set_last_error("PFOutlineStrokeToFill: unknown line cap or line join");
         return nullptr;
     }
     const float radius = style->line_width * 0.5f;

@@ -87,11 +87,95 @@ def polygon_area_flattened(pts, flags, steps=32):
     return polygon_area(np.asarray(out))
 
 
-def test_round_joins_and_caps_are_refused():
-    for kw in ({"line_join": "round"}, {"line_cap": "round"}):
-        with pytest.raises(L.PathfinderCudaError) as e:
-            api.stroke_to_fill([(0, 0), (10, 0)], [0, 0], [0, 2], [0], line_width=2.0, **kw)
-        assert e.value.status == L.PF_CUDA_ERROR_UNSUPPORTED
+def flatten(pts, flags, steps=24):
+    out, i, n = [], 0, len(pts)
+    while i < n:
+        if flags[i] == 0:
+            out.append(np.asarray(pts[i], np.float64)); i += 1
+            continue
+        p0, ctrl = out[-1], [np.asarray(pts[i], np.float64)]
+        if flags[i + 1] != 0:
+            ctrl.append(np.asarray(pts[i + 1], np.float64))
+        p_end = np.asarray(pts[i + len(ctrl)], np.float64)
+        for s in range(1, steps + 1):
+            t = s / steps
+            if len(ctrl) == 1:
+                out.append((1 - t) ** 2 * p0 + 2 * t * (1 - t) * ctrl[0] + t * t * p_end)
+            else:
+                out.append((1 - t) ** 3 * p0 + 3 * t * (1 - t) ** 2 * ctrl[0] + 3 * t * t * (1 - t) * ctrl[1] + t ** 3 * p_end)
+        i += len(ctrl) + 1
+    return np.asarray(out)
+
+
+def winding_area(pts, flags, offs, lo, hi, step=0.05):
+    """Area where the winding number of the (closed) contours is non-zero, by sampling a regular grid."""
+    xs = np.arange(lo[0] + step / 2, hi[0], step)
+    ys = np.arange(lo[1] + step / 2, hi[1], step)
+    gx, gy = np.meshgrid(xs, ys)
+    winding = np.zeros(gx.shape, np.int32)
+    for c in range(len(offs) - 1):
+        poly = flatten(pts[offs[c]:offs[c + 1]], flags[offs[c]:offs[c + 1]])
+        a, b = poly, np.roll(poly, -1, axis=0)
+        for (x0, y0), (x1, y1) in zip(a, b):
+            if y0 == y1:
+                continue
+            up = (y0 <= gy) & (gy < y1)
+            down = (y1 <= gy) & (gy < y0)
+            xi = x0 + (gy - y0) * (x1 - x0) / (y1 - y0)
+            winding += (up & (xi > gx)).astype(np.int32) - (down & (xi > gx)).astype(np.int32)
+    return float((winding != 0).sum()) * step * step
+
+
+def test_round_caps_are_half_discs():
+    """A line with round caps: rectangle plus one disc of the stroke's radius; every arc point lies on the circle
+    around the end point (Contour::push_arc_from_unit_chord, outline.rs:632-680)."""
+    pts, flags, offs = api.stroke_to_fill([(20, 30), (70, 30)], [0, 0], [0, 2], [0], line_width=8.0, line_cap="round")
+    assert len(offs) == 2 and flags.any()
+    area = polygon_area_flattened(pts, flags)
+    assert abs(area - (50 * 8 + np.pi * 16)) < 0.05
+    on_curve = pts[flags == 0]
+    right = on_curve[on_curve[:, 0] > 70 + 1e-3]
+    left = on_curve[on_curve[:, 0] < 20 - 1e-3]
+    assert len(right) and len(left)
+    assert np.allclose(np.hypot(right[:, 0] - 70, right[:, 1] - 30), 4.0, atol=1e-4)
+    assert np.allclose(np.hypot(left[:, 0] - 20, left[:, 1] - 30), 4.0, atol=1e-4)
+    assert abs(pts[:, 0].max() - 74) < 1e-3 and abs(pts[:, 0].min() - 16) < 1e-3
+
+
+def test_joins_fill_the_outer_corner():
+    """A right-angle polyline, filled with the winding rule: the union of the two legs, plus on the outer side of
+    the corner the full square (miter), half of it (bevel) or a quarter disc (round)."""
+    corner = [(10, 10), (60, 10), (60, 50)]
+    w, r = 6.0, 3.0
+    union = 50 * w + 40 * w - r * r
+    expected = {"miter": union + r * r, "bevel": union + 0.5 * r * r, "round": union + 0.25 * np.pi * r * r}
+    for join, want in expected.items():
+        pts, flags, offs = api.stroke_to_fill(corner, [0] * 3, [0, 3], [0], line_width=w, line_join=join, miter_limit=10.0)
+        assert len(offs) == 2
+        got = winding_area(pts, flags, offs, (0, 0), (70, 60))
+        assert abs(got - want) < 0.15, (join, got, want)
+
+
+def test_closed_circle_with_round_joins_is_an_annulus():
+    """A circle of four cubics, stroked and filled with the winding rule: an annulus. (Round joins are always drawn
+    clockwise, so on one side of the path they go the long way round — inside the stroke, where they change nothing.)"""
+    k, R = 0.5522847498 * 40, 40.0
+    c = [(R, 0), (R, k), (k, R), (0, R), (-k, R), (-R, k), (-R, 0), (-R, -k), (-k, -R), (0, -R), (k, -R), (R, -k), (R, 0)]
+    f = [0, 1, 2] * 4 + [0]
+    for join in ("round", "bevel"):
+        pts, flags, offs = api.stroke_to_fill(np.asarray(c) + 64, f, [0, 13], [1], line_width=10.0, line_join=join)
+        assert len(offs) == 3
+        got = winding_area(pts, flags, offs, (10, 10), (118, 118), step=0.25)
+        assert abs(got - np.pi * (45 ** 2 - 35 ** 2)) < 8.0, (join, got)
+
+
+def test_unknown_styles_are_refused():
+    style = L.PFStrokeStyle(2.0, 7, 0, 4.0)
+    pts = np.zeros((2, 2), np.float32)
+    flags, offs, closed = np.zeros(2, np.uint8), np.array([0, 2], np.uint32), np.zeros(1, np.uint8)
+    import ctypes as C
+    assert not L.lib().PFOutlineStrokeToFill(pts.ctypes.data, flags.ctypes.data, offs.ctypes.data, closed.ctypes.data, 1, C.byref(style))
+    assert b"unknown" in L.lib().PFCudaGetLastError()
 
 
 @pytest.mark.skipif(not os.path.exists(TIGER_SVG), reason="needs the reference's tiger SVG (build container only)")
