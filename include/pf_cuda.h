@@ -458,7 +458,14 @@ uint32_t PFOutlineGetContourCount(PFOutlineRef outline);
 size_t PFOutlineGetPointCount(PFOutlineRef outline);
 /* points / point_flags: PFOutlineGetPointCount entries; contour_offsets: PFOutlineGetContourCount + 1. */
 void PFOutlineCopy(PFOutlineRef outline, PFVector2F *points, uint8_t *point_flags, uint32_t *contour_offsets);
+/* closed: one flag per contour (PFOutlineGetContourCount entries). */
+void PFOutlineCopyClosed(PFOutlineRef outline, uint8_t *closed);
 void PFOutlineDestroy(PFOutlineRef outline);
+
+/* SVG path data ("M10 10 C ... z") -> outline: absolute and relative commands, implicit repetition, smooth curves,
+ * arcs as cubics (one per <= 90 degrees). The reference gets this from usvg 0.9.1 (svg/src/lib.rs:386-456), which
+ * is not vendored: parity unpinned, W3C SVG 1.1 rules followed. Returns NULL on malformed data. */
+PFOutlineRef PFSvgPathDataToOutline(const char *path_data);
 
 /* Scene::build_and_render (scene.rs:369-378) against the CUDA renderer: begin_scene, build with a
  * listener forwarding to PFCudaRendererRenderCommand, end_scene. Borrows everything

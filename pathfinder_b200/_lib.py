@@ -243,7 +243,9 @@ SIGNATURES = {
     "PFOutlineGetContourCount": (C.c_uint32, [C.c_void_p]),
     "PFOutlineGetPointCount": (C.c_size_t, [C.c_void_p]),
     "PFOutlineCopy": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "PFOutlineCopyClosed": (None, [C.c_void_p, C.c_void_p]),
     "PFOutlineDestroy": (None, [C.c_void_p]),
+    "PFSvgPathDataToOutline": (C.c_void_p, [C.c_char_p]),
     "PFScenePushClipPath": (C.c_uint32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_uint8, C.c_uint32]),
     "PFScenePushDrawPaths": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,

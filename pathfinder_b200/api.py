@@ -204,6 +204,23 @@ def stroke_to_fill(points, point_flags, contour_offsets, contour_closed, line_wi
     return out_p, out_f, out_c
 
 
+def svg_path_to_outline(path_data: str):
+    """SVG path data -> (points, point_flags, contour_offsets, contour_closed), see PFSvgPathDataToOutline."""
+    lib = L.lib()
+    h = lib.PFSvgPathDataToOutline(path_data.encode("utf-8"))
+    if not h:
+        raise L.PathfinderCudaError(L.PF_CUDA_ERROR_INVALID_ARGUMENT, lib.PFCudaGetLastError().decode("utf-8", "replace"))
+    try:
+        n, k = int(lib.PFOutlineGetPointCount(h)), int(lib.PFOutlineGetContourCount(h))
+        pts, flags = np.zeros((n, 2), np.float32), np.zeros(n, np.uint8)
+        offsets, closed = np.zeros(k + 1, np.uint32), np.zeros(k, np.uint8)
+        lib.PFOutlineCopy(h, pts.ctypes.data, flags.ctypes.data, offsets.ctypes.data)
+        lib.PFOutlineCopyClosed(h, closed.ctypes.data)
+    finally:
+        lib.PFOutlineDestroy(h)
+    return pts, flags, offsets, closed
+
+
 def ipc_export(device_ptr: int):
     """(handle bytes, offset) of a device allocation, to be opened by peer processes."""
     h = (C.c_uint8 * 64)()

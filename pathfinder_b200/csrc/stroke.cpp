@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/pf_cuda.h"
+#include "outline.h"
 
 namespace pf {
 void set_last_error(const std::string &msg);
@@ -381,12 +382,6 @@ void add_cap(Contour &c, uint32_t cap, float width) {
 
 } // namespace
 
-struct PFOutline {
-    std::vector<PFVector2F> points;
-    std::vector<uint8_t> flags;
-    std::vector<uint32_t> contour_offsets{0};
-};
-
 extern "C" {
 
 // OutlineStrokeToFill::{new, offset, into_outline} (stroke.rs:88-131).
@@ -413,6 +408,7 @@ PFOutlineRef PFOutlineStrokeToFill(const PFVector2F *points, const uint8_t *poin
             out->flags.push_back(c.flags[i]);
         }
         out->contour_offsets.push_back((uint32_t)out->points.size());
+        out->closed.push_back(1); // stroker.output.closed = true (stroke.rs:148)
     };
     for (uint32_t ci = 0; ci < contour_count; ci++) {
         const uint32_t p0 = contour_offsets[ci], n = contour_offsets[ci + 1] - p0;
@@ -447,6 +443,11 @@ void PFOutlineCopy(PFOutlineRef outline, PFVector2F *points, uint8_t *point_flag
     if (points && !outline->points.empty()) memcpy(points, outline->points.data(), outline->points.size() * sizeof(PFVector2F));
     if (point_flags && !outline->flags.empty()) memcpy(point_flags, outline->flags.data(), outline->flags.size());
     if (contour_offsets) memcpy(contour_offsets, outline->contour_offsets.data(), outline->contour_offsets.size() * sizeof(uint32_t));
+}
+
+/* closed: PFOutlineGetContourCount flags. */
+void PFOutlineCopyClosed(PFOutlineRef outline, uint8_t *closed) {
+    if (outline && closed && !outline->closed.empty()) memcpy(closed, outline->closed.data(), outline->closed.size());
 }
 
 void PFOutlineDestroy(PFOutlineRef outline) { delete outline; }
