@@ -287,3 +287,29 @@ def test_tiger_fixture_is_reproducible():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "tools/make_tiger_scene.py", "--check"], cwd=root, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_strip_partition_and_threading_on_fuzzed_scenes(area_lut):
+    """The oracle itself, on the seeded fuzz scenes the GPU tests use: uneven strips partition the tile lists and
+    reproduce the frame; a threaded build equals the sequential one up to alpha tile numbering."""
+    from tests.test_parity_gpu import fuzz_scene
+    key = lambda t: (int(t["path_id"]), int(t["tile_y"]), int(t["tile_x"]), int(t["backdrop"]), int(t["alpha_tile_id"] == INVALID))
+    for seed in range(0, 60, 3):
+        flat, xf, (w, h) = fuzz_scene(seed, rotate=seed % 2 == 0)
+        full = H.oracle_build(flat, xf)
+        full_img = full.render(area_lut, w, h, background=(1, 1, 1, 1))
+        rows = (h + 15) // 16
+        cuts = sorted({0, rows // 3, (2 * rows + 2) // 3, rows})
+        got, fills = [], 0
+        stitched = np.zeros_like(full_img)
+        for y0, y1 in zip(cuts[:-1], cuts[1:]):
+            part = H.oracle_build(flat, xf, strip=(y0, y1))
+            got += [key(t) for t in part.tiles]
+            fills += len(part.fills)
+            img = part.render(area_lut, w, h, background=(1, 1, 1, 1))
+            stitched[y0 * 16:y1 * 16] = img[y0 * 16:y1 * 16]
+        assert sorted(got) == sorted(key(t) for t in full.tiles), seed
+        assert fills == len(full.fills) and np.array_equal(stitched, full_img), seed
+        threaded = H.oracle_build(flat, xf, n_threads=4)
+        assert sorted(key(t) for t in threaded.tiles) == sorted(key(t) for t in full.tiles), seed
+        assert len(threaded.fills) == len(full.fills) and threaded.alpha_tile_count == full.alpha_tile_count, seed
