@@ -48,6 +48,8 @@ def workload_scenes(which: str):
         out.append(("random100k@8192", scenes.random_paths(100000, 8192, 0x5EED0004), None, 8192))
     if which == "random1m":
         out.append(("random1m@16384", scenes.random_paths(1000000, 16384, 0x5EED0005), None, 16384))
+    if which == "text10k":
+        out.append(("text10k@2048", scenes.text_page(10000, 2048), None, 2048))
     if which == "smoke":
         flat, xf = scenes.tiger(512)
         out.append(("tiger@512", flat, xf, 512))
@@ -61,6 +63,7 @@ WORKLOAD_NAMES = {
     "tiger4k": "tiger@4096 (winding + even-odd variants)",
     "random100k": "random100k@8192",
     "random1m": "random1m@16384",
+    "text10k": "text page: 10,000 Roboto glyphs at 12-16 px @2048 (outlines only)",
     "smoke": "tiger@512",
 }
 

@@ -313,3 +313,56 @@ def test_strip_partition_and_threading_on_fuzzed_scenes(area_lut):
         threaded = H.oracle_build(flat, xf, n_threads=4)
         assert sorted(key(t) for t in threaded.tiles) == sorted(key(t) for t in full.tiles), seed
         assert len(threaded.fills) == len(full.fills) and threaded.alpha_tile_count == full.alpha_tile_count, seed
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/resources/fonts/Roboto-Regular.ttf"),
+                    reason="the reference checkout (and its fonts) is only present in the build container")
+def test_glyph_fixture_is_reproducible():
+    """tests/golden/roboto_glyphs.npz is what tools/make_glyph_fixture.py reads out of the reference's Roboto-Regular.ttf."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "tools/make_glyph_fixture.py", "--check"], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def _contour_area(pts, flags):
+    """Signed area of a closed contour of lines and quadratics (flag 1 = control point): Green's theorem, with
+    integral(B x B') = 2/3 (p0 x c) + 2/3 (c x p1) + 1/3 (p0 x p1) for a quadratic."""
+    cross = lambda a, b: float(a[0]) * float(b[1]) - float(a[1]) * float(b[0])
+    total, i, n = 0.0, 0, len(pts)
+    while i + 1 < n:
+        if flags[i + 1] == 1:
+            p0, c, p1 = pts[i], pts[i + 1], pts[i + 2]
+            total += (2 * cross(p0, c) + 2 * cross(c, p1) + cross(p0, p1)) / 3.0
+            i += 2
+        else:
+            total += cross(pts[i], pts[i + 1])
+            i += 1
+    total += cross(pts[n - 1], pts[0])  # the implicit closing line
+    return total / 2.0
+
+
+def test_text_page_scene(area_lut):
+    """The text-page scene (BASELINE.json configs[2], outlines only): one small winding-rule path per glyph. The
+    rendered ink equals the analytic area of the glyph outlines (holes are opposite-wound contours of the same path)."""
+    n, size = 300, 384
+    flat = scenes.text_page(n, size)
+    assert len(flat.fill_rules) == n and (flat.fill_rules == 0).all()
+    again = scenes.text_page(n, size)
+    assert np.array_equal(flat.points, again.points) and np.array_equal(flat.contour_offsets, again.contour_offsets)
+    assert flat.points.min() >= 0 and flat.points.max() <= size
+    assert (np.asarray(flat.point_flags) <= 1).all()  # TrueType outlines: lines and quadratics only
+
+    co = np.asarray(flat.contour_offsets)
+    ink = 0.0
+    for p in range(n):
+        c0, c1 = int(flat.path_contour_offsets[p]), int(flat.path_contour_offsets[p + 1])
+        ink += abs(sum(_contour_area(flat.points[co[c]:co[c + 1]], flat.point_flags[co[c]:co[c + 1]]) for c in range(c0, c1)))
+
+    b = H.oracle_build(flat, None)
+    assert len(b.fills) > 0 and b.alpha_tile_count > 0
+    img = b.render(area_lut, size, size)
+    assert (img[:, :, :3][img[:, :, 3] > 0] == 0).all()  # black ink only
+    rendered = img[:, :, 3].astype(np.float64).sum() / 255.0
+    assert abs(rendered - ink) <= 0.02 * ink

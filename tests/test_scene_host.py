@@ -127,6 +127,17 @@ def test_random_scene_rects_match_cpu_tiler():
     assert draw["tile_count"] == built.bbox_tile_count
 
 
+def test_text_page_rects_match_cpu_tiler():
+    """Many tiny paths of quadratics (BASELINE.json configs[2] outlines): same dense tile maps and segment count."""
+    flat = scenes.text_page(2000, 1024)
+    cmds = collect(api.Scene.from_flat(flat), api.BuildOptions())
+    draw = [c for c in cmds if c["kind"] == "DrawTilesD3D11"][0]
+    built = H.oracle_build(flat, None)
+    assert draw["path_count"] == 2000
+    assert draw["tile_count"] == built.bbox_tile_count
+    assert draw["segment_count"] == built.input_segment_count
+
+
 def test_unsupported_options_are_refused():
     flat = small_scene()
     with pytest.raises(L.PathfinderCudaError) as e:
