@@ -136,18 +136,19 @@ def _glyph_fixture():
     return _GLYPHS
 
 
-def text_page(n_glyphs: int = 10000, size: int = 2048, seed: int = 0x5EED0007, px_min: float = 12.0,
-              px_max: float = 16.0) -> FlatScene:
-    """BASELINE.json configs[2], outlines only: `n_glyphs` glyphs of Roboto Regular (tests/golden/roboto_glyphs.npz,
-    built by tools/make_glyph_fixture.py) set in lines of random words at 12-16 px on a size x size page, one path per
-    glyph, black on white, winding rule. Many tiny paths of quadratics: the opposite regime of the tiger. (Subpixel AA,
-    stem darkening and the gamma LUT of the reference's text demo are SURVEY.md §8 f3 and not applied.)"""
+def text_page(n_glyphs: int = 10000, size: int = 2048, seed: int = 0x5EED0003, layout: str = "grid") -> FlatScene:
+    """BASELINE.json configs[2] / SURVEY.md §8d config 3, outlines only: `n_glyphs` glyphs of Roboto Regular
+    (tests/golden/roboto_glyphs.npz, built by tools/make_glyph_fixture.py), sizes uniform in {12..16} px, one path per
+    glyph, black, winding rule, on a size x size page. layout "grid" (config 3): glyph ids uniform over the printable
+    ASCII set, one glyph per cell of a ceil(sqrt(n))^2 grid; "lines": lines of random lower-case words, which puts
+    neighbouring glyphs in the same tiles like running text does. Many tiny paths of quadratics: the opposite regime
+    of the tiger. (Subpixel AA, stem darkening and the text filter of the reference's demo are §8 f3, not applied.)"""
     g = _glyph_fixture()
     upem = float(g["units_per_em"])
     codes, advances = g["codes"], g["advances"].astype(np.float64)
     letters = np.nonzero((codes >= ord("a")) & (codes <= ord("z")))[0]
-    others = np.arange(len(codes))
-    stream = splitmix64(seed, 0, 4 * n_glyphs + 4096)  # more draws than the layout can use
+    n_codes = len(codes)
+    stream = splitmix64(seed, 0, 4 * n_glyphs + 4096)  # more draws than either layout can use
     cursor = [0]
 
     def rnd() -> int:
@@ -155,42 +156,56 @@ def text_page(n_glyphs: int = 10000, size: int = 2048, seed: int = 0x5EED0007, p
         return int(stream[cursor[0] - 1])
 
     points, flags, contour_offsets, path_contour_offsets = [], [], [0], [0]
-    margin = 0.04 * size
-    y = margin
-    placed = 0
-    while placed < n_glyphs:
-        px = px_min + (px_max - px_min) * (rnd() % 1000) / 999.0
-        scale = px / upem
-        y += 1.3 * px
-        if y > size - margin:  # page full: start over at the top, shifted, so any glyph count fits
-            y = margin + 1.3 * px + 0.37 * px
-        x = margin
+
+    def place(gi: int, x: float, y: float, scale: float):
+        c0, c1 = int(g["glyph_contours"][gi]), int(g["glyph_contours"][gi + 1])
+        for c in range(c0, c1):
+            p0, p1 = int(g["contour_offsets"][c]), int(g["contour_offsets"][c + 1])
+            pts = g["points"][p0:p1].astype(np.float64)
+            out = np.empty_like(pts)
+            out[:, 0] = x + pts[:, 0] * scale
+            out[:, 1] = y - pts[:, 1] * scale
+            # (a contour whose last segment is a curve ends on a copy of its first point, as pathfinder's
+            # contours do: the implicit closing line is then empty)
+            points.append(out)
+            flags.append(g["point_flags"][p0:p1])
+            contour_offsets.append(contour_offsets[-1] + len(out))
+        path_contour_offsets.append(len(contour_offsets) - 1)
+
+    if layout == "grid":
+        side = int(np.ceil(np.sqrt(n_glyphs)))
+        cell = size / side
+        for i in range(n_glyphs):
+            px = 12 + rnd() % 5
+            gi = rnd() % n_codes
+            place(gi, (i % side) * cell + 0.15 * cell, (i // side) * cell + 0.75 * cell, px / upem)
+    elif layout == "lines":
+        margin = 0.04 * size
+        y = margin
+        placed = 0
         while placed < n_glyphs:
-            word = 1 + rnd() % 9
-            glyph_ids = [int(letters[rnd() % len(letters)]) if rnd() % 8 else int(others[rnd() % len(others)]) for _ in range(word)]
-            word_width = float(sum(advances[i] for i in glyph_ids)) * scale
-            if x + word_width > size - margin:
-                break
-            for gi in glyph_ids:
-                if placed >= n_glyphs:
+            px = 12 + rnd() % 5
+            scale = px / upem
+            y += 1.3 * px
+            if y > size - margin:  # page full: start over at the top, shifted, so any glyph count fits
+                y = margin + 1.3 * px + 0.37 * px
+            x = margin
+            while placed < n_glyphs:
+                word = 1 + rnd() % 9
+                glyph_ids = [int(letters[rnd() % len(letters)]) if rnd() % 8 else rnd() % n_codes for _ in range(word)]
+                word_width = float(sum(advances[i] for i in glyph_ids)) * scale
+                if x + word_width > size - margin:
                     break
-                c0, c1 = int(g["glyph_contours"][gi]), int(g["glyph_contours"][gi + 1])
-                for c in range(c0, c1):
-                    p0, p1 = int(g["contour_offsets"][c]), int(g["contour_offsets"][c + 1])
-                    pts = g["points"][p0:p1].astype(np.float64)
-                    out = np.empty_like(pts)
-                    out[:, 0] = x + pts[:, 0] * scale
-                    out[:, 1] = y - pts[:, 1] * scale
-                    # (a contour whose last segment is a curve ends on a copy of its first point, as pathfinder's
-                    # contours do: the implicit closing line is then empty)
-                    points.append(out)
-                    flags.append(g["point_flags"][p0:p1])
-                    contour_offsets.append(contour_offsets[-1] + len(out))
-                path_contour_offsets.append(len(contour_offsets) - 1)
-                placed += 1
-                x += float(advances[gi]) * scale
-            x += float(g["space_advance"]) * scale
+                for gi in glyph_ids:
+                    if placed >= n_glyphs:
+                        break
+                    place(gi, x, y, scale)
+                    placed += 1
+                    x += float(advances[gi]) * scale
+                x += float(g["space_advance"]) * scale
+    else:
+        raise ValueError(f"unknown layout {layout!r}")
     n_paths = len(path_contour_offsets) - 1
     return FlatScene(np.concatenate(points).astype(np.float32), np.concatenate(flags), contour_offsets, path_contour_offsets,
                      np.zeros(n_paths, np.uint8), np.zeros(n_paths, np.uint16), np.asarray([[0, 0, 0, 255]], np.uint8),
-                     (0.0, 0.0, float(size), float(size)), f"text{n_glyphs}@{size}")
+                     (0.0, 0.0, float(size), float(size)), f"text{n_glyphs}@{size}/{layout}", {"seed": seed, "size": size})

@@ -343,13 +343,14 @@ def _contour_area(pts, flags):
     return total / 2.0
 
 
-def test_text_page_scene(area_lut):
+@pytest.mark.parametrize("layout", ["grid", "lines"])
+def test_text_page_scene(area_lut, layout):
     """The text-page scene (BASELINE.json configs[2], outlines only): one small winding-rule path per glyph. The
     rendered ink equals the analytic area of the glyph outlines (holes are opposite-wound contours of the same path)."""
     n, size = 300, 384
-    flat = scenes.text_page(n, size)
+    flat = scenes.text_page(n, size, layout=layout)
     assert len(flat.fill_rules) == n and (flat.fill_rules == 0).all()
-    again = scenes.text_page(n, size)
+    again = scenes.text_page(n, size, layout=layout)
     assert np.array_equal(flat.points, again.points) and np.array_equal(flat.contour_offsets, again.contour_offsets)
     assert flat.points.min() >= 0 and flat.points.max() <= size
     assert (np.asarray(flat.point_flags) <= 1).all()  # TrueType outlines: lines and quadratics only

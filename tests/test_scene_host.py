@@ -129,7 +129,7 @@ def test_random_scene_rects_match_cpu_tiler():
 
 def test_text_page_rects_match_cpu_tiler():
     """Many tiny paths of quadratics (BASELINE.json configs[2] outlines): same dense tile maps and segment count."""
-    flat = scenes.text_page(2000, 1024)
+    flat = scenes.text_page(2000, 1024, layout="lines")
     cmds = collect(api.Scene.from_flat(flat), api.BuildOptions())
     draw = [c for c in cmds if c["kind"] == "DrawTilesD3D11"][0]
     built = H.oracle_build(flat, None)
