@@ -467,6 +467,14 @@ void PFOutlineDestroy(PFOutlineRef outline);
  * is not vendored: parity unpinned, W3C SVG 1.1 rules followed. Returns NULL on malformed data. */
 PFOutlineRef PFSvgPathDataToOutline(const char *path_data);
 
+/* Outline::dilate (content/src/outline.rs:243-249; ContourDilator, content/src/dilation.rs:34-125) in place on an
+ * outline given as flat arrays: every distinct position moves along the bisector of its neighbouring edges by
+ * `amount` per axis, outwards for the outline's outermost winding (Orientation::from_outline). This is the stem
+ * darkening of the text path; PFSceneBuild applies it itself when the build options carry a
+ * dilation, after the transform, as Scene::apply_render_options does (renderer/src/scene.rs:249-270). */
+void PFOutlineDilate(PFVector2F *points, const uint32_t *contour_offsets, uint32_t contour_count,
+                     const PFVector2F *amount);
+
 /* Scene::build_and_render (scene.rs:369-378) against the CUDA renderer: begin_scene, build with a
  * listener forwarding to PFCudaRendererRenderCommand, end_scene. Borrows everything
  * (as PFSceneProxyBuildAndRenderGL, c/src/lib.rs:672-681). */

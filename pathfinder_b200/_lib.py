@@ -246,6 +246,7 @@ SIGNATURES = {
     "PFOutlineCopyClosed": (None, [C.c_void_p, C.c_void_p]),
     "PFOutlineDestroy": (None, [C.c_void_p]),
     "PFSvgPathDataToOutline": (C.c_void_p, [C.c_char_p]),
+    "PFOutlineDilate": (None, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "PFScenePushClipPath": (C.c_uint32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_uint8, C.c_uint32]),
     "PFScenePushDrawPaths": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,

@@ -204,6 +204,15 @@ def stroke_to_fill(points, point_flags, contour_offsets, contour_closed, line_wi
     return out_p, out_f, out_c
 
 
+def dilate_outline(points, contour_offsets, amount):
+    """Outline::dilate (content/src/outline.rs:243-249) on flat arrays; returns the moved points."""
+    pts = np.array(points, dtype=np.float32).reshape(-1, 2)
+    co = np.ascontiguousarray(contour_offsets, dtype=np.uint32)
+    a = L.PFVector2F(float(amount[0]), float(amount[1]))
+    L.lib().PFOutlineDilate(pts.ctypes.data, co.ctypes.data, len(co) - 1, C.byref(a))
+    return pts
+
+
 def svg_path_to_outline(path_data: str):
     """SVG path data -> (points, point_flags, contour_offsets, contour_closed), see PFSvgPathDataToOutline."""
     lib = L.lib()

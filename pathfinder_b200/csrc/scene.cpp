@@ -24,6 +24,7 @@
 
 #include "../../include/pf_cuda.h"
 #include "common.cuh"
+#include "dilate.h"
 
 #include <cuda_runtime.h>
 
@@ -158,6 +159,13 @@ struct PFScene {
     uint32_t built_clip_tile_count = 0, built_clip_segment_count = 0, built_clipped_path_count = 0,
              built_clipped_tile_count = 0;
     std::vector<uint32_t> seg_path_offsets; // per-path output offsets of build_segments
+    // BuildOptions with a dilation (prepare_paths): the points after Scene::apply_render_options, same layout as
+    // `points`, and the bounds the CPU tiler sees for every path. segments_key identifies what the segment arrays
+    // currently hold (scene epoch x prepared options); upload_serial counts their rewrites for the sinks.
+    std::vector<PFVector2F> prepared_points;
+    std::vector<RectF> prepared_draw_bounds, prepared_clip_bounds;
+    uint64_t segments_key = 0;
+    uint32_t upload_serial = 0;
     std::vector<PFRectI> path_tile_rects;   // scratch of the batch build (kept == rect non-empty)
     std::vector<uint32_t> path_batch_offsets;
     std::vector<uint32_t> draw_segment_ranges; // [n_draw][2]
@@ -247,7 +255,8 @@ void wait_for_borrowers(PFScene *s) {
 }
 
 // SegmentsD3D11::add_path for every path of one kind (builder.rs:817-857).
-void build_path_segments(PFScene *s, const std::vector<Path> &paths, HostBuffer<PFVector2F> &seg_points,
+void build_path_segments(PFScene *s, const PFVector2F *scene_points, const std::vector<Path> &paths,
+                         HostBuffer<PFVector2F> &seg_points,
                          HostBuffer<PFSegmentIndicesD3D11> &seg_indices, size_t &seg_point_count, size_t &seg_index_count,
                          std::vector<uint32_t> &path_offsets, std::vector<uint32_t> &segment_ranges) {
     const size_t n_paths = paths.size();
@@ -274,7 +283,7 @@ void build_path_segments(PFScene *s, const std::vector<Path> &paths, HostBuffer<
             for (uint32_t c = path.first_contour; c < path.end_contour; c++) {
                 const uint32_t p0 = s->contour_offsets[c], point_count = s->contour_offsets[c + 1] - p0;
                 const uint8_t *flags = s->flags.data() + p0;
-                const PFVector2F *pts = s->points.data() + p0;
+                const PFVector2F *pts = scene_points + p0;
                 memcpy(out_points + wp, pts, (size_t)point_count * sizeof(PFVector2F));
                 for (uint32_t i = 0; i < point_count; i++) {
                     if (flags[i] & ctrl_mask) continue;
@@ -295,12 +304,48 @@ void build_path_segments(PFScene *s, const std::vector<Path> &paths, HostBuffer<
     seg_index_count = ni;
 }
 
-void build_segments(PFScene *s) {
+// `scene_points`: the scene's own points, or their prepared copy.
+void build_segments(PFScene *s, const PFVector2F *scene_points) {
     wait_for_borrowers(s);
-    build_path_segments(s, s->draw_paths, s->seg_points, s->seg_indices, s->seg_point_count, s->seg_index_count,
+    build_path_segments(s, scene_points, s->draw_paths, s->seg_points, s->seg_indices, s->seg_point_count, s->seg_index_count,
                         s->seg_path_offsets, s->draw_segment_ranges);
-    build_path_segments(s, s->clip_paths, s->clip_seg_points, s->clip_seg_indices, s->clip_seg_point_count,
+    build_path_segments(s, scene_points, s->clip_paths, s->clip_seg_points, s->clip_seg_indices, s->clip_seg_point_count,
                         s->clip_seg_index_count, s->clip_seg_path_offsets, s->clip_segment_ranges);
+}
+
+// Scene::apply_render_options, 2-D branch (renderer/src/scene.rs:249-270), for every path of one kind, when the
+// build options carry a dilation: transform the points (Outline::transform, outline.rs:208-221, skipped for the
+// identity), recompute the bounds over all points, dilate (dilate.cpp) and grow the bounds by the amount
+// (Outline::dilate, outline.rs:243-249). The reference's D3D11 builder drops the dilation (options.rs:165-180 hands
+// only the transform to the GPU); the CPU tiler, which is the parity target, applies it here, so the host does the
+// same and the device then dices already-prepared points under an identity transform.
+void prepare_paths(PFScene *s, const std::vector<Path> &paths, const Transform &xf, const float dilation[2],
+                   std::vector<RectF> &bounds_out) {
+    bounds_out.resize(paths.size());
+    const bool identity = xf.is_identity();
+    PFVector2F *out = s->prepared_points.data();
+    parallel_ranges(paths.size(), 1024, [&](size_t begin, size_t end) {
+        for (size_t pi = begin; pi < end; pi++) {
+            const Path &path = paths[pi];
+            const uint32_t *offsets = s->contour_offsets.data() + path.first_contour;
+            const uint32_t contours = path.end_contour - path.first_contour;
+            RectF bounds{0, 0, 0, 0};
+            for (uint32_t c = 0; c < contours; c++) {
+                RectF cb{0, 0, 0, 0};
+                for (uint32_t i = offsets[c]; i < offsets[c + 1]; i++) {
+                    PFVector2F p = s->points[i];
+                    if (!identity) xf.apply(p.x, p.y, p.x, p.y);
+                    out[i] = p;
+                    if (i == offsets[c]) cb = RectF{p.x, p.y, p.x, p.y};
+                    cb = RectF{sse_min(cb.min_x, p.x), sse_min(cb.min_y, p.y), sse_max(cb.max_x, p.x), sse_max(cb.max_y, p.y)};
+                }
+                bounds = c == 0 ? cb : union_rect(bounds, cb); // the scene holds no empty contours (append_outline)
+            }
+            pf::dilate_outline(out, offsets, contours, dilation[0], dilation[1]);
+            bounds_out[pi] = RectF{bounds.min_x - dilation[0], bounds.min_y - dilation[1], bounds.max_x + dilation[0],
+                                   bounds.max_y + dilation[1]}; // RectF::dilate (rect.rs:171-180)
+        }
+    });
 }
 
 // RectF::intersection (geometry/src/rect.rs:122-137), strict comparisons.
@@ -458,13 +503,15 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         if (st != PF_CUDA_OK) return st;           \
     } while (0)
 
-    if (opts->dilation[0] != 0.0f || opts->dilation[1] != 0.0f || opts->subpixel_aa_enabled) {
-        // The reference's GPU prepare mode silently ignores both; the text
-        // configuration that needs them is a 'next' row (f3). Refuse rather than render differently
-        // from the CPU tiler.
-        pf::set_last_error("dilation / subpixel AA are not implemented on the D3D11-level path yet");
+    if (opts->subpixel_aa_enabled) {
+        // The reference's GPU prepare mode silently ignores it; it needs the 3x-wide
+        // render target and the text filter of the 'next' row f3. Refuse rather than render differently from
+        // the CPU tiler.
+        pf::set_last_error("subpixel AA is not implemented on the D3D11-level path yet");
         return PF_CUDA_ERROR_UNSUPPORTED;
     }
+    // A dilation is applied on the host, after the transform, like the CPU tiler does (prepare_paths above).
+    const bool prepared = opts->dilation[0] != 0.0f || opts->dilation[1] != 0.0f;
 
     // builder.rs:160-164
     PFRenderCommand start = make_command(PF_RENDER_COMMAND_START);
@@ -491,10 +538,29 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
     meta.u.upload_texture_metadata.content_key = paint_key;
     SEND(meta);
 
-    // Scene upload when dirty (builder.rs:190-216).
-    bool dirty = !sink->has_last_scene || sink->last_scene_id != s->id || sink->last_scene_epoch != s->epoch;
-    if (dirty || s->draw_segment_ranges.size() != 2 * s->draw_paths.size()) {
-        build_segments(s);
+    // Scene upload when dirty (builder.rs:190-216). The segment arrays are rebuilt when the scene changed or, with
+    // a dilation, when the options that shaped the prepared points did.
+    uint64_t segments_key = mix_key(mix_key(0x5e65u, s->id), s->epoch);
+    if (prepared) {
+        uint32_t bits[8];
+        const float f[8] = {opts->transform.m11, opts->transform.m21, opts->transform.m12, opts->transform.m22,
+                            opts->transform.tx,  opts->transform.ty,  opts->dilation[0],   opts->dilation[1]};
+        memcpy(bits, f, sizeof(bits));
+        for (uint32_t v : bits) segments_key = mix_key(segments_key, v);
+    }
+    if (segments_key == 0) segments_key = 1;
+    if (s->segments_key != segments_key) {
+        if (prepared) {
+            s->prepared_points.resize(s->points.size());
+            prepare_paths(s, s->draw_paths, opts->transform, opts->dilation, s->prepared_draw_bounds);
+            prepare_paths(s, s->clip_paths, opts->transform, opts->dilation, s->prepared_clip_bounds);
+        }
+        build_segments(s, prepared ? s->prepared_points.data() : s->points.data());
+        s->segments_key = segments_key;
+        s->upload_serial++;
+    }
+    const bool dirty = !sink->has_last_scene || sink->last_scene_id != s->id || sink->last_scene_epoch != s->upload_serial;
+    if (dirty) {
         PFRenderCommand up = make_command(PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11);
         up.u.upload_scene_d3d11.draw_segments =
             PFSegmentsD3D11{s->seg_points.ptr, s->seg_point_count, s->seg_indices.ptr, s->seg_index_count};
@@ -504,12 +570,14 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         SEND(up);
         sink->has_last_scene = 1;
         sink->last_scene_id = s->id;
-        sink->last_scene_epoch = s->epoch;
+        sink->last_scene_epoch = s->upload_serial;
     }
 
     // build_tile_batches at the D3D11 level (builder.rs:327-357, 886-1056): solid colours never
     // break a batch (fixup_batch_for_new_path_if_possible, :1227-1243), so one DrawTilesD3D11.
-    const Transform &xf = opts->transform; // PrepareMode::GPU { transform } (options.rs:165-180)
+    // PrepareMode::GPU { transform } (options.rs:165-180); prepared points are already in device space.
+    const Transform identity_transform;
+    const Transform &xf = prepared ? identity_transform : opts->transform;
     const RectF effective_view_box = s->view_box; // subpixel AA refused above (scene.rs:276-282)
     // The batch arrays depend only on (scene, epoch, transform, view box): keep them across frames
     // and tell the renderer through content_key that nothing changed.
@@ -520,6 +588,7 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                              effective_view_box.min_y, effective_view_box.max_x, effective_view_box.max_y};
         memcpy(bits, f, sizeof(bits));
         for (uint32_t v : bits) batch_key = mix_key(batch_key, v);
+        if (prepared) batch_key = mix_key(batch_key, segments_key);
         if (batch_key == 0) batch_key = 1;
     }
     uint32_t tile_count = s->built_tile_count, segment_count = s->built_segment_count;
@@ -553,7 +622,9 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                 return PF_CUDA_ERROR_UNSUPPORTED;
             }
             PFRectI tile_rect{{0, 0}, {0, 0}};
-            RectF bounds = xf.is_identity() ? cp.bounds : xf.apply_rect(cp.bounds), clipped;
+            RectF bounds = prepared ? s->prepared_clip_bounds[p.clip_path]
+                                    : xf.is_identity() ? cp.bounds : xf.apply_rect(cp.bounds);
+            RectF clipped;
             if (cp.first_contour != cp.end_contour && rect_intersection(bounds, effective_view_box, clipped)) {
                 const float k = 1.0f / 16.0f;
                 tile_rect.origin.x = (int32_t)floorf(clipped.min_x * k);
@@ -611,7 +682,8 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                 const Path &p = s->draw_paths[i];
                 if (p.blend_mode != PF_BLEND_MODE_SRC_OVER) unsupported.store(2, std::memory_order_relaxed);
                 PFRectI tile_rect{{0, 0}, {0, 0}};
-                RectF path_bounds = xf.is_identity() ? p.bounds : xf.apply_rect(p.bounds);
+                RectF path_bounds = prepared ? s->prepared_draw_bounds[i]
+                                             : xf.is_identity() ? p.bounds : xf.apply_rect(p.bounds);
                 RectF clipped;
                 if (rect_intersection(path_bounds, effective_view_box, clipped)) {
                     // round_rect_out_to_tile_bounds (tiles.rs:64-66); floor/ceil results are integral,

@@ -18,17 +18,18 @@ def oracle_scene(flat: FlatScene) -> O.OracleScene:
                         draw_clip_paths=flat.draw_clip_paths if flat.n_clip_paths else None)
 
 
-def oracle_options(xf=None, strip=None):
+def oracle_options(xf=None, strip=None, dilation=(0.0, 0.0)):
     """xf = (m11, m12, m21, m22, tx, ty) as pathfinder_b200.scenes returns it."""
     t = None if xf is None else (xf[0], xf[2], xf[1], xf[3], xf[4], xf[5])
-    return O.make_options(transform=t, strip=strip)
+    return O.make_options(transform=t, strip=strip, dilation=dilation)
 
 
-def oracle_build(flat: FlatScene, xf=None, strip=None, keep_lines=False, n_threads=1) -> O.Built:
-    return O.Built(oracle_scene(flat), oracle_options(xf, strip), n_threads=n_threads, keep_lines=keep_lines)
+def oracle_build(flat: FlatScene, xf=None, strip=None, keep_lines=False, n_threads=1, dilation=(0.0, 0.0)) -> O.Built:
+    return O.Built(oracle_scene(flat), oracle_options(xf, strip, dilation), n_threads=n_threads, keep_lines=keep_lines)
 
 
-def cuda_render(flat: FlatScene, xf=None, size=None, background=None, debug=True, strip=None, renderer=None):
+def cuda_render(flat: FlatScene, xf=None, size=None, background=None, debug=True, strip=None, renderer=None,
+                dilation=(0.0, 0.0)):
     """Renders through the public API (Scene::build_and_render). Returns (renderer, image)."""
     from pathfinder_b200 import api
     w = int(size[0]) if size else int(flat.view_box[2])
@@ -39,7 +40,7 @@ def cuda_render(flat: FlatScene, xf=None, size=None, background=None, debug=True
         r.set_strip(*strip)
     scene = api.Scene.from_flat(flat)
     t = None if xf is None else api.Transform2F(*xf)
-    scene.build_and_render(r, api.BuildOptions(transform=t))
+    scene.build_and_render(r, api.BuildOptions(transform=t, dilation=dilation))
     return r, r.read_pixels()
 
 

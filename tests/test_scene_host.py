@@ -24,6 +24,8 @@ def collect(scene, options, sink=None):
             b = cmd.u.draw_tiles_d3d11.tile_batch_data
             rec.update(path_count=b.path_count, tile_count=b.tile_count, segment_count=b.segment_count,
                        content_key=b.content_key, batch_id=b.batch_id)
+            t = b.prepare_info.transform
+            rec["transform"] = (t.matrix.m00, t.matrix.m01, t.matrix.m10, t.matrix.m11, t.vector.x, t.vector.y)
             pm = C.cast(b.prepare_info.propagate_metadata, C.POINTER(L.PFPropagateMetadataD3D11))
             dm = C.cast(b.prepare_info.dice_metadata, C.POINTER(L.PFDiceMetadataD3D11))
             tp = C.cast(b.prepare_info.tile_path_info, C.POINTER(L.PFTilePathInfoD3D11))
