@@ -388,7 +388,9 @@ void PFSceneGetBounds(PFSceneRef scene, PFRectF *bounds);
 /* Scene::push_paint for a solid colour (scene.rs:186-190, paint.rs Palette::push_paint dedups). */
 uint16_t PFScenePushPaint(PFSceneRef scene, const PFColorU *color);
 /* Scene::push_draw_path (scene.rs:77-82). The outline is given as contours of points + flags:
- * contour i owns points [contour_offsets[i], contour_offsets[i+1]). Returns the DrawPathId. */
+ * contour i owns points [contour_offsets[i], contour_offsets[i+1]). Returns the DrawPathId, or
+ * PF_PATH_INDEX_NONE (see PFCudaGetLastError) and leaves the scene unchanged when the paint id or fill rule is
+ * unknown or the offsets decrease — mistakes the reference panics on later, when it indexes the palette. */
 uint32_t PFScenePushDrawPath(PFSceneRef scene, const PFVector2F *points, const uint8_t *point_flags,
                              const uint32_t *contour_offsets, uint32_t contour_count,
                              uint16_t paint_id, uint8_t fill_rule, uint8_t blend_mode,

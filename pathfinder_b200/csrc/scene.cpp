@@ -241,6 +241,23 @@ Path append_outline(PFScene *s, const PFVector2F *points, const uint8_t *point_f
     return p;
 }
 
+// Arguments of the push calls that would otherwise be read out of bounds later (the reference panics on the
+// same mistakes, e.g. an unknown PaintId indexes Palette::paints in build_paint_info).
+bool outline_args_ok(const PFScene *s, const PFVector2F *points, const uint8_t *point_flags,
+                     const uint32_t *contour_offsets, uint32_t contour_count, const char *who) {
+    if (!s || (contour_count && (!contour_offsets || !points || !point_flags))) {
+        pf::set_last_error(std::string(who) + ": null argument");
+        return false;
+    }
+    for (uint32_t c = 0; c < contour_count; c++) {
+        if (contour_offsets[c] > contour_offsets[c + 1]) {
+            pf::set_last_error(std::string(who) + ": contour_offsets must not decrease");
+            return false;
+        }
+    }
+    return true;
+}
+
 using pf::parallel_ranges;
 
 // BuiltSegments::from_scene + SegmentsD3D11::add_path (renderer/src/builder.rs:777-841) for the draw
@@ -410,6 +427,15 @@ uint16_t PFScenePushPaint(PFSceneRef s, const PFColorU *color) {
 uint32_t PFScenePushDrawPath(PFSceneRef s, const PFVector2F *points, const uint8_t *point_flags,
                              const uint32_t *contour_offsets, uint32_t contour_count, uint16_t paint_id,
                              uint8_t fill_rule, uint8_t blend_mode, uint32_t clip_path_id) {
+    if (!outline_args_ok(s, points, point_flags, contour_offsets, contour_count, "PFScenePushDrawPath")) return PF_PATH_INDEX_NONE;
+    if (paint_id >= s->paints.size()) {
+        pf::set_last_error("PFScenePushDrawPath: unknown paint id");
+        return PF_PATH_INDEX_NONE;
+    }
+    if (fill_rule != PF_FILL_RULE_WINDING && fill_rule != PF_FILL_RULE_EVEN_ODD) {
+        pf::set_last_error("PFScenePushDrawPath: unknown fill rule");
+        return PF_PATH_INDEX_NONE;
+    }
     Path p = append_outline(s, points, point_flags, contour_offsets, contour_count);
     p.paint = paint_id;
     p.fill_rule = fill_rule;
@@ -424,6 +450,11 @@ uint32_t PFScenePushDrawPath(PFSceneRef s, const PFVector2F *points, const uint8
 uint32_t PFScenePushClipPath(PFSceneRef s, const PFVector2F *points, const uint8_t *point_flags,
                              const uint32_t *contour_offsets, uint32_t contour_count, uint8_t fill_rule,
                              uint32_t clip_path_id) {
+    if (!outline_args_ok(s, points, point_flags, contour_offsets, contour_count, "PFScenePushClipPath")) return PF_PATH_INDEX_NONE;
+    if (fill_rule != PF_FILL_RULE_WINDING && fill_rule != PF_FILL_RULE_EVEN_ODD) {
+        pf::set_last_error("PFScenePushClipPath: unknown fill rule");
+        return PF_PATH_INDEX_NONE;
+    }
     Path p = append_outline(s, points, point_flags, contour_offsets, contour_count);
     p.paint = 0;
     p.fill_rule = fill_rule;
@@ -440,9 +471,35 @@ PFCudaStatus PFScenePushDrawPaths(PFSceneRef s, const PFVector2F *points, const 
                                   const uint32_t *path_contour_offsets, size_t path_count,
                                   const uint16_t *paint_ids, const uint8_t *fill_rules,
                                   const uint32_t *clip_path_ids) {
+    // Validate everything before touching the scene, so that a refused call leaves it unchanged.
+    if (!s || (path_count && (!path_contour_offsets || !paint_ids || !fill_rules)) ||
+        (contour_count && (!contour_offsets || !points || !point_flags))) {
+        pf::set_last_error("PFScenePushDrawPaths: null argument");
+        return PF_CUDA_ERROR_INVALID_ARGUMENT;
+    }
     if (contour_count && contour_offsets[contour_count] != point_count) {
         pf::set_last_error("PFScenePushDrawPaths: contour_offsets do not cover the points");
         return PF_CUDA_ERROR_INVALID_ARGUMENT;
+    }
+    for (size_t c = 0; c < contour_count; c++) {
+        if (contour_offsets[c] > contour_offsets[c + 1]) {
+            pf::set_last_error("PFScenePushDrawPaths: contour_offsets must not decrease");
+            return PF_CUDA_ERROR_INVALID_ARGUMENT;
+        }
+    }
+    for (size_t i = 0; i < path_count; i++) {
+        if (path_contour_offsets[i] > path_contour_offsets[i + 1] || path_contour_offsets[i + 1] > contour_count) {
+            pf::set_last_error("PFScenePushDrawPaths: path_contour_offsets do not index the contours");
+            return PF_CUDA_ERROR_INVALID_ARGUMENT;
+        }
+        if (paint_ids[i] >= s->paints.size()) {
+            pf::set_last_error("PFScenePushDrawPaths: unknown paint id");
+            return PF_CUDA_ERROR_INVALID_ARGUMENT;
+        }
+        if (fill_rules[i] != PF_FILL_RULE_WINDING && fill_rules[i] != PF_FILL_RULE_EVEN_ODD) {
+            pf::set_last_error("PFScenePushDrawPaths: unknown fill rule");
+            return PF_CUDA_ERROR_INVALID_ARGUMENT;
+        }
     }
     s->points.reserve(s->points.size() + point_count);
     s->flags.reserve(s->flags.size() + point_count);
@@ -455,10 +512,6 @@ PFCudaStatus PFScenePushDrawPaths(PFSceneRef s, const PFVector2F *points, const 
         p.fill_rule = fill_rules[i];
         p.blend_mode = PF_BLEND_MODE_SRC_OVER;
         p.clip_path = clip_path_ids ? clip_path_ids[i] : PF_CLIP_PATH_NONE;
-        if (p.paint >= s->paints.size()) {
-            pf::set_last_error("PFScenePushDrawPaths: unknown paint id");
-            return PF_CUDA_ERROR_INVALID_ARGUMENT;
-        }
         s->bounds = union_rect(s->bounds, p.bounds);
         s->draw_paths.push_back(p);
     }

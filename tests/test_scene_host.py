@@ -240,3 +240,41 @@ def test_concurrent_scene_builds_share_the_worker_pool():
     assert not errors, errors
     for r in results:
         assert r == expected
+
+
+def test_push_calls_refuse_arguments_they_could_not_index():
+    """An unknown paint id, fill rule or a decreasing offset table is refused when pushed (the reference panics
+    later, when it indexes the palette or the outline); a refused call leaves the scene as it was."""
+    lib = L.lib()
+    scene = api.Scene()
+    scene.set_view_box((0, 0, 64, 64))
+    paint = scene.push_paint((255, 0, 0, 255))
+    tri = np.array([(1, 1), (30, 2), (10, 40)], np.float32)
+    ok = scene.push_draw_path(tri, [0, 0, 0], [0, 3], paint)
+    assert ok == 0 and scene.draw_path_count() == 1
+    epoch = lib.PFSceneGetEpoch(scene._h)
+    none = 0xFFFFFFFF
+    assert scene.push_draw_path(tri, [0, 0, 0], [0, 3], paint + 1) == none
+    assert b"paint" in lib.PFCudaGetLastError()
+    assert scene.push_draw_path(tri, [0, 0, 0], [0, 3], paint, fill_rule=7) == none
+    assert scene.push_draw_path(tri, [0, 0, 0], [0, 3, 2], paint) == none
+    assert scene.push_clip_path(tri, [0, 0, 0], [0, 3], fill_rule=9) == none
+    assert scene.draw_path_count() == 1 and lib.PFSceneGetEpoch(scene._h) == epoch
+
+    def push_many(contour_offsets, path_contour_offsets, paints, rules):
+        pts = np.concatenate([tri, tri + 5]).astype(np.float32)
+        fl = np.zeros(6, np.uint8)
+        co = np.asarray(contour_offsets, np.uint32)
+        pco = np.asarray(path_contour_offsets, np.uint32)
+        pa, ru = np.asarray(paints, np.uint16), np.asarray(rules, np.uint8)
+        return lib.PFScenePushDrawPaths(scene._h, pts.ctypes.data, fl.ctypes.data, 6, co.ctypes.data, len(co) - 1,
+                                        pco.ctypes.data, len(pco) - 1, pa.ctypes.data, ru.ctypes.data, None)
+
+    bad = L.PF_CUDA_ERROR_INVALID_ARGUMENT
+    assert push_many([0, 3, 5], [0, 1, 2], [paint, paint], [0, 0]) == bad      # offsets do not cover the points
+    assert push_many([0, 3, 6], [0, 1, 3], [paint, paint], [0, 0]) == bad      # path 1 reaches past the contours
+    assert push_many([0, 3, 6], [0, 1, 2], [paint, paint + 3], [0, 0]) == bad  # second path's paint: nothing is kept
+    assert push_many([0, 3, 6], [0, 1, 2], [paint, paint], [0, 2]) == bad
+    assert scene.draw_path_count() == 1 and lib.PFSceneGetEpoch(scene._h) == epoch
+    assert push_many([0, 3, 6], [0, 1, 2], [paint, paint], [0, 1]) == 0
+    assert scene.draw_path_count() == 3
