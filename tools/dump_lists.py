@@ -17,6 +17,7 @@ List format, one record per line:
 Scene format:
   viewbox <min_x> <min_y> <max_x> <max_y>
   transform <m11> <m12> <m21> <m22> <tx> <ty>               (BuildOptions transform, Transform2F row-major)
+  dilation <x> <y>                                           (BuildOptions dilation; absent = zero)
   paint <r> <g> <b> <a>
   clippath <fill_rule> <contour count>                       (clip paths first, ids in file order)
   path <fill_rule: 0 winding | 1 even-odd> <paint index> <contour count> [<clip path id> | -1]
@@ -44,18 +45,23 @@ def load(spec, size):
     if spec.startswith("random:"):
         _, n, seed = spec.split(":")
         return scenes.random_paths(int(n), size, int(seed)), None
-    raise SystemExit(f"unknown scene {spec!r} (tiger | clips | random:<paths>:<seed>)")
+    if spec.startswith("text:"):
+        _, n, layout = spec.split(":")
+        return scenes.text_page(int(n), size, layout=layout), None
+    raise SystemExit(f"unknown scene {spec!r} (tiger | clips | random:<paths>:<seed> | text:<glyphs>:<grid|lines>)")
 
 
 def bits(v):
     return "%08x" % struct.unpack("<I", struct.pack("<f", float(v)))[0]
 
 
-def write_scene(flat, xf, path):
+def write_scene(flat, xf, path, dilation=(0.0, 0.0)):
     with open(path, "w") as f:
         f.write("viewbox " + " ".join(bits(v) for v in flat.view_box) + "\n")
         t = (1, 0, 0, 1, 0, 0) if xf is None else xf
         f.write("transform " + " ".join(bits(v) for v in t) + "\n")
+        if dilation[0] != 0.0 or dilation[1] != 0.0:
+            f.write("dilation " + " ".join(bits(v) for v in dilation) + "\n")
         for c in np.asarray(flat.paint_colors).reshape(-1, 4):
             f.write("paint %d %d %d %d\n" % tuple(int(v) for v in c))
         def contours(c0, c1):
@@ -95,17 +101,20 @@ def main():
     ap.add_argument("--source", default="oracle", choices=["oracle", "cuda"])
     ap.add_argument("--out", required=True)
     ap.add_argument("--scene-out")
+    ap.add_argument("--dilation", type=float, nargs=2, default=(0.0, 0.0), metavar=("X", "Y"),
+                    help="BuildOptions dilation in pixels, applied after the transform (stem darkening)")
     args = ap.parse_args()
     flat, xf = load(args.scene, args.size)
+    dilation = (float(np.float32(args.dilation[0])), float(np.float32(args.dilation[1])))
     if args.scene_out:
-        write_scene(flat, xf, args.scene_out)
+        write_scene(flat, xf, args.scene_out, dilation)
     if args.source == "oracle":
         from tests import helpers as H
-        b = H.oracle_build(flat, xf)
+        b = H.oracle_build(flat, xf, dilation=dilation)
         write_lists(b.fills, b.tiles, b.z_buffer, args.out, b.clips)
     else:
         from tests import helpers as H
-        r, _ = H.cuda_render(flat, xf, size=(args.size, args.size), debug=True)
+        r, _ = H.cuda_render(flat, xf, size=(args.size, args.size), debug=True, dilation=dilation)
         z, _rect = r.debug_z_buffer()
         write_lists(r.debug_fills(), r.debug_tiles(), z, args.out, r.debug_clips())
 

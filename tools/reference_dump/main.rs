@@ -43,6 +43,7 @@ fn main() {
     let text = fs::read_to_string(path).unwrap();
     let mut scene = Scene::new();
     let mut transform = Transform2F::default();
+    let mut dilation = vec2f(0.0, 0.0);
     let mut paints = vec![];
     // (fill rule, paint (None: a clip path), clip path of a draw path, outline)
     let mut current: Option<(FillRule, Option<usize>, Option<ClipPathId>, Outline)> = None;
@@ -98,6 +99,7 @@ fn main() {
                     vector: vec2f(f(w[5]), f(w[6])),
                 }
             }
+            Some("dilation") => dilation = vec2f(f(w[1]), f(w[2])),
             Some("paint") => {
                 let c: Vec<u8> = w[1..5].iter().map(|v| v.parse().unwrap()).collect();
                 paints.push(scene.push_paint(&Paint::from_color(ColorU::new(c[0], c[1], c[2], c[3]))));
@@ -143,6 +145,7 @@ fn main() {
     let mut sink = SceneSink::new(listener, RendererLevel::D3D9);
     let options = BuildOptions {
         transform: RenderTransform::Transform2D(transform),
+        dilation,
         ..BuildOptions::default()
     };
     scene.build(options, &mut sink, &SequentialExecutor);
