@@ -201,6 +201,11 @@ void scene_note_borrowed(PFScene *s, cudaStream_t stream, int device) {
     if (!s->borrowed_event) {
         PF_CUDA_CHECK(cudaEventCreateWithFlags(&s->borrowed_event, cudaEventDisableTiming));
         s->borrowed_device = device;
+    } else if (s->borrowed) {
+        // A second renderer borrows the same arrays while an earlier copy may still be in flight on another
+        // stream (the arrays are not rebuilt for a new sink when the scene has not changed): one event can only
+        // stand for one of them, so finish the earlier one first. Never taken with one renderer per scene.
+        if (cudaEventSynchronize(s->borrowed_event) != cudaSuccess) (void)cudaGetLastError();
     }
     PF_CUDA_CHECK(cudaEventRecord(s->borrowed_event, stream));
     s->borrowed = true;
