@@ -2,7 +2,8 @@
 spent: the text-page scene and host-side dilation. Their host halves are pinned on the CPU (tests/test_oracle.py,
 tests/test_dilate_host.py) and the device sees nothing new — more small paths, or already-prepared points under an
 identity transform — but they have NOT run on a B200 yet, so they are marked xfail(strict=False): a pass shows up as
-XPASS, a failure does not hide the verified suite. Drop the marker once they have been seen green."""
+XPASS, a failure does not hide the verified suite — and the file is named to be collected last, so that even a fault
+that poisoned the CUDA context could not reach the verified tests. Drop the marker (and the zz) once seen green."""
 import numpy as np
 import pytest
 
