@@ -469,6 +469,27 @@ void PFOutlineDestroy(PFOutlineRef outline);
  * is not vendored: parity unpinned, W3C SVG 1.1 rules followed. Returns NULL on malformed data. */
 PFOutlineRef PFSvgPathDataToOutline(const char *path_data);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Glyph outlines. The reference reads fonts through font-kit 0.6.0                  */
+/* (text/src/lib.rs:80-160: Loader::glyph_for_char, advance, outline with HintingOptions::None), which */
+/* is not vendored: parity unpinned upstream of the Scene. TrueType (`glyf`) outlines only.            */
+/* ------------------------------------------------------------------------------------------- */
+
+typedef struct PFFont *PFFontRef;
+
+/* Copies `length` bytes of an sfnt file. Returns NULL (see PFCudaGetLastError) for anything but a readable
+ * TrueType-flavoured font; every later read is bounds-checked against the copy. */
+PFFontRef PFFontCreateFromBytes(const uint8_t *data, size_t length);
+void PFFontDestroy(PFFontRef font);
+uint32_t PFFontGetUnitsPerEm(PFFontRef font);                              /* Metrics::units_per_em */
+uint32_t PFFontGetGlyphCount(PFFontRef font);
+uint32_t PFFontGetGlyphForCodepoint(PFFontRef font, uint32_t codepoint);   /* glyph_for_char; 0 = none */
+float PFFontGetGlyphAdvance(PFFontRef font, uint32_t glyph_id);            /* advance().x, font units */
+/* The glyph's contours in font units, y up, as pathfinder point lists (quadratic control points flagged
+ * PF_POINT_FLAGS_CONTROL_POINT_0), all closed; composite glyphs are resolved. An empty outline for a glyph
+ * without contours (space); NULL for a glyph id out of range or malformed glyph data. */
+PFOutlineRef PFFontGetGlyphOutline(PFFontRef font, uint32_t glyph_id);
+
 /* Outline::dilate (content/src/outline.rs:243-249; ContourDilator, content/src/dilation.rs:34-125) in place on an
  * outline given as flat arrays: every distinct position moves along the bisector of its neighbouring edges by
  * `amount` per axis, outwards for the outline's outermost winding (Orientation::from_outline). This is the stem

@@ -247,6 +247,13 @@ SIGNATURES = {
     "PFOutlineDestroy": (None, [C.c_void_p]),
     "PFSvgPathDataToOutline": (C.c_void_p, [C.c_char_p]),
     "PFOutlineDilate": (None, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "PFFontCreateFromBytes": (C.c_void_p, [C.c_char_p, C.c_size_t]),
+    "PFFontDestroy": (None, [C.c_void_p]),
+    "PFFontGetUnitsPerEm": (C.c_uint32, [C.c_void_p]),
+    "PFFontGetGlyphCount": (C.c_uint32, [C.c_void_p]),
+    "PFFontGetGlyphForCodepoint": (C.c_uint32, [C.c_void_p, C.c_uint32]),
+    "PFFontGetGlyphAdvance": (C.c_float, [C.c_void_p, C.c_uint32]),
+    "PFFontGetGlyphOutline": (C.c_void_p, [C.c_void_p, C.c_uint32]),
     "PFScenePushClipPath": (C.c_uint32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_uint8, C.c_uint32]),
     "PFScenePushDrawPaths": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,

@@ -230,6 +230,79 @@ def svg_path_to_outline(path_data: str):
     return pts, flags, offsets, closed
 
 
+class Font:
+    """A TrueType font read by csrc/font.cpp (the reference uses font-kit's Loader, text/src/lib.rs:80-160)."""
+
+    def __init__(self, data: bytes):
+        lib = L.lib()
+        self._h = lib.PFFontCreateFromBytes(data, len(data))
+        if not self._h:
+            raise L.PathfinderCudaError(L.PF_CUDA_ERROR_INVALID_ARGUMENT, lib.PFCudaGetLastError().decode("utf-8", "replace"))
+        self.units_per_em = int(lib.PFFontGetUnitsPerEm(self._h))
+        self.glyph_count = int(lib.PFFontGetGlyphCount(self._h))
+
+    @staticmethod
+    def from_path(path: str) -> "Font":
+        with open(path, "rb") as f:
+            return Font(f.read())
+
+    def close(self):
+        if self._h:
+            L.lib().PFFontDestroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def glyph_for_char(self, ch) -> int:
+        return int(L.lib().PFFontGetGlyphForCodepoint(self._h, ord(ch) if isinstance(ch, str) else int(ch)))
+
+    def advance(self, glyph_id: int) -> float:
+        return float(L.lib().PFFontGetGlyphAdvance(self._h, int(glyph_id)))
+
+    def outline(self, glyph_id: int):
+        """(points, point_flags, contour_offsets) in font units, y up (HintingOptions::None)."""
+        lib = L.lib()
+        h = lib.PFFontGetGlyphOutline(self._h, int(glyph_id))
+        if not h:
+            raise L.PathfinderCudaError(L.PF_CUDA_ERROR_INVALID_ARGUMENT, lib.PFCudaGetLastError().decode("utf-8", "replace"))
+        try:
+            n, k = int(lib.PFOutlineGetPointCount(h)), int(lib.PFOutlineGetContourCount(h))
+            pts, flags, offsets = np.zeros((n, 2), np.float32), np.zeros(n, np.uint8), np.zeros(k + 1, np.uint32)
+            lib.PFOutlineCopy(h, pts.ctypes.data, flags.ctypes.data, offsets.ctypes.data)
+        finally:
+            lib.PFOutlineDestroy(h)
+        return pts, flags, offsets
+
+    def glyph_outline_at(self, glyph_id: int, glyph_offset, font_size: float, transform: Transform2F | None = None):
+        """The outline FontContext::push_glyph hands to Scene::push_draw_path for unhinted text
+        (text/src/lib.rs:118-146), with its f32 operation order: the cached outline is the font-unit outline scaled by
+        units_per_em, and it is transformed by
+            render_options.transform * from_scale(s, -s).translate(offset) * from_scale(1 / units_per_em),
+        s = font_size / units_per_em (Transform2F products: matrix * matrix, matrix * vector + vector)."""
+        f = np.float32
+        pts, flags, offsets = self.outline(glyph_id)
+        upem = f(self.units_per_em)
+        cached = pts * upem                                            # OutlinePathBuilder(from_scale(units_per_em))
+        s = f(font_size) / upem
+        t = transform or Transform2F()
+        # from_scale(s, -s).translate(offset) = from_translation(offset) * from_scale: matrix diag(s, -s), vector offset
+        gm = (s, f(0.0), f(0.0), -s)
+        gv = (f(glyph_offset[0]), f(glyph_offset[1]))
+        # render_transform = t * glyph transform (transform2d.rs Mul: matrix = a.m * b.m, vector = a.m * b.v + a.v)
+        rm = (t.m11 * gm[0] + t.m12 * gm[2], t.m11 * gm[1] + t.m12 * gm[3],
+              t.m21 * gm[0] + t.m22 * gm[2], t.m21 * gm[1] + t.m22 * gm[3])
+        rv = ((t.m11 * gv[0] + t.m12 * gv[1]) + t.tx, (t.m21 * gv[0] + t.m22 * gv[1]) + t.ty)
+        k = f(1.0) / upem
+        fm = (rm[0] * k, rm[1] * k, rm[2] * k, rm[3] * k)              # * from_scale(1 / units_per_em): vector unchanged
+        x, y = cached[:, 0], cached[:, 1]
+        out = np.stack([(fm[0] * x + fm[1] * y) + rv[0], (fm[2] * x + fm[3] * y) + rv[1]], axis=1).astype(np.float32)
+        return out, flags, offsets
+
+
 def ipc_export(device_ptr: int):
     """(handle bytes, offset) of a device allocation, to be opened by peer processes."""
     h = (C.c_uint8 * 64)()

@@ -249,6 +249,12 @@ void Contour::push_arc_from_unit_chord(const Xf &transform, V2 chord_from, V2 ch
 struct Stroker {
     uint32_t join;
     float miter_limit;
+    // The reference's recursion (stroke.rs:243-261) only ends when the error is within tolerance or the piece is
+    // shorter than the tolerance; on geometry where neither happens soon (cusps a million pixels long) it produces
+    // pieces without bound. The C ABI gives up instead once one call has emitted this many pieces.
+    static constexpr size_t MAX_PIECES = 1u << 20;
+    mutable size_t pieces = 0;
+    struct TooManyPieces {};
 
     // Offset::offset_once (stroke.rs:286-348)
     static V2 control_point(Line s0, Line s1) {
@@ -306,6 +312,7 @@ struct Stroker {
     // Offset::offset (stroke.rs:243-261)
     void offset(const Segment &s, float distance, uint32_t seg_join, Contour &out, int depth = 0) const {
         const V2 join_point = s.baseline.from;
+        if (++pieces > MAX_PIECES) throw TooManyPieces{};
         if (s.baseline.square_length() < TOLERANCE * TOLERANCE || depth > 64) {
             add_to_contour(s, distance, seg_join, join_point, out);
             return;
@@ -395,9 +402,23 @@ PFOutlineRef PFOutlineStrokeToFill(const PFVector2F *points, const uint8_t *poin
         pf::set_last_error("PFOutlineStrokeToFill: unknown line cap or line join");
         return nullptr;
     }
+    // Coordinates whose squares overflow f32 (or that are not numbers at all) can never meet the tolerance test: the
+    // reference would recurse until its stack ran out. Refuse them here.
+    const size_t point_count = contour_count ? contour_offsets[contour_count] : 0;
+    for (size_t i = 0; i < point_count; i++) {
+        if (!(std::fabs(points[i].x) < 1e18f) || !(std::fabs(points[i].y) < 1e18f)) {
+            pf::set_last_error("PFOutlineStrokeToFill: coordinates must be finite and below 1e18 in magnitude");
+            return nullptr;
+        }
+    }
+    if (!(std::fabs(style->line_width) < 1e18f) || !(std::fabs(style->miter_limit) < 1e18f)) {
+        pf::set_last_error("PFOutlineStrokeToFill: line width and miter limit must be finite");
+        return nullptr;
+    }
     const float radius = style->line_width * 0.5f;
     const Stroker stroker{style->line_join, style->miter_limit};
     PFOutline *out = new PFOutline;
+    try {
     auto push_contour = [&](Contour &c, bool closed, V2 input_first_point) { // push_stroked_contour (stroke.rs:133-149)
         if (closed && c.might_need_join(style->line_join)) {
             const V2 p1 = c.points[1], p0 = c.points[0];
@@ -431,6 +452,15 @@ PFOutlineRef PFOutlineStrokeToFill(const PFVector2F *points, const uint8_t *poin
                            i == 0 ? (uint32_t)PF_LINE_JOIN_BEVEL : style->line_join, c);
         if (!closed) add_cap(c, style->line_cap, style->line_width);
         push_contour(c, closed, pts[0]);
+    }
+    } catch (const Stroker::TooManyPieces &) {
+        pf::set_last_error("PFOutlineStrokeToFill: the offset curves did not converge (more than 1M pieces)");
+        delete out;
+        return nullptr;
+    } catch (const std::exception &e) {
+        pf::set_last_error(std::string("PFOutlineStrokeToFill: ") + e.what());
+        delete out;
+        return nullptr;
     }
     return out;
 }

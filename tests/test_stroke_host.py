@@ -252,3 +252,23 @@ def test_stroked_path_in_a_scene_matches_the_oracle_tiling():
 
     scene.build(api.BuildOptions(), listener)
     assert seen["segments"] == built.input_segment_count and seen["tiles"] == built.bbox_tile_count
+
+
+def test_input_the_offsetter_cannot_converge_on_is_refused():
+    """Offset::offset (stroke.rs:243-261) recurses until the offset curve is within tolerance or the piece is shorter
+    than the tolerance; with coordinates whose squares overflow f32, or that are not numbers, neither ever happens
+    (found by fuzzing: the reference would recurse until its stack ran out). The C ABI refuses such input, and gives
+    up with an error rather than allocating without bound when finite geometry needs more than a million pieces."""
+    curve = [(10, 10), (1e30, 50), (40, 80)]
+    for bad in (curve, [(10, 10), (float("nan"), 50), (40, 80)], [(10, 10), (float("inf"), 50), (40, 80)]):
+        with pytest.raises(L.PathfinderCudaError):
+            api.stroke_to_fill(bad, [0, 1, 0], [0, 3], [0], line_width=3.0)
+    with pytest.raises(L.PathfinderCudaError):
+        api.stroke_to_fill([(0, 0), (10, 0)], [0, 0], [0, 2], [0], line_width=float("inf"))
+    # at 1e6 px an f32 ulp (0.06) is coarser than the tolerance (0.01): the recursion can only end piece by piece
+    with pytest.raises(L.PathfinderCudaError) as e:
+        api.stroke_to_fill([(0, 0), (5e5, 1e6), (1e6, 0)], [0, 1, 0], [0, 3], [0], line_width=4.0)
+    assert "converge" in str(e.value)
+    # large geometry that f32 can resolve still strokes
+    pts, flags, offs = api.stroke_to_fill([(0, 0), (5e3, 1e4), (1e4, 0)], [0, 1, 0], [0, 3], [0], line_width=4.0)
+    assert len(pts) > 8 and np.isfinite(pts).all()

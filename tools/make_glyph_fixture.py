@@ -154,14 +154,15 @@ def to_quadratics(contour):
     n = len(contour)
     if n == 0:
         return [], []
-    start = next((i for i, p in enumerate(contour) if p[2]), None)
-    if start is None:  # all off-curve: start at the midpoint of the first two
-        (x0, y0, _), (x1, y1, _) = contour[0], contour[1 % n]
-        first = ((x0 + x1) / 2.0, (y0 + y1) / 2.0)
-        seq = contour[1:] + contour[:1]
+    # FreeType's outline decomposition (font-kit's loader on Linux): start at the first point if it is on the curve,
+    # else at the last point if that one is, else halfway between the two (csrc/font.cpp follows the same rule).
+    if contour[0][2]:
+        first, seq = contour[0][:2], contour[1:]
+    elif contour[-1][2]:
+        first, seq = contour[-1][:2], contour[:-1]
     else:
-        first = contour[start][:2]
-        seq = contour[start + 1:] + contour[:start]
+        (x0, y0, _), (x1, y1, _) = contour[0], contour[-1]
+        first, seq = ((x0 + x1) / 2.0, (y0 + y1) / 2.0), contour
     pts, flags = [first], [0]
     pending = None
     for x, y, on in seq:
