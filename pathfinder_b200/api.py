@@ -132,6 +132,30 @@ class Scene:
                                              line_join, miter_limit, line_cap)
         return self.push_draw_path(pts, flags, offsets, paint_id, fill_rule=0, clip_path_id=clip_path_id)
 
+    def push_glyph(self, font: "Font", glyph_id: int, glyph_offset, font_size: float, paint_id: int,
+                   transform: "Transform2F | None" = None, clip_path_id=0xFFFFFFFF) -> int:
+        """FontContext::push_glyph (text/src/lib.rs:83-146) for unhinted, filled text: one draw path per glyph,
+        winding rule. Returns the DrawPathId, or None for a glyph without contours (the reference pushes an empty
+        path there; it tiles to nothing)."""
+        pts, flags, offsets = font.glyph_outline_at(glyph_id, glyph_offset, font_size, transform)
+        if len(pts) == 0:
+            return None
+        return self.push_draw_path(pts, flags, offsets, paint_id, fill_rule=0, clip_path_id=clip_path_id)
+
+    def push_text(self, font: "Font", text: str, origin, font_size: float, paint_id: int,
+                  transform: "Transform2F | None" = None) -> float:
+        """FontContext::push_text (text/src/lib.rs:197-207) with the simplest possible layout in place of skribo's
+        (a dependency that is not vendored): glyphs of one font set left to right by their advances, no kerning or
+        shaping. Returns the pen's x position after the last glyph."""
+        f = np.float32
+        x, y = f(origin[0]), f(origin[1])
+        scale = f(font_size) / f(font.units_per_em)
+        for ch in text:
+            glyph = font.glyph_for_char(ch)
+            self.push_glyph(font, glyph, (x, y), font_size, paint_id, transform)
+            x = f(x + f(font.advance(glyph)) * scale)
+        return float(x)
+
     def push_clip_path(self, points, point_flags, contour_offsets, fill_rule=0, clip_path_id=0xFFFFFFFF) -> int:
         """Scene::push_clip_path (scene.rs:99-106); returns the ClipPathId."""
         pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)

@@ -122,3 +122,44 @@ def test_truncated_and_corrupted_fonts_never_fault():
                 blob[pos] ^= int(rng.integers(1, 256))
             poke(bytes(blob))
     assert poke(data) == 1
+
+
+@needs_font
+def test_push_text_builds_the_same_scene_as_the_fixture_layout(font, area_lut):
+    """Scene.push_text (advance-only layout) -> host SceneBuilder: the batch the renderer would receive has one path
+    per inked glyph, and the oracle renders the same outlines to the ink their contours enclose."""
+    from pathfinder_b200.flat_scene import FlatScene
+    from tests import helpers as H
+    from tests.test_scene_host import collect
+    text = "Hamburgefonstiv 0123"
+    scene = api.Scene()
+    scene.set_view_box((0, 0, 256, 64))
+    paint = scene.push_paint((0, 0, 0, 255))
+    end_x = scene.push_text(font, text, (8.0, 40.0), 20.0, paint)
+    inked = [c for c in text if c != " "]
+    assert scene.draw_path_count() == len(inked)
+    want = 8.0 + sum(font.advance(font.glyph_for_char(c)) for c in text) * 20.0 / 2048
+    assert abs(end_x - want) < 1e-2
+    cmds = collect(scene, api.BuildOptions())
+    draw = [c for c in cmds if c["kind"] == "DrawTilesD3D11"][0]
+    assert draw["path_count"] == len(inked)
+
+    # the same outlines as a FlatScene through the oracle
+    pts, flags, offs, path_offs = [], [], [0], [0]
+    x = np.float32(8.0)
+    for ch in text:
+        g = font.glyph_for_char(ch)
+        p, f, o = font.glyph_outline_at(g, (x, np.float32(40.0)), 20.0)
+        x = np.float32(x + np.float32(font.advance(g)) * (np.float32(20.0) / np.float32(2048)))
+        if len(p) == 0:
+            continue
+        base = offs[-1]
+        pts.append(p); flags.append(f); offs += [int(v) + base for v in o[1:]]
+        path_offs.append(len(offs) - 1)
+    n = len(path_offs) - 1
+    flat = FlatScene(np.concatenate(pts), np.concatenate(flags), offs, path_offs, np.zeros(n, np.uint8),
+                     np.zeros(n, np.uint16), np.asarray([[0, 0, 0, 255]], np.uint8), (0.0, 0.0, 256.0, 64.0), "text")
+    built = H.oracle_build(flat, None)
+    assert draw["tile_count"] == built.bbox_tile_count and draw["segment_count"] == built.input_segment_count
+    img = built.render(area_lut, 256, 64)
+    assert 150 < img[:, :, 3].astype(np.float64).sum() / 255.0 < 1500   # some ink, not a filled page
