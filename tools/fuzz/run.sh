@@ -1,0 +1,25 @@
+#!/bin/bash
+# tools/fuzz/run.sh — sanitizer fuzzing of the host-side code above and beside the C ABI (no GPU needed).
+# Every run is bounded by `timeout`; a finding aborts with the sanitizer's report.  Usage: tools/fuzz/run.sh [seconds]
+set -u
+cd "$(dirname "$0")"
+LIMIT=${1:-240}
+CSRC=../../pathfinder_b200/csrc
+SAN="-fsanitize=address,undefined -fno-sanitize-recover=all"
+OUT=${TMPDIR:-/tmp}/pf_fuzz
+mkdir -p "$OUT"
+status=0
+run() { # name, command...
+    local name=$1; shift
+    echo "== $name"
+    ( cd "$OUT" && ASAN_OPTIONS=protect_shadow_gap=0:detect_leaks=0:hard_rss_limit_mb=6000 timeout "$LIMIT" "$@" ) | tail -2
+    local rc=${PIPESTATUS[0]}
+    if [ "$rc" = 124 ]; then echo "   (time limit reached without a finding)"; elif [ "$rc" != 0 ]; then echo "   FAILED ($rc)"; status=1; fi
+}
+g++ -std=c++17 -O1 -g $SAN font_asan.cpp $CSRC/font.cpp -o "$OUT/font_asan" && run font "$OUT/font_asan" "${FONT:-/root/reference/resources/fonts/Roboto-Regular.ttf}"
+g++ -std=c++17 -O1 -g $SAN host_asan.cpp $CSRC/svg.cpp $CSRC/stroke.cpp $CSRC/dilate.cpp -o "$OUT/host_asan" && run svg+stroke+dilate "$OUT/host_asan"
+nvcc -Wno-deprecated-gpu-targets -std=c++17 -O1 -g -Xcompiler -fsanitize=address,-fsanitize=undefined,-fno-sanitize-recover=all \
+    -x cu scene_fuzz.cpp $CSRC/scene.cpp $CSRC/dilate.cpp -o "$OUT/scene_fuzz" && run scene-builder "$OUT/scene_fuzz"
+nvcc -Wno-deprecated-gpu-targets -std=c++17 -O1 -g -Xcompiler -fsanitize=thread \
+    -x cu scene_tsan.cpp $CSRC/scene.cpp $CSRC/dilate.cpp -o "$OUT/scene_tsan" && run scene-builder-threads "$OUT/scene_tsan"
+exit $status
