@@ -22,4 +22,6 @@ nvcc -Wno-deprecated-gpu-targets -std=c++17 -O1 -g -Xcompiler -fsanitize=address
     -x cu scene_fuzz.cpp $CSRC/scene.cpp $CSRC/dilate.cpp -o "$OUT/scene_fuzz" && run scene-builder "$OUT/scene_fuzz"
 nvcc -Wno-deprecated-gpu-targets -std=c++17 -O1 -g -Xcompiler -fsanitize=thread \
     -x cu scene_tsan.cpp $CSRC/scene.cpp $CSRC/dilate.cpp -o "$OUT/scene_tsan" && run scene-builder-threads "$OUT/scene_tsan"
+g++ -O1 -g -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -msse4.1 -pthread $SAN -shared -o "$OUT/libpf_oracle_asan.so" ../../oracle/pf_oracle.cpp && \
+    LD_PRELOAD="$(gcc -print-file-name=libasan.so):$(gcc -print-file-name=libubsan.so)" run oracle python "$PWD/oracle_asan.py" "$OUT/libpf_oracle_asan.so"
 exit $status
