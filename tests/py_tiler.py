@@ -1,0 +1,305 @@
+"""A second, independent restatement of the reference's CPU tiler in scalar numpy float32 — test infrastructure.
+
+oracle/pf_oracle.cpp is "parity unpinned": nothing in this image can run the Rust tiler. This module narrows the room
+for a transcription error by restating the same functions a second time, straight from the Rust sources and without
+looking at the C++, in the slowest and plainest form available (one np.float32 operation per Rust operation, Python
+loops), so that tests/test_py_tiler.py can demand bit-identical fills, alpha-tile ids and backdrops from both on
+small scenes. Restated here:
+  ContourIter::next                      content/src/outline.rs:1019-1062
+  Segment::to_cubic                      content/src/segment.rs:171-183
+  CubicSegment::is_flat / split          content/src/segment.rs:292-360
+  process_segment / process_line_segment renderer/src/tiler.rs:166-308
+  clip_line_segment_to_rect              content/src/clip.rs:494-565
+  ObjectBuilder::add_fill, adjust_alpha_tile_backdrop, get_or_allocate_alpha_tile_index
+                                         renderer/src/builder.rs:509-616
+  Tiler::new bounds, round_rect_out_to_tile_bounds, prepare_tiles (no clip path)
+                                         renderer/src/tiler.rs:47-50,100-165; renderer/src/tiles.rs:64-66
+Only solid-colour draw paths without clip paths; sequential order (SequentialExecutor)."""
+from __future__ import annotations
+
+import numpy as np
+
+f = np.float32
+TILE = 16
+INVALID = 0xFFFFFFFF
+
+
+def contour_segments(pts, flags):
+    """ContourIter with the close segment of a closed contour: ('line' | 'quad' | 'cubic', points...)."""
+    n = len(pts)
+    out, index = [], 1
+    while True:
+        if index == n + 1:
+            break
+        p0 = pts[index - 1]
+        if index == n:
+            out.append(("line", p0, pts[0]))
+            index += 1
+            continue
+        p1 = pts[index]
+        index += 1
+        if flags[index - 1] == 0:
+            out.append(("line", p0, p1))
+            continue
+        p2 = pts[index]
+        index += 1
+        if flags[index - 1] == 0:
+            out.append(("quad", p0, p1, p2))
+            continue
+        p3 = pts[index]
+        index += 1
+        out.append(("cubic", p0, p1, p2, p3))
+    return out
+
+
+def add(a, b):
+    return (a[0] + b[0], a[1] + b[1])
+
+
+def sub(a, b):
+    return (a[0] - b[0], a[1] - b[1])
+
+
+def scale(a, k):
+    return (a[0] * k, a[1] * k)
+
+
+def lerp_pt(a, b, t):  # a + t * (b - a), per component
+    return (a[0] + t * (b[0] - a[0]), a[1] + t * (b[1] - a[1]))
+
+
+def is_flat(p0, c0, c1, p3):
+    three = f(3.0)
+    uv = [three * c0[0] - p0[0] - p0[0] - p3[0], three * c0[1] - p0[1] - p0[1] - p3[1],
+          three * c1[0] - p3[0] - p3[0] - p0[0], three * c1[1] - p3[1] - p3[1] - p0[1]]
+    uv = [v * v for v in uv]
+    m0 = uv[0] if uv[0] > uv[2] else uv[2]   # uv.max(uv.zwxy())
+    m1 = uv[1] if uv[1] > uv[3] else uv[3]
+    return m0 + m1 <= f(16.0) * f(0.25) * f(0.25)
+
+
+def split_half(p0, c0, c1, p3):
+    t = f(0.5)
+    p01, p12, p23 = lerp_pt(p0, c0, t), lerp_pt(c0, c1, t), lerp_pt(c1, p3, t)
+    p012, p123 = lerp_pt(p01, p12, t), lerp_pt(p12, p23, t)
+    p0123 = lerp_pt(p012, p123, t)
+    return (p0, p01, p012, p0123), (p0123, p123, p23, p3)
+
+
+class PathBuilder:
+    """ObjectBuilder for one path: dense tile map over the tile rect, per-column backdrops above it."""
+
+    def __init__(self, bounds, view_box, state):
+        self.view_box = view_box
+        self.state = state  # shared: {"next_alpha": int, "fills": list}
+        b = intersection(bounds, view_box)
+        k = f(1.0) / f(TILE)
+        self.x0, self.y0 = int(np.floor(b[0] * k)), int(np.floor(b[1] * k))
+        self.x1, self.y1 = int(np.ceil(b[2] * k)), int(np.ceil(b[3] * k))
+        self.w, self.h = self.x1 - self.x0, self.y1 - self.y0
+        self.alpha = {}      # (tx, ty) -> alpha tile id
+        self.backdrop = {}   # (tx, ty) -> i8 delta, then the propagated backdrop
+        self.col_backdrop = [0] * max(self.w, 0)
+
+    def inside(self, tx, ty):
+        return self.x0 <= tx < self.x1 and self.y0 <= ty < self.y1
+
+    def add_fill(self, frm, to, tx, ty):
+        if not self.inside(tx, ty):
+            return
+        ox, oy = f(tx) * f(TILE), f(ty) * f(TILE)
+        vals = [(frm[0] - ox) * f(256.0), (frm[1] - oy) * f(256.0), (to[0] - ox) * f(256.0), (to[1] - oy) * f(256.0)]
+        hi = f(TILE * 256 - 1)
+        q = []
+        for v in vals:
+            v = v if v > f(0.0) else f(0.0)       # clamp: max(min), then min(max)
+            v = v if v < hi else hi
+            q.append(int(np.rint(v)))             # cvtps: round to nearest, ties to even
+        if q[0] == q[2]:
+            return
+        key = (tx, ty)
+        if key not in self.alpha:
+            self.alpha[key] = self.state["next_alpha"]
+            self.state["next_alpha"] += 1
+        self.state["fills"].append((q[0], q[1], q[2], q[3], self.alpha[key]))
+
+    def adjust_backdrop(self, tx, ty, delta):
+        ox, oy = tx - self.x0, ty - self.y0
+        if ox < 0 or ox >= self.w or oy >= self.h:
+            return
+        if oy < 0:
+            self.col_backdrop[ox] += delta
+            return
+        self.backdrop[(tx, ty)] = self.backdrop.get((tx, ty), 0) + delta
+
+    def prepare_tiles(self):
+        """Returns {(tx, ty): (alpha tile id | INVALID, backdrop)} for every tile of the rect."""
+        out = {}
+        cols = list(self.col_backdrop)
+        for ty in range(self.y0, self.y1):
+            for tx in range(self.x0, self.x1):
+                col = tx - self.x0
+                delta = self.backdrop.get((tx, ty), 0)
+                out[(tx, ty)] = (self.alpha.get((tx, ty), INVALID), ((cols[col] + 128) % 256) - 128)
+                cols[col] += delta
+        return out
+
+
+def intersection(a, b):
+    """RectF::intersection(...).unwrap_or(RectF::default()) (geometry/src/rect.rs:122-137)."""
+    if not (a[0] < b[2] and a[1] < b[3] and b[0] < a[2] and b[1] < a[3]):
+        return (f(0), f(0), f(0), f(0))
+    return (max(a[0], b[0]), max(a[1], b[1]), min(a[2], b[2]), min(a[3], b[3]))
+
+
+def outcode(p, r):
+    code = 0
+    if p[0] < r[0]:
+        code |= 1   # LEFT
+    if p[1] < r[1]:
+        code |= 4   # TOP
+    if p[0] > r[2]:
+        code |= 2   # RIGHT
+    if p[1] > r[3]:
+        code |= 8   # BOTTOM
+    return code
+
+
+def lerp(a, b, t):  # util.rs: a + (b - a) * t
+    return a + (b - a) * t
+
+
+def clip_line(frm, to, r):
+    cf, ct = outcode(frm, r), outcode(to, r)
+    while True:
+        if cf == 0 and ct == 0:
+            return frm, to
+        if cf & ct:
+            return None
+        clip_from = cf > ct
+        code = cf if clip_from else ct
+        if code & 1:
+            p = (r[0], lerp(frm[1], to[1], (r[0] - frm[0]) / (to[0] - frm[0])))
+        elif code & 2:
+            p = (r[2], lerp(frm[1], to[1], (r[2] - frm[0]) / (to[0] - frm[0])))
+        elif code & 4:
+            p = (lerp(frm[0], to[0], (r[1] - frm[1]) / (to[1] - frm[1])), r[1])
+        else:
+            p = (lerp(frm[0], to[0], (r[3] - frm[1]) / (to[1] - frm[1])), r[3])
+        if clip_from:
+            frm, cf = p, outcode(p, r)
+        else:
+            to, ct = p, outcode(p, r)
+
+
+def process_line_segment(frm, to, b: PathBuilder, lines=None):
+    if lines is not None:
+        lines.append((frm[0], frm[1], to[0], to[1]))
+    vb = b.view_box
+    with np.errstate(all="ignore"):
+        clipped = clip_line(frm, to, (vb[0], f(-np.inf), vb[2], vb[3]))
+        if clipped is None:
+            return
+        frm, to = clipped
+        k = f(1.0) / f(TILE)
+        ftx, fty = int(np.floor(frm[0] * k)), int(np.floor(frm[1] * k))
+        ttx, tty = int(np.floor(to[0] * k)), int(np.floor(to[1] * k))
+        vx, vy = to[0] - frm[0], to[1] - frm[1]
+        neg_x, neg_y = bool(vx < 0), bool(vy < 0)
+        step_x, step_y = (-1 if neg_x else 1), (-1 if neg_y else 1)
+        cross_x = f(ftx + (0 if neg_x else 1)) * f(TILE)
+        cross_y = f(fty + (0 if neg_y else 1)) * f(TILE)
+        t_max_x, t_max_y = (cross_x - frm[0]) / vx, (cross_y - frm[1]) / vy
+        t_delta_x, t_delta_y = abs(f(TILE) / vx), abs(f(TILE) / vy)
+        cur = frm
+        tx, ty = ftx, fty
+        last = None
+        while True:
+            if t_max_x < t_max_y:
+                nxt = "x"
+            elif t_max_x > t_max_y:
+                nxt = "y"
+            else:
+                nxt = "x" if step_x > 0 else "y"
+            next_t = t_max_x if nxt == "x" else t_max_y
+            next_t = next_t if next_t < f(1.0) else f(1.0)   # f32::min(next_t, 1.0); NaN -> 1.0
+            if not (next_t == next_t):
+                next_t = f(1.0)
+            if (tx, ty) == (ttx, tty):
+                nxt = None
+            nxt_pos = (frm[0] + vx * next_t, frm[1] + vy * next_t)
+            b.add_fill(cur, nxt_pos, tx, ty)
+            corner = (f(tx) * f(TILE), f(ty) * f(TILE))
+            if step_y < 0 and nxt == "y":
+                b.add_fill(nxt_pos, corner, tx, ty)
+            elif step_y > 0 and last == "y":
+                b.add_fill(corner, cur, tx, ty)
+            if step_x < 0 and last == "x":
+                b.adjust_backdrop(tx, ty, 1)
+            elif step_x > 0 and nxt == "x":
+                b.adjust_backdrop(tx, ty, -1)
+            if nxt is None:
+                break
+            if nxt == "x":
+                if tx == ttx:
+                    break
+                t_max_x = t_max_x + t_delta_x
+                tx += step_x
+            else:
+                if ty == tty:
+                    break
+                t_max_y = t_max_y + t_delta_y
+                ty += step_y
+            cur = nxt_pos
+            last = nxt
+
+
+def process_cubic(p0, c0, c1, p3, b, lines):
+    if is_flat(p0, c0, c1, p3):
+        process_line_segment(p0, p3, b, lines)
+        return
+    first, second = split_half(p0, c0, c1, p3)
+    process_cubic(*first, b, lines)
+    process_cubic(*second, b, lines)
+
+
+def process_segment(seg, b, lines):
+    if seg[0] == "line":
+        process_line_segment(seg[1], seg[2], b, lines)
+    elif seg[0] == "quad":
+        p0, c, p3 = seg[1], seg[2], seg[3]
+        c2 = add(c, c)
+        third = f(1.0) / f(3.0)
+        process_cubic(p0, scale(add(p0, c2), third), scale(add(c2, p3), third), p3, b, lines)
+    else:
+        process_cubic(seg[1], seg[2], seg[3], seg[4], b, lines)
+
+
+def tile_scene(flat):
+    """Tiles every draw path of a FlatScene (no transform, no clip paths). Returns (fills, tiles, lines):
+    fills = [(from_x, from_y, to_x, to_y, alpha tile id)] in emission order; tiles[path] = {(tx, ty): (alpha id,
+    backdrop)}; lines[path] = flattened segments in emission order."""
+    state = {"next_alpha": 0, "fills": []}
+    vb = tuple(f(v) for v in flat.view_box)
+    co = [int(v) for v in flat.contour_offsets]
+    tiles, lines = [], []
+    for p in range(flat.n_paths):
+        c0, c1 = int(flat.path_contour_offsets[p]), int(flat.path_contour_offsets[p + 1])
+        contours = []
+        for c in range(c0, c1):
+            pts = [(f(x), f(y)) for x, y in flat.points[co[c]:co[c + 1]]]
+            if pts:
+                contours.append((pts, [int(v) for v in flat.point_flags[co[c]:co[c + 1]]]))
+        allp = [q for pts, _ in contours for q in pts]
+        if allp:
+            bounds = (min(q[0] for q in allp), min(q[1] for q in allp), max(q[0] for q in allp), max(q[1] for q in allp))
+        else:
+            bounds = (f(0), f(0), f(0), f(0))
+        b = PathBuilder(bounds, vb, state)
+        path_lines = []
+        for pts, fl in contours:
+            for seg in contour_segments(pts, fl):
+                process_segment(seg, b, path_lines)
+        tiles.append(b.prepare_tiles())
+        lines.append(path_lines)
+    return state["fills"], tiles, lines
