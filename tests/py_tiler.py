@@ -12,9 +12,10 @@ small scenes. Restated here:
   clip_line_segment_to_rect              content/src/clip.rs:494-565
   ObjectBuilder::add_fill, adjust_alpha_tile_backdrop, get_or_allocate_alpha_tile_index
                                          renderer/src/builder.rs:509-616
-  Tiler::new bounds, round_rect_out_to_tile_bounds, prepare_tiles (no clip path)
+  Tiler::new bounds, round_rect_out_to_tile_bounds, prepare_tiles (with the four clip cases)
                                          renderer/src/tiler.rs:47-50,100-165; renderer/src/tiles.rs:64-66
-Only solid-colour draw paths without clip paths; sequential order (SequentialExecutor)."""
+plus the D3D9 batch pack with its z-buffer (renderer/src/builder.rs:1011-1040). Solid-colour draw paths, clip paths one
+level deep, no transform; sequential order (SequentialExecutor)."""
 from __future__ import annotations
 
 import numpy as np
@@ -132,17 +133,33 @@ class PathBuilder:
             return
         self.backdrop[(tx, ty)] = self.backdrop.get((tx, ty), 0) + delta
 
-    def prepare_tiles(self):
-        """Returns {(tx, ty): (alpha tile id | INVALID, backdrop)} for every tile of the rect."""
-        out = {}
+    def prepare_tiles(self, clip=None):
+        """Tiler::prepare_tiles (tiler.rs:100-165). `clip` = (tile rect, prepared tiles) of the built clip path, or
+        None. Returns ({(tx, ty): (alpha tile id | INVALID, backdrop)} for every tile of the rect, clip records in
+        row-major order as (dest_tile_id, dest_backdrop, src_tile_id, src_backdrop))."""
+        out, clips = {}, []
         cols = list(self.col_backdrop)
         for ty in range(self.y0, self.y1):
             for tx in range(self.x0, self.x1):
                 col = tx - self.x0
                 delta = self.backdrop.get((tx, ty), 0)
-                out[(tx, ty)] = (self.alpha.get((tx, ty), INVALID), ((cols[col] + 128) % 256) - 128)
+                alpha, backdrop = self.alpha.get((tx, ty), INVALID), ((cols[col] + 128) % 256) - 128
+                if clip is not None:
+                    (cx0, cy0, cx1, cy1), clip_tiles = clip
+                    if cx0 <= tx < cx1 and cy0 <= ty < cy1:
+                        clip_alpha, clip_backdrop = clip_tiles[(tx, ty)]
+                        if clip_alpha != INVALID and alpha != INVALID:
+                            clips.append((alpha, backdrop, clip_alpha, clip_backdrop))  # combine the two masks
+                            backdrop = 0
+                        elif clip_alpha != INVALID and alpha == INVALID and backdrop != 0:
+                            alpha, backdrop = clip_alpha, clip_backdrop                 # solid tile: the clip's mask
+                        elif clip_alpha == INVALID and clip_backdrop == 0:
+                            alpha, backdrop = INVALID, 0                                # blank clip tile: cull
+                    else:
+                        alpha, backdrop = INVALID, 0                                    # outside the clip's rect
+                out[(tx, ty)] = (alpha, backdrop)
                 cols[col] += delta
-        return out
+        return out, clips
 
 
 def intersection(a, b):
@@ -275,31 +292,64 @@ def process_segment(seg, b, lines):
         process_cubic(seg[1], seg[2], seg[3], seg[4], b, lines)
 
 
+def _tile_outline(flat, c0, c1, vb, state, clip=None):
+    co = flat.contour_offsets
+    contours = []
+    for c in range(int(c0), int(c1)):
+        pts = [(f(x), f(y)) for x, y in flat.points[int(co[c]):int(co[c + 1])]]
+        if pts:
+            contours.append((pts, [int(v) for v in flat.point_flags[int(co[c]):int(co[c + 1])]]))
+    allp = [q for pts, _ in contours for q in pts]
+    if allp:
+        bounds = (min(q[0] for q in allp), min(q[1] for q in allp), max(q[0] for q in allp), max(q[1] for q in allp))
+    else:
+        bounds = (f(0), f(0), f(0), f(0))
+    b = PathBuilder(bounds, vb, state)
+    path_lines = []
+    for pts, fl in contours:
+        for seg in contour_segments(pts, fl):
+            process_segment(seg, b, path_lines)
+    tiles, clips = b.prepare_tiles(clip)
+    return (b.x0, b.y0, b.x1, b.y1), tiles, clips, path_lines
+
+
 def tile_scene(flat):
-    """Tiles every draw path of a FlatScene (no transform, no clip paths). Returns (fills, tiles, lines):
-    fills = [(from_x, from_y, to_x, to_y, alpha tile id)] in emission order; tiles[path] = {(tx, ty): (alpha id,
-    backdrop)}; lines[path] = flattened segments in emission order."""
+    """Tiles a FlatScene (no transform; clip paths one level deep) the way SceneBuilder::build does on the CPU with a
+    SequentialExecutor: every clip path first, then the draw paths (builder.rs:224-325). Returns a dict:
+      fills       [(from_x, from_y, to_x, to_y, alpha tile id)] in emission order
+      lines       flattened segments per path, clip paths first
+      tiles       the D3D9 batch's tile list (builder.rs:1011-1028): (tile_x, tile_y, alpha id, draw path id, backdrop)
+                  of every tile with a mask or a backdrop, path by path, row-major
+      clips       the batch's Clip records (builder.rs:1031-1040)
+      z_buffer    max draw path id over solid tiles of occluding paths, over the view box's tile rect, initially 0"""
     state = {"next_alpha": 0, "fills": []}
     vb = tuple(f(v) for v in flat.view_box)
-    co = [int(v) for v in flat.contour_offsets]
-    tiles, lines = [], []
-    for p in range(flat.n_paths):
-        c0, c1 = int(flat.path_contour_offsets[p]), int(flat.path_contour_offsets[p + 1])
-        contours = []
-        for c in range(c0, c1):
-            pts = [(f(x), f(y)) for x, y in flat.points[co[c]:co[c + 1]]]
-            if pts:
-                contours.append((pts, [int(v) for v in flat.point_flags[co[c]:co[c + 1]]]))
-        allp = [q for pts, _ in contours for q in pts]
-        if allp:
-            bounds = (min(q[0] for q in allp), min(q[1] for q in allp), max(q[0] for q in allp), max(q[1] for q in allp))
-        else:
-            bounds = (f(0), f(0), f(0), f(0))
-        b = PathBuilder(bounds, vb, state)
-        path_lines = []
-        for pts, fl in contours:
-            for seg in contour_segments(pts, fl):
-                process_segment(seg, b, path_lines)
-        tiles.append(b.prepare_tiles())
+    lines, built_clips = [], []
+    for (c0, c1) in flat.clip_contour_ranges:
+        rect, tiles, _, path_lines = _tile_outline(flat, c0, c1, vb, state)
+        built_clips.append((rect, tiles))
         lines.append(path_lines)
-    return state["fills"], tiles, lines
+    k = f(1.0) / f(TILE)
+    zx0, zy0 = int(np.floor(vb[0] * k)), int(np.floor(vb[1] * k))
+    zx1, zy1 = int(np.ceil(vb[2] * k)), int(np.ceil(vb[3] * k))
+    z = np.zeros((max(zy1 - zy0, 0), max(zx1 - zx0, 0)), np.int32)
+    batch_tiles, batch_clips = [], []
+    paints, colors = flat.palette()
+    for p in range(flat.n_paths):
+        clip_id = int(flat.draw_clip_paths[p])
+        clip = None if clip_id == INVALID else built_clips[clip_id]
+        rect, tiles, clips, path_lines = _tile_outline(flat, flat.path_contour_offsets[p], flat.path_contour_offsets[p + 1],
+                                                       vb, state, clip)
+        lines.append(path_lines)
+        occludes = int(colors[int(paints[p])][3]) == 255   # BuiltDrawPath::new: opaque paint and SrcOver
+        for ty in range(rect[1], rect[3]):
+            for tx in range(rect[0], rect[2]):
+                alpha, backdrop = tiles[(tx, ty)]
+                if alpha == INVALID and backdrop == 0:
+                    continue
+                batch_tiles.append((tx, ty, alpha, p, backdrop))
+                if occludes and alpha == INVALID:
+                    z[ty - zy0, tx - zx0] = max(z[ty - zy0, tx - zx0], p)
+        batch_clips += [c for c in clips if c[0] != INVALID and c[2] != INVALID]
+    return {"fills": state["fills"], "lines": lines, "tiles": batch_tiles, "clips": batch_clips, "z_buffer": z,
+            "z_rect": (zx0, zy0, zx1, zy1)}

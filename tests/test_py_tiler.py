@@ -14,21 +14,31 @@ INVALID = 0xFFFFFFFF
 
 def compare(flat: FlatScene):
     built = H.oracle_build(flat, None, keep_lines=True)
-    fills, tiles, lines = P.tile_scene(flat)
-    for p in range(flat.n_paths):
+    mine = P.tile_scene(flat)
+    for p in range(flat.n_clip_paths + flat.n_paths):   # clip paths first
         want = built.path_lines(p)
-        got = np.asarray(lines[p], np.float32).reshape(-1, 4)
+        got = np.asarray(mine["lines"][p], np.float32).reshape(-1, 4)
         assert want.tobytes() == got.tobytes(), f"path {p}: flattened lines differ"
+    fills = mine["fills"]
     assert len(fills) == len(built.fills)
     got = np.asarray(fills, np.int64).reshape(-1, 5)
     for k, name in enumerate(("from_x", "from_y", "to_x", "to_y", "link")):
         assert np.array_equal(got[:, k], built.fills[name].astype(np.int64)), name
-    # Every tile the oracle's batch lists (non-empty tiles that survive the z-buffer) carries the alpha-tile id and
-    # the propagated backdrop the second tiler derives for that path and position.
-    assert len(built.tiles) > 0 or len(fills) == 0
-    for t in built.tiles:
-        alpha, backdrop = tiles[int(t["path_id"])][(int(t["tile_x"]), int(t["tile_y"]))]
-        assert alpha == int(t["alpha_tile_id"]) and backdrop == int(t["backdrop"]), t
+    # the whole D3D9 batch: every non-empty tile in path order, the Clip records, the z-buffer
+    got = np.asarray(mine["tiles"], np.int64).reshape(-1, 5)
+    assert len(got) == len(built.tiles)
+    for k, name in enumerate(("tile_x", "tile_y", "alpha_tile_id", "path_id", "backdrop")):
+        assert np.array_equal(got[:, k], built.tiles[name].astype(np.int64)), name
+    paints, _ = flat.palette()
+    assert np.array_equal(built.tiles["color"], np.asarray(paints)[built.tiles["path_id"]])
+    assert np.array_equal(built.tiles["ctrl"], np.where(flat.fill_rules[built.tiles["path_id"]] == 1, 2, 1))
+    got = np.asarray(mine["clips"], np.int64).reshape(-1, 4)
+    assert len(got) == len(built.clips)
+    for k, name in enumerate(("dest_tile_id", "dest_backdrop", "src_tile_id", "src_backdrop")):
+        assert np.array_equal(got[:, k], built.clips[name].astype(np.int64)), name
+    x0, y0, x1, y1 = mine["z_rect"]
+    assert tuple(built.z_rect) == (x0, y0, x1, y1) or tuple(built.z_rect) == (x0, y0, x1 - x0, y1 - y0)
+    assert np.array_equal(mine["z_buffer"], built.z_buffer)
     return len(fills)
 
 
@@ -77,6 +87,20 @@ def test_axis_aligned_and_degenerate_edges():
     b.move_to(100, 100); b.line_to(120, 100); b.line_to(110, 130); b.close()                     # outside the view box
     b.end_path((9, 9, 9, 255))
     assert compare(b.finish("edges")) > 0
+
+
+def test_clipped_scenes():
+    """The four cases of Tiler::prepare_tiles with a clip path, Clip records included, on the seeded clip scenes of
+    the GPU fuzz (clip paths used in scene order, draw paths clipped or not) with their transforms dropped."""
+    from tests.test_parity_gpu import clip_scene, fuzz_clip_scene
+    assert compare(clip_scene(128)) > 0
+    n_clips = 0
+    for seed in range(12):
+        flat = fuzz_clip_scene(seed)
+        flat = flat[0] if isinstance(flat, tuple) else flat
+        compare(flat)
+        n_clips += len(H.oracle_build(flat, None).clips)
+    assert n_clips > 20
 
 
 def test_tiger_and_text_page():
