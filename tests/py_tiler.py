@@ -353,3 +353,90 @@ def tile_scene(flat):
         batch_clips += [c for c in clips if c[0] != INVALID and c[2] != INVALID]
     return {"fills": state["fills"], "lines": lines, "tiles": batch_tiles, "clips": batch_clips, "z_buffer": z,
             "z_rect": (zx0, zy0, zx1, zy1)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Coverage and compositing, restated from the shaders (floating point: compared within a tolerance, not bit for bit).
+#   computeCoverage                 shaders/fill_area.inc.glsl:11-27
+#   accumulateCoverageForFillList   shaders/d3d11/fill_compute.inc.glsl:11-25
+#   clip combine                    shaders/d3d9/tile_clip_combine.fs.glsl:28-31
+#   sampleMask, calculateColor      shaders/tile_fragment.inc.glsl:539-614
+#   dest = dest * (1 - a) + src     shaders/d3d11/tile.cs.glsl:155
+# with the decisions of DESIGN.md §2 (D3D9 semantics: unclamped coverage, fill rule at composite, solid tiles use
+# coverage = backdrop through the same rule; tiles behind an occluder are skipped: path id < z).
+# ---------------------------------------------------------------------------------------------------------------
+
+def sample_lut(lut, u, v):
+    """texture(areaLUT, vec2(u, v)) over the (256, 256, 4) RGBA8 table: bilinear, clamp to edge."""
+    h, w, _ = lut.shape
+    table = lut.astype(np.float32) / f(255.0)
+    x, y = u * f(w) - f(0.5), v * f(h) - f(0.5)
+    x0, y0 = np.floor(x), np.floor(y)
+    fx, fy = (x - x0)[..., None], (y - y0)[..., None]
+    xa, xb = np.clip(x0.astype(np.int64), 0, w - 1), np.clip(x0.astype(np.int64) + 1, 0, w - 1)
+    ya, yb = np.clip(y0.astype(np.int64), 0, h - 1), np.clip(y0.astype(np.int64) + 1, 0, h - 1)
+    top = table[ya, xa] * (f(1.0) - fx) + table[ya, xb] * fx
+    bottom = table[yb, xa] * (f(1.0) - fx) + table[yb, xb] * fx
+    return top * (f(1.0) - fy) + bottom * fy
+
+
+def alpha_masks(fills, n_alpha, lut):
+    """(n_alpha, 16, 16) float32 coverage sums: thread (x, strip) handles pixel column x, rows 4 strip .. 4 strip + 3."""
+    masks = np.zeros((n_alpha, 16, 16), np.float32)
+    cx = (np.arange(16, dtype=np.float32) + f(0.5))[None, :]                # (1, 16): tileFragCoord.x
+    cy = (np.arange(4, dtype=np.float32) * f(4.0) + f(0.5))[:, None]        # (4, 1):  tileFragCoord.y of each strip
+    with np.errstate(all="ignore"):
+        for fx, fy, tx, ty, link in fills:
+            from_x, from_y = f(fx) / f(256.0) - cx, f(fy) / f(256.0) - cy
+            to_x, to_y = f(tx) / f(256.0) - cx, f(ty) / f(256.0) - cy
+            from_x, to_x = np.broadcast_to(from_x, (4, 16)), np.broadcast_to(to_x, (4, 16))
+            from_y, to_y = np.broadcast_to(from_y, (4, 16)), np.broadcast_to(to_y, (4, 16))
+            from_left = from_x < to_x
+            lx, ly = np.where(from_left, from_x, to_x), np.where(from_left, from_y, to_y)
+            rx, ry = np.where(from_left, to_x, from_x), np.where(from_left, to_y, from_y)
+            wx, wy = np.clip(from_x, f(-0.5), f(0.5)), np.clip(to_x, f(-0.5), f(0.5))
+            offset = (wx * f(0.5) + wy * f(0.5)) - lx                        # mix(window.x, window.y, 0.5) - left.x
+            t = offset / (rx - lx)
+            y = ly * (f(1.0) - t) + ry * t                                   # mix(left.y, right.y, t)
+            d = (ry - ly) / (rx - lx)
+            dx = wx - wy
+            tex = sample_lut(lut, (y + f(8.0)) / f(16.0), np.abs(d * dx) / f(16.0))   # (4, 16, 4): channel k = row + k
+            cov = tex * dx[..., None]
+            cov = np.where((dx == 0)[..., None], f(0.0), cov)                # 0 * NaN: columns outside the segment
+            masks[link] += cov.transpose(0, 2, 1).reshape(16, 16)
+    return masks
+
+
+def f16_round(x):
+    return np.asarray(x, np.float32).astype(np.float16).astype(np.float32)
+
+
+def render(flat, result, lut, width, height, background=(0.0, 0.0, 0.0, 0.0)):
+    """The frame as float32 RGBA (premultiplied), before the RGBA8 store."""
+    n_alpha = 1 + max([t[4] for t in result["fills"]], default=-1)
+    masks = alpha_masks(result["fills"], n_alpha, lut)
+    for dest_id, dest_backdrop, src_id, src_backdrop in result["clips"]:
+        masks[dest_id] = np.minimum(np.abs(masks[dest_id] + f(dest_backdrop)), np.abs(masks[src_id] + f(src_backdrop)))
+    dest = np.empty((height, width, 4), np.float32)
+    dest[:] = np.asarray(background, np.float32)
+    paints, colors = flat.palette()
+    zx0, zy0, _, _ = result["z_rect"]
+    for tx, ty, alpha, path, backdrop in result["tiles"]:
+        if path < result["z_buffer"][ty - zy0, tx - zx0]:
+            continue
+        x0, y0 = tx * TILE, ty * TILE
+        x1, y1 = min(x0 + TILE, width), min(y0 + TILE, height)
+        if x0 < 0 or y0 < 0 or x1 <= x0 or y1 <= y0:
+            continue
+        coverage = (masks[alpha] if alpha != INVALID else np.zeros((16, 16), np.float32)) + f(backdrop)
+        if int(flat.fill_rules[path]) == 0:
+            coverage = np.abs(coverage)
+        else:
+            m = coverage - f(2.0) * np.floor(coverage / f(2.0))             # mod(coverage, 2.0)
+            coverage = f(1.0) - np.abs(f(1.0) - m)
+        mask_alpha = np.minimum(f(1.0), coverage)[: y1 - y0, : x1 - x0]
+        base = f16_round(colors[int(paints[path])].astype(np.float32) * (f(1.0) / f(255.0)))  # RGBA16F paint texel
+        a = base[3] * mask_alpha
+        src = np.stack([base[0] * a, base[1] * a, base[2] * a, a], axis=-1)
+        dest[y0:y1, x0:x1] = dest[y0:y1, x0:x1] * (f(1.0) - a)[..., None] + src
+    return dest

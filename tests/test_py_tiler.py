@@ -110,3 +110,30 @@ def test_tiger_and_text_page():
     flat, xf = scenes.tiger(128)
     assert compare(prepared_scene(flat, xf, (0.0, 0.0))) > 1000
     assert compare(scenes.text_page(60, 128, layout="lines")) > 500
+
+
+def compare_pixels(flat, area_lut, background=(1.0, 1.0, 1.0, 1.0)):
+    w, h = int(flat.view_box[2]), int(flat.view_box[3])
+    built = H.oracle_build(flat, None)
+    mine = P.tile_scene(flat)
+    masks = P.alpha_masks(mine["fills"], built.alpha_tile_count, area_lut)
+    want = built.alpha_masks(area_lut)
+    assert masks.shape == want.shape
+    assert np.abs(masks - want).max() <= 2e-5, np.abs(masks - want).max()
+    frame = P.render(flat, mine, area_lut, w, h, background)
+    ref = built.render(area_lut, w, h, background=background, want_f32=True)
+    ref = ref[1] if isinstance(ref, tuple) else ref
+    assert np.abs(frame - ref.reshape(h, w, 4)).max() <= 1e-4
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_coverage_and_composite_random(area_lut, seed):
+    compare_pixels(random_scene(100 + seed), area_lut)
+
+
+def test_coverage_and_composite_clipped(area_lut):
+    from tests.test_parity_gpu import clip_scene, fuzz_clip_scene
+    compare_pixels(clip_scene(128), area_lut)
+    for seed in range(4):
+        flat = fuzz_clip_scene(seed)
+        compare_pixels(flat[0] if isinstance(flat, tuple) else flat, area_lut, background=(0.0, 0.0, 0.0, 0.0))
