@@ -8,8 +8,12 @@
  *
  * PARITY UNPINNED: the reference holds no tests or golden vectors for this path
  *  and cannot be compiled here (no rustc/cargo); this restatement
- * is pinned only by the weak simd KATs (simd/src/test.rs) and by its own
- * property tests (tests/test_oracle_*.py).
+ * is pinned only by the weak simd KATs (simd/src/test.rs), by its own property
+ * tests (tests/test_oracle.py), by the reference's shipped LUT textures, and by
+ * double entry: tests/py_tiler.py restates the tiler, the batch pack and the
+ * shader math a second time, independently, and tests/test_py_tiler.py demands
+ * bit-identical lists (float-tolerant pixels) from both. Neither is the Rust
+ * tiler itself: tools/reference_dump/ is the kit that pins it where cargo exists.
  */
 #ifndef PF_ORACLE_H
 #define PF_ORACLE_H
