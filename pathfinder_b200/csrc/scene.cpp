@@ -743,7 +743,11 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                 RectF path_bounds = prepared ? s->prepared_draw_bounds[i]
                                              : xf.is_identity() ? p.bounds : xf.apply_rect(p.bounds);
                 RectF clipped;
-                if (rect_intersection(path_bounds, effective_view_box, clipped)) {
+                // (An outline without contours has the bounds (0, 0, 0, 0); grown by a dilation they would reach
+                // into the view box and keep a path that has nothing to tile. The CPU tiler builds one blank tile
+                // for it, which never reaches a batch; here the path is skipped like any other invisible one.)
+                const bool has_outline = p.first_contour != p.end_contour;
+                if ((has_outline || !prepared) && rect_intersection(path_bounds, effective_view_box, clipped)) {
                     // round_rect_out_to_tile_bounds (tiles.rs:64-66); floor/ceil results are integral,
                     // so the float -> int conversion is exact in any rounding mode.
                     const float k = 1.0f / 16.0f;

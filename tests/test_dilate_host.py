@@ -202,3 +202,19 @@ def test_clip_paths_are_dilated_too():
     assert np.allclose(seen["clip_points"], want, atol=1e-5)
     api.Scene.from_flat(flat).build(api.BuildOptions(), listener)
     assert seen["rect"] == (2, 2, 6, 6)
+
+
+def test_empty_paths_stay_out_of_a_dilated_batch():
+    """An outline without contours has zero bounds; dilated they overlap the view box's corner. The CPU tiler builds
+    one blank tile for such a path (never listed in a batch); the D3D11-level builder skips it like without dilation."""
+    b = SceneBuilderPy((0, 0, 64, 64))
+    b.end_path((1, 2, 3, 255))                                    # nothing pushed
+    b.move_to(8, 8); b.line_to(40, 12); b.line_to(20, 44); b.close()
+    b.end_path((200, 0, 0, 255))
+    flat = b.finish("with-empty")
+    for dilation in ((0.0, 0.0), (1.0, 1.0)):
+        cmds = collect(api.Scene.from_flat(flat), api.BuildOptions(dilation=dilation))
+        draw = [c for c in cmds if c["kind"] == "DrawTilesD3D11"][0]
+        assert draw["path_count"] == 1 and draw["global_path_ids"] == [1]
+        built = H.oracle_build(flat, None, dilation=dilation)
+        assert len(built.tiles) > 0 and (built.tiles["path_id"] == 1).all()
