@@ -467,6 +467,8 @@ def main():
         return
 
     value = seg_per_step * args.steps / dev_s / 1e9
+    inputs_per_step = sum(int(f.full_stats.get("input_segment_count", 0)) for f in frames)
+    fills_per_step = sum(int(f.full_stats.get("fill_count", 0)) for f in frames)
     e2e_value = seg_per_step * e2e_steps / e2e_s / 1e9
 
     # Roofline of the dominant kernel (fused fill + tile) on the largest scene: algorithmic bytes
@@ -512,6 +514,10 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAMES[args.workload], "frames_per_step": len(frames),
                    "segments_per_step": seg_per_step,
+                   # the same step counted in input segments (SegmentIndicesD3D11) and in fills
+                   "input_segments_per_step": inputs_per_step, "fills_per_step": fills_per_step,
+                   "input_gsegments_per_s": inputs_per_step * args.steps / dev_s / 1e9,
+                   "gfills_per_s": fills_per_step * args.steps / dev_s / 1e9,
                    "parallelism": f"tile-strip x{world}" + ((" + fused peer-store gather (NVLink P2P) + barrier" if args.gather == "peer"
                                                              else " + NCCL all-gather overlapped with the next frame") if world > 1 else ""),
                    "l2": "inputs larger than L2: a step touches > 1 GB of stage buffers and frames",
