@@ -286,9 +286,12 @@ struct BuiltPath {
 struct SceneCtx {
     RectF view_box;            // scene.view_box(): what process_line_segment clips to (quirk 1)
     RectF effective_view_box;  // scene.effective_view_box(): bounds / tile rect
-    std::atomic<uint32_t> next_alpha_tile{0}; // next_alpha_tile_indices[0], builder.rs:55
     bool keep_lines = false;
     int32_t strip_y0 = 0, strip_y1 = 0;
+    // next_alpha_tile_indices[0], builder.rs:55. On its own cache line: every worker increments it per alpha tile,
+    // and every line segment reads the fields above.
+    alignas(64) std::atomic<uint32_t> next_alpha_tile{0};
+    char pad_[60];
 };
 
 // RectF::intersects + intersection (rect.rs:122-137): strict '<' on all four lanes.
@@ -714,7 +717,7 @@ PFOBuilt *pfo_build(const PFOScene *scene, const PFOBuildOptions *options, int n
     b->z_buffer.assign((size_t)std::max(zr.width(), 0) * std::max(zr.height(), 0), 0);
     size_t total_tiles = 0;
     for (const BuiltPath &bp : b->draw_paths) total_tiles += bp.tiles.size();
-    b->tiles.reserve(total_tiles / 2);
+    b->tiles.reserve(total_tiles); // address space only: pages are touched as tiles are appended, and nothing is copied
     for (uint32_t pi = 0; pi < s.n_draw_paths; pi++) {
         const BuiltPath &bp = b->draw_paths[pi];
         for (const PFOTileObjectPrimitive &tile : bp.tiles) { // builder.rs:1013-1029
