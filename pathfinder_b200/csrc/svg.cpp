@@ -91,10 +91,14 @@ void arc_to_cubics(Builder &b, P p0, double rx, double ry, double phi_deg, bool 
     const double dx2 = (p0.x - p1.x) / 2.0, dy2 = (p0.y - p1.y) / 2.0;
     const double x1p = cphi * dx2 + sphi * dy2, y1p = -sphi * dx2 + cphi * dy2;
     const double lam = (x1p * x1p) / (rx * rx) + (y1p * y1p) / (ry * ry);
-    if (lam > 1.0) rx *= std::sqrt(lam), ry *= std::sqrt(lam);
+    const bool scaled_up = lam > 1.0; // F.6.6.3: radii too small for the chord are scaled until it is a diameter
+    if (scaled_up) rx *= std::sqrt(lam), ry *= std::sqrt(lam);
     const double num = rx * rx * ry * ry - rx * rx * y1p * y1p - ry * ry * x1p * x1p;
     const double den = rx * rx * y1p * y1p + ry * ry * x1p * x1p;
-    const double coef = std::sqrt(std::fmax(num / den, 0.0)) * (large == sweep ? -1.0 : 1.0);
+    // With scaled-up radii the centre is the chord's midpoint exactly; computing it from num / den leaves a
+    // rounding residue of either sign there, which makes the sweep (exactly half a turn) come out as pi +- 1e-8 and
+    // the number of pieces depend on the compiler.
+    const double coef = scaled_up ? 0.0 : std::sqrt(std::fmax(num / den, 0.0)) * (large == sweep ? -1.0 : 1.0);
     const double cxp = coef * rx * y1p / ry, cyp = -coef * ry * x1p / rx;
     const double cx = cphi * cxp - sphi * cyp + (p0.x + p1.x) / 2.0, cy = sphi * cxp + cphi * cyp + (p0.y + p1.y) / 2.0;
     auto angle = [](double ux, double uy, double vx, double vy) { return std::atan2(ux * vy - uy * vx, ux * vx + uy * vy); };

@@ -117,3 +117,62 @@ def test_tiger_scene_from_the_cpp_front_end_equals_the_fixture():
                 assert tuple(fixture.paint_colors[fixture.paints[path_index]]) == T.parse_color(stroke)
                 path_index += 1
     assert path_index == fixture.n_paths == 182
+
+
+def random_path_data(rng):
+    """Grammatical path data: every command with the right number of arguments (sometimes repeated), in the
+    number syntaxes SVG allows (signs as separators, leading dots, exponents, commas)."""
+    def number(lo=-200.0, hi=200.0):
+        v = rng.uniform(lo, hi)
+        style = rng.randint(0, 5)
+        if style == 0:
+            return "%d" % int(v)
+        if style == 1:
+            return ("%.3f" % v).replace("0.", ".", 1) if abs(v) < 1 else "%.3f" % v
+        if style == 2:
+            return "%.2e" % v
+        return "%g" % round(v, int(rng.randint(0, 4)))
+
+    def sep():
+        return str(rng.choice([" ", ",", " , ", "\n", ""]))
+
+    def args(n):
+        out = ""
+        for i in range(n):
+            s = number()
+            out += (sep() or (" " if not s.startswith("-") else "")) if i else ""
+            if out and out[-1] not in " ,\n" and not s.startswith("-"):
+                out += " "
+            out += s
+        return out
+
+    d = "M" + args(2)
+    for _ in range(int(rng.randint(1, 10))):
+        c = str(rng.choice(list("MmLlHhVvCcSsQqTtAaZz")))
+        n = {"M": 2, "L": 2, "H": 1, "V": 1, "C": 6, "S": 4, "Q": 4, "T": 2, "A": 7, "Z": 0}[c.upper()]
+        d += str(rng.choice(["", " "])) + c
+        for _rep in range(int(rng.randint(1, 3)) if n else 0):
+            if c.upper() == "A":
+                d += " " + " ".join([number(1, 80), number(1, 80), number(-180, 180), str(rng.randint(0, 2)),
+                                     str(rng.randint(0, 2)), number(), number()])
+            else:
+                d += " " + args(n)
+    return d
+
+
+def test_fuzzed_path_data_matches_the_python_parser():
+    """Differential fuzz of the two independent parsers (C++ in csrc/svg.cpp, Python in tools/make_tiger_scene.py):
+    same contours, flags and closedness; coordinates equal up to the libm calls of the arc conversion."""
+    rng = np.random.RandomState(21)
+    compared = 0
+    for _ in range(400):
+        d = random_path_data(rng)
+        pts, flags, offsets, closed = api.svg_path_to_outline(d)
+        ref_pts, ref_flags, ref_offsets, ref_closed = python_outline(d)
+        assert list(offsets) == ref_offsets, d
+        assert list(closed) == ref_closed and list(flags) == list(ref_flags), d
+        if len(pts):
+            scale = max(1.0, float(np.abs(ref_pts).max()))
+            assert np.abs(pts - ref_pts).max() <= 1e-5 * scale, d
+            compared += len(pts)
+    assert compared > 5000

@@ -50,11 +50,13 @@ def arc_to_cubics(p0, rx, ry, phi_deg, large, sweep, p1):
     dx2, dy2 = (p0[0] - p1[0]) / 2.0, (p0[1] - p1[1]) / 2.0
     x1p, y1p = cphi * dx2 + sphi * dy2, -sphi * dx2 + cphi * dy2
     lam = (x1p * x1p) / (rx * rx) + (y1p * y1p) / (ry * ry)
-    if lam > 1:
+    scaled_up = lam > 1
+    if scaled_up:
         rx, ry = rx * math.sqrt(lam), ry * math.sqrt(lam)
     num = rx * rx * ry * ry - rx * rx * y1p * y1p - ry * ry * x1p * x1p
     den = rx * rx * y1p * y1p + ry * ry * x1p * x1p
-    coef = math.sqrt(max(num / den, 0.0)) * (-1 if large == sweep else 1)
+    # scaled-up radii: the centre is the chord's midpoint exactly (no rounding residue, see csrc/svg.cpp)
+    coef = 0.0 if scaled_up else math.sqrt(max(num / den, 0.0)) * (-1 if large == sweep else 1)
     cxp, cyp = coef * rx * y1p / ry, -coef * ry * x1p / rx
     cx = cphi * cxp - sphi * cyp + (p0[0] + p1[0]) / 2.0
     cy = sphi * cxp + cphi * cyp + (p0[1] + p1[1]) / 2.0
