@@ -137,3 +137,28 @@ def test_coverage_and_composite_clipped(area_lut):
     for seed in range(4):
         flat = fuzz_clip_scene(seed)
         compare_pixels(flat[0] if isinstance(flat, tuple) else flat, area_lut, background=(0.0, 0.0, 0.0, 0.0))
+
+
+def test_off_origin_view_boxes_and_oversized_geometry():
+    """View boxes that start off the origin and off the tile grid (negative, fractional), with geometry up to forty
+    times larger than the view box: clipping to the view box, auxiliary fills and column backdrops above the rect."""
+    rng = np.random.RandomState(5)
+    for case in range(40):
+        x0, y0 = float(rng.choice([0, 16, 37.5, -40, 1000])), float(rng.choice([0, 8, -33.25, 500]))
+        w, h = float(rng.choice([33, 64, 100.5])), float(rng.choice([20, 64, 77.75]))
+        b = SceneBuilderPy((x0, y0, x0 + w, y0 + h))
+        for _ in range(int(rng.randint(1, 4))):
+            s = 40.0 if rng.rand() < 0.2 else 1.0
+            pt = lambda: (x0 + rng.uniform(-0.6, 1.6) * w * s, y0 + rng.uniform(-0.6, 1.6) * h * s)
+            b.move_to(*pt())
+            for _ in range(int(rng.randint(2, 6))):
+                k = rng.randint(0, 3)
+                if k == 0:
+                    b.line_to(*pt())
+                elif k == 1:
+                    b.quad_to(*pt(), *pt())
+                else:
+                    b.cubic_to(*pt(), *pt(), *pt())
+            b.close()
+            b.end_path((int(rng.randint(0, 256)), 9, 9, 255 if rng.rand() < 0.5 else 100), int(rng.randint(0, 2)))
+        compare(b.finish(f"adv{case}"))
