@@ -12,8 +12,10 @@ from tests import py_tiler as P
 INVALID = 0xFFFFFFFF
 
 
-def compare(flat: FlatScene):
-    built = H.oracle_build(flat, None, keep_lines=True)
+def compare(flat: FlatScene, oracle_input=None):
+    """`oracle_input` = (scene, transform) when the oracle is to apply a BuildOptions transform itself; `flat` then
+    holds the same points already transformed for the second tiler, which has no transform stage."""
+    built = H.oracle_build(*(oracle_input or (flat, None)), keep_lines=True)
     mine = P.tile_scene(flat)
     for p in range(flat.n_clip_paths + flat.n_paths):   # clip paths first
         want = built.path_lines(p)
@@ -109,6 +111,12 @@ def test_tiger_and_text_page():
     from tests.test_dilate_host import prepared_scene
     flat, xf = scenes.tiger(128)
     assert compare(prepared_scene(flat, xf, (0.0, 0.0))) > 1000
+    # and with the oracle applying the transform itself (Scene::apply_render_options): Transform2F * Vector2F is
+    # (m11 x + m12 y) + tx, (m21 x + m22 y) + ty, one rounding per operation
+    assert compare(prepared_scene(flat, xf, (0.0, 0.0)), oracle_input=(flat, xf)) > 1000
+    rotated = (0.8, -0.45, 0.3, 0.9, 20.0, 5.0)
+    text = scenes.text_page(40, 128, layout="lines")
+    assert compare(prepared_scene(text, rotated, (0.0, 0.0)), oracle_input=(text, rotated)) > 300
     assert compare(scenes.text_page(60, 128, layout="lines")) > 500
 
 
