@@ -128,14 +128,72 @@ typedef struct PFClip {                    /* gpu_data.rs:376-383 */
     int32_t src_backdrop;
 } PFClip;
 
-/* TextureMetadataEntry (gpu_data.rs:336-344). Only solid colours are on the hot path (SURVEY.md
- * §2 row 7): color_0_combine_mode must be 0 (None), filter 0 (None), blend_mode 0 (SrcOver). */
+/* BlendMode (content/src/effects.rs:99-163), numbered like the reference's enum. The Rust glue maps each
+ * variant to these constants explicitly (it must not rely on Rust discriminants or layouts). */
+#define PF_BLEND_MODE_CLEAR 0
+#define PF_BLEND_MODE_COPY 1
+#define PF_BLEND_MODE_SRC_IN 2
+#define PF_BLEND_MODE_SRC_OUT 3
+#define PF_BLEND_MODE_SRC_OVER 4
+#define PF_BLEND_MODE_SRC_ATOP 5
+#define PF_BLEND_MODE_DEST_IN 6
+#define PF_BLEND_MODE_DEST_OUT 7
+#define PF_BLEND_MODE_DEST_OVER 8
+#define PF_BLEND_MODE_DEST_ATOP 9
+#define PF_BLEND_MODE_XOR 10
+#define PF_BLEND_MODE_LIGHTER 11
+#define PF_BLEND_MODE_DARKEN 12
+#define PF_BLEND_MODE_LIGHTEN 13
+#define PF_BLEND_MODE_MULTIPLY 14
+#define PF_BLEND_MODE_SCREEN 15
+#define PF_BLEND_MODE_HARD_LIGHT 16
+#define PF_BLEND_MODE_OVERLAY 17
+#define PF_BLEND_MODE_COLOR_DODGE 18
+#define PF_BLEND_MODE_COLOR_BURN 19
+#define PF_BLEND_MODE_SOFT_LIGHT 20
+#define PF_BLEND_MODE_DIFFERENCE 21
+#define PF_BLEND_MODE_EXCLUSION 22
+#define PF_BLEND_MODE_HUE 23
+#define PF_BLEND_MODE_SATURATION 24
+#define PF_BLEND_MODE_COLOR 25
+#define PF_BLEND_MODE_LUMINOSITY 26
+
+#define PF_COLOR_COMBINE_MODE_NONE 0 /* ColorCombineMode, gpu_data.rs:346-352 */
+#define PF_COLOR_COMBINE_MODE_SRC_IN 1
+#define PF_COLOR_COMBINE_MODE_DEST_IN 2
+
+/* Filter (content/src/effects.rs:44-97), flattened: the Rust type is a data-carrying enum with no C layout.
+ *   NONE             no parameters
+ *   RADIAL_GRADIENT  params = line.from.xy, line.to.xy, radii.xy, uv_origin.xy
+ *   TEXT             params = fg rgba, bg rgba, defringing kernel[4] (PF_FILTER_FLAG_TEXT_HAS_KERNEL),
+ *                    gamma correction (PF_FILTER_FLAG_TEXT_GAMMA_CORRECTION)
+ *   BLUR             params[0] = sigma; PF_FILTER_FLAG_BLUR_Y for BlurDirection::Y
+ *   COLOR_MATRIX     params = the five F32x4 columns */
+#define PF_FILTER_NONE 0
+#define PF_FILTER_RADIAL_GRADIENT 1
+#define PF_FILTER_TEXT 2
+#define PF_FILTER_BLUR 3
+#define PF_FILTER_COLOR_MATRIX 4
+#define PF_FILTER_FLAG_TEXT_HAS_KERNEL 0x1
+#define PF_FILTER_FLAG_TEXT_GAMMA_CORRECTION 0x2
+#define PF_FILTER_FLAG_BLUR_Y 0x1
+typedef struct PFFilter {
+    uint32_t kind;
+    uint32_t flags;
+    float params[20];
+} PFFilter;
+
+/* The C-side form of TextureMetadataEntry (gpu_data.rs:336-344). NOT the memory layout of the Rust struct
+ * (its Transform2F is a 16-byte aligned F32x4 + F32x2, its Filter a data-carrying enum, its BlendMode a one-byte
+ * enum): the Rust glue converts every entry (integration/pathfinder_cuda/src/lib.rs
+ * `texture_metadata_entry`). On the hot path today: colour combine mode NONE, filter NONE or TEXT, blend mode
+ * SRC_OVER; anything else is refused with PF_CUDA_ERROR_UNSUPPORTED. */
 typedef struct PFTextureMetadataEntry {
     PFTransform2F color_0_transform;
-    uint32_t color_0_combine_mode;
+    uint32_t color_0_combine_mode;   /* PF_COLOR_COMBINE_MODE_* */
     PFColorU base_color;
-    uint32_t filter;
-    uint32_t blend_mode;
+    uint32_t blend_mode;             /* PF_BLEND_MODE_* */
+    PFFilter filter;
 } PFTextureMetadataEntry;
 
 /* PrepareTilesInfoD3D11 (gpu_data.rs:149-168) with the Vecs flattened. `backdrops` may be NULL
@@ -375,7 +433,6 @@ typedef struct PFRenderTransform *PFRenderTransformRef;
 
 #define PF_FILL_RULE_WINDING 0   /* content/src/fill.rs */
 #define PF_FILL_RULE_EVEN_ODD 1
-#define PF_BLEND_MODE_SRC_OVER 0 /* content/src/effects.rs: only SrcOver is on the hot path */
 #define PF_POINT_FLAGS_CONTROL_POINT_0 0x1 /* content/src/outline.rs PointFlags */
 #define PF_POINT_FLAGS_CONTROL_POINT_1 0x2
 #define PF_CLIP_PATH_NONE 0xffffffffu

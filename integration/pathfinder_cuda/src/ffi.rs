@@ -1,12 +1,20 @@
-//! Raw bindings to include/pf_cuda.h (the renderer half). The `#[repr(C)]` payload records
-//! (`SegmentIndicesD3D11`, `PropagateMetadataD3D11`, `DiceMetadataD3D11`, `TilePathInfoD3D11`,
-//! `BackdropInfoD3D11`, `TextureMetadataEntry`) are the reference's own, so the `Vec`s inside a
-//! `RenderCommand` are passed by pointer without conversion.
+//! Raw bindings to include/pf_cuda.h (the renderer half).
+//!
+//! Passed by pointer without conversion — the reference's own `#[repr(C)]` plain-old-data records, whose
+//! field order, sizes and alignment pf_cuda.h mirrors one to one (checked by the `const _` size assertions
+//! at the end of this file): `Vector2F` (8 bytes), `SegmentIndicesD3D11` (8), `PropagateMetadataD3D11`
+//! (48), `DiceMetadataD3D11` (16), `TilePathInfoD3D11` (16), `BackdropInfoD3D11` (12).
+//!
+//! Converted field by field — everything else. In particular `TextureMetadataEntry` is NOT layout
+//! compatible with `PFTextureMetadataEntry`: its `Transform2F` holds a 16-byte aligned `F32x4` matrix
+//! (lanes m11, m21, m12, m22; geometry/src/transform2d.rs:23,134-137), its `Filter` is a data-carrying
+//! enum (content/src/effects.rs:44-60) and its `BlendMode` a one-byte enum whose `SrcOver` is
+//! discriminant 4, not 0 (effects.rs:99-110). lib.rs `texture_metadata_entry` builds the C record.
 
 use pathfinder_geometry::rect::RectF;
 use pathfinder_geometry::vector::Vector2F;
 use pathfinder_renderer::gpu_data::{BackdropInfoD3D11, DiceMetadataD3D11, PropagateMetadataD3D11};
-use pathfinder_renderer::gpu_data::{SegmentIndicesD3D11, TextureMetadataEntry, TilePathInfoD3D11};
+use pathfinder_renderer::gpu_data::{SegmentIndicesD3D11, TilePathInfoD3D11};
 use std::os::raw::{c_char, c_void};
 
 pub const PF_CUDA_OK: i32 = 0;
@@ -29,7 +37,66 @@ pub const FINISH: u32 = 13;
 
 #[repr(C)]
 pub struct PFRendererMode {
-    pub level: u32, // 1 = D3D9, 2 = D3D11
+    pub level: u8, // 1 = D3D9, 2 = D3D11 (uint8_t in pf_cuda.h)
+}
+
+// PF_BLEND_MODE_*, PF_COLOR_COMBINE_MODE_*, PF_FILTER_* of pf_cuda.h
+pub const BLEND_MODE_CLEAR: u32 = 0;
+pub const BLEND_MODE_COPY: u32 = 1;
+pub const BLEND_MODE_SRC_IN: u32 = 2;
+pub const BLEND_MODE_SRC_OUT: u32 = 3;
+pub const BLEND_MODE_SRC_OVER: u32 = 4;
+pub const BLEND_MODE_SRC_ATOP: u32 = 5;
+pub const BLEND_MODE_DEST_IN: u32 = 6;
+pub const BLEND_MODE_DEST_OUT: u32 = 7;
+pub const BLEND_MODE_DEST_OVER: u32 = 8;
+pub const BLEND_MODE_DEST_ATOP: u32 = 9;
+pub const BLEND_MODE_XOR: u32 = 10;
+pub const BLEND_MODE_LIGHTER: u32 = 11;
+pub const BLEND_MODE_DARKEN: u32 = 12;
+pub const BLEND_MODE_LIGHTEN: u32 = 13;
+pub const BLEND_MODE_MULTIPLY: u32 = 14;
+pub const BLEND_MODE_SCREEN: u32 = 15;
+pub const BLEND_MODE_HARD_LIGHT: u32 = 16;
+pub const BLEND_MODE_OVERLAY: u32 = 17;
+pub const BLEND_MODE_COLOR_DODGE: u32 = 18;
+pub const BLEND_MODE_COLOR_BURN: u32 = 19;
+pub const BLEND_MODE_SOFT_LIGHT: u32 = 20;
+pub const BLEND_MODE_DIFFERENCE: u32 = 21;
+pub const BLEND_MODE_EXCLUSION: u32 = 22;
+pub const BLEND_MODE_HUE: u32 = 23;
+pub const BLEND_MODE_SATURATION: u32 = 24;
+pub const BLEND_MODE_COLOR: u32 = 25;
+pub const BLEND_MODE_LUMINOSITY: u32 = 26;
+pub const COLOR_COMBINE_MODE_NONE: u32 = 0;
+pub const COLOR_COMBINE_MODE_SRC_IN: u32 = 1;
+pub const COLOR_COMBINE_MODE_DEST_IN: u32 = 2;
+pub const FILTER_NONE: u32 = 0;
+pub const FILTER_RADIAL_GRADIENT: u32 = 1;
+pub const FILTER_TEXT: u32 = 2;
+pub const FILTER_BLUR: u32 = 3;
+pub const FILTER_COLOR_MATRIX: u32 = 4;
+pub const FILTER_FLAG_TEXT_HAS_KERNEL: u32 = 0x1;
+pub const FILTER_FLAG_TEXT_GAMMA_CORRECTION: u32 = 0x2;
+pub const FILTER_FLAG_BLUR_Y: u32 = 0x1;
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFFilter {
+    pub kind: u32,
+    pub flags: u32,
+    pub params: [f32; 20],
+}
+
+/// The C-side form of `TextureMetadataEntry` (pf_cuda.h): built field by field, never cast.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFTextureMetadataEntry {
+    pub color_0_transform: [f32; 6], // m00 m01 m10 m11 tx ty
+    pub color_0_combine_mode: u32,
+    pub base_color: [u8; 4],
+    pub blend_mode: u32,
+    pub filter: PFFilter,
 }
 
 #[repr(C)]
@@ -91,7 +158,7 @@ pub struct PFStart {
 #[repr(C)]
 #[derive(Clone, Copy)]
 pub struct PFUploadTextureMetadata {
-    pub entries: *const TextureMetadataEntry,
+    pub entries: *const PFTextureMetadataEntry,
     pub entry_count: usize,
     pub content_key: u64,
 }
@@ -144,3 +211,15 @@ extern "C" {
     pub fn PFCudaRendererReadPixels(renderer: *mut c_void, dst: *mut u8, stride: usize) -> i32;
     pub fn PFCudaRendererSynchronize(renderer: *mut c_void) -> i32;
 }
+
+// Layout checks (compile time): the C records this file declares, and the reference records it passes by
+// pointer, have the sizes pf_cuda.h states. A mismatch fails the build instead of rendering garbage.
+const _: () = assert!(std::mem::size_of::<PFRendererMode>() == 1);
+const _: () = assert!(std::mem::size_of::<PFFilter>() == 88);
+const _: () = assert!(std::mem::size_of::<PFTextureMetadataEntry>() == 124);
+const _: () = assert!(std::mem::size_of::<Vector2F>() == 8);
+const _: () = assert!(std::mem::size_of::<SegmentIndicesD3D11>() == 8);
+const _: () = assert!(std::mem::size_of::<PropagateMetadataD3D11>() == 48);
+const _: () = assert!(std::mem::size_of::<DiceMetadataD3D11>() == 16);
+const _: () = assert!(std::mem::size_of::<TilePathInfoD3D11>() == 16);
+const _: () = assert!(std::mem::size_of::<BackdropInfoD3D11>() == 12);

@@ -9,11 +9,13 @@
 mod ffi;
 
 use pathfinder_color::ColorF;
+use pathfinder_content::effects::{BlendMode, BlurDirection, Filter, PatternFilter};
 use pathfinder_geometry::rect::RectF;
 use pathfinder_geometry::vector::Vector2I;
 use pathfinder_renderer::concurrent::executor::Executor;
 use pathfinder_renderer::gpu::options::{RendererLevel, RendererMode};
-use pathfinder_renderer::gpu_data::{PathSource, RenderCommand, SegmentsD3D11, TileBatchDataD3D11};
+use pathfinder_renderer::gpu_data::{ColorCombineMode, PathSource, RenderCommand, SegmentsD3D11};
+use pathfinder_renderer::gpu_data::{TextureMetadataEntry, TileBatchDataD3D11};
 use pathfinder_renderer::options::{BuildOptions, RenderCommandListener};
 use pathfinder_renderer::scene::{Scene, SceneSink};
 use pathfinder_resources::ResourceLoader;
@@ -73,6 +75,98 @@ fn batch(b: &TileBatchDataD3D11) -> ffi::PFTileBatchDataD3D11 {
     }
 }
 
+// BlendMode -> PF_BLEND_MODE_*: an explicit table, not `as u32` (the header does not promise to follow the
+// order of the Rust enum, content/src/effects.rs:99-163).
+fn blend_mode(mode: BlendMode) -> u32 {
+    match mode {
+        BlendMode::Clear => ffi::BLEND_MODE_CLEAR,
+        BlendMode::Copy => ffi::BLEND_MODE_COPY,
+        BlendMode::SrcIn => ffi::BLEND_MODE_SRC_IN,
+        BlendMode::SrcOut => ffi::BLEND_MODE_SRC_OUT,
+        BlendMode::SrcOver => ffi::BLEND_MODE_SRC_OVER,
+        BlendMode::SrcAtop => ffi::BLEND_MODE_SRC_ATOP,
+        BlendMode::DestIn => ffi::BLEND_MODE_DEST_IN,
+        BlendMode::DestOut => ffi::BLEND_MODE_DEST_OUT,
+        BlendMode::DestOver => ffi::BLEND_MODE_DEST_OVER,
+        BlendMode::DestAtop => ffi::BLEND_MODE_DEST_ATOP,
+        BlendMode::Xor => ffi::BLEND_MODE_XOR,
+        BlendMode::Lighter => ffi::BLEND_MODE_LIGHTER,
+        BlendMode::Darken => ffi::BLEND_MODE_DARKEN,
+        BlendMode::Lighten => ffi::BLEND_MODE_LIGHTEN,
+        BlendMode::Multiply => ffi::BLEND_MODE_MULTIPLY,
+        BlendMode::Screen => ffi::BLEND_MODE_SCREEN,
+        BlendMode::HardLight => ffi::BLEND_MODE_HARD_LIGHT,
+        BlendMode::Overlay => ffi::BLEND_MODE_OVERLAY,
+        BlendMode::ColorDodge => ffi::BLEND_MODE_COLOR_DODGE,
+        BlendMode::ColorBurn => ffi::BLEND_MODE_COLOR_BURN,
+        BlendMode::SoftLight => ffi::BLEND_MODE_SOFT_LIGHT,
+        BlendMode::Difference => ffi::BLEND_MODE_DIFFERENCE,
+        BlendMode::Exclusion => ffi::BLEND_MODE_EXCLUSION,
+        BlendMode::Hue => ffi::BLEND_MODE_HUE,
+        BlendMode::Saturation => ffi::BLEND_MODE_SATURATION,
+        BlendMode::Color => ffi::BLEND_MODE_COLOR,
+        BlendMode::Luminosity => ffi::BLEND_MODE_LUMINOSITY,
+    }
+}
+
+// Filter (content/src/effects.rs:44-97) -> PFFilter: kind, flags and up to 20 floats, in the order pf_cuda.h states.
+fn filter(f: &Filter) -> ffi::PFFilter {
+    let mut out = ffi::PFFilter { kind: ffi::FILTER_NONE, flags: 0, params: [0.0; 20] };
+    match *f {
+        Filter::None => {}
+        Filter::RadialGradient { line, radii, uv_origin } => {
+            out.kind = ffi::FILTER_RADIAL_GRADIENT;
+            out.params[..8].copy_from_slice(&[line.from_x(), line.from_y(), line.to_x(), line.to_y(),
+                                              radii.x(), radii.y(), uv_origin.x(), uv_origin.y()]);
+        }
+        Filter::PatternFilter(PatternFilter::Text { fg_color, bg_color, defringing_kernel, gamma_correction }) => {
+            out.kind = ffi::FILTER_TEXT;
+            out.params[..8].copy_from_slice(&[fg_color.r(), fg_color.g(), fg_color.b(), fg_color.a(),
+                                              bg_color.r(), bg_color.g(), bg_color.b(), bg_color.a()]);
+            if let Some(kernel) = defringing_kernel {
+                out.flags |= ffi::FILTER_FLAG_TEXT_HAS_KERNEL;
+                out.params[8..12].copy_from_slice(&kernel.0);
+            }
+            if gamma_correction {
+                out.flags |= ffi::FILTER_FLAG_TEXT_GAMMA_CORRECTION;
+            }
+        }
+        Filter::PatternFilter(PatternFilter::Blur { direction, sigma }) => {
+            out.kind = ffi::FILTER_BLUR;
+            out.params[0] = sigma;
+            if let BlurDirection::Y = direction {
+                out.flags |= ffi::FILTER_FLAG_BLUR_Y;
+            }
+        }
+        Filter::PatternFilter(PatternFilter::ColorMatrix(ref matrix)) => {
+            out.kind = ffi::FILTER_COLOR_MATRIX;
+            for (column, lanes) in matrix.0.iter().enumerate() {
+                out.params[column * 4..column * 4 + 4]
+                    .copy_from_slice(&[lanes.x(), lanes.y(), lanes.z(), lanes.w()]);
+            }
+        }
+    }
+    out
+}
+
+// TextureMetadataEntry (renderer/src/gpu_data.rs:336-344) -> PFTextureMetadataEntry, field by field. The
+// transform is read through its accessors, as Renderer::upload_texture_metadata does (gpu/renderer.rs:712-722),
+// so the lane order of the F32x4 behind Matrix2x2F never matters here.
+fn texture_metadata_entry(e: &TextureMetadataEntry) -> ffi::PFTextureMetadataEntry {
+    let t = &e.color_0_transform;
+    ffi::PFTextureMetadataEntry {
+        color_0_transform: [t.m11(), t.m12(), t.m21(), t.m22(), t.m13(), t.m23()],
+        color_0_combine_mode: match e.color_0_combine_mode {
+            ColorCombineMode::None => ffi::COLOR_COMBINE_MODE_NONE,
+            ColorCombineMode::SrcIn => ffi::COLOR_COMBINE_MODE_SRC_IN,
+            ColorCombineMode::DestIn => ffi::COLOR_COMBINE_MODE_DEST_IN,
+        },
+        base_color: [e.base_color.r, e.base_color.g, e.base_color.b, e.base_color.a],
+        blend_mode: blend_mode(e.blend_mode),
+        filter: filter(&e.filter),
+    }
+}
+
 fn simple(kind: u32) -> ffi::PFRenderCommand {
     ffi::PFRenderCommand { kind, u: ffi::PFRenderCommandPayload { push_render_target: 0 } }
 }
@@ -110,6 +204,8 @@ impl CudaRenderer {
 
     /// Payloads are borrowed for the call; the renderer copies what it keeps.
     pub fn render_command(&mut self, command: &RenderCommand) {
+        // (kept alive until the call returns: the command borrows it)
+        let converted_metadata: Vec<ffi::PFTextureMetadataEntry>;
         let c = match *command {
             RenderCommand::Start { path_count, needs_readable_framebuffer, .. } => ffi::PFRenderCommand {
                 kind: ffi::START,
@@ -118,14 +214,19 @@ impl CudaRenderer {
                                           needs_readable_framebuffer: needs_readable_framebuffer as u32 },
                 },
             },
-            RenderCommand::UploadTextureMetadata(ref entries) => ffi::PFRenderCommand {
-                kind: ffi::UPLOAD_TEXTURE_METADATA,
-                u: ffi::PFRenderCommandPayload {
-                    upload_texture_metadata: ffi::PFUploadTextureMetadata {
-                        entries: entries.as_ptr(), entry_count: entries.len(), content_key: 0,
+            RenderCommand::UploadTextureMetadata(ref entries) => {
+                converted_metadata = entries.iter().map(texture_metadata_entry).collect();
+                ffi::PFRenderCommand {
+                    kind: ffi::UPLOAD_TEXTURE_METADATA,
+                    u: ffi::PFRenderCommandPayload {
+                        upload_texture_metadata: ffi::PFUploadTextureMetadata {
+                            entries: converted_metadata.as_ptr(),
+                            entry_count: converted_metadata.len(),
+                            content_key: 0,
+                        },
                     },
-                },
-            },
+                }
+            }
             RenderCommand::UploadSceneD3D11 { ref draw_segments, ref clip_segments } => ffi::PFRenderCommand {
                 kind: ffi::UPLOAD_SCENE_D3D11,
                 u: ffi::PFRenderCommandPayload {

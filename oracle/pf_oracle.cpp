@@ -843,6 +843,24 @@ static inline float half_round(float f) {
     return (float)h;
 }
 
+// One fill's contribution to its alpha tile's mask (16 x 16 f32): D3D9 draws one instanced quad per fill
+// with additive blending (d3d9/renderer.rs:237-263); D3D11: accumulateCoverageForFillList
+// (fill_compute.inc.glsl:11-25).
+static void add_fill_to_mask(const PFOFill &f, const uint8_t *lut, float *mask) {
+    // lineSegment = vec4(packed) / 256.0
+    V2 from = v2((float)f.from_x / 256.0f, (float)f.from_y / 256.0f);
+    V2 to = v2((float)f.to_x / 256.0f, (float)f.to_y / 256.0f);
+    for (int strip = 0; strip < 4; strip++) {
+        for (int x = 0; x < 16; x++) {
+            // tileFragCoord = vec2(tileSubCoord) + 0.5 with tileSubCoord = (x, 4*strip)
+            V2 c = v2((float)x + 0.5f, (float)(4 * strip) + 0.5f);
+            float cov[4];
+            compute_coverage(from - c, to - c, lut, cov);
+            for (int k = 0; k < 4; k++) mask[(4 * strip + k) * 16 + x] += cov[k];
+        }
+    }
+}
+
 } // namespace
 
 extern "C" {
@@ -850,36 +868,47 @@ extern "C" {
 void pfo_alpha_masks(const PFOBuilt *b, const uint8_t *lut, float *out) {
     size_t n = (size_t)b->alpha_tile_count * 256;
     for (size_t i = 0; i < n; i++) out[i] = 0.0f;
-    // D3D9: one instanced quad per fill, additive blend into the tile's mask
-    // (d3d9/renderer.rs:237-263); D3D11: accumulateCoverageForFillList (fill_compute.inc.glsl:11-25).
     // Fills are accumulated in emission order.
-    for (const PFOFill &f : b->fills) {
-        float *mask = out + (size_t)f.link * 256;
-        // lineSegment = vec4(packed) / 256.0
-        V2 from = v2((float)f.from_x / 256.0f, (float)f.from_y / 256.0f);
-        V2 to = v2((float)f.to_x / 256.0f, (float)f.to_y / 256.0f);
-        for (int strip = 0; strip < 4; strip++) {
-            for (int x = 0; x < 16; x++) {
-                // tileFragCoord = vec2(tileSubCoord) + 0.5 with tileSubCoord = (x, 4*strip)
-                V2 c = v2((float)x + 0.5f, (float)(4 * strip) + 0.5f);
-                float cov[4];
-                compute_coverage(from - c, to - c, lut, cov);
-                for (int k = 0; k < 4; k++) mask[(4 * strip + k) * 16 + x] += cov[k];
-            }
-        }
-    }
+    for (const PFOFill &f : b->fills) add_fill_to_mask(f, lut, out + (size_t)f.link * 256);
 }
 
-void pfo_render(const PFOBuilt *b, const PFOScene *scene, const uint8_t *lut, const float background[4],
-                uint32_t width, uint32_t height, uint8_t *out_rgba, float *out_f32) {
-    std::vector<float> masks((size_t)b->alpha_tile_count * 256);
-    pfo_alpha_masks(b, lut, masks.data());
+// Composites the pixels [x0, x0 + width) x [y0, y0 + height) of the frame (frame_w x frame_h pixels). Only the
+// masks of alpha tiles that reach the crop are evaluated, so a crop of a frame too large to hold every mask
+// (1M paths at 16384^2) costs what its own tiles cost.
+void pfo_render_crop(const PFOBuilt *b, const PFOScene *scene, const uint8_t *lut, const float background[4],
+                     uint32_t frame_w, uint32_t frame_h, uint32_t x0, uint32_t y0, uint32_t width, uint32_t height,
+                     uint8_t *out_rgba, float *out_f32) {
+    const RectI zr = b->z_rect;
+    const int64_t cx0 = x0, cy0 = y0, cx1 = std::min<int64_t>((int64_t)x0 + width, frame_w),
+                  cy1 = std::min<int64_t>((int64_t)y0 + height, frame_h);
+    auto tile_drawn = [&](const PFOTileObjectPrimitive &tile) {
+        if (!zr.contains_point(tile.tile_x, tile.tile_y)) return false;
+        const int64_t tx = (int64_t)tile.tile_x * 16, ty = (int64_t)tile.tile_y * 16;
+        if (tx + 16 <= cx0 || tx >= cx1 || ty + 16 <= cy0 || ty >= cy1) return false;
+        // culled when path_id < z (d3d9/tile.vs.glsl:52-56 / sort.cs.glsl:74)
+        int32_t z = b->z_buffer[(size_t)(tile.tile_y - zr.min_y) * zr.width() + (tile.tile_x - zr.min_x)];
+        return (int32_t)tile.path_id >= z;
+    };
+    // Which alpha tiles are needed: those of drawn tiles, and for every Clip record whose destination is
+    // needed, its source.
+    const uint32_t NONE = 0xffffffffu;
+    std::vector<uint32_t> slot(b->alpha_tile_count, NONE);
+    uint32_t n_slots = 0;
+    for (const PFOTileObjectPrimitive &tile : b->tiles)
+        if (tile.alpha_tile_id != INVALID_ALPHA && tile_drawn(tile) && slot[tile.alpha_tile_id] == NONE)
+            slot[tile.alpha_tile_id] = n_slots++;
+    for (const PFOClip &cl : b->clips)
+        if (slot[cl.dest_tile_id] != NONE && slot[cl.src_tile_id] == NONE) slot[cl.src_tile_id] = n_slots++;
+    std::vector<float> masks((size_t)n_slots * 256, 0.0f);
+    for (const PFOFill &f : b->fills) // emission order
+        if (slot[f.link] != NONE) add_fill_to_mask(f, lut, masks.data() + (size_t)slot[f.link] * 256);
     // D3D9 clip combine (shaders/d3d9/tile_clip_combine.fs.glsl:28-31):
     // dest = min(abs(dest + dest_backdrop), abs(src + src_backdrop)); the draw tile's backdrop was
     // zeroed by prepare_tiles.
     for (const PFOClip &cl : b->clips) {
-        float *dst = masks.data() + (size_t)cl.dest_tile_id * 256;
-        const float *src = masks.data() + (size_t)cl.src_tile_id * 256;
+        if (slot[cl.dest_tile_id] == NONE) continue;
+        float *dst = masks.data() + (size_t)slot[cl.dest_tile_id] * 256;
+        const float *src = masks.data() + (size_t)slot[cl.src_tile_id] * 256;
         for (int i = 0; i < 256; i++)
             dst[i] = fminf(fabsf(dst[i] + (float)cl.dest_backdrop), fabsf(src[i] + (float)cl.src_backdrop));
     }
@@ -892,21 +921,17 @@ void pfo_render(const PFOBuilt *b, const PFOScene *scene, const uint8_t *lut, co
     std::vector<float> paint((size_t)scene->n_paints * 4);
     for (size_t i = 0; i < paint.size(); i++) paint[i] = half_round((float)scene->paint_colors[i] * (1.0f / 255.0f));
 
-    const RectI zr = b->z_rect;
-    // Tiles are in ascending draw order = painter's order (sort.cs.glsl:60-95); culled when
-    // path_id < z (d3d9/tile.vs.glsl:52-56 / sort.cs.glsl:74).
+    // Tiles are in ascending draw order = painter's order (sort.cs.glsl:60-95).
     for (const PFOTileObjectPrimitive &tile : b->tiles) {
-        if (!zr.contains_point(tile.tile_x, tile.tile_y)) continue;
-        int32_t z = b->z_buffer[(size_t)(tile.tile_y - zr.min_y) * zr.width() + (tile.tile_x - zr.min_x)];
-        if ((int32_t)tile.path_id < z) continue;
+        if (!tile_drawn(tile)) continue;
         const float *base = &paint[4 * (size_t)tile.color];
-        const float *mask = tile.alpha_tile_id != INVALID_ALPHA ? masks.data() + (size_t)tile.alpha_tile_id * 256 : nullptr;
+        const float *mask = tile.alpha_tile_id != INVALID_ALPHA ? masks.data() + (size_t)slot[tile.alpha_tile_id] * 256 : nullptr;
         for (int py = 0; py < 16; py++) {
             int64_t y = (int64_t)tile.tile_y * 16 + py;
-            if (y < 0 || y >= (int64_t)height) continue;
+            if (y < cy0 || y >= cy1) continue;
             for (int px = 0; px < 16; px++) {
                 int64_t x = (int64_t)tile.tile_x * 16 + px;
-                if (x < 0 || x >= (int64_t)width) continue;
+                if (x < cx0 || x >= cx1) continue;
                 // sampleMask (tile_fragment.inc.glsl:539-556): coverage = texel + backdrop, then rule.
                 float coverage = (mask ? mask[py * 16 + px] : 0.0f) + (float)tile.backdrop;
                 float mask_alpha;
@@ -922,7 +947,7 @@ void pfo_render(const PFOBuilt *b, const PFOScene *scene, const uint8_t *lut, co
                 // calculateColor (tile_fragment.inc.glsl:560-614), solid colour, SrcOver.
                 float a = base[3] * mask_alpha;
                 float src[4] = {base[0] * a, base[1] * a, base[2] * a, a};
-                float *d = &dest[4 * ((size_t)y * width + (size_t)x)];
+                float *d = &dest[4 * ((size_t)(y - cy0) * width + (size_t)(x - cx0))];
                 for (int k = 0; k < 4; k++) d[k] = d[k] * (1.0f - a) + src[k]; // tile.cs.glsl:155
             }
         }
@@ -933,6 +958,11 @@ void pfo_render(const PFOBuilt *b, const PFOScene *scene, const uint8_t *lut, co
         float v = fminf(fmaxf(dest[i], 0.0f), 1.0f) * 255.0f;
         out_rgba[i] = (uint8_t)lrintf(v);
     }
+}
+
+void pfo_render(const PFOBuilt *b, const PFOScene *scene, const uint8_t *lut, const float background[4],
+                uint32_t width, uint32_t height, uint8_t *out_rgba, float *out_f32) {
+    pfo_render_crop(b, scene, lut, background, width, height, 0, 0, width, height, out_rgba, out_f32);
 }
 
 } // extern "C"

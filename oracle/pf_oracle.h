@@ -141,6 +141,13 @@ void pfo_render(const PFOBuilt *b, const PFOScene *scene, const uint8_t *area_lu
                 const float background[4], uint32_t width, uint32_t height, uint8_t *out_rgba,
                 float *out_f32);
 
+/* The same for the pixels [x0, x0 + width) x [y0, y0 + height) of a frame_w x frame_h frame (out_rgba /
+ * out_f32 hold width x height pixels). Only the masks of alpha tiles that reach the crop are evaluated, so
+ * crops of frames too large to composite whole on the CPU stay cheap. */
+void pfo_render_crop(const PFOBuilt *b, const PFOScene *scene, const uint8_t *area_lut_rgba,
+                     const float background[4], uint32_t frame_w, uint32_t frame_h, uint32_t x0, uint32_t y0,
+                     uint32_t width, uint32_t height, uint8_t *out_rgba, float *out_f32);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,8 @@ def lib():
         l.pfo_alpha_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         l.pfo_render.argtypes = [C.c_void_p, C.POINTER(_Scene), C.c_void_p, C.POINTER(C.c_float * 4),
                                  C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        l.pfo_render_crop.argtypes = [C.c_void_p, C.POINTER(_Scene), C.c_void_p, C.POINTER(C.c_float * 4)] + \
+                                     [C.c_uint32] * 6 + [C.c_void_p, C.c_void_p]
         _lib = l
     return _lib
 
@@ -219,6 +221,17 @@ class Built:
         lib().pfo_render(self._h, C.byref(self.scene.c), lut.ctypes.data, C.byref(bg), width, height,
                          out.ctypes.data, outf.ctypes.data if want_f32 else None)
         return (out, outf) if want_f32 else out
+
+    def render_crop(self, area_lut: np.ndarray, frame_size, origin, size, background=(0, 0, 0, 0)):
+        """RGBA8 of the pixels [x0, x0 + w) x [y0, y0 + h) of a frame of frame_size = (W, H) pixels; only the
+        alpha masks that reach the crop are evaluated."""
+        lut = _arr(area_lut, np.uint8).reshape(256, 256, 4)
+        (x0, y0), (w, h) = origin, size
+        out = np.zeros((h, w, 4), dtype=np.uint8)
+        bg = (C.c_float * 4)(*[float(v) for v in background])
+        lib().pfo_render_crop(self._h, C.byref(self.scene.c), lut.ctypes.data, C.byref(bg), int(frame_size[0]),
+                              int(frame_size[1]), int(x0), int(y0), int(w), int(h), out.ctypes.data, None)
+        return out
 
     def close(self):
         if self._h:

@@ -75,9 +75,13 @@ class PFBackdropInfoD3D11(C.Structure):
                 ("path_index", C.c_uint32)]
 
 
+class PFFilter(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("flags", C.c_uint32), ("params", C.c_float * 20)]
+
+
 class PFTextureMetadataEntry(C.Structure):
     _fields_ = [("color_0_transform", PFTransform2F), ("color_0_combine_mode", C.c_uint32),
-                ("base_color", PFColorU), ("filter", C.c_uint32), ("blend_mode", C.c_uint32)]
+                ("base_color", PFColorU), ("blend_mode", C.c_uint32), ("filter", PFFilter)]
 
 
 class PFPrepareTilesInfoD3D11(C.Structure):

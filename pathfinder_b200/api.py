@@ -19,6 +19,7 @@ from .flat_scene import FlatScene
 FILL_DTYPE = np.dtype([("from_x", "<u2"), ("from_y", "<u2"), ("to_x", "<u2"), ("to_y", "<u2"), ("link", "<u4")])
 TILE_DTYPE = np.dtype([("tile_x", "<i2"), ("tile_y", "<i2"), ("alpha_tile_id", "<u4"), ("path_id", "<u4"),
                        ("color", "<u2"), ("ctrl", "u1"), ("backdrop", "i1")])
+BLEND_MODE_SRC_OVER = 4  # PF_BLEND_MODE_SRC_OVER (BlendMode::SrcOver, content/src/effects.rs:99-163)
 CLIP_DTYPE = np.dtype([("dest_tile_id", "<u4"), ("dest_backdrop", "<i4"), ("src_tile_id", "<u4"), ("src_backdrop", "<i4")])
 
 
@@ -116,7 +117,7 @@ class Scene:
         c = L.PFColorU(int(rgba[0]), int(rgba[1]), int(rgba[2]), int(rgba[3]))
         return int(L.lib().PFScenePushPaint(self._h, C.byref(c)))
 
-    def push_draw_path(self, points, point_flags, contour_offsets, paint_id, fill_rule=0, blend_mode=0,
+    def push_draw_path(self, points, point_flags, contour_offsets, paint_id, fill_rule=0, blend_mode=BLEND_MODE_SRC_OVER,
                        clip_path_id=0xFFFFFFFF) -> int:
         pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
         fl = np.ascontiguousarray(point_flags, dtype=np.uint8)

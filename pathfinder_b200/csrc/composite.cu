@@ -1,0 +1,637 @@
+// pathfinder_b200/csrc/composite.cu — fill + tile (fused): exact-area coverage from the LUT, fill rule,
+// paint, SrcOver blend, RGBA8 store. The alpha mask never exists in HBM.
+//
+// Reference math restated here (paths relative to the reference checkout):
+//   fill   shaders/fill_area.inc.glsl:11-27 (computeCoverage), shaders/d3d11/fill_compute.inc.glsl:11-25
+//   tile   shaders/d3d11/tile.cs.glsl:91-159 (painter's-order loop, dest * (1 - a) + src),
+//          shaders/tile_fragment.inc.glsl:539-614 (sampleMask, calculateColor),
+//          shaders/d3d9/tile_clip_combine.fs.glsl:28-31 (clip mask combine)
+//
+// Two kernels instead of one warp per framebuffer tile for everything (round 1):
+//   k_tile_solid   one LANE per framebuffer tile. A tile whose list holds only solid entries (no fills,
+//                  no clip mask) has a single colour: the lane blends the few entries in draw order and the
+//                  warp then writes its 32 tiles row by row with 512-byte coalesced 128-bit stores. Tiles
+//                  that need per-pixel work are appended to a queue.
+//   k_tile_alpha   persistent warps pull queued tiles. Between two tiles with fills, solid entries are
+//                  folded into one affine map (d -> d * s + o), so only entries with fills touch the 256
+//                  pixels. Per fill, everything that does not depend on the pixel column is computed once
+//                  by the lane that loaded the fill and broadcast through shared memory; the pixel state
+//                  lives in shared memory while the fills are evaluated, so the loop runs at low register
+//                  count. Finished tiles are transposed through shared memory and leave as 128-bit stores.
+// This file is compiled with FMA contraction on (nothing here is compared bit-exactly with the CPU tiler;
+// the bar is 1/255 per channel), unlike kernels.cu.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace pf {
+
+namespace {
+
+#ifndef PF_TILE_WARPS
+#define PF_TILE_WARPS 4 // warps per block of k_tile_alpha
+#endif
+#ifndef PF_TILE_MIN_BLOCKS
+#define PF_TILE_MIN_BLOCKS 6 // resident blocks per SM the register allocation must allow
+#endif
+#ifndef PF_PREFETCH
+#define PF_PREFETCH 1
+#endif
+
+constexpr int TILE_WARPS = PF_TILE_WARPS;
+constexpr int ENTRY_CAP = 32;  // entries rank-sorted in shared memory; deeper lists are walked by selection
+constexpr int SOLID_MAX = 8;   // deepest all-solid list k_tile_solid blends itself
+constexpr uint32_t WORK_PARKED = 0xf0000000u; // k_list_emit parks the tile counter here when a stage overflowed
+
+// Coverage contributions are accumulated as integers so the sum does not depend on the order of a tile's
+// fills (the tile-grouped fill array is filled through an atomic cursor): adding 1.5 * 2^8 pins the
+// float's exponent so its mantissa is the contribution in units of 2^-15.
+constexpr float COV_MAGIC = 384.0f;
+constexpr uint32_t COV_MAGIC_BITS = 0x43c00000u;
+constexpr float COV_SCALE = 1.0f / 32768.0f;
+
+// sampleMask (shaders/tile_fragment.inc.glsl:539-556) on coverage = mask + backdrop.
+__device__ __forceinline__ float mask_alpha(float coverage, uint32_t ctrl) {
+    if (ctrl & 1u) { // TILE_CTRL_MASK_WINDING
+        coverage = fabsf(coverage);
+    } else if (ctrl & 2u) { // TILE_CTRL_MASK_EVEN_ODD
+        float m = coverage - 2.0f * floorf(coverage * 0.5f);
+        coverage = 1.0f - fabsf(1.0f - m);
+    } else {
+        coverage = 1.0f;
+    }
+    return fminf(1.0f, coverage);
+}
+
+// Packed f32x2 arithmetic (sm_100: FFMA2 / FMUL2 issue two fp32 operations per lane per instruction).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// A pixel as two packed pairs (r, g), (b, a).
+struct Px {
+    f32x2 rg, ba;
+};
+__device__ __forceinline__ Px px_from(float4 c) { return Px{pack2(c.x, c.y), pack2(c.z, c.w)}; }
+__device__ __forceinline__ float4 px_to(Px p) {
+    float4 c;
+    unpack2(p.rg, c.x, c.y);
+    unpack2(p.ba, c.z, c.w);
+    return c;
+}
+
+// dest = dest * (1 - a) + src (shaders/d3d11/tile.cs.glsl:155) with src = (rgb * a, a), a = paint alpha * mask:
+// with the paint premultiplied, P = (rgb * w, w), this is d + m * (P - w * d) — two packed FMAs per pair.
+__device__ __forceinline__ void over(Px &d, Px paint, f32x2 neg_w, float m) {
+    const f32x2 mm = pack2(m, m);
+    d.rg = fma2(mm, fma2(neg_w, d.rg, paint.rg), d.rg);
+    d.ba = fma2(mm, fma2(neg_w, d.ba, paint.ba), d.ba);
+}
+
+// clamp-free x * 255 rounded to nearest even in the low mantissa bits of x * 255 + 2^23 (no F2I on the slow
+// pipe); colours are convex combinations of values in [0, 1], so only rounding noise can leave the range
+// and it vanishes in the rounding. The four bytes are packed with PRMT.
+__device__ __forceinline__ uint32_t pack_rgba8(Px p) {
+    const f32x2 scale = pack2(255.0f, 255.0f), magic = pack2(8388608.0f, 8388608.0f);
+    float r, g, b, a;
+    unpack2(fma2(p.rg, scale, magic), r, g);
+    unpack2(fma2(p.ba, scale, magic), b, a);
+    const uint32_t rg = __byte_perm(__float_as_uint(r), __float_as_uint(g), 0x0040); // bytes: r0, g0, 0, 0
+    const uint32_t ba = __byte_perm(__float_as_uint(b), __float_as_uint(a), 0x0040);
+    return __byte_perm(rg, ba, 0x5410);
+}
+
+__device__ __forceinline__ float4 unpack_rgba8(uint32_t v) {
+    const float s = 1.0f / 255.0f;
+    return make_float4((float)(v & 0xff) * s, (float)((v >> 8) & 0xff) * s, (float)((v >> 16) & 0xff) * s,
+                       (float)(v >> 24) * s);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---------------------------------------------------------------------------------------------
+// k_tile_solid — single-colour tiles, one lane per framebuffer tile; queues the others.
+// ---------------------------------------------------------------------------------------------
+
+template <bool LOAD_DEST>
+__global__ void __launch_bounds__(128) k_tile_solid(CompositeArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int fb_w = a.fb.max_x - a.fb.min_x;
+    const uint32_t segs = ((uint32_t)fb_w + 31u) >> 5; // 32-tile row segments per tile row
+    const uint32_t rows = (uint32_t)(a.tile_y1 - a.tile_y0);
+    if (warp_global >= segs * rows) return;
+    if (*a.work_counter >= WORK_PARKED) return; // a stage overflowed: the batch is re-run, leave the image alone
+    const uint32_t tile_row = warp_global / segs, seg = warp_global - tile_row * segs;
+    const int col = (int)(seg * 32u) + lane;
+    const int ty = a.tile_y0 + (int)tile_row;
+    const bool in_row = col < fb_w;
+    uint32_t n = 0, e0 = 0;
+    bool has_alpha = false;
+    if (in_row && ty >= a.fb.min_y && ty < a.fb.max_y) {
+        const size_t index = (size_t)(ty - a.fb.min_y) * (size_t)fb_w + (size_t)col;
+        n = __ldg(a.fb_count + index);
+        if (n) {
+            e0 = __ldg(a.fb_start + index);
+            has_alpha = __ldg(a.fb_alpha + index) != 0u;
+        }
+    }
+    // Tiles that need per-pixel work go to the queue of k_tile_alpha (one counter increment per warp).
+    const bool queued = in_row && (has_alpha || n > (uint32_t)SOLID_MAX || (LOAD_DEST && n > 0));
+    const uint32_t queued_mask = __ballot_sync(0xffffffffu, queued);
+    if (queued_mask) {
+        uint32_t base = 0;
+        const int leader = __ffs(queued_mask) - 1;
+        if (lane == leader) base = atomicAdd(a.queue_count, (uint32_t)__popc(queued_mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (queued) a.queue[base + (uint32_t)__popc(queued_mask & ((1u << lane) - 1u))] = (tile_row << 16) | (uint32_t)col;
+    }
+    // LOAD_ACTION_LOAD: a tile without entries keeps what the previous batches drew.
+    const bool paints = in_row && !queued && !(LOAD_DEST && n == 0);
+    const uint32_t paint_mask = __ballot_sync(0xffffffffu, paints);
+    if (paint_mask == 0) return;
+
+    // The tile's colour: its (few, solid) entries blended in draw order = ascending tile index, selected by
+    // repeated minimum (the run is in arbitrary order).
+    Px c = px_from(a.clear_color);
+    if (paints) {
+        uint32_t last = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            uint32_t best = 0xffffffffu, best_j = 0;
+            for (uint32_t j = 0; j < n; j++) {
+                const uint32_t key = __ldg(&a.entries[e0 + j].tile_index);
+                if ((i == 0 || key > last) && key < best) best = key, best_j = j;
+            }
+            last = best;
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + best_j));
+            const float4 paint = __ldg(&a.entries[e0 + best_j].color);
+            // Solid tile: coverage = backdrop for every pixel (tile_fragment.inc.glsl:548).
+            const float m = mask_alpha((float)(int)(int8_t)(raw.y >> 24), (raw.z >> 16) & 0xffu);
+            over(c, px_from(paint), pack2(-paint.w, -paint.w), m);
+        }
+    }
+    const uint32_t packed = pack_rgba8(c);
+
+    // Store: image row r of the segment's 32 tiles is 2 KB of consecutive bytes; lane l writes the 16-byte
+    // chunks l, l + 32, l + 64, l + 96 of it, chunk c belonging to tile c / 4.
+    uint32_t chunk_color[4];
+    bool chunk_on[4], chunk_full[4];
+    int chunk_px[4];
+    const int seg_tx = a.fb.min_x + (int)(seg * 32u);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int j = q * 8 + (lane >> 2);
+        chunk_color[q] = __shfl_sync(0xffffffffu, packed, j);
+        chunk_px[q] = (seg_tx + j) * 16 + (lane & 3) * 4;
+        chunk_on[q] = ((paint_mask >> j) & 1u) && chunk_px[q] + 4 > 0 && chunk_px[q] < a.dest_w;
+        chunk_full[q] = chunk_px[q] >= 0 && chunk_px[q] + 4 <= a.dest_w && (a.dest_align_mask & 15u) == 0;
+    }
+    const int y_lo = max(0, ty * 16), y_hi = min(a.dest_h, ty * 16 + 16);
+    for (int d = 0; d < a.n_dest; d++) {
+        uint8_t *row = a.dests[d] + (ptrdiff_t)y_lo * (ptrdiff_t)a.dest_pitch;
+        for (int y = y_lo; y < y_hi; y++, row += a.dest_pitch) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (!chunk_on[q]) continue;
+                if (chunk_full[q]) {
+                    *reinterpret_cast<uint4 *>(row + (ptrdiff_t)chunk_px[q] * 4) =
+                        make_uint4(chunk_color[q], chunk_color[q], chunk_color[q], chunk_color[q]);
+                } else {
+                    for (int k = 0; k < 4; k++) {
+                        const int px = chunk_px[q] + k;
+                        if (px >= 0 && px < a.dest_w) *reinterpret_cast<uint32_t *>(row + (ptrdiff_t)px * 4) = chunk_color[q];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_tile_alpha — tiles with fills (or clip masks, or deep lists), one warp per tile.
+// ---------------------------------------------------------------------------------------------
+
+// Column-independent part of computeCoverage for one fill, computed once by the lane that loaded it.
+struct __align__(16) FillParams {
+    float lx, rx;   // x of the left / right end point, tile space [0, 16]
+    float ly05;     // y of the left end point minus 0.5 (the centre of pixel row 0)
+    float dy;       // right.y - left.y
+    float inv;      // 1 / (right.x - left.x)
+    float slope16;  // |dy / dx| / 16: the LUT's second coordinate per unit of window width
+    float sign;     // sign of dX = window(from).x - window(to).x: -1 when `from` is the left end
+    float pad;
+};
+
+__device__ __forceinline__ FillParams fill_params(uint2 fill) {
+    const float s = 1.0f / 256.0f;
+    const float fx = (float)(fill.x & 0xffffu) * s, fy = (float)(fill.x >> 16) * s;
+    const float tx = (float)(fill.y & 0xffffu) * s, ty = (float)(fill.y >> 16) * s;
+    const bool from_left = fx < tx;
+    FillParams p;
+    p.lx = from_left ? fx : tx;
+    p.rx = from_left ? tx : fx;
+    const float ly = from_left ? fy : ty, ry = from_left ? ty : fy;
+    p.ly05 = ly - 0.5f;
+    p.dy = ry - ly;
+    p.inv = __fdividef(1.0f, p.rx - p.lx); // from_x != to_x (degenerate fills are culled by add_fill)
+    p.slope16 = fabsf(p.dy * p.inv) * (1.0f / 16.0f);
+    p.sign = from_left ? -1.0f : 1.0f;
+    p.pad = 0.0f;
+    return p;
+}
+
+// computeCoverage (shaders/fill_area.inc.glsl:11-27) of one fill for pixel column `xf` (its left edge) and
+// the two vertically adjacent 4-row strips this lane owns (u_off: LUT coordinate offset of the first).
+// Branch-free: a column outside the fill's x range has dX = 0 and adds exactly COV_MAGIC, like the
+// reference's `texture(...) * dX`, so every fill counts as one contribution on every lane.
+__device__ __forceinline__ void accumulate_fill(const float4 p0, const float4 p1, float xf, float u_off,
+                                                cudaTextureObject_t lut, uint32_t (&acc)[8]) {
+    // p0 = {lx, rx, ly05, dy}, p1 = {inv, slope16, sign, -}
+    const float l0 = p0.x - xf;                             // left.x relative to the column's left edge
+    const float wl = __saturatef(l0), wr = __saturatef(p0.y - xf); // window = clamp(x, -0.5, 0.5) + 0.5
+    const float width = wr - wl;
+    const float dX = p1.z * width;
+    const float t = fmaf(wl + wr, 0.5f, -l0) * p1.x;        // (mid(window) - left.x) / (right.x - left.x)
+    const float y = fmaf(p0.w, t, p0.z);                    // mix(left.y, right.y, t), relative to row 0's centre
+    const float v = p1.y * width;                           // abs(d * dX) / 16
+    const float u = fmaf(y, 1.0f / 16.0f, u_off);           // (y + 8) / 16 for the first strip
+    const float4 a0 = tex2D<float4>(lut, u, v);
+    const float4 a1 = tex2D<float4>(lut, u - 0.25f, v);     // the strip 4 rows lower sees the segment 4 px higher
+    acc[0] += __float_as_uint(fmaf(a0.x, dX, COV_MAGIC));
+    acc[1] += __float_as_uint(fmaf(a0.y, dX, COV_MAGIC));
+    acc[2] += __float_as_uint(fmaf(a0.z, dX, COV_MAGIC));
+    acc[3] += __float_as_uint(fmaf(a0.w, dX, COV_MAGIC));
+    acc[4] += __float_as_uint(fmaf(a1.x, dX, COV_MAGIC));
+    acc[5] += __float_as_uint(fmaf(a1.y, dX, COV_MAGIC));
+    acc[6] += __float_as_uint(fmaf(a1.z, dX, COV_MAGIC));
+    acc[7] += __float_as_uint(fmaf(a1.w, dX, COV_MAGIC));
+}
+
+template <bool HAS_CLIP>
+struct __align__(16) TileWarpShared {
+    float4 dst[8 * 32];         // the tile's pixels between two entries with fills: [row k of the lane][lane]
+    uint4 entry[ENTRY_CAP];     // the run in draw order: {fill_end, count | backdrop, paint | ctrl | flags, tile index}
+    float4 paint[ENTRY_CAP];    // premultiplied paint colour
+    union {
+        float4 fill[32][2];     // FillParams of up to 32 fills
+        uint32_t stage[16 * 16 + 16]; // finished RGBA8 tile, row-major (+16 words for rows 8..15: conflict-free)
+    };
+    uint2 clip[HAS_CLIP ? ENTRY_CAP : 1]; // {clip fill end, clip tile word}
+};
+
+// Sums the coverage contributions of fills [begin, end) into acc (integer units, order-independent).
+template <bool HAS_CLIP>
+__device__ __forceinline__ void fill_loop(TileWarpShared<HAS_CLIP> &sh, const PackedFill *__restrict__ fills,
+                                          uint32_t begin, uint32_t end, float xf, float u_off,
+                                          cudaTextureObject_t lut, int lane, uint32_t (&acc)[8]) {
+    for (uint32_t f0 = begin; f0 < end; f0 += 32) {
+        const uint32_t m = min(32u, end - f0);
+        if ((uint32_t)lane < m) {
+            const FillParams p = fill_params(__ldg(fills + f0 + lane));
+            sh.fill[lane][0] = make_float4(p.lx, p.rx, p.ly05, p.dy);
+            sh.fill[lane][1] = make_float4(p.inv, p.slope16, p.sign, 0.0f);
+        }
+        __syncwarp();
+#pragma unroll 2
+        for (uint32_t j = 0; j < m; j++) accumulate_fill(sh.fill[j][0], sh.fill[j][1], xf, u_off, lut, acc);
+        __syncwarp(); // the next batch (or the store staging) overwrites the parameters
+    }
+}
+
+// acc -> coverage for `count` contributions. Up to 127 contributions of magnitude <= 2^15 units: |sum| <
+// 2^22, so the signed sum can be read off the mantissa of 1.5 * 2^23 + sum (no I2F on the quarter-rate
+// pipe) and scaled, un-biased (12582912 * 2^-15 = 384) and offset by the backdrop in one FFMA.
+__device__ __forceinline__ void coverage_of(const uint32_t (&acc)[8], uint32_t count, float backdrop, float (&cov)[8]) {
+    if (count <= 127u) {
+        const uint32_t bias = 0x4b400000u - count * COV_MAGIC_BITS;
+        const float offset = backdrop - 384.0f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) cov[k] = fmaf(__uint_as_float(acc[k] + bias), COV_SCALE, offset);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) cov[k] = (float)(int32_t)(acc[k] - count * COV_MAGIC_BITS) * COV_SCALE + backdrop;
+    }
+}
+
+// coverage -> mask alpha by the tile's fill rule (sampleMask), eight pixels.
+__device__ __forceinline__ void rule_of(float (&cov)[8], uint32_t ctrl) {
+    if (ctrl & 1u) { // TILE_CTRL_MASK_WINDING
+#pragma unroll
+        for (int k = 0; k < 8; k++) cov[k] = fminf(fabsf(cov[k]), 1.0f);
+    } else if (ctrl & 2u) { // TILE_CTRL_MASK_EVEN_ODD
+        // 1 - |1 - (c mod 2)| is the distance from c to the nearest even integer: 2 * |c/2 - rint(c/2)|.
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            // (rint from the 1.5 * 2^23 trick: |c/2| < 2^22 here; no FRND on the slow pipe)
+            const float t = cov[k] * 0.5f;
+            const float nearest = __fadd_rn(__fadd_rn(t, 12582912.0f), -12582912.0f);
+            cov[k] = 2.0f * fabsf(t - nearest);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) cov[k] = 1.0f;
+    }
+}
+
+template <bool LOAD_DEST, bool HAS_CLIP>
+__global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_alpha(CompositeArgs a) {
+    __shared__ TileWarpShared<HAS_CLIP> sh_all[TILE_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TileWarpShared<HAS_CLIP> &sh = sh_all[warp];
+    const int fb_w = a.fb.max_x - a.fb.min_x;
+    const uint32_t n_queue = *a.queue_count; // written by k_tile_solid
+    const int64_t fb_base = (int64_t)(a.tile_y0 - a.fb.min_y) * fb_w;
+    const int x = lane & 15, half = lane >> 4;
+    const float xf = (float)x;
+    const float u_off = 0.5f - 0.5f * (float)half; // (8 - 8 * half) / 16
+
+    // Persistent warps: tiles differ wildly in depth, so every warp pulls its next tile from a global
+    // counter. The pull is software-pipelined two deep: while tile i is composited, the counter increment
+    // for tile i + 2 and the queue slot + list header of tile i + 1 are in flight.
+    auto claim = [&]() -> uint32_t {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(a.work_counter, 1u);
+        return c; // lane 0 only; broadcast when it is needed, not before
+    };
+    auto fetch = [&](uint32_t k, uint32_t &work, uint32_t &count, uint32_t &start) {
+        work = count = start = 0;
+        if (k < n_queue) {
+            work = __ldg(a.queue + k);
+            const int64_t index = (int64_t)(work >> 16) * fb_w + (int64_t)(work & 0xffffu) + fb_base;
+            count = __ldg(a.fb_count + index);
+            start = __ldg(a.fb_start + index);
+        }
+    };
+    uint32_t pending = claim();
+    uint32_t k_cur = __shfl_sync(0xffffffffu, pending, 0);
+    pending = claim();
+    uint32_t work, n, e0;
+    fetch(k_cur, work, n, e0);
+    for (;;) {
+        if (k_cur >= n_queue) return;
+        const uint32_t k_next = __shfl_sync(0xffffffffu, pending, 0);
+        pending = claim();
+        uint32_t work_next, n_next, e0_next;
+        fetch(k_next, work_next, n_next, e0_next);
+
+        const int ty = a.tile_y0 + (int)(work >> 16), tx = a.fb.min_x + (int)(work & 0xffffu);
+        const int px = tx * 16 + x, py0 = ty * 16 + half * 8;
+
+        // ---- bring the run into draw order: rank sort by tile index (tiles are allocated path by path, so
+        // ascending tile index is draw order; replaces the insertion sort of shaders/d3d11/sort.cs.glsl).
+        const bool in_smem = n <= (uint32_t)ENTRY_CAP;
+        if (in_smem) {
+            uint4 raw = make_uint4(0, 0, 0, 0xffffffffu);
+            float4 paint = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if ((uint32_t)lane < n) {
+                raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + lane));
+                paint = __ldg(&a.entries[e0 + lane].color);
+#if PF_PREFETCH
+                if (raw.y & 0x00ffffffu) prefetch_l2(a.fills + (raw.x - (raw.y & 0x00ffffffu)));
+#endif
+            }
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n; j++) rank += __shfl_sync(0xffffffffu, raw.w, j) < raw.w ? 1u : 0u;
+            if ((uint32_t)lane < n) {
+                sh.entry[rank] = raw;
+                sh.paint[rank] = paint;
+                if (HAS_CLIP) sh.clip[rank] = __ldg(a.entry_clip + e0 + lane);
+            }
+            __syncwarp();
+        }
+
+        // Pixel state: while `expanded` is false every pixel is `o`; afterwards pixel k of this lane is
+        // sh.dst[k * 32 + lane] * s + o (solid entries only update s and o).
+        bool expanded = false;
+        float s = 1.0f;
+        Px o = px_from(a.clear_color);
+        if (LOAD_DEST) {
+            // Rows / columns outside the image read as the clear colour (they are never stored).
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                float4 d = a.clear_color;
+                const int py = py0 + k;
+                if (px >= 0 && px < a.dest_w && py >= 0 && py < a.dest_h)
+                    d = unpack_rgba8(*reinterpret_cast<const uint32_t *>(a.dest + (size_t)py * a.dest_pitch + (size_t)px * 4));
+                sh.dst[k * 32 + lane] = d;
+            }
+            expanded = true;
+            o = px_from(make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        }
+
+        uint32_t next_key = 0; // selection path cursor: smallest tile index not yet drawn
+        for (uint32_t ei = 0; ei < n; ei++) {
+            uint4 raw;
+            float4 paint;
+            uint2 clip_entry = make_uint2(0, 0);
+            if (in_smem) {
+                raw = sh.entry[ei];
+                paint = sh.paint[ei];
+                if (HAS_CLIP) clip_entry = sh.clip[ei];
+            } else {
+                // Very deep lists: select the next entry in draw order by a min-scan.
+                uint32_t best = 0xffffffffu, best_i = 0;
+                for (uint32_t i = lane; i < n; i += 32) {
+                    const uint32_t key = __ldg(&a.entries[e0 + i].tile_index);
+                    if (key >= next_key && key < best) best = key, best_i = i;
+                }
+                for (int d = 16; d > 0; d >>= 1) {
+                    const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, d), oi = __shfl_xor_sync(0xffffffffu, best_i, d);
+                    if (ob < best) best = ob, best_i = oi;
+                }
+                next_key = best + 1;
+                raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + best_i));
+                paint = __ldg(&a.entries[e0 + best_i].color);
+                if (HAS_CLIP) clip_entry = __ldg(a.entry_clip + e0 + best_i);
+            }
+            const uint32_t fill_end = raw.x, count = raw.y & 0x00ffffffu;
+            const float backdrop = (float)(int)(int8_t)(raw.y >> 24);
+            const uint32_t ctrl = (raw.z >> 16) & 0xffu;
+            const Px pp = px_from(paint);
+            const f32x2 neg_w = pack2(-paint.w, -paint.w);
+            const bool clipped = HAS_CLIP && (raw.z & ENTRY_HAS_CLIP);
+
+            if (count == 0 && !clipped) {
+                // Solid tile: coverage = backdrop for every pixel (tile_fragment.inc.glsl:548) — the same
+                // blend for all 256 pixels, folded into the affine map.
+                const float m = mask_alpha(backdrop, ctrl);
+                s = fmaf(-paint.w * m, s, s);
+                over(o, pp, neg_w, m);
+                continue;
+            }
+
+            float cov[8];
+            if (!clipped) {
+                uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                fill_loop<HAS_CLIP>(sh, a.fills, fill_end - count, fill_end, xf, u_off, a.area_lut, lane, acc);
+                coverage_of(acc, count, backdrop, cov);
+                rule_of(cov, ctrl);
+            } else {
+                // A tile of a clipped path that meets an alpha tile of its clip path (tiler.rs:114-156). D3D9
+                // combines the masks as min(|draw + backdrop|, |clip + backdrop|) with the draw tile's
+                // backdrop then zeroed (tile_clip_combine.fs.glsl:28-31); a solid draw tile simply takes
+                // over the clip tile's mask and backdrop.
+                const bool replace = (raw.z & ENTRY_CLIP_REPLACE) != 0;
+                const uint32_t clip_count = clip_entry.y & 0x00ffffffu;
+                const float clip_backdrop = (float)(int)(int8_t)(clip_entry.y >> 24);
+                uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                fill_loop<HAS_CLIP>(sh, a.clip_fills, clip_entry.x - clip_count, clip_entry.x, xf, u_off, a.area_lut, lane, acc);
+                coverage_of(acc, clip_count, clip_backdrop, cov);
+                if (!replace) {
+                    uint32_t acc_draw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    float cov_draw[8];
+                    fill_loop<HAS_CLIP>(sh, a.fills, fill_end - count, fill_end, xf, u_off, a.area_lut, lane, acc_draw);
+                    coverage_of(acc_draw, count, backdrop, cov_draw);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) cov[k] = fminf(fabsf(cov_draw[k]), fabsf(cov[k]));
+                }
+                rule_of(cov, ctrl);
+            }
+
+            // calculateColor (tile_fragment.inc.glsl:560-614), solid colour, SrcOver — per pixel.
+            const f32x2 ss = pack2(s, s);
+            if (expanded) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float4 v = sh.dst[k * 32 + lane];
+                    Px d{fma2(pack2(v.x, v.y), ss, o.rg), fma2(pack2(v.z, v.w), ss, o.ba)};
+                    over(d, pp, neg_w, cov[k]);
+                    sh.dst[k * 32 + lane] = px_to(d);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    Px d = o;
+                    over(d, pp, neg_w, cov[k]);
+                    sh.dst[k * 32 + lane] = px_to(d);
+                }
+                expanded = true;
+            }
+            s = 1.0f;
+            o = px_from(make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        }
+
+        // ---- store. The tile is transposed through shared memory so that it leaves as 128-bit stores (two
+        // per lane) instead of eight 32-bit ones; when the frame is strip-partitioned over several GPUs the
+        // same stores also go straight into every peer's copy of the frame over NVLink.
+        uint32_t pk[8];
+        if (expanded) {
+            const f32x2 ss = pack2(s, s);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float4 v = sh.dst[k * 32 + lane];
+                pk[k] = pack_rgba8(Px{fma2(pack2(v.x, v.y), ss, o.rg), fma2(pack2(v.z, v.w), ss, o.ba)});
+            }
+        } else {
+            const uint32_t packed = pack_rgba8(o);
+#pragma unroll
+            for (int k = 0; k < 8; k++) pk[k] = packed;
+        }
+        const bool inside = tx >= 0 && ty >= 0 && tx * 16 + 16 <= a.dest_w && ty * 16 + 16 <= a.dest_h;
+        if (inside && (a.dest_align_mask & 15u) == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) sh.stage[(half * 8 + k) * 16 + half * 16 + x] = pk[k];
+            __syncwarp();
+            // chunk c = lane (rows 0..7) and lane + 32 (rows 8..15): row c / 4, 16-byte quarter c % 4
+            const int row0 = lane >> 2, quarter = lane & 3;
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(&sh.stage[row0 * 16 + quarter * 4]);
+            const uint4 v1 = *reinterpret_cast<const uint4 *>(&sh.stage[(row0 + 8) * 16 + 16 + quarter * 4]);
+            const size_t off0 = (size_t)(ty * 16 + row0) * a.dest_pitch + (size_t)tx * 64 + (size_t)quarter * 16;
+            const size_t off1 = off0 + 8 * a.dest_pitch;
+            for (int d = 0; d < a.n_dest; d++) {
+                *reinterpret_cast<uint4 *>(a.dests[d] + off0) = v0;
+                *reinterpret_cast<uint4 *>(a.dests[d] + off1) = v1;
+            }
+        } else if (px >= 0 && px < a.dest_w) {
+            for (int d = 0; d < a.n_dest; d++) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int py = py0 + k;
+                    if (py >= 0 && py < a.dest_h)
+                        *reinterpret_cast<uint32_t *>(a.dests[d] + (size_t)py * a.dest_pitch + (size_t)px * 4) = pk[k];
+                }
+            }
+        }
+        __syncwarp(); // the next tile reuses this warp's shared-memory slots
+#if PF_PREFETCH
+        if ((uint32_t)lane < n_next && n_next <= (uint32_t)ENTRY_CAP) prefetch_l2(a.entries + e0_next + lane);
+#endif
+        k_cur = k_next, work = work_next, n = n_next, e0 = e0_next;
+    }
+}
+
+// Resident blocks of the persistent kernel per device (one process may drive several GPUs).
+struct Residency {
+    int sm_count = 0;
+    int blocks[2][2] = {{0, 0}, {0, 0}}; // [load_dest][has_clip]
+};
+Residency &residency_of_current_device() {
+    static Residency table[64];
+    int dev = 0;
+    PF_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) throw Error(2, "device ordinal out of range");
+    Residency &r = table[dev];
+    if (r.sm_count == 0) {
+        int sm = 0;
+        PF_CUDA_CHECK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+        const int threads = 32 * TILE_WARPS;
+        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r.blocks[0][0], k_tile_alpha<false, false>, threads, 0));
+        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r.blocks[1][0], k_tile_alpha<true, false>, threads, 0));
+        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r.blocks[0][1], k_tile_alpha<false, true>, threads, 0));
+        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r.blocks[1][1], k_tile_alpha<true, true>, threads, 0));
+        r.sm_count = sm;
+    }
+    return r;
+}
+
+} // namespace
+
+int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
+    const int fb_w = a.fb.max_x - a.fb.min_x;
+    const int rows = a.tile_y1 - a.tile_y0;
+    if (fb_w <= 0 || rows <= 0) return 0;
+    if (fb_w > 65535 || rows > 65535) throw Error(2, "framebuffer larger than 65535 tiles on a side");
+    // The caller has zeroed a.work_counter and a.queue_count (the tile-list kernel may since have parked the
+    // work counter past the end).
+    const uint64_t segments = (uint64_t)((fb_w + 31) / 32) * (uint64_t)rows;
+    const unsigned solid_grid = (unsigned)((segments + 3) / 4); // 4 warps per block
+    if (a.load_dest)
+        k_tile_solid<true><<<solid_grid, 128, 0, stream>>>(a);
+    else
+        k_tile_solid<false><<<solid_grid, 128, 0, stream>>>(a);
+    PF_CUDA_CHECK(cudaGetLastError());
+    if (!a.entries) return 1; // a frame without batches: every list is empty, nothing was queued
+
+    // One resident wave of persistent warps, or fewer when the whole frame has fewer tiles.
+    const Residency &res = residency_of_current_device();
+    const bool has_clip = a.entry_clip != nullptr;
+    const uint64_t n_work = (uint64_t)fb_w * (uint64_t)rows;
+    const uint64_t want = (n_work + TILE_WARPS - 1) / TILE_WARPS;
+    const uint64_t resident = (uint64_t)res.sm_count * (uint64_t)res.blocks[a.load_dest ? 1 : 0][has_clip ? 1 : 0];
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min(want, resident));
+    const int threads = 32 * TILE_WARPS;
+    if (has_clip) {
+        if (a.load_dest)
+            k_tile_alpha<true, true><<<grid, threads, 0, stream>>>(a);
+        else
+            k_tile_alpha<false, true><<<grid, threads, 0, stream>>>(a);
+    } else if (a.load_dest) {
+        k_tile_alpha<true, false><<<grid, threads, 0, stream>>>(a);
+    } else {
+        k_tile_alpha<false, false><<<grid, threads, 0, stream>>>(a);
+    }
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 2;
+}
+
+} // namespace pf

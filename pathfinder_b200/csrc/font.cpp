@@ -75,6 +75,7 @@ using GlyphContour = std::vector<GlyphPoint>;
 
 constexpr int MAX_COMPONENT_DEPTH = 8;
 constexpr size_t MAX_GLYPH_POINTS = 1u << 20; // composite glyphs of a hostile file cannot blow up memory
+constexpr size_t MAX_COMPONENT_VISITS = 4096;  // ... nor recurse without end through empty components
 
 void glyph_range(const PFFont &f, const Reader &r, uint32_t gid, uint32_t &begin, uint32_t &end) {
     if (gid >= f.glyph_count) throw Bad{};
@@ -202,6 +203,11 @@ void read_contours(const PFFont &f, const Reader &r, uint32_t gid, int depth, st
             for (int i = 0; i < 4; i++) m[i] = (float)r.i16(p + 2 * (size_t)i) * k;
             p += 8;
         }
+        // Every component visit counts against the budget too: a hostile font whose composites fan out into
+        // empty glyphs would otherwise recurse ~1000^8 times without ever adding a point (FreeType caps the
+        // same way through maxp.maxComponentElements / maxComponentDepth).
+        total_points += MAX_GLYPH_POINTS / MAX_COMPONENT_VISITS;
+        if (total_points > MAX_GLYPH_POINTS) throw Bad{};
         std::vector<GlyphContour> sub;
         read_contours(f, r, component, depth + 1, sub, total_points);
         for (GlyphContour &c : sub) {

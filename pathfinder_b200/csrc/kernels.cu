@@ -945,7 +945,8 @@ __global__ void __launch_bounds__(256)
                  uint32_t *__restrict__ tile_fb, uint32_t *__restrict__ fb_count,
                  uint32_t *__restrict__ tile_fill_pos, uint32_t *__restrict__ fill_cursor,
                  uint32_t *__restrict__ path_live, int keep_all_fills, const uint32_t *__restrict__ run_counts,
-                 uint32_t *__restrict__ live_tiles, uint32_t live_capacity, uint32_t *__restrict__ live_count) {
+                 uint32_t *__restrict__ live_tiles, uint32_t live_capacity, uint32_t *__restrict__ live_count,
+                 uint32_t *__restrict__ fb_alpha, const uint32_t *__restrict__ tile_clip) {
     __shared__ uint32_t smem[256 / 32 + 1];
     __shared__ uint32_t s_base;
     const uint32_t base = blockIdx.x * LIST_TILE + threadIdx.x;
@@ -976,6 +977,9 @@ __global__ void __launch_bounds__(256)
                     live_mask |= 1u << r;
                     atomicAdd(fb_count + fbi, 1u);
                     if (count != 0) path_live[p] = 1u; // some fills of this path will be read: its lines must be walked again
+                    // The framebuffer tile needs per-pixel work (a mask of fills or a clip mask): plain store,
+                    // every writer stores the same value.
+                    if (count != 0 || (tile_clip && __ldg(tile_clip + t) != 0u)) fb_alpha[fbi] = 1u;
                 }
             }
         }
@@ -1027,12 +1031,12 @@ __global__ void __launch_bounds__(256)
 int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
                       uint32_t *fb_count, uint32_t *tile_fill_pos, uint32_t *fill_cursor, uint32_t *path_live,
                       bool keep_all_fills, const uint32_t *run_counts, uint32_t *live_tiles, uint32_t live_capacity,
-                      uint32_t *live_count, cudaStream_t stream) {
+                      uint32_t *live_count, uint32_t *fb_alpha, const uint32_t *tile_clip, cudaStream_t stream) {
     if (b.n_tiles == 0) return 0;
     k_list_count<<<div_up(b.n_tiles, LIST_TILE), 256, 0, stream>>>(b, tile_word, z_buffer, tile_fb, fb_count,
                                                                     tile_fill_pos, fill_cursor, path_live,
                                                                     keep_all_fills ? 1 : 0, run_counts, live_tiles,
-                                                                    live_capacity, live_count);
+                                                                    live_capacity, live_count, fb_alpha, tile_clip);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -1068,7 +1072,10 @@ __global__ void __launch_bounds__(256)
         e.paint_ctrl = __ldg(&b.paths[p].paint_ctrl) & 0x00ffffffu;
         e.tile_index = t;
         uint32_t slot = __ldg(fb_start + fbi) + atomicAdd(fb_cursor + fbi, 1u);
-        const float4 color = __ldg(paints + (e.paint_ctrl & 0xffffu));
+        // The paint premultiplied, (rgb * a, a): what the compositing kernels blend with (color.rgb *= color.a,
+        // shaders/tile_fragment.inc.glsl:611).
+        float4 color = __ldg(paints + (e.paint_ctrl & 0xffffu));
+        color.x *= color.w, color.y *= color.w, color.z *= color.w;
         uint2 clip_entry = make_uint2(0, 0);
         if (tile_clip) { // the batch has clipped paths
             const uint32_t ref = __ldg(tile_clip + t);
@@ -1106,7 +1113,9 @@ int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-// fill + tile (fused) — exact-area coverage from the LUT, fill rule, paint, SrcOver blend.
+// fill + tile (fused) live in composite.cu. What follows is the coverage evaluation kept for the
+// parity dumps (k_alpha_masks): computeCoverage in the form round 1 shipped, one lane per
+// (column, 8-row half) — an independent evaluation of the same reference math.
 // ---------------------------------------------------------------------------------------------
 
 // Coverage contributions are accumulated as integers so the sum does not depend on the order of
@@ -1151,400 +1160,6 @@ __device__ __forceinline__ bool accumulate_fill(uint32_t from_w, uint32_t to_w, 
 
 __device__ __forceinline__ float finish_coverage(uint32_t acc, uint32_t contributions) {
     return (float)(int32_t)(acc - contributions * COV_MAGIC_BITS) * COV_SCALE;
-}
-
-// sampleMask (shaders/tile_fragment.inc.glsl:539-556) on coverage = mask + backdrop.
-__device__ __forceinline__ float mask_alpha(float coverage, uint32_t ctrl) {
-    if (ctrl & 1u) { // TILE_CTRL_MASK_WINDING
-        coverage = fabsf(coverage);
-    } else if (ctrl & 2u) { // TILE_CTRL_MASK_EVEN_ODD
-        float m = coverage - 2.0f * floorf(coverage * 0.5f);
-        coverage = 1.0f - fabsf(1.0f - m);
-    } else {
-        coverage = 1.0f;
-    }
-    return fminf(1.0f, coverage);
-}
-
-// clamp to [0,1], scale by 255, round to nearest even: the integer lands in the low mantissa bits
-// of x * 255 + 2^23 (no F2I on the slow pipe), then the four bytes are packed with PRMT.
-__device__ __forceinline__ uint32_t pack_rgba8(float4 c) {
-    const float magic = 8388608.0f;
-    uint32_t r = __float_as_uint(fmaf(__saturatef(c.x), 255.0f, magic));
-    uint32_t g = __float_as_uint(fmaf(__saturatef(c.y), 255.0f, magic));
-    uint32_t b = __float_as_uint(fmaf(__saturatef(c.z), 255.0f, magic));
-    uint32_t a = __float_as_uint(fmaf(__saturatef(c.w), 255.0f, magic));
-    uint32_t rg = __byte_perm(r, g, 0x0040); // bytes: r0, g0, 0, 0
-    uint32_t ba = __byte_perm(b, a, 0x0040);
-    return __byte_perm(rg, ba, 0x5410);
-}
-
-// Packed f32x2 arithmetic (sm_100: FFMA2 / FMUL2 issue two fp32 operations per lane per instruction;
-// the compositing loop is issue-bound, not FP32-pipe-bound). Same roundings as the scalar forms.
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-
-// dest = dest * (1 - a) + src with premultiplied src (shaders/d3d11/tile.cs.glsl:155):
-// d = fma(d, 1 - a, (base.rgb * a, a)), two channels per instruction.
-__device__ __forceinline__ void blend(float4 &d, float4 base, float alpha) {
-    const float ia = 1.0f - alpha;
-    const unsigned long long ii = pack2(ia, ia);
-    const unsigned long long src_xy = mul2(pack2(base.x, base.y), pack2(alpha, alpha));
-    const unsigned long long xy = fma2(pack2(d.x, d.y), ii, src_xy);
-    const unsigned long long zw = fma2(pack2(d.z, d.w), ii, pack2(base.z * alpha, alpha));
-    unpack2(xy, d.x, d.y);
-    unpack2(zw, d.z, d.w);
-}
-
-// One warp per framebuffer tile: lane (x, half) owns column x, rows 8*half .. 8*half+7 (two of the
-// 4-row strips of shaders/d3d11/tile.cs.glsl:22). Fill (coverage) and tile (composite) are one
-// kernel — the mask never leaves registers. Entries and fills are loaded cooperatively (lane i
-// loads element i) and broadcast with shuffles / shared memory. While every entry drawn so far is a
-// solid tile the whole tile has one colour, so a single pixel is blended per lane ("uniform"
-// prefix); per-pixel state is only expanded at the first tile that has fills.
-constexpr int COMPOSITE_WARPS = 2;       // tiles per block, horizontally adjacent
-constexpr int COMPOSITE_SORT_CAP = 128;  // entries sorted in shared memory; longer lists use the slow path
-
-template <bool LOAD_DEST, bool HAS_CLIP>
-__global__ void __launch_bounds__(32 * COMPOSITE_WARPS, 10) k_composite(CompositeArgs a) {
-    __shared__ uint4 s_entries[COMPOSITE_WARPS][COMPOSITE_SORT_CAP];
-    __shared__ float4 s_paints[COMPOSITE_WARPS][COMPOSITE_SORT_CAP];
-    __shared__ uint32_t s_keys[COMPOSITE_WARPS][COMPOSITE_SORT_CAP];
-    __shared__ uint2 s_clip[COMPOSITE_WARPS][HAS_CLIP ? COMPOSITE_SORT_CAP : 1]; // {clip fill end, clip tile word}
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int fb_w = a.fb.max_x - a.fb.min_x;
-    const uint32_t n_work = (uint32_t)fb_w * (uint32_t)(a.tile_y1 - a.tile_y0);
-    // Persistent warps: tiles differ wildly in depth, so every warp pulls its next tile from a
-    // global counter instead of owning a fixed one (row-major, so neighbours stay neighbours).
-    // The pull is software-pipelined two deep: while tile i is composited, the counter increment for
-    // tile i + 2 and the list header (start, count) of tile i + 1 are in flight, so neither the atomic's
-    // nor the header's latency sits on a tile's critical path. (Claiming several consecutive tiles per
-    // atomic was measured: no gain on the 100k-path scene, and the tiger's clustered deep tiles
-    // unbalance the tail.)
-    const int64_t fb_base = (int64_t)(a.tile_y0 - a.fb.min_y) * fb_w; // list index of work item 0
-    const int64_t n_fb = (int64_t)fb_w * (a.fb.max_y - a.fb.min_y);
-    auto claim = [&]() -> uint32_t {
-        uint32_t c = 0;
-        if (lane == 0) c = atomicAdd(a.work_counter, 1u);
-        return c; // lane 0 only; broadcast when it is needed, not before
-    };
-    auto load_header = [&](uint32_t w, uint32_t &count, uint32_t &start) {
-        count = start = 0;
-        const int64_t index = (int64_t)w + fb_base;
-        if (w < n_work && index >= 0 && index < n_fb) {
-            count = __ldg(a.fb_count + index);
-            start = __ldg(a.fb_start + index);
-        }
-    };
-    uint32_t pending = claim();
-    uint32_t work = __shfl_sync(0xffffffffu, pending, 0);
-    pending = claim();
-    uint32_t n, e0;
-    load_header(work, n, e0);
-    for (;;) {
-    if (work >= n_work) return;
-    const uint32_t work_next = __shfl_sync(0xffffffffu, pending, 0);
-    pending = claim();
-    uint32_t n_next, e0_next;
-    load_header(work_next, n_next, e0_next);
-
-    // work / fb_w by multiplication: fb_w_recip = floor(2^32 / fb_w) under-estimates the quotient by at most one.
-    uint32_t tile_row = __umulhi(work, a.fb_w_recip), tile_col_u = work - tile_row * (uint32_t)fb_w;
-    if (tile_col_u >= (uint32_t)fb_w) tile_row++, tile_col_u -= (uint32_t)fb_w;
-    const int tile_col = (int)tile_col_u;
-    const int ty = a.tile_y0 + (int)tile_row; // absolute tile y
-    const int tx = a.fb.min_x + tile_col;
-    const int x = lane & 15, half = lane >> 4;
-    const int px = tx * 16 + x, py0 = ty * 16 + half * 8;
-    // Rows of this lane that exist in the destination image (bit k = row py0 + k).
-    uint32_t row_mask = 0;
-    if (px >= 0 && px < a.dest_w) {
-        int lo = max(0, -py0), hi = min(8, a.dest_h - py0);
-        row_mask = hi > lo ? ((0xffu >> (8 - hi)) & (0xffu << lo)) : 0u;
-    }
-    uint8_t *out = a.dest + (ptrdiff_t)py0 * (ptrdiff_t)a.dest_pitch + (ptrdiff_t)px * 4;
-
-    // ---- bring the run into draw order: rank sort by tile index in shared memory ----
-    const bool in_smem = n <= COMPOSITE_SORT_CAP;
-    if (in_smem && n > 0) {
-        if (n == 1) {
-            if (lane == 0) {
-                s_entries[warp][0] = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0));
-                s_paints[warp][0] = __ldg(&a.entries[e0].color);
-                if (HAS_CLIP) s_clip[warp][0] = __ldg(a.entry_clip + e0);
-            }
-        } else if (n <= 32) {
-            // One entry per lane: loaded once, ranked against the keys in shared memory.
-            uint4 raw = make_uint4(0, 0, 0, 0);
-            float4 color = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if ((uint32_t)lane < n) {
-                raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + lane));
-                color = __ldg(&a.entries[e0 + lane].color);
-                s_keys[warp][lane] = raw.w;
-            }
-            __syncwarp();
-            if ((uint32_t)lane < n) {
-                uint32_t rank = 0;
-                for (uint32_t j = 0; j < n; j++) rank += s_keys[warp][j] < raw.w ? 1u : 0u;
-                s_entries[warp][rank] = raw;
-                s_paints[warp][rank] = color;
-                if (HAS_CLIP) s_clip[warp][rank] = __ldg(a.entry_clip + e0 + lane);
-            }
-        } else {
-            for (uint32_t i = lane; i < n; i += 32) s_keys[warp][i] = __ldg(&a.entries[e0 + i].tile_index);
-            __syncwarp();
-            for (uint32_t i = lane; i < n; i += 32) {
-                const uint32_t key = s_keys[warp][i];
-                uint32_t rank = 0;
-                for (uint32_t j = 0; j < n; j++) rank += s_keys[warp][j] < key ? 1u : 0u;
-                s_entries[warp][rank] = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + i));
-                s_paints[warp][rank] = __ldg(&a.entries[e0 + i].color);
-                if (HAS_CLIP) s_clip[warp][rank] = __ldg(a.entry_clip + e0 + i);
-            }
-        }
-        __syncwarp();
-    }
-
-    float4 dst[8];
-    float4 uni = a.clear_color; // the tile's single colour while `uniform`
-    bool uniform = !LOAD_DEST;
-    if (LOAD_DEST) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            dst[k] = a.clear_color;
-            if (row_mask & (1u << k)) {
-                uint32_t v = *reinterpret_cast<const uint32_t *>(out + (size_t)k * a.dest_pitch);
-                const float s = 1.0f / 255.0f;
-                dst[k] = make_float4((float)(v & 0xff) * s, (float)((v >> 8) & 0xff) * s,
-                                     (float)((v >> 16) & 0xff) * s, (float)(v >> 24) * s);
-            }
-        }
-    }
-
-    const float cx = (float)x + 0.5f, cy = (float)(half * 8) + 0.5f;
-    uint32_t next_key = 0; // slow path cursor: smallest tile index not yet drawn
-    for (uint32_t ei = 0; ei < n; ei++) {
-        uint4 raw;
-        float4 base;
-        uint2 clip_entry = make_uint2(0, 0);
-        if (in_smem) {
-            raw = s_entries[warp][ei];
-            base = s_paints[warp][ei];
-            if (HAS_CLIP) clip_entry = s_clip[warp][ei];
-        } else {
-            // Slow path for very deep lists: select the next entry in draw order by a min-scan.
-            uint32_t best = 0xffffffffu, best_i = 0;
-            for (uint32_t i = lane; i < n; i += 32) {
-                uint32_t key = __ldg(&a.entries[e0 + i].tile_index);
-                if (key >= next_key && key < best) best = key, best_i = i;
-            }
-            for (int d = 16; d > 0; d >>= 1) {
-                uint32_t ob = __shfl_xor_sync(0xffffffffu, best, d), oi = __shfl_xor_sync(0xffffffffu, best_i, d);
-                if (ob < best) best = ob, best_i = oi;
-            }
-            next_key = best + 1;
-            raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + best_i));
-            base = __ldg(&a.entries[e0 + best_i].color);
-            if (HAS_CLIP) clip_entry = __ldg(a.entry_clip + e0 + best_i);
-        }
-        const uint32_t fill_end = raw.x, word = raw.y;
-        const uint32_t count = word & 0x00ffffffu;
-        const float backdrop = (float)(int)(int8_t)(word >> 24);
-        const uint32_t ctrl = (raw.z >> 16) & 0xffu;
-        if (HAS_CLIP && (raw.z & ENTRY_HAS_CLIP)) {
-            // A tile of a clipped path that meets an alpha tile of its clip path (tiler.rs:114-156). Both
-            // masks are evaluated here; D3D9 combines them as min(|draw + backdrop|, |clip + backdrop|)
-            // with the draw tile's backdrop then zeroed (tile_clip_combine.fs.glsl:28-31); a solid
-            // draw tile simply takes over the clip tile's mask and backdrop.
-            if (uniform) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) dst[k] = uni;
-                uniform = false;
-            }
-            const bool replace = (raw.z & ENTRY_CLIP_REPLACE) != 0;
-            const uint32_t clip_count = clip_entry.y & 0x00ffffffu;
-            const float clip_backdrop = (float)(int)(int8_t)(clip_entry.y >> 24);
-            uint32_t acc_draw[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, acc_clip[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-            uint32_t n_draw = 0, n_clip = 0;
-            if (!replace)
-                for (uint32_t f = fill_end - count; f < fill_end; f++) {
-                    const uint2 fill = __ldg(a.fills + f);
-                    n_draw += accumulate_fill<2>(fill.x, fill.y, cx, cy, a.area_lut, acc_draw) ? 1u : 0u;
-                }
-            for (uint32_t f = clip_entry.x - clip_count; f < clip_entry.x; f++) {
-                const uint2 fill = __ldg(a.clip_fills + f);
-                n_clip += accumulate_fill<2>(fill.x, fill.y, cx, cy, a.area_lut, acc_clip) ? 1u : 0u;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const float clip_cov = finish_coverage(acc_clip[k >> 2][k & 3], n_clip) + clip_backdrop;
-                float coverage = clip_cov;
-                if (!replace)
-                    coverage = fminf(fabsf(finish_coverage(acc_draw[k >> 2][k & 3], n_draw) + backdrop), fabsf(clip_cov));
-                blend(dst[k], base, base.w * mask_alpha(coverage, ctrl));
-            }
-            continue;
-        }
-        if (count == 0) {
-            // Solid tile: coverage = backdrop for every pixel (tile_fragment.inc.glsl:548).
-            const float alpha = base.w * mask_alpha(backdrop, ctrl);
-            if (uniform) {
-                blend(uni, base, alpha);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; k++) blend(dst[k], base, alpha);
-            }
-            continue;
-        }
-        if (uniform) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) dst[k] = uni;
-            uniform = false;
-        }
-        uint32_t acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-        uint32_t contributions = 0;
-        for (uint32_t f0 = fill_end - count; f0 < fill_end; f0 += 32) {
-            const uint32_t m = min(32u, fill_end - f0);
-            uint2 mine = make_uint2(0, 0);
-            if ((uint32_t)lane < m) mine = __ldg(a.fills + f0 + lane);
-            for (uint32_t j = 0; j < m; j++) {
-                uint32_t from_w = __shfl_sync(0xffffffffu, mine.x, j), to_w = __shfl_sync(0xffffffffu, mine.y, j);
-                contributions += accumulate_fill<2>(from_w, to_w, cx, cy, a.area_lut, acc) ? 1u : 0u;
-            }
-        }
-        // calculateColor (tile_fragment.inc.glsl:560-614), solid colour, SrcOver.
-        if (count <= 127u) {
-            // At most 127 contributions of magnitude <= 2^15 units: |sum| < 2^22, so the signed sum
-            // can be read off the mantissa of 1.5 * 2^23 + sum (no I2F on the quarter-rate pipe) and
-            // scaled, un-biased (12582912 * 2^-15 = 384) and offset by the backdrop in one FFMA —
-            // the same single rounding as float(sum) * 2^-15 + backdrop.
-            const uint32_t bias = 0x4b400000u - contributions * COV_MAGIC_BITS;
-            const float offset = backdrop - 384.0f;
-            if (ctrl & 1u) { // TILE_CTRL_MASK_WINDING
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const float coverage = fmaf(__uint_as_float(acc[k >> 2][k & 3] + bias), COV_SCALE, offset);
-                    blend(dst[k], base, base.w * fminf(fabsf(coverage), 1.0f));
-                }
-            } else if (ctrl & 2u) { // TILE_CTRL_MASK_EVEN_ODD
-                // 1 - |1 - (c mod 2)| is the distance from c to the nearest even integer:
-                // 2 * |c/2 - rint(c/2)|, with rint from the 1.5 * 2^23 trick (|c/2| < 2^22 here).
-                const float twice_alpha = 2.0f * base.w;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const float coverage = fmaf(__uint_as_float(acc[k >> 2][k & 3] + bias), COV_SCALE, offset);
-                    const float t = coverage * 0.5f;
-                    const float nearest = (t + 12582912.0f) - 12582912.0f;
-                    blend(dst[k], base, twice_alpha * fabsf(t - nearest));
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; k++) blend(dst[k], base, base.w);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const float coverage = finish_coverage(acc[k >> 2][k & 3], contributions) + backdrop;
-                blend(dst[k], base, base.w * mask_alpha(coverage, ctrl));
-            }
-        }
-    }
-    // ---- store: into the local image and, when the frame is strip-partitioned over several GPUs,
-    // straight into every peer's copy of the frame over NVLink (P2P stores to IPC-mapped buffers) —
-    // the all-gather that assembles the frame is fused into this kernel's epilogue, so it overlaps
-    // the compositing of the other tiles instead of running as a separate collective afterwards.
-    uint32_t pk[8];
-    if (uniform) {
-        const uint32_t packed = pack_rgba8(uni);
-#pragma unroll
-        for (int k = 0; k < 8; k++) pk[k] = packed;
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; k++) pk[k] = pack_rgba8(dst[k]);
-    }
-    // One colour for the whole tile: when the tile lies inside the image and rows are 16-byte
-    // aligned, lane l writes half of row l/2 with two 128-bit stores instead of eight 32-bit ones.
-    const bool vec = uniform && tx >= 0 && ty >= 0 && tx * 16 + 16 <= a.dest_w && ty * 16 + 16 <= a.dest_h &&
-                     (a.dest_align_mask & 15) == 0;
-    const size_t vec_off = (size_t)(ty * 16 + (lane >> 1)) * a.dest_pitch + (size_t)tx * 64 + (size_t)(lane & 1) * 32;
-    const ptrdiff_t px_off = (ptrdiff_t)py0 * (ptrdiff_t)a.dest_pitch + (ptrdiff_t)px * 4;
-    for (int d = 0; d < a.n_dest; d++) {
-        uint8_t *base = a.dests[d];
-        if (vec) {
-            const uint4 v = make_uint4(pk[0], pk[0], pk[0], pk[0]);
-            reinterpret_cast<uint4 *>(base + vec_off)[0] = v;
-            reinterpret_cast<uint4 *>(base + vec_off)[1] = v;
-        } else if (row_mask == 0xffu) {
-            uint8_t *o = base + px_off;
-#pragma unroll
-            for (int k = 0; k < 8; k++, o += a.dest_pitch) *reinterpret_cast<uint32_t *>(o) = pk[k];
-        } else {
-            uint8_t *o = base + px_off;
-#pragma unroll
-            for (int k = 0; k < 8; k++, o += a.dest_pitch)
-                if (row_mask & (1u << k)) *reinterpret_cast<uint32_t *>(o) = pk[k];
-        }
-    }
-    __syncwarp(); // the next tile reuses this warp's shared-memory slots
-    work = work_next, n = n_next, e0 = e0_next;
-    }
-}
-
-int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
-    int fb_w = a.fb.max_x - a.fb.min_x;
-    int rows = a.tile_y1 - a.tile_y0;
-    if (fb_w <= 0 || rows <= 0) return 0;
-    // One resident wave of persistent warps: SM count x resident blocks per SM.
-    static int blocks_per_sm[2] = {0, 0}, clip_blocks_per_sm[2] = {0, 0}, sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        PF_CUDA_CHECK(cudaGetDevice(&dev));
-        PF_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], k_composite<false, false>, 32 * COMPOSITE_WARPS, 0));
-        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], k_composite<true, false>, 32 * COMPOSITE_WARPS, 0));
-        // the clip variants keep one more shared array per warp; never more resident blocks than the plain ones
-        int with_clip[2];
-        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_clip[0], k_composite<false, true>, 32 * COMPOSITE_WARPS, 0));
-        PF_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&with_clip[1], k_composite<true, true>, 32 * COMPOSITE_WARPS, 0));
-        clip_blocks_per_sm[0] = with_clip[0], clip_blocks_per_sm[1] = with_clip[1];
-    }
-    const uint64_t n_work = (uint64_t)fb_w * (uint64_t)rows;
-    CompositeArgs args = a;
-    args.fb_w_recip = (uint32_t)std::min<uint64_t>(0xffffffffull, (1ull << 32) / (uint64_t)fb_w);
-    uint64_t want = (n_work + COMPOSITE_WARPS - 1) / COMPOSITE_WARPS;
-    const bool has_clip = a.entry_clip != nullptr;
-    uint64_t resident = (uint64_t)sm_count * (uint64_t)(has_clip ? clip_blocks_per_sm : blocks_per_sm)[a.load_dest ? 1 : 0];
-    unsigned grid = (unsigned)(want < resident ? want : resident);
-    // The caller has zeroed a.work_counter (the tile-list kernel may since have parked it past the end).
-    if (has_clip) {
-        if (a.load_dest)
-            k_composite<true, true><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(args);
-        else
-            k_composite<false, true><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(args);
-    } else if (a.load_dest) {
-        k_composite<true, false><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(args);
-    } else {
-        k_composite<false, false><<<grid, 32 * COMPOSITE_WARPS, 0, stream>>>(args);
-    }
-    PF_CUDA_CHECK(cudaGetLastError());
-    return 1;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -43,7 +43,7 @@ struct __align__(32) TileEntry {
     uint32_t word;        // fill count (low 24 bits) | backdrop i8 << 24
     uint32_t paint_ctrl;  // color u16 | ctrl u8 << 16
     uint32_t tile_index;  // dense tile index: ascending = draw order (sort key inside a list)
-    float4 color;         // base colour of the paint, already rounded through f16
+    float4 color;         // the paint premultiplied, (rgb * a, a); base colour already rounded through f16
 };
 
 // Tile-grouped fill: the 4.8 fixed point segment (LineSegmentU16) as one 64-bit word.
@@ -145,8 +145,9 @@ int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_
 int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_t *z_buffer, uint32_t *tile_fb,
                       uint32_t *fb_count, uint32_t *tile_fill_pos, uint32_t *fill_cursor, uint32_t *path_live,
                       bool keep_all_fills, const uint32_t *run_counts, uint32_t *live_tiles, uint32_t live_capacity,
-                      uint32_t *live_count, cudaStream_t stream);
+                      uint32_t *live_count, uint32_t *fb_alpha, const uint32_t *tile_clip, cudaStream_t stream);
 // (live_tiles, optional: the surviving tiles as a compact list, *live_count of them, for launch_list_emit)
+// (fb_alpha[fb] = 1 when a surviving tile there has fills or — tile_clip, optional — a clip mask)
 // Device-side totals ([0] lines, [2] entries, [5] visible fills) and the capacities they must fit.
 struct OverflowGuard {
     const uint32_t *totals;
@@ -165,6 +166,9 @@ struct CompositeArgs {
     const uint2 *entry_clip;    // per entry {clip fill end, clip tile word}, for entries with ENTRY_HAS_CLIP (else NULL)
     const PackedFill *clip_fills;
     const uint32_t *fb_start, *fb_count;
+    const uint32_t *fb_alpha;  // per framebuffer tile: some entry has fills or a clip mask (per-pixel work)
+    uint32_t *queue;           // framebuffer tiles (row << 16 | column within the strip) that need per-pixel work,
+    uint32_t *queue_count;     //   appended by k_tile_solid, consumed by k_tile_alpha; zeroed by the caller
     const PackedFill *fills;
     cudaTextureObject_t area_lut;
     FbRect fb;
@@ -177,8 +181,7 @@ struct CompositeArgs {
     int32_t dest_w, dest_h;
     float4 clear_color;
     int load_dest;             // LOAD_ACTION_LOAD for batches after the first
-    uint32_t *work_counter;    // device word used by the persistent warps to pull tiles
-    uint32_t fb_w_recip;       // floor(2^32 / framebuffer width in tiles); set by launch_composite
+    uint32_t *work_counter;    // device word used by the persistent warps to pull queued tiles; zeroed by the caller
 };
 int launch_composite(const CompositeArgs &args, cudaStream_t stream);
 

@@ -122,6 +122,7 @@ struct PFCudaRenderer {
     uint8_t *dest = nullptr;
     size_t dest_pitch = 0;
     bool dest_external = false;
+    int32_t dest_external_rows = 0; // rows the external / peer destinations were installed for
 
     // Area LUT texture (textures/area-lut.png; renderer/src/gpu/renderer.rs:207-214).
     cudaArray_t lut_array = nullptr;
@@ -153,12 +154,13 @@ struct PFCudaRenderer {
     // Everything a frame needs zeroed lives in one allocation and is cleared by one memset (carve_zeroed).
     DeviceBuffer<uint32_t> zeroed;
     ZeroedView<uint32_t> counters;  // device-side totals: [0]=lines [1]=fills [2]=entries [3]=alpha tiles [4]=dump tiles
-                                    // [5]=visible fills [6,7]/[13,14]=long-line queues [8,9]=u64 scratch [12]=tile counter [15]=surviving tiles
+                                    // [5]=visible fills [6,7]/[13,14]=long-line queues [8,9]=u64 scratch [10]=queued framebuffer tiles
+                                    // [12]=tile counter [15]=surviving tiles
     ZeroedView<uint32_t> path_live; // per path: some tile with fills survived the z-cull
     ZeroedView<uint32_t> tile_word;
     ZeroedView<int32_t> col_backdrop;
     ZeroedView<int32_t> z_buffer;
-    ZeroedView<uint32_t> fb_count, fb_cursor;
+    ZeroedView<uint32_t> fb_count, fb_cursor, fb_alpha;
     DeviceBuffer<uint32_t> tile_fill_pos, tile_first_fill, tile_fb, tile_pos, tile_alpha_id;
     DeviceBuffer<int32_t> col_backdrop_init;
     DeviceBuffer<uint32_t> long_queue; // lines walked by whole warps (k_bin_long)
@@ -182,6 +184,7 @@ struct PFCudaRenderer {
     DeviceBuffer<PackedFill> fills;
     DeviceBuffer<EmitFill> fills_emit;
     DeviceBuffer<uint32_t> fb_start;
+    DeviceBuffer<uint32_t> tile_queue; // framebuffer tiles that need per-pixel compositing (k_tile_solid -> k_tile_alpha)
     DeviceBuffer<TileEntry> entries;
     PinnedBuffer<uint32_t> counters_host;
     ScanScratch scan_scratch;
@@ -267,6 +270,7 @@ void setup_tracking(PFCudaRenderer *r) {
     track(r, r->fills);
     track(r, r->fills_emit);
     track(r, r->fb_start);
+    track(r, r->tile_queue);
     track(r, r->entries);
     track(r, r->scan_scratch.control);
     track(r, r->scan_scratch.status);
@@ -310,8 +314,10 @@ float4 clear_color(const PFCudaRenderer *r) {
     // Renderer::clear_color_for_draw_operation (gpu/renderer.rs): background colour if set,
     // otherwise transparent black.
     if (r->options.flags & PF_RENDERER_OPTIONS_FLAGS_HAS_BACKGROUND_COLOR) {
+        // (clamped: the compositing kernels pack without saturating — every colour they blend lies in [0, 1])
         const PFColorF &c = r->options.background_color;
-        return make_float4(c.r, c.g, c.b, c.a);
+        auto unit = [](float v) { return v >= 0.0f ? (v <= 1.0f ? v : 1.0f) : 0.0f; }; // NaN -> 0
+        return make_float4(unit(c.r), unit(c.g), unit(c.b), unit(c.a));
     }
     return make_float4(0, 0, 0, 0);
 }
@@ -340,6 +346,23 @@ struct HostTimer {
 void upload_segments(PFCudaRenderer *r, SceneSegments &dst, const PFSegmentsD3D11 &src, bool payload_persists) {
     HostTimer timer("upload_segments");
     LapTimer laps;
+    // Every index must address its 2, 3 or 4 points inside `points` (SegmentsD3D11::add_path, builder.rs:807-841):
+    // dice reads them unchecked.
+    {
+        std::atomic<bool> bad{false};
+        const PFSegmentIndicesD3D11 *idx = src.indices;
+        const size_t n_points = src.point_count;
+        parallel_ranges(src.index_count, 65536, [&](size_t begin, size_t end) {
+            bool b = false;
+            for (size_t i = begin; i < end; i++) {
+                const uint32_t flags = idx[i].flags;
+                const size_t last = (size_t)idx[i].first_point_index + ((flags & 0x40000000u) ? 3u : (flags & 0x80000000u) ? 2u : 1u);
+                b |= last >= n_points;
+            }
+            if (b) bad.store(true, std::memory_order_relaxed);
+        });
+        if (bad.load()) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "UploadSceneD3D11: a segment index points past the point array");
+    }
     dst.n_points = src.point_count;
     dst.n_indices = src.index_count;
     dst.points.ensure(src.point_count + 4);
@@ -367,7 +390,8 @@ void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *en
     std::vector<float4> table(n);
     for (size_t i = 0; i < n; i++) {
         const PFTextureMetadataEntry &e = entries[i];
-        if (e.color_0_combine_mode != 0 || e.filter != 0 || e.blend_mode != 0)
+        if (e.color_0_combine_mode != PF_COLOR_COMBINE_MODE_NONE || e.filter.kind != PF_FILTER_NONE ||
+            e.blend_mode != PF_BLEND_MODE_SRC_OVER)
             throw Error(PF_CUDA_ERROR_UNSUPPORTED,
                         "only solid-colour SrcOver paints are on the hot path (SURVEY.md §2 row 7)");
         // ColorU::to_f32 (color/src/lib.rs:70-73) then f16 (gpu/renderer.rs:726-729).
@@ -424,9 +448,25 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
     };
     const size_t chunks = chunk_count(P, 8192);
     std::vector<ChunkSums> sums(chunks + 1);
+    // The payload is not trusted: a stale or malformed batch (say DrawTilesD3D11 after a smaller UploadSceneD3D11)
+    // must come back as a status, not as an out-of-bounds read on the device that poisons the CUDA context.
+    // 1: segment indices not monotonic / past segment_count, 2: segments outside the uploaded scene,
+    // 3: inverted tile rect, 4: clip path index outside the clip batch.
+    std::atomic<int> malformed{0};
+    const uint32_t clip_paths = is_clip_batch ? 0u : (r->clip.valid ? r->clip.n_paths : 0u);
     parallel_chunks(P, chunks, [&](size_t chunk, size_t begin, size_t end) {
         ChunkSums sum;
         for (size_t i = begin; i < end; i++) {
+            const uint32_t seg_begin = info.dice_metadata[i].first_batch_segment_index;
+            const uint32_t seg_end = i + 1 < P ? info.dice_metadata[i + 1].first_batch_segment_index : batch.segment_count;
+            if (seg_end < seg_begin || seg_end > batch.segment_count) malformed.store(1, std::memory_order_relaxed);
+            else if ((uint64_t)info.dice_metadata[i].first_global_segment_index + (seg_end - seg_begin) > segments.n_indices)
+                malformed.store(2, std::memory_order_relaxed);
+            const PFRectI &tr = info.propagate_metadata[i].tile_rect;
+            if (tr.lower_right.x < tr.origin.x || tr.lower_right.y < tr.origin.y) malformed.store(3, std::memory_order_relaxed);
+            const uint32_t clip_index = info.propagate_metadata[i].clip_path_index;
+            if (clip_index != 0xffffffffu && clip_index >= clip_paths) malformed.store(4, std::memory_order_relaxed);
+            if (malformed.load(std::memory_order_relaxed)) continue;
             int32_t w, h;
             if (!strip_rect((uint32_t)i, w, h)) continue;
             sum.kept++;
@@ -441,6 +481,13 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
         sums[c].segments += sums[c - 1].segments;
         sums[c].tiles += sums[c - 1].tiles;
         sums[c].columns += sums[c - 1].columns;
+    }
+    switch (malformed.load()) {
+    case 1: throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "batch: first_batch_segment_index is not monotonic or exceeds segment_count");
+    case 2: throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "batch: a path's segments lie outside the uploaded scene (stale batch?)");
+    case 3: throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "batch: inverted tile rect");
+    case 4: throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "batch: clip_path_index outside the clip batch");
+    default: break;
     }
     if (sums[chunks].tiles >= 0xfffffff0ull) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "more than 2^32 bbox tiles in one batch");
     const uint32_t kept = (uint32_t)sums[chunks].kept, n_segments = (uint32_t)sums[chunks].segments,
@@ -595,7 +642,7 @@ void ensure_alpha_ids(PFCudaRenderer *r, const uint32_t *counts = nullptr, uint3
 // (eight separate clears cost more in launch gaps than in bandwidth on the small scenes).
 void carve_zeroed(PFCudaRenderer *r, size_t n_paths, size_t n_tiles, size_t n_cols, size_t n_fb) {
     auto padded = [](size_t n) { return (n + 4) & ~(size_t)3; }; // >= n + 1, keeps every array 16-byte aligned
-    const size_t total = 16 + padded(n_paths) + padded(n_tiles) + padded(n_cols) + 3 * padded(n_fb);
+    const size_t total = 16 + padded(n_paths) + padded(n_tiles) + padded(n_cols) + 4 * padded(n_fb);
     r->zeroed.ensure(total, 1.25);
     uint32_t *p = r->zeroed.ptr;
     r->counters.ptr = p, p += 16;
@@ -604,7 +651,9 @@ void carve_zeroed(PFCudaRenderer *r, size_t n_paths, size_t n_tiles, size_t n_co
     r->col_backdrop.ptr = reinterpret_cast<int32_t *>(p), p += padded(n_cols);
     r->z_buffer.ptr = reinterpret_cast<int32_t *>(p), p += padded(n_fb);
     r->fb_count.ptr = p, p += padded(n_fb);
-    r->fb_cursor.ptr = p;
+    r->fb_cursor.ptr = p, p += padded(n_fb);
+    r->fb_alpha.ptr = p;
+    r->tile_queue.ensure(n_fb + 1);
     PF_CUDA_CHECK(cudaMemsetAsync(r->zeroed.ptr, 0, total * sizeof(uint32_t), r->stream));
 }
 
@@ -730,7 +779,8 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
     launches += launch_list_count(b, r->tile_word.ptr, r->z_buffer.ptr, r->tile_fb.ptr, r->fb_count.ptr,
                                   r->tile_fill_pos.ptr, r->counters.ptr + C_VISIBLE_FILLS, r->path_live.ptr,
                                   r->debug_lists, clip_dumps ? r->tile_orig.ptr : nullptr,
-                                  compact_lists ? r->live_tiles.ptr : nullptr, live_capacity, r->counters.ptr + 15, st);
+                                  compact_lists ? r->live_tiles.ptr : nullptr, live_capacity, r->counters.ptr + 15,
+                                  r->fb_alpha.ptr, use_clip ? r->tile_clip.ptr : nullptr, st);
     launches += exclusive_scan(LoadU32{r->fb_count.ptr}, r->fb_start.ptr, n_fb, r->counters.ptr + C_ENTRIES,
                                r->scan_scratch, st);
     uint32_t entry_bound, fill_bound;
@@ -820,6 +870,9 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
     ca.clip_fills = use_clip ? r->clip.fills.ptr : nullptr;
     ca.fb_start = r->fb_start.ptr;
     ca.fb_count = r->fb_count.ptr;
+    ca.fb_alpha = r->fb_alpha.ptr;
+    ca.queue = r->tile_queue.ptr;
+    ca.queue_count = r->counters.ptr + 10;
     ca.fills = r->fills.ptr;
     ca.area_lut = r->lut_tex;
     ca.fb = fb;
@@ -1156,6 +1209,12 @@ PFCudaStatus PFCudaRendererSetOptions(PFCudaRendererRef r, const PFCudaRendererO
         verify_pending(r);
         if (!options) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null options");
         PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        // A caller-provided (or peer) destination was validated for the size it was installed with: a frame
+        // that no longer fits its rows or its height must not be composited into it.
+        if ((r->dest_external || r->n_peers > 0) &&
+            ((size_t)options->dest_size.x * 4 > r->dest_pitch || options->dest_size.y > r->dest_external_rows))
+            throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT,
+                        "dest_size exceeds the installed external destination (reset it with SetDestDevicePointer first)");
         r->options = *options;
         allocate_dest(r);
     });
@@ -1245,6 +1304,9 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
             CompositeArgs ca{};
             ca.fb_start = r->fb_start.ptr;
             ca.fb_count = r->fb_count.ptr;
+            ca.fb_alpha = r->fb_alpha.ptr;
+            ca.queue = r->tile_queue.ptr;
+            ca.queue_count = r->counters.ptr + 10;
             ca.fb = fb;
             ca.tile_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
             ca.tile_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
@@ -1297,6 +1359,7 @@ PFCudaStatus PFCudaRendererSetDestDevicePointer(PFCudaRendererRef r, uint64_t de
             r->dest_external = true;
             r->dest = reinterpret_cast<uint8_t *>((uintptr_t)device_ptr);
             r->dest_pitch = pitch;
+            r->dest_external_rows = r->options.dest_size.y; // the caller sized the buffer for the current frame
         }
     });
 }
@@ -1342,6 +1405,7 @@ PFCudaStatus PFCudaRendererSetPeerDests(PFCudaRendererRef r, const uint8_t *hand
             r->peer_dest[i] = static_cast<uint8_t *>(base) + offsets[i];
             r->n_peers = i + 1;
         }
+        if (count > 0 && !r->dest_external) r->dest_external_rows = r->options.dest_size.y;
     });
 }
 

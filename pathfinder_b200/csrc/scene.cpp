@@ -587,6 +587,9 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
             memset(&e, 0, sizeof(e));
             e.color_0_transform.matrix = PFMatrix2x2F{1, 0, 0, 1};
             e.base_color = s->paints[i];
+            e.color_0_combine_mode = PF_COLOR_COMBINE_MODE_NONE;
+            e.blend_mode = PF_BLEND_MODE_SRC_OVER;
+            e.filter.kind = PF_FILTER_NONE;
         }
         s->built_paint_key = paint_key;
     }

@@ -52,3 +52,74 @@ def assert_records_equal(a: np.ndarray, b: np.ndarray, what: str):
         bad = np.nonzero((av != bv).any(axis=1))[0]
         i = int(bad[0])
         raise AssertionError(f"{what}: {len(bad)} of {len(a)} records differ; first at {i}: {a[i]} != {b[i]}")
+
+
+def live_tile_stats(built: O.Built):
+    """Per framebuffer tile of the oracle's batch: number of list entries that survive the z-cull and the
+    total number of fills behind them (what the fused fill+tile kernel has to walk there)."""
+    tiles, z, rect = built.tiles, built.z_buffer, built.z_rect
+    w = rect[2] - rect[0]
+    inside = ((tiles["tile_x"] >= rect[0]) & (tiles["tile_x"] < rect[2]) &
+              (tiles["tile_y"] >= rect[1]) & (tiles["tile_y"] < rect[3]))
+    t = tiles[inside]
+    fb = (t["tile_y"].astype(np.int64) - rect[1]) * w + (t["tile_x"].astype(np.int64) - rect[0])
+    live = t["path_id"].astype(np.int64) >= z.reshape(-1)[fb]
+    t, fb = t[live], fb[live]
+    entries = np.bincount(fb, minlength=z.size)
+    per_alpha = np.bincount(built.fills["link"], minlength=built.alpha_tile_count)
+    alpha = t["alpha_tile_id"] != 0xFFFFFFFF
+    per_tile = np.zeros(len(t), np.int64)
+    per_tile[alpha] = per_alpha[t["alpha_tile_id"][alpha]]
+    fills = np.bincount(fb, weights=per_tile, minlength=z.size).astype(np.int64)
+    deepest_single = np.zeros(z.size, np.int64)
+    np.maximum.at(deepest_single, fb, per_tile)
+    return entries.reshape(z.shape), fills.reshape(z.shape), deepest_single.reshape(z.shape)
+
+
+def interesting_crops(built: O.Built, frame_size, crop=512, n_random=5, seed=1):
+    """Crop origins (pixels) for comparing a large frame with the oracle: around the framebuffer tile with the
+    longest list, the one with the most fills, the one holding the alpha tile with the most fills, plus a few
+    seeded random positions."""
+    entries, fills, single = live_tile_stats(built)
+    W, H = frame_size
+    origins = []
+    for grid in (entries, fills, single):
+        ty, tx = np.unravel_index(int(grid.argmax()), grid.shape)
+        origins.append((int(tx) * 16 + 8 - crop // 2, int(ty) * 16 + 8 - crop // 2))
+    rng = np.random.default_rng(seed)
+    for _ in range(n_random):
+        origins.append((int(rng.integers(0, max(1, W - crop))), int(rng.integers(0, max(1, H - crop)))))
+    clamp = lambda v, hi: max(0, min(v, hi))
+    return [(clamp(x, max(0, W - crop)), clamp(y, max(0, H - crop))) for x, y in origins]
+
+
+def assert_crops_match(built: O.Built, img: np.ndarray, area_lut, crops, crop=512, background=(0, 0, 0, 0), tol=1):
+    """img (H x W x 4, RGBA8) against the oracle's composite on the given crops, within tol/255."""
+    H_, W_ = img.shape[:2]
+    for x0, y0 in crops:
+        w, h = min(crop, W_ - x0), min(crop, H_ - y0)
+        ref = built.render_crop(area_lut, (W_, H_), (x0, y0), (w, h), background=background)
+        diff = np.abs(img[y0:y0 + h, x0:x0 + w].astype(np.int32) - ref.astype(np.int32))
+        assert diff.max() <= tol, (f"crop at ({x0}, {y0}): max RGBA diff {diff.max()} at "
+                                   f"{np.unravel_index(diff.argmax(), diff.shape)}")
+
+
+def assert_lines_match(renderer, built: O.Built, n_paths: int):
+    """Flattened lines, bit for bit and per path. The D3D11 builder drops paths whose tile rect is empty, the CPU
+    tiler still flattens them: every group of GPU lines (one per kept path, in path order) must equal the oracle's
+    lines of a distinct path, in order, and exactly path_count paths must be matched."""
+    lines, paths = renderer.debug_lines()
+    assert len(lines) == len(paths)
+    starts = np.flatnonzero(np.r_[True, paths[1:] != paths[:-1]]) if len(paths) else np.zeros(0, np.int64)
+    ends = np.r_[starts[1:], len(paths)]
+    assert np.all(np.diff(paths[starts].astype(np.int64)) > 0), "lines are not grouped by ascending path"
+    g = 0
+    for p in range(n_paths):
+        if g == len(starts):
+            break
+        ref = built.path_lines(p)
+        mine = lines[starts[g]:ends[g]]
+        if len(ref) == len(mine) and ref.view(np.uint32).tobytes() == mine.view(np.uint32).tobytes():
+            g += 1
+    assert g == len(starts), f"flattened lines differ: GPU path group {g} of {len(starts)} matches no oracle path"
+    # (a kept path always has at least one line: closed contours, builder.rs:835)

@@ -57,20 +57,81 @@ def test_record_layouts():
     assert api.FILL_DTYPE.itemsize == 12 and api.TILE_DTYPE.itemsize == 16
 
 
+def _root():
+    import os
+    return os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
 def test_rust_bindings_agree_with_the_header():
-    """integration/pathfinder_cuda/src/ffi.rs (source only) uses the header's command kinds and declares only
-    entry points the header declares."""
+    """integration/pathfinder_cuda/src/ffi.rs (source only) uses the header's command kinds, blend / combine /
+    filter constants, and declares only entry points the header declares."""
     import os
     import re
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    root = _root()
     header = open(os.path.join(root, "include", "pf_cuda.h")).read()
     ffi = open(os.path.join(root, "integration", "pathfinder_cuda", "src", "ffi.rs")).read()
     kinds = {m.group(1): int(m.group(2)) for m in re.finditer(r"PF_RENDER_COMMAND_(\w+) = (\d+)", header)}
-    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"pub const (\w+): u32 = (\d+);", ffi)}
-    assert len(kinds) == 14 and consts == kinds
+    consts = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"pub const (\w+): u32 = (\w+);", ffi)}
+    assert len(kinds) == 14
+    for name, value in kinds.items():
+        assert consts.get(name) == value, name
+    # every PF_BLEND_MODE_* / PF_COLOR_COMBINE_MODE_* / PF_FILTER_* of the header has the same value in ffi.rs
+    defines = {m.group(1): int(m.group(2), 0) for m in
+               re.finditer(r"#define PF_((?:BLEND_MODE|COLOR_COMBINE_MODE|FILTER)_\w+) (\w+)", header)}
+    assert len([k for k in defines if k.startswith("BLEND_MODE_")]) == 27
+    for name, value in defines.items():
+        assert consts.get(name) == value, name
     declared = set(re.findall(r"\b(PF[A-Z]\w+)\s*\(", header))
     for fn in re.findall(r"pub fn (PF\w+)\(", ffi):
         assert fn in declared, fn
     # the extension fields are present on both sides
     for field in ("content_key", "payload_persists", "has_clipped_path_info"):
         assert field in header and field in ffi
+
+
+def test_rust_bindings_pass_only_verified_pod_records_by_pointer():
+    """The glue may hand a `Vec<T>` of a *reference* type to C by pointer only when T is one of the `#[repr(C)]`
+    plain-old-data records whose layout pf_cuda.h mirrors (sizes pinned in test_record_layouts and by the `const _`
+    assertions in ffi.rs). Everything else — TextureMetadataEntry above all: its Transform2F, Filter and BlendMode
+    have no C layout — must be converted into a struct ffi.rs itself declares."""
+    import os
+    import re
+    root = _root()
+    ffi = open(os.path.join(root, "integration", "pathfinder_cuda", "src", "ffi.rs")).read()
+    lib = open(os.path.join(root, "integration", "pathfinder_cuda", "src", "lib.rs")).read()
+    allowed = {"Vector2F", "SegmentIndicesD3D11", "PropagateMetadataD3D11", "DiceMetadataD3D11", "TilePathInfoD3D11",
+               "BackdropInfoD3D11", "RectF"}
+    own = set(re.findall(r"pub (?:struct|union) (\w+)", ffi))
+    primitives = {"u8", "c_char", "c_void", "f32", "u32", "i32", "u64"}
+    for type_name in re.findall(r"\*(?:const|mut) (\w+)", ffi):
+        assert type_name in allowed | own | primitives, f"ffi.rs passes {type_name} by pointer"
+    # each allowed reference record has a size assertion
+    for type_name in allowed - {"RectF"}:
+        assert re.search(r"size_of::<%s>\(\) == \d+" % type_name, ffi), type_name
+    assert "TextureMetadataEntry" not in re.findall(r"\*const (\w+)", ffi)
+    # the conversion exists and is used for UploadTextureMetadata
+    assert "fn texture_metadata_entry(" in lib and "map(texture_metadata_entry)" in lib
+    assert "entries.as_ptr()" not in lib
+    # RendererMode.level is one byte on both sides
+    assert re.search(r"pub struct PFRendererMode \{\s*pub level: u8", ffi)
+
+
+def test_build_rs_compiles_what_the_makefile_compiles():
+    """build.rs (source only) and INTEGRATION.md name exactly the sources csrc/Makefile builds — a stale list links
+    a library with unresolved symbols."""
+    import os
+    import re
+    root = _root()
+    makefile = open(os.path.join(root, "pathfinder_b200", "csrc", "Makefile")).read()
+    srcs = set(re.search(r"^SRCS := (.*)$", makefile, re.M).group(1).split())
+    assert srcs == {f for f in os.listdir(os.path.join(root, "pathfinder_b200", "csrc")) if f.endswith((".cu", ".cpp"))}
+    build_rs = open(os.path.join(root, "integration", "pathfinder_cuda", "build.rs")).read()
+    exact = set(re.findall(r'"(\w+\.(?:cu|cpp))"', re.search(r"EXACT_SOURCES[^;]*;", build_rs).group(0)))
+    contracted = set(re.findall(r'"(\w+\.(?:cu|cpp))"', re.search(r"CONTRACTED_SOURCES[^;]*;", build_rs).group(0)))
+    assert exact | contracted == srcs and not (exact & contracted)
+    # the one file the Makefile compiles without -fmad=false is the one build.rs compiles that way
+    assert contracted == set(re.findall(r"^\$\(OBJ\)/(\w+)\.o: \w+\.cu", makefile, re.M) and ["composite.cu"])
+    assert "$(OBJ)/composite.o: composite.cu" in makefile
+    integration_md = open(os.path.join(root, "INTEGRATION.md")).read()
+    for f in srcs:
+        assert f in integration_md, f"INTEGRATION.md does not mention {f}"

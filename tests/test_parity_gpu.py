@@ -23,12 +23,8 @@ def check_scene(flat, xf, area_lut, size=None, background=(1.0, 1.0, 1.0, 1.0), 
     h = int(size[1]) if size else int(flat.view_box[3])
 
     if check_lines:
-        lines, _paths = r.debug_lines()
-        ref = np.concatenate([built.path_lines(p) for p in range(flat.n_paths)] or [np.zeros((0, 4), np.float32)])
-        # Paths outside the view box are skipped by the D3D11 builder but still flattened by the
-        # CPU tiler; compare only when every path was kept.
-        if len(lines) == len(ref):
-            assert lines.view(np.uint32).tobytes() == ref.view(np.uint32).tobytes(), "flattened lines differ"
+        # (paths outside the view box are skipped by the D3D11 builder but still flattened by the CPU tiler)
+        H.assert_lines_match(r, built, flat.n_paths)
     H.assert_records_equal(r.debug_fills(), built.fills, "fills")
     H.assert_records_equal(r.debug_tiles(), built.tiles, "tiles")
     z, rect = r.debug_z_buffer()
@@ -123,6 +119,48 @@ def test_offscreen_and_clipped_paths(area_lut):
     b.close()
     b.end_path((0, 0, 255, 255))
     check_scene(b.finish("offscreen"), None, area_lut, check_lines=False)
+
+
+def _star(b, cx, cy, r_out, r_in, points):
+    """A closed star polygon with 2 * points short edges around (cx, cy)."""
+    for i in range(2 * points):
+        a = np.pi * i / points
+        r = r_out if i % 2 == 0 else r_in
+        x, y = cx + r * np.cos(a), cy + r * np.sin(a)
+        b.move_to(x, y) if i == 0 else b.line_to(x, y)
+    b.close()
+
+
+@pytest.mark.parametrize("layers", [40, 200])
+def test_deep_lists_and_dense_tiles(area_lut, layers):
+    """The paths the headline scenes never reach (random100k@8192 tops out at 27 entries and 18 fills per
+    tile): lists deeper than the in-shared-memory sort (32 entries) and than the round-1 cap (128), alpha tiles
+    with more fills than one cooperative batch (32) and than the fast integer-to-float conversion covers (127),
+    under both fill rules, and translucent solid layers interleaved with masks."""
+    b = SceneBuilderPy((0, 0, 96, 64))
+    rng = np.random.default_rng(layers)
+    for i in range(layers):
+        # translucent layers over the same few tiles: half of them whole-tile rectangles (solid entries), half
+        # small shapes with edges (entries with fills), interleaved
+        color = tuple(int(v) for v in rng.integers(0, 256, 3)) + (int(rng.integers(8, 64)),)
+        if i % 2 == 0:
+            x0, y0 = float(rng.uniform(-8, 20)), float(rng.uniform(-8, 12))
+            b.move_to(x0, y0), b.line_to(x0 + 70, y0), b.line_to(x0 + 70, y0 + 50), b.line_to(x0, y0 + 50)
+            b.close()
+        else:
+            cx, cy = float(rng.uniform(20, 70)), float(rng.uniform(16, 48))
+            _star(b, cx, cy, float(rng.uniform(6, 20)), float(rng.uniform(2, 6)), int(rng.integers(3, 9)))
+        b.end_path(color, FILL_RULE_EVEN_ODD if i % 3 == 0 else FILL_RULE_WINDING)
+    # dense alpha tiles: stars with 40 and 180 short edges inside one 16-px tile
+    _star(b, 40.0, 24.0, 7.5, 5.0, 20)
+    b.end_path((10, 10, 200, 200), FILL_RULE_WINDING)
+    _star(b, 56.0, 40.0, 7.8, 6.0, 90)
+    b.end_path((200, 10, 10, 180), FILL_RULE_EVEN_ODD)
+    flat = b.finish("deep")
+    img, built = check_scene(flat, None, area_lut, background=(1.0, 1.0, 1.0, 1.0))
+    entries, fills, single = H.live_tile_stats(built)
+    assert entries.max() > (128 if layers >= 200 else 32), entries.max()
+    assert single.max() > 127, single.max()
 
 
 @pytest.mark.parametrize("size,even_odd", [(256, False), (1024, False), (1024, True)])
@@ -275,10 +313,12 @@ def test_full_size_tiger_4096(area_lut, even_odd):
     r2.close()
 
 
-def test_full_size_random100k_8192():
+def test_full_size_random100k_8192(area_lut):
     """configs[3]: 100k random cubic paths at 8192x8192. Fills, tiles and z-buffer bit-exact against
-    the CPU tiler; the frame is checked through size-independent properties (strips stitched =
-    full frame, production path = instrumented path, deterministic across runs)."""
+    the CPU tiler; RGBA within 1/255 of the oracle on eight 512x512 crops (around the longest list, the
+    tile with the most fills, the densest alpha tile, and seeded random positions); the whole frame through
+    size-independent properties (strips stitched = full frame, production path = instrumented path,
+    deterministic across runs)."""
     from pathfinder_b200 import api
     flat = scenes.random_paths(100000, 8192, 0x5EED0004)
     built = H.oracle_build(flat, None)
@@ -292,6 +332,8 @@ def test_full_size_random100k_8192():
     assert np.array_equal(z, built.z_buffer)
     assert s["alpha_tile_count"] == built.alpha_tile_count
     r.close()
+    H.assert_crops_match(built, img, area_lut, H.interesting_crops(built, (8192, 8192)),
+                         background=(1.0, 1.0, 1.0, 1.0), tol=RGBA_TOL)
     # production path, twice (sizing frame, then cached batch), and two strips
     rp = api.CudaRenderer((8192, 8192), background_color=(1.0, 1.0, 1.0, 1.0))
     scene = api.Scene.from_flat(flat)
@@ -309,11 +351,12 @@ def test_full_size_random100k_8192():
     rp.close()
 
 
-def test_full_size_random1m_16384():
+def test_full_size_random1m_16384(area_lut):
     """configs[4]: 1M random cubic paths at 16384x16384 (the multi-GPU configuration), on one GPU. Tiles, z-buffer
     and the fill / alpha-tile / line totals bit-exact against the CPU tiler (the 120M-record fill list itself is
-    compared at 100k paths above); the 1 GiB frame through size-independent properties: production path =
-    instrumented path, cached batch = first frame, two of the eight strips = the same rows of the full frame."""
+    compared at 100k paths above); RGBA within 1/255 of the oracle on eight 512x512 crops (deepest lists
+    included); the 1 GiB frame through size-independent properties: production path = instrumented path,
+    cached batch = first frame, two of the eight strips = the same rows of the full frame."""
     from pathfinder_b200 import api
     size = 16384
     flat = scenes.random_paths(1000000, size, 0x5EED0005)
@@ -327,6 +370,8 @@ def test_full_size_random1m_16384():
     z, _ = r.debug_z_buffer()
     assert np.array_equal(z, built.z_buffer)
     r.close()
+    H.assert_crops_match(built, img, area_lut, H.interesting_crops(built, (size, size)),
+                         background=(1.0, 1.0, 1.0, 1.0), tol=RGBA_TOL)
     del built
     rp = api.CudaRenderer((size, size), background_color=(1.0, 1.0, 1.0, 1.0))
     scene = api.Scene.from_flat(flat)

@@ -1,9 +1,7 @@
-"""GPU parity checks for pieces of the 'next' rows that landed after the round's GPU budget was
-spent: the text-page scene and host-side dilation. Their host halves are pinned on the CPU (tests/test_oracle.py,
-tests/test_dilate_host.py) and the device sees nothing new — more small paths, or already-prepared points under an
-identity transform — but they have NOT run on a B200 yet, so they are marked xfail(strict=False): a pass shows up as
-XPASS, a failure does not hide the verified suite — and the file is named to be collected last, so that even a fault
-that poisoned the CUDA context could not reach the verified tests. Drop the marker (and the zz) once seen green."""
+"""GPU parity for the text-page scene (BASELINE.json configs[2], outlines) and host-side dilation (stem
+darkening): more small paths, or already-prepared points under an identity transform, through the same device
+pipeline. Their host halves are pinned on the CPU (tests/test_oracle.py, tests/test_dilate_host.py). First seen
+green on a B200 at the end of round 1 (as XPASS) and again at the start of round 2."""
 import numpy as np
 import pytest
 
@@ -11,8 +9,7 @@ from pathfinder_b200 import scenes
 from tests import helpers as H
 from tests.test_parity_gpu import COVERAGE_TOL, RGBA_TOL
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="not yet run on a GPU (landed after the round's GPU budget was spent)", strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 def check(flat, xf, area_lut, dilation=(0.0, 0.0)):
@@ -20,10 +17,7 @@ def check(flat, xf, area_lut, dilation=(0.0, 0.0)):
     background = (1.0, 1.0, 1.0, 1.0)
     built = H.oracle_build(flat, xf, keep_lines=True, dilation=dilation)
     r, img = H.cuda_render(flat, xf, background=background, dilation=dilation)
-    lines, _paths = r.debug_lines()
-    ref = np.concatenate([built.path_lines(p) for p in range(flat.n_paths)])
-    if len(lines) == len(ref):  # (paths outside the view box are skipped by the D3D11 builder)
-        assert lines.view(np.uint32).tobytes() == ref.view(np.uint32).tobytes(), "flattened lines differ"
+    H.assert_lines_match(r, built, flat.n_paths)
     H.assert_records_equal(r.debug_fills(), built.fills, "fills")
     H.assert_records_equal(r.debug_tiles(), built.tiles, "tiles")
     z, rect = r.debug_z_buffer()
