@@ -12,7 +12,9 @@ bin (one process_line_segment call, renderer/src/tiler.rs:177). `value` = segmen
 the step / device time with the scenes resident in HBM; `e2e` = the same through the public API
 with the scene re-uploaded from host memory and the frame read back to pinned host memory every
 frame. With N > 1 GPUs every frame is partitioned by horizontal tile strips (one rank per GPU) and
-assembled with one NCCL all-gather, so scaling is strong (fixed work per step).
+assembled on every rank by the library itself (PFCudaRendererGatherFrame: ncclAllGather on the renderer's
+gather stream), so scaling is strong (fixed work per step). torch.distributed only boots the ranks, ships
+the gather id and reduces the timings.
 """
 from __future__ import annotations
 
@@ -184,21 +186,22 @@ def run_reference(args):
 
 
 def ncu_dram_bytes(world: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_composite launch on random100k@8192 from the committed
-    `ncu --set full` summary (profiles/r*_composite_ncu.md, newest round); only meaningful for the whole frame (N = 1)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fill + tile stage (k_tile_solid + k_tile_alpha, one frame of
+    random100k@8192) from the committed `ncu --set full` capture (profiles/r*_fill_tile_traffic.json, newest round).
+    Only meaningful for the whole frame (N = 1), and only while composite.cu is still the file that was profiled:
+    the capture records its SHA-256 and a stale capture reads as null."""
     import glob
-    import re
+    import hashlib
     if world != 1:
         return None
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_composite_ncu.md")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_fill_tile_traffic.json")))
     if not files:
         return None
-    text = open(files[-1]).read().split("## tiger4k")[0]
-    got = {k: re.search(r"`%s` \| (\w+) \| ([0-9.]+)" % re.escape(k), text) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")}
-    if not all(got.values()):
+    rec = json.load(open(files[-1]))
+    src = os.path.join(ROOT, "pathfinder_b200", "csrc", "composite.cu")
+    if not os.path.exists(src) or hashlib.sha256(open(src, "rb").read()).hexdigest() != rec.get("composite_cu_sha256"):
         return None
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    return int(sum(float(m.group(2)) * scale.get(m.group(1), 1.0) for m in got.values()))
+    return int(rec["dram_bytes_per_frame"])
 
 
 def main():
@@ -210,9 +213,9 @@ def main():
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOAD_NAMES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="nccl", choices=["peer", "nccl"],
-                    help="N > 1: 'nccl' = all_gather_into_tensor on NCCL's stream, overlapped with the next frame; "
-                         "'peer' = the fused fill+tile kernel stores every tile into all peers' frames over NVLink "
-                         "(IPC-mapped buffers) + one barrier (measured slower at 8 GPUs: 64-byte remote stores)")
+                    help="N > 1: 'nccl' = PFCudaRendererGatherFrame (ncclAllGather issued by the library on the renderer's "
+                         "gather stream, overlapped with the next frame); 'peer' = the fill+tile kernels store every tile "
+                         "into all peers' frames over NVLink (IPC-mapped buffers) + one barrier")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3
@@ -270,10 +273,7 @@ def main():
     for name, flat, xf, size in scene_list:
         f = Frame()
         f.name, f.flat, f.size = name, flat, size
-        tile_rows = (size + 15) // 16
-        assert tile_rows % world == 0, "tile rows must divide evenly across ranks"
-        rows_per = tile_rows // world
-        f.y0, f.y1 = rank * rows_per, (rank + 1) * rows_per
+        f.y0, f.y1 = api.strip_of_rank((size + 15) // 16, rank, world)
         f.full = torch.empty((size, size, 4), dtype=torch.uint8, device="cuda")
         f.renderer = api.CudaRenderer((size, size), background_color=(1.0, 1.0, 1.0, 1.0), device_ordinal=local_rank)
         f.stream = torch.cuda.Stream()
@@ -289,8 +289,14 @@ def main():
         # the next use of the renderer instead of stalling the host at the end of every batch.
         f.renderer.set_deferred_verification(True)
         if world > 1:
-            f.renderer.set_strip(f.y0, f.y1)
-            f.strip_view = f.full[f.y0 * 16:f.y1 * 16]
+            if args.gather == "nccl":
+                # The library assembles the frame: rank 0 creates the group id, torch.distributed only ships it.
+                box = [api.gather_create_id() if rank == 0 else None]
+                dist.broadcast_object_list(box, src=0)
+                f.renderer.gather_init(box[0], rank, world)  # also sets this rank's strip
+            else:
+                f.renderer.set_strip(f.y0, f.y1)
+            f.strip_view = f.full[f.y0 * 16:min(f.y1 * 16, size)]
         f.host = torch.empty((size, size, 4), dtype=torch.uint8, pin_memory=True) if (rank == 0 and world == 1) else None
         f.host_shared = None
         if world > 1:
@@ -305,7 +311,6 @@ def main():
             rc = torch.cuda.cudart().cudaHostRegister(f.host_shared.data_ptr(), size * size * 4, 0)
             f.host_registered = int(rc[0] if isinstance(rc, tuple) else rc) == 0  # else: pageable copies (slower)
         f.copied = None
-        f.gather = None
         f.peer = False
         if world > 1 and args.gather == "peer":
             # Exchange CUDA IPC handles of the frame buffers; every rank then writes its strip into all copies.
@@ -329,16 +334,14 @@ def main():
             f.scene.set_view_box(f.flat.view_box)  # bumps the epoch: the scene is re-uploaded from host memory
             if f.copied is not None:
                 f.stream.wait_event(f.copied)  # the previous read-back of this frame buffer must be done
-        if f.gather is not None:
-            f.gather.wait()  # the previous all-gather of this frame buffer must be done before it is redrawn
-            f.gather = None
         f.scene.build_and_render(f.renderer, f.options)
         if dist is not None and not e2e:
             if f.peer:
                 dist.all_reduce(flag)  # barrier on the stream: every rank's strip has landed in every frame copy
             else:
-                # Asynchronous: runs on NCCL's stream after this frame's kernels, while the next frame renders.
-                f.gather = dist.all_gather_into_tensor(f.full.view(-1), f.strip_view.reshape(-1), async_op=True)
+                # Asynchronous: on the renderer's gather stream after this frame's kernels, while the next frame's
+                # stages run; the library orders the next compositing of this buffer after it.
+                f.renderer.gather_frame()
         if e2e and dist is not None:
             # Every rank reads its own strip back into the shared host frame.
             done = torch.cuda.Event()
@@ -365,10 +368,8 @@ def main():
 
     def join():  # ... and `stream` (the end event) waits for all of them, frame assembly included
         for f in frames:
-            if f.gather is not None:
-                with torch.cuda.stream(f.stream):
-                    f.gather.wait()
-                f.gather = None
+            if dist is not None and not f.peer:
+                f.renderer.gather_wait()  # the frame's stream waits for its last gather
             stream.wait_stream(f.stream)
 
     def step(e2e: bool):
@@ -436,7 +437,32 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_s = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+
+    # "ms/frame" proper: every scene alone on the GPU, K frames back to back on its stream (no other scene's
+    # kernels in the shadow), frame assembly included; CUDA events around the K frames, max over ranks. The stage
+    # times of the same frames feed the roofline: a kernel timed alone, not under three-way overlap.
+    isolated_ms, isolated_stage = {}, {}
     for f in frames:
+        f.renderer.set_timing_enabled(False)
+        f.renderer.set_timing_enabled(True)  # resets the accumulated stage times
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        f.stream.wait_stream(stream)
+        for _ in range(args.steps):
+            render_frame(f, False)
+        if dist is not None and not f.peer:
+            f.renderer.gather_wait()
+        stream.wait_stream(f.stream)
+        s1.record(stream)
+        barrier()
+        totals, batches = f.renderer.accumulated_times()
+        assert batches == args.steps, (batches, args.steps)
+        ms = torch.tensor([s0.elapsed_time(s1) / args.steps], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        isolated_ms[f.name] = float(ms.item())
+        isolated_stage[f.name] = {k: v / args.steps for k, v in totals.items()}
         f.renderer.set_timing_enabled(False)
 
     # End to end: scene upload from host memory + render + read-back of the frame, every frame.
@@ -471,8 +497,10 @@ def main():
     fills_per_step = sum(int(f.full_stats.get("fill_count", 0)) for f in frames)
     e2e_value = seg_per_step * e2e_steps / e2e_s / 1e9
 
-    # Roofline of the dominant kernel (fused fill + tile) on the largest scene: algorithmic bytes
-    # = 8 B per visible fill read + 32 B per tile-list entry + 4 B per pixel written.
+    # Roofline of the dominant stage (fill + tile: k_tile_solid + k_tile_alpha, launched back to back) on the largest
+    # scene. Algorithmic bytes per SURVEY.md §8(d) "fused fill+composite": 12 B per visible fill (the reference's
+    # Fill record) + 16 B per tile-list entry (TileD3D11) + 4 B per pixel written. (What this implementation
+    # actually moves is 8 B per fill and 32 B per entry: `implementation_bytes_per_launch`.)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs"
@@ -481,14 +509,18 @@ def main():
     big = max(frames, key=lambda f: f.size)
     bs = per_scene[big.name]
     rows = (big.y1 - big.y0) * 16
-    # Only the fills of tiles that survive the z-cull are ever stored or read (8 B each).
-    algo_bytes = 8 * bs["visible_fill_count"] + 32 * bs["tile_list_entry_count"] + 4 * big.size * rows
-    kernel_ms = stage_acc[big.name]["fill_tile_ms"] / args.steps
+    # Only the fills of tiles that survive the z-cull are ever stored or read.
+    algo_bytes = 12 * bs["visible_fill_count"] + 16 * bs["tile_list_entry_count"] + 4 * big.size * rows
+    impl_bytes = 8 * bs["visible_fill_count"] + 32 * bs["tile_list_entry_count"] + 4 * big.size * rows
+    kernel_ms = isolated_stage[big.name]["fill_tile_ms"]
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "k_composite (fused fill + tile)", "scene": big.name,
+    roofline = {"bound": "hbm", "kernel": "fill + tile: k_tile_solid + k_tile_alpha (one stage, two launches)", "scene": big.name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": ncu_dram_bytes(world),
-                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms, "peak_source": peak_src}
+                "algorithmic_bytes_per_launch": algo_bytes, "implementation_bytes_per_launch": impl_bytes,
+                "kernel_ms": kernel_ms, "kernel_ms_in_overlapped_step": stage_acc[big.name]["fill_tile_ms"] / args.steps,
+                "timing": "CUDA events around the stage on the renderer's stream, the scene rendering alone (isolated phase)",
+                "peak_source": peak_src}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -519,11 +551,13 @@ def main():
                    "input_gsegments_per_s": inputs_per_step * args.steps / dev_s / 1e9,
                    "gfills_per_s": fills_per_step * args.steps / dev_s / 1e9,
                    "parallelism": f"tile-strip x{world}" + ((" + fused peer-store gather (NVLink P2P) + barrier" if args.gather == "peer"
-                                                             else " + NCCL all-gather overlapped with the next frame") if world > 1 else ""),
+                                                             else " + ncclAllGather issued by the library (PFCudaRendererGatherFrame), overlapped with the next frame") if world > 1 else ""),
                    "l2": "inputs larger than L2: a step touches > 1 GB of stage buffers and frames",
                    "streams": "the frames of a step are independent scenes and render concurrently on one CUDA stream each "
                               "(forked from / joined to the timing stream); no host wait inside the timed region "
                               "(deferred verification); ms_per_frame / stage_ms are per-stream event times and overlap",
+                   "ms_per_frame_isolated": isolated_ms,
+                   "stage_ms_isolated": isolated_stage,
                    "ms_per_frame": {f.name: stage_acc[f.name]["total_ms"] / args.steps for f in frames},
                    "stage_ms": {f.name: {k: v / args.steps for k, v in stage_acc[f.name].items()} for f in frames}},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "assembly": e2e_assembly,

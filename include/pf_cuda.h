@@ -352,6 +352,35 @@ PFCudaStatus PFCudaRendererSynchronize(PFCudaRendererRef renderer);
  * tile_y0 = tile_y1 = 0 restores the full frame. */
 PFCudaStatus PFCudaRendererSetStrip(PFCudaRendererRef renderer, int32_t tile_y0, int32_t tile_y1);
 
+/* ---- Frame assembly across GPUs (SURVEY.md §8e "distributed communication backend"; new work: the reference
+ * has no multi-GPU path). One process per GPU; every rank renders its strip into its own copy of the frame and the
+ * copies are completed over NCCL / NVLink from inside the library, on a stream of the renderer's own that is
+ * ordered after the frame's compositing — the next frame's earlier stages overlap it. NCCL is resolved at run
+ * time (libnccl.so.2), so the library loads where it is absent; the calls then return PF_CUDA_ERROR_UNSUPPORTED. */
+#define PF_CUDA_GATHER_ID_BYTES 128 /* ncclUniqueId */
+typedef struct PFCudaGatherId {
+    uint8_t bytes[PF_CUDA_GATHER_ID_BYTES];
+} PFCudaGatherId;
+/* The tile rows [*tile_y0, *tile_y1) rank `rank` of `world_size` owns out of `tile_rows`: as equal as whole rows allow. */
+void PFCudaStripOfRank(int32_t tile_rows, int32_t rank, int32_t world_size, int32_t *tile_y0, int32_t *tile_y1);
+/* On one rank; ship the bytes to the others through any host channel (ncclGetUniqueId). */
+PFCudaStatus PFCudaGatherCreateId(PFCudaGatherId *id_out);
+/* Collective (every rank calls it with the same id): joins the renderer to the group (ncclCommInitRank) and sets its
+ * strip to PFCudaStripOfRank of the destination's tile rows. The destination must have contiguous rows (pitch = 4 * width). */
+PFCudaStatus PFCudaRendererGatherInit(PFCudaRendererRef renderer, const PFCudaGatherId *id, int32_t rank,
+                                      int32_t world_size);
+/* Collective, asynchronous: after the frame just rendered, completes every rank's copy of the frame with the other
+ * ranks' strips (ncclAllGather in place when the strips are equal, grouped ncclBroadcast otherwise). ReadPixels,
+ * Synchronize and the next frame's compositing wait for it. With deferred verification a frame that overflowed a
+ * stage bound is repaired at the next use of the renderer, after its (stale) strip has been gathered: render with
+ * verification on when every gathered frame must be final. */
+PFCudaStatus PFCudaRendererGatherFrame(PFCudaRendererRef renderer);
+/* Orders the renderer's stream after the gather in flight, without a host wait (for callers that continue on that
+ * stream, e.g. to time the assembled frame or to hand it to another consumer). */
+PFCudaStatus PFCudaRendererGatherWait(PFCudaRendererRef renderer);
+/* Leaves the group (ncclCommDestroy) and restores the full-frame strip. */
+PFCudaStatus PFCudaRendererGatherDestroy(PFCudaRendererRef renderer);
+
 /* scene.view_box() as process_line_segment sees it (renderer/src/tiler.rs:194-200): segments are
  * clipped to [min_x, max_x] x (-inf, max_y]. The RenderCommand stream does not carry it; the Rust
  * glue sets it from Scene::view_box() before begin_scene. NULL = the destination rect (what the

@@ -223,6 +223,12 @@ SIGNATURES = {
     "PFCudaRendererSynchronize": (C.c_int32, [C.c_void_p]),
     "PFCudaRendererSetDeferredVerification": (C.c_int32, [C.c_void_p, C.c_int32]),
     "PFCudaRendererSetStrip": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
+    "PFCudaStripOfRank": (None, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "PFCudaGatherCreateId": (C.c_int32, [C.c_void_p]),
+    "PFCudaRendererGatherInit": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "PFCudaRendererGatherFrame": (C.c_int32, [C.c_void_p]),
+    "PFCudaRendererGatherWait": (C.c_int32, [C.c_void_p]),
+    "PFCudaRendererGatherDestroy": (C.c_int32, [C.c_void_p]),
     "PFCudaRendererSetViewBox": (C.c_int32, [C.c_void_p, C.POINTER(PFRectF)]),
     "PFCudaRendererGetStats": (C.c_int32, [C.c_void_p, C.POINTER(PFCudaRenderStats)]),
     "PFCudaRendererSetTimingEnabled": (C.c_int32, [C.c_void_p, C.c_int32]),

@@ -336,6 +336,20 @@ def ipc_export(device_ptr: int):
     return bytes(h), int(off.value)
 
 
+def strip_of_rank(tile_rows: int, rank: int, world_size: int):
+    """Tile rows [y0, y1) of `rank` out of `world_size` (PFCudaStripOfRank: as equal as whole rows allow)."""
+    y0, y1 = C.c_int32(), C.c_int32()
+    L.lib().PFCudaStripOfRank(tile_rows, rank, world_size, C.byref(y0), C.byref(y1))
+    return int(y0.value), int(y1.value)
+
+
+def gather_create_id() -> bytes:
+    """The 128-byte id (ncclUniqueId) rank 0 creates and ships to the other ranks before gather_init."""
+    buf = (C.c_uint8 * 128)()
+    L.check(L.lib().PFCudaGatherCreateId(buf))
+    return bytes(buf)
+
+
 class CudaRenderer:
     """Renderer<CudaDevice> at RendererLevel::D3D11."""
 
@@ -382,6 +396,23 @@ class CudaRenderer:
 
     def set_strip(self, tile_y0: int, tile_y1: int):
         L.check(L.lib().PFCudaRendererSetStrip(self._h, tile_y0, tile_y1))
+
+    # -- frame assembly across GPUs (one process per GPU; NCCL inside the library) ---------------
+    def gather_init(self, gather_id: bytes, rank: int, world_size: int):
+        """Collective. Joins the group and sets this renderer's strip to its share of the tile rows."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(gather_id))
+        L.check(L.lib().PFCudaRendererGatherInit(self._h, buf, rank, world_size))
+
+    def gather_frame(self):
+        """Collective, asynchronous: completes this rank's copy of the frame with the other ranks' strips."""
+        L.check(L.lib().PFCudaRendererGatherFrame(self._h))
+
+    def gather_wait(self):
+        """Orders the renderer's stream after the gather in flight (no host wait)."""
+        L.check(L.lib().PFCudaRendererGatherWait(self._h))
+
+    def gather_destroy(self):
+        L.check(L.lib().PFCudaRendererGatherDestroy(self._h))
 
     def set_stream(self, cuda_stream: int):
         L.check(L.lib().PFCudaRendererSetStream(self._h, cuda_stream))

@@ -15,6 +15,7 @@
 //   * clip paths (one level) are a second batch through the same stages, resolved in propagate.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <dlfcn.h>
 
 #include <atomic>
 #include <chrono>
@@ -142,6 +143,14 @@ struct PFCudaRenderer {
     uint8_t *peer_dest[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void *peer_base[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int n_peers = 0;
+
+    // Frame assembly across GPUs (PFCudaRendererGather*): NCCL communicator, its stream, and the two events that
+    // order it after this frame's compositing and the next frame's compositing after it.
+    void *gather_comm = nullptr; // ncclComm_t
+    int gather_rank = 0, gather_world = 0;
+    cudaStream_t gather_stream = nullptr;
+    cudaEvent_t gather_ready = nullptr, gather_done = nullptr;
+    bool gather_in_flight = false;
 
     // Per-batch device buffers.
     DeviceBuffer<uint8_t> batch_meta; // PathInfo[P] + 3 search arrays
@@ -308,6 +317,14 @@ void fill_destinations(const PFCudaRenderer *r, CompositeArgs &ca) {
         bits |= (uintptr_t)r->peer_dest[i];
     }
     ca.dest_align_mask = (uint32_t)(bits & 0xffffffffu);
+}
+
+// The previous frame may still be on its way to the other ranks from the destination buffer (PFCudaRendererGatherFrame):
+// whatever writes the destination next is ordered after it.
+void wait_for_gather(PFCudaRenderer *r, cudaStream_t st) {
+    if (!r->gather_in_flight) return;
+    PF_CUDA_CHECK(cudaStreamWaitEvent(st, r->gather_done, 0));
+    r->gather_in_flight = false;
 }
 
 float4 clear_color(const PFCudaRenderer *r) {
@@ -886,6 +903,7 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
     ca.clear_color = clear_color(r);
     ca.load_dest = r->batches_drawn > 0;
     ca.work_counter = r->counters.ptr + 12;
+    wait_for_gather(r, st);
     launches += launch_composite(ca, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[7], st));
 
@@ -1101,6 +1119,81 @@ void close_peers(PFCudaRenderer *r) {
     r->n_peers = 0;
 }
 
+
+// ---- NCCL, resolved at run time: the library must load (and every single-GPU path work) where libnccl is absent.
+struct Nccl {
+    typedef int (*GetUniqueIdFn)(void *);
+    typedef int (*CommInitRankFn)(void **, int, PFCudaGatherId, int); // ncclUniqueId is 128 bytes passed by value
+    typedef int (*CommDestroyFn)(void *);
+    typedef int (*AllGatherFn)(const void *, void *, size_t, int, void *, cudaStream_t);
+    typedef int (*BroadcastFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    typedef int (*GroupFn)();
+    typedef const char *(*ErrorStringFn)(int);
+    GetUniqueIdFn get_unique_id = nullptr;
+    CommInitRankFn comm_init_rank = nullptr;
+    CommDestroyFn comm_destroy = nullptr;
+    AllGatherFn all_gather = nullptr;
+    BroadcastFn broadcast = nullptr;
+    GroupFn group_start = nullptr, group_end = nullptr;
+    ErrorStringFn error_string = nullptr;
+    bool ok = false;
+    static constexpr int UINT8 = 1; // ncclUint8
+
+    static const Nccl &get() {
+        static const Nccl instance = load();
+        return instance;
+    }
+    static Nccl load() {
+        Nccl n;
+        // A process that already has NCCL (PyTorch bundles its own copy) must share it: two copies of the
+        // library would each open the devices' NVLink resources.
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return n;
+        n.get_unique_id = (GetUniqueIdFn)dlsym(h, "ncclGetUniqueId");
+        n.comm_init_rank = (CommInitRankFn)dlsym(h, "ncclCommInitRank");
+        n.comm_destroy = (CommDestroyFn)dlsym(h, "ncclCommDestroy");
+        n.all_gather = (AllGatherFn)dlsym(h, "ncclAllGather");
+        n.broadcast = (BroadcastFn)dlsym(h, "ncclBroadcast");
+        n.group_start = (GroupFn)dlsym(h, "ncclGroupStart");
+        n.group_end = (GroupFn)dlsym(h, "ncclGroupEnd");
+        n.error_string = (ErrorStringFn)dlsym(h, "ncclGetErrorString");
+        n.ok = n.get_unique_id && n.comm_init_rank && n.comm_destroy && n.all_gather && n.broadcast && n.group_start &&
+               n.group_end && n.error_string;
+        return n;
+    }
+    void check(int result, const char *what) const {
+        if (result != 0) throw Error(PF_CUDA_ERROR_CUDA, std::string(what) + " failed: " + error_string(result));
+    }
+};
+
+const Nccl &nccl_or_throw() {
+    const Nccl &n = Nccl::get();
+    if (!n.ok) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "libnccl.so.2 not found: frame assembly across GPUs is unavailable");
+    return n;
+}
+
+void strip_of_rank(int32_t rows, int32_t rank, int32_t world, int32_t &y0, int32_t &y1) {
+    y0 = (int32_t)((int64_t)rows * rank / world);
+    y1 = (int32_t)((int64_t)rows * (rank + 1) / world);
+}
+
+void gather_destroy(PFCudaRenderer *r) {
+    if (!r->gather_comm) return;
+    cudaStreamSynchronize(r->gather_stream);
+    Nccl::get().comm_destroy(r->gather_comm);
+    r->gather_comm = nullptr;
+    r->gather_in_flight = false;
+    cudaEventDestroy(r->gather_ready);
+    cudaEventDestroy(r->gather_done);
+    cudaStreamDestroy(r->gather_stream);
+    r->gather_stream = nullptr;
+    r->gather_ready = r->gather_done = nullptr;
+    r->gather_world = 0;
+    r->strip_y0 = r->strip_y1 = 0;
+}
+
 template <typename F>
 PFCudaStatus guarded(PFCudaRenderer *r, F &&f) {
     try {
@@ -1194,6 +1287,7 @@ void PFCudaRendererDestroy(PFCudaRendererRef r) {
     cudaSetDevice(r->ordinal);
     cudaStreamSynchronize(r->stream);
     close_peers(r);
+    gather_destroy(r);
     if (r->verify_event) cudaEventDestroy(r->verify_event);
     if (r->lut_tex) cudaDestroyTextureObject(r->lut_tex);
     if (r->lut_array) cudaFreeArray(r->lut_array);
@@ -1317,6 +1411,7 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
             ca.dest_h = r->options.dest_size.y;
             ca.clear_color = clear_color(r);
             ca.work_counter = r->counters.ptr + 12;
+            wait_for_gather(r, r->stream);
             r->stats.drawcall_count += (uint64_t)launch_composite(ca, r->stream);
         }
         if (r->borrowed_copies_pending && !r->pending.active) {
@@ -1334,6 +1429,7 @@ PFCudaStatus PFCudaRendererReadPixels(PFCudaRendererRef r, uint8_t *dst, size_t 
         verify_pending(r);
         size_t row = (size_t)r->options.dest_size.x * 4;
         if (!dst || stride < row) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "bad destination / stride");
+        wait_for_gather(r, r->stream); // the other ranks' strips
         PF_CUDA_CHECK(cudaMemcpy2DAsync(dst, stride, r->dest, r->dest_pitch, row, (size_t)r->options.dest_size.y,
                                         cudaMemcpyDeviceToHost, r->stream));
         PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
@@ -1419,7 +1515,109 @@ PFCudaStatus PFCudaRendererSetStream(PFCudaRendererRef r, uint64_t cuda_stream) 
 
 PFCudaStatus PFCudaRendererSynchronize(PFCudaRendererRef r) {
     return guarded(r, [&]() {
-        verify_pending(r); PF_CUDA_CHECK(cudaStreamSynchronize(r->stream)); });
+        verify_pending(r);
+        wait_for_gather(r, r->stream);
+        PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    });
+}
+
+void PFCudaStripOfRank(int32_t tile_rows, int32_t rank, int32_t world_size, int32_t *tile_y0, int32_t *tile_y1) {
+    int32_t y0 = 0, y1 = 0;
+    if (world_size > 0 && rank >= 0 && rank < world_size && tile_rows >= 0) strip_of_rank(tile_rows, rank, world_size, y0, y1);
+    if (tile_y0) *tile_y0 = y0;
+    if (tile_y1) *tile_y1 = y1;
+}
+
+PFCudaStatus PFCudaGatherCreateId(PFCudaGatherId *id_out) {
+    try {
+        if (!id_out) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "null id");
+        static_assert(sizeof(PFCudaGatherId) == 128, "ncclUniqueId size");
+        const Nccl &n = nccl_or_throw();
+        n.check(n.get_unique_id(id_out), "ncclGetUniqueId");
+        return PF_CUDA_OK;
+    } catch (const Error &e) {
+        set_last_error(e.what());
+        return (PFCudaStatus)e.status;
+    }
+}
+
+PFCudaStatus PFCudaRendererGatherInit(PFCudaRendererRef r, const PFCudaGatherId *id, int32_t rank, int32_t world_size) {
+    return guarded(r, [&]() {
+        verify_pending(r);
+        if (!id || world_size < 1 || rank < 0 || rank >= world_size)
+            throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "bad gather id / rank / world size");
+        if (r->dest_pitch != (size_t)r->options.dest_size.x * 4)
+            throw Error(PF_CUDA_ERROR_UNSUPPORTED, "frame assembly needs a destination with contiguous rows");
+        const Nccl &n = nccl_or_throw();
+        gather_destroy(r);
+        PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        void *comm = nullptr;
+        n.check(n.comm_init_rank(&comm, world_size, *id, rank), "ncclCommInitRank");
+        r->gather_comm = comm;
+        r->gather_rank = rank;
+        r->gather_world = world_size;
+        PF_CUDA_CHECK(cudaStreamCreateWithFlags(&r->gather_stream, cudaStreamNonBlocking));
+        PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->gather_ready, cudaEventDisableTiming));
+        PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->gather_done, cudaEventDisableTiming));
+        const FbRect fb = framebuffer_tile_rect(r);
+        strip_of_rank(fb.max_y - fb.min_y, rank, world_size, r->strip_y0, r->strip_y1);
+        if (r->strip_y1 == r->strip_y0) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "more ranks than tile rows");
+    });
+}
+
+PFCudaStatus PFCudaRendererGatherFrame(PFCudaRendererRef r) {
+    return guarded(r, [&]() {
+        if (!r->gather_comm) throw Error(PF_CUDA_ERROR_PROTOCOL, "PFCudaRendererGatherFrame before PFCudaRendererGatherInit");
+        if (r->in_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "PFCudaRendererGatherFrame inside begin_scene / end_scene");
+        const Nccl &n = Nccl::get();
+        const FbRect fb = framebuffer_tile_rect(r);
+        const int32_t rows = fb.max_y - fb.min_y, height = r->options.dest_size.y;
+        const size_t pitch = r->dest_pitch;
+        auto span = [&](int32_t rank, size_t &offset, size_t &bytes) { // the rank's strip in the frame, in bytes
+            int32_t y0, y1;
+            strip_of_rank(rows, rank, r->gather_world, y0, y1);
+            const int32_t p0 = std::min(y0 * PF_TILE_HEIGHT, height), p1 = std::min(y1 * PF_TILE_HEIGHT, height);
+            offset = (size_t)p0 * pitch, bytes = (size_t)(p1 - p0) * pitch;
+        };
+        // Ordered after this frame's compositing (and a gather still in flight on the same stream).
+        PF_CUDA_CHECK(cudaEventRecord(r->gather_ready, r->stream));
+        PF_CUDA_CHECK(cudaStreamWaitEvent(r->gather_stream, r->gather_ready, 0));
+        size_t my_offset, my_bytes, offset0, bytes0;
+        span(r->gather_rank, my_offset, my_bytes);
+        span(0, offset0, bytes0);
+        bool equal = true;
+        for (int32_t g = 0; g < r->gather_world; g++) {
+            size_t o, b;
+            span(g, o, b);
+            equal = equal && b == bytes0 && o == (size_t)g * bytes0;
+        }
+        if (equal) {
+            n.check(n.all_gather(r->dest + my_offset, r->dest, my_bytes, Nccl::UINT8, r->gather_comm, r->gather_stream),
+                    "ncclAllGather");
+        } else {
+            n.check(n.group_start(), "ncclGroupStart");
+            for (int32_t g = 0; g < r->gather_world; g++) {
+                size_t o, b;
+                span(g, o, b);
+                n.check(n.broadcast(r->dest + o, r->dest + o, b, Nccl::UINT8, g, r->gather_comm, r->gather_stream),
+                        "ncclBroadcast");
+            }
+            n.check(n.group_end(), "ncclGroupEnd");
+        }
+        PF_CUDA_CHECK(cudaEventRecord(r->gather_done, r->gather_stream));
+        r->gather_in_flight = true;
+    });
+}
+
+PFCudaStatus PFCudaRendererGatherWait(PFCudaRendererRef r) {
+    return guarded(r, [&]() { wait_for_gather(r, r->stream); });
+}
+
+PFCudaStatus PFCudaRendererGatherDestroy(PFCudaRendererRef r) {
+    return guarded(r, [&]() {
+        verify_pending(r);
+        gather_destroy(r);
+    });
 }
 
 PFCudaStatus PFCudaRendererSetStrip(PFCudaRendererRef r, int32_t tile_y0, int32_t tile_y1) {

@@ -1,6 +1,8 @@
 """Screen-space strip partition for multi-GPU rendering (new work, the reference has
 no multi-GPU path). Rank g of G owns whole tile rows [y0, y1) so its output is one contiguous block
-of the row-major RGBA8 frame; the frame is assembled with one all-gather."""
+of the row-major RGBA8 frame; the frame is assembled inside the library (PFCudaRendererGatherFrame).
+The same arithmetic as PFCudaStripOfRank (csrc/renderer.cu strip_of_rank), restated for host code that
+has no GPU library loaded (tests/test_strip_gloo.py checks the two against each other)."""
 from __future__ import annotations
 
 TILE = 16
@@ -11,15 +13,15 @@ def tile_rows(height_px: int) -> int:
 
 
 def strip_rows(height_px: int, world: int, rank: int) -> tuple[int, int]:
-    """Equal strips of whole tile rows; requires world | tile_rows so that the gather is uniform
-    (torch.distributed.all_gather_into_tensor)."""
+    """Tile rows [y0, y1) of `rank`: as equal as whole rows allow (rows * rank // world)."""
     rows = tile_rows(height_px)
-    if rows % world != 0:
-        raise ValueError(f"{rows} tile rows do not divide evenly across {world} ranks")
-    per = rows // world
-    return rank * per, (rank + 1) * per
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"rank {rank} of {world}")
+    if rows < world:
+        raise ValueError(f"{rows} tile rows cannot be split across {world} ranks")
+    return rows * rank // world, rows * (rank + 1) // world
 
 
 def strip_pixel_rows(height_px: int, world: int, rank: int) -> tuple[int, int]:
     y0, y1 = strip_rows(height_px, world, rank)
-    return y0 * TILE, min(y1 * TILE, height_px)
+    return min(y0 * TILE, height_px), min(y1 * TILE, height_px)

@@ -30,9 +30,14 @@ def _worker(rank, world, port, out_path):
         built = H.oracle_build(flat, xf, strip=(y0, y1))
         img = built.render(area_lut.generate(), SIZE, SIZE, background=(1, 1, 1, 1))
         p0, p1 = partition.strip_pixel_rows(SIZE, world, rank)
-        strip = torch.from_numpy(np.ascontiguousarray(img[p0:p1]))
-        full = torch.empty((SIZE, SIZE, 4), dtype=torch.uint8)
-        dist.all_gather_into_tensor(full.view(-1), strip.reshape(-1))
+        # the library's gather for unequal strips: one broadcast per rank, in place (grouped ncclBroadcast)
+        full = torch.zeros((SIZE, SIZE, 4), dtype=torch.uint8)
+        full[p0:p1] = torch.from_numpy(np.ascontiguousarray(img[p0:p1]))
+        for g in range(world):
+            g0, g1 = partition.strip_pixel_rows(SIZE, world, g)
+            part = full[g0:g1].contiguous()
+            dist.broadcast(part, src=g)
+            full[g0:g1] = part
         counts = torch.tensor([len(built.fills), len(built.tiles)], dtype=torch.int64)
         dist.all_reduce(counts)
         if rank == 0:
@@ -41,9 +46,14 @@ def _worker(rank, world, port, out_path):
         dist.destroy_process_group()
 
 
-def test_two_rank_strip_render_and_gather(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_strip_render_and_gather(tmp_path, world):
+    """world = 3: 16 tile rows split 5 / 5 / 6 — the unequal strips the grouped-broadcast path assembles."""
     out = str(tmp_path / "gathered.npz")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     z = np.load(out)
     flat, xf = scenes.tiger(SIZE)
     full = H.oracle_build(flat, xf)
@@ -55,6 +65,12 @@ def test_two_rank_strip_render_and_gather(tmp_path):
 def test_strip_rows():
     assert partition.strip_rows(8192, 8, 3) == (192, 256)
     assert partition.strip_pixel_rows(4096, 2, 1) == (2048, 4096)
-    import pytest
+    assert [partition.strip_rows(256, 3, g) for g in range(3)] == [(0, 5), (5, 10), (10, 16)]
+    assert partition.strip_pixel_rows(100, 2, 1) == (48, 100)  # 7 tile rows, the last one partial
     with pytest.raises(ValueError):
-        partition.strip_rows(100, 3, 0)
+        partition.strip_rows(16, 3, 0)
+    # the host restatement agrees with the library's PFCudaStripOfRank
+    from pathfinder_b200 import api
+    for rows_px, world in [(8192, 8), (4096, 3), (1000, 7), (16384, 5)]:
+        for g in range(world):
+            assert api.strip_of_rank(partition.tile_rows(rows_px), g, world) == partition.strip_rows(rows_px, world, g)

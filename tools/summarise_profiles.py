@@ -53,21 +53,72 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio"]
-lines = [f"# {tag} — `ncu --set full` of the dominant kernel: k_composite (fused fill + tile)", ""]
-for scene in ("random100k", "tiger4k"):
-    rep = os.path.join(ROOT, "gpurun_out", f"{tag}_composite_{scene}.ncu-rep")
-    if not os.path.exists(rep):
-        continue
+import hashlib, json
+
+
+def raw_metrics(rep, launch=0):
+    """{metric: (unit, value)} of one launch of an .ncu-rep (page raw)."""
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    lines += [f"## {scene}", "", "| metric | unit | value |", "|---|---|---:|"]
-    for k in KEYS:
-        if k in hdr:
-            i = hdr.index(k)
-            lines.append(f"| `{k}` | {units[i]} | {vals[i]} |")
-    lines.append("")
-open(os.path.join(out_dir, f"{tag}_composite_ncu.md"), "w").write("\n".join(lines))
+    if len(rows) < 3 + launch:
+        return {}
+    return {h: (u, v) for h, u, v in zip(rows[0], rows[1], rows[2 + launch])}
+
+
+def number(text):
+    try:
+        return float(text.replace(",", ""))
+    except ValueError:
+        return 0.0
+
+
+SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+lines = [f"# {tag} — `ncu --set full` of the fill + tile stage: k_tile_solid + k_tile_alpha", "",
+         "One steady-state frame per scene; the two kernels run back to back on the renderer's stream (profiles are "
+         "serialised and cold-cache: compare shares and counters, the CUDA-event stage time is in the bench line).", ""]
+traffic = {}
+for scene in ("random100k", "tiger4k"):
+    for kernel in ("k_tile_solid", "k_tile_alpha"):
+        rep = os.path.join(ROOT, "gpurun_out", f"{tag}_{kernel}_{scene}.ncu-rep")
+        if not os.path.exists(rep):
+            continue
+        m = raw_metrics(rep)
+        lines += [f"## {scene} — {kernel}", "", "| metric | unit | value |", "|---|---|---:|"]
+        for k in KEYS + ["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+                         "l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed",
+                         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_requests_pipe_tex_mem_texture.sum"]:
+            if k in m:
+                lines.append(f"| `{k}` | {m[k][0]} | {m[k][1]} |")
+        lines.append("")
+        if scene == "random100k":
+            traffic[kernel] = sum(number(m[k][1]) * SCALE.get(m[k][0], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in m)
+open(os.path.join(out_dir, f"{tag}_fill_tile_ncu.md"), "w").write("\n".join(lines))
+if len(traffic) == 2:
+    # bench.py reports this as roofline.traffic — only while composite.cu is the file that was profiled
+    src = open(os.path.join(ROOT, "pathfinder_b200", "csrc", "composite.cu"), "rb").read()
+    json.dump({"scene": "random100k@8192", "dram_bytes_per_frame": int(sum(traffic.values())),
+               "per_kernel": {k: int(v) for k, v in traffic.items()}, "composite_cu_sha256": hashlib.sha256(src).hexdigest()},
+              open(os.path.join(out_dir, f"{tag}_fill_tile_traffic.json"), "w"), indent=1)
+
+# bin (count pass): the L2 atomic / reduction evidence the north star names
+rep = os.path.join(ROOT, "gpurun_out", f"{tag}_k_bin_random100k.ncu-rep")
+if os.path.exists(rep):
+    BIN_KEYS = KEYS + ["lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum", "lts__t_requests_op_atom.sum", "lts__t_requests_op_red.sum",
+                       "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum", "l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum",
+                       "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
+    lines = [f"# {tag} — `ncu --set full` of bin: k_bin<1> (count pass) and the launch after it, random100k@8192", "",
+             "Every fill and every backdrop change of the count pass is one 32-bit L2 reduction (`RED`, no return value) on the "
+             "tile word; the emit pass claims its slot with one `ATOMG` per surviving fill.", ""]
+    for launch in (0, 1):
+        m = raw_metrics(rep, launch)
+        if not m:
+            continue
+        lines += [f"## launch {launch}: `{m.get('Kernel Name', ('', '?'))[1]}`", "", "| metric | unit | value |", "|---|---|---:|"]
+        for k in BIN_KEYS:
+            if k in m:
+                lines.append(f"| `{k}` | {m[k][0]} | {m[k][1]} |")
+        lines.append("")
+    open(os.path.join(out_dir, f"{tag}_bin_ncu.md"), "w").write("\n".join(lines))
 
 # SASS evidence: memory / texture / atomic / shuffle mnemonics per kernel.
 so = os.path.join(ROOT, "pathfinder_b200", "libpf_cuda.so")
@@ -97,4 +148,36 @@ for name, c in kernels.items():
     short = re.sub(r"^_ZN2pf\d+", "", name)[:40]
     lines.append(f"| `{short}` | " + " | ".join(str(c.get(k, 0)) for k in ["LDG.E.128", "LDG.E.64", "LDG", "STG.E.128", "STG", "TEX", "ATOMG", "RED", "ATOMS", "SHFL", "VOTE", "LDS", "STS", "LDL", "STL", "BAR", "FFMA2", "FMUL2", "FFMA", "HMMA", "UTC", "UTMA"]) + " |")
 open(os.path.join(out_dir, f"{tag}_sass.md"), "w").write("\n".join(lines) + "\n")
+
+# SASS excerpts: the inner loops themselves, not only counts.
+def function_sass(match):
+    out, on = [], False
+    for ln in sass.splitlines():
+        if "Function :" in ln:
+            on = match in ln
+        elif on and "/*" in ln and ";" in ln:
+            out.append(ln.split("*/")[1].split(";")[0].strip() if ln.strip().startswith("/*") else ln.strip())
+    return out
+
+
+def excerpt(body, first_pat, last_pat, before=24, after=30):
+    idx = [i for i, l in enumerate(body) if first_pat in l]
+    if not idx:
+        return []
+    end = [i for i, l in enumerate(body) if last_pat in l and i >= idx[0]]
+    lo, hi = max(0, idx[0] - before), min(len(body), (end[0] if end else idx[0]) + after)
+    return body[lo:hi]
+
+
+ex = [f"# {tag} — SASS excerpts (`cuobjdump -sass libpf_cuda.so`, sm_100a)", ""]
+alpha = function_sass("k_tile_alphaILb0ELb0")
+ex += ["## k_tile_alpha<false,false>: the per-fill loop (two fills per round: 2 x LDS.128 of the staged parameters each, "
+       "window / t / y arithmetic, 2 x TEX.LL of the area LUT each, 8 FFMA + 8 integer adds into the coverage accumulators)", "", "```"]
+ex += excerpt(alpha, "TEX.LL", "TEX.LL", before=40, after=40) + ["```", ""]
+ex += ["## k_tile_alpha<false,false>: the blend of a mask over the 8 pixels of a lane (LDS.128 pixel, FFMA2 pairs, STS.128)", "", "```"]
+ex += excerpt(alpha, "FFMA2", "FFMA2", before=6, after=40) + ["```", ""]
+binc = function_sass("k_binILi1E")
+ex += ["## k_bin<1> (count pass): add_fill's quantisation and the reduction on the tile word", "", "```"]
+ex += excerpt(binc, "RED", "RED", before=40, after=12) + ["```", ""]
+open(os.path.join(out_dir, f"{tag}_sass_excerpts.md"), "w").write("\n".join(ex) + "\n")
 print("wrote", [f for f in os.listdir(out_dir) if f.startswith(tag)])
