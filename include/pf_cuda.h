@@ -251,10 +251,39 @@ typedef enum PFRenderCommandKind {
     PF_RENDER_COMMAND_FINISH = 13
 } PFRenderCommandKind;
 
+/* TextureLocation (gpu_data.rs:222-226): a rectangle of texels inside a texture page. */
+typedef struct PFTextureLocation {
+    uint32_t page; /* TexturePageId */
+    PFRectI rect;
+} PFTextureLocation;
+
+/* TextureSamplingFlags (gpu/src/lib.rs:521-528) and TileBatchTexture (gpu_data.rs:247-254). composite_op is
+ * PaintCompositeOp (paint.rs): only SrcIn (0) is on the path today. */
+#define PF_TEXTURE_SAMPLING_FLAGS_REPEAT_U 0x1
+#define PF_TEXTURE_SAMPLING_FLAGS_REPEAT_V 0x2
+#define PF_TEXTURE_SAMPLING_FLAGS_NEAREST_MIN 0x4
+#define PF_TEXTURE_SAMPLING_FLAGS_NEAREST_MAG 0x8
+#define PF_PAINT_COMPOSITE_OP_SRC_IN 0
+#define PF_PAINT_COMPOSITE_OP_DEST_IN 1
+typedef struct PFTileBatchTexture {
+    uint32_t page;
+    uint8_t sampling_flags;
+    uint8_t composite_op;
+} PFTileBatchTexture;
+
 typedef struct PFRenderCommand {
     uint32_t kind; /* PFRenderCommandKind */
     union {
         struct { uint64_t path_count; uint32_t needs_readable_framebuffer; } start;
+        /* AllocateTexturePage { page_id, descriptor } (gpu_data.rs:53-54): an RGBA8 page of `size` texels. */
+        struct { uint32_t page_id; PFVector2I size; } allocate_texture_page;
+        /* UploadTexelData { texels, location } (gpu_data.rs:56-57): location.rect.area() texels, row-major. */
+        struct { const PFColorU *texels; size_t texel_count; PFTextureLocation location; } upload_texel_data;
+        /* DeclareRenderTarget { id, location } (gpu_data.rs:59-62). Rendering to it starts from transparent black.
+         * As in the reference's GL backend, texture coordinates address a render target bottom-up (v = 1 is its
+         * top row: paint.rs:628-634 flips v for PatternSource::RenderTarget), pages filled by UploadTexelData
+         * top-down. */
+        struct { uint32_t render_target_id; PFTextureLocation location; } declare_render_target;
         struct { const PFTextureMetadataEntry *entries; size_t entry_count; uint64_t content_key; /* as
                  PFTileBatchDataD3D11.content_key */ } upload_texture_metadata;
         struct { PFSegmentsD3D11 draw_segments, clip_segments;
@@ -265,7 +294,8 @@ typedef struct PFRenderCommand {
                   * on this renderer — so the host-to-device copies are enqueued without a wait. */
                  uint32_t payload_persists; } upload_scene_d3d11;
         struct { PFTileBatchDataD3D11 batch; } prepare_clip_tiles_d3d11;
-        struct { PFTileBatchDataD3D11 tile_batch_data; uint32_t has_color_texture; } draw_tiles_d3d11;
+        struct { PFTileBatchDataD3D11 tile_batch_data; uint32_t has_color_texture; /* Option<TileBatchTexture> */
+                 PFTileBatchTexture color_texture; } draw_tiles_d3d11;
         struct { uint32_t render_target_id; } push_render_target;
         struct { uint64_t cpu_build_time_ns; } finish;
     } u;
@@ -319,6 +349,10 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef renderer);
 /* Reads the destination image back (row-major, top-left origin, `stride` bytes per row >= 4*w).
  * Synchronises the renderer's stream. Replaces Device::read_pixels (gpu/src/lib.rs:100-104). */
 PFCudaStatus PFCudaRendererReadPixels(PFCudaRendererRef renderer, uint8_t *dst, size_t stride);
+/* Reads a texture page back (RGBA8, row-major, rows top-down, `stride` bytes per row >= 4 * page width): what a
+ * render target holds after the frame, or what UploadTexelData put there. Synchronises the renderer's stream. */
+PFCudaStatus PFCudaRendererReadTexturePage(PFCudaRendererRef renderer, uint32_t page_id, uint8_t *dst, size_t stride,
+                                           PFVector2I *size_out);
 /* Device pointer of the destination image (for peer copies / collectives) and its row pitch. */
 PFCudaStatus PFCudaRendererGetDestDevicePointer(PFCudaRendererRef renderer, uint64_t *device_ptr,
                                                 size_t *pitch_bytes);
@@ -473,6 +507,17 @@ void PFSceneGetViewBox(PFSceneRef scene, PFRectF *view_box);
 void PFSceneGetBounds(PFSceneRef scene, PFRectF *bounds);
 /* Scene::push_paint for a solid colour (scene.rs:186-190, paint.rs Palette::push_paint dedups). */
 uint16_t PFScenePushPaint(PFSceneRef scene, const PFColorU *color);
+/* Scene::push_render_target(RenderTarget::new(size, name)) (scene.rs:110-119): an off-screen RGBA8 image; paths
+ * pushed until the matching PFScenePopRenderTarget (scene.rs:121-123) are drawn into it. Returns the
+ * RenderTargetId (PF_PATH_INDEX_NONE on a bad size). */
+uint32_t PFScenePushRenderTarget(PFSceneRef scene, int32_t width, int32_t height);
+void PFScenePopRenderTarget(PFSceneRef scene);
+/* Scene::push_paint(&Paint::from_pattern(pattern)) for pattern = Pattern::from_render_target(id, size) with
+ * pattern.apply_transform(*pattern_transform) (NULL: identity) and pattern.set_filter(filter) (NULL or kind
+ * PF_FILTER_NONE: no filter; PF_FILTER_TEXT: PatternFilter::Text) — content/src/pattern.rs:105-140,
+ * renderer/src/paint.rs:138-146. The pattern transform maps render-target pixels to scene coordinates. */
+uint16_t PFScenePushPaintRenderTargetPattern(PFSceneRef scene, uint32_t render_target_id,
+                                             const PFTransform2F *pattern_transform, const PFFilter *filter);
 /* Scene::push_draw_path (scene.rs:77-82). The outline is given as contours of points + flags:
  * contour i owns points [contour_offsets[i], contour_offsets[i+1]). Returns the DrawPathId, or
  * PF_PATH_INDEX_NONE (see PFCudaGetLastError) and leaves the scene unchanged when the paint id or fill rule is

@@ -75,6 +75,11 @@ class PFBackdropInfoD3D11(C.Structure):
                 ("path_index", C.c_uint32)]
 
 
+PF_COLOR_COMBINE_MODE_NONE, PF_COLOR_COMBINE_MODE_SRC_IN, PF_COLOR_COMBINE_MODE_DEST_IN = 0, 1, 2
+PF_FILTER_NONE, PF_FILTER_TEXT = 0, 2
+PF_FILTER_FLAG_TEXT_HAS_KERNEL, PF_FILTER_FLAG_TEXT_GAMMA_CORRECTION = 0x1, 0x2
+
+
 class PFFilter(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("flags", C.c_uint32), ("params", C.c_float * 20)]
 
@@ -123,8 +128,29 @@ class _PrepareClipTiles(C.Structure):
     _fields_ = [("batch", PFTileBatchDataD3D11)]
 
 
+class PFTextureLocation(C.Structure):
+    _fields_ = [("page", C.c_uint32), ("rect", PFRectI)]
+
+
+class PFTileBatchTexture(C.Structure):
+    _fields_ = [("page", C.c_uint32), ("sampling_flags", C.c_uint8), ("composite_op", C.c_uint8)]
+
+
+class _AllocateTexturePage(C.Structure):
+    _fields_ = [("page_id", C.c_uint32), ("size", PFVector2I)]
+
+
+class _UploadTexelData(C.Structure):
+    _fields_ = [("texels", C.c_void_p), ("texel_count", C.c_size_t), ("location", PFTextureLocation)]
+
+
+class _DeclareRenderTarget(C.Structure):
+    _fields_ = [("render_target_id", C.c_uint32), ("location", PFTextureLocation)]
+
+
 class _DrawTilesD3D11(C.Structure):
-    _fields_ = [("tile_batch_data", PFTileBatchDataD3D11), ("has_color_texture", C.c_uint32)]
+    _fields_ = [("tile_batch_data", PFTileBatchDataD3D11), ("has_color_texture", C.c_uint32),
+                ("color_texture", PFTileBatchTexture)]
 
 
 class _PushRenderTarget(C.Structure):
@@ -136,7 +162,9 @@ class _Finish(C.Structure):
 
 
 class _CommandUnion(C.Union):
-    _fields_ = [("start", _Start), ("upload_texture_metadata", _UploadTextureMetadata),
+    _fields_ = [("start", _Start), ("allocate_texture_page", _AllocateTexturePage),
+                ("upload_texel_data", _UploadTexelData), ("declare_render_target", _DeclareRenderTarget),
+                ("upload_texture_metadata", _UploadTextureMetadata),
                 ("upload_scene_d3d11", _UploadSceneD3D11),
                 ("prepare_clip_tiles_d3d11", _PrepareClipTiles),
                 ("draw_tiles_d3d11", _DrawTilesD3D11), ("push_render_target", _PushRenderTarget),
@@ -222,6 +250,7 @@ SIGNATURES = {
     "PFCudaRendererSetStream": (C.c_int32, [C.c_void_p, C.c_uint64]),
     "PFCudaRendererSynchronize": (C.c_int32, [C.c_void_p]),
     "PFCudaRendererSetDeferredVerification": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "PFCudaRendererReadTexturePage": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.POINTER(PFVector2I)]),
     "PFCudaRendererSetStrip": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
     "PFCudaStripOfRank": (None, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "PFCudaGatherCreateId": (C.c_int32, [C.c_void_p]),
@@ -247,6 +276,9 @@ SIGNATURES = {
     "PFSceneGetViewBox": (None, [C.c_void_p, C.POINTER(PFRectF)]),
     "PFSceneGetBounds": (None, [C.c_void_p, C.POINTER(PFRectF)]),
     "PFScenePushPaint": (C.c_uint16, [C.c_void_p, C.POINTER(PFColorU)]),
+    "PFScenePushRenderTarget": (C.c_uint32, [C.c_void_p, C.c_int32, C.c_int32]),
+    "PFScenePopRenderTarget": (None, [C.c_void_p]),
+    "PFScenePushPaintRenderTargetPattern": (C.c_uint16, [C.c_void_p, C.c_uint32, C.POINTER(PFTransform2F), C.POINTER(PFFilter)]),
     "PFScenePushDrawPath": (C.c_uint32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint32]),
     "PFOutlineStrokeToFill": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),

@@ -86,6 +86,12 @@ class Scene:
     def from_flat(flat: FlatScene) -> "Scene":
         s = Scene()
         s.set_view_box(flat.view_box)
+        s.push_flat(flat)
+        return s
+
+    def push_flat(self, flat: FlatScene):
+        """Appends every clip and draw path of a FlatScene (its view box is not touched)."""
+        s = self
         lib = L.lib()
         remap = np.zeros(len(flat.paint_colors), dtype=np.uint16)
         for i, c in enumerate(flat.paint_colors):
@@ -102,7 +108,6 @@ class Scene:
             flat.contour_offsets.ctypes.data, n_draw_contours, flat.path_contour_offsets.ctypes.data,
             flat.n_paths, paints.ctypes.data, flat.fill_rules.ctypes.data,
             clip_ids.ctypes.data if clip_ids is not None else None))
-        return s
 
     def set_view_box(self, view_box):
         r = L.PFRectF(L.PFVector2F(view_box[0], view_box[1]), L.PFVector2F(view_box[2], view_box[3]))
@@ -116,6 +121,44 @@ class Scene:
     def push_paint(self, rgba) -> int:
         c = L.PFColorU(int(rgba[0]), int(rgba[1]), int(rgba[2]), int(rgba[3]))
         return int(L.lib().PFScenePushPaint(self._h, C.byref(c)))
+
+    def push_render_target(self, width: int, height: int) -> int:
+        """Scene::push_render_target: the paths pushed until pop_render_target are drawn into an off-screen image."""
+        rid = int(L.lib().PFScenePushRenderTarget(self._h, int(width), int(height)))
+        if rid == 0xFFFFFFFF:
+            raise L.PathfinderCudaError(L.PF_CUDA_ERROR_INVALID_ARGUMENT, L.lib().PFCudaGetLastError().decode())
+        return rid
+
+    def pop_render_target(self):
+        L.lib().PFScenePopRenderTarget(self._h)
+
+    def push_render_target_pattern(self, render_target_id: int, transform=None, text_filter=None) -> int:
+        """Paint::from_pattern(Pattern::from_render_target(id, size)). transform = (m11, m12, m21, m22, tx, ty) maps
+        render-target pixels to scene coordinates (pattern.apply_transform). text_filter = dict(fg=rgb, bg=rgb,
+        kernel=(4 floats) | None, gamma=bool) for PatternFilter::Text."""
+        t = None
+        if transform is not None:
+            m11, m12, m21, m22, tx, ty = [float(v) for v in transform]
+            t = L.PFTransform2F(L.PFMatrix2x2F(m11, m12, m21, m22), L.PFVector2F(tx, ty))
+        f = None
+        if text_filter is not None:
+            f = L.PFFilter()
+            f.kind = L.PF_FILTER_TEXT
+            fg, bg = list(text_filter["fg"]) + [1.0], list(text_filter["bg"]) + [1.0]
+            for i in range(4):
+                f.params[i], f.params[4 + i] = float(fg[i]), float(bg[i])
+            if text_filter.get("kernel") is not None:
+                f.flags |= L.PF_FILTER_FLAG_TEXT_HAS_KERNEL
+                for i in range(4):
+                    f.params[8 + i] = float(text_filter["kernel"][i])
+            if text_filter.get("gamma"):
+                f.flags |= L.PF_FILTER_FLAG_TEXT_GAMMA_CORRECTION
+        pid = int(L.lib().PFScenePushPaintRenderTargetPattern(self._h, int(render_target_id),
+                                                             C.byref(t) if t is not None else None,
+                                                             C.byref(f) if f is not None else None))
+        if pid == 0xFFFF:
+            raise L.PathfinderCudaError(L.PF_CUDA_ERROR_INVALID_ARGUMENT, L.lib().PFCudaGetLastError().decode())
+        return pid
 
     def push_draw_path(self, points, point_flags, contour_offsets, paint_id, fill_rule=0, blend_mode=BLEND_MODE_SRC_OVER,
                        clip_path_id=0xFFFFFFFF) -> int:
@@ -363,7 +406,11 @@ class CudaRenderer:
         lut = np.ascontiguousarray(_area_lut.generate() if area_lut is None else area_lut, dtype=np.uint8)
         self._options = self._make_options(self.dest_size, background_color)
         mode = L.PFRendererMode(level)
-        self._h = lib.PFCudaRendererCreate(dev, lut.ctypes.data, None, C.byref(mode), C.byref(self._options))
+        # textures/gamma-lut.png (256 x 8 L8): only the text filter's gamma correction reads it
+        from . import gamma_lut as _gamma_lut
+        gamma = np.ascontiguousarray(_gamma_lut.generate(), dtype=np.uint8)
+        assert gamma.shape == (8, 256)
+        self._h = lib.PFCudaRendererCreate(dev, lut.ctypes.data, gamma.ctypes.data, C.byref(mode), C.byref(self._options))
         if not self._h:
             raise L.PathfinderCudaError(L.PF_CUDA_ERROR_CUDA, lib.PFCudaGetLastError().decode())
 
@@ -445,6 +492,14 @@ class CudaRenderer:
 
     def synchronize(self):
         L.check(L.lib().PFCudaRendererSynchronize(self._h))
+
+    def read_texture_page(self, page_id: int) -> np.ndarray:
+        """(H, W, 4) uint8 of a texture page: what a render target holds after the frame."""
+        size = L.PFVector2I()
+        L.check(L.lib().PFCudaRendererReadTexturePage(self._h, page_id, None, 0, C.byref(size)))
+        out = np.zeros((size.y, size.x, 4), dtype=np.uint8)
+        L.check(L.lib().PFCudaRendererReadTexturePage(self._h, page_id, out.ctypes.data, size.x * 4, None))
+        return out
 
     # -- results ----------------------------------------------------------------------------
     def read_pixels(self, out: np.ndarray | None = None) -> np.ndarray:

@@ -40,6 +40,7 @@ namespace {
 constexpr int TILE_WARPS = PF_TILE_WARPS;
 constexpr int ENTRY_CAP = 32;  // entries rank-sorted in shared memory; deeper lists are walked by selection
 constexpr int SOLID_MAX = 8;   // deepest all-solid list k_tile_solid blends itself
+constexpr uint32_t PF_FILTER_TEXT_KIND = 2; // PF_FILTER_TEXT (include/pf_cuda.h)
 constexpr uint32_t WORK_PARKED = 0xf0000000u; // k_list_emit parks the tile counter here when a stage overflowed
 
 // Coverage contributions are accumulated as integers so the sum does not depend on the order of a tile's
@@ -277,7 +278,7 @@ __device__ __forceinline__ void accumulate_fill(const float4 p0, const float4 p1
     acc[7] += __float_as_uint(fmaf(a1.w, dX, COV_MAGIC));
 }
 
-template <bool HAS_CLIP>
+template <bool GENERAL>
 struct __align__(16) TileWarpShared {
     float4 dst[8 * 32];         // the tile's pixels between two entries with fills: [row k of the lane][lane]
     uint4 entry[ENTRY_CAP];     // the run in draw order: {fill_end, count | backdrop, paint | ctrl | flags, tile index}
@@ -286,12 +287,12 @@ struct __align__(16) TileWarpShared {
         float4 fill[32][2];     // FillParams of up to 32 fills
         uint32_t stage[16 * 16 + 16]; // finished RGBA8 tile, row-major (+16 words for rows 8..15: conflict-free)
     };
-    uint2 clip[HAS_CLIP ? ENTRY_CAP : 1]; // {clip fill end, clip tile word}
+    uint2 clip[GENERAL ? ENTRY_CAP : 1]; // {clip fill end, clip tile word} (batches with clipped paths)
 };
 
 // Sums the coverage contributions of fills [begin, end) into acc (integer units, order-independent).
-template <bool HAS_CLIP>
-__device__ __forceinline__ void fill_loop(TileWarpShared<HAS_CLIP> &sh, const PackedFill *__restrict__ fills,
+template <bool GENERAL>
+__device__ __forceinline__ void fill_loop(TileWarpShared<GENERAL> &sh, const PackedFill *__restrict__ fills,
                                           uint32_t begin, uint32_t end, float xf, float u_off,
                                           cudaTextureObject_t lut, int lane, uint32_t (&acc)[8]) {
     for (uint32_t f0 = begin; f0 < end; f0 += 32) {
@@ -343,11 +344,83 @@ __device__ __forceinline__ void rule_of(float (&cov)[8], uint32_t ctrl) {
     }
 }
 
-template <bool LOAD_DEST, bool HAS_CLIP>
+
+// ---- colour textures (pattern paints): the text filter of shaders/tile_fragment.inc.glsl:91-166 and the plain
+// pattern (filterNone, :361-363), evaluated per pixel. `x`, `y` are texel coordinates (texel centres at
+// integers, rows top-down); LINEAR filtering with CLAMP_TO_EDGE, the sampler state of a pattern without the
+// repeat flags.
+__device__ __forceinline__ float4 sample_texture(const ColorTexture &t, float x, float y) {
+    const float fx = floorf(x), fy = floorf(y);
+    const float ax = x - fx, ay = y - fy;
+    const int x0 = min(max((int)fx, 0), t.width - 1), x1 = min(max((int)fx + 1, 0), t.width - 1);
+    const int y0 = min(max((int)fy, 0), t.height - 1), y1 = min(max((int)fy + 1, 0), t.height - 1);
+    auto texel = [&](int xx, int yy) {
+        return unpack_rgba8(__ldg(reinterpret_cast<const uint32_t *>(t.pixels + (size_t)yy * t.pitch + (size_t)xx * 4)));
+    };
+    const float4 c00 = texel(x0, y0);
+    if (ax == 0.0f && ay == 0.0f) return c00; // a texel centre: the usual case (render targets sampled pixel for pixel)
+    const float4 c10 = texel(x1, y0), c01 = texel(x0, y1), c11 = texel(x1, y1);
+    auto mix = [](float p, float q, float w) { return p + (q - p) * w; };
+    return make_float4(mix(mix(c00.x, c10.x, ax), mix(c01.x, c11.x, ax), ay), mix(mix(c00.y, c10.y, ax), mix(c01.y, c11.y, ax), ay),
+                       mix(mix(c00.z, c10.z, ax), mix(c01.z, c11.z, ax), ay), mix(mix(c00.w, c10.w, ax), mix(c01.w, c11.w, ax), ay));
+}
+
+// texture(gammaLUT, vec2(alpha, 1 - bg)).r: 256 x 8 L8, LINEAR, CLAMP_TO_EDGE (filterTextGammaCorrectChannel, :122-124).
+__device__ __forceinline__ float sample_gamma(const uint8_t *__restrict__ lut, float u, float v) {
+    const float x = u * 256.0f - 0.5f, y = v * 8.0f - 0.5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float ax = x - fx, ay = y - fy;
+    const int x0 = min(max((int)fx, 0), 255), x1 = min(max((int)fx + 1, 0), 255);
+    const int y0 = min(max((int)fy, 0), 7), y1 = min(max((int)fy + 1, 0), 7);
+    const float s = 1.0f / 255.0f;
+    const float top = (float)__ldg(lut + y0 * 256 + x0) * s * (1.0f - ax) + (float)__ldg(lut + y0 * 256 + x1) * s * ax;
+    const float bottom = (float)__ldg(lut + y1 * 256 + x0) * s * (1.0f - ax) + (float)__ldg(lut + y1 * 256 + x1) * s * ax;
+    return top * (1.0f - ay) + bottom * ay;
+}
+
+// filterColor + combineColor0 (SrcIn) for the pixel whose centre is (fx, fy): returns the colour, NOT premultiplied,
+// alpha = texture alpha * base alpha (tile_fragment.inc.glsl:81-89,365-412).
+__device__ __forceinline__ float4 textured_color(const PaintTexture &p, const ColorTexture &t, const uint8_t *gamma_lut,
+                                                 float fx, float fy) {
+    const float u = p.m00 * fx + p.m01 * fy + p.tx, v = p.m10 * fx + p.m11 * fy + p.ty; // computeTileVaryings
+    const float x = u * (float)t.width - 0.5f;
+    const float y = t.bottom_up ? ((float)t.height - 0.5f - v * (float)t.height) : (v * (float)t.height - 0.5f);
+    if (p.filter_kind != PF_FILTER_TEXT_KIND) {
+        const float4 c = sample_texture(t, x, y);
+        return make_float4(c.x, c.y, c.z, c.w * p.base.w);
+    }
+    // filterText: nine taps one texel apart (onePixel = 1 / colorTextureSize.x), red channel only.
+    float3 alpha;
+    if (p.kernel.w == 0.0f) {
+        const float r = sample_texture(t, x, y).x;
+        alpha = make_float3(r, r, r);
+    } else {
+        const bool wide = p.kernel.x > 0.0f;
+        float tap[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) tap[k] = ((k == 0 || k == 8) && !wide) ? 0.0f : sample_texture(t, x + (float)(k - 4), y).x;
+        // filterTextConvolve7Tap(alpha0, alpha1, kernel) = dot(alpha0, kernel) + dot(alpha1, kernel.zyx)
+        auto convolve = [&](int first) {
+            return (((tap[first] * p.kernel.x + tap[first + 1] * p.kernel.y) + tap[first + 2] * p.kernel.z) + tap[first + 3] * p.kernel.w) +
+                   ((tap[first + 4] * p.kernel.z + tap[first + 5] * p.kernel.y) + tap[first + 6] * p.kernel.x);
+        };
+        alpha = make_float3(convolve(0), convolve(1), convolve(2));
+    }
+    if (p.gamma_correction && gamma_lut) {
+        alpha.x = sample_gamma(gamma_lut, alpha.x, 1.0f - p.bg.x);
+        alpha.y = sample_gamma(gamma_lut, alpha.y, 1.0f - p.bg.y);
+        alpha.z = sample_gamma(gamma_lut, alpha.z, 1.0f - p.bg.z);
+    }
+    // vec4(mix(bgColor, fgColor, alpha), 1.0), then SrcIn with the base colour
+    return make_float4(p.bg.x + (p.fg.x - p.bg.x) * alpha.x, p.bg.y + (p.fg.y - p.bg.y) * alpha.y,
+                       p.bg.z + (p.fg.z - p.bg.z) * alpha.z, p.base.w);
+}
+
+template <bool LOAD_DEST, bool GENERAL>
 __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_alpha(CompositeArgs a) {
-    __shared__ TileWarpShared<HAS_CLIP> sh_all[TILE_WARPS];
+    __shared__ TileWarpShared<GENERAL> sh_all[TILE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    TileWarpShared<HAS_CLIP> &sh = sh_all[warp];
+    TileWarpShared<GENERAL> &sh = sh_all[warp];
     const int fb_w = a.fb.max_x - a.fb.min_x;
     const uint32_t n_queue = *a.queue_count; // written by k_tile_solid
     const int64_t fb_base = (int64_t)(a.tile_y0 - a.fb.min_y) * fb_w;
@@ -405,7 +478,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
             if ((uint32_t)lane < n) {
                 sh.entry[rank] = raw;
                 sh.paint[rank] = paint;
-                if (HAS_CLIP) sh.clip[rank] = __ldg(a.entry_clip + e0 + lane);
+                if (GENERAL && a.entry_clip) sh.clip[rank] = __ldg(a.entry_clip + e0 + lane);
             }
             __syncwarp();
         }
@@ -437,7 +510,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
             if (in_smem) {
                 raw = sh.entry[ei];
                 paint = sh.paint[ei];
-                if (HAS_CLIP) clip_entry = sh.clip[ei];
+                if (GENERAL && a.entry_clip) clip_entry = sh.clip[ei];
             } else {
                 // Very deep lists: select the next entry in draw order by a min-scan.
                 uint32_t best = 0xffffffffu, best_i = 0;
@@ -452,16 +525,17 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
                 next_key = best + 1;
                 raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + best_i));
                 paint = __ldg(&a.entries[e0 + best_i].color);
-                if (HAS_CLIP) clip_entry = __ldg(a.entry_clip + e0 + best_i);
+                if (GENERAL && a.entry_clip) clip_entry = __ldg(a.entry_clip + e0 + best_i);
             }
             const uint32_t fill_end = raw.x, count = raw.y & 0x00ffffffu;
             const float backdrop = (float)(int)(int8_t)(raw.y >> 24);
             const uint32_t ctrl = (raw.z >> 16) & 0xffu;
             const Px pp = px_from(paint);
             const f32x2 neg_w = pack2(-paint.w, -paint.w);
-            const bool clipped = HAS_CLIP && (raw.z & ENTRY_HAS_CLIP);
+            const bool clipped = GENERAL && (raw.z & ENTRY_HAS_CLIP);
+            const bool textured = GENERAL && (raw.z & ENTRY_TEXTURED);
 
-            if (count == 0 && !clipped) {
+            if (count == 0 && !clipped && !textured) {
                 // Solid tile: coverage = backdrop for every pixel (tile_fragment.inc.glsl:548) — the same
                 // blend for all 256 pixels, folded into the affine map.
                 const float m = mask_alpha(backdrop, ctrl);
@@ -471,9 +545,13 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
             }
 
             float cov[8];
-            if (!clipped) {
+            if (!clipped && count == 0) { // a solid tile of a textured paint: the same mask for every pixel
+                const float m = mask_alpha(backdrop, ctrl);
+#pragma unroll
+                for (int k = 0; k < 8; k++) cov[k] = m;
+            } else if (!clipped) {
                 uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                fill_loop<HAS_CLIP>(sh, a.fills, fill_end - count, fill_end, xf, u_off, a.area_lut, lane, acc);
+                fill_loop<GENERAL>(sh, a.fills, fill_end - count, fill_end, xf, u_off, a.area_lut, lane, acc);
                 coverage_of(acc, count, backdrop, cov);
                 rule_of(cov, ctrl);
             } else {
@@ -485,12 +563,12 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
                 const uint32_t clip_count = clip_entry.y & 0x00ffffffu;
                 const float clip_backdrop = (float)(int)(int8_t)(clip_entry.y >> 24);
                 uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                fill_loop<HAS_CLIP>(sh, a.clip_fills, clip_entry.x - clip_count, clip_entry.x, xf, u_off, a.area_lut, lane, acc);
+                fill_loop<GENERAL>(sh, a.clip_fills, clip_entry.x - clip_count, clip_entry.x, xf, u_off, a.area_lut, lane, acc);
                 coverage_of(acc, clip_count, clip_backdrop, cov);
                 if (!replace) {
                     uint32_t acc_draw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                     float cov_draw[8];
-                    fill_loop<HAS_CLIP>(sh, a.fills, fill_end - count, fill_end, xf, u_off, a.area_lut, lane, acc_draw);
+                    fill_loop<GENERAL>(sh, a.fills, fill_end - count, fill_end, xf, u_off, a.area_lut, lane, acc_draw);
                     coverage_of(acc_draw, count, backdrop, cov_draw);
 #pragma unroll
                     for (int k = 0; k < 8; k++) cov[k] = fminf(fabsf(cov_draw[k]), fabsf(cov[k]));
@@ -498,9 +576,28 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
                 rule_of(cov, ctrl);
             }
 
-            // calculateColor (tile_fragment.inc.glsl:560-614), solid colour, SrcOver — per pixel.
+            // calculateColor (tile_fragment.inc.glsl:560-614), SrcOver — per pixel.
             const f32x2 ss = pack2(s, s);
-            if (expanded) {
+            if (textured) {
+                // The paint samples the batch's colour texture: a colour per pixel (filterColor + combineColor0).
+                const PaintTexture pt = a.paint_textures[raw.z & 0xffffu];
+                const float4 o4 = px_to(o);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    float4 d = o4;
+                    if (expanded) {
+                        const float4 v = sh.dst[k * 32 + lane];
+                        d = make_float4(fmaf(v.x, s, o4.x), fmaf(v.y, s, o4.y), fmaf(v.z, s, o4.z), fmaf(v.w, s, o4.w));
+                    }
+                    const float4 c = textured_color(pt, a.color_texture, a.gamma_lut, (float)px + 0.5f, (float)(py0 + k) + 0.5f);
+                    // color.a *= maskAlpha; color.rgb *= color.a; dest = dest * (1 - color.a) + color
+                    const float alpha = c.w * cov[k], keep = 1.0f - alpha;
+                    d = make_float4(fmaf(d.x, keep, c.x * alpha), fmaf(d.y, keep, c.y * alpha), fmaf(d.z, keep, c.z * alpha),
+                                    fmaf(d.w, keep, alpha));
+                    sh.dst[k * 32 + lane] = d;
+                }
+                expanded = true;
+            } else if (expanded) {
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const float4 v = sh.dst[k * 32 + lane];
@@ -614,7 +711,7 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
 
     // One resident wave of persistent warps, or fewer when the whole frame has fewer tiles.
     const Residency &res = residency_of_current_device();
-    const bool has_clip = a.entry_clip != nullptr;
+    const bool has_clip = a.entry_clip != nullptr || a.paint_textures != nullptr; // the GENERAL kernel variants
     const uint64_t n_work = (uint64_t)fb_w * (uint64_t)rows;
     const uint64_t want = (n_work + TILE_WARPS - 1) / TILE_WARPS;
     const uint64_t resident = (uint64_t)res.sm_count * (uint64_t)res.blocks[a.load_dest ? 1 : 0][has_clip ? 1 : 0];

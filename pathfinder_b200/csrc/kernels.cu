@@ -979,7 +979,8 @@ __global__ void __launch_bounds__(256)
                     if (count != 0) path_live[p] = 1u; // some fills of this path will be read: its lines must be walked again
                     // The framebuffer tile needs per-pixel work (a mask of fills or a clip mask): plain store,
                     // every writer stores the same value.
-                    if (count != 0 || (tile_clip && __ldg(tile_clip + t) != 0u)) fb_alpha[fbi] = 1u;
+                    if (count != 0 || (path.paint_ctrl & PATH_TEXTURED) || (tile_clip && __ldg(tile_clip + t) != 0u))
+                        fb_alpha[fbi] = 1u;
                 }
             }
         }
@@ -1069,7 +1070,8 @@ __global__ void __launch_bounds__(256)
         TileEntry e;
         e.fill_end = __ldg(tile_fill_pos + t); // the bin emit pass left the cursor at the end of the run
         e.word = __ldg(tile_word + t);
-        e.paint_ctrl = __ldg(&b.paths[p].paint_ctrl) & 0x00ffffffu;
+        const uint32_t path_paint_ctrl = __ldg(&b.paths[p].paint_ctrl);
+        e.paint_ctrl = (path_paint_ctrl & 0x00ffffffu) | ((path_paint_ctrl & PATH_TEXTURED) ? ENTRY_TEXTURED : 0u);
         e.tile_index = t;
         uint32_t slot = __ldg(fb_start + fbi) + atomicAdd(fb_cursor + fbi, 1u);
         // The paint premultiplied, (rgb * a, a): what the compositing kernels blend with (color.rgb *= color.a,

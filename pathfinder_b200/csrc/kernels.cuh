@@ -17,11 +17,13 @@ struct __align__(16) PathInfo {
     uint32_t seg_batch_first;           // DiceMetadataD3D11.first_batch_segment_index
     uint32_t seg_global_first;          // DiceMetadataD3D11.first_global_segment_index
     uint32_t global_path_id;            // DiceMetadataD3D11.global_path_id (draw path id)
-    uint32_t paint_ctrl;                // color u16 | ctrl u8 << 16 | z_write << 24
+    uint32_t paint_ctrl;                // color u16 | ctrl u8 << 16 | z_write << 24 | PATH_TEXTURED
     uint32_t clip_path_index;           // PropagateMetadataD3D11.clip_path_index
     uint32_t pad;
 };
 static_assert(sizeof(PathInfo) == 48, "PathInfo layout");
+
+constexpr uint32_t PATH_TEXTURED = 1u << 25; // PathInfo.paint_ctrl: the paint samples a colour texture (per-pixel colour)
 
 struct Transform {
     float m11, m21, m12, m22, tx, ty;
@@ -131,7 +133,27 @@ struct ClipDev {
 // the clip tile's mask and backdrop instead of min-combining its own mask with it.
 constexpr uint32_t TILE_CLIP_REPLACE = 0x80000000u;
 // TileEntry.paint_ctrl flag bits (the low 24 bits are colour | ctrl).
-constexpr uint32_t ENTRY_HAS_CLIP = 1u << 24, ENTRY_CLIP_REPLACE = 1u << 25;
+constexpr uint32_t ENTRY_HAS_CLIP = 1u << 24, ENTRY_CLIP_REPLACE = 1u << 25, ENTRY_TEXTURED = 1u << 26;
+
+// A paint that samples a colour texture (TextureMetadataEntry with a colour combine mode, gpu_data.rs:336-344;
+// the ten RGBA16F texels of gpu/renderer.rs:712-763 as one device record). Only the text filter
+// (PatternFilter::Text, shaders/tile_fragment.inc.glsl:91-166) and the unfiltered pattern are evaluated.
+struct __align__(16) PaintTexture {
+    float m00, m01, m10, m11, tx, ty; // framebuffer position (pixel centre) -> normalised texture coordinate
+    uint32_t filter_kind;             // PF_FILTER_NONE / PF_FILTER_TEXT
+    uint32_t gamma_correction;
+    float4 kernel;                    // defringing kernel (w = 0: no defringing)
+    float4 bg, fg;                    // text filter colours (rgb)
+    float4 base;                      // base colour, rounded through f16, not premultiplied
+};
+
+// The colour texture of a draw batch (DrawTileBatchD3D11.color_texture): one RGBA8 page in device memory.
+struct ColorTexture {
+    const uint8_t *pixels; // NULL: the batch has no colour texture
+    size_t pitch;
+    int32_t width, height;
+    int32_t bottom_up;     // the page is a render target: v = 1 addresses its top row (see pf_cuda.h)
+};
 
 // clip / tile_clip: NULL unless the batch has clipped paths.
 int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_backdrop, int32_t *z_buffer,
@@ -164,6 +186,9 @@ int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t 
 struct CompositeArgs {
     const TileEntry *entries;   // runs in arbitrary order; the kernel sorts each by tile_index
     const uint2 *entry_clip;    // per entry {clip fill end, clip tile word}, for entries with ENTRY_HAS_CLIP (else NULL)
+    const PaintTexture *paint_textures; // per paint id, for entries with ENTRY_TEXTURED (else NULL)
+    ColorTexture color_texture;
+    const uint8_t *gamma_lut;   // 256 x 8 L8 (textures/gamma-lut.png), NULL when the renderer was created without it
     const PackedFill *clip_fills;
     const uint32_t *fb_start, *fb_count;
     const uint32_t *fb_alpha;  // per framebuffer tile: some entry has fills or a clip mask (per-pixel work)

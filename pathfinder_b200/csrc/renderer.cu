@@ -74,6 +74,7 @@ struct BatchCache {
     BatchDev batch{};
     bool has_initial_backdrops = false;
     bool has_clips = false; // the batch has clipped paths (resolved against r->clip)
+    ColorTexture color_texture{nullptr, 0, 0, 0, 0}; // DrawTileBatchD3D11.color_texture, resolved to its page
     bool counts_valid = false; // n_lines / n_fills / n_entries hold the last frame's totals
     uint32_t n_lines = 0, n_fills = 0, n_entries = 0, n_visible_fills = 0;
     uint32_t command_paths = 0, command_segments = 0; // as sent (before strip culling)
@@ -136,6 +137,31 @@ struct PFCudaRenderer {
     // Paint table (UploadTextureMetadata), base colours rounded through f16.
     DeviceBuffer<float4> paints;
     size_t n_paints = 0;
+    // Paints that sample a colour texture (colour combine mode SrcIn): per-paint record for the compositing kernel,
+    // and which paints those are (PathInfo gets PATH_TEXTURED).
+    DeviceBuffer<PaintTexture> paint_textures;
+    std::vector<uint8_t> paint_is_textured;
+    bool any_textured_paint = false;
+    DeviceBuffer<uint8_t> gamma_lut; // textures/gamma-lut.png, 256 x 8 L8 (only the text filter reads it)
+    bool has_gamma_lut = false;
+
+    // Texture pages (AllocateTexturePage) and render targets (DeclareRenderTarget / PushRenderTarget /
+    // PopRenderTarget; renderer/src/gpu/renderer.rs:462-520,1151-1209). Draw batches go to the render target on
+    // top of the stack, or to the destination image when the stack is empty.
+    struct TexturePage {
+        DeviceBuffer<uint8_t> pixels; // RGBA8, pitch = 4 * width
+        int32_t width = 0, height = 0;
+        bool is_render_target = false;
+    };
+    struct RenderTargetSlot {
+        bool declared = false;
+        uint32_t page = 0;
+        PFRectI rect{{0, 0}, {0, 0}};
+        int batches_drawn = 0; // this frame: the first batch starts from transparent black
+    };
+    std::vector<std::unique_ptr<TexturePage>> pages;
+    std::vector<RenderTargetSlot> render_targets;
+    std::vector<uint32_t> target_stack;
 
     // Strip partition.
     int32_t strip_y0 = 0, strip_y1 = 0;
@@ -253,6 +279,8 @@ void setup_tracking(PFCudaRenderer *r) {
     track(r, r->clip_segments.points);
     track(r, r->clip_segments.indices);
     track(r, r->paints);
+    track(r, r->paint_textures);
+    track(r, r->gamma_lut);
     track(r, r->batch_meta);
     track(r, r->seg_line_offset);
     track(r, r->lines);
@@ -297,7 +325,36 @@ void allocate_dest(PFCudaRenderer *r) {
     r->dest_pitch = (size_t)w * 4;
 }
 
-// round_out(view_box / 16): the framebuffer tile rect (renderer/src/builder.rs:949-953).
+// Where draw batches currently go: the render target on top of the stack, or the destination image
+// (Renderer::draw_render_target / main_viewport, renderer/src/gpu/renderer.rs:1151-1209).
+struct DrawTarget {
+    uint8_t *pixels;
+    size_t pitch;
+    int32_t width, height;
+    bool is_main;
+    int *batches_drawn;
+};
+DrawTarget current_target(PFCudaRenderer *r) {
+    if (r->target_stack.empty())
+        return DrawTarget{r->dest, r->dest_pitch, r->options.dest_size.x, r->options.dest_size.y, true, &r->batches_drawn};
+    PFCudaRenderer::RenderTargetSlot &slot = r->render_targets[r->target_stack.back()];
+    PFCudaRenderer::TexturePage &page = *r->pages[slot.page];
+    const size_t pitch = (size_t)page.width * 4;
+    return DrawTarget{page.pixels.ptr + (size_t)slot.rect.origin.y * pitch + (size_t)slot.rect.origin.x * 4, pitch,
+                      slot.rect.lower_right.x - slot.rect.origin.x, slot.rect.lower_right.y - slot.rect.origin.y, false,
+                      &slot.batches_drawn};
+}
+
+// round_out(view_box / 16): the framebuffer tile rect (renderer/src/builder.rs:949-953) of the current draw target.
+FbRect target_tile_rect(const DrawTarget &t) {
+    FbRect fb;
+    fb.min_x = 0;
+    fb.min_y = 0;
+    fb.max_x = (t.width + PF_TILE_WIDTH - 1) / PF_TILE_WIDTH;
+    fb.max_y = (t.height + PF_TILE_HEIGHT - 1) / PF_TILE_HEIGHT;
+    return fb;
+}
+// ... of the destination image.
 FbRect framebuffer_tile_rect(const PFCudaRenderer *r) {
     FbRect fb;
     fb.min_x = 0;
@@ -307,12 +364,16 @@ FbRect framebuffer_tile_rect(const PFCudaRenderer *r) {
     return fb;
 }
 
-// Local image first, then the peers' images (fused all-gather, see k_composite).
-void fill_destinations(const PFCudaRenderer *r, CompositeArgs &ca) {
-    ca.dests[0] = r->dest;
+// Local image first, then — for the destination image only — the peers' images (fused all-gather, see composite.cu).
+void fill_destinations(const PFCudaRenderer *r, const DrawTarget &target, CompositeArgs &ca) {
+    ca.dest = target.pixels;
+    ca.dests[0] = target.pixels;
     ca.n_dest = 1;
-    uintptr_t bits = (uintptr_t)r->dest | (uintptr_t)r->dest_pitch;
-    for (int i = 0; i < r->n_peers && ca.n_dest < 8; i++) {
+    ca.dest_pitch = target.pitch;
+    ca.dest_w = target.width;
+    ca.dest_h = target.height;
+    uintptr_t bits = (uintptr_t)target.pixels | (uintptr_t)target.pitch;
+    for (int i = 0; target.is_main && i < r->n_peers && ca.n_dest < 8; i++) {
         ca.dests[ca.n_dest++] = r->peer_dest[i];
         bits |= (uintptr_t)r->peer_dest[i];
     }
@@ -405,24 +466,58 @@ void upload_segments(PFCudaRenderer *r, SceneSegments &dst, const PFSegmentsD3D1
 
 void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *entries, size_t n) {
     std::vector<float4> table(n);
+    std::vector<PaintTexture> textures(n);
+    r->paint_is_textured.assign(n, 0);
+    r->any_textured_paint = false;
+    auto half_round = [](float v) { return __half2float(__float2half_rn(v)); }; // the metadata texture is RGBA16F
     for (size_t i = 0; i < n; i++) {
         const PFTextureMetadataEntry &e = entries[i];
-        if (e.color_0_combine_mode != PF_COLOR_COMBINE_MODE_NONE || e.filter.kind != PF_FILTER_NONE ||
-            e.blend_mode != PF_BLEND_MODE_SRC_OVER)
+        const bool textured = e.color_0_combine_mode == PF_COLOR_COMBINE_MODE_SRC_IN;
+        if ((e.color_0_combine_mode != PF_COLOR_COMBINE_MODE_NONE && !textured) || e.blend_mode != PF_BLEND_MODE_SRC_OVER ||
+            (e.filter.kind != PF_FILTER_NONE && !(textured && e.filter.kind == PF_FILTER_TEXT)))
             throw Error(PF_CUDA_ERROR_UNSUPPORTED,
-                        "only solid-colour SrcOver paints are on the hot path (SURVEY.md §2 row 7)");
+                        "paints on the hot path: solid colours, and patterns (SrcIn) unfiltered or with the text filter; "
+                        "SrcOver only (SURVEY.md §8 f3 / f4)");
         // ColorU::to_f32 (color/src/lib.rs:70-73) then f16 (gpu/renderer.rs:726-729).
         const float s = 1.0f / 255.0f;
         float c[4] = {(float)e.base_color.r * s, (float)e.base_color.g * s, (float)e.base_color.b * s,
                       (float)e.base_color.a * s};
-        for (float &v : c) v = __half2float(__float2half_rn(v));
+        for (float &v : c) v = half_round(v);
         table[i] = make_float4(c[0], c[1], c[2], c[3]);
+        PaintTexture &pt = textures[i];
+        memset(&pt, 0, sizeof(pt));
+        if (textured) {
+            // gpu/renderer.rs:712-763: transform, filter parameters and colours all pass through f16.
+            const PFTransform2F &t = e.color_0_transform;
+            pt.m00 = half_round(t.matrix.m00), pt.m01 = half_round(t.matrix.m01);
+            pt.m10 = half_round(t.matrix.m10), pt.m11 = half_round(t.matrix.m11);
+            pt.tx = half_round(t.vector.x), pt.ty = half_round(t.vector.y);
+            pt.filter_kind = e.filter.kind;
+            pt.base = table[i];
+            if (e.filter.kind == PF_FILTER_TEXT) {
+                // compute_filter_params (gpu/renderer.rs:777-800): p0 = kernel (or zero), p1 = bg, p2 = fg + gamma flag
+                const float *fp = e.filter.params;
+                pt.fg = make_float4(half_round(fp[0]), half_round(fp[1]), half_round(fp[2]), 0.0f);
+                pt.bg = make_float4(half_round(fp[4]), half_round(fp[5]), half_round(fp[6]), 0.0f);
+                if (e.filter.flags & PF_FILTER_FLAG_TEXT_HAS_KERNEL)
+                    pt.kernel = make_float4(half_round(fp[8]), half_round(fp[9]), half_round(fp[10]), half_round(fp[11]));
+                pt.gamma_correction = (e.filter.flags & PF_FILTER_FLAG_TEXT_GAMMA_CORRECTION) ? 1u : 0u;
+                if (pt.gamma_correction && !r->has_gamma_lut)
+                    throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "a text filter asks for gamma correction but the renderer was created without the gamma LUT");
+            }
+            r->paint_is_textured[i] = 1;
+            r->any_textured_paint = true;
+        }
     }
     r->n_paints = n;
     r->paints.ensure(n + 1);
+    r->paint_textures.ensure(n + 1);
     if (n) {
         PF_CUDA_CHECK(cudaMemcpyAsync(r->paints.ptr, table.data(), n * sizeof(float4), cudaMemcpyHostToDevice,
                                       r->stream));
+        if (r->any_textured_paint)
+            PF_CUDA_CHECK(cudaMemcpyAsync(r->paint_textures.ptr, textures.data(), n * sizeof(PaintTexture),
+                                          cudaMemcpyHostToDevice, r->stream));
         PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
         r->stats.h2d_bytes += n * sizeof(float4);
     }
@@ -550,6 +645,7 @@ void upload_batch_metadata(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch,
             pi.seg_global_first = dm.first_global_segment_index;
             pi.global_path_id = dm.global_path_id;
             pi.paint_ctrl = (uint32_t)tp.color | ((uint32_t)tp.ctrl << 16) | ((pm.z_write ? 1u : 0u) << 24);
+            if (!is_clip_batch && tp.color < n_paints && r->paint_is_textured[tp.color]) pi.paint_ctrl |= PATH_TEXTURED;
             pi.clip_path_index = pm.clip_path_index;
             pi.pad = (uint32_t)i; // index in the command's arrays (initial backdrops are keyed by it)
             h_paths[k] = pi;
@@ -895,13 +991,16 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
     ca.fb = fb;
     ca.tile_y0 = c.strip_y0;
     ca.tile_y1 = c.strip_y1;
-    ca.dest = r->dest;
-    fill_destinations(r, ca);
-    ca.dest_pitch = r->dest_pitch;
-    ca.dest_w = r->options.dest_size.x;
-    ca.dest_h = r->options.dest_size.y;
-    ca.clear_color = clear_color(r);
-    ca.load_dest = r->batches_drawn > 0;
+    const DrawTarget target = current_target(r);
+    fill_destinations(r, target, ca);
+    // A render target starts from transparent black (Renderer::clear_color_for_draw_operation, gpu/renderer.rs).
+    ca.clear_color = target.is_main ? clear_color(r) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    ca.load_dest = *target.batches_drawn > 0;
+    if (c.color_texture.pixels) { // the batch samples a colour texture
+        ca.paint_textures = r->paint_textures.ptr;
+        ca.color_texture = c.color_texture;
+        ca.gamma_lut = r->has_gamma_lut ? r->gamma_lut.ptr : nullptr;
+    }
     ca.work_counter = r->counters.ptr + 12;
     wait_for_gather(r, st);
     launches += launch_composite(ca, st);
@@ -915,7 +1014,7 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
     PendingVerify &pv = r->pending;
     pv.line_bound = line_bound, pv.fill_bound = fill_bound, pv.entry_bound = entry_bound, pv.emit_bound = emit_bound;
     pv.launches = launches;
-    pv.batches_drawn_before = r->batches_drawn;
+    pv.batches_drawn_before = *target.batches_drawn;
     if (r->deferred_verify && !sizing) {
         if (!r->verify_event) PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->verify_event, cudaEventDisableTiming));
         PF_CUDA_CHECK(cudaEventRecord(r->verify_event, st));
@@ -998,10 +1097,11 @@ void verify_pending(PFCudaRenderer *r) {
     r->borrowed_copies_pending = false; // the event was recorded after every copy of that frame
     r->stats.host_sync_count++;
     if (finalize_batch(r)) return;
-    const int drawn_now = r->batches_drawn;
-    r->batches_drawn = r->pending.batches_drawn_before; // same load action as the failed attempt
+    int &drawn = *current_target(r).batches_drawn; // (verification is never deferred across a target change)
+    const int drawn_now = drawn;
+    drawn = r->pending.batches_drawn_before; // same load action as the failed attempt
     const bool ok = run_pipeline(r, true);
-    r->batches_drawn = drawn_now;
+    drawn = drawn_now;
     r->stats.reruns++;
     if (!ok) throw Error(PF_CUDA_ERROR_CUDA, "stage buffer overflow after exact sizing (internal error)");
 }
@@ -1020,19 +1120,40 @@ void prepare_clip_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     if (batch.has_clipped_path_info && batch.clipped_path_info.clipped_path_count > 0)
         throw Error(PF_CUDA_ERROR_UNSUPPORTED, "nested clip paths are not implemented");
     if (r->clip.valid) throw Error(PF_CUDA_ERROR_UNSUPPORTED, "more than one clip batch per frame (nested clip levels)");
+    if (!r->target_stack.empty())
+        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "clip batches inside a render target are not implemented");
     const FbRect fb = framebuffer_tile_rect(r);
     const int32_t strip_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
     const int32_t strip_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
     BatchCache &c = r->cache;
     c.valid = false; // the stage buffers and the batch slot are borrowed; the draw batch re-uploads
     c.has_clips = false;
+    c.color_texture = ColorTexture{nullptr, 0, 0, 0, 0};
     upload_batch_metadata(r, batch, fb, strip_y0, strip_y1, c.batch, c.has_initial_backdrops, r->clip_segments, true);
     c.strip_y0 = strip_y0;
     c.strip_y1 = strip_y1;
     run_pipeline(r, true, true);
 }
 
-void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
+// DrawTileBatchD3D11.color_texture -> the page it names (Renderer::draw_tiles binds it as uColorTexture0,
+// renderer/src/gpu/d3d11/renderer.rs:733-741).
+ColorTexture resolve_color_texture(PFCudaRenderer *r, bool has_color_texture, const PFTileBatchTexture &texture) {
+    if (!has_color_texture) return ColorTexture{nullptr, 0, 0, 0, 0};
+    if (texture.page >= r->pages.size() || !r->pages[texture.page])
+        throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "draw batch names a texture page that was never allocated");
+    if (texture.sampling_flags & (PF_TEXTURE_SAMPLING_FLAGS_REPEAT_U | PF_TEXTURE_SAMPLING_FLAGS_REPEAT_V |
+                                  PF_TEXTURE_SAMPLING_FLAGS_NEAREST_MIN | PF_TEXTURE_SAMPLING_FLAGS_NEAREST_MAG))
+        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "colour textures are sampled LINEAR + CLAMP_TO_EDGE only (repeat / nearest: f4)");
+    if (texture.composite_op != PF_PAINT_COMPOSITE_OP_SRC_IN)
+        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "only PaintCompositeOp::SrcIn is implemented");
+    const PFCudaRenderer::TexturePage &page = *r->pages[texture.page];
+    if (!r->target_stack.empty() && r->render_targets[r->target_stack.back()].page == texture.page)
+        throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "draw batch samples the render target it draws to");
+    return ColorTexture{page.pixels.ptr, (size_t)page.width * 4, page.width, page.height, page.is_render_target ? 1 : 0};
+}
+
+void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch, bool has_color_texture,
+                     const PFTileBatchTexture &texture) {
     verify_pending(r);
     if (!r->has_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "DrawTilesD3D11 before UploadSceneD3D11");
     if (batch.path_source != PF_PATH_SOURCE_DRAW)
@@ -1040,9 +1161,15 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     const bool has_clips = batch.has_clipped_path_info && batch.clipped_path_info.clipped_path_count > 0;
     if (has_clips && !r->clip.valid)
         throw Error(PF_CUDA_ERROR_PROTOCOL, "draw batch with clipped paths before PrepareClipTilesD3D11");
-    const FbRect fb = framebuffer_tile_rect(r);
-    const int32_t strip_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
-    const int32_t strip_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
+    const DrawTarget target = current_target(r);
+    const ColorTexture color_texture = resolve_color_texture(r, has_color_texture, texture);
+    if (has_clips && !target.is_main)
+        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "clipped paths inside a render target are not implemented");
+    const FbRect fb = target_tile_rect(target);
+    // Strips partition the destination image; a render target is needed whole by whichever rank samples it.
+    const bool strip = target.is_main && r->strip_y1 > r->strip_y0;
+    const int32_t strip_y0 = strip ? r->strip_y0 : fb.min_y;
+    const int32_t strip_y1 = strip ? r->strip_y1 : fb.max_y;
     const ViewBox vb = r->has_view_box
                            ? r->view_box
                            : ViewBox{0.0f, 0.0f, (float)r->options.dest_size.x, (float)r->options.dest_size.y};
@@ -1078,13 +1205,64 @@ void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     } else {
         r->stats.batch_cache_hits++;
     }
+    c.color_texture = color_texture;
     bool ok = run_pipeline(r, !c.counts_valid || r->always_size);
     if (!ok) {
         ok = run_pipeline(r, true);
         r->stats.reruns++;
         if (!ok) throw Error(PF_CUDA_ERROR_CUDA, "stage buffer overflow after exact sizing (internal error)");
     }
-    r->batches_drawn++;
+    (*target.batches_drawn)++;
+}
+
+// ---- texture pages and render targets (Renderer::allocate_pattern_texture_page / upload_texel_data /
+// declare_render_target / push_render_target / pop_render_target, renderer/src/gpu/renderer.rs:462-520).
+void allocate_texture_page(PFCudaRenderer *r, uint32_t page_id, PFVector2I size) {
+    if (page_id >= 4096 || size.x <= 0 || size.y <= 0 || (int64_t)size.x * size.y > (1ll << 30))
+        throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "bad texture page id / size");
+    if (r->pages.size() <= page_id) r->pages.resize(page_id + 1);
+    if (!r->pages[page_id]) r->pages[page_id].reset(new PFCudaRenderer::TexturePage());
+    PFCudaRenderer::TexturePage &page = *r->pages[page_id];
+    if (page.width == size.x && page.height == size.y) return; // the reference re-allocates only on a size change
+    verify_pending(r);
+    PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    page.pixels.bytes_allocated = &r->bytes_allocated;
+    page.pixels.ensure((size_t)size.x * size.y * 4);
+    page.width = size.x, page.height = size.y;
+    PF_CUDA_CHECK(cudaMemsetAsync(page.pixels.ptr, 0, (size_t)size.x * size.y * 4, r->stream));
+}
+
+const PFCudaRenderer::TexturePage &page_of(PFCudaRenderer *r, const PFTextureLocation &loc, const char *what) {
+    if (loc.page >= r->pages.size() || !r->pages[loc.page])
+        throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, std::string(what) + ": texture page was never allocated");
+    const PFCudaRenderer::TexturePage &page = *r->pages[loc.page];
+    if (loc.rect.origin.x < 0 || loc.rect.origin.y < 0 || loc.rect.lower_right.x > page.width ||
+        loc.rect.lower_right.y > page.height || loc.rect.lower_right.x <= loc.rect.origin.x ||
+        loc.rect.lower_right.y <= loc.rect.origin.y)
+        throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, std::string(what) + ": rectangle outside its texture page");
+    return page;
+}
+
+void upload_texel_data(PFCudaRenderer *r, const PFColorU *texels, size_t count, const PFTextureLocation &loc) {
+    const PFCudaRenderer::TexturePage &page = page_of(r, loc, "UploadTexelData");
+    const size_t w = (size_t)(loc.rect.lower_right.x - loc.rect.origin.x), h = (size_t)(loc.rect.lower_right.y - loc.rect.origin.y);
+    if (!texels || count != w * h) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "UploadTexelData: texel count does not match the rectangle");
+    uint8_t *dst = page.pixels.ptr + ((size_t)loc.rect.origin.y * page.width + (size_t)loc.rect.origin.x) * 4;
+    PF_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)page.width * 4, texels, w * 4, w * 4, h, cudaMemcpyHostToDevice, r->stream));
+    PF_CUDA_CHECK(cudaStreamSynchronize(r->stream)); // the payload is borrowed for the call
+    r->stats.h2d_bytes += w * h * 4;
+}
+
+void declare_render_target(PFCudaRenderer *r, uint32_t id, const PFTextureLocation &loc) {
+    if (id >= 4096) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "bad render target id");
+    page_of(r, loc, "DeclareRenderTarget");
+    if (r->render_targets.size() <= id) r->render_targets.resize(id + 1);
+    PFCudaRenderer::RenderTargetSlot &slot = r->render_targets[id];
+    slot.declared = true;
+    slot.page = loc.page;
+    slot.rect = loc.rect;
+    slot.batches_drawn = 0;
+    r->pages[loc.page]->is_render_target = true;
 }
 
 // Alpha tile ids in SequentialExecutor order for the last batch (needs debug lists).
@@ -1241,7 +1419,7 @@ void PFCudaDeviceDestroy(PFCudaDeviceRef device) { delete device; }
 
 uint8_t PFCudaDeviceGetFeatureLevel(PFCudaDeviceRef) { return PF_RENDERER_LEVEL_D3D11; }
 
-PFCudaRendererRef PFCudaRendererCreate(PFCudaDeviceRef device, const uint8_t *area_lut_rgba8, const uint8_t *,
+PFCudaRendererRef PFCudaRendererCreate(PFCudaDeviceRef device, const uint8_t *area_lut_rgba8, const uint8_t *gamma_lut_l8,
                                        const PFRendererMode *mode, const PFCudaRendererOptions *options) {
     if (!device || !area_lut_rgba8 || !mode || !options) {
         set_last_error("PFCudaRendererCreate: null argument");
@@ -1275,6 +1453,11 @@ PFCudaRendererRef PFCudaRendererCreate(PFCudaDeviceRef device, const uint8_t *ar
         tex.readMode = cudaReadModeNormalizedFloat;
         tex.normalizedCoords = 1;
         PF_CUDA_CHECK(cudaCreateTextureObject(&r->lut_tex, &res, &tex, nullptr));
+        if (gamma_lut_l8) { // textures/gamma-lut.png: 256 x 8, one byte per texel (gpu/renderer.rs:215-222)
+            r->gamma_lut.ensure(256 * 8);
+            PF_CUDA_CHECK(cudaMemcpy(r->gamma_lut.ptr, gamma_lut_l8, 256 * 8, cudaMemcpyHostToDevice));
+            r->has_gamma_lut = true;
+        }
     } catch (const std::exception &e) {
         set_last_error(e.what());
         return nullptr;
@@ -1321,6 +1504,8 @@ PFCudaStatus PFCudaRendererBeginScene(PFCudaRendererRef r) {
         r->in_scene = true;
         r->clip.valid = false;
         r->batches_drawn = 0;
+        r->target_stack.clear();
+        for (auto &slot : r->render_targets) slot.batches_drawn = 0;
         r->stats = PFCudaRenderStats{};
         r->times = PFCudaRenderTime{};
     });
@@ -1357,9 +1542,31 @@ PFCudaStatus PFCudaRendererRenderCommand(PFCudaRendererRef r, const PFRenderComm
                 prepare_clip_batch(r, cmd->u.prepare_clip_tiles_d3d11.batch);
             break;
         case PF_RENDER_COMMAND_DRAW_TILES_D3D11:
-            if (cmd->u.draw_tiles_d3d11.has_color_texture)
-                throw Error(PF_CUDA_ERROR_UNSUPPORTED, "colour textures (gradients/patterns) are out of scope");
-            draw_tile_batch(r, cmd->u.draw_tiles_d3d11.tile_batch_data);
+            draw_tile_batch(r, cmd->u.draw_tiles_d3d11.tile_batch_data, cmd->u.draw_tiles_d3d11.has_color_texture != 0,
+                            cmd->u.draw_tiles_d3d11.color_texture);
+            break;
+        case PF_RENDER_COMMAND_ALLOCATE_TEXTURE_PAGE:
+            allocate_texture_page(r, cmd->u.allocate_texture_page.page_id, cmd->u.allocate_texture_page.size);
+            break;
+        case PF_RENDER_COMMAND_UPLOAD_TEXEL_DATA:
+            upload_texel_data(r, cmd->u.upload_texel_data.texels, cmd->u.upload_texel_data.texel_count,
+                              cmd->u.upload_texel_data.location);
+            break;
+        case PF_RENDER_COMMAND_DECLARE_RENDER_TARGET:
+            declare_render_target(r, cmd->u.declare_render_target.render_target_id, cmd->u.declare_render_target.location);
+            break;
+        case PF_RENDER_COMMAND_PUSH_RENDER_TARGET: {
+            const uint32_t id = cmd->u.push_render_target.render_target_id;
+            if (id >= r->render_targets.size() || !r->render_targets[id].declared)
+                throw Error(PF_CUDA_ERROR_PROTOCOL, "PushRenderTarget before DeclareRenderTarget");
+            verify_pending(r); // a deferred verification belongs to the target it drew to
+            r->target_stack.push_back(id);
+            break;
+        }
+        case PF_RENDER_COMMAND_POP_RENDER_TARGET:
+            if (r->target_stack.empty()) throw Error(PF_CUDA_ERROR_PROTOCOL, "PopRenderTarget without PushRenderTarget");
+            verify_pending(r);
+            r->target_stack.pop_back();
             break;
         case PF_RENDER_COMMAND_FINISH:
             r->stats.cpu_build_time_ns = cmd->u.finish.cpu_build_time_ns;
@@ -1369,12 +1576,6 @@ PFCudaStatus PFCudaRendererRenderCommand(PFCudaRendererRef r, const PFRenderComm
         case PF_RENDER_COMMAND_DRAW_TILES_D3D9:
             // Renderer::require_d3d11 (gpu/renderer.rs:1349-1360) panics here.
             throw Error(PF_CUDA_ERROR_WRONG_LEVEL, "D3D9-level command sent to the D3D11-level CUDA renderer");
-        case PF_RENDER_COMMAND_ALLOCATE_TEXTURE_PAGE:
-        case PF_RENDER_COMMAND_UPLOAD_TEXEL_DATA:
-        case PF_RENDER_COMMAND_DECLARE_RENDER_TARGET:
-        case PF_RENDER_COMMAND_PUSH_RENDER_TARGET:
-        case PF_RENDER_COMMAND_POP_RENDER_TARGET:
-            throw Error(PF_CUDA_ERROR_UNSUPPORTED, "texture pages / render targets are 'next' rows (SURVEY.md §8 f3, f4)");
         default:
             throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "unknown render command kind");
         }
@@ -1385,6 +1586,10 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
     return guarded(r, [&]() {
         if (!r->in_scene) throw Error(PF_CUDA_ERROR_PROTOCOL, "end_scene without begin_scene");
         r->in_scene = false;
+        if (!r->target_stack.empty()) {
+            r->target_stack.clear();
+            throw Error(PF_CUDA_ERROR_PROTOCOL, "end_scene with a render target still pushed");
+        }
         if (r->batches_drawn == 0) {
             // Nothing drawn: the frame is the clear colour (tile.cs.glsl LOAD_ACTION_CLEAR).
             const FbRect fb = framebuffer_tile_rect(r);
@@ -1404,11 +1609,7 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
             ca.fb = fb;
             ca.tile_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
             ca.tile_y1 = r->strip_y1 > r->strip_y0 ? r->strip_y1 : fb.max_y;
-            ca.dest = r->dest;
-            fill_destinations(r, ca);
-            ca.dest_pitch = r->dest_pitch;
-            ca.dest_w = r->options.dest_size.x;
-            ca.dest_h = r->options.dest_size.y;
+            fill_destinations(r, current_target(r), ca);
             ca.clear_color = clear_color(r);
             ca.work_counter = r->counters.ptr + 12;
             wait_for_gather(r, r->stream);
@@ -1432,6 +1633,21 @@ PFCudaStatus PFCudaRendererReadPixels(PFCudaRendererRef r, uint8_t *dst, size_t 
         wait_for_gather(r, r->stream); // the other ranks' strips
         PF_CUDA_CHECK(cudaMemcpy2DAsync(dst, stride, r->dest, r->dest_pitch, row, (size_t)r->options.dest_size.y,
                                         cudaMemcpyDeviceToHost, r->stream));
+        PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    });
+}
+
+PFCudaStatus PFCudaRendererReadTexturePage(PFCudaRendererRef r, uint32_t page_id, uint8_t *dst, size_t stride,
+                                           PFVector2I *size_out) {
+    return guarded(r, [&]() {
+        verify_pending(r);
+        if (page_id >= r->pages.size() || !r->pages[page_id]) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "texture page was never allocated");
+        const PFCudaRenderer::TexturePage &page = *r->pages[page_id];
+        if (size_out) *size_out = PFVector2I{page.width, page.height};
+        if (!dst) return; // size query
+        const size_t row = (size_t)page.width * 4;
+        if (stride < row) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "stride too small");
+        PF_CUDA_CHECK(cudaMemcpy2DAsync(dst, stride, page.pixels.ptr, row, row, (size_t)page.height, cudaMemcpyDeviceToHost, r->stream));
         PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
     });
 }

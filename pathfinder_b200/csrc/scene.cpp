@@ -121,6 +121,30 @@ struct Path {
     uint32_t segment_indices; // on-curve points = segments
 };
 
+// Scene::display_list (scene.rs:500-509): draw path ranges interleaved with render target pushes / pops.
+struct DisplayItem {
+    enum Kind : uint8_t { DRAW_PATHS, PUSH_RENDER_TARGET, POP_RENDER_TARGET } kind;
+    uint32_t a, b; // DRAW_PATHS: draw path ids [a, b); PUSH_RENDER_TARGET: a = render target id
+};
+struct RenderTargetDesc { // scene.rs:493-497
+    int32_t width, height;
+};
+// Paint::overlay for PaintContents::Pattern over a render target (paint.rs:108-146, pattern.rs:52-140).
+struct PatternOverlay {
+    uint32_t render_target;
+    Transform transform; // pattern space (render target pixels) -> scene space
+    PFFilter filter;
+};
+// One DrawTilesD3D11 batch of a scene with a display list (the general builder below).
+struct GeneralBatch {
+    std::vector<PFPropagateMetadataD3D11> propagate_metadata;
+    std::vector<PFDiceMetadataD3D11> dice_metadata;
+    std::vector<PFTilePathInfoD3D11> tile_path_info;
+    uint32_t tile_count = 0, column_count = 0, segment_count = 0;
+    bool has_color_texture = false;
+    PFTileBatchTexture color_texture{0, 0, 0};
+};
+
 std::atomic<uint32_t> g_next_scene_id{0}; // NEXT_SCENE_ID, scene.rs:34
 
 } // namespace
@@ -132,6 +156,12 @@ struct PFScene {
     std::vector<Path> draw_paths, clip_paths;
     std::vector<PFColorU> paints;
     std::unordered_map<uint32_t, uint16_t> paint_cache; // Palette::push_paint dedup (paint.rs:115-131)
+    // Render targets, pattern paints over them (paint id -> overlay) and the display list. A scene without
+    // render targets has the display list [DrawPaths(0..n)] and takes the cached single-batch build.
+    std::vector<RenderTargetDesc> render_targets;
+    std::unordered_map<uint16_t, PatternOverlay> overlays;
+    std::vector<DisplayItem> display_list;
+    std::vector<GeneralBatch> general_batches; // scratch of the general builder (kept alive while commands are sent)
     RectF bounds{0, 0, 0, 0};
     RectF view_box{0, 0, 0, 0};
     uint32_t id;
@@ -189,6 +219,36 @@ struct PFBuildOptions {
     float dilation[2] = {0, 0};
     bool subpixel_aa_enabled = false;
 };
+
+namespace {
+// Scene::push_draw_path (scene.rs:87-92): extend the trailing DrawPaths item or start a new one.
+void note_draw_paths_pushed(PFScene *s, uint32_t count) {
+    const uint32_t end = (uint32_t)s->draw_paths.size();
+    if (!s->display_list.empty() && s->display_list.back().kind == DisplayItem::DRAW_PATHS)
+        s->display_list.back().b = end;
+    else
+        s->display_list.push_back(DisplayItem{DisplayItem::DRAW_PATHS, end - count, end});
+}
+
+// Transform2F::inverse (geometry/src/transform2d.rs:289-293) and a * b (apply b first), in f32.
+Transform transform_inverse(const Transform &t) {
+    const float det = t.m11 * t.m22 - t.m12 * t.m21;
+    const float inv = 1.0f / det;
+    Transform r;
+    r.m11 = t.m22 * inv, r.m12 = -t.m12 * inv, r.m21 = -t.m21 * inv, r.m22 = t.m11 * inv;
+    r.tx = -(r.m11 * t.tx + r.m12 * t.ty);
+    r.ty = -(r.m21 * t.tx + r.m22 * t.ty);
+    return r;
+}
+Transform transform_mul(const Transform &a, const Transform &b) {
+    Transform r;
+    r.m11 = a.m11 * b.m11 + a.m12 * b.m21, r.m12 = a.m11 * b.m12 + a.m12 * b.m22;
+    r.m21 = a.m21 * b.m11 + a.m22 * b.m21, r.m22 = a.m21 * b.m12 + a.m22 * b.m22;
+    r.tx = a.m11 * b.tx + a.m12 * b.ty + a.tx;
+    r.ty = a.m21 * b.tx + a.m22 * b.ty + a.ty;
+    return r;
+}
+} // namespace
 
 namespace pf {
 void scene_note_borrowed(PFScene *s, cudaStream_t stream, int device) {
@@ -448,6 +508,7 @@ uint32_t PFScenePushDrawPath(PFSceneRef s, const PFVector2F *points, const uint8
     p.clip_path = clip_path_id;
     s->bounds = union_rect(s->bounds, p.bounds); // scene.rs:84-86
     s->draw_paths.push_back(p);
+    note_draw_paths_pushed(s, 1);
     s->epoch++;
     return (uint32_t)s->draw_paths.size() - 1;
 }
@@ -520,8 +581,52 @@ PFCudaStatus PFScenePushDrawPaths(PFSceneRef s, const PFVector2F *points, const 
         s->bounds = union_rect(s->bounds, p.bounds);
         s->draw_paths.push_back(p);
     }
+    if (path_count) note_draw_paths_pushed(s, (uint32_t)path_count);
     s->epoch++;
     return PF_CUDA_OK;
+}
+
+uint32_t PFScenePushRenderTarget(PFSceneRef s, int32_t width, int32_t height) {
+    if (!s || width <= 0 || height <= 0 || (int64_t)width * height > (1ll << 30)) {
+        pf::set_last_error("PFScenePushRenderTarget: bad size");
+        return PF_PATH_INDEX_NONE;
+    }
+    const uint32_t id = (uint32_t)s->render_targets.size(); // Palette::push_render_target (paint.rs:133-137)
+    s->render_targets.push_back(RenderTargetDesc{width, height});
+    s->display_list.push_back(DisplayItem{DisplayItem::PUSH_RENDER_TARGET, id, 0});
+    s->epoch++;
+    return id;
+}
+
+void PFScenePopRenderTarget(PFSceneRef s) {
+    s->display_list.push_back(DisplayItem{DisplayItem::POP_RENDER_TARGET, 0, 0});
+    s->epoch++;
+}
+
+uint16_t PFScenePushPaintRenderTargetPattern(PFSceneRef s, uint32_t render_target_id, const PFTransform2F *pattern_transform,
+                                             const PFFilter *filter) {
+    if (!s || render_target_id >= s->render_targets.size() || s->paints.size() >= 65535) {
+        pf::set_last_error("PFScenePushPaintRenderTargetPattern: unknown render target");
+        return 0xffff;
+    }
+    if (filter && filter->kind != PF_FILTER_NONE && filter->kind != PF_FILTER_TEXT) {
+        pf::set_last_error("PFScenePushPaintRenderTargetPattern: only PatternFilter::Text is implemented");
+        return 0xffff;
+    }
+    PatternOverlay overlay;
+    overlay.render_target = render_target_id;
+    if (pattern_transform) {
+        overlay.transform.m11 = pattern_transform->matrix.m00, overlay.transform.m12 = pattern_transform->matrix.m01;
+        overlay.transform.m21 = pattern_transform->matrix.m10, overlay.transform.m22 = pattern_transform->matrix.m11;
+        overlay.transform.tx = pattern_transform->vector.x, overlay.transform.ty = pattern_transform->vector.y;
+    }
+    memset(&overlay.filter, 0, sizeof(overlay.filter));
+    if (filter) overlay.filter = *filter;
+    const uint16_t id = (uint16_t)s->paints.size();
+    s->paints.push_back(PFColorU{255, 255, 255, 255}); // Paint::from_pattern: base colour white (paint.rs:138-146)
+    s->overlays.emplace(id, overlay);                    // (pattern paints are never deduplicated)
+    s->epoch++;
+    return id;
 }
 
 uint32_t PFSceneGetDrawPathCount(PFSceneRef s) { return (uint32_t)s->draw_paths.size(); }
@@ -579,9 +684,32 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
 
     // Paint data (builder.rs:174-180): one TextureMetadataEntry per paint (paint.rs:641-659).
     // Paints are append-only, so (scene id, paint count) identifies the table.
-    const uint64_t paint_key = mix_key(mix_key(0x9a1f7u, s->id), s->paints.size());
+    uint64_t paint_key = mix_key(mix_key(0x9a1f7u, s->id), s->paints.size());
+    if (!s->overlays.empty()) { // texture transforms depend on the build transform (paint.rs:637)
+        uint32_t bits[6];
+        const float f[6] = {opts->transform.m11, opts->transform.m21, opts->transform.m12, opts->transform.m22,
+                            opts->transform.tx,  opts->transform.ty};
+        memcpy(bits, f, sizeof(bits));
+        for (uint32_t v : bits) paint_key = mix_key(paint_key, v);
+        paint_key = mix_key(paint_key, s->epoch);
+    }
+    // Render targets first (Palette::build_paint_info, paint.rs:399-437: AllocateTexturePage and DeclareRenderTarget
+    // precede the metadata). One page per render target, the target covering the whole page; page ids = target ids.
+    for (size_t i = 0; i < s->render_targets.size(); i++) {
+        PFRenderCommand page = make_command(PF_RENDER_COMMAND_ALLOCATE_TEXTURE_PAGE);
+        page.u.allocate_texture_page.page_id = (uint32_t)i;
+        page.u.allocate_texture_page.size = PFVector2I{s->render_targets[i].width, s->render_targets[i].height};
+        SEND(page);
+        PFRenderCommand declare = make_command(PF_RENDER_COMMAND_DECLARE_RENDER_TARGET);
+        declare.u.declare_render_target.render_target_id = (uint32_t)i;
+        declare.u.declare_render_target.location =
+            PFTextureLocation{(uint32_t)i, PFRectI{{0, 0}, {s->render_targets[i].width, s->render_targets[i].height}}};
+        SEND(declare);
+    }
     if (s->built_paint_key != paint_key) {
         s->texture_metadata.resize(s->paints.size());
+        // render_transform = the 2-D build transform inverted (builder.rs:168-171)
+        const Transform render_transform = transform_inverse(opts->transform);
         for (size_t i = 0; i < s->paints.size(); i++) {
             PFTextureMetadataEntry &e = s->texture_metadata[i];
             memset(&e, 0, sizeof(e));
@@ -590,6 +718,18 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
             e.color_0_combine_mode = PF_COLOR_COMBINE_MODE_NONE;
             e.blend_mode = PF_BLEND_MODE_SRC_OVER;
             e.filter.kind = PF_FILTER_NONE;
+            auto overlay = s->overlays.find((uint16_t)i);
+            if (overlay == s->overlays.end()) continue;
+            // calculate_texture_transforms, PatternSource::RenderTarget (paint.rs:626-637):
+            //   translate(rect_to_uv(rect, scale).lower_left()) * scale(scale * (1, -1)) * pattern.transform().inverse()
+            //   * render_transform — v runs bottom-up over a render target (the GL convention, see pf_cuda.h).
+            const RenderTargetDesc &rt = s->render_targets[overlay->second.render_target];
+            const float sx = 1.0f / (float)rt.width, sy = 1.0f / (float)rt.height;
+            const Transform to_pattern = transform_mul(transform_inverse(overlay->second.transform), render_transform);
+            e.color_0_transform.matrix = PFMatrix2x2F{sx * to_pattern.m11, sx * to_pattern.m12, -sy * to_pattern.m21, -sy * to_pattern.m22};
+            e.color_0_transform.vector = PFVector2F{sx * to_pattern.tx, 1.0f - sy * to_pattern.ty};
+            e.color_0_combine_mode = PF_COLOR_COMBINE_MODE_SRC_IN; // create_texture_metadata (paint.rs:649-653)
+            e.filter = overlay->second.filter;
         }
         s->built_paint_key = paint_key;
     }
@@ -632,6 +772,145 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         sink->has_last_scene = 1;
         sink->last_scene_id = s->id;
         sink->last_scene_epoch = s->upload_serial;
+    }
+
+    bool display_ops = false; // a push / pop anywhere in the display list
+    for (const DisplayItem &item : s->display_list) display_ops |= item.kind != DisplayItem::DRAW_PATHS;
+    if (display_ops || !s->render_targets.empty() || !s->overlays.empty()) {
+        // A scene with a display list: one batch per DrawPaths item, split again wherever the colour texture
+        // changes (build_tile_batches / build_tile_batches_for_draw_path_display_item / fixup_batch_for_new_path_if_possible,
+        // builder.rs:327-357,886-940,1227-1243). Built sequentially and afresh every frame (content_key = 0): these
+        // scenes are a handful of batches around a text page, not the 100k-path case the cached builder below serves.
+        const Transform identity_transform;
+        const Transform &gxf = prepared ? identity_transform : opts->transform;
+        s->general_batches.clear();
+        size_t n_batches = 0;
+        for (const DisplayItem &item : s->display_list) n_batches += item.kind == DisplayItem::DRAW_PATHS ? (item.b - item.a) : 0;
+        s->general_batches.reserve(n_batches + 1); // (upper bound: pointers into the vector stay valid)
+        uint32_t next_batch_id = 32; // MAX_CLIP_BATCHES
+        auto send_batch = [&](GeneralBatch &gb) -> PFCudaStatus {
+            if (gb.propagate_metadata.empty()) return PF_CUDA_OK;
+            PFRenderCommand draw = make_command(PF_RENDER_COMMAND_DRAW_TILES_D3D11);
+            PFTileBatchDataD3D11 &b = draw.u.draw_tiles_d3d11.tile_batch_data;
+            b.batch_id = next_batch_id++;
+            b.path_count = (uint32_t)gb.propagate_metadata.size();
+            b.tile_count = gb.tile_count;
+            b.segment_count = gb.segment_count;
+            b.prepare_info.backdrops = nullptr;
+            b.prepare_info.backdrop_count = 0;
+            b.prepare_info.propagate_metadata = gb.propagate_metadata.data();
+            b.prepare_info.dice_metadata = gb.dice_metadata.data();
+            b.prepare_info.tile_path_info = gb.tile_path_info.data();
+            b.prepare_info.transform.matrix = PFMatrix2x2F{gxf.m11, gxf.m12, gxf.m21, gxf.m22};
+            b.prepare_info.transform.vector = PFVector2F{gxf.tx, gxf.ty};
+            b.path_source = PF_PATH_SOURCE_DRAW;
+            b.has_clipped_path_info = 0;
+            b.content_key = 0;
+            draw.u.draw_tiles_d3d11.has_color_texture = gb.has_color_texture ? 1 : 0;
+            draw.u.draw_tiles_d3d11.color_texture = gb.color_texture;
+            return listener(&draw, userdata);
+        };
+        int nesting = 0;
+        for (const DisplayItem &item : s->display_list) {
+            if (item.kind == DisplayItem::PUSH_RENDER_TARGET) {
+                PFRenderCommand push = make_command(PF_RENDER_COMMAND_PUSH_RENDER_TARGET);
+                push.u.push_render_target.render_target_id = item.a;
+                SEND(push);
+                nesting++;
+                continue;
+            }
+            if (item.kind == DisplayItem::POP_RENDER_TARGET) {
+                if (nesting == 0) {
+                    pf::set_last_error("PFScenePopRenderTarget without a matching push");
+                    return PF_CUDA_ERROR_PROTOCOL;
+                }
+                PFRenderCommand pop = make_command(PF_RENDER_COMMAND_POP_RENDER_TARGET);
+                SEND(pop);
+                nesting--;
+                continue;
+            }
+            s->general_batches.emplace_back();
+            GeneralBatch *gb = &s->general_batches.back();
+            for (uint32_t i = item.a; i < item.b; i++) {
+                const Path &p = s->draw_paths[i];
+                if (p.blend_mode != PF_BLEND_MODE_SRC_OVER) {
+                    pf::set_last_error("only BlendMode::SrcOver is on the hot path");
+                    return PF_CUDA_ERROR_UNSUPPORTED;
+                }
+                if (p.clip_path != PF_CLIP_PATH_NONE) {
+                    pf::set_last_error("clip paths in a scene with render targets are not implemented");
+                    return PF_CUDA_ERROR_UNSUPPORTED;
+                }
+                // prepare_draw_path_for_gpu_binning (builder.rs:1058-1095)
+                RectF path_bounds = prepared ? s->prepared_draw_bounds[i] : gxf.is_identity() ? p.bounds : gxf.apply_rect(p.bounds);
+                RectF clipped;
+                const bool has_outline = p.first_contour != p.end_contour;
+                if (!((has_outline || !prepared) && rect_intersection(path_bounds, s->view_box, clipped))) continue;
+                const float k = 1.0f / 16.0f;
+                PFRectI tile_rect;
+                tile_rect.origin.x = (int32_t)floorf(clipped.min_x * k);
+                tile_rect.origin.y = (int32_t)floorf(clipped.min_y * k);
+                tile_rect.lower_right.x = (int32_t)ceilf(clipped.max_x * k);
+                tile_rect.lower_right.y = (int32_t)ceilf(clipped.max_y * k);
+                // the path's colour texture (PaintMetadata::tile_batch_texture, paint.rs:802-804)
+                auto overlay = s->overlays.find(p.paint);
+                const bool has_texture = overlay != s->overlays.end();
+                const PFTileBatchTexture texture{has_texture ? overlay->second.render_target : 0u, 0, PF_PAINT_COMPOSITE_OP_SRC_IN};
+                if (has_texture) {
+                    if (gb->has_color_texture && gb->color_texture.page != texture.page) { // batch break
+                        s->general_batches.emplace_back();
+                        gb = &s->general_batches.back();
+                    }
+                    gb->has_color_texture = true;
+                    gb->color_texture = texture;
+                }
+                const uint32_t w = (uint32_t)(tile_rect.lower_right.x - tile_rect.origin.x),
+                               h = (uint32_t)(tile_rect.lower_right.y - tile_rect.origin.y);
+                const uint32_t bi = (uint32_t)gb->propagate_metadata.size();
+                // BuiltDrawPath::new (builder.rs:80-94): occludes = opaque paint && SrcOver; a render-target pattern
+                // is never "obviously opaque" (pattern.rs:264-272).
+                const bool occludes = !has_texture && s->paints[p.paint].a == 255;
+                PFPropagateMetadataD3D11 pm;
+                memset(&pm, 0, sizeof(pm));
+                pm.tile_rect = tile_rect;
+                pm.tile_offset = gb->tile_count;
+                pm.path_index = bi;
+                pm.z_write = occludes ? 1 : 0;
+                pm.clip_path_index = PF_PATH_INDEX_NONE;
+                pm.backdrop_offset = gb->column_count;
+                gb->propagate_metadata.push_back(pm);
+                gb->dice_metadata.push_back(PFDiceMetadataD3D11{i, s->draw_segment_ranges[2 * i], gb->segment_count, 0});
+                PFTilePathInfoD3D11 tp;
+                tp.tile_min_x = (int16_t)tile_rect.origin.x;
+                tp.tile_min_y = (int16_t)tile_rect.origin.y;
+                tp.tile_max_x = (int16_t)tile_rect.lower_right.x;
+                tp.tile_max_y = (int16_t)tile_rect.lower_right.y;
+                tp.first_tile_index = gb->tile_count;
+                tp.color = p.paint;
+                tp.ctrl = p.fill_rule == PF_FILL_RULE_EVEN_ODD ? PF_TILE_CTRL_MASK_EVEN_ODD : PF_TILE_CTRL_MASK_WINDING;
+                tp.backdrop = 0;
+                gb->tile_path_info.push_back(tp);
+                gb->tile_count += w * h;
+                gb->column_count += w;
+                gb->segment_count += s->draw_segment_ranges[2 * i + 1] - s->draw_segment_ranges[2 * i];
+            }
+            // the batches of this display item, in order
+            for (GeneralBatch &b : s->general_batches) {
+                if (b.tile_path_info.empty() || b.segment_count == 0xffffffffu) continue;
+                st = send_batch(b);
+                if (st != PF_CUDA_OK) return st;
+                b.segment_count = 0xffffffffu; // sent
+            }
+        }
+        if (nesting != 0) {
+            pf::set_last_error("a render target is still pushed at the end of the display list");
+            return PF_CUDA_ERROR_PROTOCOL;
+        }
+        PFRenderCommand finish = make_command(PF_RENDER_COMMAND_FINISH);
+        finish.u.finish.cpu_build_time_ns =
+            (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - start_time).count();
+        SEND(finish);
+        return PF_CUDA_OK;
     }
 
     // build_tile_batches at the D3D11 level (builder.rs:327-357, 886-1056): solid colours never

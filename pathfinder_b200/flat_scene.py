@@ -152,6 +152,18 @@ class SceneBuilderPy:
     def close(self):
         self._end_contour()
 
+    def add_outline(self, points, point_flags, contour_offsets):
+        """Appends whole contours (points + PointFlags, contour i = points [offsets[i], offsets[i + 1])) to the
+        path being built — the form PFSvgPathDataToOutline / PFOutlineStrokeToFill return."""
+        self._end_contour()
+        pts = np.asarray(points, dtype=np.float32).reshape(-1, 2)
+        for i in range(len(contour_offsets) - 1):
+            a, b = int(contour_offsets[i]), int(contour_offsets[i + 1])
+            if b > a:
+                self._points += [(float(x), float(y)) for x, y in pts[a:b]]
+                self._flags += [int(f) for f in point_flags[a:b]]
+                self._contour_offsets.append(len(self._points))
+
     def _end_contour(self):
         if self._open and len(self._points) > self._contour_offsets[-1]:
             self._contour_offsets.append(len(self._points))

@@ -209,3 +209,38 @@ def text_page(n_glyphs: int = 10000, size: int = 2048, seed: int = 0x5EED0003, l
     return FlatScene(np.concatenate(points).astype(np.float32), np.concatenate(flags), contour_offsets, path_contour_offsets,
                      np.zeros(n_paths, np.uint8), np.zeros(n_paths, np.uint16), np.asarray([[0, 0, 0, 255]], np.uint8),
                      (0.0, 0.0, float(size), float(size)), f"text{n_glyphs}@{size}/{layout}", {"seed": seed, "size": size})
+
+
+def text_page_subpixel(n_glyphs: int, size: int, layout: str = "grid"):
+    """BASELINE.json configs[2] the way the reference's demo renders text with subpixel AA
+    (demo/common/src/lib.rs:804-834): the page's glyphs, white, x scaled by 3, for a render target three times as
+    wide as the page; one page-sized rectangle then samples that target through PatternFilter::Text. Returns the
+    glyph scene (view box (0, 0, 3 * size, size)); `subpixel_scene` below assembles the whole Scene."""
+    flat = text_page(n_glyphs, size, layout=layout)
+    wide = flat.with_view_box((0.0, 0.0, 3.0 * size, float(size)))
+    pts = wide.points.copy()
+    pts[:, 0] = pts[:, 0] * np.float32(3.0)  # what Transform2F::from_scale(vec2f(3.0, 1.0)) does to a point (scene.rs:260-262)
+    wide.points = pts
+    wide.paint_colors = np.asarray([[255, 255, 255, 255]], np.uint8)  # the filter reads the red channel as coverage
+    wide.paints = np.zeros_like(wide.paints)
+    wide.name = f"text{n_glyphs}@{size}/subpixel"
+    return wide
+
+
+def subpixel_scene(wide: FlatScene, size: int, fg=(0.0, 0.0, 0.0), bg=(1.0, 1.0, 1.0),
+                   kernel=(0.033165660, 0.102074051, 0.221434336, 0.286651906), gamma: bool = True):
+    """The demo's wrapping (build_svg_tree, demo/common/src/lib.rs:804-834) as an api.Scene: render target 3 * size
+    wide <- glyphs; page rectangle painted with the target as a pattern under PatternFilter::Text
+    (defringing kernel DEFRINGING_KERNEL_CORE_GRAPHICS by default). The pattern transform scale(1/3, 1) makes page
+    pixel x sample target texel 3x + 1 (its centre subpixel)."""
+    from . import api
+    scene = api.Scene()
+    scene.set_view_box((0.0, 0.0, 3.0 * size, float(size)))
+    target = scene.push_render_target(3 * size, size)
+    scene.push_flat(wide)
+    scene.pop_render_target()
+    paint = scene.push_render_target_pattern(target, transform=(1.0 / 3.0, 0.0, 0.0, 1.0, 0.0, 0.0),
+                                             text_filter={"fg": fg, "bg": bg, "kernel": kernel, "gamma": gamma})
+    rect = np.asarray([[0, 0], [size, 0], [size, size], [0, size]], np.float32)
+    scene.push_draw_path(rect, np.zeros(4, np.uint8), np.asarray([0, 4], np.uint32), paint)
+    return scene

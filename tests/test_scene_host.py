@@ -278,3 +278,56 @@ def test_push_calls_refuse_arguments_they_could_not_index():
     assert scene.draw_path_count() == 1 and lib.PFSceneGetEpoch(scene._h) == epoch
     assert push_many([0, 3, 6], [0, 1, 2], [paint, paint], [0, 1]) == 0
     assert scene.draw_path_count() == 3
+
+
+def test_display_list_with_a_render_target_becomes_the_reference_command_order():
+    """Scene::push_render_target / pop_render_target + a pattern paint (scene.rs:110-123, paint.rs:138-146): the
+    build emits AllocateTexturePage and DeclareRenderTarget before the metadata, one DrawTilesD3D11 per display item
+    between PushRenderTarget / PopRenderTarget, and the batch that samples the target names its page
+    (builder.rs:327-357, paint.rs:399-437,626-659)."""
+    from pathfinder_b200 import scenes
+    size = 128
+    wide = scenes.text_page_subpixel(40, size, layout="lines")
+    scene = scenes.subpixel_scene(wide, size)
+    kinds, draws, paints = [], [], []
+
+    def listener(cmd_ptr, _userdata):
+        cmd = cmd_ptr.contents
+        kinds.append(cmd.kind)
+        if cmd.kind == L.PF_RENDER_COMMAND_DRAW_TILES_D3D11:
+            d = cmd.u.draw_tiles_d3d11
+            draws.append((d.tile_batch_data.path_count, d.has_color_texture, d.color_texture.page, d.tile_batch_data.batch_id))
+        elif cmd.kind == L.PF_RENDER_COMMAND_UPLOAD_TEXTURE_METADATA:
+            e = C.cast(cmd.u.upload_texture_metadata.entries, C.POINTER(L.PFTextureMetadataEntry))
+            for i in range(cmd.u.upload_texture_metadata.entry_count):
+                t = e[i].color_0_transform
+                paints.append((e[i].color_0_combine_mode, e[i].filter.kind, e[i].filter.flags,
+                               (t.matrix.m00, t.matrix.m01, t.matrix.m10, t.matrix.m11, t.vector.x, t.vector.y)))
+        elif cmd.kind == L.PF_RENDER_COMMAND_ALLOCATE_TEXTURE_PAGE:
+            assert (cmd.u.allocate_texture_page.size.x, cmd.u.allocate_texture_page.size.y) == (3 * size, size)
+        elif cmd.kind == L.PF_RENDER_COMMAND_DECLARE_RENDER_TARGET:
+            r = cmd.u.declare_render_target.location.rect
+            assert (r.origin.x, r.origin.y, r.lower_right.x, r.lower_right.y) == (0, 0, 3 * size, size)
+        return 0
+
+    sink = L.PFSceneSinkState(0, 0, 0)
+    fn = L.LISTENER_FN(listener)
+    assert L.lib().PFSceneBuild(scene._h, api.BuildOptions()._h, C.byref(sink), fn, None) == 0
+    K = L
+    assert kinds == [K.PF_RENDER_COMMAND_START, K.PF_RENDER_COMMAND_ALLOCATE_TEXTURE_PAGE, K.PF_RENDER_COMMAND_DECLARE_RENDER_TARGET,
+                     K.PF_RENDER_COMMAND_UPLOAD_TEXTURE_METADATA, K.PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11,
+                     K.PF_RENDER_COMMAND_PUSH_RENDER_TARGET, K.PF_RENDER_COMMAND_DRAW_TILES_D3D11,
+                     K.PF_RENDER_COMMAND_POP_RENDER_TARGET, K.PF_RENDER_COMMAND_DRAW_TILES_D3D11, K.PF_RENDER_COMMAND_FINISH]
+    assert draws[0][1] == 0 and draws[0][0] > 30                      # the glyphs, no colour texture
+    assert draws[1][:3] == (1, 1, 0) and draws[1][3] == draws[0][3] + 1  # the page rectangle samples page 0
+    solid, pattern = paints
+    assert solid[:2] == (L.PF_COLOR_COMBINE_MODE_NONE, L.PF_FILTER_NONE)
+    assert pattern[0] == L.PF_COLOR_COMBINE_MODE_SRC_IN and pattern[1] == L.PF_FILTER_TEXT
+    assert pattern[2] == (L.PF_FILTER_FLAG_TEXT_HAS_KERNEL | L.PF_FILTER_FLAG_TEXT_GAMMA_CORRECTION)
+    # pixel centre (x + 0.5, y + 0.5) of the page -> u = (3x + 1.5) / 3W, v = 1 - (y + 0.5) / H (bottom-up, like the GL backend)
+    m00, m01, m10, m11, tx, ty = pattern[3]
+    assert np.allclose([m00, m01, m10, m11, tx, ty], [1.0 / size, 0.0, 0.0, -1.0 / size, 0.0, 1.0], atol=1e-7)
+    # a pop without a push is refused
+    bad = api.Scene()
+    bad.pop_render_target()
+    assert L.lib().PFSceneBuild(bad._h, api.BuildOptions()._h, C.byref(L.PFSceneSinkState(0, 0, 0)), fn, None) == L.PF_CUDA_ERROR_PROTOCOL

@@ -51,3 +51,31 @@ def test_stem_darkened_text(area_lut):
     """Stem darkening as the reference's demo sets it: dilation = STEM_DARKENING_FACTORS * font size
     (content/src/effects.rs:32; demo/common/src/lib.rs:273-276), here for 16 px."""
     check(scenes.text_page(2000, 1024, layout="lines"), None, area_lut, dilation=(0.0121 * 16, 0.0121 * 1.25 * 16))
+
+
+def test_svg_paths_and_strokes_render(area_lut):
+    """SURVEY.md §8 f2 end to end on the device: SVG path data (relative commands, smooth curves, arcs) through
+    PFSvgPathDataToOutline, strokes of every join and cap through PFOutlineStrokeToFill, into a Scene, through the
+    CUDA pipeline — lists bit-exact and RGBA within 1/255 of the oracle given the same outlines."""
+    from pathfinder_b200 import api
+    from pathfinder_b200.flat_scene import FILL_RULE_EVEN_ODD, FILL_RULE_WINDING, SceneBuilderPy
+    shapes = [
+        ("M40 40 h120 v90 h-120z M70 60 v50 h60 v-50z", (200, 40, 40, 255), FILL_RULE_EVEN_ODD, None),
+        ("M30 200 C80 120 160 280 220 190 S300 120 330 210 q10 40 -40 50 t-60 -20z", (30, 90, 200, 200), FILL_RULE_WINDING, None),
+        ("M260 60 a50 30 20 1 0 80 20 a20 20 0 0 1 -80 -20z", (20, 160, 60, 230), FILL_RULE_WINDING, None),
+        ("M40 320 L120 260 200 330 280 250 360 330", (0, 0, 0, 255), FILL_RULE_WINDING, (9.0, "miter", "butt")),
+        ("M60 360 C120 300 180 420 240 350", (160, 0, 160, 180), FILL_RULE_WINDING, (14.0, "round", "round")),
+        ("M300 280 l40 60 l30 -70", (220, 120, 0, 255), FILL_RULE_WINDING, (6.0, "bevel", "square")),
+        ("M200 100 a40 40 0 1 1 0.1 0z", (90, 90, 90, 128), FILL_RULE_WINDING, (3.5, "miter", "butt")),
+    ]
+    b = SceneBuilderPy((0, 0, 704, 704))
+    for d, rgba, rule, stroke in shapes:
+        pts, flags, offsets, closed = api.svg_path_to_outline(d)
+        if stroke is not None:
+            width, join, cap = stroke
+            pts, flags, offsets = api.stroke_to_fill(pts, flags, offsets, closed, width, line_join=join, line_cap=cap)
+        b.add_outline(pts, flags, offsets)
+        b.end_path(rgba, rule)
+    flat = b.finish("svg-strokes")
+    assert flat.n_paths == len(shapes)
+    check(flat, (1.7, 0.0, 0.0, 1.7, 10.0, -20.0), area_lut)
