@@ -51,7 +51,9 @@ def workload_scenes(which: str):
     if which == "random1m":
         out.append(("random1m@16384", scenes.random_paths(1000000, 16384, 0x5EED0005), None, 16384))
     if which == "text10k":
-        out.append(("text10k@2048", scenes.text_page(10000, 2048), None, 2048))
+        # BASELINE.json configs[2]: the glyphs, white and x-scaled by 3, for the 3x-wide render target; device_frames()
+        # wraps them like the reference's demo (render target + page rectangle under PatternFilter::Text)
+        out.append(("text10k@2048/subpixel", scenes.text_page_subpixel(10000, 2048), None, 2048))
     if which == "smoke":
         flat, xf = scenes.tiger(512)
         out.append(("tiger@512", flat, xf, 512))
@@ -65,7 +67,8 @@ WORKLOAD_NAMES = {
     "tiger4k": "tiger@4096 (winding + even-odd variants)",
     "random100k": "random100k@8192",
     "random1m": "random1m@16384",
-    "text10k": "text page: 10,000 Roboto glyphs at 12-16 px @2048 (outlines only)",
+    "text10k": "text page: 10,000 Roboto glyphs at 12-16 px @2048, subpixel AA (3x-wide render target + text filter: "
+               "defringing kernel, gamma LUT), stem darkening",
     "smoke": "tiger@512",
 }
 
@@ -122,13 +125,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_scene_and_options(flat, xf):
+STEM_DARKENING_16PX = (0.0121 * 16 * 3, 0.0121 * 1.25 * 16)  # STEM_DARKENING_FACTORS * font size, x in subpixels
+
+
+def oracle_scene_and_options(flat, xf, dilation=(0.0, 0.0)):
     from oracle import pf_oracle as O
     sc = O.make_scene(points=flat.points, point_flags=flat.point_flags, contour_offsets=flat.contour_offsets,
                       draw_contour_ranges=flat.contour_ranges(), draw_fill_rules=flat.fill_rules,
                       draw_paints=flat.paints, paint_colors=flat.paint_colors, view_box=flat.view_box)
     t = None if xf is None else (xf[0], xf[2], xf[1], xf[3], xf[4], xf[5])
-    return sc, O.make_options(transform=t)
+    return sc, O.make_options(transform=t, dilation=dilation)
 
 
 def cpu_tiler_step(prepared, n_threads: int):
@@ -145,8 +151,8 @@ def cpu_tiler_step(prepared, n_threads: int):
 def prepare_cpu(scene_list):
     from oracle import pf_oracle as O
     prepared = []
-    for _name, flat, xf, _size in scene_list:
-        sc, opt = oracle_scene_and_options(flat, xf)
+    for name, flat, xf, _size in scene_list:
+        sc, opt = oracle_scene_and_options(flat, xf, STEM_DARKENING_16PX if name.endswith("/subpixel") else (0.0, 0.0))
         b = O.Built(sc, opt, n_threads=max(1, os.cpu_count() or 1))
         prepared.append((sc, opt, b.line_segment_count))
         b.close()
@@ -212,10 +218,12 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOAD_NAMES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="nccl", choices=["peer", "nccl"],
-                    help="N > 1: 'nccl' = PFCudaRendererGatherFrame (ncclAllGather issued by the library on the renderer's "
-                         "gather stream, overlapped with the next frame); 'peer' = the fill+tile kernels store every tile "
-                         "into all peers' frames over NVLink (IPC-mapped buffers) + one barrier")
+    ap.add_argument("--gather", default="tiles", choices=["tiles", "nccl", "peer"],
+                    help="N > 1, how the frame is assembled on every rank. 'tiles' (default) = PFCudaRendererGatherFrame in "
+                         "tile mode: compact exports (4 B per single-colour tile, 1 KB per other tile) pulled from the peers' "
+                         "memory over NVLink after an NCCL barrier; 'nccl' = the same call in frame mode (ncclAllGather of the "
+                         "finished strips); 'peer' = the fill+tile kernels store every tile into all peers' frames "
+                         "(IPC-mapped buffers) + one barrier. All overlap the next frame's stages.")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3
@@ -279,8 +287,13 @@ def main():
         f.stream = torch.cuda.Stream()
         f.renderer.set_stream(f.stream.cuda_stream)
         f.renderer.set_dest_device_pointer(f.full.data_ptr(), size * 4)
-        f.scene = api.Scene.from_flat(flat)
-        f.options = api.BuildOptions(transform=None if xf is None else api.Transform2F(*xf))
+        if name.endswith("/subpixel"):
+            from pathfinder_b200 import scenes as _scenes
+            f.scene = _scenes.subpixel_scene(flat, size)
+            f.options = api.BuildOptions(dilation=STEM_DARKENING_16PX)
+        else:
+            f.scene = api.Scene.from_flat(flat)
+            f.options = api.BuildOptions(transform=None if xf is None else api.Transform2F(*xf))
         # The metric counts the flattened segments of the WHOLE frame (fixed work, independent of
         # N): one untimed full-frame render gives the count before the strip is set.
         f.scene.build_and_render(f.renderer, f.options)
@@ -289,11 +302,15 @@ def main():
         # the next use of the renderer instead of stalling the host at the end of every batch.
         f.renderer.set_deferred_verification(True)
         if world > 1:
-            if args.gather == "nccl":
+            if args.gather in ("nccl", "tiles"):
                 # The library assembles the frame: rank 0 creates the group id, torch.distributed only ships it.
                 box = [api.gather_create_id() if rank == 0 else None]
                 dist.broadcast_object_list(box, src=0)
                 f.renderer.gather_init(box[0], rank, world)  # also sets this rank's strip
+                if args.gather == "nccl":
+                    f.renderer.gather_set_mode(api.CudaRenderer.GATHER_MODE_FRAME)
+                else:  # tiles: refuse to report a frame-mode number under the tile-mode label
+                    f.renderer.gather_set_mode(api.CudaRenderer.GATHER_MODE_TILES)
             else:
                 f.renderer.set_strip(f.y0, f.y1)
             f.strip_view = f.full[f.y0 * 16:min(f.y1 * 16, size)]
@@ -429,7 +446,7 @@ def main():
     barrier()
     for f in frames:
         totals, batches = f.renderer.accumulated_times()
-        assert batches == args.steps, (batches, args.steps)
+        assert batches and batches % args.steps == 0, (batches, args.steps)  # (several draw batches per frame: render targets)
         stage_acc[f.name] = totals
     dev_s = start.elapsed_time(end) / 1e3
     t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
@@ -444,24 +461,29 @@ def main():
     isolated_ms, isolated_stage = {}, {}
     for f in frames:
         f.renderer.set_timing_enabled(False)
-        f.renderer.set_timing_enabled(True)  # resets the accumulated stage times
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(stream)
-        f.stream.wait_stream(stream)
-        for _ in range(args.steps):
-            render_frame(f, False)
-        if dist is not None and not f.peer:
-            f.renderer.gather_wait()
-        stream.wait_stream(f.stream)
-        s1.record(stream)
-        barrier()
+
+        def isolated_run():
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            f.stream.wait_stream(stream)
+            for _ in range(args.steps):
+                render_frame(f, False)
+            if dist is not None and not f.peer:
+                f.renderer.gather_wait()
+            stream.wait_stream(f.stream)
+            s1.record(stream)
+            barrier()
+            ms = torch.tensor([s0.elapsed_time(s1) / args.steps], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item())
+
+        isolated_ms[f.name] = isolated_run()  # without the stage events (eight event records per batch)
+        f.renderer.set_timing_enabled(True)   # resets the accumulated stage times
+        isolated_run()
         totals, batches = f.renderer.accumulated_times()
-        assert batches == args.steps, (batches, args.steps)
-        ms = torch.tensor([s0.elapsed_time(s1) / args.steps], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        isolated_ms[f.name] = float(ms.item())
+        assert batches and batches % args.steps == 0, (batches, args.steps)
         isolated_stage[f.name] = {k: v / args.steps for k, v in totals.items()}
         f.renderer.set_timing_enabled(False)
 
@@ -535,7 +557,16 @@ def main():
             seg_cpu += n
             reps += 1
         s1, n1 = cpu_tiler_step(prepared, 1)
+        # how the port scales with threads (one build each): the all-core figure is the reported baseline, and how
+        # far it is from cores x the single-thread figure says how much a better-parallelised tiler could gain
+        scaling = {"1": n1 / s1 / 1e9}
+        for nt in (2, 4, 8, 16, 32, 64):
+            if nt < cores:
+                st_, nn = cpu_tiler_step(prepared, nt)
+                scaling[str(nt)] = nn / st_ / 1e9
+        scaling[str(cores)] = seg_cpu / t_cpu / 1e9
         cpu_baseline = {"value": seg_cpu / t_cpu / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+                        "thread_scaling": scaling,
                         "sample": f"{reps} full CPU-tiler builds of every scene of the workload (scene build only: "
                                   "flatten + tile + propagate + pack, the reference's cpu_build_time)",
                         "single_thread_value": n1 / s1 / 1e9}
@@ -551,7 +582,8 @@ def main():
                    "input_gsegments_per_s": inputs_per_step * args.steps / dev_s / 1e9,
                    "gfills_per_s": fills_per_step * args.steps / dev_s / 1e9,
                    "parallelism": f"tile-strip x{world}" + ((" + fused peer-store gather (NVLink P2P) + barrier" if args.gather == "peer"
-                                                             else " + ncclAllGather issued by the library (PFCudaRendererGatherFrame), overlapped with the next frame") if world > 1 else ""),
+                                                             else (" + compact tile exports pulled over NVLink by the library (PFCudaRendererGatherFrame, tile mode), overlapped with the next frame" if args.gather == "tiles"
+                                                                   else " + ncclAllGather issued by the library (PFCudaRendererGatherFrame, frame mode), overlapped with the next frame")) if world > 1 else ""),
                    "l2": "inputs larger than L2: a step touches > 1 GB of stage buffers and frames",
                    "streams": "the frames of a step are independent scenes and render concurrently on one CUDA stream each "
                               "(forked from / joined to the timing stream); no host wait inside the timed region "

@@ -403,9 +403,19 @@ PFCudaStatus PFCudaGatherCreateId(PFCudaGatherId *id_out);
  * strip to PFCudaStripOfRank of the destination's tile rows. The destination must have contiguous rows (pitch = 4 * width). */
 PFCudaStatus PFCudaRendererGatherInit(PFCudaRendererRef renderer, const PFCudaGatherId *id, int32_t rank,
                                       int32_t world_size);
+/* How PFCudaRendererGatherFrame moves the strips (default: PF_CUDA_GATHER_MODE_TILES when the GPUs can map each
+ * other's memory, else PF_CUDA_GATHER_MODE_FRAME). Collective: every rank must choose the same mode.
+ *   FRAME  all-gather of the finished strips (ncclAllGather in place when the strips are equal, grouped
+ *          ncclBroadcast otherwise): every rank receives the whole frame, (N - 1) / N x 4 bytes per pixel.
+ *   TILES  every rank keeps a compact export of its strip — 4 bytes per single-colour tile, one contiguous 1 KB block
+ *          per other tile — in memory its peers map (CUDA IPC over NVLink); after a barrier (ncclAllReduce of one
+ *          word) a kernel on each rank reads the peers' exports and writes the pixels into its own copy of the frame.
+ *          Frames with more than one draw batch on the destination fall back to FRAME for that frame. */
+#define PF_CUDA_GATHER_MODE_FRAME 0
+#define PF_CUDA_GATHER_MODE_TILES 1
+PFCudaStatus PFCudaRendererGatherSetMode(PFCudaRendererRef renderer, int32_t mode);
 /* Collective, asynchronous: after the frame just rendered, completes every rank's copy of the frame with the other
- * ranks' strips (ncclAllGather in place when the strips are equal, grouped ncclBroadcast otherwise). ReadPixels,
- * Synchronize and the next frame's compositing wait for it. With deferred verification a frame that overflowed a
+ * ranks' strips. ReadPixels, Synchronize and the next frame's compositing wait for what they need of it. With deferred verification a frame that overflowed a
  * stage bound is repaired at the next use of the renderer, after its (stale) strip has been gathered: render with
  * verification on when every gathered frame must be final. */
 PFCudaStatus PFCudaRendererGatherFrame(PFCudaRendererRef renderer);

@@ -255,6 +255,7 @@ SIGNATURES = {
     "PFCudaStripOfRank": (None, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "PFCudaGatherCreateId": (C.c_int32, [C.c_void_p]),
     "PFCudaRendererGatherInit": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "PFCudaRendererGatherSetMode": (C.c_int32, [C.c_void_p, C.c_int32]),
     "PFCudaRendererGatherFrame": (C.c_int32, [C.c_void_p]),
     "PFCudaRendererGatherWait": (C.c_int32, [C.c_void_p]),
     "PFCudaRendererGatherDestroy": (C.c_int32, [C.c_void_p]),

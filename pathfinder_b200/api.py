@@ -450,6 +450,13 @@ class CudaRenderer:
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(gather_id))
         L.check(L.lib().PFCudaRendererGatherInit(self._h, buf, rank, world_size))
 
+    GATHER_MODE_FRAME, GATHER_MODE_TILES = 0, 1
+
+    def gather_set_mode(self, mode: int):
+        """FRAME: all-gather of the finished strips; TILES: compact exports pulled over NVLink (the default when the
+        GPUs can map each other's memory). Collective: every rank must choose the same mode."""
+        L.check(L.lib().PFCudaRendererGatherSetMode(self._h, int(mode)))
+
     def gather_frame(self):
         """Collective, asynchronous: completes this rank's copy of the frame with the other ranks' strips."""
         L.check(L.lib().PFCudaRendererGatherFrame(self._h))

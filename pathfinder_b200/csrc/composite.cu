@@ -160,7 +160,10 @@ __global__ void __launch_bounds__(128) k_tile_solid(CompositeArgs a) {
     // LOAD_ACTION_LOAD: a tile without entries keeps what the previous batches drew.
     const bool paints = in_row && !queued && !(LOAD_DEST && n == 0);
     const uint32_t paint_mask = __ballot_sync(0xffffffffu, paints);
-    if (paint_mask == 0) return;
+    if (paint_mask == 0) {
+        if (a.export_solid_mask && lane == 0) a.export_solid_mask[warp_global] = 0u;
+        return;
+    }
 
     // The tile's colour: its (few, solid) entries blended in draw order = ascending tile index, selected by
     // repeated minimum (the run is in arbitrary order).
@@ -182,6 +185,10 @@ __global__ void __launch_bounds__(128) k_tile_solid(CompositeArgs a) {
         }
     }
     const uint32_t packed = pack_rgba8(c);
+    if (a.export_solid_color) { // the other ranks expand these tiles themselves from 4 bytes each
+        a.export_solid_color[(size_t)warp_global * 32u + (uint32_t)lane] = packed;
+        if (lane == 0) a.export_solid_mask[warp_global] = paint_mask;
+    }
 
     // Store: image row r of the segment's 32 tiles is 2 KB of consecutive bytes; lane l writes the 16-byte
     // chunks l, l + 32, l + 64, l + 96 of it, chunk c belonging to tile c / 4.
@@ -423,6 +430,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
     TileWarpShared<GENERAL> &sh = sh_all[warp];
     const int fb_w = a.fb.max_x - a.fb.min_x;
     const uint32_t n_queue = *a.queue_count; // written by k_tile_solid
+    if (a.export_alpha_count && blockIdx.x == 0 && threadIdx.x == 0) *a.export_alpha_count = n_queue;
     const int64_t fb_base = (int64_t)(a.tile_y0 - a.fb.min_y) * fb_w;
     const int x = lane & 15, half = lane >> 4;
     const float xf = (float)x;
@@ -635,7 +643,8 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
             for (int k = 0; k < 8; k++) pk[k] = packed;
         }
         const bool inside = tx >= 0 && ty >= 0 && tx * 16 + 16 <= a.dest_w && ty * 16 + 16 <= a.dest_h;
-        if (inside && (a.dest_align_mask & 15u) == 0) {
+        const bool vector_store = inside && (a.dest_align_mask & 15u) == 0;
+        if (vector_store || a.export_blocks) {
 #pragma unroll
             for (int k = 0; k < 8; k++) sh.stage[(half * 8 + k) * 16 + half * 16 + x] = pk[k];
             __syncwarp();
@@ -643,13 +652,21 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
             const int row0 = lane >> 2, quarter = lane & 3;
             const uint4 v0 = *reinterpret_cast<const uint4 *>(&sh.stage[row0 * 16 + quarter * 4]);
             const uint4 v1 = *reinterpret_cast<const uint4 *>(&sh.stage[(row0 + 8) * 16 + 16 + quarter * 4]);
-            const size_t off0 = (size_t)(ty * 16 + row0) * a.dest_pitch + (size_t)tx * 64 + (size_t)quarter * 16;
-            const size_t off1 = off0 + 8 * a.dest_pitch;
-            for (int d = 0; d < a.n_dest; d++) {
-                *reinterpret_cast<uint4 *>(a.dests[d] + off0) = v0;
-                *reinterpret_cast<uint4 *>(a.dests[d] + off1) = v1;
+            if (a.export_blocks) { // slot k_cur: the tile as one contiguous 1 KB block for the other ranks
+                uint4 *block = reinterpret_cast<uint4 *>(a.export_blocks + (size_t)k_cur * 1024u);
+                block[lane] = v0;
+                block[lane + 32] = v1;
             }
-        } else if (px >= 0 && px < a.dest_w) {
+            if (vector_store) {
+                const size_t off0 = (size_t)(ty * 16 + row0) * a.dest_pitch + (size_t)tx * 64 + (size_t)quarter * 16;
+                const size_t off1 = off0 + 8 * a.dest_pitch;
+                for (int d = 0; d < a.n_dest; d++) {
+                    *reinterpret_cast<uint4 *>(a.dests[d] + off0) = v0;
+                    *reinterpret_cast<uint4 *>(a.dests[d] + off1) = v1;
+                }
+            }
+        }
+        if (!vector_store && px >= 0 && px < a.dest_w) {
             for (int d = 0; d < a.n_dest; d++) {
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
@@ -729,6 +746,101 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
     }
     PF_CUDA_CHECK(cudaGetLastError());
     return 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_pull_tiles — frame assembly across GPUs from compact exports: every rank reads the other ranks' strips over
+// NVLink (IPC-mapped export regions) as 4 bytes per single-colour tile and one contiguous 1 KB block per other tile,
+// and writes the pixels into its own copy of the frame at HBM speed. Compared with an all-gather of the finished
+// strips this moves a fraction of the bytes over the links (tiger frames: a few per cent; random100k: under half),
+// and every remote access is a coalesced read of at least 128 bytes.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(128) k_pull_tiles(PullArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int fb_w = a.fb.max_x - a.fb.min_x;
+    const uint32_t segs = ((uint32_t)fb_w + 31u) >> 5;
+    const bool aligned = (((uintptr_t)a.dest | (uintptr_t)a.dest_pitch) & 15u) == 0;
+    for (int p = 0; p < a.n_peers; p++) {
+        const PullPeer peer = a.peers[p];
+        // ---- single-colour tiles, one 32-tile row segment per warp iteration (as k_tile_solid stores them)
+        const uint32_t n_segments = segs * (uint32_t)(peer.tile_y1 - peer.tile_y0);
+        for (uint32_t segment = warp_global; segment < n_segments; segment += n_warps) {
+            const uint32_t paint_mask = __ldg(peer.solid_mask + segment);
+            if (paint_mask == 0) continue;
+            const uint32_t packed = __ldg(peer.solid_color + (size_t)segment * 32u + (uint32_t)lane);
+            const uint32_t tile_row = segment / segs, seg = segment - tile_row * segs;
+            const int ty = peer.tile_y0 + (int)tile_row;
+            const int seg_tx = a.fb.min_x + (int)(seg * 32u);
+            uint32_t chunk_color[4];
+            bool chunk_on[4], chunk_full[4];
+            int chunk_px[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = q * 8 + (lane >> 2);
+                chunk_color[q] = __shfl_sync(0xffffffffu, packed, j);
+                chunk_px[q] = (seg_tx + j) * 16 + (lane & 3) * 4;
+                chunk_on[q] = ((paint_mask >> j) & 1u) && chunk_px[q] + 4 > 0 && chunk_px[q] < a.dest_w;
+                chunk_full[q] = chunk_px[q] >= 0 && chunk_px[q] + 4 <= a.dest_w && aligned;
+            }
+            const int y_lo = max(0, ty * 16), y_hi = min(a.dest_h, ty * 16 + 16);
+            uint8_t *row = a.dest + (ptrdiff_t)y_lo * (ptrdiff_t)a.dest_pitch;
+            for (int y = y_lo; y < y_hi; y++, row += a.dest_pitch) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (!chunk_on[q]) continue;
+                    if (chunk_full[q]) {
+                        *reinterpret_cast<uint4 *>(row + (ptrdiff_t)chunk_px[q] * 4) =
+                            make_uint4(chunk_color[q], chunk_color[q], chunk_color[q], chunk_color[q]);
+                    } else {
+                        for (int k = 0; k < 4; k++) {
+                            const int px = chunk_px[q] + k;
+                            if (px >= 0 && px < a.dest_w) *reinterpret_cast<uint32_t *>(row + (ptrdiff_t)px * 4) = chunk_color[q];
+                        }
+                    }
+                }
+            }
+        }
+        // ---- the other tiles: one 1 KB block per warp iteration, two 128-bit loads and stores per lane
+        const uint32_t n_alpha = __ldg(peer.alpha_count);
+        for (uint32_t k = warp_global; k < n_alpha; k += n_warps) {
+            const uint32_t work = __ldg(peer.queue + k); // row << 16 | column within the peer's strip
+            const uint4 *block = reinterpret_cast<const uint4 *>(peer.blocks + (size_t)k * 1024u);
+            const uint4 v0 = __ldg(block + lane), v1 = __ldg(block + lane + 32);
+            const int ty = peer.tile_y0 + (int)(work >> 16), tx = a.fb.min_x + (int)(work & 0xffffu);
+            const int row0 = lane >> 2, quarter = lane & 3;
+            const bool inside = tx >= 0 && ty >= 0 && tx * 16 + 16 <= a.dest_w && ty * 16 + 16 <= a.dest_h;
+            if (inside && aligned) {
+                uint8_t *o = a.dest + (size_t)(ty * 16 + row0) * a.dest_pitch + (size_t)tx * 64 + (size_t)quarter * 16;
+                *reinterpret_cast<uint4 *>(o) = v0;
+                *reinterpret_cast<uint4 *>(o + 8 * a.dest_pitch) = v1;
+            } else {
+                const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+                for (int i = 0; i < 4; i++) {
+                    const int px = tx * 16 + quarter * 4 + i;
+                    if (px < 0 || px >= a.dest_w) continue;
+                    const int py_a = ty * 16 + row0, py_b = py_a + 8;
+                    if (py_a >= 0 && py_a < a.dest_h) *reinterpret_cast<uint32_t *>(a.dest + (size_t)py_a * a.dest_pitch + (size_t)px * 4) = w0[i];
+                    if (py_b >= 0 && py_b < a.dest_h) *reinterpret_cast<uint32_t *>(a.dest + (size_t)py_b * a.dest_pitch + (size_t)px * 4) = w1[i];
+                }
+            }
+        }
+    }
+}
+
+} // namespace
+
+int launch_pull_tiles(const PullArgs &args, cudaStream_t stream) {
+    if (args.n_peers <= 0) return 0;
+    int dev = 0, sm = 0;
+    PF_CUDA_CHECK(cudaGetDevice(&dev));
+    PF_CUDA_CHECK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    // Latency-bound remote reads: many warps in flight, but not the whole GPU — the next frame's stages run beside it.
+    k_pull_tiles<<<(unsigned)sm * 4u, 128, 0, stream>>>(args);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
 }
 
 } // namespace pf

@@ -176,7 +176,21 @@ struct PFCudaRenderer {
     int gather_rank = 0, gather_world = 0;
     cudaStream_t gather_stream = nullptr;
     cudaEvent_t gather_ready = nullptr, gather_done = nullptr;
-    bool gather_in_flight = false;
+    bool gather_in_flight = false, gather_last_was_tiles = false;
+    // Tile mode (PF_CUDA_GATHER_MODE_TILES): two compact export buffers in one allocation that the peers map through
+    // CUDA IPC; frame i exports into buffer i % 2. Layout of one buffer (the same on every rank, sized for the tallest
+    // strip): [alpha count, 64 B][queue: u32 per tile][solid colour: u32 per tile slot][solid mask: u32 per segment]
+    // [blocks: 1 KB per tile].
+    int gather_mode = 0;
+    DeviceBuffer<uint8_t> export_region;
+    size_t export_buffer_bytes = 0, export_queue_off = 0, export_color_off = 0, export_mask_off = 0, export_blocks_off = 0;
+    uint8_t *peer_export[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // by rank (own: local pointer)
+    void *peer_export_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t gather_frame_serial = 0;  // frames gathered so far: selects the export buffer
+    bool frame_exported = false;       // this frame's (single) destination batch wrote the current export buffer
+    int main_batches_this_frame = 0;
+    uint32_t *barrier_word = nullptr;  // device word all-reduced as the barrier
+    cudaEvent_t gather_barrier_done = nullptr; // tile mode: every rank has finished compositing the gathered frame
 
     // Per-batch device buffers.
     DeviceBuffer<uint8_t> batch_meta; // PathInfo[P] + 3 search arrays
@@ -386,6 +400,17 @@ void wait_for_gather(PFCudaRenderer *r, cudaStream_t st) {
     if (!r->gather_in_flight) return;
     PF_CUDA_CHECK(cudaStreamWaitEvent(st, r->gather_done, 0));
     r->gather_in_flight = false;
+}
+// What the next compositing of the destination has to wait for. FRAME mode: the whole gather (it sends from and
+// receives into the buffer the compositing writes). TILES mode: only the barrier inside the previous gather — the
+// pull kernel writes the OTHER ranks' strips, the compositing this rank's own; once every rank has passed that barrier
+// it has also finished pulling the frame before (stream order), so the export buffer about to be reused is free.
+void wait_for_gather_before_compositing(PFCudaRenderer *r, cudaStream_t st, bool last_was_tiles) {
+    if (!r->gather_in_flight) return;
+    if (last_was_tiles)
+        PF_CUDA_CHECK(cudaStreamWaitEvent(st, r->gather_barrier_done, 0)); // (gather_in_flight stays: readers still wait for the pull)
+    else
+        wait_for_gather(r, st);
 }
 
 float4 clear_color(const PFCudaRenderer *r) {
@@ -1002,7 +1027,22 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
         ca.gamma_lut = r->has_gamma_lut ? r->gamma_lut.ptr : nullptr;
     }
     ca.work_counter = r->counters.ptr + 12;
-    wait_for_gather(r, st);
+    wait_for_gather_before_compositing(r, st, r->gather_last_was_tiles);
+    if (target.is_main) {
+        // Tile mode: the (first) destination batch of the frame also writes the compact export of this strip.
+        r->main_batches_this_frame++;
+        r->frame_exported = false;
+        if (r->gather_comm && r->gather_mode == PF_CUDA_GATHER_MODE_TILES && r->main_batches_this_frame == 1 && !ca.load_dest &&
+            r->peer_export[r->gather_rank]) {
+            uint8_t *buffer = r->peer_export[r->gather_rank] + (r->gather_frame_serial & 1) * r->export_buffer_bytes;
+            ca.export_alpha_count = reinterpret_cast<uint32_t *>(buffer);
+            ca.queue = reinterpret_cast<uint32_t *>(buffer + r->export_queue_off);
+            ca.export_solid_color = reinterpret_cast<uint32_t *>(buffer + r->export_color_off);
+            ca.export_solid_mask = reinterpret_cast<uint32_t *>(buffer + r->export_mask_off);
+            ca.export_blocks = buffer + r->export_blocks_off;
+            r->frame_exported = true;
+        }
+    }
     launches += launch_composite(ca, st);
     if (r->timing) PF_CUDA_CHECK(cudaEventRecord(r->timer.ev[7], st));
 
@@ -1305,6 +1345,7 @@ struct Nccl {
     typedef int (*CommDestroyFn)(void *);
     typedef int (*AllGatherFn)(const void *, void *, size_t, int, void *, cudaStream_t);
     typedef int (*BroadcastFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    typedef int (*AllReduceFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
     typedef int (*GroupFn)();
     typedef const char *(*ErrorStringFn)(int);
     GetUniqueIdFn get_unique_id = nullptr;
@@ -1312,10 +1353,11 @@ struct Nccl {
     CommDestroyFn comm_destroy = nullptr;
     AllGatherFn all_gather = nullptr;
     BroadcastFn broadcast = nullptr;
+    AllReduceFn all_reduce = nullptr;
     GroupFn group_start = nullptr, group_end = nullptr;
     ErrorStringFn error_string = nullptr;
     bool ok = false;
-    static constexpr int UINT8 = 1; // ncclUint8
+    static constexpr int UINT8 = 1, UINT32 = 3, SUM = 0; // ncclUint8, ncclUint32, ncclSum
 
     static const Nccl &get() {
         static const Nccl instance = load();
@@ -1334,10 +1376,11 @@ struct Nccl {
         n.comm_destroy = (CommDestroyFn)dlsym(h, "ncclCommDestroy");
         n.all_gather = (AllGatherFn)dlsym(h, "ncclAllGather");
         n.broadcast = (BroadcastFn)dlsym(h, "ncclBroadcast");
+        n.all_reduce = (AllReduceFn)dlsym(h, "ncclAllReduce");
         n.group_start = (GroupFn)dlsym(h, "ncclGroupStart");
         n.group_end = (GroupFn)dlsym(h, "ncclGroupEnd");
         n.error_string = (ErrorStringFn)dlsym(h, "ncclGetErrorString");
-        n.ok = n.get_unique_id && n.comm_init_rank && n.comm_destroy && n.all_gather && n.broadcast && n.group_start &&
+        n.ok = n.get_unique_id && n.comm_init_rank && n.comm_destroy && n.all_gather && n.broadcast && n.all_reduce && n.group_start &&
                n.group_end && n.error_string;
         return n;
     }
@@ -1365,6 +1408,17 @@ void gather_destroy(PFCudaRenderer *r) {
     r->gather_in_flight = false;
     cudaEventDestroy(r->gather_ready);
     cudaEventDestroy(r->gather_done);
+    if (r->gather_barrier_done) cudaEventDestroy(r->gather_barrier_done);
+    r->gather_barrier_done = nullptr;
+    for (int g = 0; g < 8; g++) {
+        if (r->peer_export_base[g]) cudaIpcCloseMemHandle(r->peer_export_base[g]);
+        r->peer_export_base[g] = nullptr;
+        r->peer_export[g] = nullptr;
+    }
+    r->export_region.release();
+    if (r->barrier_word) cudaFree(r->barrier_word);
+    r->barrier_word = nullptr;
+    r->gather_last_was_tiles = false;
     cudaStreamDestroy(r->gather_stream);
     r->gather_stream = nullptr;
     r->gather_ready = r->gather_done = nullptr;
@@ -1506,6 +1560,8 @@ PFCudaStatus PFCudaRendererBeginScene(PFCudaRendererRef r) {
         r->batches_drawn = 0;
         r->target_stack.clear();
         for (auto &slot : r->render_targets) slot.batches_drawn = 0;
+        r->main_batches_this_frame = 0;
+        r->frame_exported = false;
         r->stats = PFCudaRenderStats{};
         r->times = PFCudaRenderTime{};
     });
@@ -1612,7 +1668,7 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
             fill_destinations(r, current_target(r), ca);
             ca.clear_color = clear_color(r);
             ca.work_counter = r->counters.ptr + 12;
-            wait_for_gather(r, r->stream);
+            wait_for_gather(r, r->stream); // (an empty frame is gathered as a whole frame: nothing was exported)
             r->stats.drawcall_count += (uint64_t)launch_composite(ca, r->stream);
         }
         if (r->borrowed_copies_pending && !r->pending.active) {
@@ -1775,9 +1831,98 @@ PFCudaStatus PFCudaRendererGatherInit(PFCudaRendererRef r, const PFCudaGatherId 
         PF_CUDA_CHECK(cudaStreamCreateWithFlags(&r->gather_stream, cudaStreamNonBlocking));
         PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->gather_ready, cudaEventDisableTiming));
         PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->gather_done, cudaEventDisableTiming));
+        PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->gather_barrier_done, cudaEventDisableTiming));
         const FbRect fb = framebuffer_tile_rect(r);
         strip_of_rank(fb.max_y - fb.min_y, rank, world_size, r->strip_y0, r->strip_y1);
         if (r->strip_y1 == r->strip_y0) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "more ranks than tile rows");
+
+        // Tile mode: allocate the export region, exchange its IPC handle with the peers (an ncclAllGather of the 64-byte
+        // handles), map theirs. Any failure (no peer access, more than 8 ranks, IPC refused) leaves FRAME mode on.
+        r->gather_mode = PF_CUDA_GATHER_MODE_FRAME;
+        r->gather_frame_serial = 0;
+        PF_CUDA_CHECK(cudaMalloc((void **)&r->barrier_word, 64));
+        PF_CUDA_CHECK(cudaMemset(r->barrier_word, 0, 64));
+        if (world_size > 1 && world_size <= 8) {
+            const int fb_w = fb.max_x - fb.min_x;
+            int32_t max_rows = 0;
+            for (int32_t g = 0; g < world_size; g++) {
+                int32_t y0, y1;
+                strip_of_rank(fb.max_y - fb.min_y, g, world_size, y0, y1);
+                max_rows = std::max(max_rows, y1 - y0);
+            }
+            const size_t tiles = (size_t)fb_w * (size_t)max_rows, segments = (size_t)((fb_w + 31) / 32) * (size_t)max_rows;
+            auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+            r->export_queue_off = 256;
+            r->export_color_off = align(r->export_queue_off + tiles * 4);
+            r->export_mask_off = align(r->export_color_off + segments * 32 * 4);
+            r->export_blocks_off = align(r->export_mask_off + segments * 4);
+            r->export_buffer_bytes = align(r->export_blocks_off + tiles * 1024);
+            r->export_region.bytes_allocated = &r->bytes_allocated;
+            r->export_region.ensure(2 * r->export_buffer_bytes);
+            PF_CUDA_CHECK(cudaMemset(r->export_region.ptr, 0, 2 * r->export_buffer_bytes));
+            cudaIpcMemHandle_t mine;
+            uint8_t *handles_dev = nullptr;
+            std::vector<cudaIpcMemHandle_t> handles(world_size);
+            bool ok = cudaIpcGetMemHandle(&mine, r->export_region.ptr) == cudaSuccess;
+            if (!ok) cudaGetLastError();
+            // (collective either way: a rank whose export failed sends a zeroed handle and every rank falls back)
+            if (!ok) memset(&mine, 0, sizeof(mine));
+            PF_CUDA_CHECK(cudaMalloc((void **)&handles_dev, (size_t)world_size * 64));
+            PF_CUDA_CHECK(cudaMemcpy(handles_dev + (size_t)rank * 64, &mine, 64, cudaMemcpyHostToDevice));
+            n.check(n.all_gather(handles_dev + (size_t)rank * 64, handles_dev, 64, Nccl::UINT8, r->gather_comm, r->gather_stream),
+                    "ncclAllGather (IPC handles)");
+            PF_CUDA_CHECK(cudaStreamSynchronize(r->gather_stream));
+            PF_CUDA_CHECK(cudaMemcpy(handles.data(), handles_dev, (size_t)world_size * 64, cudaMemcpyDeviceToHost));
+            cudaFree(handles_dev);
+            const cudaIpcMemHandle_t zero{};
+            for (int32_t g = 0; g < world_size && ok; g++) {
+                if (memcmp(&handles[g], &zero, sizeof(zero)) == 0) ok = false;
+            }
+            for (int32_t g = 0; g < world_size && ok; g++) {
+                if (g == rank) {
+                    r->peer_export[g] = r->export_region.ptr;
+                    continue;
+                }
+                void *base = nullptr;
+                if (cudaIpcOpenMemHandle(&base, handles[g], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = false;
+                    break;
+                }
+                r->peer_export_base[g] = base;
+                r->peer_export[g] = static_cast<uint8_t *>(base);
+            }
+            // every rank must end up in the same mode: agree on the minimum
+            uint32_t vote = ok ? 1u : 0u, *vote_dev = r->barrier_word + 8;
+            PF_CUDA_CHECK(cudaMemcpy(vote_dev, &vote, 4, cudaMemcpyHostToDevice));
+            n.check(n.all_reduce(vote_dev, vote_dev, 1, Nccl::UINT32, Nccl::SUM, r->gather_comm, r->gather_stream), "ncclAllReduce (mode vote)");
+            PF_CUDA_CHECK(cudaStreamSynchronize(r->gather_stream));
+            PF_CUDA_CHECK(cudaMemcpy(&vote, vote_dev, 4, cudaMemcpyDeviceToHost));
+            if (vote == (uint32_t)world_size) {
+                r->gather_mode = PF_CUDA_GATHER_MODE_TILES;
+            } else {
+                for (int g = 0; g < 8; g++) {
+                    if (r->peer_export_base[g]) cudaIpcCloseMemHandle(r->peer_export_base[g]);
+                    r->peer_export_base[g] = nullptr;
+                    r->peer_export[g] = nullptr;
+                }
+                r->export_region.release();
+            }
+        }
+    });
+}
+
+PFCudaStatus PFCudaRendererGatherSetMode(PFCudaRendererRef r, int32_t mode) {
+    return guarded(r, [&]() {
+        verify_pending(r);
+        if (!r->gather_comm) throw Error(PF_CUDA_ERROR_PROTOCOL, "PFCudaRendererGatherSetMode before PFCudaRendererGatherInit");
+        if (mode != PF_CUDA_GATHER_MODE_FRAME && mode != PF_CUDA_GATHER_MODE_TILES)
+            throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "unknown gather mode");
+        if (mode == PF_CUDA_GATHER_MODE_TILES && !r->peer_export[r->gather_rank])
+            throw Error(PF_CUDA_ERROR_UNSUPPORTED, "tile mode needs the ranks' export regions mapped over CUDA IPC (not available here)");
+        wait_for_gather(r, r->stream);
+        PF_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        r->gather_mode = mode;
     });
 }
 
@@ -1798,6 +1943,37 @@ PFCudaStatus PFCudaRendererGatherFrame(PFCudaRendererRef r) {
         // Ordered after this frame's compositing (and a gather still in flight on the same stream).
         PF_CUDA_CHECK(cudaEventRecord(r->gather_ready, r->stream));
         PF_CUDA_CHECK(cudaStreamWaitEvent(r->gather_stream, r->gather_ready, 0));
+        if (r->gather_mode == PF_CUDA_GATHER_MODE_TILES && r->frame_exported) {
+            // Barrier (every rank's export of this frame is complete), then pull the peers' strips.
+            n.check(n.all_reduce(r->barrier_word, r->barrier_word, 1, Nccl::UINT32, Nccl::SUM, r->gather_comm, r->gather_stream),
+                    "ncclAllReduce (barrier)");
+            PF_CUDA_CHECK(cudaEventRecord(r->gather_barrier_done, r->gather_stream));
+            PullArgs pa{};
+            const size_t buffer_off = (r->gather_frame_serial & 1) * r->export_buffer_bytes;
+            for (int32_t g = 0; g < r->gather_world; g++) {
+                if (g == r->gather_rank) continue;
+                const uint8_t *buffer = r->peer_export[g] + buffer_off;
+                PullPeer &peer = pa.peers[pa.n_peers++];
+                peer.alpha_count = reinterpret_cast<const uint32_t *>(buffer);
+                peer.queue = reinterpret_cast<const uint32_t *>(buffer + r->export_queue_off);
+                peer.solid_color = reinterpret_cast<const uint32_t *>(buffer + r->export_color_off);
+                peer.solid_mask = reinterpret_cast<const uint32_t *>(buffer + r->export_mask_off);
+                peer.blocks = buffer + r->export_blocks_off;
+                strip_of_rank(rows, g, r->gather_world, peer.tile_y0, peer.tile_y1);
+            }
+            pa.fb = fb;
+            pa.dest = r->dest;
+            pa.dest_pitch = pitch;
+            pa.dest_w = r->options.dest_size.x;
+            pa.dest_h = height;
+            r->stats.drawcall_count += (uint64_t)launch_pull_tiles(pa, r->gather_stream);
+            PF_CUDA_CHECK(cudaEventRecord(r->gather_done, r->gather_stream));
+            r->gather_in_flight = true;
+            r->gather_last_was_tiles = true;
+            r->gather_frame_serial++;
+            return;
+        }
+        r->gather_last_was_tiles = false;
         size_t my_offset, my_bytes, offset0, bytes0;
         span(r->gather_rank, my_offset, my_bytes);
         span(0, offset0, bytes0);

@@ -42,15 +42,18 @@ for width, height in [(2048, 2048), (1536, 1000)]:
     box = [api.gather_create_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     r1.gather_init(box[0], rank, world)
-    for deferred in (False, True):
-        r1.set_deferred_verification(deferred)
-        for _ in range(3):
-            scene.build_and_render(r1, opts)
-            r1.gather_frame()
-        r1.synchronize()
-        same = bool(torch.equal(f1, ref))
-        ok = ok and same
-        print(f"rank {rank}: {width}x{height} library gather (deferred={deferred}) == full frame: {same}", flush=True)
+    for mode, mode_name in ((api.CudaRenderer.GATHER_MODE_FRAME, "frame"), (api.CudaRenderer.GATHER_MODE_TILES, "tiles")):
+        r1.gather_set_mode(mode)
+        for deferred in (False, True):
+            r1.set_deferred_verification(deferred)
+            f1.zero_()
+            for _ in range(4):
+                scene.build_and_render(r1, opts)
+                r1.gather_frame()
+            r1.synchronize()
+            same = bool(torch.equal(f1, ref))
+            ok = ok and same
+            print(f"rank {rank}: {width}x{height} library gather, {mode_name} mode (deferred={deferred}) == full frame: {same}", flush=True)
     r1.gather_destroy()
 
     # fused peer stores (IPC-mapped frames)
