@@ -407,10 +407,11 @@ PFCudaStatus PFCudaRendererGatherInit(PFCudaRendererRef renderer, const PFCudaGa
  * other's memory, else PF_CUDA_GATHER_MODE_FRAME). Collective: every rank must choose the same mode.
  *   FRAME  all-gather of the finished strips (ncclAllGather in place when the strips are equal, grouped
  *          ncclBroadcast otherwise): every rank receives the whole frame, (N - 1) / N x 4 bytes per pixel.
- *   TILES  every rank keeps a compact export of its strip — 4 bytes per single-colour tile, one contiguous 1 KB block
- *          per other tile — in memory its peers map (CUDA IPC over NVLink); after a barrier (ncclAllReduce of one
- *          word) a kernel on each rank reads the peers' exports and writes the pixels into its own copy of the frame.
- *          Frames with more than one draw batch on the destination fall back to FRAME for that frame. */
+ *   TILES  the fill + tile kernels of every rank push a compact export of their strip — 4 bytes per single-colour tile,
+ *          one contiguous 1 KB block per other tile — straight into receive slots in the other ranks' memory (CUDA IPC
+ *          over NVLink) as they finish tiles; after a barrier (ncclAllReduce of one word) a kernel on each rank expands
+ *          what it received into its own copy of the frame. Frames with more than one draw batch on the destination
+ *          fall back to FRAME for that frame. */
 #define PF_CUDA_GATHER_MODE_FRAME 0
 #define PF_CUDA_GATHER_MODE_TILES 1
 PFCudaStatus PFCudaRendererGatherSetMode(PFCudaRendererRef renderer, int32_t mode);

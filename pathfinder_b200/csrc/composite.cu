@@ -749,11 +749,15 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_pull_tiles — frame assembly across GPUs from compact exports: every rank reads the other ranks' strips over
-// NVLink (IPC-mapped export regions) as 4 bytes per single-colour tile and one contiguous 1 KB block per other tile,
-// and writes the pixels into its own copy of the frame at HBM speed. Compared with an all-gather of the finished
-// strips this moves a fraction of the bytes over the links (tiger frames: a few per cent; random100k: under half),
-// and every remote access is a coalesced read of at least 128 bytes.
+// k_push_export / k_pull_tiles — frame assembly across GPUs from compact exports. The fill + tile kernels leave a
+// compact export of their strip next to the frame (4 bytes per single-colour tile, one contiguous 1 KB block per other
+// tile); k_push_export copies the used part of it into a receive slot in every other rank's memory over NVLink
+// (coalesced 16-byte posted writes, the source read once for all peers), and after a barrier k_pull_tiles expands what
+// arrived — all of it local memory by then — into the rank's own copy of the frame. Both run on the gather stream
+// beside the next frame's stages. Compared with an all-gather of the finished strips a fraction of the bytes crosses
+// the links (tiger frames: a few per cent; random100k: under half). Measured alternatives (B200 x 8): peers READING
+// the exports over NVLink (340 GB/s, latency-bound), and the compositing kernel storing the blocks into the peers
+// itself (480 GB/s, but serialised with the rank's own compute instead of overlapping the next frame).
 // ---------------------------------------------------------------------------------------------
 namespace {
 
@@ -803,27 +807,44 @@ __global__ void __launch_bounds__(128) k_pull_tiles(PullArgs a) {
                 }
             }
         }
-        // ---- the other tiles: one 1 KB block per warp iteration, two 128-bit loads and stores per lane
+        // ---- the other tiles, 32 per warp iteration: one coalesced read of their positions, then the 1 KB blocks
+        // four at a time (eight 128-bit loads in flight per lane) and
+        // two 128-bit stores per lane and tile into the local frame.
         const uint32_t n_alpha = __ldg(peer.alpha_count);
-        for (uint32_t k = warp_global; k < n_alpha; k += n_warps) {
-            const uint32_t work = __ldg(peer.queue + k); // row << 16 | column within the peer's strip
-            const uint4 *block = reinterpret_cast<const uint4 *>(peer.blocks + (size_t)k * 1024u);
-            const uint4 v0 = __ldg(block + lane), v1 = __ldg(block + lane + 32);
-            const int ty = peer.tile_y0 + (int)(work >> 16), tx = a.fb.min_x + (int)(work & 0xffffu);
-            const int row0 = lane >> 2, quarter = lane & 3;
-            const bool inside = tx >= 0 && ty >= 0 && tx * 16 + 16 <= a.dest_w && ty * 16 + 16 <= a.dest_h;
-            if (inside && aligned) {
-                uint8_t *o = a.dest + (size_t)(ty * 16 + row0) * a.dest_pitch + (size_t)tx * 64 + (size_t)quarter * 16;
-                *reinterpret_cast<uint4 *>(o) = v0;
-                *reinterpret_cast<uint4 *>(o + 8 * a.dest_pitch) = v1;
-            } else {
-                const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+        for (uint32_t k0 = warp_global * 32u; k0 < n_alpha; k0 += n_warps * 32u) {
+            const uint32_t m = min(32u, n_alpha - k0);
+            const uint32_t my_work = (uint32_t)lane < m ? __ldg(peer.queue + k0 + lane) : 0u;
+            const uint4 *blocks = reinterpret_cast<const uint4 *>(peer.blocks + (size_t)k0 * 1024u);
+            for (uint32_t t0 = 0; t0 < m; t0 += 4) {
+                uint4 v0[4], v1[4];
+#pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int px = tx * 16 + quarter * 4 + i;
-                    if (px < 0 || px >= a.dest_w) continue;
-                    const int py_a = ty * 16 + row0, py_b = py_a + 8;
-                    if (py_a >= 0 && py_a < a.dest_h) *reinterpret_cast<uint32_t *>(a.dest + (size_t)py_a * a.dest_pitch + (size_t)px * 4) = w0[i];
-                    if (py_b >= 0 && py_b < a.dest_h) *reinterpret_cast<uint32_t *>(a.dest + (size_t)py_b * a.dest_pitch + (size_t)px * 4) = w1[i];
+                    if (t0 + i < m) {
+                        v0[i] = __ldg(blocks + (size_t)(t0 + i) * 64u + lane);
+                        v1[i] = __ldg(blocks + (size_t)(t0 + i) * 64u + lane + 32);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t work = __shfl_sync(0xffffffffu, my_work, (int)((t0 + i) & 31u));
+                    if (t0 + i >= m) continue;
+                    const int ty = peer.tile_y0 + (int)(work >> 16), tx = a.fb.min_x + (int)(work & 0xffffu);
+                    const int row0 = lane >> 2, quarter = lane & 3;
+                    const bool inside = tx >= 0 && ty >= 0 && tx * 16 + 16 <= a.dest_w && ty * 16 + 16 <= a.dest_h;
+                    if (inside && aligned) {
+                        uint8_t *o = a.dest + (size_t)(ty * 16 + row0) * a.dest_pitch + (size_t)tx * 64 + (size_t)quarter * 16;
+                        *reinterpret_cast<uint4 *>(o) = v0[i];
+                        *reinterpret_cast<uint4 *>(o + 8 * a.dest_pitch) = v1[i];
+                    } else {
+                        const uint32_t w0[4] = {v0[i].x, v0[i].y, v0[i].z, v0[i].w}, w1[4] = {v1[i].x, v1[i].y, v1[i].z, v1[i].w};
+                        for (int c = 0; c < 4; c++) {
+                            const int px = tx * 16 + quarter * 4 + c;
+                            if (px < 0 || px >= a.dest_w) continue;
+                            const int py_a = ty * 16 + row0, py_b = py_a + 8;
+                            if (py_a >= 0 && py_a < a.dest_h) *reinterpret_cast<uint32_t *>(a.dest + (size_t)py_a * a.dest_pitch + (size_t)px * 4) = w0[c];
+                            if (py_b >= 0 && py_b < a.dest_h) *reinterpret_cast<uint32_t *>(a.dest + (size_t)py_b * a.dest_pitch + (size_t)px * 4) = w1[c];
+                        }
+                    }
                 }
             }
         }
@@ -832,13 +853,51 @@ __global__ void __launch_bounds__(128) k_pull_tiles(PullArgs a) {
 
 } // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) k_push_export(PushArgs a) {
+    const uint32_t n_alpha = *reinterpret_cast<const uint32_t *>(a.local);
+    // the used ranges of the slot, in 16-byte units: {count}, queue, colours, masks, blocks
+    const size_t begin[5] = {0, a.queue_off / 16, a.color_off / 16, a.mask_off / 16, a.blocks_off / 16};
+    const size_t length[5] = {1, ((size_t)n_alpha * 4 + 15) / 16, ((size_t)a.segments * 128 + 15) / 16,
+                              ((size_t)a.segments * 4 + 15) / 16, (size_t)n_alpha * 64};
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.local);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (int range = 0; range < 5; range++) {
+        const uint4 *s = src + begin[range];
+        size_t i = tid;
+        for (; i + 3 * stride < length[range]; i += 4 * stride) { // four loads in flight, each stored to every peer
+            const uint4 v0 = s[i], v1 = s[i + stride], v2 = s[i + 2 * stride], v3 = s[i + 3 * stride];
+            for (int p = 0; p < a.n_remote; p++) {
+                uint4 *d = reinterpret_cast<uint4 *>(a.remote[p]) + begin[range];
+                d[i] = v0, d[i + stride] = v1, d[i + 2 * stride] = v2, d[i + 3 * stride] = v3;
+            }
+        }
+        for (; i < length[range]; i += stride) {
+            const uint4 v = s[i];
+            for (int p = 0; p < a.n_remote; p++) (reinterpret_cast<uint4 *>(a.remote[p]) + begin[range])[i] = v;
+        }
+    }
+}
+} // namespace
+
+int launch_push_export(const PushArgs &args, cudaStream_t stream) {
+    if (args.n_remote <= 0) return 0;
+    int dev = 0, sm = 0;
+    PF_CUDA_CHECK(cudaGetDevice(&dev));
+    PF_CUDA_CHECK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    // NVLink-bound: a block per SM keeps the links busy and leaves the SMs to the next frame's stages.
+    k_push_export<<<(unsigned)sm, 256, 0, stream>>>(args);
+    PF_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
 int launch_pull_tiles(const PullArgs &args, cudaStream_t stream) {
     if (args.n_peers <= 0) return 0;
     int dev = 0, sm = 0;
     PF_CUDA_CHECK(cudaGetDevice(&dev));
     PF_CUDA_CHECK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
     // Latency-bound remote reads: many warps in flight, but not the whole GPU — the next frame's stages run beside it.
-    k_pull_tiles<<<(unsigned)sm * 4u, 128, 0, stream>>>(args);
+    k_pull_tiles<<<(unsigned)sm * 8u, 128, 0, stream>>>(args);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

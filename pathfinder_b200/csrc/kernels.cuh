@@ -207,17 +207,17 @@ struct CompositeArgs {
     float4 clear_color;
     int load_dest;             // LOAD_ACTION_LOAD for batches after the first
     uint32_t *work_counter;    // device word used by the persistent warps to pull queued tiles; zeroed by the caller
-    // Compact export of this strip for the other ranks (PFCudaRendererGatherFrame, tile mode; all NULL otherwise):
-    // which tiles of each 32-tile row segment have a single colour and that colour, the number of queued tiles, and —
-    // slot k for queue entry k — the finished pixels of every queued tile as one contiguous 1 KB block (16 rows x 64 B).
-    // `queue` itself then points into the export region too.
+    // Compact export of this strip for the other ranks (PFCudaRendererGatherFrame, tile mode; all NULL otherwise),
+    // written next to the frame by the fill + tile kernels: which tiles of each 32-tile row segment have a single
+    // colour and that colour, the number of queued tiles, and — slot k for queue entry k — the finished pixels of
+    // every queued tile as one contiguous 1 KB block (16 rows x 64 B). `queue` then points into the export too.
     uint32_t *export_solid_color, *export_solid_mask, *export_alpha_count;
     uint8_t *export_blocks;
 };
 int launch_composite(const CompositeArgs &args, cudaStream_t stream);
 
-// One peer's compact export as seen from this rank (pointers into the peer's IPC-mapped export region) and where
-// its strip lies in the frame.
+// One peer's compact export as received by this rank (pointers into this rank's own receive slot for that peer) and
+// where the peer's strip lies in the frame.
 struct PullPeer {
     const uint32_t *queue;        // tile (row << 16 | column within the peer's strip) of every queued tile
     const uint32_t *alpha_count;
@@ -233,9 +233,21 @@ struct PullArgs {
     size_t dest_pitch;
     int32_t dest_w, dest_h;
 };
-// Completes the local frame with the other ranks' strips, read from their compact exports over NVLink: single-colour
-// tiles are expanded from 4 bytes, the others copied as 1 KB blocks.
+// Completes the local frame with the other ranks' strips from the compact exports they pushed into this rank's
+// receive slots: single-colour tiles are expanded from 4 bytes, the others copied as 1 KB blocks (all local memory).
 int launch_pull_tiles(const PullArgs &args, cudaStream_t stream);
+
+// Pushes this rank's compact export (the used part of one slot: count, queue, colours, masks, blocks) into the same
+// slot of every peer's receive region over NVLink. Slot layout: the byte offsets below; `segments` = 32-tile row
+// segments of this rank's strip.
+struct PushArgs {
+    const uint8_t *local;
+    uint8_t *remote[7];
+    int n_remote;
+    size_t queue_off, color_off, mask_off, blocks_off;
+    uint32_t segments;
+};
+int launch_push_export(const PushArgs &args, cudaStream_t stream);
 
 // ---- parity-dump helpers ----
 int launch_alpha_flags(uint32_t n_tiles, const uint32_t *tile_word, const uint32_t *tile_first_fill,

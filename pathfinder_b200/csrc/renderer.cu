@@ -177,10 +177,11 @@ struct PFCudaRenderer {
     cudaStream_t gather_stream = nullptr;
     cudaEvent_t gather_ready = nullptr, gather_done = nullptr;
     bool gather_in_flight = false, gather_last_was_tiles = false;
-    // Tile mode (PF_CUDA_GATHER_MODE_TILES): two compact export buffers in one allocation that the peers map through
-    // CUDA IPC; frame i exports into buffer i % 2. Layout of one buffer (the same on every rank, sized for the tallest
-    // strip): [alpha count, 64 B][queue: u32 per tile][solid colour: u32 per tile slot][solid mask: u32 per segment]
-    // [blocks: 1 KB per tile].
+    // Tile mode (PF_CUDA_GATHER_MODE_TILES): every rank owns a receive region that its peers map through CUDA IPC,
+    // with one slot per (source rank, frame parity); frame i of rank g lands in slot (g, i % 2) of every other rank —
+    // and first, written by rank g's own fill + tile kernels, in slot (g, i % 2) of its own region.
+    // Layout of one slot (the same everywhere, sized for the tallest strip): [alpha count, 256 B][queue: u32 per tile]
+    // [solid colour: u32 per tile slot][solid mask: u32 per segment][blocks: 1 KB per tile].
     int gather_mode = 0;
     DeviceBuffer<uint8_t> export_region;
     size_t export_buffer_bytes = 0, export_queue_off = 0, export_color_off = 0, export_mask_off = 0, export_blocks_off = 0;
@@ -190,7 +191,9 @@ struct PFCudaRenderer {
     bool frame_exported = false;       // this frame's (single) destination batch wrote the current export buffer
     int main_batches_this_frame = 0;
     uint32_t *barrier_word = nullptr;  // device word all-reduced as the barrier
-    cudaEvent_t gather_barrier_done = nullptr; // tile mode: every rank has finished compositing the gathered frame
+    cudaEvent_t gather_barrier_done = nullptr; // tile mode: every rank's push of the gathered frame has landed
+    cudaEvent_t push_done[2] = {nullptr, nullptr}; // tile mode: the push that read the local export slot of that parity
+    bool push_recorded[2] = {false, false};
 
     // Per-batch device buffers.
     DeviceBuffer<uint8_t> batch_meta; // PathInfo[P] + 3 search arrays
@@ -402,15 +405,12 @@ void wait_for_gather(PFCudaRenderer *r, cudaStream_t st) {
     r->gather_in_flight = false;
 }
 // What the next compositing of the destination has to wait for. FRAME mode: the whole gather (it sends from and
-// receives into the buffer the compositing writes). TILES mode: only the barrier inside the previous gather — the
-// pull kernel writes the OTHER ranks' strips, the compositing this rank's own; once every rank has passed that barrier
-// it has also finished pulling the frame before (stream order), so the export buffer about to be reused is free.
+// receives into the buffer the compositing writes). TILES mode: nothing of the previous gather — its push reads the
+// other export slot, its pull kernel writes the OTHER ranks' strips — only the push two frames back, which read the
+// local export slot this frame is about to overwrite (run_pipeline waits for that one).
 void wait_for_gather_before_compositing(PFCudaRenderer *r, cudaStream_t st, bool last_was_tiles) {
-    if (!r->gather_in_flight) return;
-    if (last_was_tiles)
-        PF_CUDA_CHECK(cudaStreamWaitEvent(st, r->gather_barrier_done, 0)); // (gather_in_flight stays: readers still wait for the pull)
-    else
-        wait_for_gather(r, st);
+    if (!r->gather_in_flight || last_was_tiles) return; // (gather_in_flight stays set in tile mode: readers still wait for the pull)
+    wait_for_gather(r, st);
 }
 
 float4 clear_color(const PFCudaRenderer *r) {
@@ -1034,7 +1034,9 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
         r->frame_exported = false;
         if (r->gather_comm && r->gather_mode == PF_CUDA_GATHER_MODE_TILES && r->main_batches_this_frame == 1 && !ca.load_dest &&
             r->peer_export[r->gather_rank]) {
-            uint8_t *buffer = r->peer_export[r->gather_rank] + (r->gather_frame_serial & 1) * r->export_buffer_bytes;
+            const int parity = (int)(r->gather_frame_serial & 1);
+            if (r->push_recorded[parity]) PF_CUDA_CHECK(cudaStreamWaitEvent(st, r->push_done[parity], 0));
+            uint8_t *buffer = r->export_region.ptr + ((size_t)r->gather_rank * 2 + parity) * r->export_buffer_bytes;
             ca.export_alpha_count = reinterpret_cast<uint32_t *>(buffer);
             ca.queue = reinterpret_cast<uint32_t *>(buffer + r->export_queue_off);
             ca.export_solid_color = reinterpret_cast<uint32_t *>(buffer + r->export_color_off);
@@ -1410,6 +1412,11 @@ void gather_destroy(PFCudaRenderer *r) {
     cudaEventDestroy(r->gather_done);
     if (r->gather_barrier_done) cudaEventDestroy(r->gather_barrier_done);
     r->gather_barrier_done = nullptr;
+    for (int q = 0; q < 2; q++) {
+        if (r->push_done[q]) cudaEventDestroy(r->push_done[q]);
+        r->push_done[q] = nullptr;
+        r->push_recorded[q] = false;
+    }
     for (int g = 0; g < 8; g++) {
         if (r->peer_export_base[g]) cudaIpcCloseMemHandle(r->peer_export_base[g]);
         r->peer_export_base[g] = nullptr;
@@ -1832,6 +1839,10 @@ PFCudaStatus PFCudaRendererGatherInit(PFCudaRendererRef r, const PFCudaGatherId 
         PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->gather_ready, cudaEventDisableTiming));
         PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->gather_done, cudaEventDisableTiming));
         PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->gather_barrier_done, cudaEventDisableTiming));
+        for (int q = 0; q < 2; q++) {
+            PF_CUDA_CHECK(cudaEventCreateWithFlags(&r->push_done[q], cudaEventDisableTiming));
+            r->push_recorded[q] = false;
+        }
         const FbRect fb = framebuffer_tile_rect(r);
         strip_of_rank(fb.max_y - fb.min_y, rank, world_size, r->strip_y0, r->strip_y1);
         if (r->strip_y1 == r->strip_y0) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "more ranks than tile rows");
@@ -1858,8 +1869,8 @@ PFCudaStatus PFCudaRendererGatherInit(PFCudaRendererRef r, const PFCudaGatherId 
             r->export_blocks_off = align(r->export_mask_off + segments * 4);
             r->export_buffer_bytes = align(r->export_blocks_off + tiles * 1024);
             r->export_region.bytes_allocated = &r->bytes_allocated;
-            r->export_region.ensure(2 * r->export_buffer_bytes);
-            PF_CUDA_CHECK(cudaMemset(r->export_region.ptr, 0, 2 * r->export_buffer_bytes));
+            r->export_region.ensure((size_t)world_size * 2 * r->export_buffer_bytes);
+            PF_CUDA_CHECK(cudaMemset(r->export_region.ptr, 0, (size_t)world_size * 2 * r->export_buffer_bytes));
             cudaIpcMemHandle_t mine;
             uint8_t *handles_dev = nullptr;
             std::vector<cudaIpcMemHandle_t> handles(world_size);
@@ -1944,15 +1955,29 @@ PFCudaStatus PFCudaRendererGatherFrame(PFCudaRendererRef r) {
         PF_CUDA_CHECK(cudaEventRecord(r->gather_ready, r->stream));
         PF_CUDA_CHECK(cudaStreamWaitEvent(r->gather_stream, r->gather_ready, 0));
         if (r->gather_mode == PF_CUDA_GATHER_MODE_TILES && r->frame_exported) {
-            // Barrier (every rank's export of this frame is complete), then pull the peers' strips.
+            // Push this strip's export into every peer's slot for this rank, barrier (every rank's push has landed), then
+            // expand what the peers pushed into this rank's receive slots.
+            {
+                const size_t slot = ((size_t)r->gather_rank * 2 + (r->gather_frame_serial & 1)) * r->export_buffer_bytes;
+                PushArgs push{};
+                push.local = r->export_region.ptr + slot;
+                for (int32_t g = 0; g < r->gather_world; g++)
+                    if (g != r->gather_rank) push.remote[push.n_remote++] = r->peer_export[g] + slot;
+                push.queue_off = r->export_queue_off, push.color_off = r->export_color_off;
+                push.mask_off = r->export_mask_off, push.blocks_off = r->export_blocks_off;
+                push.segments = (uint32_t)((fb.max_x - fb.min_x + 31) / 32) * (uint32_t)(r->strip_y1 - r->strip_y0);
+                r->stats.drawcall_count += (uint64_t)launch_push_export(push, r->gather_stream);
+                const int parity = (int)(r->gather_frame_serial & 1);
+                PF_CUDA_CHECK(cudaEventRecord(r->push_done[parity], r->gather_stream));
+                r->push_recorded[parity] = true;
+            }
             n.check(n.all_reduce(r->barrier_word, r->barrier_word, 1, Nccl::UINT32, Nccl::SUM, r->gather_comm, r->gather_stream),
                     "ncclAllReduce (barrier)");
             PF_CUDA_CHECK(cudaEventRecord(r->gather_barrier_done, r->gather_stream));
             PullArgs pa{};
-            const size_t buffer_off = (r->gather_frame_serial & 1) * r->export_buffer_bytes;
             for (int32_t g = 0; g < r->gather_world; g++) {
                 if (g == r->gather_rank) continue;
-                const uint8_t *buffer = r->peer_export[g] + buffer_off;
+                const uint8_t *buffer = r->export_region.ptr + ((size_t)g * 2 + (r->gather_frame_serial & 1)) * r->export_buffer_bytes;
                 PullPeer &peer = pa.peers[pa.n_peers++];
                 peer.alpha_count = reinterpret_cast<const uint32_t *>(buffer);
                 peer.queue = reinterpret_cast<const uint32_t *>(buffer + r->export_queue_off);
