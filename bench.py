@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOAD_NAMES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-random1m", action="store_true", help="skip the random1m@16384 sub-record of the headline line")
     ap.add_argument("--gather", default="tiles", choices=["tiles", "nccl", "peer"],
                     help="N > 1, how the frame is assembled on every rank. 'tiles' (default) = PFCudaRendererGatherFrame in "
                          "tile mode: compact exports (4 B per single-colour tile, 1 KB per other tile) pulled from the peers' "
@@ -278,7 +279,8 @@ def main():
         return os.path.join(base, "pf_bench_%s_%d_%d.frame" % (os.environ.get("MASTER_PORT", "0"), index, size))
 
     frames = []
-    for name, flat, xf, size in scene_list:
+
+    def make_frame(name, flat, xf, size, index, device_only=False):
         f = Frame()
         f.name, f.flat, f.size = name, flat, size
         f.y0, f.y1 = api.strip_of_rank((size + 15) // 16, rank, world)
@@ -314,12 +316,12 @@ def main():
             else:
                 f.renderer.set_strip(f.y0, f.y1)
             f.strip_view = f.full[f.y0 * 16:min(f.y1 * 16, size)]
-        f.host = torch.empty((size, size, 4), dtype=torch.uint8, pin_memory=True) if (rank == 0 and world == 1) else None
+        f.host = torch.empty((size, size, 4), dtype=torch.uint8, pin_memory=True) if (rank == 0 and world == 1 and not device_only) else None
         f.host_shared = None
-        if world > 1:
+        if world > 1 and not device_only:
             # End to end at N > 1 the frame is assembled in HOST memory: one shared, page-locked frame that every
             # rank's GPU writes its strip into over its own PCIe link (no device-side gather on this path).
-            f.shm_path = shared_frame_path(len(frames), size)
+            f.shm_path = shared_frame_path(index, size)
             if rank == 0:
                 with open(f.shm_path, "wb") as fh:
                     fh.truncate(size * size * 4)
@@ -337,7 +339,10 @@ def main():
             peers = [everyone[i] for i in range(world) if i != rank]
             f.renderer.set_peer_dests([h for h, _ in peers], [o for _, o in peers])
             f.peer = True
-        frames.append(f)
+        return f
+
+    for name, flat, xf, size in scene_list:
+        frames.append(make_frame(name, flat, xf, size, len(frames)))
 
     copy_stream = torch.cuda.Stream()
     flag = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -459,29 +464,29 @@ def main():
     # kernels in the shadow), frame assembly included; CUDA events around the K frames, max over ranks. The stage
     # times of the same frames feed the roofline: a kernel timed alone, not under three-way overlap.
     isolated_ms, isolated_stage = {}, {}
+
+    def isolated_run(f, steps):
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        f.stream.wait_stream(stream)
+        for _ in range(steps):
+            render_frame(f, False)
+        if dist is not None and not f.peer:
+            f.renderer.gather_wait()
+        stream.wait_stream(f.stream)
+        s1.record(stream)
+        barrier()
+        ms = torch.tensor([s0.elapsed_time(s1) / steps], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
     for f in frames:
         f.renderer.set_timing_enabled(False)
-
-        def isolated_run():
-            barrier()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record(stream)
-            f.stream.wait_stream(stream)
-            for _ in range(args.steps):
-                render_frame(f, False)
-            if dist is not None and not f.peer:
-                f.renderer.gather_wait()
-            stream.wait_stream(f.stream)
-            s1.record(stream)
-            barrier()
-            ms = torch.tensor([s0.elapsed_time(s1) / args.steps], dtype=torch.float64, device="cuda")
-            if dist is not None:
-                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            return float(ms.item())
-
-        isolated_ms[f.name] = isolated_run()  # without the stage events (eight event records per batch)
+        isolated_ms[f.name] = isolated_run(f, args.steps)  # without the stage events (eight event records per batch)
         f.renderer.set_timing_enabled(True)   # resets the accumulated stage times
-        isolated_run()
+        isolated_run(f, args.steps)
         totals, batches = f.renderer.accumulated_times()
         assert batches and batches % args.steps == 0, (batches, args.steps)
         isolated_stage[f.name] = {k: v / args.steps for k, v in totals.items()}
@@ -493,6 +498,25 @@ def main():
     e2e_s = timed(True, e2e_steps)
     h2d = sum(int(f.flat.points.nbytes + f.flat.n_contours * 8 + len(f.flat.points) * 8) for f in frames)
     d2h = sum(f.size * f.size * 4 for f in frames)
+
+    # BASELINE.json configs[3] (random1m@16384: 1 GiB of frame, the case the strips are for) alone on the GPUs, device
+    # resident, same timing as the isolated frames above. A sub-record of the headline line, not the headline value.
+    random1m = None
+    if args.workload == "headline" and not args.no_random1m:
+        (name, flat, xf, size), = workload_scenes("random1m")
+        f = make_frame(name, flat, xf, size, len(frames), device_only=True)
+        r1m_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            render_frame(f, False)
+        ms = isolated_run(f, r1m_steps)
+        segs = f.full_stats["line_segment_count"]
+        random1m = {"workload": WORKLOAD_NAMES["random1m"], "ms_per_step": ms, "steps": r1m_steps, "segments_per_step": segs,
+                    "value": segs / (ms * 1e-3) / 1e9, "unit": UNIT,
+                    "timing": "CUDA events around the steps, frame assembly included, max over ranks; scene resident in HBM"}
+        if dist is not None and args.gather in ("nccl", "tiles"):
+            f.renderer.gather_destroy()
+        del f
+        torch.cuda.empty_cache()
 
     e2e_assembly = "device frame -> pinned host frame"
     if dist is not None:
@@ -582,12 +606,13 @@ def main():
                    "input_gsegments_per_s": inputs_per_step * args.steps / dev_s / 1e9,
                    "gfills_per_s": fills_per_step * args.steps / dev_s / 1e9,
                    "parallelism": f"tile-strip x{world}" + ((" + fused peer-store gather (NVLink P2P) + barrier" if args.gather == "peer"
-                                                             else (" + compact tile exports pulled over NVLink by the library (PFCudaRendererGatherFrame, tile mode), overlapped with the next frame" if args.gather == "tiles"
+                                                             else (" + compact tile exports pushed to the peers over NVLink by the library (PFCudaRendererGatherFrame, tile mode), overlapped with the next frame" if args.gather == "tiles"
                                                                    else " + ncclAllGather issued by the library (PFCudaRendererGatherFrame, frame mode), overlapped with the next frame")) if world > 1 else ""),
                    "l2": "inputs larger than L2: a step touches > 1 GB of stage buffers and frames",
                    "streams": "the frames of a step are independent scenes and render concurrently on one CUDA stream each "
                               "(forked from / joined to the timing stream); no host wait inside the timed region "
                               "(deferred verification); ms_per_frame / stage_ms are per-stream event times and overlap",
+                   "random1m": random1m,
                    "ms_per_frame_isolated": isolated_ms,
                    "stage_ms_isolated": isolated_stage,
                    "ms_per_frame": {f.name: stage_acc[f.name]["total_ms"] / args.steps for f in frames},

@@ -3,7 +3,8 @@
 //! Passed by pointer without conversion — the reference's own `#[repr(C)]` plain-old-data records, whose
 //! field order, sizes and alignment pf_cuda.h mirrors one to one (checked by the `const _` size assertions
 //! at the end of this file): `Vector2F` (8 bytes), `SegmentIndicesD3D11` (8), `PropagateMetadataD3D11`
-//! (48), `DiceMetadataD3D11` (16), `TilePathInfoD3D11` (16), `BackdropInfoD3D11` (12).
+//! (48), `DiceMetadataD3D11` (16), `TilePathInfoD3D11` (16), `BackdropInfoD3D11` (12), `ColorU` (4: the
+//! texels of UploadTexelData).
 //!
 //! Converted field by field — everything else. In particular `TextureMetadataEntry` is NOT layout
 //! compatible with `PFTextureMetadataEntry`: its `Transform2F` holds a 16-byte aligned `F32x4` matrix
@@ -11,6 +12,7 @@
 //! enum (content/src/effects.rs:44-60) and its `BlendMode` a one-byte enum whose `SrcOver` is
 //! discriminant 4, not 0 (effects.rs:99-110). lib.rs `texture_metadata_entry` builds the C record.
 
+use pathfinder_color::ColorU;
 use pathfinder_geometry::rect::RectF;
 use pathfinder_geometry::vector::Vector2F;
 use pathfinder_renderer::gpu_data::{BackdropInfoD3D11, DiceMetadataD3D11, PropagateMetadataD3D11};
@@ -171,17 +173,67 @@ pub struct PFUploadSceneD3D11 {
     pub payload_persists: u32, // 0: borrowed for the call (the reference's semantics)
 }
 
+// TextureLocation / TileBatchTexture / the texture-page and render-target commands (pf_cuda.h). The reference's
+// RectI is an I32x4 (16-byte aligned SIMD lanes: origin x, y, lower right x, y), so locations are converted too.
+pub const TEXTURE_SAMPLING_FLAGS_REPEAT_U: u8 = 0x1;
+pub const TEXTURE_SAMPLING_FLAGS_REPEAT_V: u8 = 0x2;
+pub const TEXTURE_SAMPLING_FLAGS_NEAREST_MIN: u8 = 0x4;
+pub const TEXTURE_SAMPLING_FLAGS_NEAREST_MAG: u8 = 0x8;
+pub const PAINT_COMPOSITE_OP_SRC_IN: u8 = 0;
+pub const PAINT_COMPOSITE_OP_DEST_IN: u8 = 1;
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFTextureLocation {
+    pub page: u32,
+    pub rect: [i32; 4], // origin x, y, lower right x, y
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFTileBatchTexture {
+    pub page: u32,
+    pub sampling_flags: u8,
+    pub composite_op: u8,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFAllocateTexturePage {
+    pub page_id: u32,
+    pub size: [i32; 2],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFUploadTexelData {
+    pub texels: *const ColorU, // four bytes r, g, b, a: PFColorU
+    pub texel_count: usize,
+    pub location: PFTextureLocation,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct PFDeclareRenderTarget {
+    pub render_target_id: u32,
+    pub location: PFTextureLocation,
+}
+
 #[repr(C)]
 #[derive(Clone, Copy)]
 pub struct PFDrawTilesD3D11 {
     pub tile_batch_data: PFTileBatchDataD3D11,
     pub has_color_texture: u32,
+    pub color_texture: PFTileBatchTexture,
 }
 
 #[repr(C)]
 #[derive(Clone, Copy)]
 pub union PFRenderCommandPayload {
     pub start: PFStart,
+    pub allocate_texture_page: PFAllocateTexturePage,
+    pub upload_texel_data: PFUploadTexelData,
+    pub declare_render_target: PFDeclareRenderTarget,
     pub upload_texture_metadata: PFUploadTextureMetadata,
     pub upload_scene_d3d11: PFUploadSceneD3D11,
     pub prepare_clip_tiles_d3d11: PFTileBatchDataD3D11,
@@ -210,6 +262,16 @@ extern "C" {
     pub fn PFCudaRendererEndScene(renderer: *mut c_void) -> i32;
     pub fn PFCudaRendererReadPixels(renderer: *mut c_void, dst: *mut u8, stride: usize) -> i32;
     pub fn PFCudaRendererSynchronize(renderer: *mut c_void) -> i32;
+    pub fn PFCudaRendererReadTexturePage(renderer: *mut c_void, page_id: u32, dst: *mut u8, stride: usize,
+                                         size_out: *mut i32) -> i32; // size_out: PFVector2I, two i32
+    // Several GPUs, one frame (pf_cuda.h "Frame assembly"): rank 0 makes the id, the application ships its 128 bytes.
+    pub fn PFCudaGatherCreateId(id_out: *mut u8) -> i32; // PFCudaGatherId: 128 opaque bytes
+    pub fn PFCudaStripOfRank(tile_rows: i32, rank: i32, world: i32, y0: *mut i32, y1: *mut i32);
+    pub fn PFCudaRendererGatherInit(renderer: *mut c_void, id: *const u8, rank: i32, world: i32) -> i32;
+    pub fn PFCudaRendererGatherSetMode(renderer: *mut c_void, mode: i32) -> i32;
+    pub fn PFCudaRendererGatherFrame(renderer: *mut c_void) -> i32;
+    pub fn PFCudaRendererGatherWait(renderer: *mut c_void) -> i32;
+    pub fn PFCudaRendererGatherDestroy(renderer: *mut c_void) -> i32;
 }
 
 // Layout checks (compile time): the C records this file declares, and the reference records it passes by
@@ -217,6 +279,9 @@ extern "C" {
 const _: () = assert!(std::mem::size_of::<PFRendererMode>() == 1);
 const _: () = assert!(std::mem::size_of::<PFFilter>() == 88);
 const _: () = assert!(std::mem::size_of::<PFTextureMetadataEntry>() == 124);
+const _: () = assert!(std::mem::size_of::<PFTextureLocation>() == 20);
+const _: () = assert!(std::mem::size_of::<PFTileBatchTexture>() == 8);
+const _: () = assert!(std::mem::size_of::<ColorU>() == 4);
 const _: () = assert!(std::mem::size_of::<Vector2F>() == 8);
 const _: () = assert!(std::mem::size_of::<SegmentIndicesD3D11>() == 8);
 const _: () = assert!(std::mem::size_of::<PropagateMetadataD3D11>() == 48);

@@ -15,13 +15,12 @@ use pathfinder_geometry::vector::Vector2I;
 use pathfinder_renderer::concurrent::executor::Executor;
 use pathfinder_renderer::gpu::options::{RendererLevel, RendererMode};
 use pathfinder_renderer::gpu_data::{ColorCombineMode, PathSource, RenderCommand, SegmentsD3D11};
-use pathfinder_renderer::gpu_data::{TextureMetadataEntry, TileBatchDataD3D11};
+use pathfinder_renderer::gpu_data::{TextureLocation, TextureMetadataEntry, TileBatchDataD3D11, TileBatchTexture};
 use pathfinder_renderer::options::{BuildOptions, RenderCommandListener};
 use pathfinder_renderer::scene::{Scene, SceneSink};
 use pathfinder_resources::ResourceLoader;
 use std::ffi::CStr;
 use std::os::raw::c_void;
-use std::ptr;
 use std::sync::{Arc, Mutex};
 
 pub struct CudaRenderer {
@@ -167,6 +166,29 @@ fn texture_metadata_entry(e: &TextureMetadataEntry) -> ffi::PFTextureMetadataEnt
     }
 }
 
+fn texture_location(l: &TextureLocation) -> ffi::PFTextureLocation {
+    // RectI is SIMD lanes with 16-byte alignment: copied out lane by lane, never cast.
+    ffi::PFTextureLocation {
+        page: l.page.0,
+        rect: [l.rect.origin_x(), l.rect.origin_y(), l.rect.lower_right().x(), l.rect.lower_right().y()],
+    }
+}
+
+fn tile_batch_texture(t: &Option<TileBatchTexture>) -> ffi::PFTileBatchTexture {
+    match *t {
+        None => ffi::PFTileBatchTexture { page: 0, sampling_flags: 0, composite_op: ffi::PAINT_COMPOSITE_OP_SRC_IN },
+        Some(ref t) => ffi::PFTileBatchTexture {
+            page: t.page.0,
+            sampling_flags: t.sampling_flags.bits(), // the PF_TEXTURE_SAMPLING_FLAGS_* bits are the reference's
+            // `composite_op` is pub(crate) in the reference (gpu_data.rs:252). Inside the crate (this file moved
+            // next to gpu/d3d11/renderer.rs) read the field; outside, either add a one-line accessor there or,
+            // as here, tell the two variants apart through the derived Debug.
+            composite_op: if format!("{:?}", t).contains("DestIn") { ffi::PAINT_COMPOSITE_OP_DEST_IN }
+                          else { ffi::PAINT_COMPOSITE_OP_SRC_IN },
+        },
+    }
+}
+
 fn simple(kind: u32) -> ffi::PFRenderCommand {
     ffi::PFRenderCommand { kind, u: ffi::PFRenderCommandPayload { push_render_target: 0 } }
 }
@@ -176,14 +198,16 @@ impl CudaRenderer {
                background: Option<ColorF>) -> CudaRenderer {
         assert_eq!(mode.level, RendererLevel::D3D11);
         // The same resource Renderer::new loads (gpu/renderer.rs:207-222).
-        let area = image::load_from_memory(&resources.slurp("textures/area-lut.png").unwrap()).unwrap().to_rgba();
+        let area = image::load_from_memory(&resources.slurp("textures/area-lut.png").unwrap()).unwrap().to_rgba8();
+        // textures/gamma-lut.png, the 256 x 8 L8 table of the text filter (gpu/renderer.rs:207-222 loads both)
+        let gamma = image::load_from_memory(&resources.slurp("textures/gamma-lut.png").unwrap()).unwrap().to_luma8();
         let options = ffi::PFCudaRendererOptions {
             dest_size: [dest_size.x(), dest_size.y()],
             background_color: background.map_or([0.0; 4], |c| [c.r(), c.g(), c.b(), c.a()]),
             flags: background.is_some() as u8,
         };
         let raw = unsafe {
-            ffi::PFCudaRendererCreate(ffi::PFCudaDeviceCreate(ordinal), area.as_ptr(), ptr::null(),
+            ffi::PFCudaRendererCreate(ffi::PFCudaDeviceCreate(ordinal), area.as_ptr(), gamma.as_ptr(),
                                       &ffi::PFRendererMode { level: 2 }, &options)
         };
         assert!(!raw.is_null(), "{}", last_error());
@@ -247,6 +271,7 @@ impl CudaRenderer {
                     draw_tiles_d3d11: ffi::PFDrawTilesD3D11 {
                         tile_batch_data: batch(&draw.tile_batch_data),
                         has_color_texture: draw.color_texture.is_some() as u32,
+                        color_texture: tile_batch_texture(&draw.color_texture),
                     },
                 },
             },
@@ -259,14 +284,39 @@ impl CudaRenderer {
                 kind: ffi::FINISH,
                 u: ffi::PFRenderCommandPayload { finish_cpu_build_time_ns: cpu_build_time.as_nanos() as u64 },
             },
-            // D3D9-level commands are refused with PF_CUDA_ERROR_WRONG_LEVEL, textures / render targets
-            // with PF_CUDA_ERROR_UNSUPPORTED: `check` turns both into a panic, like the reference.
+            RenderCommand::AllocateTexturePage { page_id, ref descriptor } => ffi::PFRenderCommand {
+                kind: ffi::ALLOCATE_TEXTURE_PAGE,
+                u: ffi::PFRenderCommandPayload {
+                    allocate_texture_page: ffi::PFAllocateTexturePage {
+                        page_id: page_id.0,
+                        size: [descriptor.size.x(), descriptor.size.y()],
+                    },
+                },
+            },
+            RenderCommand::UploadTexelData { ref texels, ref location } => ffi::PFRenderCommand {
+                kind: ffi::UPLOAD_TEXEL_DATA,
+                u: ffi::PFRenderCommandPayload {
+                    upload_texel_data: ffi::PFUploadTexelData {
+                        texels: texels.as_ptr(),
+                        texel_count: texels.len(),
+                        location: texture_location(location),
+                    },
+                },
+            },
+            RenderCommand::DeclareRenderTarget { id, ref location } => ffi::PFRenderCommand {
+                kind: ffi::DECLARE_RENDER_TARGET,
+                u: ffi::PFRenderCommandPayload {
+                    declare_render_target: ffi::PFDeclareRenderTarget {
+                        render_target_id: id.render_target,
+                        location: texture_location(location),
+                    },
+                },
+            },
+            // D3D9-level commands are refused with PF_CUDA_ERROR_WRONG_LEVEL, paints / blends / filters outside
+            // the built set with PF_CUDA_ERROR_UNSUPPORTED: `check` turns both into a panic, like the reference.
             RenderCommand::AddFillsD3D9(_) => simple(ffi::ADD_FILLS_D3D9),
             RenderCommand::FlushFillsD3D9 => simple(ffi::FLUSH_FILLS_D3D9),
             RenderCommand::DrawTilesD3D9(_) => simple(ffi::DRAW_TILES_D3D9),
-            RenderCommand::AllocateTexturePage { .. } => simple(ffi::ALLOCATE_TEXTURE_PAGE),
-            RenderCommand::UploadTexelData { .. } => simple(ffi::UPLOAD_TEXEL_DATA),
-            RenderCommand::DeclareRenderTarget { .. } => simple(ffi::DECLARE_RENDER_TARGET),
         };
         check(unsafe { ffi::PFCudaRendererRenderCommand(self.raw, &c) })
     }

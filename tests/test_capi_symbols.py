@@ -85,8 +85,13 @@ def test_rust_bindings_agree_with_the_header():
     for fn in re.findall(r"pub fn (PF\w+)\(", ffi):
         assert fn in declared, fn
     # the extension fields are present on both sides
-    for field in ("content_key", "payload_persists", "has_clipped_path_info"):
-        assert field in header and field in ffi
+    for field in ("content_key", "payload_persists", "has_clipped_path_info", "color_texture", "allocate_texture_page",
+                  "upload_texel_data", "declare_render_target", "sampling_flags", "composite_op"):
+        assert field in header and field in ffi, field
+    # texture sampling flags / composite ops (u8 on both sides)
+    small = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"pub const (\w+): u8 = (\w+);", ffi)}
+    for name, value in re.findall(r"#define PF_((?:TEXTURE_SAMPLING_FLAGS|PAINT_COMPOSITE_OP)_\w+) (\w+)", header):
+        assert small.get(name) == int(value, 0), name
 
 
 def test_rust_bindings_pass_only_verified_pod_records_by_pointer():
@@ -100,7 +105,7 @@ def test_rust_bindings_pass_only_verified_pod_records_by_pointer():
     ffi = open(os.path.join(root, "integration", "pathfinder_cuda", "src", "ffi.rs")).read()
     lib = open(os.path.join(root, "integration", "pathfinder_cuda", "src", "lib.rs")).read()
     allowed = {"Vector2F", "SegmentIndicesD3D11", "PropagateMetadataD3D11", "DiceMetadataD3D11", "TilePathInfoD3D11",
-               "BackdropInfoD3D11", "RectF"}
+               "BackdropInfoD3D11", "RectF", "ColorU"}
     own = set(re.findall(r"pub (?:struct|union) (\w+)", ffi))
     primitives = {"u8", "c_char", "c_void", "f32", "u32", "i32", "u64"}
     for type_name in re.findall(r"\*(?:const|mut) (\w+)", ffi):
@@ -112,6 +117,10 @@ def test_rust_bindings_pass_only_verified_pod_records_by_pointer():
     # the conversion exists and is used for UploadTextureMetadata
     assert "fn texture_metadata_entry(" in lib and "map(texture_metadata_entry)" in lib
     assert "entries.as_ptr()" not in lib
+    # texture pages, render targets and colour textures reach the library with their payloads (no `simple(...)` stub)
+    for kind in ("ALLOCATE_TEXTURE_PAGE", "UPLOAD_TEXEL_DATA", "DECLARE_RENDER_TARGET"):
+        assert "simple(ffi::%s)" % kind not in lib and "kind: ffi::%s" % kind in lib, kind
+    assert "color_texture: tile_batch_texture(" in lib and "fn texture_location(" in lib
     # RendererMode.level is one byte on both sides
     assert re.search(r"pub struct PFRendererMode \{\s*pub level: u8", ffi)
 
