@@ -31,14 +31,23 @@ namespace {
 #define PF_TILE_WARPS 4 // warps per block of k_tile_alpha
 #endif
 #ifndef PF_TILE_MIN_BLOCKS
-#define PF_TILE_MIN_BLOCKS 6 // resident blocks per SM the register allocation must allow
+#define PF_TILE_MIN_BLOCKS 7 // resident blocks per SM the register allocation must allow (70 registers; 6 and 8 measured slower)
 #endif
 #ifndef PF_PREFETCH
 #define PF_PREFETCH 1
 #endif
+#ifndef PF_FILL_FFMA2
+#define PF_FILL_FFMA2 1
+#endif
+#ifndef PF_SIMPLE_STORE
+#define PF_SIMPLE_STORE 1
+#endif
 
 constexpr int TILE_WARPS = PF_TILE_WARPS;
-constexpr int ENTRY_CAP = 32;  // entries rank-sorted in shared memory; deeper lists are walked by selection
+#ifndef PF_ENTRY_CAP
+#define PF_ENTRY_CAP 32
+#endif
+constexpr int ENTRY_CAP = PF_ENTRY_CAP;  // entries rank-sorted in shared memory; deeper lists are walked by selection
 constexpr int SOLID_MAX = 8;   // deepest all-solid list k_tile_solid blends itself
 constexpr uint32_t PF_FILTER_TEXT_KIND = 2; // PF_FILTER_TEXT (include/pf_cuda.h)
 constexpr uint32_t WORK_PARKED = 0xf0000000u; // k_list_emit parks the tile counter here when a stage overflowed
@@ -141,11 +150,10 @@ __global__ void __launch_bounds__(128) k_tile_solid(CompositeArgs a) {
     bool has_alpha = false;
     if (in_row && ty >= a.fb.min_y && ty < a.fb.max_y) {
         const size_t index = (size_t)(ty - a.fb.min_y) * (size_t)fb_w + (size_t)col;
+        // (three independent loads: no load waits for another)
         n = __ldg(a.fb_count + index);
-        if (n) {
-            e0 = __ldg(a.fb_start + index);
-            has_alpha = __ldg(a.fb_alpha + index) != 0u;
-        }
+        e0 = __ldg(a.fb_start + index);
+        has_alpha = __ldg(a.fb_alpha + index) != 0u;
     }
     // Tiles that need per-pixel work go to the queue of k_tile_alpha (one counter increment per warp).
     const bool queued = in_row && (has_alpha || n > (uint32_t)SOLID_MAX || (LOAD_DEST && n > 0));
@@ -169,13 +177,15 @@ __global__ void __launch_bounds__(128) k_tile_solid(CompositeArgs a) {
     // repeated minimum (the run is in arbitrary order).
     Px c = px_from(a.clear_color);
     if (paints) {
+        uint32_t keys[SOLID_MAX]; // one round of loads for all the keys, then selection in registers
+#pragma unroll
+        for (int j = 0; j < SOLID_MAX; j++) keys[j] = (uint32_t)j < n ? __ldg(&a.entries[e0 + j].tile_index) : 0xffffffffu;
         uint32_t last = 0;
         for (uint32_t i = 0; i < n; i++) {
             uint32_t best = 0xffffffffu, best_j = 0;
-            for (uint32_t j = 0; j < n; j++) {
-                const uint32_t key = __ldg(&a.entries[e0 + j].tile_index);
-                if ((i == 0 || key > last) && key < best) best = key, best_j = j;
-            }
+#pragma unroll
+            for (int j = 0; j < SOLID_MAX; j++)
+                if ((i == 0 || keys[j] > last) && keys[j] < best) best = keys[j], best_j = (uint32_t)j;
             last = best;
             const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + best_j));
             const float4 paint = __ldg(&a.entries[e0 + best_j].color);
@@ -275,6 +285,23 @@ __device__ __forceinline__ void accumulate_fill(const float4 p0, const float4 p1
     const float u = fmaf(y, 1.0f / 16.0f, u_off);           // (y + 8) / 16 for the first strip
     const float4 a0 = tex2D<float4>(lut, u, v);
     const float4 a1 = tex2D<float4>(lut, u - 0.25f, v);     // the strip 4 rows lower sees the segment 4 px higher
+#if PF_FILL_FFMA2
+    // two packed FMAs per strip: the texture unit returns the four rows in consecutive registers
+    const f32x2 dd = pack2(dX, dX), magic = pack2(COV_MAGIC, COV_MAGIC);
+    float c0, c1, c2, c3, c4, c5, c6, c7;
+    unpack2(fma2(pack2(a0.x, a0.y), dd, magic), c0, c1);
+    unpack2(fma2(pack2(a0.z, a0.w), dd, magic), c2, c3);
+    unpack2(fma2(pack2(a1.x, a1.y), dd, magic), c4, c5);
+    unpack2(fma2(pack2(a1.z, a1.w), dd, magic), c6, c7);
+    acc[0] += __float_as_uint(c0);
+    acc[1] += __float_as_uint(c1);
+    acc[2] += __float_as_uint(c2);
+    acc[3] += __float_as_uint(c3);
+    acc[4] += __float_as_uint(c4);
+    acc[5] += __float_as_uint(c5);
+    acc[6] += __float_as_uint(c6);
+    acc[7] += __float_as_uint(c7);
+#else
     acc[0] += __float_as_uint(fmaf(a0.x, dX, COV_MAGIC));
     acc[1] += __float_as_uint(fmaf(a0.y, dX, COV_MAGIC));
     acc[2] += __float_as_uint(fmaf(a0.z, dX, COV_MAGIC));
@@ -283,6 +310,7 @@ __device__ __forceinline__ void accumulate_fill(const float4 p0, const float4 p1
     acc[5] += __float_as_uint(fmaf(a1.y, dX, COV_MAGIC));
     acc[6] += __float_as_uint(fmaf(a1.z, dX, COV_MAGIC));
     acc[7] += __float_as_uint(fmaf(a1.w, dX, COV_MAGIC));
+#endif
 }
 
 template <bool GENERAL>
@@ -424,7 +452,7 @@ __device__ __forceinline__ float4 textured_color(const PaintTexture &p, const Co
 }
 
 template <bool LOAD_DEST, bool GENERAL>
-__global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_alpha(CompositeArgs a) {
+__global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? PF_TILE_MIN_BLOCKS - 1 : PF_TILE_MIN_BLOCKS) k_tile_alpha(CompositeArgs a) {
     __shared__ TileWarpShared<GENERAL> sh_all[TILE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TileWarpShared<GENERAL> &sh = sh_all[warp];
@@ -435,6 +463,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
     const int x = lane & 15, half = lane >> 4;
     const float xf = (float)x;
     const float u_off = 0.5f - 0.5f * (float)half; // (8 - 8 * half) / 16
+    const bool simple_store = a.n_dest == 1 && a.export_blocks == nullptr && (a.dest_align_mask & 15u) == 0;
 
     // Persistent warps: tiles differ wildly in depth, so every warp pulls its next tile from a global
     // counter. The pull is software-pipelined two deep: while tile i is composited, the counter increment
@@ -631,11 +660,19 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
         // same stores also go straight into every peer's copy of the frame over NVLink.
         uint32_t pk[8];
         if (expanded) {
-            const f32x2 ss = pack2(s, s);
+            // (v * s + o) * 255 + 2^23 = v * (255 s) + (255 o + 2^23): the affine map and the scaling in one FMA
+            const f32x2 scale = pack2(255.0f, 255.0f), magic = pack2(8388608.0f, 8388608.0f);
+            const f32x2 s255 = pack2(s * 255.0f, s * 255.0f);
+            const f32x2 o_rg = fma2(o.rg, scale, magic), o_ba = fma2(o.ba, scale, magic);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const float4 v = sh.dst[k * 32 + lane];
-                pk[k] = pack_rgba8(Px{fma2(pack2(v.x, v.y), ss, o.rg), fma2(pack2(v.z, v.w), ss, o.ba)});
+                float r, g, b, al;
+                unpack2(fma2(pack2(v.x, v.y), s255, o_rg), r, g);
+                unpack2(fma2(pack2(v.z, v.w), s255, o_ba), b, al);
+                const uint32_t lo = __byte_perm(__float_as_uint(r), __float_as_uint(g), 0x0040);
+                const uint32_t hi = __byte_perm(__float_as_uint(b), __float_as_uint(al), 0x0040);
+                pk[k] = __byte_perm(lo, hi, 0x5410);
             }
         } else {
             const uint32_t packed = pack_rgba8(o);
@@ -643,6 +680,18 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
             for (int k = 0; k < 8; k++) pk[k] = packed;
         }
         const bool inside = tx >= 0 && ty >= 0 && tx * 16 + 16 <= a.dest_w && ty * 16 + 16 <= a.dest_h;
+        if (PF_SIMPLE_STORE && simple_store && inside) {
+            // One local, aligned image, nothing exported: no loop over destinations, no per-destination checks.
+#pragma unroll
+            for (int k = 0; k < 8; k++) sh.stage[(half * 8 + k) * 16 + half * 16 + x] = pk[k];
+            __syncwarp();
+            const int row0 = lane >> 2, quarter = lane & 3;
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(&sh.stage[row0 * 16 + quarter * 4]);
+            const uint4 v1 = *reinterpret_cast<const uint4 *>(&sh.stage[(row0 + 8) * 16 + 16 + quarter * 4]);
+            uint8_t *out = a.dest + (size_t)(ty * 16 + row0) * a.dest_pitch + (size_t)(tx * 64 + quarter * 16);
+            *reinterpret_cast<uint4 *>(out) = v0;
+            *reinterpret_cast<uint4 *>(out + 8 * a.dest_pitch) = v1;
+        } else {
         const bool vector_store = inside && (a.dest_align_mask & 15u) == 0;
         if (vector_store || a.export_blocks) {
 #pragma unroll
@@ -675,6 +724,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, PF_TILE_MIN_BLOCKS) k_tile_al
                         *reinterpret_cast<uint32_t *>(a.dests[d] + (size_t)py * a.dest_pitch + (size_t)px * 4) = pk[k];
                 }
             }
+        }
         }
         __syncwarp(); // the next tile reuses this warp's shared-memory slots
 #if PF_PREFETCH
