@@ -186,8 +186,9 @@ typedef struct PFFilter {
 /* The C-side form of TextureMetadataEntry (gpu_data.rs:336-344). NOT the memory layout of the Rust struct
  * (its Transform2F is a 16-byte aligned F32x4 + F32x2, its Filter a data-carrying enum, its BlendMode a one-byte
  * enum): the Rust glue converts every entry (integration/pathfinder_cuda/src/lib.rs
- * `texture_metadata_entry`). On the hot path today: colour combine mode NONE, filter NONE or TEXT, blend mode
- * SRC_OVER; anything else is refused with PF_CUDA_ERROR_UNSUPPORTED. */
+ * `texture_metadata_entry`). Evaluated: colour combine modes NONE and SRC_IN, every filter, every blend mode that is
+ * not destructive (BlendMode::is_destructive: CLEAR, COPY, SRC_IN, DEST_IN, SRC_OUT, DEST_ATOP are refused with
+ * PF_CUDA_ERROR_UNSUPPORTED, as is the DEST_IN combine mode). */
 typedef struct PFTextureMetadataEntry {
     PFTransform2F color_0_transform;
     uint32_t color_0_combine_mode;   /* PF_COLOR_COMBINE_MODE_* */
@@ -258,7 +259,7 @@ typedef struct PFTextureLocation {
 } PFTextureLocation;
 
 /* TextureSamplingFlags (gpu/src/lib.rs:521-528) and TileBatchTexture (gpu_data.rs:247-254). composite_op is
- * PaintCompositeOp (paint.rs): only SrcIn (0) is on the path today. */
+ * PaintCompositeOp (paint.rs): SrcIn (0) only; DestIn is refused. */
 #define PF_TEXTURE_SAMPLING_FLAGS_REPEAT_U 0x1
 #define PF_TEXTURE_SAMPLING_FLAGS_REPEAT_V 0x2
 #define PF_TEXTURE_SAMPLING_FLAGS_NEAREST_MIN 0x4
@@ -529,6 +530,31 @@ void PFScenePopRenderTarget(PFSceneRef scene);
  * renderer/src/paint.rs:138-146. The pattern transform maps render-target pixels to scene coordinates. */
 uint16_t PFScenePushPaintRenderTargetPattern(PFSceneRef scene, uint32_t render_target_id,
                                              const PFTransform2F *pattern_transform, const PFFilter *filter);
+/* Scene::push_paint(&Paint::from_pattern(Pattern::from_image(image))) (content/src/pattern.rs:52-103,
+ * renderer/src/paint.rs:138-146): `pixels` = width x height RGBA8 texels, row-major, top row first, not
+ * premultiplied (copied). The pattern transform maps image pixels to scene coordinates (NULL: identity). */
+#define PF_PATTERN_FLAG_REPEAT_X 0x1      /* PatternFlags, pattern.rs:40-50 */
+#define PF_PATTERN_FLAG_REPEAT_Y 0x2
+#define PF_PATTERN_FLAG_NO_SMOOTHING 0x4
+uint16_t PFScenePushPaintImagePattern(PFSceneRef scene, const PFColorU *pixels, int32_t width, int32_t height,
+                                      const PFTransform2F *pattern_transform, uint32_t flags, const PFFilter *filter);
+/* Scene::push_paint(&Paint::from_gradient(gradient)) (content/src/gradient.rs:30-186, paint.rs:126-136).
+ * Linear: colours run along from -> to. Radial: the circles (from, radii[0]) -> (to, radii[1]) in the space
+ * `transform` maps to scene coordinates (GradientGeometry::Radial). Stops sorted by offset. */
+#define PF_GRADIENT_LINEAR 0
+#define PF_GRADIENT_RADIAL 1
+#define PF_GRADIENT_WRAP_CLAMP 0          /* GradientWrap, gradient.rs:62-70 */
+#define PF_GRADIENT_WRAP_REPEAT 1
+typedef struct PFColorStop { PFColorU color; float offset; } PFColorStop; /* gradient.rs:54-60 */
+typedef struct PFGradient {
+    uint32_t kind, wrap;
+    PFVector2F from, to;
+    float radii[2];
+    PFTransform2F transform;
+    const PFColorStop *stops;
+    size_t stop_count;
+} PFGradient;
+uint16_t PFScenePushPaintGradient(PFSceneRef scene, const PFGradient *gradient);
 /* Scene::push_draw_path (scene.rs:77-82). The outline is given as contours of points + flags:
  * contour i owns points [contour_offsets[i], contour_offsets[i+1]). Returns the DrawPathId, or
  * PF_PATH_INDEX_NONE (see PFCudaGetLastError) and leaves the scene unchanged when the paint id or fill rule is

@@ -76,12 +76,28 @@ class PFBackdropInfoD3D11(C.Structure):
 
 
 PF_COLOR_COMBINE_MODE_NONE, PF_COLOR_COMBINE_MODE_SRC_IN, PF_COLOR_COMBINE_MODE_DEST_IN = 0, 1, 2
-PF_FILTER_NONE, PF_FILTER_TEXT = 0, 2
+PF_FILTER_NONE, PF_FILTER_RADIAL_GRADIENT, PF_FILTER_TEXT, PF_FILTER_BLUR, PF_FILTER_COLOR_MATRIX = 0, 1, 2, 3, 4
+PF_FILTER_FLAG_BLUR_Y = 0x1
+PF_PATTERN_FLAG_REPEAT_X, PF_PATTERN_FLAG_REPEAT_Y, PF_PATTERN_FLAG_NO_SMOOTHING = 0x1, 0x2, 0x4
+PF_GRADIENT_LINEAR, PF_GRADIENT_RADIAL = 0, 1
+PF_GRADIENT_WRAP_CLAMP, PF_GRADIENT_WRAP_REPEAT = 0, 1
+PF_TEXTURE_SAMPLING_FLAGS_REPEAT_U, PF_TEXTURE_SAMPLING_FLAGS_REPEAT_V = 0x1, 0x2
+PF_TEXTURE_SAMPLING_FLAGS_NEAREST_MIN, PF_TEXTURE_SAMPLING_FLAGS_NEAREST_MAG = 0x4, 0x8
 PF_FILTER_FLAG_TEXT_HAS_KERNEL, PF_FILTER_FLAG_TEXT_GAMMA_CORRECTION = 0x1, 0x2
 
 
 class PFFilter(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("flags", C.c_uint32), ("params", C.c_float * 20)]
+
+
+class PFColorStop(C.Structure):
+    _fields_ = [("color", PFColorU), ("offset", C.c_float)]
+
+
+class PFGradient(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("wrap", C.c_uint32), ("from_", PFVector2F), ("to", PFVector2F),
+                ("radii", C.c_float * 2), ("transform", PFTransform2F), ("stops", C.POINTER(PFColorStop)),
+                ("stop_count", C.c_size_t)]
 
 
 class PFTextureMetadataEntry(C.Structure):
@@ -280,6 +296,9 @@ SIGNATURES = {
     "PFScenePushRenderTarget": (C.c_uint32, [C.c_void_p, C.c_int32, C.c_int32]),
     "PFScenePopRenderTarget": (None, [C.c_void_p]),
     "PFScenePushPaintRenderTargetPattern": (C.c_uint16, [C.c_void_p, C.c_uint32, C.POINTER(PFTransform2F), C.POINTER(PFFilter)]),
+    "PFScenePushPaintImagePattern": (C.c_uint16, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(PFTransform2F),
+                                                  C.c_uint32, C.POINTER(PFFilter)]),
+    "PFScenePushPaintGradient": (C.c_uint16, [C.c_void_p, C.POINTER(PFGradient)]),
     "PFScenePushDrawPath": (C.c_uint32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint32]),
     "PFOutlineStrokeToFill": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),

@@ -20,6 +20,11 @@ FILL_DTYPE = np.dtype([("from_x", "<u2"), ("from_y", "<u2"), ("to_x", "<u2"), ("
 TILE_DTYPE = np.dtype([("tile_x", "<i2"), ("tile_y", "<i2"), ("alpha_tile_id", "<u4"), ("path_id", "<u4"),
                        ("color", "<u2"), ("ctrl", "u1"), ("backdrop", "i1")])
 BLEND_MODE_SRC_OVER = 4  # PF_BLEND_MODE_SRC_OVER (BlendMode::SrcOver, content/src/effects.rs:99-163)
+# BlendMode, numbered like include/pf_cuda.h PF_BLEND_MODE_*
+BLEND_MODES = {name: i for i, name in enumerate(
+    ["clear", "copy", "src_in", "src_out", "src_over", "src_atop", "dest_in", "dest_out", "dest_over", "dest_atop", "xor",
+     "lighter", "darken", "lighten", "multiply", "screen", "hard_light", "overlay", "color_dodge", "color_burn",
+     "soft_light", "difference", "exclusion", "hue", "saturation", "color", "luminosity"])}
 CLIP_DTYPE = np.dtype([("dest_tile_id", "<u4"), ("dest_backdrop", "<i4"), ("src_tile_id", "<u4"), ("src_backdrop", "<i4")])
 
 
@@ -132,7 +137,7 @@ class Scene:
     def pop_render_target(self):
         L.lib().PFScenePopRenderTarget(self._h)
 
-    def push_render_target_pattern(self, render_target_id: int, transform=None, text_filter=None) -> int:
+    def push_render_target_pattern(self, render_target_id: int, transform=None, text_filter=None, pattern_filter=None) -> int:
         """Paint::from_pattern(Pattern::from_render_target(id, size)). transform = (m11, m12, m21, m22, tx, ty) maps
         render-target pixels to scene coordinates (pattern.apply_transform). text_filter = dict(fg=rgb, bg=rgb,
         kernel=(4 floats) | None, gamma=bool) for PatternFilter::Text."""
@@ -140,7 +145,7 @@ class Scene:
         if transform is not None:
             m11, m12, m21, m22, tx, ty = [float(v) for v in transform]
             t = L.PFTransform2F(L.PFMatrix2x2F(m11, m12, m21, m22), L.PFVector2F(tx, ty))
-        f = None
+        f = self._pattern_filter_c(pattern_filter)
         if text_filter is not None:
             f = L.PFFilter()
             f.kind = L.PF_FILTER_TEXT
@@ -156,6 +161,70 @@ class Scene:
         pid = int(L.lib().PFScenePushPaintRenderTargetPattern(self._h, int(render_target_id),
                                                              C.byref(t) if t is not None else None,
                                                              C.byref(f) if f is not None else None))
+        if pid == 0xFFFF:
+            raise L.PathfinderCudaError(L.PF_CUDA_ERROR_INVALID_ARGUMENT, L.lib().PFCudaGetLastError().decode())
+        return pid
+
+    @staticmethod
+    def _transform_c(transform):
+        if transform is None:
+            return None
+        m11, m12, m21, m22, tx, ty = [float(v) for v in transform]
+        return L.PFTransform2F(L.PFMatrix2x2F(m11, m12, m21, m22), L.PFVector2F(tx, ty))
+
+    @staticmethod
+    def _pattern_filter_c(pattern_filter):
+        """dict(blur=sigma, direction="x" | "y") or dict(color_matrix=20 floats: the five F32x4 columns)."""
+        if pattern_filter is None:
+            return None
+        f = L.PFFilter()
+        if "blur" in pattern_filter:
+            f.kind = L.PF_FILTER_BLUR
+            f.params[0] = float(pattern_filter["blur"])
+            if pattern_filter.get("direction", "x") == "y":
+                f.flags |= L.PF_FILTER_FLAG_BLUR_Y
+        elif "color_matrix" in pattern_filter:
+            f.kind = L.PF_FILTER_COLOR_MATRIX
+            for i, v in enumerate(pattern_filter["color_matrix"]):
+                f.params[i] = float(v)
+        else:
+            raise ValueError("unknown pattern filter")
+        return f
+
+    def push_image_pattern(self, pixels, transform=None, repeat_x=False, repeat_y=False, smoothing=True,
+                           pattern_filter=None) -> int:
+        """Paint::from_pattern(Pattern::from_image(image)): pixels = (h, w, 4) uint8, not premultiplied; transform maps
+        image pixels to scene coordinates."""
+        px = np.ascontiguousarray(pixels, dtype=np.uint8)
+        h, w = px.shape[:2]
+        flags = (L.PF_PATTERN_FLAG_REPEAT_X if repeat_x else 0) | (L.PF_PATTERN_FLAG_REPEAT_Y if repeat_y else 0) | \
+                (0 if smoothing else L.PF_PATTERN_FLAG_NO_SMOOTHING)
+        t, f = self._transform_c(transform), self._pattern_filter_c(pattern_filter)
+        pid = int(L.lib().PFScenePushPaintImagePattern(self._h, px.ctypes.data, w, h, C.byref(t) if t is not None else None,
+                                                       flags, C.byref(f) if f is not None else None))
+        if pid == 0xFFFF:
+            raise L.PathfinderCudaError(L.PF_CUDA_ERROR_INVALID_ARGUMENT, L.lib().PFCudaGetLastError().decode())
+        return pid
+
+    def push_gradient(self, stops, line, radii=None, transform=None, repeat=False) -> int:
+        """Paint::from_gradient: stops = [(offset, (r, g, b, a) bytes)], sorted; line = ((x0, y0), (x1, y1));
+        radii = (r0, r1) makes it radial, in the space `transform` maps to scene coordinates."""
+        g = L.PFGradient()
+        g.kind = L.PF_GRADIENT_LINEAR if radii is None else L.PF_GRADIENT_RADIAL
+        g.wrap = L.PF_GRADIENT_WRAP_REPEAT if repeat else L.PF_GRADIENT_WRAP_CLAMP
+        g.from_ = L.PFVector2F(float(line[0][0]), float(line[0][1]))
+        g.to = L.PFVector2F(float(line[1][0]), float(line[1][1]))
+        if radii is not None:
+            g.radii[0], g.radii[1] = float(radii[0]), float(radii[1])
+        t = self._transform_c(transform if transform is not None else (1, 0, 0, 1, 0, 0))
+        g.transform = t
+        arr = (L.PFColorStop * len(stops))()
+        for i, (offset, rgba) in enumerate(stops):
+            arr[i].offset = float(offset)
+            arr[i].color = L.PFColorU(int(rgba[0]), int(rgba[1]), int(rgba[2]), int(rgba[3]))
+        g.stops = arr
+        g.stop_count = len(stops)
+        pid = int(L.lib().PFScenePushPaintGradient(self._h, C.byref(g)))
         if pid == 0xFFFF:
             raise L.PathfinderCudaError(L.PF_CUDA_ERROR_INVALID_ARGUMENT, L.lib().PFCudaGetLastError().decode())
         return pid

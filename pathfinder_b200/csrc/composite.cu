@@ -380,24 +380,45 @@ __device__ __forceinline__ void rule_of(float (&cov)[8], uint32_t ctrl) {
 }
 
 
-// ---- colour textures (pattern paints): the text filter of shaders/tile_fragment.inc.glsl:91-166 and the plain
-// pattern (filterNone, :361-363), evaluated per pixel. `x`, `y` are texel coordinates (texel centres at
-// integers, rows top-down); LINEAR filtering with CLAMP_TO_EDGE, the sampler state of a pattern without the
-// repeat flags.
+// ---- paints evaluated per pixel (GENERAL variant): colour textures with their filters
+// (shaders/tile_fragment.inc.glsl:91-359: text, radial gradient, blur, colour matrix, none), SrcIn combine, and the
+// blend modes (composite(), :414-535, + the blend states of renderer/src/gpu/blend.rs:43-163).
+// `x`, `y` are texel coordinates (texel centres at integers, rows top-down). Sampler state = the batch's
+// TextureSamplingFlags (gpu/src/lib.rs:521-528): LINEAR + CLAMP_TO_EDGE unless REPEAT_U / REPEAT_V / NEAREST_* say otherwise.
+constexpr uint32_t SAMPLE_REPEAT_U = 0x1, SAMPLE_REPEAT_V = 0x2, SAMPLE_NEAREST_MIN = 0x4, SAMPLE_NEAREST_MAG = 0x8;
+
+__device__ __forceinline__ int wrap_texel(int i, int n, bool repeat) {
+    if (repeat) {
+        i %= n;
+        return i < 0 ? i + n : i;
+    }
+    return min(max(i, 0), n - 1);
+}
+
 __device__ __forceinline__ float4 sample_texture(const ColorTexture &t, float x, float y) {
-    const float fx = floorf(x), fy = floorf(y);
-    const float ax = x - fx, ay = y - fy;
-    const int x0 = min(max((int)fx, 0), t.width - 1), x1 = min(max((int)fx + 1, 0), t.width - 1);
-    const int y0 = min(max((int)fy, 0), t.height - 1), y1 = min(max((int)fy + 1, 0), t.height - 1);
+    const bool rep_u = (t.sampling_flags & SAMPLE_REPEAT_U) != 0, rep_v = (t.sampling_flags & SAMPLE_REPEAT_V) != 0;
     auto texel = [&](int xx, int yy) {
         return unpack_rgba8(__ldg(reinterpret_cast<const uint32_t *>(t.pixels + (size_t)yy * t.pitch + (size_t)xx * 4)));
     };
+    if (t.sampling_flags & (SAMPLE_NEAREST_MIN | SAMPLE_NEAREST_MAG)) // (the paint sets both or neither, paint.rs:560-563)
+        return texel(wrap_texel((int)floorf(x + 0.5f), t.width, rep_u), wrap_texel((int)floorf(y + 0.5f), t.height, rep_v));
+    const float fx = floorf(x), fy = floorf(y);
+    const float ax = x - fx, ay = y - fy;
+    const int x0 = wrap_texel((int)fx, t.width, rep_u), x1 = wrap_texel((int)fx + 1, t.width, rep_u);
+    const int y0 = wrap_texel((int)fy, t.height, rep_v), y1 = wrap_texel((int)fy + 1, t.height, rep_v);
     const float4 c00 = texel(x0, y0);
     if (ax == 0.0f && ay == 0.0f) return c00; // a texel centre: the usual case (render targets sampled pixel for pixel)
     const float4 c10 = texel(x1, y0), c01 = texel(x0, y1), c11 = texel(x1, y1);
     auto mix = [](float p, float q, float w) { return p + (q - p) * w; };
     return make_float4(mix(mix(c00.x, c10.x, ax), mix(c01.x, c11.x, ax), ay), mix(mix(c00.y, c10.y, ax), mix(c01.y, c11.y, ax), ay),
                        mix(mix(c00.z, c10.z, ax), mix(c01.z, c11.z, ax), ay), mix(mix(c00.w, c10.w, ax), mix(c01.w, c11.w, ax), ay));
+}
+
+// texture(colorTexture, uv): normalised coordinates -> texels (render targets are addressed bottom-up).
+__device__ __forceinline__ float4 sample_uv(const ColorTexture &t, float u, float v) {
+    const float x = u * (float)t.width - 0.5f;
+    const float y = t.bottom_up ? ((float)t.height - 0.5f - v * (float)t.height) : (v * (float)t.height - 0.5f);
+    return sample_texture(t, x, y);
 }
 
 // texture(gammaLUT, vec2(alpha, 1 - bg)).r: 256 x 8 L8, LINEAR, CLAMP_TO_EDGE (filterTextGammaCorrectChannel, :122-124).
@@ -413,46 +434,187 @@ __device__ __forceinline__ float sample_gamma(const uint8_t *__restrict__ lut, f
     return top * (1.0f - ay) + bottom * ay;
 }
 
-// filterColor + combineColor0 (SrcIn) for the pixel whose centre is (fx, fy): returns the colour, NOT premultiplied,
-// alpha = texture alpha * base alpha (tile_fragment.inc.glsl:81-89,365-412).
-__device__ __forceinline__ float4 textured_color(const PaintTexture &p, const ColorTexture &t, const uint8_t *gamma_lut,
-                                                 float fx, float fy) {
-    const float u = p.m00 * fx + p.m01 * fy + p.tx, v = p.m10 * fx + p.m11 * fy + p.ty; // computeTileVaryings
+// filterText (tile_fragment.inc.glsl:91-166): nine taps one texel apart (onePixel = 1 / colorTextureSize.x), red
+// channel only. p0 = kernel, p1 = bg, p2 = fg (w: gamma correction).
+__device__ __forceinline__ float4 filter_text(const PaintTexture &p, const ColorTexture &t, const uint8_t *gamma_lut, float u, float v) {
     const float x = u * (float)t.width - 0.5f;
     const float y = t.bottom_up ? ((float)t.height - 0.5f - v * (float)t.height) : (v * (float)t.height - 0.5f);
-    if (p.filter_kind != PF_FILTER_TEXT_KIND) {
-        const float4 c = sample_texture(t, x, y);
-        return make_float4(c.x, c.y, c.z, c.w * p.base.w);
-    }
-    // filterText: nine taps one texel apart (onePixel = 1 / colorTextureSize.x), red channel only.
     float3 alpha;
-    if (p.kernel.w == 0.0f) {
+    if (p.p0.w == 0.0f) {
         const float r = sample_texture(t, x, y).x;
         alpha = make_float3(r, r, r);
     } else {
-        const bool wide = p.kernel.x > 0.0f;
+        const bool wide = p.p0.x > 0.0f;
         float tap[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) tap[k] = ((k == 0 || k == 8) && !wide) ? 0.0f : sample_texture(t, x + (float)(k - 4), y).x;
         // filterTextConvolve7Tap(alpha0, alpha1, kernel) = dot(alpha0, kernel) + dot(alpha1, kernel.zyx)
         auto convolve = [&](int first) {
-            return (((tap[first] * p.kernel.x + tap[first + 1] * p.kernel.y) + tap[first + 2] * p.kernel.z) + tap[first + 3] * p.kernel.w) +
-                   ((tap[first + 4] * p.kernel.z + tap[first + 5] * p.kernel.y) + tap[first + 6] * p.kernel.x);
+            return (((tap[first] * p.p0.x + tap[first + 1] * p.p0.y) + tap[first + 2] * p.p0.z) + tap[first + 3] * p.p0.w) +
+                   ((tap[first + 4] * p.p0.z + tap[first + 5] * p.p0.y) + tap[first + 6] * p.p0.x);
         };
         alpha = make_float3(convolve(0), convolve(1), convolve(2));
     }
-    if (p.gamma_correction && gamma_lut) {
-        alpha.x = sample_gamma(gamma_lut, alpha.x, 1.0f - p.bg.x);
-        alpha.y = sample_gamma(gamma_lut, alpha.y, 1.0f - p.bg.y);
-        alpha.z = sample_gamma(gamma_lut, alpha.z, 1.0f - p.bg.z);
+    if (p.p2.w != 0.0f && gamma_lut) {
+        alpha.x = sample_gamma(gamma_lut, alpha.x, 1.0f - p.p1.x);
+        alpha.y = sample_gamma(gamma_lut, alpha.y, 1.0f - p.p1.y);
+        alpha.z = sample_gamma(gamma_lut, alpha.z, 1.0f - p.p1.z);
     }
-    // vec4(mix(bgColor, fgColor, alpha), 1.0), then SrcIn with the base colour
-    return make_float4(p.bg.x + (p.fg.x - p.bg.x) * alpha.x, p.bg.y + (p.fg.y - p.bg.y) * alpha.y,
-                       p.bg.z + (p.fg.z - p.bg.z) * alpha.z, p.base.w);
+    // vec4(mix(bgColor, fgColor, alpha), 1.0)
+    return make_float4(p.p1.x + (p.p2.x - p.p1.x) * alpha.x, p.p1.y + (p.p2.y - p.p1.y) * alpha.y,
+                       p.p1.z + (p.p2.z - p.p1.z) * alpha.z, 1.0f);
+}
+
+// filterRadialGradient (tile_fragment.inc.glsl:274-300): p0 = line from, line vector; p1 = radii, uv origin.
+__device__ __forceinline__ float4 filter_radial_gradient(const PaintTexture &p, const ColorTexture &t, float u, float v) {
+    const float dpx = u - p.p0.x, dpy = v - p.p0.y, dcx = p.p0.z, dcy = p.p0.w;
+    const float dr = p.p1.y - p.p1.x;
+    const float a = (dcx * dcx + dcy * dcy) - dr * dr;
+    const float b = (dpx * dcx + dpy * dcy) + p.p1.x * dr;
+    const float c = (dpx * dpx + dpy * dpy) - p.p1.x * p.p1.x;
+    const float discrim = b * b - a * c;
+    if (discrim == 0.0f) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const float root = sqrtf(discrim);
+    float t0 = (root + b) / a, t1 = (-root + b) / a;
+    if (t0 > t1) {
+        const float swap = t0;
+        t0 = t1, t1 = swap;
+    }
+    const float tt = t0 >= 0.0f ? t0 : t1;
+    return sample_uv(t, p.p1.z + tt, p.p1.w);
+}
+
+// filterBlur (tile_fragment.inc.glsl:302-339): p0 = direction, support; p1 = Gaussian coefficients.
+__device__ __forceinline__ float4 filter_blur(const PaintTexture &p, const ColorTexture &t, float u, float v) {
+    const float ox = p.p0.x / (float)t.width, oy = p.p0.y / (float)t.height;
+    const int support = (int)p.p0.z;
+    float gx = p.p1.x, gy = p.p1.y;
+    const float gz = p.p1.z;
+    float sum = gx;
+    float4 color = sample_uv(t, u, v);
+    color = make_float4(color.x * gx, color.y * gx, color.z * gx, color.w * gx);
+    gx *= gy, gy *= gz;
+    for (int i = 1; i <= support; i += 2) {
+        float partial = gx;
+        gx *= gy, gy *= gz;
+        partial += gx;
+        const float off = (float)i + gx / partial;
+        const float4 lo = sample_uv(t, u - ox * off, v - oy * off), hi = sample_uv(t, u + ox * off, v + oy * off);
+        color = make_float4(color.x + (lo.x + hi.x) * partial, color.y + (lo.y + hi.y) * partial,
+                            color.z + (lo.z + hi.z) * partial, color.w + (lo.w + hi.w) * partial);
+        sum += 2.0f * partial;
+        gx *= gy, gy *= gz;
+    }
+    return make_float4(color.x / sum, color.y / sum, color.z / sum, color.w / sum);
+}
+
+// filterColor + combineColor0 (SrcIn) for the pixel whose centre is (fx, fy): the paint's colour, NOT premultiplied
+// (tile_fragment.inc.glsl:81-89,361-412,583-603). A paint without a colour texture is its base colour.
+__device__ __forceinline__ float4 paint_color(const PaintTexture &p, const ColorTexture &t, const uint8_t *gamma_lut,
+                                              float fx, float fy) {
+    if (!(p.flags & PAINT_HAS_TEXTURE) || t.pixels == nullptr) return p.base;
+    const float u = p.m00 * fx + p.m01 * fy + p.tx, v = p.m10 * fx + p.m11 * fy + p.ty; // computeTileVaryings
+    float4 c;
+    switch (p.filter_kind) {
+    case 1: c = filter_radial_gradient(p, t, u, v); break;                 // PF_FILTER_RADIAL_GRADIENT
+    case PF_FILTER_TEXT_KIND: c = filter_text(p, t, gamma_lut, u, v); break;
+    case 3: c = filter_blur(p, t, u, v); break;                            // PF_FILTER_BLUR
+    case 4: {                                                              // PF_FILTER_COLOR_MATRIX: matrix * colour + p4
+        const float4 q = sample_uv(t, u, v);
+        c = make_float4(p.p0.x * q.x + p.p1.x * q.y + p.p2.x * q.z + p.p3.x * q.w + p.p4.x,
+                        p.p0.y * q.x + p.p1.y * q.y + p.p2.y * q.z + p.p3.y * q.w + p.p4.y,
+                        p.p0.z * q.x + p.p1.z * q.y + p.p2.z * q.z + p.p3.z * q.w + p.p4.z,
+                        p.p0.w * q.x + p.p1.w * q.y + p.p2.w * q.z + p.p3.w * q.w + p.p4.w);
+        break;
+    }
+    default: c = sample_uv(t, u, v); break;                                // filterNone
+    }
+    return make_float4(c.x, c.y, c.z, c.w * p.base.w); // combineColor0, SrcIn: (src.rgb, src.a * dest.a)
+}
+
+// ---- blend modes. Values of PF_BLEND_MODE_* (include/pf_cuda.h).
+__device__ __forceinline__ float composite_divide(float num, float denom) { return denom != 0.0f ? num / denom : 0.0f; }
+__device__ __forceinline__ float color_dodge1(float d, float s) { return d == 0.0f ? 0.0f : (s == 1.0f ? 1.0f : d / (1.0f - s)); }
+__device__ __forceinline__ float screen1(float d, float s) { return d + s - d * s; }
+__device__ __forceinline__ float hard_light1(float d, float s) { return s <= 0.5f ? d * 2.0f * s : screen1(d, 2.0f * s - 1.0f); }
+__device__ __forceinline__ float soft_light1(float d, float s) {
+    const float darkened = d <= 0.25f ? ((16.0f * d - 12.0f) * d + 4.0f) * d : sqrtf(d);
+    const float factor = s <= 0.5f ? d * (1.0f - d) : darkened - d;
+    return d + (s * 2.0f - 1.0f) * factor;
+}
+__device__ __forceinline__ float3 rgb_to_hsl(float3 c) { // compositeRGBToHSL (:443-453)
+    const float v = fmaxf(fmaxf(c.x, c.y), c.z), x_min = fminf(fminf(c.x, c.y), c.z);
+    const float ch = v - x_min, l = x_min + (v - x_min) * 0.5f;
+    float3 terms = c.x == v ? make_float3(0.0f, c.y, c.z) : (c.y == v ? make_float3(2.0f, c.z, c.x) : make_float3(4.0f, c.x, c.y));
+    const float h = 1.0471975511965976f * composite_divide(terms.x * ch + terms.y - terms.z, ch); // FRAC_PI_3
+    return make_float3(h, composite_divide(ch, v), l);
+}
+__device__ __forceinline__ float3 hsl_to_rgb(float3 hsl) { // compositeHSLToRGB (:436-440)
+    const float a = hsl.y * fminf(hsl.z, 1.0f - hsl.z);
+    const float hk = hsl.x * 1.9098593171027440f; // FRAC_6_PI
+    auto channel = [&](float n) {
+        float k = n + hk;
+        k = k - 12.0f * floorf(k / 12.0f); // mod(k, 12)
+        return hsl.z - fminf(fmaxf(fminf(k - 3.0f, 9.0f - k), -1.0f), 1.0f) * a;
+    };
+    return make_float3(channel(0.0f), channel(8.0f), channel(4.0f));
+}
+// compositeRGB (:488-523), for the blend modes the shader evaluates itself.
+__device__ __forceinline__ float3 composite_rgb(float3 d, float3 s, uint32_t mode) {
+    switch (mode) {
+    case 14: return make_float3(d.x * s.x, d.y * s.y, d.z * s.z);                                        // Multiply
+    case 15: return make_float3(screen1(d.x, s.x), screen1(d.y, s.y), screen1(d.z, s.z));                // Screen
+    case 17: return make_float3(hard_light1(s.x, d.x), hard_light1(s.y, d.y), hard_light1(s.z, d.z));    // Overlay
+    case 12: return make_float3(fminf(d.x, s.x), fminf(d.y, s.y), fminf(d.z, s.z));                      // Darken
+    case 13: return make_float3(fmaxf(d.x, s.x), fmaxf(d.y, s.y), fmaxf(d.z, s.z));                      // Lighten
+    case 18: return make_float3(color_dodge1(d.x, s.x), color_dodge1(d.y, s.y), color_dodge1(d.z, s.z)); // ColorDodge
+    case 19:                                                                                              // ColorBurn
+        return make_float3(1.0f - color_dodge1(1.0f - d.x, 1.0f - s.x), 1.0f - color_dodge1(1.0f - d.y, 1.0f - s.y),
+                           1.0f - color_dodge1(1.0f - d.z, 1.0f - s.z));
+    case 16: return make_float3(hard_light1(d.x, s.x), hard_light1(d.y, s.y), hard_light1(d.z, s.z));    // HardLight
+    case 20: return make_float3(soft_light1(d.x, s.x), soft_light1(d.y, s.y), soft_light1(d.z, s.z));    // SoftLight
+    case 21: return make_float3(fabsf(d.x - s.x), fabsf(d.y - s.y), fabsf(d.z - s.z));                   // Difference
+    case 22: return make_float3(d.x + s.x - 2.0f * d.x * s.x, d.y + s.y - 2.0f * d.y * s.y, d.z + s.z - 2.0f * d.z * s.z); // Exclusion
+    case 23: case 24: case 25: case 26: {                                                                // Hue, Saturation, Color, Luminosity
+        const float3 dh = rgb_to_hsl(d), sh = rgb_to_hsl(s);
+        const float3 pick = mode == 23 ? make_float3(sh.x, dh.y, dh.z)
+                          : mode == 24 ? make_float3(dh.x, sh.y, dh.z)
+                          : mode == 25 ? make_float3(sh.x, sh.y, dh.z)
+                                       : make_float3(dh.x, dh.y, sh.z);
+        return hsl_to_rgb(pick);
+    }
+    default: return s;
+    }
+}
+
+// One pixel of one path: dest (premultiplied) under the paint's colour c (not premultiplied) with mask alpha m.
+// SrcOver: dest * (1 - a) + (rgb * a, a). The other Porter-Duff modes: the blend factors of gpu/blend.rs:43-143 on the
+// premultiplied source. The modes the shader evaluates itself (Darken .. Luminosity): composite() reads the
+// destination, mixes, forces alpha to 1 and the result replaces the pixel (blending disabled, blend.rs:144-163).
+__device__ __forceinline__ float4 blend_pixel(float4 d, float4 c, float m, uint32_t mode) {
+    const float sa = c.w * m;
+    if (mode >= 12u) { // PF_BLEND_MODE_DARKEN ..
+        const float3 b = composite_rgb(make_float3(d.x, d.y, d.z), make_float3(c.x, c.y, c.z), mode);
+        const float k0 = sa * (1.0f - d.w), k1 = sa * d.w, k2 = 1.0f - sa;
+        return make_float4(k0 * c.x + k1 * b.x + k2 * d.x, k0 * c.y + k1 * b.y + k2 * d.y, k0 * c.z + k1 * b.z + k2 * d.z, 1.0f);
+    }
+    float sf, df; // source / destination factors (the same for colour and alpha in every mode)
+    switch (mode) {
+    case 8: sf = 1.0f - d.w, df = 1.0f; break;        // DestOver
+    case 7: sf = 0.0f, df = 1.0f - sa; break;         // DestOut
+    case 5: sf = d.w, df = 1.0f - sa; break;          // SrcAtop
+    case 10: sf = 1.0f - d.w, df = 1.0f - sa; break;  // Xor
+    case 11: sf = 1.0f, df = 1.0f; break;             // Lighter
+    default: sf = 1.0f, df = 1.0f - sa; break;        // SrcOver
+    }
+    const float k = sa * sf;
+    float4 out = make_float4(fmaf(d.x, df, c.x * k), fmaf(d.y, df, c.y * k), fmaf(d.z, df, c.z * k), fmaf(d.w, df, k));
+    if (mode == 11u) out = make_float4(fminf(out.x, 1.0f), fminf(out.y, 1.0f), fminf(out.z, 1.0f), fminf(out.w, 1.0f)); // UNORM target
+    return out;
 }
 
 template <bool LOAD_DEST, bool GENERAL>
-__global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? PF_TILE_MIN_BLOCKS - 1 : PF_TILE_MIN_BLOCKS) k_tile_alpha(CompositeArgs a) {
+__global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? 4 : PF_TILE_MIN_BLOCKS) k_tile_alpha(CompositeArgs a) {
     __shared__ TileWarpShared<GENERAL> sh_all[TILE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TileWarpShared<GENERAL> &sh = sh_all[warp];
@@ -626,11 +788,9 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? PF_TILE_MIN_BLOCKS 
                         const float4 v = sh.dst[k * 32 + lane];
                         d = make_float4(fmaf(v.x, s, o4.x), fmaf(v.y, s, o4.y), fmaf(v.z, s, o4.z), fmaf(v.w, s, o4.w));
                     }
-                    const float4 c = textured_color(pt, a.color_texture, a.gamma_lut, (float)px + 0.5f, (float)(py0 + k) + 0.5f);
-                    // color.a *= maskAlpha; color.rgb *= color.a; dest = dest * (1 - color.a) + color
-                    const float alpha = c.w * cov[k], keep = 1.0f - alpha;
-                    d = make_float4(fmaf(d.x, keep, c.x * alpha), fmaf(d.y, keep, c.y * alpha), fmaf(d.z, keep, c.z * alpha),
-                                    fmaf(d.w, keep, alpha));
+                    const float4 c = paint_color(pt, a.color_texture, a.gamma_lut, (float)px + 0.5f, (float)(py0 + k) + 0.5f);
+                    // color.a *= maskAlpha; composite; color.rgb *= color.a; blend (tile_fragment.inc.glsl:583-614)
+                    d = blend_pixel(d, c, cov[k], pt.blend_mode);
                     sh.dst[k * 32 + lane] = d;
                 }
                 expanded = true;

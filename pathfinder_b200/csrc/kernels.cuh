@@ -135,16 +135,20 @@ constexpr uint32_t TILE_CLIP_REPLACE = 0x80000000u;
 // TileEntry.paint_ctrl flag bits (the low 24 bits are colour | ctrl).
 constexpr uint32_t ENTRY_HAS_CLIP = 1u << 24, ENTRY_CLIP_REPLACE = 1u << 25, ENTRY_TEXTURED = 1u << 26;
 
-// A paint that samples a colour texture (TextureMetadataEntry with a colour combine mode, gpu_data.rs:336-344;
-// the ten RGBA16F texels of gpu/renderer.rs:712-763 as one device record). Only the text filter
-// (PatternFilter::Text, shaders/tile_fragment.inc.glsl:91-166) and the unfiltered pattern are evaluated.
+// A paint that needs per-pixel evaluation: it samples a colour texture (TextureMetadataEntry with a colour combine
+// mode, gpu_data.rs:336-344) and / or blends with something other than SrcOver. The ten RGBA16F texels of
+// gpu/renderer.rs:712-763 as one device record: p0..p4 are filterParams0..4 exactly as compute_filter_params packs
+// them (gpu/renderer.rs:967-1049) — text: kernel, bg, fg (w = gamma correction); radial gradient: line from + vector,
+// radii + uv origin; blur: direction + support, Gaussian coefficients; colour matrix: its five columns.
+constexpr uint32_t PAINT_HAS_TEXTURE = 1u;
 struct __align__(16) PaintTexture {
     float m00, m01, m10, m11, tx, ty; // framebuffer position (pixel centre) -> normalised texture coordinate
-    uint32_t filter_kind;             // PF_FILTER_NONE / PF_FILTER_TEXT
-    uint32_t gamma_correction;
-    float4 kernel;                    // defringing kernel (w = 0: no defringing)
-    float4 bg, fg;                    // text filter colours (rgb)
+    uint32_t filter_kind;             // PF_FILTER_*
+    uint32_t flags;                   // PAINT_HAS_TEXTURE
+    float4 p0, p1, p2, p3, p4;
     float4 base;                      // base colour, rounded through f16, not premultiplied
+    uint32_t blend_mode;              // PF_BLEND_MODE_*
+    uint32_t pad[3];
 };
 
 // The colour texture of a draw batch (DrawTileBatchD3D11.color_texture): one RGBA8 page in device memory.
@@ -153,6 +157,7 @@ struct ColorTexture {
     size_t pitch;
     int32_t width, height;
     int32_t bottom_up;     // the page is a render target: v = 1 addresses its top row (see pf_cuda.h)
+    uint32_t sampling_flags; // PF_TEXTURE_SAMPLING_FLAGS_* (TileBatchTexture.sampling_flags)
 };
 
 // clip / tile_clip: NULL unless the batch has clipped paths.

@@ -74,7 +74,7 @@ struct BatchCache {
     BatchDev batch{};
     bool has_initial_backdrops = false;
     bool has_clips = false; // the batch has clipped paths (resolved against r->clip)
-    ColorTexture color_texture{nullptr, 0, 0, 0, 0}; // DrawTileBatchD3D11.color_texture, resolved to its page
+    ColorTexture color_texture{nullptr, 0, 0, 0, 0, 0}; // DrawTileBatchD3D11.color_texture, resolved to its page
     bool counts_valid = false; // n_lines / n_fills / n_entries hold the last frame's totals
     uint32_t n_lines = 0, n_fills = 0, n_entries = 0, n_visible_fills = 0;
     uint32_t command_paths = 0, command_segments = 0; // as sent (before strip culling)
@@ -489,6 +489,13 @@ void upload_segments(PFCudaRenderer *r, SceneSegments &dst, const PFSegmentsD3D1
     r->stats.h2d_bytes += src.point_count * sizeof(float2) + src.index_count * sizeof(uint2);
 }
 
+// BlendMode::is_destructive (content/src/effects.rs:222-235): the path changes pixels outside its own coverage, so
+// the reference tiles it over the whole view box (builder.rs:430-434). Not built.
+bool blend_mode_is_destructive(uint32_t mode) {
+    return mode == PF_BLEND_MODE_CLEAR || mode == PF_BLEND_MODE_COPY || mode == PF_BLEND_MODE_SRC_IN ||
+           mode == PF_BLEND_MODE_DEST_IN || mode == PF_BLEND_MODE_SRC_OUT || mode == PF_BLEND_MODE_DEST_ATOP;
+}
+
 void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *entries, size_t n) {
     std::vector<float4> table(n);
     std::vector<PaintTexture> textures(n);
@@ -498,11 +505,15 @@ void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *en
     for (size_t i = 0; i < n; i++) {
         const PFTextureMetadataEntry &e = entries[i];
         const bool textured = e.color_0_combine_mode == PF_COLOR_COMBINE_MODE_SRC_IN;
-        if ((e.color_0_combine_mode != PF_COLOR_COMBINE_MODE_NONE && !textured) || e.blend_mode != PF_BLEND_MODE_SRC_OVER ||
-            (e.filter.kind != PF_FILTER_NONE && !(textured && e.filter.kind == PF_FILTER_TEXT)))
+        if (e.color_0_combine_mode != PF_COLOR_COMBINE_MODE_NONE && !textured)
+            throw Error(PF_CUDA_ERROR_UNSUPPORTED, "ColorCombineMode::DestIn is not implemented");
+        if (e.blend_mode > PF_BLEND_MODE_LUMINOSITY) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "unknown blend mode");
+        if (blend_mode_is_destructive(e.blend_mode))
             throw Error(PF_CUDA_ERROR_UNSUPPORTED,
-                        "paints on the hot path: solid colours, and patterns (SrcIn) unfiltered or with the text filter; "
-                        "SrcOver only (SURVEY.md §8 f3 / f4)");
+                        "destructive blend modes (Clear, Copy, SrcIn, DestIn, SrcOut, DestAtop) are not implemented");
+        if (e.filter.kind > PF_FILTER_COLOR_MATRIX) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "unknown filter kind");
+        if (e.filter.kind != PF_FILTER_NONE && !textured)
+            throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "a filter on a paint without a colour texture");
         // ColorU::to_f32 (color/src/lib.rs:70-73) then f16 (gpu/renderer.rs:726-729).
         const float s = 1.0f / 255.0f;
         float c[4] = {(float)e.base_color.r * s, (float)e.base_color.g * s, (float)e.base_color.b * s,
@@ -511,6 +522,8 @@ void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *en
         table[i] = make_float4(c[0], c[1], c[2], c[3]);
         PaintTexture &pt = textures[i];
         memset(&pt, 0, sizeof(pt));
+        pt.base = table[i];
+        pt.blend_mode = e.blend_mode;
         if (textured) {
             // gpu/renderer.rs:712-763: transform, filter parameters and colours all pass through f16.
             const PFTransform2F &t = e.color_0_transform;
@@ -518,19 +531,41 @@ void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *en
             pt.m10 = half_round(t.matrix.m10), pt.m11 = half_round(t.matrix.m11);
             pt.tx = half_round(t.vector.x), pt.ty = half_round(t.vector.y);
             pt.filter_kind = e.filter.kind;
-            pt.base = table[i];
+            pt.flags = PAINT_HAS_TEXTURE;
+            const float *fp = e.filter.params;
+            auto h4 = [&](float x, float y, float z, float w) { return make_float4(half_round(x), half_round(y), half_round(z), half_round(w)); };
+            // compute_filter_params (gpu/renderer.rs:967-1049)
             if (e.filter.kind == PF_FILTER_TEXT) {
-                // compute_filter_params (gpu/renderer.rs:777-800): p0 = kernel (or zero), p1 = bg, p2 = fg + gamma flag
-                const float *fp = e.filter.params;
-                pt.fg = make_float4(half_round(fp[0]), half_round(fp[1]), half_round(fp[2]), 0.0f);
-                pt.bg = make_float4(half_round(fp[4]), half_round(fp[5]), half_round(fp[6]), 0.0f);
-                if (e.filter.flags & PF_FILTER_FLAG_TEXT_HAS_KERNEL)
-                    pt.kernel = make_float4(half_round(fp[8]), half_round(fp[9]), half_round(fp[10]), half_round(fp[11]));
-                pt.gamma_correction = (e.filter.flags & PF_FILTER_FLAG_TEXT_GAMMA_CORRECTION) ? 1u : 0u;
-                if (pt.gamma_correction && !r->has_gamma_lut)
+                // p0 = kernel (or zero), p1 = bg, p2 = fg + gamma flag
+                const bool gamma = (e.filter.flags & PF_FILTER_FLAG_TEXT_GAMMA_CORRECTION) != 0;
+                if (e.filter.flags & PF_FILTER_FLAG_TEXT_HAS_KERNEL) pt.p0 = h4(fp[8], fp[9], fp[10], fp[11]);
+                pt.p1 = h4(fp[4], fp[5], fp[6], 0.0f);
+                pt.p2 = h4(fp[0], fp[1], fp[2], gamma ? 1.0f : 0.0f);
+                if (gamma && !r->has_gamma_lut)
                     throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "a text filter asks for gamma correction but the renderer was created without the gamma LUT");
+            } else if (e.filter.kind == PF_FILTER_RADIAL_GRADIENT) {
+                // params = line.from, line.to, radii, uv_origin -> p0 = from, vector; p1 = radii, uv origin
+                pt.p0 = h4(fp[0], fp[1], fp[2] - fp[0], fp[3] - fp[1]);
+                pt.p1 = h4(fp[4], fp[5], fp[6], fp[7]);
+            } else if (e.filter.kind == PF_FILTER_BLUR) {
+                const float sigma = fp[0];
+                if (!(sigma > 0.0f) || sigma > 1024.0f) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "blur sigma out of range");
+                const float sigma_inv = 1.0f / sigma;
+                const float gx = 0.3989422804014327f * sigma_inv; // SQRT_2_PI_INV
+                const float gy = expf(-0.5f * sigma_inv * sigma_inv);
+                const bool vertical = (e.filter.flags & PF_FILTER_FLAG_BLUR_Y) != 0;
+                pt.p0 = h4(vertical ? 0.0f : 1.0f, vertical ? 1.0f : 0.0f, ceilf(1.5f * sigma) * 2.0f, 0.0f);
+                pt.p1 = h4(gx, gy, gy * gy, 0.0f);
+            } else if (e.filter.kind == PF_FILTER_COLOR_MATRIX) {
+                pt.p0 = h4(fp[0], fp[1], fp[2], fp[3]);
+                pt.p1 = h4(fp[4], fp[5], fp[6], fp[7]);
+                pt.p2 = h4(fp[8], fp[9], fp[10], fp[11]);
+                pt.p3 = h4(fp[12], fp[13], fp[14], fp[15]);
+                pt.p4 = h4(fp[16], fp[17], fp[18], fp[19]);
             }
-            r->paint_is_textured[i] = 1;
+        }
+        if (textured || e.blend_mode != PF_BLEND_MODE_SRC_OVER) {
+            r->paint_is_textured[i] = 1; // evaluated per pixel by the GENERAL variant of k_tile_alpha
             r->any_textured_paint = true;
         }
     }
@@ -1021,7 +1056,7 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
     // A render target starts from transparent black (Renderer::clear_color_for_draw_operation, gpu/renderer.rs).
     ca.clear_color = target.is_main ? clear_color(r) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     ca.load_dest = *target.batches_drawn > 0;
-    if (c.color_texture.pixels) { // the batch samples a colour texture
+    if (r->any_textured_paint) { // some paint samples the batch's colour texture or blends per pixel
         ca.paint_textures = r->paint_textures.ptr;
         ca.color_texture = c.color_texture;
         ca.gamma_lut = r->has_gamma_lut ? r->gamma_lut.ptr : nullptr;
@@ -1170,7 +1205,7 @@ void prepare_clip_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
     BatchCache &c = r->cache;
     c.valid = false; // the stage buffers and the batch slot are borrowed; the draw batch re-uploads
     c.has_clips = false;
-    c.color_texture = ColorTexture{nullptr, 0, 0, 0, 0};
+    c.color_texture = ColorTexture{nullptr, 0, 0, 0, 0, 0};
     upload_batch_metadata(r, batch, fb, strip_y0, strip_y1, c.batch, c.has_initial_backdrops, r->clip_segments, true);
     c.strip_y0 = strip_y0;
     c.strip_y1 = strip_y1;
@@ -1180,18 +1215,16 @@ void prepare_clip_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch) {
 // DrawTileBatchD3D11.color_texture -> the page it names (Renderer::draw_tiles binds it as uColorTexture0,
 // renderer/src/gpu/d3d11/renderer.rs:733-741).
 ColorTexture resolve_color_texture(PFCudaRenderer *r, bool has_color_texture, const PFTileBatchTexture &texture) {
-    if (!has_color_texture) return ColorTexture{nullptr, 0, 0, 0, 0};
+    if (!has_color_texture) return ColorTexture{nullptr, 0, 0, 0, 0, 0};
     if (texture.page >= r->pages.size() || !r->pages[texture.page])
         throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "draw batch names a texture page that was never allocated");
-    if (texture.sampling_flags & (PF_TEXTURE_SAMPLING_FLAGS_REPEAT_U | PF_TEXTURE_SAMPLING_FLAGS_REPEAT_V |
-                                  PF_TEXTURE_SAMPLING_FLAGS_NEAREST_MIN | PF_TEXTURE_SAMPLING_FLAGS_NEAREST_MAG))
-        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "colour textures are sampled LINEAR + CLAMP_TO_EDGE only (repeat / nearest: f4)");
     if (texture.composite_op != PF_PAINT_COMPOSITE_OP_SRC_IN)
         throw Error(PF_CUDA_ERROR_UNSUPPORTED, "only PaintCompositeOp::SrcIn is implemented");
     const PFCudaRenderer::TexturePage &page = *r->pages[texture.page];
     if (!r->target_stack.empty() && r->render_targets[r->target_stack.back()].page == texture.page)
         throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "draw batch samples the render target it draws to");
-    return ColorTexture{page.pixels.ptr, (size_t)page.width * 4, page.width, page.height, page.is_render_target ? 1 : 0};
+    return ColorTexture{page.pixels.ptr, (size_t)page.width * 4, page.width, page.height, page.is_render_target ? 1 : 0,
+                        (uint32_t)texture.sampling_flags};
 }
 
 void draw_tile_batch(PFCudaRenderer *r, const PFTileBatchDataD3D11 &batch, bool has_color_texture,

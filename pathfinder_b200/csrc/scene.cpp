@@ -129,11 +129,25 @@ struct DisplayItem {
 struct RenderTargetDesc { // scene.rs:493-497
     int32_t width, height;
 };
-// Paint::overlay for PaintContents::Pattern over a render target (paint.rs:108-146, pattern.rs:52-140).
+// Paint::overlay (paint.rs:108-146): a pattern over a render target or an image (pattern.rs:52-140), or a gradient
+// (content/src/gradient.rs).
 struct PatternOverlay {
-    uint32_t render_target;
-    Transform transform; // pattern space (render target pixels) -> scene space
+    enum Kind : uint8_t { RENDER_TARGET, IMAGE, GRADIENT } kind = RENDER_TARGET;
+    uint32_t render_target = 0;
+    Transform transform; // pattern space (render target / image pixels) -> scene space; radial gradients: Radial.transform
     PFFilter filter;
+    // IMAGE
+    std::vector<PFColorU> pixels;
+    int32_t width = 0, height = 0;
+    uint32_t pattern_flags = 0; // PF_PATTERN_FLAG_*
+    // GRADIENT
+    uint32_t gradient_kind = 0, gradient_wrap = 0;
+    float from[2] = {0, 0}, to[2] = {0, 0}, radii[2] = {0, 0};
+    std::vector<PFColorStop> stops;
+    // assigned by the build (Palette::assign_paint_locations, paint.rs:456-595)
+    uint32_t page = 0;
+    int32_t row = 0;          // gradients: the row of the 256 x 256 gradient tile
+    int32_t page_w = 0, page_h = 0;
 };
 // One DrawTilesD3D11 batch of a scene with a display list (the general builder below).
 struct GeneralBatch {
@@ -144,6 +158,37 @@ struct GeneralBatch {
     bool has_color_texture = false;
     PFTileBatchTexture color_texture{0, 0, 0};
 };
+
+// Gradient::sample (content/src/gradient.rs:188-211): the colour at t in [0, 1], stops sorted by offset.
+PFColorU gradient_sample(const std::vector<PFColorStop> &stops, float t) {
+    if (stops.empty()) return PFColorU{0, 0, 0, 0};
+    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+    const size_t last = stops.size() - 1;
+    // binary_search_by(|stop| if stop.offset < t || stop.offset == 0.0 { Less } else { Greater }): the first stop
+    // that is neither before t nor at offset zero
+    size_t lo = 0, hi = stops.size();
+    while (lo < hi) {
+        const size_t mid = lo + (hi - lo) / 2;
+        if (stops[mid].offset < t || stops[mid].offset == 0.0f) lo = mid + 1;
+        else hi = mid;
+    }
+    const size_t upper = lo < last ? lo : last;
+    const size_t lower = upper > 0 ? upper - 1 : upper;
+    const PFColorStop &a = stops[lower], &b = stops[upper];
+    const float denom = b.offset - a.offset;
+    if (denom == 0.0f) return a.color;
+    float ratio = (t - a.offset) / denom;
+    if (ratio > 1.0f) ratio = 1.0f;
+    // ColorU::to_f32().lerp(..).to_u8(): (x / 255 + (y / 255 - x / 255) * ratio) * 255 through F32x4::to_i32x4, i.e.
+    // cvtps: round to nearest even (color/src/lib.rs:70-73,163-171)
+    auto lerp8 = [&](uint8_t x, uint8_t y) {
+        const float fx = (float)x * (1.0f / 255.0f), fy = (float)y * (1.0f / 255.0f);
+        const float v = (fx + (fy - fx) * ratio) * 255.0f;
+        const float r = nearbyintf(v);
+        return (uint8_t)(r < 0.0f ? 0.0f : (r > 255.0f ? 255.0f : r));
+    };
+    return PFColorU{lerp8(a.color.r, b.color.r), lerp8(a.color.g, b.color.g), lerp8(a.color.b, b.color.b), lerp8(a.color.a, b.color.a)};
+}
 
 std::atomic<uint32_t> g_next_scene_id{0}; // NEXT_SCENE_ID, scene.rs:34
 
@@ -162,6 +207,9 @@ struct PFScene {
     std::unordered_map<uint16_t, PatternOverlay> overlays;
     std::vector<DisplayItem> display_list;
     std::vector<GeneralBatch> general_batches; // scratch of the general builder (kept alive while commands are sent)
+    bool any_blend = false;                    // some draw path blends with something other than SrcOver
+    std::unordered_map<uint32_t, uint16_t> blend_entries; // paint | blend mode << 16 -> texture metadata entry
+    std::vector<std::vector<PFColorU>> gradient_tiles; // scratch: texels of the gradient pages of this build
     RectF bounds{0, 0, 0, 0};
     RectF view_box{0, 0, 0, 0};
     uint32_t id;
@@ -505,6 +553,7 @@ uint32_t PFScenePushDrawPath(PFSceneRef s, const PFVector2F *points, const uint8
     p.paint = paint_id;
     p.fill_rule = fill_rule;
     p.blend_mode = blend_mode;
+    if (blend_mode != PF_BLEND_MODE_SRC_OVER) s->any_blend = true;
     p.clip_path = clip_path_id;
     s->bounds = union_rect(s->bounds, p.bounds); // scene.rs:84-86
     s->draw_paths.push_back(p);
@@ -609,11 +658,13 @@ uint16_t PFScenePushPaintRenderTargetPattern(PFSceneRef s, uint32_t render_targe
         pf::set_last_error("PFScenePushPaintRenderTargetPattern: unknown render target");
         return 0xffff;
     }
-    if (filter && filter->kind != PF_FILTER_NONE && filter->kind != PF_FILTER_TEXT) {
-        pf::set_last_error("PFScenePushPaintRenderTargetPattern: only PatternFilter::Text is implemented");
+    if (filter && filter->kind != PF_FILTER_NONE && filter->kind != PF_FILTER_TEXT && filter->kind != PF_FILTER_BLUR &&
+        filter->kind != PF_FILTER_COLOR_MATRIX) {
+        pf::set_last_error("PFScenePushPaintRenderTargetPattern: a pattern filter is Text, Blur or ColorMatrix (effects.rs:63-97)");
         return 0xffff;
     }
     PatternOverlay overlay;
+    overlay.kind = PatternOverlay::RENDER_TARGET;
     overlay.render_target = render_target_id;
     if (pattern_transform) {
         overlay.transform.m11 = pattern_transform->matrix.m00, overlay.transform.m12 = pattern_transform->matrix.m01;
@@ -625,6 +676,66 @@ uint16_t PFScenePushPaintRenderTargetPattern(PFSceneRef s, uint32_t render_targe
     const uint16_t id = (uint16_t)s->paints.size();
     s->paints.push_back(PFColorU{255, 255, 255, 255}); // Paint::from_pattern: base colour white (paint.rs:138-146)
     s->overlays.emplace(id, overlay);                    // (pattern paints are never deduplicated)
+    s->epoch++;
+    return id;
+}
+
+uint16_t PFScenePushPaintImagePattern(PFSceneRef s, const PFColorU *pixels, int32_t width, int32_t height,
+                                      const PFTransform2F *pattern_transform, uint32_t flags, const PFFilter *filter) {
+    if (!s || !pixels || width <= 0 || height <= 0 || (int64_t)width * height > (1ll << 26) || s->paints.size() >= 65535) {
+        pf::set_last_error("PFScenePushPaintImagePattern: bad image");
+        return 0xffff;
+    }
+    if (filter && filter->kind != PF_FILTER_NONE && filter->kind != PF_FILTER_TEXT && filter->kind != PF_FILTER_BLUR &&
+        filter->kind != PF_FILTER_COLOR_MATRIX) {
+        pf::set_last_error("PFScenePushPaintImagePattern: a pattern filter is Text, Blur or ColorMatrix (effects.rs:63-97)");
+        return 0xffff;
+    }
+    PatternOverlay overlay;
+    overlay.kind = PatternOverlay::IMAGE;
+    overlay.pixels.assign(pixels, pixels + (size_t)width * height);
+    overlay.width = width, overlay.height = height;
+    overlay.pattern_flags = flags;
+    if (pattern_transform) {
+        overlay.transform.m11 = pattern_transform->matrix.m00, overlay.transform.m12 = pattern_transform->matrix.m01;
+        overlay.transform.m21 = pattern_transform->matrix.m10, overlay.transform.m22 = pattern_transform->matrix.m11;
+        overlay.transform.tx = pattern_transform->vector.x, overlay.transform.ty = pattern_transform->vector.y;
+    }
+    memset(&overlay.filter, 0, sizeof(overlay.filter));
+    if (filter) overlay.filter = *filter;
+    const uint16_t id = (uint16_t)s->paints.size();
+    s->paints.push_back(PFColorU{255, 255, 255, 255}); // Paint::from_pattern: base colour white (paint.rs:138-146)
+    s->overlays.emplace(id, std::move(overlay));
+    s->epoch++;
+    return id;
+}
+
+uint16_t PFScenePushPaintGradient(PFSceneRef s, const PFGradient *g) {
+    if (!s || !g || (g->stop_count && !g->stops) || g->stop_count > 4096 || s->paints.size() >= 65535 ||
+        (g->kind != PF_GRADIENT_LINEAR && g->kind != PF_GRADIENT_RADIAL) ||
+        (g->wrap != PF_GRADIENT_WRAP_CLAMP && g->wrap != PF_GRADIENT_WRAP_REPEAT)) {
+        pf::set_last_error("PFScenePushPaintGradient: bad gradient");
+        return 0xffff;
+    }
+    for (size_t i = 0; i + 1 < g->stop_count; i++) {
+        if (!(g->stops[i].offset <= g->stops[i + 1].offset)) { // Gradient::add_color_stop keeps them sorted (gradient.rs:141-150)
+            pf::set_last_error("PFScenePushPaintGradient: colour stops must be sorted by offset");
+            return 0xffff;
+        }
+    }
+    PatternOverlay overlay;
+    overlay.kind = PatternOverlay::GRADIENT;
+    overlay.gradient_kind = g->kind, overlay.gradient_wrap = g->wrap;
+    overlay.from[0] = g->from.x, overlay.from[1] = g->from.y, overlay.to[0] = g->to.x, overlay.to[1] = g->to.y;
+    overlay.radii[0] = g->radii[0], overlay.radii[1] = g->radii[1];
+    overlay.transform.m11 = g->transform.matrix.m00, overlay.transform.m12 = g->transform.matrix.m01;
+    overlay.transform.m21 = g->transform.matrix.m10, overlay.transform.m22 = g->transform.matrix.m11;
+    overlay.transform.tx = g->transform.vector.x, overlay.transform.ty = g->transform.vector.y;
+    overlay.stops.assign(g->stops, g->stops + g->stop_count);
+    memset(&overlay.filter, 0, sizeof(overlay.filter));
+    const uint16_t id = (uint16_t)s->paints.size();
+    s->paints.push_back(PFColorU{255, 255, 255, 255}); // Paint::from_gradient: base colour white (paint.rs:127-136)
+    s->overlays.emplace(id, std::move(overlay));
     s->epoch++;
     return id;
 }
@@ -679,13 +790,25 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
     // builder.rs:160-164
     PFRenderCommand start = make_command(PF_RENDER_COMMAND_START);
     start.u.start.path_count = s->clip_paths.size() + s->draw_paths.size();
-    start.u.start.needs_readable_framebuffer = 0; // only SrcOver is in scope (builder.rs:372-393)
+    // needs_readable_framebuffer (builder.rs:372-393): a path outside any render target blends with a mode the
+    // shader evaluates itself. (This renderer keeps the pixels of a tile in shared memory, so it needs no copy.)
+    start.u.start.needs_readable_framebuffer = 0;
+    if (s->any_blend) {
+        int depth = 0;
+        for (const DisplayItem &item : s->display_list) {
+            if (item.kind == DisplayItem::PUSH_RENDER_TARGET) depth++;
+            else if (item.kind == DisplayItem::POP_RENDER_TARGET) depth--;
+            else if (depth == 0)
+                for (uint32_t i = item.a; i < item.b; i++)
+                    if (s->draw_paths[i].blend_mode >= PF_BLEND_MODE_DARKEN) start.u.start.needs_readable_framebuffer = 1;
+        }
+    }
     SEND(start);
 
     // Paint data (builder.rs:174-180): one TextureMetadataEntry per paint (paint.rs:641-659).
     // Paints are append-only, so (scene id, paint count) identifies the table.
     uint64_t paint_key = mix_key(mix_key(0x9a1f7u, s->id), s->paints.size());
-    if (!s->overlays.empty()) { // texture transforms depend on the build transform (paint.rs:637)
+    if (!s->overlays.empty() || s->any_blend) { // texture transforms depend on the build transform (paint.rs:637)
         uint32_t bits[6];
         const float f[6] = {opts->transform.m11, opts->transform.m21, opts->transform.m12, opts->transform.m22,
                             opts->transform.tx,  opts->transform.ty};
@@ -706,6 +829,58 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
             PFTextureLocation{(uint32_t)i, PFRectI{{0, 0}, {s->render_targets[i].width, s->render_targets[i].height}}};
         SEND(declare);
     }
+    // Gradients and images (Palette::assign_paint_locations, paint.rs:456-595; GradientTileBuilder, :813-873): every
+    // gradient is one row of a 256 x 256 tile on a page of its own kind, sampled at t = (x + 0.5) / 256; every image
+    // gets a page of its own, with a texel of border on the sides it does not repeat on. Pages follow the render
+    // targets' pages. (No atlas allocator and no image cache: pages are named and filled afresh by every build.)
+    {
+        uint32_t next_page = (uint32_t)s->render_targets.size();
+        uint32_t n_gradients = 0;
+        s->gradient_tiles.clear();
+        std::vector<uint16_t> ids;
+        for (auto &kv : s->overlays) ids.push_back(kv.first);
+        std::sort(ids.begin(), ids.end()); // paint order, like the reference's loop over the palette
+        uint32_t gradient_first_page = next_page;
+        for (uint16_t id : ids) {
+            PatternOverlay &o = s->overlays[id];
+            if (o.kind != PatternOverlay::GRADIENT) continue;
+            if (n_gradients % 256 == 0) s->gradient_tiles.emplace_back(256 * 256, PFColorU{0, 0, 0, 255}); // ColorU::black()
+            o.page = gradient_first_page + n_gradients / 256;
+            o.row = (int32_t)(n_gradients % 256);
+            o.page_w = o.page_h = 256;
+            PFColorU *row = s->gradient_tiles.back().data() + (size_t)o.row * 256;
+            for (int x = 0; x < 256; x++) row[x] = gradient_sample(o.stops, ((float)x + 0.5f) / 256.0f);
+            n_gradients++;
+        }
+        next_page += (uint32_t)s->gradient_tiles.size();
+        for (size_t t = 0; t < s->gradient_tiles.size(); t++) {
+            PFRenderCommand page = make_command(PF_RENDER_COMMAND_ALLOCATE_TEXTURE_PAGE);
+            page.u.allocate_texture_page.page_id = gradient_first_page + (uint32_t)t;
+            page.u.allocate_texture_page.size = PFVector2I{256, 256};
+            SEND(page);
+            PFRenderCommand up = make_command(PF_RENDER_COMMAND_UPLOAD_TEXEL_DATA);
+            up.u.upload_texel_data.texels = s->gradient_tiles[t].data();
+            up.u.upload_texel_data.texel_count = 256 * 256;
+            up.u.upload_texel_data.location = PFTextureLocation{gradient_first_page + (uint32_t)t, PFRectI{{0, 0}, {256, 256}}};
+            SEND(up);
+        }
+        for (uint16_t id : ids) {
+            PatternOverlay &o = s->overlays[id];
+            if (o.kind != PatternOverlay::IMAGE) continue;
+            const int bx = (o.pattern_flags & PF_PATTERN_FLAG_REPEAT_X) ? 0 : 1, by = (o.pattern_flags & PF_PATTERN_FLAG_REPEAT_Y) ? 0 : 1;
+            o.page = next_page++;
+            o.page_w = o.width + 2 * bx, o.page_h = o.height + 2 * by;
+            PFRenderCommand page = make_command(PF_RENDER_COMMAND_ALLOCATE_TEXTURE_PAGE);
+            page.u.allocate_texture_page.page_id = o.page;
+            page.u.allocate_texture_page.size = PFVector2I{o.page_w, o.page_h};
+            SEND(page);
+            PFRenderCommand up = make_command(PF_RENDER_COMMAND_UPLOAD_TEXEL_DATA);
+            up.u.upload_texel_data.texels = o.pixels.data();
+            up.u.upload_texel_data.texel_count = o.pixels.size();
+            up.u.upload_texel_data.location = PFTextureLocation{o.page, PFRectI{{bx, by}, {bx + o.width, by + o.height}}}; // rect.contract(border)
+            SEND(up);
+        }
+    }
     if (s->built_paint_key != paint_key) {
         s->texture_metadata.resize(s->paints.size());
         // render_transform = the 2-D build transform inverted (builder.rs:168-171)
@@ -720,16 +895,67 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
             e.filter.kind = PF_FILTER_NONE;
             auto overlay = s->overlays.find((uint16_t)i);
             if (overlay == s->overlays.end()) continue;
-            // calculate_texture_transforms, PatternSource::RenderTarget (paint.rs:626-637):
-            //   translate(rect_to_uv(rect, scale).lower_left()) * scale(scale * (1, -1)) * pattern.transform().inverse()
-            //   * render_transform — v runs bottom-up over a render target (the GL convention, see pf_cuda.h).
-            const RenderTargetDesc &rt = s->render_targets[overlay->second.render_target];
-            const float sx = 1.0f / (float)rt.width, sy = 1.0f / (float)rt.height;
-            const Transform to_pattern = transform_mul(transform_inverse(overlay->second.transform), render_transform);
-            e.color_0_transform.matrix = PFMatrix2x2F{sx * to_pattern.m11, sx * to_pattern.m12, -sy * to_pattern.m21, -sy * to_pattern.m22};
-            e.color_0_transform.vector = PFVector2F{sx * to_pattern.tx, 1.0f - sy * to_pattern.ty};
+            const PatternOverlay &o = overlay->second;
+            Transform t; // calculate_texture_transforms (paint.rs:597-639), before `*= render_transform`
+            e.filter = o.filter;
+            if (o.kind == PatternOverlay::RENDER_TARGET) {
+                //   translate(rect_to_uv(rect, scale).lower_left()) * scale(scale * (1, -1)) * pattern.transform().inverse()
+                // — v runs bottom-up over a render target (the GL convention, see pf_cuda.h).
+                const RenderTargetDesc &rt = s->render_targets[o.render_target];
+                const float sx = 1.0f / (float)rt.width, sy = 1.0f / (float)rt.height;
+                const Transform inv = transform_inverse(o.transform);
+                t.m11 = sx * inv.m11, t.m12 = sx * inv.m12, t.m21 = -sy * inv.m21, t.m22 = -sy * inv.m22;
+                t.tx = sx * inv.tx, t.ty = 1.0f - sy * inv.ty;
+            } else if (o.kind == PatternOverlay::IMAGE) {
+                //   from_scale(texture_scale).translate(rect_to_uv(rect, scale).origin()) * pattern.transform().inverse()
+                // The rect is the page (origin 0): the border is NOT added back (the `transform` assign_paint_locations
+                // stored is overwritten here), so an image that does not repeat sits one texel further right / down.
+                const float sx = 1.0f / (float)o.page_w, sy = 1.0f / (float)o.page_h;
+                const Transform inv = transform_inverse(o.transform);
+                t.m11 = sx * inv.m11, t.m12 = sx * inv.m12, t.m21 = sy * inv.m21, t.m22 = sy * inv.m22;
+                t.tx = sx * inv.tx, t.ty = sy * inv.ty;
+            } else if (o.gradient_kind == PF_GRADIENT_LINEAR) {
+                // Project the gradient line onto (0..1, v0): v0 = the row's centre (paint.rs:611-618).
+                const float v0 = ((float)o.row + 0.5f) * (1.0f / 256.0f);
+                const float dx = o.to[0] - o.from[0], dy = o.to[1] - o.from[1];
+                const float len2 = dx * dx + dy * dy;
+                const float m0x = dx / len2, m0y = dy / len2;
+                t.m11 = m0x, t.m12 = m0y, t.m21 = 0.0f, t.m22 = 0.0f;
+                t.tx = m0x * -o.from[0] + m0y * -o.from[1], t.ty = v0;
+            } else {
+                // Radial: the gradient's own transform inverted; the filter finds t and samples (uv_origin + (t, 0))
+                // (paint.rs:619-622,788-793: uv_origin = the row's rect contracted by half a texel vertically).
+                t = transform_inverse(o.transform);
+                e.filter.kind = PF_FILTER_RADIAL_GRADIENT;
+                e.filter.flags = 0;
+                const float params[8] = {o.from[0], o.from[1], o.to[0], o.to[1], o.radii[0], o.radii[1], 0.0f,
+                                         ((float)o.row + 0.5f) * (1.0f / 256.0f)};
+                memset(e.filter.params, 0, sizeof(e.filter.params));
+                memcpy(e.filter.params, params, sizeof(params));
+            }
+            const Transform full = transform_mul(t, render_transform);
+            e.color_0_transform.matrix = PFMatrix2x2F{full.m11, full.m12, full.m21, full.m22};
+            e.color_0_transform.vector = PFVector2F{full.tx, full.ty};
             e.color_0_combine_mode = PF_COLOR_COMBINE_MODE_SRC_IN; // create_texture_metadata (paint.rs:649-653)
-            e.filter = overlay->second.filter;
+        }
+        // Blend modes: the reference's TextureMetadataEntry carries one (gpu_data.rs:343) that its palette never sets
+        // (paint.rs:576 "FIXME"); here every (paint, blend mode) pair a draw path uses gets an entry of its own after
+        // the palette's, and the path's tiles name that entry.
+        s->blend_entries.clear();
+        if (s->any_blend) {
+            for (const Path &dp : s->draw_paths) {
+                if (dp.blend_mode == PF_BLEND_MODE_SRC_OVER) continue;
+                const uint32_t key = (uint32_t)dp.paint | ((uint32_t)dp.blend_mode << 16);
+                if (s->blend_entries.count(key)) continue;
+                if (s->texture_metadata.size() >= 65535) {
+                    pf::set_last_error("more than 65535 (paint, blend mode) pairs");
+                    return PF_CUDA_ERROR_UNSUPPORTED;
+                }
+                PFTextureMetadataEntry e = s->texture_metadata[dp.paint];
+                e.blend_mode = dp.blend_mode;
+                s->blend_entries.emplace(key, (uint16_t)s->texture_metadata.size());
+                s->texture_metadata.push_back(e);
+            }
         }
         s->built_paint_key = paint_key;
     }
@@ -776,7 +1002,7 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
 
     bool display_ops = false; // a push / pop anywhere in the display list
     for (const DisplayItem &item : s->display_list) display_ops |= item.kind != DisplayItem::DRAW_PATHS;
-    if (display_ops || !s->render_targets.empty() || !s->overlays.empty()) {
+    if (display_ops || !s->render_targets.empty() || !s->overlays.empty() || s->any_blend) {
         // A scene with a display list: one batch per DrawPaths item, split again wherever the colour texture
         // changes (build_tile_batches / build_tile_batches_for_draw_path_display_item / fixup_batch_for_new_path_if_possible,
         // builder.rs:327-357,886-940,1227-1243). Built sequentially and afresh every frame (content_key = 0): these
@@ -833,8 +1059,11 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
             GeneralBatch *gb = &s->general_batches.back();
             for (uint32_t i = item.a; i < item.b; i++) {
                 const Path &p = s->draw_paths[i];
-                if (p.blend_mode != PF_BLEND_MODE_SRC_OVER) {
-                    pf::set_last_error("only BlendMode::SrcOver is on the hot path");
+                if (p.blend_mode == PF_BLEND_MODE_CLEAR || p.blend_mode == PF_BLEND_MODE_COPY || p.blend_mode == PF_BLEND_MODE_SRC_IN ||
+                    p.blend_mode == PF_BLEND_MODE_DEST_IN || p.blend_mode == PF_BLEND_MODE_SRC_OUT ||
+                    p.blend_mode == PF_BLEND_MODE_DEST_ATOP || p.blend_mode > PF_BLEND_MODE_LUMINOSITY) {
+                    // BlendMode::is_destructive (effects.rs:222-235): tiled over the whole view box (builder.rs:430-434)
+                    pf::set_last_error("destructive blend modes (Clear, Copy, SrcIn, DestIn, SrcOut, DestAtop) are not implemented");
                     return PF_CUDA_ERROR_UNSUPPORTED;
                 }
                 if (p.clip_path != PF_CLIP_PATH_NONE) {
@@ -855,21 +1084,40 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                 // the path's colour texture (PaintMetadata::tile_batch_texture, paint.rs:802-804)
                 auto overlay = s->overlays.find(p.paint);
                 const bool has_texture = overlay != s->overlays.end();
-                const PFTileBatchTexture texture{has_texture ? overlay->second.render_target : 0u, 0, PF_PAINT_COMPOSITE_OP_SRC_IN};
+                PFTileBatchTexture texture{0u, 0, PF_PAINT_COMPOSITE_OP_SRC_IN};
                 if (has_texture) {
-                    if (gb->has_color_texture && gb->color_texture.page != texture.page) { // batch break
+                    const PatternOverlay &o = overlay->second;
+                    uint8_t flags = 0; // TextureSamplingFlags (paint.rs:470-476,553-563)
+                    if (o.kind == PatternOverlay::RENDER_TARGET) {
+                        texture.page = o.render_target;
+                    } else if (o.kind == PatternOverlay::GRADIENT) {
+                        texture.page = o.page;
+                        if (o.gradient_wrap == PF_GRADIENT_WRAP_REPEAT) flags |= PF_TEXTURE_SAMPLING_FLAGS_REPEAT_U;
+                    } else {
+                        texture.page = o.page;
+                        if (o.pattern_flags & PF_PATTERN_FLAG_REPEAT_X) flags |= PF_TEXTURE_SAMPLING_FLAGS_REPEAT_U;
+                        if (o.pattern_flags & PF_PATTERN_FLAG_REPEAT_Y) flags |= PF_TEXTURE_SAMPLING_FLAGS_REPEAT_V;
+                        if (o.pattern_flags & PF_PATTERN_FLAG_NO_SMOOTHING)
+                            flags |= PF_TEXTURE_SAMPLING_FLAGS_NEAREST_MIN | PF_TEXTURE_SAMPLING_FLAGS_NEAREST_MAG;
+                    }
+                    texture.sampling_flags = flags;
+                    if (gb->has_color_texture && (gb->color_texture.page != texture.page ||
+                                                  gb->color_texture.sampling_flags != texture.sampling_flags)) { // batch break
                         s->general_batches.emplace_back();
                         gb = &s->general_batches.back();
                     }
                     gb->has_color_texture = true;
                     gb->color_texture = texture;
                 }
+                uint16_t entry = p.paint; // the texture metadata entry the path's tiles name
+                if (p.blend_mode != PF_BLEND_MODE_SRC_OVER)
+                    entry = s->blend_entries.at((uint32_t)p.paint | ((uint32_t)p.blend_mode << 16));
                 const uint32_t w = (uint32_t)(tile_rect.lower_right.x - tile_rect.origin.x),
                                h = (uint32_t)(tile_rect.lower_right.y - tile_rect.origin.y);
                 const uint32_t bi = (uint32_t)gb->propagate_metadata.size();
                 // BuiltDrawPath::new (builder.rs:80-94): occludes = opaque paint && SrcOver; a render-target pattern
                 // is never "obviously opaque" (pattern.rs:264-272).
-                const bool occludes = !has_texture && s->paints[p.paint].a == 255;
+                const bool occludes = !has_texture && s->paints[p.paint].a == 255 && p.blend_mode == PF_BLEND_MODE_SRC_OVER;
                 PFPropagateMetadataD3D11 pm;
                 memset(&pm, 0, sizeof(pm));
                 pm.tile_rect = tile_rect;
@@ -886,7 +1134,7 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                 tp.tile_max_x = (int16_t)tile_rect.lower_right.x;
                 tp.tile_max_y = (int16_t)tile_rect.lower_right.y;
                 tp.first_tile_index = gb->tile_count;
-                tp.color = p.paint;
+                tp.color = entry;
                 tp.ctrl = p.fill_rule == PF_FILL_RULE_EVEN_ODD ? PF_TILE_CTRL_MASK_EVEN_ODD : PF_TILE_CTRL_MASK_WINDING;
                 tp.backdrop = 0;
                 gb->tile_path_info.push_back(tp);
