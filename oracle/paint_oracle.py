@@ -340,12 +340,10 @@ def blend(dest, color, mask, mode="src_over"):
     if BLEND_MODES.index(mode) >= BLEND_MODES.index("darken"):
         blended = composite_rgb(d_rgb, s_rgb, mode)
         rgb = sa * (F(1.0) - da) * s_rgb + sa * da * blended + (F(1.0) - sa) * d_rgb
-        return np.concatenate([rgb, np.ones_like(sa)], axis=-1).astype(np.float32)
+        return np.concatenate([np.clip(rgb, F(0.0), F(1.0)), np.ones_like(sa)], axis=-1).astype(np.float32)  # UNORM target
     one = np.ones_like(sa)
     sf, df = {"src_over": (one, one - sa), "dest_over": (one - da, one), "dest_out": (0 * one, one - sa),
               "src_atop": (da, one - sa), "xor": (one - da, one - sa), "lighter": (one, one)}[mode]
     src = np.concatenate([s_rgb * sa, sa], axis=-1)
     out = src * sf + dest * df
-    if mode == "lighter":
-        out = np.minimum(out, F(1.0))  # the render target is UNORM
-    return out.astype(np.float32)
+    return np.clip(out, F(0.0), F(1.0)).astype(np.float32)  # the render target is UNORM (Lighter adds; a colour matrix can overshoot)

@@ -596,7 +596,9 @@ __device__ __forceinline__ float4 blend_pixel(float4 d, float4 c, float m, uint3
     if (mode >= 12u) { // PF_BLEND_MODE_DARKEN ..
         const float3 b = composite_rgb(make_float3(d.x, d.y, d.z), make_float3(c.x, c.y, c.z), mode);
         const float k0 = sa * (1.0f - d.w), k1 = sa * d.w, k2 = 1.0f - sa;
-        return make_float4(k0 * c.x + k1 * b.x + k2 * d.x, k0 * c.y + k1 * b.y + k2 * d.y, k0 * c.z + k1 * b.z + k2 * d.z, 1.0f);
+        // (dodge and burn leave [0, 1]; the render target is UNORM, and so is what the next path reads)
+        return make_float4(__saturatef(k0 * c.x + k1 * b.x + k2 * d.x), __saturatef(k0 * c.y + k1 * b.y + k2 * d.y),
+                           __saturatef(k0 * c.z + k1 * b.z + k2 * d.z), 1.0f);
     }
     float sf, df; // source / destination factors (the same for colour and alpha in every mode)
     switch (mode) {
@@ -609,8 +611,8 @@ __device__ __forceinline__ float4 blend_pixel(float4 d, float4 c, float m, uint3
     }
     const float k = sa * sf;
     float4 out = make_float4(fmaf(d.x, df, c.x * k), fmaf(d.y, df, c.y * k), fmaf(d.z, df, c.z * k), fmaf(d.w, df, k));
-    if (mode == 11u) out = make_float4(fminf(out.x, 1.0f), fminf(out.y, 1.0f), fminf(out.z, 1.0f), fminf(out.w, 1.0f)); // UNORM target
-    return out;
+    // The render target is UNORM: Lighter adds, and a colour-matrix filter can hand out colours outside [0, 1].
+    return make_float4(__saturatef(out.x), __saturatef(out.y), __saturatef(out.z), __saturatef(out.w));
 }
 
 template <bool LOAD_DEST, bool GENERAL>
