@@ -218,6 +218,12 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOAD_NAMES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames-in-flight", type=int, default=1, choices=[1, 2],
+                    help="renderer instances per scene in the device-resident timed region: with 2, consecutive frames of a "
+                         "scene alternate between two renderers on their own streams (double buffering), so the stages of "
+                         "frame i + 1 overlap those of frame i; isolated per-frame times and e2e always use one. Measured on a "
+                         "B200: 1.003 -> 0.953 ms/step (+5 %): the three scenes of a step already fill the GPU, so 1 stays "
+                         "the default")
     ap.add_argument("--no-random1m", action="store_true", help="skip the random1m@16384 sub-record of the headline line")
     ap.add_argument("--gather", default="tiles", choices=["tiles", "nccl", "peer"],
                     help="N > 1, how the frame is assembled on every rank. 'tiles' (default) = PFCudaRendererGatherFrame in "
@@ -343,6 +349,18 @@ def main():
 
     for name, flat, xf, size in scene_list:
         frames.append(make_frame(name, flat, xf, size, len(frames)))
+    # Frames in flight: a second renderer (own stream, own stage buffers, own frame buffer, own gather group) per
+    # scene; steps alternate between the two. Every step still renders every scene once, into a complete frame.
+    for f in frames:
+        f.alt = None
+    if args.frames_in_flight == 2:
+        for i, (name, flat, xf, size) in enumerate(scene_list):
+            frames[i].alt = make_frame(name, flat, xf, size, len(scene_list) + i, device_only=True)
+            frames[i].alt.alt = None
+    instances = [g for f in frames for g in ((f, f.alt) if f.alt is not None else (f,))]
+
+    def instance_of(f, step_index):
+        return f.alt if (f.alt is not None and step_index % 2 == 1) else f
 
     copy_stream = torch.cuda.Stream()
     flag = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -385,11 +403,11 @@ def main():
                 f.copied.record(copy_stream)
 
     def fork():  # the frames' streams start after everything already on `stream` (the start event)
-        for f in frames:
+        for f in instances:
             f.stream.wait_stream(stream)
 
     def join():  # ... and `stream` (the end event) waits for all of them, frame assembly included
-        for f in frames:
+        for f in instances:
             if dist is not None and not f.peer:
                 f.renderer.gather_wait()  # the frame's stream waits for its last gather
             stream.wait_stream(f.stream)
@@ -418,8 +436,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(args.warmup):
-        step(False)
+    for w in range(max(args.warmup, 2 * args.frames_in_flight)):
+        for f in frames:
+            render_frame(instance_of(f, w), False)
     barrier()
 
     # Per-frame stats after warm-up.
@@ -434,7 +453,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for f in frames:
+    for f in instances:
         f.renderer.set_timing_enabled(True)
     stage_acc = {f.name: {} for f in frames}
 
@@ -443,14 +462,19 @@ def main():
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record(stream)
     fork()
-    for _ in range(args.steps):
+    for k in range(args.steps):
         for f in frames:
-            render_frame(f, False)  # no host wait in here: verification is deferred, stage events are read afterwards
+            render_frame(instance_of(f, k), False)  # no host wait in here: verification is deferred, stage events are read afterwards
     join()
     end.record(stream)
     barrier()
     for f in frames:
         totals, batches = f.renderer.accumulated_times()
+        if f.alt is not None:  # the scene's frames were shared between its two renderers
+            more, more_batches = f.alt.renderer.accumulated_times()
+            totals = {k: v + more.get(k, 0.0) for k, v in totals.items()}
+            batches += more_batches
+            f.alt.renderer.set_timing_enabled(False)
         assert batches and batches % args.steps == 0, (batches, args.steps)  # (several draw batches per frame: render targets)
         stage_acc[f.name] = totals
     dev_s = start.elapsed_time(end) / 1e3
@@ -609,9 +633,12 @@ def main():
                                                              else (" + compact tile exports pushed to the peers over NVLink by the library (PFCudaRendererGatherFrame, tile mode), overlapped with the next frame" if args.gather == "tiles"
                                                                    else " + ncclAllGather issued by the library (PFCudaRendererGatherFrame, frame mode), overlapped with the next frame")) if world > 1 else ""),
                    "l2": "inputs larger than L2: a step touches > 1 GB of stage buffers and frames",
+                   "frames_in_flight": args.frames_in_flight,
                    "streams": "the frames of a step are independent scenes and render concurrently on one CUDA stream each "
-                              "(forked from / joined to the timing stream); no host wait inside the timed region "
-                              "(deferred verification); ms_per_frame / stage_ms are per-stream event times and overlap",
+                              "(forked from / joined to the timing stream); consecutive frames of a scene alternate between "
+                              "%d renderer instance(s) with their own streams, stage buffers and frame buffers; no host wait "
+                              "inside the timed region (deferred verification); ms_per_frame / stage_ms are per-stream event "
+                              "times and overlap; ms_per_frame_isolated = one scene, one renderer, alone on the GPU" % args.frames_in_flight,
                    "random1m": random1m,
                    "ms_per_frame_isolated": isolated_ms,
                    "stage_ms_isolated": isolated_stage,
