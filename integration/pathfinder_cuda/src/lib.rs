@@ -322,6 +322,37 @@ impl CudaRenderer {
     }
 
     /// RGBA8 rows, top-left origin, into `dst` (`stride` bytes per row).
+    /// Multi-GPU frame assembly (one process per GPU; include/pf_cuda.h "PFCudaRendererGather*"). `id` comes from
+    /// `gather_create_id()` on one rank and reaches the others through any host channel.
+    pub fn gather_create_id() -> [u8; 128] {
+        let mut id = [0u8; 128];
+        check(unsafe { ffi::PFCudaGatherCreateId(id.as_mut_ptr()) });
+        id
+    }
+
+    /// Collective: joins the group and sets this renderer's strip of tile rows.
+    pub fn gather_init(&mut self, id: &[u8; 128], rank: i32, world_size: i32) {
+        check(unsafe { ffi::PFCudaRendererGatherInit(self.raw, id.as_ptr(), rank, world_size) })
+    }
+
+    /// 0 = all-gather of the finished strips, 1 = compact tile exports pushed over NVLink (the default where possible).
+    pub fn gather_set_mode(&mut self, mode: i32) {
+        check(unsafe { ffi::PFCudaRendererGatherSetMode(self.raw, mode) })
+    }
+
+    /// Collective, asynchronous: completes every rank's copy of the frame just rendered.
+    pub fn gather_frame(&mut self) {
+        check(unsafe { ffi::PFCudaRendererGatherFrame(self.raw) })
+    }
+
+    pub fn gather_wait(&mut self) {
+        check(unsafe { ffi::PFCudaRendererGatherWait(self.raw) })
+    }
+
+    pub fn gather_destroy(&mut self) {
+        check(unsafe { ffi::PFCudaRendererGatherDestroy(self.raw) })
+    }
+
     pub fn read_pixels(&mut self, dst: &mut [u8], stride: usize) {
         check(unsafe { ffi::PFCudaRendererReadPixels(self.raw, dst.as_mut_ptr(), stride) })
     }
