@@ -133,8 +133,11 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 // k_tile_solid — single-colour tiles, one lane per framebuffer tile; queues the others.
 // ---------------------------------------------------------------------------------------------
 
+#ifndef PF_SOLID_MIN_BLOCKS
+#define PF_SOLID_MIN_BLOCKS 1
+#endif
 template <bool LOAD_DEST>
-__global__ void __launch_bounds__(128) k_tile_solid(CompositeArgs a) {
+__global__ void __launch_bounds__(128, PF_SOLID_MIN_BLOCKS) k_tile_solid(CompositeArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int fb_w = a.fb.max_x - a.fb.min_x;
@@ -179,7 +182,8 @@ __global__ void __launch_bounds__(128) k_tile_solid(CompositeArgs a) {
     if (paints) {
         uint32_t keys[SOLID_MAX]; // one round of loads for all the keys, then selection in registers
 #pragma unroll
-        for (int j = 0; j < SOLID_MAX; j++) keys[j] = (uint32_t)j < n ? __ldg(&a.entries[e0 + j].tile_index) : 0xffffffffu;
+        for (int j = 0; j < SOLID_MAX; j++) // (a list of one needs no order: no round trip for its key)
+            keys[j] = ((uint32_t)j < n && n > 1u) ? __ldg(&a.entries[e0 + j].tile_index) : ((uint32_t)j < n ? 0u : 0xffffffffu);
         uint32_t last = 0;
         for (uint32_t i = 0; i < n; i++) {
             uint32_t best = 0xffffffffu, best_j = 0;
