@@ -597,6 +597,12 @@ typedef PFCudaStatus (*PFRenderCommandListenerFn)(const PFRenderCommand *command
 typedef struct PFSceneSinkState { uint32_t has_last_scene, last_scene_id, last_scene_epoch; } PFSceneSinkState;
 PFCudaStatus PFSceneBuild(PFSceneRef scene, PFBuildOptionsRef options, PFSceneSinkState *sink_state,
                           PFRenderCommandListenerFn listener, void *userdata);
+/* The same for a renderer that owns the tile rows [tile_y0, tile_y1) of the frame (PFCudaRendererSetStrip, multi-GPU):
+ * draw paths without a tile in those rows are left out of the uploaded segments and of the batch (their ids stay
+ * global, so draw order and occlusion are those of the whole scene). PFSceneBuildAndRenderCuda applies the
+ * renderer's strip by itself. Scenes with render targets, textured paints or blend modes are built whole. */
+PFCudaStatus PFSceneBuildForStrip(PFSceneRef scene, PFBuildOptionsRef options, PFSceneSinkState *sink_state,
+                                  PFRenderCommandListenerFn listener, void *userdata, int32_t tile_y0, int32_t tile_y1);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Stroke-to-fill on the host: OutlineStrokeToFill, content/src/stroke.rs:88-448. */

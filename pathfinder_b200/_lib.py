@@ -331,6 +331,8 @@ SIGNATURES = {
     "PFBuildOptionsSetDilation": (None, [C.c_void_p, C.POINTER(PFVector2F)]),
     "PFBuildOptionsSetSubpixelAAEnabled": (None, [C.c_void_p, C.c_int32]),
     "PFSceneBuild": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(PFSceneSinkState), LISTENER_FN, C.c_void_p]),
+    "PFSceneBuildForStrip": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(PFSceneSinkState), LISTENER_FN, C.c_void_p,
+                                         C.c_int32, C.c_int32]),
     "PFSceneBuildAndRenderCuda": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -280,8 +280,9 @@ class Scene:
     def draw_path_count(self) -> int:
         return int(L.lib().PFSceneGetDrawPathCount(self._h))
 
-    def build(self, options: BuildOptions, listener, sink_state: L.PFSceneSinkState | None = None):
-        """Scene::build at the D3D11 level: calls listener(PFRenderCommand) per command."""
+    def build(self, options: BuildOptions, listener, sink_state: L.PFSceneSinkState | None = None, strip=None):
+        """Scene::build at the D3D11 level: calls listener(PFRenderCommand) per command. strip = (tile_y0, tile_y1):
+        build for a renderer that owns those tile rows (PFSceneBuildForStrip)."""
         state = sink_state if sink_state is not None else L.PFSceneSinkState()
         errors = []
 
@@ -297,7 +298,10 @@ class Scene:
                 return L.PF_CUDA_ERROR_INVALID_ARGUMENT
 
         cb = L.LISTENER_FN(trampoline)
-        status = L.lib().PFSceneBuild(self._h, options._h, C.byref(state), cb, None)
+        if strip is not None:
+            status = L.lib().PFSceneBuildForStrip(self._h, options._h, C.byref(state), cb, None, int(strip[0]), int(strip[1]))
+        else:
+            status = L.lib().PFSceneBuild(self._h, options._h, C.byref(state), cb, None)
         if errors:
             raise errors[0]
         L.check(status)

@@ -72,6 +72,9 @@ struct DeviceBuffer {
 // (they are only rewritten after the scene has waited for the renderer's copies), so UploadSceneD3D11
 // may carry payload_persists = 1.
 extern thread_local bool g_scene_payload_persists;
+// Tile rows [y0, y1) of the renderer the scene is being built for (y1 <= y0: the whole frame); set by
+// PFSceneBuildAndRenderCuda around PFSceneBuild.
+extern thread_local int32_t g_scene_strip[2];
 // Records, on the renderer's stream, the point after which the scene may rewrite the segment arrays it
 // lent to the renderer (scene.cpp waits for it before the next rebuild).
 void scene_note_borrowed(::PFScene *scene, cudaStream_t stream, int device);

@@ -23,6 +23,16 @@
 
 namespace pf {
 
+// SM count of the device current on this thread, cached per device (one process may drive several GPUs).
+static int sm_count_of_current_device() {
+    static int table[64] = {0};
+    int dev = 0;
+    PF_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) throw Error(2, "device ordinal out of range");
+    if (table[dev] == 0) PF_CUDA_CHECK(cudaDeviceGetAttribute(&table[dev], cudaDevAttrMultiProcessorCount, dev));
+    return table[dev];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Bit-exact scalar helpers (simd/src/x86/mod.rs semantics).
 // ---------------------------------------------------------------------------------------------
@@ -388,12 +398,7 @@ int launch_dice_stream(const BatchDev &b, float4 *lines, uint32_t *line_path, ui
                        uint32_t *line_count, cudaStream_t stream) {
     if (b.n_segments == 0) return 0;
     // Enough warps to give every scheduler of the GPU a few (148 SMs x 4 schedulers x 2), at most 32 curves each.
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        PF_CUDA_CHECK(cudaGetDevice(&dev));
-        PF_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int sm_count = sm_count_of_current_device();
     const uint32_t target_warps = (uint32_t)sm_count * 8u;
     const uint32_t per_warp = std::min(32u, std::max(1u, div_up(b.n_segments, target_warps)));
     const uint32_t warps = div_up(b.n_segments, per_warp);
@@ -827,7 +832,7 @@ int launch_bin(int mode, const BatchDev &b, const BinArgs &args, cudaStream_t st
     else
         k_bin<BIN_EMIT><<<grid, BIN_THREADS, 0, stream>>>(b, args);
     if (mode != BIN_EMIT && args.long_queue) {
-        const unsigned long_grid = 148 * 2; // persistent warps; exits at once when the queue is empty
+        const unsigned long_grid = (unsigned)sm_count_of_current_device() * 2u; // persistent warps; exits at once when the queue is empty
         if (mode == BIN_EMIT_LIVE)
             k_bin_long<BIN_EMIT_LIVE><<<long_grid, BIN_THREADS, 0, stream>>>(b, args);
         else
@@ -1003,7 +1008,18 @@ __global__ void __launch_bounds__(256)
             const PathInfo path = load_path(b.paths, p);
             const int w = path.max_x - path.min_x;
             const uint32_t local = t - path.tile_offset;
-            const int x = (int)(local % (uint32_t)w), y = (int)(local / (uint32_t)w);
+            // local = y * w + x without the ~60 instructions of two 32-bit divisions: a float quotient, corrected
+            // (rects of more than 2^20 tiles take the integer path)
+            uint32_t qy, qx;
+            if (local < (1u << 20)) { // (quotient error of the approximate division < 0.25: at most one off before the correction)
+                qy = (uint32_t)__float2uint_rz(__fdividef((float)local + 0.5f, (float)w));
+                qx = local - qy * (uint32_t)w;
+                if ((int32_t)qx < 0) qy--, qx += (uint32_t)w;
+                else if (qx >= (uint32_t)w) qy++, qx -= (uint32_t)w;
+            } else {
+                qy = local / (uint32_t)w, qx = local - qy * (uint32_t)w;
+            }
+            const int x = (int)qx, y = (int)qy;
             const int fx = path.min_x + x - b.fb.min_x, fy = path.min_y + y - b.fb.min_y;
             if (fx >= 0 && fy >= 0 && fx < fb_w && fy < fb_h) {
                 const uint32_t fbi = (uint32_t)(fy * fb_w + fx);

@@ -2110,7 +2110,9 @@ PFCudaStatus PFSceneBuildAndRenderCuda(PFSceneRef scene, PFCudaRendererRef r, PF
     // here: the scene itself waits (scene_note_borrowed) before it rewrites them.
     r->uploaded_scene_this_frame = false;
     pf::g_scene_payload_persists = true;
+    pf::g_scene_strip[0] = r->strip_y0, pf::g_scene_strip[1] = r->strip_y1; // the builder skips paths outside the strip
     st = PFSceneBuild(scene, options, &r->sink_state, forward_command, r);
+    pf::g_scene_strip[0] = pf::g_scene_strip[1] = 0;
     pf::g_scene_payload_persists = false;
     if (r->uploaded_scene_this_frame) {
         try {

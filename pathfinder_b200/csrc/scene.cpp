@@ -30,6 +30,7 @@
 
 namespace pf {
 thread_local bool g_scene_payload_persists = false;
+thread_local int32_t g_scene_strip[2] = {0, 0};
 void set_last_error(const std::string &msg);
 }
 
@@ -209,6 +210,8 @@ struct PFScene {
     std::vector<GeneralBatch> general_batches; // scratch of the general builder (kept alive while commands are sent)
     bool any_blend = false;                    // some draw path blends with something other than SrcOver
     std::unordered_map<uint32_t, uint16_t> blend_entries; // paint | blend mode << 16 -> texture metadata entry
+    std::vector<uint8_t> strip_included;       // per draw path: has a tile in the renderer's strip
+    std::vector<uint32_t> strip_ids;           // ... and those paths' ids, ascending (what a strip build iterates over)
     std::vector<std::vector<PFColorU>> gradient_tiles; // scratch: texels of the gradient pages of this build
     RectF bounds{0, 0, 0, 0};
     RectF view_box{0, 0, 0, 0};
@@ -388,12 +391,18 @@ void wait_for_borrowers(PFScene *s) {
 void build_path_segments(PFScene *s, const PFVector2F *scene_points, const std::vector<Path> &paths,
                          HostBuffer<PFVector2F> &seg_points,
                          HostBuffer<PFSegmentIndicesD3D11> &seg_indices, size_t &seg_point_count, size_t &seg_index_count,
-                         std::vector<uint32_t> &path_offsets, std::vector<uint32_t> &segment_ranges) {
+                         std::vector<uint32_t> &path_offsets, std::vector<uint32_t> &segment_ranges,
+                         const std::vector<uint32_t> *ids = nullptr) {
+    // `ids` (optional, ascending): the paths to emit. The others are not touched at all — a renderer that owns a strip
+    // of the frame only needs the paths that reach it, and at N ranks even reading 100k path records per frame on a
+    // rank's share of the host cores would cost more than the strip's own work.
     const size_t n_paths = paths.size();
+    const size_t n_items = ids ? ids->size() : n_paths;
     path_offsets.resize(2 * (n_paths + 1));
     uint32_t *point_off = path_offsets.data(), *index_off = point_off + (n_paths + 1);
     uint32_t np = 0, ni = 0;
-    for (size_t pi = 0; pi < n_paths; pi++) {
+    for (size_t k = 0; k < n_items; k++) {
+        const size_t pi = ids ? (*ids)[k] : k;
         point_off[pi] = np, index_off[pi] = ni;
         np += paths[pi].segment_points;
         ni += paths[pi].segment_indices;
@@ -405,8 +414,9 @@ void build_path_segments(PFScene *s, const PFVector2F *scene_points, const std::
     PFVector2F *out_points = seg_points.ptr;
     PFSegmentIndicesD3D11 *out_indices = seg_indices.ptr;
     const uint8_t ctrl_mask = PF_POINT_FLAGS_CONTROL_POINT_0 | PF_POINT_FLAGS_CONTROL_POINT_1;
-    parallel_ranges(n_paths, 4096, [&](size_t begin, size_t end) {
-        for (size_t pi = begin; pi < end; pi++) {
+    parallel_ranges(n_items, ids ? 1024 : 4096, [&](size_t begin, size_t end) {
+        for (size_t k = begin; k < end; k++) {
+            const size_t pi = ids ? (*ids)[k] : k;
             const Path &path = paths[pi];
             size_t wp = point_off[pi], wi = index_off[pi];
             segment_ranges[2 * pi] = (uint32_t)wi;
@@ -435,10 +445,10 @@ void build_path_segments(PFScene *s, const PFVector2F *scene_points, const std::
 }
 
 // `scene_points`: the scene's own points, or their prepared copy.
-void build_segments(PFScene *s, const PFVector2F *scene_points) {
+void build_segments(PFScene *s, const PFVector2F *scene_points, const std::vector<uint32_t> *draw_ids = nullptr) {
     wait_for_borrowers(s);
     build_path_segments(s, scene_points, s->draw_paths, s->seg_points, s->seg_indices, s->seg_point_count, s->seg_index_count,
-                        s->seg_path_offsets, s->draw_segment_ranges);
+                        s->seg_path_offsets, s->draw_segment_ranges, draw_ids);
     build_path_segments(s, scene_points, s->clip_paths, s->clip_seg_points, s->clip_seg_indices, s->clip_seg_point_count,
                         s->clip_seg_index_count, s->clip_seg_path_offsets, s->clip_segment_ranges);
 }
@@ -975,14 +985,57 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         memcpy(bits, f, sizeof(bits));
         for (uint32_t v : bits) segments_key = mix_key(segments_key, v);
     }
+    // A renderer that owns a strip of tile rows (PFCudaRendererSetStrip / GatherInit; handed down by
+    // PFSceneBuildAndRenderCuda) drops every path without a tile in its rows: the builder then neither copies their
+    // segments nor builds their records, so at N ranks the host work and the upload per rank shrink with the strip
+    // like the device work does. Path ids stay global (DiceMetadataD3D11.global_path_id), so draw order and the
+    // z-buffer are those of the whole scene. (Scenes with a display list are built whole.)
+    bool general_scene = !s->render_targets.empty() || !s->overlays.empty() || s->any_blend;
+    for (const DisplayItem &item : s->display_list) general_scene |= item.kind != DisplayItem::DRAW_PATHS;
+    const bool strip_on = pf::g_scene_strip[1] > pf::g_scene_strip[0] && !general_scene;
+    const int32_t strip_y0 = pf::g_scene_strip[0], strip_y1 = pf::g_scene_strip[1];
+    if (strip_on) {
+        uint32_t bits[10];
+        const float f[10] = {opts->transform.m11, opts->transform.m21, opts->transform.m12, opts->transform.m22,
+                             opts->transform.tx,  opts->transform.ty,  s->view_box.min_x,   s->view_box.min_y,
+                             s->view_box.max_x,   s->view_box.max_y};
+        memcpy(bits, f, sizeof(bits));
+        for (uint32_t v : bits) segments_key = mix_key(segments_key, v);
+        segments_key = mix_key(mix_key(segments_key, (uint32_t)strip_y0), (uint32_t)strip_y1);
+    }
     if (segments_key == 0) segments_key = 1;
+    pf::LapTimer seg_laps;
+    seg_laps.lap("paints, keys");
     if (s->segments_key != segments_key) {
         if (prepared) {
             s->prepared_points.resize(s->points.size());
             prepare_paths(s, s->draw_paths, opts->transform, opts->dilation, s->prepared_draw_bounds);
             prepare_paths(s, s->clip_paths, opts->transform, opts->dilation, s->prepared_clip_bounds);
         }
-        build_segments(s, prepared ? s->prepared_points.data() : s->points.data());
+        s->strip_ids.clear();
+        if (strip_on) {
+            // the rows of prepare_draw_path_for_gpu_binning's tile rect (builder.rs:1075-1079), as in pass 1 below
+            const size_t n = s->draw_paths.size();
+            s->strip_included.assign(n, 0);
+            const Transform identity_xf;
+            const Transform &sxf = prepared ? identity_xf : opts->transform;
+            parallel_ranges(n, 8192, [&](size_t begin, size_t end) {
+                for (size_t i = begin; i < end; i++) {
+                    const Path &p = s->draw_paths[i];
+                    const RectF b = prepared ? s->prepared_draw_bounds[i] : sxf.is_identity() ? p.bounds : sxf.apply_rect(p.bounds);
+                    RectF clipped;
+                    if (!rect_intersection(b, s->view_box, clipped)) continue;
+                    const float k = 1.0f / 16.0f;
+                    const int32_t ty0 = (int32_t)floorf(clipped.min_y * k), ty1 = (int32_t)ceilf(clipped.max_y * k);
+                    s->strip_included[i] = (ty0 < strip_y1 && ty1 > strip_y0) ? 1 : 0;
+                }
+            });
+            for (size_t i = 0; i < n; i++)
+                if (s->strip_included[i]) s->strip_ids.push_back((uint32_t)i);
+        }
+        seg_laps.lap("strip inclusion");
+        build_segments(s, prepared ? s->prepared_points.data() : s->points.data(), strip_on ? &s->strip_ids : nullptr);
+        seg_laps.lap("segment arrays");
         s->segments_key = segments_key;
         s->upload_serial++;
     }
@@ -1176,7 +1229,7 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                              effective_view_box.min_y, effective_view_box.max_x, effective_view_box.max_y};
         memcpy(bits, f, sizeof(bits));
         for (uint32_t v : bits) batch_key = mix_key(batch_key, v);
-        if (prepared) batch_key = mix_key(batch_key, segments_key);
+        if (prepared || strip_on) batch_key = mix_key(batch_key, segments_key);
         if (batch_key == 0) batch_key = 1;
     }
     uint32_t tile_count = s->built_tile_count, segment_count = s->built_segment_count;
@@ -1262,11 +1315,15 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
             uint32_t pad[10]; // one cache line per chunk
         };
         s->path_tile_rects.resize(n_paths);
-        const size_t chunks = pf::chunk_count(n_paths, 4096);
+        // (a strip build visits only the paths that reach the strip: `items` of them, ids in strip_ids)
+        const uint32_t *ids = strip_on ? s->strip_ids.data() : nullptr;
+        const size_t items = strip_on ? s->strip_ids.size() : n_paths;
+        const size_t chunks = pf::chunk_count(items, 4096);
         std::vector<ChunkSums> sums(chunks + 1);
-        pf::parallel_chunks(n_paths, chunks, [&](size_t chunk, size_t begin, size_t end) {
+        pf::parallel_chunks(items, chunks, [&](size_t chunk, size_t begin, size_t end) {
             ChunkSums sum;
-            for (size_t i = begin; i < end; i++) {
+            for (size_t k = begin; k < end; k++) {
+                const size_t i = ids ? ids[k] : k;
                 const Path &p = s->draw_paths[i];
                 if (p.blend_mode != PF_BLEND_MODE_SRC_OVER) unsupported.store(2, std::memory_order_relaxed);
                 PFRectI tile_rect{{0, 0}, {0, 0}};
@@ -1321,10 +1378,11 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         s->dice_metadata.resize(kept);
         s->tile_path_info.resize(kept);
         // Pass 2 (parallel, same chunks): the records.
-        pf::parallel_chunks(n_paths, chunks, [&](size_t chunk, size_t begin, size_t end) {
+        pf::parallel_chunks(items, chunks, [&](size_t chunk, size_t begin, size_t end) {
             uint32_t bi = sums[chunk].kept, tile_off = sums[chunk].tiles, col_off = sums[chunk].columns,
                      seg_off = sums[chunk].segments;
-            for (size_t i = begin; i < end; i++) {
+            for (size_t k = begin; k < end; k++) {
+                const size_t i = ids ? ids[k] : k;
                 const PFRectI &tile_rect = s->path_tile_rects[i];
                 if (tile_rect.origin.x > tile_rect.lower_right.x) continue;
                 const Path &p = s->draw_paths[i];
@@ -1418,6 +1476,17 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
     SEND(finish);
 #undef SEND
     return PF_CUDA_OK;
+}
+
+// PFSceneBuild for a renderer that owns the tile rows [tile_y0, tile_y1) of the frame (PFCudaRendererSetStrip): paths
+// without a tile in those rows are left out of the segment arrays and of the batch. PFSceneBuildAndRenderCuda does this
+// by itself with the renderer's strip.
+PFCudaStatus PFSceneBuildForStrip(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState *sink, PFRenderCommandListenerFn listener,
+                                  void *userdata, int32_t tile_y0, int32_t tile_y1) {
+    pf::g_scene_strip[0] = tile_y0, pf::g_scene_strip[1] = tile_y1;
+    const PFCudaStatus st = PFSceneBuild(s, opts, sink, listener, userdata);
+    pf::g_scene_strip[0] = pf::g_scene_strip[1] = 0;
+    return st;
 }
 
 } // extern "C"

@@ -331,3 +331,84 @@ def test_display_list_with_a_render_target_becomes_the_reference_command_order()
     bad = api.Scene()
     bad.pop_render_target()
     assert L.lib().PFSceneBuild(bad._h, api.BuildOptions()._h, C.byref(L.PFSceneSinkState(0, 0, 0)), fn, None) == L.PF_CUDA_ERROR_PROTOCOL
+
+
+def collect_strip(scene, options, strip):
+    """collect() for a renderer that owns the tile rows `strip` (PFSceneBuildForStrip)."""
+    out = []
+
+    def listener(cmd):
+        rec = {"kind": L.COMMAND_NAMES[cmd.kind]}
+        if cmd.kind == L.PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11:
+            ds = cmd.u.upload_scene_d3d11.draw_segments
+            rec["point_count"], rec["index_count"] = int(ds.point_count), int(ds.index_count)
+            rec["indices"] = np.ctypeslib.as_array(C.cast(ds.indices, C.POINTER(C.c_uint32)), (ds.index_count, 2)).copy()
+            rec["points"] = np.ctypeslib.as_array(C.cast(ds.points, C.POINTER(C.c_float)), (ds.point_count, 2)).copy()
+        elif cmd.kind == L.PF_RENDER_COMMAND_DRAW_TILES_D3D11:
+            b = cmd.u.draw_tiles_d3d11.tile_batch_data
+            pm = C.cast(b.prepare_info.propagate_metadata, C.POINTER(L.PFPropagateMetadataD3D11))
+            dm = C.cast(b.prepare_info.dice_metadata, C.POINTER(L.PFDiceMetadataD3D11))
+            rec.update(path_count=int(b.path_count), segment_count=int(b.segment_count), content_key=int(b.content_key))
+            rec["rects"] = [(pm[i].tile_rect.origin.x, pm[i].tile_rect.origin.y, pm[i].tile_rect.lower_right.x,
+                             pm[i].tile_rect.lower_right.y) for i in range(b.path_count)]
+            rec["global_path_ids"] = [int(dm[i].global_path_id) for i in range(b.path_count)]
+            rec["first_global_segment"] = [int(dm[i].first_global_segment_index) for i in range(b.path_count)]
+            rec["first_batch_segment"] = [int(dm[i].first_batch_segment_index) for i in range(b.path_count)]
+        out.append(rec)
+
+    scene.build(options, listener, None, strip=strip)
+    return out
+
+
+def test_build_for_a_strip_keeps_only_the_paths_that_reach_it():
+    """Multi-GPU host side: a rank builds segments and records only for the paths with a tile in its rows; ids stay
+    global; the strips together cover exactly the paths of the whole build; the kept paths' segments are the same
+    points in the same order."""
+    flat = scenes.random_paths(600, 512, 21, r_min=4.0, r_max=40.0)
+    options = api.BuildOptions(transform=api.Transform2F(0.9, 0.1, -0.05, 1.1, 6.0, -3.0))
+    whole = collect_strip(api.Scene.from_flat(flat), options, None)
+    whole_draw = next(r for r in whole if r["kind"] == "DrawTilesD3D11")
+    whole_up = next(r for r in whole if r["kind"] == "UploadSceneD3D11")
+    rect_of = dict(zip(whole_draw["global_path_ids"], whole_draw["rects"]))
+    rows = 512 // 16
+    seen = set()
+    keys = set()
+    for y0, y1 in ((0, 11), (11, 22), (22, rows)):
+        scene = api.Scene.from_flat(flat)
+        got = collect_strip(scene, options, (y0, y1))
+        draw = next(r for r in got if r["kind"] == "DrawTilesD3D11")
+        up = next(r for r in got if r["kind"] == "UploadSceneD3D11")
+        want = [pid for pid, r in rect_of.items() if r[1] < y1 and r[3] > y0]
+        assert draw["global_path_ids"] == want
+        assert draw["rects"] == [rect_of[pid] for pid in want]  # full rects: the renderer restricts them to its rows
+        # only the kept paths' segments were copied, contiguously and in path order
+        assert up["index_count"] == draw["segment_count"] < len(whole_up["indices"])
+        assert draw["first_batch_segment"] == draw["first_global_segment"]
+        # ... and they are the whole build's segments of those paths: same points behind the same flags
+        w_first = dict(zip(whole_draw["global_path_ids"], whole_draw["first_global_segment"]))
+        w_order = whole_draw["global_path_ids"]
+        for k, pid in enumerate(want[:40]):
+            a0 = draw["first_global_segment"][k]
+            a1 = draw["first_global_segment"][k + 1] if k + 1 < len(want) else up["index_count"]
+            j = w_order.index(pid)
+            b0 = w_first[pid]
+            # (the whole build's upload also holds the segments of paths outside the view box: count from the batch)
+            wb = whole_draw["first_batch_segment"]
+            b1 = b0 + ((wb[j + 1] if j + 1 < len(w_order) else whole_draw["segment_count"]) - wb[j])
+            assert a1 - a0 == b1 - b0
+            assert np.array_equal(up["indices"][a0:a1, 1], whole_up["indices"][b0:b1, 1])
+            assert np.array_equal(up["points"][up["indices"][a0:a1, 0]], whole_up["points"][whole_up["indices"][b0:b1, 0]])
+        seen.update(want)
+        keys.add(draw["content_key"])
+        # the same strip again: nothing is rebuilt or re-sent (same content key); another strip re-uploads
+        sink = L.PFSceneSinkState()
+        again = []
+        scene.build(options, lambda c: again.append(L.COMMAND_NAMES[c.kind]), sink, strip=(y0, y1))
+        again2 = []
+        scene.build(options, lambda c: again2.append(L.COMMAND_NAMES[c.kind]), sink, strip=(y0, y1))
+        assert "UploadSceneD3D11" in again and "UploadSceneD3D11" not in again2
+        again3 = []
+        scene.build(options, lambda c: again3.append(L.COMMAND_NAMES[c.kind]), sink, strip=(y0, y1 - 1))
+        assert "UploadSceneD3D11" in again3
+    assert seen == set(whole_draw["global_path_ids"])
+    assert len(keys) == 3 and whole_draw["content_key"] not in keys

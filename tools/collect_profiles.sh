@@ -17,5 +17,5 @@ for scene in random100k tiger4k; do
 done
 ncu --set full --import-source on --clock-control none \
     --metrics lts__t_sectors_op_atom.sum,lts__t_sectors_op_red.sum,lts__t_requests_op_atom.sum,lts__t_requests_op_red.sum,l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum,l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum,lts__t_sector_hit_rate.pct,lts__throughput.avg.pct_of_peak_sustained_elapsed \
-    -k regex:k_bin -s 2 -c 2 -f -o gpurun_out/${TAG}_k_bin_random100k python tools/stage_times.py random100k > gpurun_out/${TAG}_k_bin_random100k.log 2>&1
+    -k regex:k_bin -s 4 -c 4 -f -o gpurun_out/${TAG}_k_bin_random100k python tools/stage_times.py random100k > gpurun_out/${TAG}_k_bin_random100k.log 2>&1
 ls -la gpurun_out | grep ${TAG}_

@@ -106,10 +106,10 @@ if os.path.exists(rep):
     BIN_KEYS = KEYS + ["lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum", "lts__t_requests_op_atom.sum", "lts__t_requests_op_red.sum",
                        "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum", "l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum",
                        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
-    lines = [f"# {tag} — `ncu --set full` of bin: k_bin<1> (count pass) and the launch after it, random100k@8192", "",
+    lines = [f"# {tag} — `ncu --set full` of bin, one steady-state frame of random100k@8192: k_bin<1> + k_bin_long<1> (count pass), k_bin<0> + k_bin_long<0> (emit pass after the z-cull)", "",
              "Every fill and every backdrop change of the count pass is one 32-bit L2 reduction (`RED`, no return value) on the "
              "tile word; the emit pass claims its slot with one `ATOMG` per surviving fill.", ""]
-    for launch in (0, 1):
+    for launch in (0, 1, 2, 3):
         m = raw_metrics(rep, launch)
         if not m:
             continue
