@@ -156,6 +156,7 @@ struct GeneralBatch {
     std::vector<PFDiceMetadataD3D11> dice_metadata;
     std::vector<PFTilePathInfoD3D11> tile_path_info;
     uint32_t tile_count = 0, column_count = 0, segment_count = 0;
+    uint32_t clipped_paths = 0, clipped_tiles = 0; // paths with a clip path in this batch, and their tiles
     bool has_color_texture = false;
     PFTileBatchTexture color_texture{0, 0, 0};
 };
@@ -510,6 +511,97 @@ PFRenderCommand make_command(uint32_t kind) {
     c.kind = kind;
     return c;
 }
+
+// The clip batch of a build (PrepareClipTilesD3D11): fills s->clip_batch_index / clip_propagate_metadata /
+// clip_dice_metadata / clip_tile_path_info and the batch totals.
+PFCudaStatus build_clip_batch(PFScene *s, bool prepared, const Transform &xf, const RectF &view_box) {
+    // Clip batch (add_clip_path_to_batch, builder.rs:1124-1175): the clip paths some draw path uses, in
+    // order of first use, one level deep. The tile rect follows the CPU tiler, which is the parity
+    // target: outline bounds ∩ view box (Tiler::new, tiler.rs:47-50), an empty rect when they miss.
+    s->clip_batch_index.assign(s->clip_paths.size(), PF_PATH_INDEX_NONE);
+    s->clip_propagate_metadata.clear();
+    s->clip_dice_metadata.clear();
+    s->clip_tile_path_info.clear();
+    uint32_t clip_tiles = 0, clip_columns = 0, clip_segments = 0;
+    for (const Path &p : s->draw_paths) {
+        if (p.clip_path == PF_CLIP_PATH_NONE) continue;
+        if (p.clip_path >= s->clip_paths.size()) {
+            pf::set_last_error("draw path refers to a clip path that does not exist");
+            return PF_CUDA_ERROR_INVALID_ARGUMENT;
+        }
+        if (s->clip_batch_index[p.clip_path] != PF_PATH_INDEX_NONE) continue;
+        const Path &cp = s->clip_paths[p.clip_path];
+        if (cp.clip_path != PF_CLIP_PATH_NONE) {
+            pf::set_last_error("nested clip paths are not implemented");
+            return PF_CUDA_ERROR_UNSUPPORTED;
+        }
+        PFRectI tile_rect{{0, 0}, {0, 0}};
+        RectF bounds = prepared ? s->prepared_clip_bounds[p.clip_path]
+                                : xf.is_identity() ? cp.bounds : xf.apply_rect(cp.bounds);
+        RectF clipped;
+        if (cp.first_contour != cp.end_contour && rect_intersection(bounds, view_box, clipped)) {
+            const float k = 1.0f / 16.0f;
+            tile_rect.origin.x = (int32_t)floorf(clipped.min_x * k);
+            tile_rect.origin.y = (int32_t)floorf(clipped.min_y * k);
+            tile_rect.lower_right.x = (int32_t)ceilf(clipped.max_x * k);
+            tile_rect.lower_right.y = (int32_t)ceilf(clipped.max_y * k);
+        }
+        const uint32_t bi = (uint32_t)s->clip_propagate_metadata.size();
+        s->clip_batch_index[p.clip_path] = bi;
+        const uint32_t w = (uint32_t)(tile_rect.lower_right.x - tile_rect.origin.x),
+                       h = (uint32_t)(tile_rect.lower_right.y - tile_rect.origin.y);
+        PFPropagateMetadataD3D11 pm;
+        memset(&pm, 0, sizeof(pm));
+        pm.tile_rect = tile_rect;
+        pm.tile_offset = clip_tiles;
+        pm.path_index = bi;
+        pm.z_write = 0;
+        pm.clip_path_index = PF_PATH_INDEX_NONE;
+        pm.backdrop_offset = clip_columns;
+        s->clip_propagate_metadata.push_back(pm);
+        s->clip_dice_metadata.push_back(
+            PFDiceMetadataD3D11{p.clip_path, s->clip_segment_ranges[2 * p.clip_path], clip_segments, 0});
+        PFTilePathInfoD3D11 tp;
+        tp.tile_min_x = (int16_t)tile_rect.origin.x;
+        tp.tile_min_y = (int16_t)tile_rect.origin.y;
+        tp.tile_max_x = (int16_t)tile_rect.lower_right.x;
+        tp.tile_max_y = (int16_t)tile_rect.lower_right.y;
+        tp.first_tile_index = clip_tiles;
+        tp.color = 0; // TilingPathInfo::Clip: paint 0, ctrl 0 (builder.rs:423-428, tiles.rs:45-61)
+        tp.ctrl = 0;
+        tp.backdrop = 0;
+        s->clip_tile_path_info.push_back(tp);
+        clip_tiles += w * h;
+        clip_columns += w;
+        clip_segments += s->clip_segment_ranges[2 * p.clip_path + 1] - s->clip_segment_ranges[2 * p.clip_path];
+    }
+    s->built_clip_tile_count = clip_tiles;
+    s->built_clip_segment_count = clip_segments;
+    return PF_CUDA_OK;
+}
+
+// Sends the clip batch built by build_clip_batch (clip batches are prepared before the draw batches that use them,
+// builder.rs:1098-1104).
+PFCudaStatus send_clip_batch(PFScene *s, const Transform &xf, PFRenderCommandListenerFn listener, void *userdata) {
+    PFRenderCommand prepare = make_command(PF_RENDER_COMMAND_PREPARE_CLIP_TILES_D3D11);
+    PFTileBatchDataD3D11 &b = prepare.u.prepare_clip_tiles_d3d11.batch;
+    b.batch_id = 0; // clip level 0
+    b.path_count = (uint32_t)s->clip_propagate_metadata.size();
+    b.tile_count = s->built_clip_tile_count;
+    b.segment_count = s->built_clip_segment_count;
+    b.prepare_info.backdrops = nullptr;
+    b.prepare_info.backdrop_count = 0;
+    b.prepare_info.propagate_metadata = s->clip_propagate_metadata.data();
+    b.prepare_info.dice_metadata = s->clip_dice_metadata.data();
+    b.prepare_info.tile_path_info = s->clip_tile_path_info.data();
+    b.prepare_info.transform.matrix = PFMatrix2x2F{xf.m11, xf.m12, xf.m21, xf.m22};
+    b.prepare_info.transform.vector = PFVector2F{xf.tx, xf.ty};
+    b.path_source = PF_PATH_SOURCE_CLIP;
+    b.has_clipped_path_info = 0;
+    b.content_key = 0;
+    return listener(&prepare, userdata);
+}
+
 
 } // namespace
 
@@ -1067,8 +1159,21 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         for (const DisplayItem &item : s->display_list) n_batches += item.kind == DisplayItem::DRAW_PATHS ? (item.b - item.a) : 0;
         s->general_batches.reserve(n_batches + 1); // (upper bound: pointers into the vector stay valid)
         uint32_t next_batch_id = 32; // MAX_CLIP_BATCHES
+        // Clip paths (one level, outside render targets): the clip batch is built once and prepared before the first
+        // draw batch that uses it, as in the single-batch build below.
+        bool any_clip = false, clip_batch_sent = false;
+        for (const Path &dp : s->draw_paths) any_clip |= dp.clip_path != PF_CLIP_PATH_NONE;
+        if (any_clip) {
+            st = build_clip_batch(s, prepared, gxf, s->view_box);
+            if (st != PF_CUDA_OK) return st;
+        }
         auto send_batch = [&](GeneralBatch &gb) -> PFCudaStatus {
             if (gb.propagate_metadata.empty()) return PF_CUDA_OK;
+            if (gb.clipped_paths && !clip_batch_sent) {
+                const PFCudaStatus clip_status = send_clip_batch(s, gxf, listener, userdata);
+                if (clip_status != PF_CUDA_OK) return clip_status;
+                clip_batch_sent = true;
+            }
             PFRenderCommand draw = make_command(PF_RENDER_COMMAND_DRAW_TILES_D3D11);
             PFTileBatchDataD3D11 &b = draw.u.draw_tiles_d3d11.tile_batch_data;
             b.batch_id = next_batch_id++;
@@ -1083,7 +1188,8 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
             b.prepare_info.transform.matrix = PFMatrix2x2F{gxf.m11, gxf.m12, gxf.m21, gxf.m22};
             b.prepare_info.transform.vector = PFVector2F{gxf.tx, gxf.ty};
             b.path_source = PF_PATH_SOURCE_DRAW;
-            b.has_clipped_path_info = 0;
+            b.has_clipped_path_info = gb.clipped_paths ? 1 : 0;
+            b.clipped_path_info = PFClippedPathInfo{0, gb.clipped_paths, gb.clipped_tiles};
             b.content_key = 0;
             draw.u.draw_tiles_d3d11.has_color_texture = gb.has_color_texture ? 1 : 0;
             draw.u.draw_tiles_d3d11.color_texture = gb.color_texture;
@@ -1119,8 +1225,8 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                     pf::set_last_error("destructive blend modes (Clear, Copy, SrcIn, DestIn, SrcOut, DestAtop) are not implemented");
                     return PF_CUDA_ERROR_UNSUPPORTED;
                 }
-                if (p.clip_path != PF_CLIP_PATH_NONE) {
-                    pf::set_last_error("clip paths in a scene with render targets are not implemented");
+                if (p.clip_path != PF_CLIP_PATH_NONE && nesting > 0) {
+                    pf::set_last_error("clipped paths inside a render target are not implemented");
                     return PF_CUDA_ERROR_UNSUPPORTED;
                 }
                 // prepare_draw_path_for_gpu_binning (builder.rs:1058-1095)
@@ -1177,8 +1283,9 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                 pm.tile_offset = gb->tile_count;
                 pm.path_index = bi;
                 pm.z_write = occludes ? 1 : 0;
-                pm.clip_path_index = PF_PATH_INDEX_NONE;
+                pm.clip_path_index = p.clip_path == PF_CLIP_PATH_NONE ? PF_PATH_INDEX_NONE : s->clip_batch_index[p.clip_path];
                 pm.backdrop_offset = gb->column_count;
+                if (p.clip_path != PF_CLIP_PATH_NONE) gb->clipped_paths++, gb->clipped_tiles += w * h;
                 gb->propagate_metadata.push_back(pm);
                 gb->dice_metadata.push_back(PFDiceMetadataD3D11{i, s->draw_segment_ranges[2 * i], gb->segment_count, 0});
                 PFTilePathInfoD3D11 tp;
@@ -1242,68 +1349,10 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
     if (rebuild) {
         const size_t n_paths = s->draw_paths.size();
         std::atomic<int> unsupported{0}; // 2: a blend mode other than SrcOver
-        // Clip batch (add_clip_path_to_batch, builder.rs:1124-1175): the clip paths some draw path uses, in
-        // order of first use, one level deep. The tile rect follows the CPU tiler, which is the parity
-        // target: outline bounds ∩ view box (Tiler::new, tiler.rs:47-50), an empty rect when they miss.
-        s->clip_batch_index.assign(s->clip_paths.size(), PF_PATH_INDEX_NONE);
-        s->clip_propagate_metadata.clear();
-        s->clip_dice_metadata.clear();
-        s->clip_tile_path_info.clear();
-        uint32_t clip_tiles = 0, clip_columns = 0, clip_segments = 0;
-        for (const Path &p : s->draw_paths) {
-            if (p.clip_path == PF_CLIP_PATH_NONE) continue;
-            if (p.clip_path >= s->clip_paths.size()) {
-                pf::set_last_error("draw path refers to a clip path that does not exist");
-                return PF_CUDA_ERROR_INVALID_ARGUMENT;
-            }
-            if (s->clip_batch_index[p.clip_path] != PF_PATH_INDEX_NONE) continue;
-            const Path &cp = s->clip_paths[p.clip_path];
-            if (cp.clip_path != PF_CLIP_PATH_NONE) {
-                pf::set_last_error("nested clip paths are not implemented");
-                return PF_CUDA_ERROR_UNSUPPORTED;
-            }
-            PFRectI tile_rect{{0, 0}, {0, 0}};
-            RectF bounds = prepared ? s->prepared_clip_bounds[p.clip_path]
-                                    : xf.is_identity() ? cp.bounds : xf.apply_rect(cp.bounds);
-            RectF clipped;
-            if (cp.first_contour != cp.end_contour && rect_intersection(bounds, effective_view_box, clipped)) {
-                const float k = 1.0f / 16.0f;
-                tile_rect.origin.x = (int32_t)floorf(clipped.min_x * k);
-                tile_rect.origin.y = (int32_t)floorf(clipped.min_y * k);
-                tile_rect.lower_right.x = (int32_t)ceilf(clipped.max_x * k);
-                tile_rect.lower_right.y = (int32_t)ceilf(clipped.max_y * k);
-            }
-            const uint32_t bi = (uint32_t)s->clip_propagate_metadata.size();
-            s->clip_batch_index[p.clip_path] = bi;
-            const uint32_t w = (uint32_t)(tile_rect.lower_right.x - tile_rect.origin.x),
-                           h = (uint32_t)(tile_rect.lower_right.y - tile_rect.origin.y);
-            PFPropagateMetadataD3D11 pm;
-            memset(&pm, 0, sizeof(pm));
-            pm.tile_rect = tile_rect;
-            pm.tile_offset = clip_tiles;
-            pm.path_index = bi;
-            pm.z_write = 0;
-            pm.clip_path_index = PF_PATH_INDEX_NONE;
-            pm.backdrop_offset = clip_columns;
-            s->clip_propagate_metadata.push_back(pm);
-            s->clip_dice_metadata.push_back(
-                PFDiceMetadataD3D11{p.clip_path, s->clip_segment_ranges[2 * p.clip_path], clip_segments, 0});
-            PFTilePathInfoD3D11 tp;
-            tp.tile_min_x = (int16_t)tile_rect.origin.x;
-            tp.tile_min_y = (int16_t)tile_rect.origin.y;
-            tp.tile_max_x = (int16_t)tile_rect.lower_right.x;
-            tp.tile_max_y = (int16_t)tile_rect.lower_right.y;
-            tp.first_tile_index = clip_tiles;
-            tp.color = 0; // TilingPathInfo::Clip: paint 0, ctrl 0 (builder.rs:423-428, tiles.rs:45-61)
-            tp.ctrl = 0;
-            tp.backdrop = 0;
-            s->clip_tile_path_info.push_back(tp);
-            clip_tiles += w * h;
-            clip_columns += w;
-            clip_segments += s->clip_segment_ranges[2 * p.clip_path + 1] - s->clip_segment_ranges[2 * p.clip_path];
+        {
+            const PFCudaStatus clip_status = build_clip_batch(s, prepared, xf, effective_view_box);
+            if (clip_status != PF_CUDA_OK) return clip_status;
         }
-        s->built_clip_tile_count = clip_tiles;
-        s->built_clip_segment_count = clip_segments;
         // Pass 1 (parallel): prepare_draw_path_for_gpu_binning (builder.rs:1058-1095) — the tile rect
         // of every path; an empty rect marks a path outside the view box (skipped by the builder).
         // Each chunk also sums what its kept paths add to the batch's running offsets, so that pass 2
@@ -1429,24 +1478,8 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
     s->built_segment_count = segment_count;
     const bool has_clips = !s->propagate_metadata.empty() && s->built_clipped_path_count > 0;
     if (has_clips) {
-        // Clip batches are prepared before the draw batches that use them (builder.rs:1098-1104).
-        PFRenderCommand prepare = make_command(PF_RENDER_COMMAND_PREPARE_CLIP_TILES_D3D11);
-        PFTileBatchDataD3D11 &b = prepare.u.prepare_clip_tiles_d3d11.batch;
-        b.batch_id = 0; // clip level 0
-        b.path_count = (uint32_t)s->clip_propagate_metadata.size();
-        b.tile_count = s->built_clip_tile_count;
-        b.segment_count = s->built_clip_segment_count;
-        b.prepare_info.backdrops = nullptr;
-        b.prepare_info.backdrop_count = 0;
-        b.prepare_info.propagate_metadata = s->clip_propagate_metadata.data();
-        b.prepare_info.dice_metadata = s->clip_dice_metadata.data();
-        b.prepare_info.tile_path_info = s->clip_tile_path_info.data();
-        b.prepare_info.transform.matrix = PFMatrix2x2F{xf.m11, xf.m12, xf.m21, xf.m22};
-        b.prepare_info.transform.vector = PFVector2F{xf.tx, xf.ty};
-        b.path_source = PF_PATH_SOURCE_CLIP;
-        b.has_clipped_path_info = 0;
-        b.content_key = 0;
-        SEND(prepare);
+        st = send_clip_batch(s, xf, listener, userdata);
+        if (st != PF_CUDA_OK) return st;
     }
     if (!s->propagate_metadata.empty()) {
         PFRenderCommand draw = make_command(PF_RENDER_COMMAND_DRAW_TILES_D3D11);

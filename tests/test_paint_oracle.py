@@ -198,3 +198,30 @@ def test_blend_modes_get_their_own_metadata_entries():
     with pytest.raises(L.PathfinderCudaError) as e:
         collect(bad)
     assert e.value.status == L.PF_CUDA_ERROR_UNSUPPORTED
+
+
+def test_clip_paths_in_a_display_list_build():
+    """A scene that takes the display-list builder (a gradient) and has clipped paths: one PrepareClipTilesD3D11 before
+    the first draw batch that needs it, clip indices in the batches' records."""
+    scene = api.Scene()
+    scene.set_view_box((0, 0, 64, 64))
+    red = scene.push_paint((255, 0, 0, 255))
+    g = scene.push_gradient([(0.0, (255, 0, 0, 255)), (1.0, (0, 0, 255, 255))], ((0, 0), (64, 0)))
+    clip = scene.push_clip_path(RECT * 0.5 + 10, np.zeros(4, np.uint8), [0, 4])
+    push_rect(scene, red)
+    scene.push_draw_path(RECT, np.zeros(4, np.uint8), [0, 4], g, clip_path_id=clip)
+    scene.push_draw_path(RECT, np.zeros(4, np.uint8), [0, 4], red, clip_path_id=clip)
+    kinds, clipped = [], []
+
+    def listener(cmd):
+        kinds.append(L.COMMAND_NAMES[cmd.kind])
+        if cmd.kind == L.PF_RENDER_COMMAND_DRAW_TILES_D3D11:
+            b = cmd.u.draw_tiles_d3d11.tile_batch_data
+            pm = C.cast(b.prepare_info.propagate_metadata, C.POINTER(L.PFPropagateMetadataD3D11))
+            clipped.append((int(b.has_clipped_path_info), [int(pm[i].clip_path_index) for i in range(b.path_count)]))
+
+    scene.build(api.BuildOptions(), listener)
+    assert kinds.count("PrepareClipTilesD3D11") == 1
+    assert kinds.index("PrepareClipTilesD3D11") < kinds.index("DrawTilesD3D11")
+    none = 0xFFFFFFFF
+    assert clipped == [(1, [none, 0, 0])]

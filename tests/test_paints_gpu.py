@@ -249,3 +249,44 @@ def test_destructive_blend_modes_are_refused():
         scene.build_and_render(r, api.BuildOptions())
     assert e.value.status == L.PF_CUDA_ERROR_UNSUPPORTED
     r.close()
+
+
+def clipped_polygon(points, clip_points, view=SIZE):
+    b = SceneBuilderPy((0, 0, view, view))
+    b.move_to(*clip_points[0])
+    for p in clip_points[1:]:
+        b.line_to(*p)
+    b.close()
+    clip = b.end_clip_path()
+    b.move_to(*points[0])
+    for p in points[1:]:
+        b.line_to(*p)
+    b.close()
+    b.end_path((255, 255, 255, 255), clip=clip)
+    return b.finish("clipped polygon")
+
+
+@pytest.mark.parametrize("mode", ["src_over", "multiply"])
+def test_clipped_path_with_a_gradient(area_lut, mode):
+    """f1 x f4: a clip path on a path with a textured paint (and a blend mode), in a scene with a display-list build."""
+    points, clip_points = blob(128, 128, 100, wobble=0.15), blob(150, 120, 70, wobble=0.3, phase=1.0)
+    under = under_scene()
+    push, color = gradient_paint(STOPS, ((60.0, 40.0), (190.0, 200.0)), 0)
+    scene = api.Scene()
+    scene.set_view_box((0.0, 0.0, float(SIZE), float(SIZE)))
+    scene.push_flat(under)
+    cp = np.asarray(clip_points, np.float32)
+    clip_id = scene.push_clip_path(cp, np.zeros(len(cp), np.uint8), np.asarray([0, len(cp)], np.uint32))
+    pts = np.asarray(points, np.float32)
+    scene.push_draw_path(pts, np.zeros(len(pts), np.uint8), np.asarray([0, len(pts)], np.uint32), push(scene),
+                         blend_mode=api.BLEND_MODES[mode], clip_path_id=clip_id)
+    r = api.CudaRenderer((SIZE, SIZE), background_color=WHITE)
+    scene.build_and_render(r, api.BuildOptions())
+    img = r.read_pixels()
+    r.close()
+    _, dest = H.oracle_build(under, None).render(area_lut, SIZE, SIZE, background=WHITE, want_f32=True)
+    _, f = H.oracle_build(clipped_polygon(points, clip_points), None).render(area_lut, SIZE, SIZE, background=(0.0, 0.0, 0.0, 0.0),
+                                                                            want_f32=True)
+    mask = f[..., 3]
+    assert 0.05 < (mask > 0.5).mean() < (mask_of(points, area_lut) > 0.5).mean() - 0.05  # the clip removes a good part
+    check(img, P.blend(dest, color(SIZE, SIZE), mask, mode))
