@@ -42,6 +42,9 @@ namespace {
 #ifndef PF_SIMPLE_STORE
 #define PF_SIMPLE_STORE 1
 #endif
+#ifndef PF_QUEUE_HDR
+#define PF_QUEUE_HDR 1 // queued tiles carry their list header
+#endif
 
 constexpr int TILE_WARPS = PF_TILE_WARPS;
 #ifndef PF_ENTRY_CAP
@@ -129,6 +132,35 @@ __device__ __forceinline__ float4 unpack_rgba8(uint32_t v) {
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Column-independent part of computeCoverage for one fill, computed once by the lane that loaded it.
+struct __align__(16) FillParams {
+    float lx, rx;   // x of the left / right end point, tile space [0, 16]
+    float ly05;     // y of the left end point minus 0.5 (the centre of pixel row 0)
+    float dy;       // right.y - left.y
+    float inv;      // 1 / (right.x - left.x)
+    float slope16;  // |dy / dx| / 16: the LUT's second coordinate per unit of window width
+    float sign;     // sign of dX = window(from).x - window(to).x: -1 when `from` is the left end
+    float pad;
+};
+
+__device__ __forceinline__ FillParams fill_params(uint2 fill) {
+    const float s = 1.0f / 256.0f;
+    const float fx = (float)(fill.x & 0xffffu) * s, fy = (float)(fill.x >> 16) * s;
+    const float tx = (float)(fill.y & 0xffffu) * s, ty = (float)(fill.y >> 16) * s;
+    const bool from_left = fx < tx;
+    FillParams p;
+    p.lx = from_left ? fx : tx;
+    p.rx = from_left ? tx : fx;
+    const float ly = from_left ? fy : ty, ry = from_left ? ty : fy;
+    p.ly05 = ly - 0.5f;
+    p.dy = ry - ly;
+    p.inv = __fdividef(1.0f, p.rx - p.lx); // from_x != to_x (degenerate fills are culled by add_fill)
+    p.slope16 = fabsf(p.dy * p.inv) * (1.0f / 16.0f);
+    p.sign = from_left ? -1.0f : 1.0f;
+    p.pad = 0.0f;
+    return p;
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_tile_solid — single-colour tiles, one lane per framebuffer tile; queues the others.
 // ---------------------------------------------------------------------------------------------
@@ -166,7 +198,13 @@ __global__ void __launch_bounds__(128, PF_SOLID_MIN_BLOCKS) k_tile_solid(Composi
         const int leader = __ffs(queued_mask) - 1;
         if (lane == leader) base = atomicAdd(a.queue_count, (uint32_t)__popc(queued_mask));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (queued) a.queue[base + (uint32_t)__popc(queued_mask & ((1u << lane) - 1u))] = (tile_row << 16) | (uint32_t)col;
+        if (queued) {
+            const uint32_t slot = base + (uint32_t)__popc(queued_mask & ((1u << lane) - 1u));
+            a.queue[slot] = (tile_row << 16) | (uint32_t)col;
+#if PF_QUEUE_HDR
+            a.queue_hdr[slot] = make_uint2(n, e0);
+#endif
+        }
     }
     // LOAD_ACTION_LOAD: a tile without entries keeps what the previous batches drew.
     const bool paints = in_row && !queued && !(LOAD_DEST && n == 0);
@@ -243,41 +281,21 @@ __global__ void __launch_bounds__(128, PF_SOLID_MIN_BLOCKS) k_tile_solid(Composi
 // k_tile_alpha — tiles with fills (or clip masks, or deep lists), one warp per tile.
 // ---------------------------------------------------------------------------------------------
 
-// Column-independent part of computeCoverage for one fill, computed once by the lane that loaded it.
-struct __align__(16) FillParams {
-    float lx, rx;   // x of the left / right end point, tile space [0, 16]
-    float ly05;     // y of the left end point minus 0.5 (the centre of pixel row 0)
-    float dy;       // right.y - left.y
-    float inv;      // 1 / (right.x - left.x)
-    float slope16;  // |dy / dx| / 16: the LUT's second coordinate per unit of window width
-    float sign;     // sign of dX = window(from).x - window(to).x: -1 when `from` is the left end
-    float pad;
-};
-
-__device__ __forceinline__ FillParams fill_params(uint2 fill) {
-    const float s = 1.0f / 256.0f;
-    const float fx = (float)(fill.x & 0xffffu) * s, fy = (float)(fill.x >> 16) * s;
-    const float tx = (float)(fill.y & 0xffffu) * s, ty = (float)(fill.y >> 16) * s;
-    const bool from_left = fx < tx;
-    FillParams p;
-    p.lx = from_left ? fx : tx;
-    p.rx = from_left ? tx : fx;
-    const float ly = from_left ? fy : ty, ry = from_left ? ty : fy;
-    p.ly05 = ly - 0.5f;
-    p.dy = ry - ly;
-    p.inv = __fdividef(1.0f, p.rx - p.lx); // from_x != to_x (degenerate fills are culled by add_fill)
-    p.slope16 = fabsf(p.dy * p.inv) * (1.0f / 16.0f);
-    p.sign = from_left ? -1.0f : 1.0f;
-    p.pad = 0.0f;
-    return p;
-}
-
 // computeCoverage (shaders/fill_area.inc.glsl:11-27) of one fill for pixel column `xf` (its left edge) and
 // the two vertically adjacent 4-row strips this lane owns (u_off: LUT coordinate offset of the first).
 // Branch-free: a column outside the fill's x range has dX = 0 and adds exactly COV_MAGIC, like the
 // reference's `texture(...) * dX`, so every fill counts as one contribution on every lane.
+// (Measured and dropped: summing in floats with a pinned exponent and round-down FMAs — exact and order-independent
+// too, four FFMA2.RM or eight FFMA.RM per fill and no integer adds — is slower on sm_100a: 0.237 against 0.222 ms.)
+struct CovAcc {
+    uint32_t v[8];
+};
+__device__ __forceinline__ void acc_reset(CovAcc &acc) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc.v[k] = 0u;
+}
 __device__ __forceinline__ void accumulate_fill(const float4 p0, const float4 p1, float xf, float u_off,
-                                                cudaTextureObject_t lut, uint32_t (&acc)[8]) {
+                                                cudaTextureObject_t lut, CovAcc &acc) {
     // p0 = {lx, rx, ly05, dy}, p1 = {inv, slope16, sign, -}
     const float l0 = p0.x - xf;                             // left.x relative to the column's left edge
     const float wl = __saturatef(l0), wr = __saturatef(p0.y - xf); // window = clamp(x, -0.5, 0.5) + 0.5
@@ -289,32 +307,22 @@ __device__ __forceinline__ void accumulate_fill(const float4 p0, const float4 p1
     const float u = fmaf(y, 1.0f / 16.0f, u_off);           // (y + 8) / 16 for the first strip
     const float4 a0 = tex2D<float4>(lut, u, v);
     const float4 a1 = tex2D<float4>(lut, u - 0.25f, v);     // the strip 4 rows lower sees the segment 4 px higher
-#if PF_FILL_FFMA2
-    // two packed FMAs per strip: the texture unit returns the four rows in consecutive registers
+    // two packed FMAs per strip (the texture unit returns the four rows in consecutive registers): adding 1.5 * 2^8
+    // pins the product's exponent, so its mantissa is the contribution in units of 2^-15 — summed as integers
     const f32x2 dd = pack2(dX, dX), magic = pack2(COV_MAGIC, COV_MAGIC);
     float c0, c1, c2, c3, c4, c5, c6, c7;
     unpack2(fma2(pack2(a0.x, a0.y), dd, magic), c0, c1);
     unpack2(fma2(pack2(a0.z, a0.w), dd, magic), c2, c3);
     unpack2(fma2(pack2(a1.x, a1.y), dd, magic), c4, c5);
     unpack2(fma2(pack2(a1.z, a1.w), dd, magic), c6, c7);
-    acc[0] += __float_as_uint(c0);
-    acc[1] += __float_as_uint(c1);
-    acc[2] += __float_as_uint(c2);
-    acc[3] += __float_as_uint(c3);
-    acc[4] += __float_as_uint(c4);
-    acc[5] += __float_as_uint(c5);
-    acc[6] += __float_as_uint(c6);
-    acc[7] += __float_as_uint(c7);
-#else
-    acc[0] += __float_as_uint(fmaf(a0.x, dX, COV_MAGIC));
-    acc[1] += __float_as_uint(fmaf(a0.y, dX, COV_MAGIC));
-    acc[2] += __float_as_uint(fmaf(a0.z, dX, COV_MAGIC));
-    acc[3] += __float_as_uint(fmaf(a0.w, dX, COV_MAGIC));
-    acc[4] += __float_as_uint(fmaf(a1.x, dX, COV_MAGIC));
-    acc[5] += __float_as_uint(fmaf(a1.y, dX, COV_MAGIC));
-    acc[6] += __float_as_uint(fmaf(a1.z, dX, COV_MAGIC));
-    acc[7] += __float_as_uint(fmaf(a1.w, dX, COV_MAGIC));
-#endif
+    acc.v[0] += __float_as_uint(c0);
+    acc.v[1] += __float_as_uint(c1);
+    acc.v[2] += __float_as_uint(c2);
+    acc.v[3] += __float_as_uint(c3);
+    acc.v[4] += __float_as_uint(c4);
+    acc.v[5] += __float_as_uint(c5);
+    acc.v[6] += __float_as_uint(c6);
+    acc.v[7] += __float_as_uint(c7);
 }
 
 template <bool GENERAL>
@@ -329,12 +337,15 @@ struct __align__(16) TileWarpShared {
     uint2 clip[GENERAL ? ENTRY_CAP : 1]; // {clip fill end, clip tile word} (batches with clipped paths)
 };
 
-// Sums the coverage contributions of fills [begin, end) into acc (integer units, order-independent).
+// Coverage of the fills [end - count, end) plus the backdrop -> cov.
 template <bool GENERAL>
-__device__ __forceinline__ void fill_loop(TileWarpShared<GENERAL> &sh, const PackedFill *__restrict__ fills,
-                                          uint32_t begin, uint32_t end, float xf, float u_off,
-                                          cudaTextureObject_t lut, int lane, uint32_t (&acc)[8]) {
-    for (uint32_t f0 = begin; f0 < end; f0 += 32) {
+__device__ __forceinline__ void fill_coverage(TileWarpShared<GENERAL> &sh, const PackedFill *__restrict__ fills,
+                                              uint32_t end, uint32_t count,
+                                              float backdrop, float xf, float u_off, cudaTextureObject_t lut, int lane,
+                                              float (&cov)[8]) {
+    CovAcc acc;
+    acc_reset(acc);
+    for (uint32_t f0 = end - count; f0 < end; f0 += 32) {
         const uint32_t m = min(32u, end - f0);
         if ((uint32_t)lane < m) {
             const FillParams p = fill_params(__ldg(fills + f0 + lane));
@@ -346,20 +357,17 @@ __device__ __forceinline__ void fill_loop(TileWarpShared<GENERAL> &sh, const Pac
         for (uint32_t j = 0; j < m; j++) accumulate_fill(sh.fill[j][0], sh.fill[j][1], xf, u_off, lut, acc);
         __syncwarp(); // the next batch (or the store staging) overwrites the parameters
     }
-}
-
-// acc -> coverage for `count` contributions. Up to 127 contributions of magnitude <= 2^15 units: |sum| <
-// 2^22, so the signed sum can be read off the mantissa of 1.5 * 2^23 + sum (no I2F on the quarter-rate
-// pipe) and scaled, un-biased (12582912 * 2^-15 = 384) and offset by the backdrop in one FFMA.
-__device__ __forceinline__ void coverage_of(const uint32_t (&acc)[8], uint32_t count, float backdrop, float (&cov)[8]) {
+    // acc -> coverage for `count` contributions. Up to 127 contributions of magnitude <= 2^15 units: |sum| <
+    // 2^22, so the signed sum can be read off the mantissa of 1.5 * 2^23 + sum (no I2F on the quarter-rate
+    // pipe) and scaled, un-biased (12582912 * 2^-15 = 384) and offset by the backdrop in one FFMA.
     if (count <= 127u) {
         const uint32_t bias = 0x4b400000u - count * COV_MAGIC_BITS;
         const float offset = backdrop - 384.0f;
 #pragma unroll
-        for (int k = 0; k < 8; k++) cov[k] = fmaf(__uint_as_float(acc[k] + bias), COV_SCALE, offset);
+        for (int k = 0; k < 8; k++) cov[k] = fmaf(__uint_as_float(acc.v[k] + bias), COV_SCALE, offset);
     } else {
 #pragma unroll
-        for (int k = 0; k < 8; k++) cov[k] = (float)(int32_t)(acc[k] - count * COV_MAGIC_BITS) * COV_SCALE + backdrop;
+        for (int k = 0; k < 8; k++) cov[k] = (float)(int32_t)(acc.v[k] - count * COV_MAGIC_BITS) * COV_SCALE + backdrop;
     }
 }
 
@@ -645,9 +653,14 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? 4 : PF_TILE_MIN_BLO
         work = count = start = 0;
         if (k < n_queue) {
             work = __ldg(a.queue + k);
+#if PF_QUEUE_HDR
+            const uint2 hdr = __ldg(a.queue_hdr + k);
+            count = hdr.x, start = hdr.y;
+#else
             const int64_t index = (int64_t)(work >> 16) * fb_w + (int64_t)(work & 0xffffu) + fb_base;
             count = __ldg(a.fb_count + index);
             start = __ldg(a.fb_start + index);
+#endif
         }
     };
     uint32_t pending = claim();
@@ -675,7 +688,10 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? 4 : PF_TILE_MIN_BLO
                 raw = __ldg(reinterpret_cast<const uint4 *>(a.entries + e0 + lane));
                 paint = __ldg(&a.entries[e0 + lane].color);
 #if PF_PREFETCH
-                if (raw.y & 0x00ffffffu) prefetch_l2(a.fills + (raw.x - (raw.y & 0x00ffffffu)));
+                if (raw.y & 0x00ffffffu) {
+                    const uint32_t first = raw.x - (raw.y & 0x00ffffffu);
+                    prefetch_l2(a.fills + first);
+                }
 #endif
             }
             uint32_t rank = 0;
@@ -755,9 +771,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? 4 : PF_TILE_MIN_BLO
 #pragma unroll
                 for (int k = 0; k < 8; k++) cov[k] = m;
             } else if (!clipped) {
-                uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                fill_loop<GENERAL>(sh, a.fills, fill_end - count, fill_end, xf, u_off, a.area_lut, lane, acc);
-                coverage_of(acc, count, backdrop, cov);
+                fill_coverage<GENERAL>(sh, a.fills, fill_end, count, backdrop, xf, u_off, a.area_lut, lane, cov);
                 rule_of(cov, ctrl);
             } else {
                 // A tile of a clipped path that meets an alpha tile of its clip path (tiler.rs:114-156). D3D9
@@ -767,14 +781,10 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? 4 : PF_TILE_MIN_BLO
                 const bool replace = (raw.z & ENTRY_CLIP_REPLACE) != 0;
                 const uint32_t clip_count = clip_entry.y & 0x00ffffffu;
                 const float clip_backdrop = (float)(int)(int8_t)(clip_entry.y >> 24);
-                uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                fill_loop<GENERAL>(sh, a.clip_fills, clip_entry.x - clip_count, clip_entry.x, xf, u_off, a.area_lut, lane, acc);
-                coverage_of(acc, clip_count, clip_backdrop, cov);
+                fill_coverage<GENERAL>(sh, a.clip_fills, clip_entry.x, clip_count, clip_backdrop, xf, u_off, a.area_lut, lane, cov);
                 if (!replace) {
-                    uint32_t acc_draw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                     float cov_draw[8];
-                    fill_loop<GENERAL>(sh, a.fills, fill_end - count, fill_end, xf, u_off, a.area_lut, lane, acc_draw);
-                    coverage_of(acc_draw, count, backdrop, cov_draw);
+                    fill_coverage<GENERAL>(sh, a.fills, fill_end, count, backdrop, xf, u_off, a.area_lut, lane, cov_draw);
 #pragma unroll
                     for (int k = 0; k < 8; k++) cov[k] = fminf(fabsf(cov_draw[k]), fabsf(cov[k]));
                 }
@@ -926,7 +936,9 @@ Residency &residency_of_current_device() {
 
 } // namespace
 
-int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
+int launch_composite(const CompositeArgs &args, cudaStream_t stream) {
+    const CompositeArgs &a = args;
+    const bool has_clip = a.entry_clip != nullptr || a.paint_textures != nullptr; // the GENERAL kernel variants
     const int fb_w = a.fb.max_x - a.fb.min_x;
     const int rows = a.tile_y1 - a.tile_y0;
     if (fb_w <= 0 || rows <= 0) return 0;
@@ -944,7 +956,6 @@ int launch_composite(const CompositeArgs &a, cudaStream_t stream) {
 
     // One resident wave of persistent warps, or fewer when the whole frame has fewer tiles.
     const Residency &res = residency_of_current_device();
-    const bool has_clip = a.entry_clip != nullptr || a.paint_textures != nullptr; // the GENERAL kernel variants
     const uint64_t n_work = (uint64_t)fb_w * (uint64_t)rows;
     const uint64_t want = (n_work + TILE_WARPS - 1) / TILE_WARPS;
     const uint64_t resident = (uint64_t)res.sm_count * (uint64_t)res.blocks[a.load_dest ? 1 : 0][has_clip ? 1 : 0];

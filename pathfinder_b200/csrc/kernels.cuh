@@ -200,6 +200,7 @@ struct CompositeArgs {
     uint32_t *queue;           // framebuffer tiles (row << 16 | column within the strip) that need per-pixel work,
     uint32_t *queue_count;     //   appended by k_tile_solid, consumed by k_tile_alpha; zeroed by the caller
     const PackedFill *fills;
+    uint2 *queue_hdr;          // {list length, list start} of every queued tile, beside `queue` (saves a dependent load)
     cudaTextureObject_t area_lut;
     FbRect fb;
     int32_t tile_y0, tile_y1;  // tile rows composited by this renderer (strip)

@@ -237,6 +237,7 @@ struct PFCudaRenderer {
     DeviceBuffer<EmitFill> fills_emit;
     DeviceBuffer<uint32_t> fb_start;
     DeviceBuffer<uint32_t> tile_queue; // framebuffer tiles that need per-pixel compositing (k_tile_solid -> k_tile_alpha)
+    DeviceBuffer<uint2> tile_queue_hdr; // their list headers, same index
     DeviceBuffer<TileEntry> entries;
     PinnedBuffer<uint32_t> counters_host;
     ScanScratch scan_scratch;
@@ -325,6 +326,7 @@ void setup_tracking(PFCudaRenderer *r) {
     track(r, r->fills_emit);
     track(r, r->fb_start);
     track(r, r->tile_queue);
+    track(r, r->tile_queue_hdr);
     track(r, r->entries);
     track(r, r->scan_scratch.control);
     track(r, r->scan_scratch.status);
@@ -827,6 +829,7 @@ void carve_zeroed(PFCudaRenderer *r, size_t n_paths, size_t n_tiles, size_t n_co
     r->fb_cursor.ptr = p, p += padded(n_fb);
     r->fb_alpha.ptr = p;
     r->tile_queue.ensure(n_fb + 1);
+    r->tile_queue_hdr.ensure(n_fb + 1);
     PF_CUDA_CHECK(cudaMemsetAsync(r->zeroed.ptr, 0, total * sizeof(uint32_t), r->stream));
 }
 
@@ -1045,6 +1048,7 @@ bool run_pipeline(PFCudaRenderer *r, bool sizing, bool clip_pass = false) {
     ca.fb_count = r->fb_count.ptr;
     ca.fb_alpha = r->fb_alpha.ptr;
     ca.queue = r->tile_queue.ptr;
+    ca.queue_hdr = r->tile_queue_hdr.ptr;
     ca.queue_count = r->counters.ptr + 10;
     ca.fills = r->fills.ptr;
     ca.area_lut = r->lut_tex;
@@ -1701,6 +1705,7 @@ PFCudaStatus PFCudaRendererEndScene(PFCudaRendererRef r) {
             ca.fb_count = r->fb_count.ptr;
             ca.fb_alpha = r->fb_alpha.ptr;
             ca.queue = r->tile_queue.ptr;
+            ca.queue_hdr = r->tile_queue_hdr.ptr;
             ca.queue_count = r->counters.ptr + 10;
             ca.fb = fb;
             ca.tile_y0 = r->strip_y1 > r->strip_y0 ? r->strip_y0 : fb.min_y;
