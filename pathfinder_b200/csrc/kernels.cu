@@ -664,12 +664,14 @@ __device__ __forceinline__ void walk_line(float2 from, float2 to, int from_tx, i
     }
 }
 
-// The same walk by a whole warp, for lines that cross many tiles (long straight edges). The walk is serial —
-// t_max is accumulated one rounding at a time — so the kernel takes as long as its longest line: the loop below keeps
-// only what is loop-carried (the two t_max, the tile, the step taken) and what picks the step; lane k remembers the
-// parameters of step k, and the end points of the step (from + v * t, the expression the serial walk evaluates, on the
-// same t: the same bits) and its fills are computed by the 32 lanes in parallel afterwards. Must be called by all 32
-// lanes with identical arguments. Fill order within the line is not preserved (only BIN_EMIT needs it).
+// The same walk by a whole warp, for lines that cross many tiles (long straight edges). The walk is serial — t_max is
+// accumulated one rounding at a time — but what is loop-carried is small: the two t_max, the tile and the step taken.
+// The walk visits at most |dx| + |dy| + 1 tiles; lane k takes the k-th chunk of ceil(that / 32) consecutive tiles. It
+// first replays the steps before its chunk keeping only the loop-carried state (a compare, a select and one add per
+// step: the same operations on the same values as the serial walk, so the same bits), then walks its own tiles in full:
+// end points of a step (from + v * t, the expression the serial walk evaluates, on the same t), fills, backdrop change.
+// A 256-tile edge costs 31 * 8 light steps + 8 full ones instead of 256 full ones. Must be called by all 32 lanes with
+// identical arguments. Fill order within the line is not preserved (only BIN_EMIT needs it).
 template <typename Sink>
 __device__ __forceinline__ void walk_line_warp(float2 from, float2 to, int from_tx, int from_ty, int to_tx, int to_ty,
                                                Sink &sink) {
@@ -680,48 +682,59 @@ __device__ __forceinline__ void walk_line_warp(float2 from, float2 to, int from_
     int tx = from_tx, ty = from_ty, last_step = 0;
     float prev_t = 0.0f;
     bool first = true, more = true;
-    while (more) {
-        float my_prev_t = 0.0f, my_t = 0.0f;
-        int my_tx = 0, my_ty = 0, my_last = 0, my_next = 0;
-        bool my_first = false, have = false;
-        for (int k = 0; k < 32 && more; k++) {
-            int next_step;
-            if (t_max_x < t_max_y)
-                next_step = 1;
-            else if (t_max_x > t_max_y)
-                next_step = 2;
-            else
-                next_step = w.step_x > 0 ? 1 : 2;
-            const float next_t = fminf(next_step == 1 ? t_max_x : t_max_y, 1.0f);
-            if (tx == to_tx && ty == to_ty) next_step = 0;
-            if (k == lane) {
-                my_prev_t = prev_t, my_t = next_t, my_tx = tx, my_ty = ty, my_last = last_step, my_next = next_step;
-                my_first = first, have = true;
-            }
-            if (next_step == 0) {
-                more = false;
-            } else if (next_step == 1) {
-                if (tx == to_tx) more = false;
-                t_max_x += w.t_delta_x;
-                tx += w.step_x;
-            } else {
-                if (ty == to_ty) more = false;
-                t_max_y += w.t_delta_y;
-                ty += w.step_y;
-            }
-            prev_t = next_t;
-            last_step = next_step;
-            first = false;
+    const int chunk = (abs(to_tx - from_tx) + abs(to_ty - from_ty) + 1 + 31) >> 5;
+    const bool tie_x = w.step_x > 0;
+    for (int k = lane * chunk; k > 0 && more; k--) {
+        const bool step_in_x = t_max_x < t_max_y || (!(t_max_x > t_max_y) && tie_x);
+        if (tx == to_tx && ty == to_ty) { // the walk ends before this lane's chunk
+            more = false;
+            break;
         }
-        if (have) {
-            WalkStep st;
-            st.cur = my_first ? from : make_float2(from.x + w.vx * my_prev_t, from.y + w.vy * my_prev_t);
-            st.next = make_float2(from.x + w.vx * my_t, from.y + w.vy * my_t);
-            st.tx = my_tx, st.ty = my_ty, st.last_step = my_last, st.next_step = my_next;
-            walk_emit(st, w.step_x, w.step_y, sink);
+        const float chosen = step_in_x ? t_max_x : t_max_y;
+        if (step_in_x) {
+            if (tx == to_tx) more = false;
+            t_max_x += w.t_delta_x;
+            tx += w.step_x;
+        } else {
+            if (ty == to_ty) more = false;
+            t_max_y += w.t_delta_y;
+            ty += w.step_y;
         }
-        __syncwarp();
+        prev_t = fminf(chosen, 1.0f);
+        last_step = step_in_x ? 1 : 2;
+        first = false;
     }
+    for (int c = 0; c < chunk && more; c++) {
+        int next_step;
+        if (t_max_x < t_max_y)
+            next_step = 1;
+        else if (t_max_x > t_max_y)
+            next_step = 2;
+        else
+            next_step = tie_x ? 1 : 2;
+        const float next_t = fminf(next_step == 1 ? t_max_x : t_max_y, 1.0f);
+        if (tx == to_tx && ty == to_ty) next_step = 0;
+        WalkStep st;
+        st.cur = first ? from : make_float2(from.x + w.vx * prev_t, from.y + w.vy * prev_t);
+        st.next = make_float2(from.x + w.vx * next_t, from.y + w.vy * next_t);
+        st.tx = tx, st.ty = ty, st.last_step = last_step, st.next_step = next_step;
+        walk_emit(st, w.step_x, w.step_y, sink);
+        if (next_step == 0) {
+            more = false;
+        } else if (next_step == 1) {
+            if (tx == to_tx) more = false;
+            t_max_x += w.t_delta_x;
+            tx += w.step_x;
+        } else {
+            if (ty == to_ty) more = false;
+            t_max_y += w.t_delta_y;
+            ty += w.step_y;
+        }
+        prev_t = next_t;
+        last_step = next_step;
+        first = false;
+    }
+    __syncwarp();
 }
 
 constexpr int BIN_LONG_STEPS = 12; // tile crossings from which a line is walked by a whole warp
