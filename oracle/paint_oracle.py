@@ -327,12 +327,22 @@ def composite_rgb(d, s, mode):
     return _hsl_to_rgb(np.stack([pick[0][..., 0], pick[1][..., 1], pick[2][..., 2]], axis=-1))
 
 
-def blend(dest, color, mask, mode="src_over"):
+def blend(dest, color, mask, mode="src_over", drawn=None):
     """One path over the frame. dest: (h, w, 4) premultiplied float32; color: (h, w, 4) or (4,) NOT premultiplied;
-    mask: (h, w) mask alpha. calculateColor (:583-614) + the mode's blend state (blend.rs)."""
-    if mode in DESTRUCTIVE:
-        raise ValueError("destructive blend modes are not built")
+    mask: (h, w) mask alpha. calculateColor (:583-614) + the mode's blend state (blend.rs).
+    drawn: (h, w) bool, the pixels of the tiles the path draws (its tiles with fills or a non-zero backdrop: empty
+    tiles are never drawn, builder.rs:1014-1016). Needed by the destructive modes (effects.rs:222-235), which also
+    change pixels the mask leaves out; for every other mode a pixel with mask 0 keeps its value anyway."""
+    if mode in DESTRUCTIVE and drawn is None:
+        raise ValueError("a destructive blend mode needs the set of drawn tiles")
     dest = np.asarray(dest, np.float32)
+    out = _blend_everywhere(dest, color, mask, mode)
+    if drawn is not None:
+        out = np.where(np.asarray(drawn, bool)[..., None], out, dest).astype(np.float32)
+    return out
+
+
+def _blend_everywhere(dest, color, mask, mode):
     color = np.broadcast_to(np.asarray(color, np.float32), dest.shape)
     sa = (color[..., 3] * np.asarray(mask, np.float32))[..., None]
     d_rgb, da = dest[..., :3], dest[..., 3:4]
@@ -342,8 +352,12 @@ def blend(dest, color, mask, mode="src_over"):
         rgb = sa * (F(1.0) - da) * s_rgb + sa * da * blended + (F(1.0) - sa) * d_rgb
         return np.concatenate([np.clip(rgb, F(0.0), F(1.0)), np.ones_like(sa)], axis=-1).astype(np.float32)  # UNORM target
     one = np.ones_like(sa)
-    sf, df = {"src_over": (one, one - sa), "dest_over": (one - da, one), "dest_out": (0 * one, one - sa),
-              "src_atop": (da, one - sa), "xor": (one - da, one - sa), "lighter": (one, one)}[mode]
+    zero = 0 * one
+    sf, df = {"src_over": (one, one - sa), "dest_over": (one - da, one), "dest_out": (zero, one - sa),
+              "src_atop": (da, one - sa), "xor": (one - da, one - sa), "lighter": (one, one),
+              # the destructive modes (blend.rs:46-53,72-98,117-125; Copy: blending disabled, :144)
+              "clear": (zero, zero), "copy": (one, zero), "src_in": (da, zero), "src_out": (one - da, zero),
+              "dest_in": (zero, sa), "dest_atop": (one - da, sa)}[mode]
     src = np.concatenate([s_rgb * sa, sa], axis=-1)
     out = src * sf + dest * df
     return np.clip(out, F(0.0), F(1.0)).astype(np.float32)  # the render target is UNORM (Lighter adds; a colour matrix can overshoot)

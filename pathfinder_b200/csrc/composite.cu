@@ -42,9 +42,6 @@ namespace {
 #ifndef PF_SIMPLE_STORE
 #define PF_SIMPLE_STORE 1
 #endif
-#ifndef PF_QUEUE_HDR
-#define PF_QUEUE_HDR 1 // queued tiles carry their list header
-#endif
 
 constexpr int TILE_WARPS = PF_TILE_WARPS;
 #ifndef PF_ENTRY_CAP
@@ -201,9 +198,7 @@ __global__ void __launch_bounds__(128, PF_SOLID_MIN_BLOCKS) k_tile_solid(Composi
         if (queued) {
             const uint32_t slot = base + (uint32_t)__popc(queued_mask & ((1u << lane) - 1u));
             a.queue[slot] = (tile_row << 16) | (uint32_t)col;
-#if PF_QUEUE_HDR
-            a.queue_hdr[slot] = make_uint2(n, e0);
-#endif
+            a.queue_hdr[slot] = make_uint2(n, e0); // (saves k_tile_alpha a dependent load per tile)
         }
     }
     // LOAD_ACTION_LOAD: a tile without entries keeps what the previous batches drew.
@@ -541,7 +536,10 @@ __device__ __forceinline__ float4 paint_color(const PaintTexture &p, const Color
     }
     default: c = sample_uv(t, u, v); break;                                // filterNone
     }
-    return make_float4(c.x, c.y, c.z, c.w * p.base.w); // combineColor0, SrcIn: (src.rgb, src.a * dest.a)
+    // combineColor0 (tile_fragment.inc.glsl:81-89; dest = the base colour, src = the filtered texture colour):
+    // SrcIn (src.rgb, src.a * dest.a), DestIn (dest.rgb, src.a * dest.a)
+    if (p.flags & PAINT_COMBINE_DEST_IN) return make_float4(p.base.x, p.base.y, p.base.z, c.w * p.base.w);
+    return make_float4(c.x, c.y, c.z, c.w * p.base.w);
 }
 
 // ---- blend modes. Values of PF_BLEND_MODE_* (include/pf_cuda.h).
@@ -614,6 +612,14 @@ __device__ __forceinline__ float4 blend_pixel(float4 d, float4 c, float m, uint3
     }
     float sf, df; // source / destination factors (the same for colour and alpha in every mode)
     switch (mode) {
+    // (the destructive modes, effects.rs:222-235: what they do to pixels the mask leaves out — sa = 0 — is part of
+    // the mode; a tile the path does not reach is never drawn, builder.rs:1014-1016)
+    case 0: sf = 0.0f, df = 0.0f; break;              // Clear
+    case 1: sf = 1.0f, df = 0.0f; break;              // Copy (blending disabled, blend.rs:144)
+    case 2: sf = d.w, df = 0.0f; break;               // SrcIn
+    case 3: sf = 1.0f - d.w, df = 0.0f; break;        // SrcOut
+    case 6: sf = 0.0f, df = sa; break;                // DestIn
+    case 9: sf = 1.0f - d.w, df = sa; break;          // DestAtop
     case 8: sf = 1.0f - d.w, df = 1.0f; break;        // DestOver
     case 7: sf = 0.0f, df = 1.0f - sa; break;         // DestOut
     case 5: sf = d.w, df = 1.0f - sa; break;          // SrcAtop
@@ -635,7 +641,6 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? 4 : PF_TILE_MIN_BLO
     const int fb_w = a.fb.max_x - a.fb.min_x;
     const uint32_t n_queue = *a.queue_count; // written by k_tile_solid
     if (a.export_alpha_count && blockIdx.x == 0 && threadIdx.x == 0) *a.export_alpha_count = n_queue;
-    const int64_t fb_base = (int64_t)(a.tile_y0 - a.fb.min_y) * fb_w;
     const int x = lane & 15, half = lane >> 4;
     const float xf = (float)x;
     const float u_off = 0.5f - 0.5f * (float)half; // (8 - 8 * half) / 16
@@ -653,14 +658,8 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? 4 : PF_TILE_MIN_BLO
         work = count = start = 0;
         if (k < n_queue) {
             work = __ldg(a.queue + k);
-#if PF_QUEUE_HDR
             const uint2 hdr = __ldg(a.queue_hdr + k);
             count = hdr.x, start = hdr.y;
-#else
-            const int64_t index = (int64_t)(work >> 16) * fb_w + (int64_t)(work & 0xffffu) + fb_base;
-            count = __ldg(a.fb_count + index);
-            start = __ldg(a.fb_start + index);
-#endif
         }
     };
     uint32_t pending = claim();

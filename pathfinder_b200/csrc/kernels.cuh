@@ -141,10 +141,11 @@ constexpr uint32_t ENTRY_HAS_CLIP = 1u << 24, ENTRY_CLIP_REPLACE = 1u << 25, ENT
 // them (gpu/renderer.rs:967-1049) — text: kernel, bg, fg (w = gamma correction); radial gradient: line from + vector,
 // radii + uv origin; blur: direction + support, Gaussian coefficients; colour matrix: its five columns.
 constexpr uint32_t PAINT_HAS_TEXTURE = 1u;
+constexpr uint32_t PAINT_COMBINE_DEST_IN = 2u; // ColorCombineMode::DestIn (else SrcIn)
 struct __align__(16) PaintTexture {
     float m00, m01, m10, m11, tx, ty; // framebuffer position (pixel centre) -> normalised texture coordinate
     uint32_t filter_kind;             // PF_FILTER_*
-    uint32_t flags;                   // PAINT_HAS_TEXTURE
+    uint32_t flags;                   // PAINT_HAS_TEXTURE, PAINT_COMBINE_DEST_IN
     float4 p0, p1, p2, p3, p4;
     float4 base;                      // base colour, rounded through f16, not premultiplied
     uint32_t blend_mode;              // PF_BLEND_MODE_*

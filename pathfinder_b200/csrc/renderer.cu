@@ -491,13 +491,6 @@ void upload_segments(PFCudaRenderer *r, SceneSegments &dst, const PFSegmentsD3D1
     r->stats.h2d_bytes += src.point_count * sizeof(float2) + src.index_count * sizeof(uint2);
 }
 
-// BlendMode::is_destructive (content/src/effects.rs:222-235): the path changes pixels outside its own coverage, so
-// the reference tiles it over the whole view box (builder.rs:430-434). Not built.
-bool blend_mode_is_destructive(uint32_t mode) {
-    return mode == PF_BLEND_MODE_CLEAR || mode == PF_BLEND_MODE_COPY || mode == PF_BLEND_MODE_SRC_IN ||
-           mode == PF_BLEND_MODE_DEST_IN || mode == PF_BLEND_MODE_SRC_OUT || mode == PF_BLEND_MODE_DEST_ATOP;
-}
-
 void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *entries, size_t n) {
     std::vector<float4> table(n);
     std::vector<PaintTexture> textures(n);
@@ -506,13 +499,10 @@ void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *en
     auto half_round = [](float v) { return __half2float(__float2half_rn(v)); }; // the metadata texture is RGBA16F
     for (size_t i = 0; i < n; i++) {
         const PFTextureMetadataEntry &e = entries[i];
-        const bool textured = e.color_0_combine_mode == PF_COLOR_COMBINE_MODE_SRC_IN;
-        if (e.color_0_combine_mode != PF_COLOR_COMBINE_MODE_NONE && !textured)
-            throw Error(PF_CUDA_ERROR_UNSUPPORTED, "ColorCombineMode::DestIn is not implemented");
+        if (e.color_0_combine_mode > PF_COLOR_COMBINE_MODE_DEST_IN)
+            throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "unknown colour combine mode");
+        const bool textured = e.color_0_combine_mode != PF_COLOR_COMBINE_MODE_NONE;
         if (e.blend_mode > PF_BLEND_MODE_LUMINOSITY) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "unknown blend mode");
-        if (blend_mode_is_destructive(e.blend_mode))
-            throw Error(PF_CUDA_ERROR_UNSUPPORTED,
-                        "destructive blend modes (Clear, Copy, SrcIn, DestIn, SrcOut, DestAtop) are not implemented");
         if (e.filter.kind > PF_FILTER_COLOR_MATRIX) throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "unknown filter kind");
         if (e.filter.kind != PF_FILTER_NONE && !textured)
             throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "a filter on a paint without a colour texture");
@@ -533,7 +523,7 @@ void upload_texture_metadata(PFCudaRenderer *r, const PFTextureMetadataEntry *en
             pt.m10 = half_round(t.matrix.m10), pt.m11 = half_round(t.matrix.m11);
             pt.tx = half_round(t.vector.x), pt.ty = half_round(t.vector.y);
             pt.filter_kind = e.filter.kind;
-            pt.flags = PAINT_HAS_TEXTURE;
+            pt.flags = PAINT_HAS_TEXTURE | (e.color_0_combine_mode == PF_COLOR_COMBINE_MODE_DEST_IN ? PAINT_COMBINE_DEST_IN : 0u);
             const float *fp = e.filter.params;
             auto h4 = [&](float x, float y, float z, float w) { return make_float4(half_round(x), half_round(y), half_round(z), half_round(w)); };
             // compute_filter_params (gpu/renderer.rs:967-1049)
@@ -1222,8 +1212,10 @@ ColorTexture resolve_color_texture(PFCudaRenderer *r, bool has_color_texture, co
     if (!has_color_texture) return ColorTexture{nullptr, 0, 0, 0, 0, 0};
     if (texture.page >= r->pages.size() || !r->pages[texture.page])
         throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "draw batch names a texture page that was never allocated");
-    if (texture.composite_op != PF_PAINT_COMPOSITE_OP_SRC_IN)
-        throw Error(PF_CUDA_ERROR_UNSUPPORTED, "only PaintCompositeOp::SrcIn is implemented");
+    // (TileBatchTexture::composite_op travels with the batch but no renderer of the reference reads it: how the
+    // texture combines with the base colour is the texture metadata entry's color_0_combine_mode, paint.rs:649-653)
+    if (texture.composite_op > PF_PAINT_COMPOSITE_OP_DEST_IN)
+        throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "unknown PaintCompositeOp");
     const PFCudaRenderer::TexturePage &page = *r->pages[texture.page];
     if (!r->target_stack.empty() && r->render_targets[r->target_stack.back()].page == texture.page)
         throw Error(PF_CUDA_ERROR_INVALID_ARGUMENT, "draw batch samples the render target it draws to");

@@ -1218,12 +1218,9 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
             GeneralBatch *gb = &s->general_batches.back();
             for (uint32_t i = item.a; i < item.b; i++) {
                 const Path &p = s->draw_paths[i];
-                if (p.blend_mode == PF_BLEND_MODE_CLEAR || p.blend_mode == PF_BLEND_MODE_COPY || p.blend_mode == PF_BLEND_MODE_SRC_IN ||
-                    p.blend_mode == PF_BLEND_MODE_DEST_IN || p.blend_mode == PF_BLEND_MODE_SRC_OUT ||
-                    p.blend_mode == PF_BLEND_MODE_DEST_ATOP || p.blend_mode > PF_BLEND_MODE_LUMINOSITY) {
-                    // BlendMode::is_destructive (effects.rs:222-235): tiled over the whole view box (builder.rs:430-434)
-                    pf::set_last_error("destructive blend modes (Clear, Copy, SrcIn, DestIn, SrcOut, DestAtop) are not implemented");
-                    return PF_CUDA_ERROR_UNSUPPORTED;
+                if (p.blend_mode > PF_BLEND_MODE_LUMINOSITY) {
+                    pf::set_last_error("unknown blend mode");
+                    return PF_CUDA_ERROR_INVALID_ARGUMENT;
                 }
                 if (p.clip_path != PF_CLIP_PATH_NONE && nesting > 0) {
                     pf::set_last_error("clipped paths inside a render target are not implemented");
@@ -1234,6 +1231,13 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                 RectF clipped;
                 const bool has_outline = p.first_contour != p.end_contour;
                 if (!((has_outline || !prepared) && rect_intersection(path_bounds, s->view_box, clipped))) continue;
+                // BlendMode::is_destructive (effects.rs:222-235): the path's tile map covers the whole view box
+                // (BuiltPath::new, builder.rs:430-434). Its empty tiles are still never drawn (builder.rs:1014-1016,
+                // propagate.cs.glsl:210-213), so the mode acts on the tiles the path reaches.
+                const bool destructive = p.blend_mode == PF_BLEND_MODE_CLEAR || p.blend_mode == PF_BLEND_MODE_COPY ||
+                                         p.blend_mode == PF_BLEND_MODE_SRC_IN || p.blend_mode == PF_BLEND_MODE_DEST_IN ||
+                                         p.blend_mode == PF_BLEND_MODE_SRC_OUT || p.blend_mode == PF_BLEND_MODE_DEST_ATOP;
+                if (destructive) clipped = s->view_box;
                 const float k = 1.0f / 16.0f;
                 PFRectI tile_rect;
                 tile_rect.origin.x = (int32_t)floorf(clipped.min_x * k);
@@ -1274,9 +1278,10 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
                 const uint32_t w = (uint32_t)(tile_rect.lower_right.x - tile_rect.origin.x),
                                h = (uint32_t)(tile_rect.lower_right.y - tile_rect.origin.y);
                 const uint32_t bi = (uint32_t)gb->propagate_metadata.size();
-                // BuiltDrawPath::new (builder.rs:80-94): occludes = opaque paint && SrcOver; a render-target pattern
-                // is never "obviously opaque" (pattern.rs:264-272).
-                const bool occludes = !has_texture && s->paints[p.paint].a == 255 && p.blend_mode == PF_BLEND_MODE_SRC_OVER;
+                // BuiltDrawPath::new (builder.rs:80-94): occludes = opaque paint && the mode ignores the backdrop
+                // (SrcOver, Clear: effects.rs:202-204); a render-target pattern is never "obviously opaque" (pattern.rs:264-272).
+                const bool occludes = !has_texture && s->paints[p.paint].a == 255 &&
+                                      (p.blend_mode == PF_BLEND_MODE_SRC_OVER || p.blend_mode == PF_BLEND_MODE_CLEAR);
                 PFPropagateMetadataD3D11 pm;
                 memset(&pm, 0, sizeof(pm));
                 pm.tile_rect = tile_rect;

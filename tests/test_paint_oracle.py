@@ -109,7 +109,10 @@ def collect(scene, options=None):
             n = d.tile_batch_data.path_count
             out["batches"].append({"texture": (int(d.color_texture.page), int(d.color_texture.sampling_flags)) if d.has_color_texture else None,
                                    "colors": [int(infos[i].color) for i in range(n)],
-                                   "z_write": [int(props[i].z_write) for i in range(n)]})
+                                   "z_write": [int(props[i].z_write) for i in range(n)],
+                                   "tile_rects": [(props[i].tile_rect.origin.x, props[i].tile_rect.origin.y,
+                                                   props[i].tile_rect.lower_right.x, props[i].tile_rect.lower_right.y)
+                                                  for i in range(n)]})
 
     scene.build(options or api.BuildOptions(), listener)
     return out
@@ -191,13 +194,24 @@ def test_blend_modes_get_their_own_metadata_entries():
     (batch,) = got["batches"]
     assert batch["colors"] == [red, 2, 2, 3, blue] and batch["texture"] is None
     assert batch["z_write"] == [1, 0, 0, 0, 1]  # occludes = opaque && SrcOver (builder.rs:83)
-    # destructive modes are refused loudly
-    bad = api.Scene()
-    bad.set_view_box((0, 0, 64, 64))
-    push_rect(bad, bad.push_paint((1, 2, 3, 255)), "copy")
-    with pytest.raises(L.PathfinderCudaError) as e:
-        collect(bad)
-    assert e.value.status == L.PF_CUDA_ERROR_UNSUPPORTED
+    assert batch["tile_rects"] == [(0, 0, 4, 4)] * 5  # RECT rounded out to tiles
+
+
+def test_destructive_blend_modes_are_tiled_over_the_view_box():
+    """BuiltPath::new (builder.rs:430-434): tile map bounds = the view box for Clear, Copy, SrcIn, DestIn, SrcOut and
+    DestAtop; an opaque Clear occludes like an opaque SrcOver (effects.rs:202-204, builder.rs:83)."""
+    scene = api.Scene()
+    scene.set_view_box((0, 0, 100, 70))
+    opaque, translucent = scene.push_paint((1, 2, 3, 255)), scene.push_paint((1, 2, 3, 128))
+    small = RECT * 0.25 + 20  # 22..34: tiles (1, 1) .. (3, 3)
+    modes = ["clear", "copy", "src_in", "dest_in", "src_out", "dest_atop", "clear", "src_atop"]
+    for k, mode in enumerate(modes):
+        scene.push_draw_path(small, np.zeros(4, np.uint8), [0, 4], translucent if k == 6 else opaque, blend_mode=api.BLEND_MODES[mode])
+    got = collect(scene)
+    (batch,) = got["batches"]
+    assert batch["tile_rects"] == [(0, 0, 7, 5)] * 7 + [(1, 1, 3, 3)]
+    assert batch["z_write"] == [1, 0, 0, 0, 0, 0, 0, 0]
+    assert [got["meta"][c]["blend"] for c in batch["colors"]] == [api.BLEND_MODES[m] for m in modes]
 
 
 def test_clip_paths_in_a_display_list_build():
@@ -225,3 +239,27 @@ def test_clip_paths_in_a_display_list_build():
     assert kinds.index("PrepareClipTilesD3D11") < kinds.index("DrawTilesD3D11")
     none = 0xFFFFFFFF
     assert clipped == [(1, [none, 0, 0])]
+
+
+def test_porter_duff_identities_of_the_destructive_modes():
+    """The twelve Porter-Duff operators partition source and destination: SrcIn + SrcOut = Copy, DestIn + DestOut =
+    the destination, SrcOver = Copy + DestOut, DestAtop = SrcOut + DestIn (all on premultiplied colour, unclamped
+    operands in [0, 1]); and nothing changes outside the drawn tiles."""
+    rng = np.random.default_rng(11)
+    dest = rng.random((8, 8, 4)).astype(np.float32)
+    dest[..., :3] *= dest[..., 3:4]
+    color = rng.random((8, 8, 4)).astype(np.float32)
+    mask = rng.random((8, 8)).astype(np.float32)
+    everywhere = np.ones((8, 8), bool)
+    b = lambda mode: P.blend(dest, color, mask, mode, drawn=everywhere)
+    assert np.allclose(b("src_in") + b("src_out"), b("copy"), atol=1e-6)
+    assert np.allclose(b("dest_in") + b("dest_out"), dest, atol=1e-6)
+    assert np.allclose(b("copy") + b("dest_out"), b("src_over"), atol=1e-6)
+    assert np.allclose(b("src_out") + b("dest_in"), b("dest_atop"), atol=1e-6)
+    assert not b("clear").any()
+    drawn = np.zeros((8, 8), bool)
+    drawn[:4] = True
+    half = P.blend(dest, color, mask, "copy", drawn=drawn)
+    assert np.array_equal(half[4:], dest[4:]) and np.array_equal(half[:4], b("copy")[:4])
+    with pytest.raises(ValueError):
+        P.blend(dest, color, mask, "copy")

@@ -54,6 +54,16 @@ def mask_of(points, area_lut, xf=None):
     return f[..., 3]
 
 
+def drawn_of(points, xf=None):
+    """Pixels of the tiles the path draws: the tile records of the path alone (empty tiles are never packed,
+    builder.rs:1014-1016)."""
+    drawn = np.zeros((SIZE, SIZE), bool)
+    for t in H.oracle_build(polygon(points), xf).tiles:
+        x, y = int(t["tile_x"]) * 16, int(t["tile_y"]) * 16
+        drawn[max(y, 0):y + 16, max(x, 0):x + 16] = True
+    return drawn
+
+
 def run(under, paths, area_lut, xf=None, background=WHITE):
     """paths = [(points, push_paint(scene) -> paint id, color_fn(width, height) -> colour array or tuple, blend)].
     Returns (GPU frame RGBA8, expected frame float32)."""
@@ -75,7 +85,8 @@ def run(under, paths, area_lut, xf=None, background=WHITE):
     else:
         dest = np.broadcast_to(np.asarray(background, np.float32), (SIZE, SIZE, 4)).copy()
     for points, _, color_fn, blend in paths:
-        dest = P.blend(dest, color_fn(SIZE, SIZE), mask_of(points, area_lut, xf), blend)
+        dest = P.blend(dest, color_fn(SIZE, SIZE), mask_of(points, area_lut, xf), blend,
+                       drawn=drawn_of(points, xf) if blend in P.DESTRUCTIVE else None)
     return img, dest
 
 
@@ -237,18 +248,21 @@ def test_pattern_filters(area_lut, pattern_filter):
     check(img, want)
 
 
-def test_destructive_blend_modes_are_refused():
-    from pathfinder_b200 import _lib as L
-    scene = api.Scene()
-    scene.set_view_box((0.0, 0.0, 64.0, 64.0))
-    pts = np.asarray([[4, 4], [60, 4], [60, 60], [4, 60]], np.float32)
-    scene.push_draw_path(pts, np.zeros(4, np.uint8), np.asarray([0, 4], np.uint32), scene.push_paint((1, 2, 3, 255)),
-                         blend_mode=api.BLEND_MODES["src_in"])
-    r = api.CudaRenderer((64, 64))
-    with pytest.raises(L.PathfinderCudaError) as e:
-        scene.build_and_render(r, api.BuildOptions())
-    assert e.value.status == L.PF_CUDA_ERROR_UNSUPPORTED
-    r.close()
+@pytest.mark.parametrize("mode", sorted(P.DESTRUCTIVE))
+def test_destructive_blend_modes(area_lut, mode):
+    """Clear, Copy, SrcIn, DestIn, SrcOut, DestAtop (effects.rs:222-235) change the pixels their mask leaves out too —
+    on the tiles the path draws; the rest of the frame stays (builder.rs:1014-1016)."""
+    push_a, color_a = solid((250, 200, 30, 255))
+    push_b, color_b = solid((60, 120, 240, 150))
+    paths = [(blob(120, 110, 80, phase=2.0), push_a, color_a, mode), (blob(150, 160, 75, phase=0.5), push_b, color_b, mode)]
+    for background in ((0.0, 0.0, 0.0, 0.0), WHITE): # (destination alpha 0 outside the shapes underneath / 1 everywhere)
+        img, want = run(under_scene(), paths, area_lut, background=background)
+        check(img, want)
+        plain, _ = run(under_scene(), [], area_lut, background=background)
+        changed = np.abs(img.astype(np.int32) - plain.astype(np.int32)).max(axis=2) > 0
+        assert changed.mean() > 0.02
+        # tiles neither path draws keep what was there
+        assert not changed[~(drawn_of(paths[0][0]) | drawn_of(paths[1][0]))].any()
 
 
 def clipped_polygon(points, clip_points, view=SIZE):
