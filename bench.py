@@ -225,6 +225,8 @@ def main():
                          "B200: 1.003 -> 0.953 ms/step (+5 %): the three scenes of a step already fill the GPU, so 1 stays "
                          "the default")
     ap.add_argument("--no-random1m", action="store_true", help="skip the random1m@16384 sub-record of the headline line")
+    ap.add_argument("--no-e2e-double-buffer", action="store_true",
+                    help="end to end at one GPU: one renderer + frame buffer per scene instead of two alternating ones")
     ap.add_argument("--gather", default="tiles", choices=["tiles", "nccl", "peer"],
                     help="N > 1, how the frame is assembled on every rank. 'tiles' (default) = PFCudaRendererGatherFrame in "
                          "tile mode: compact exports (4 B per single-colour tile, 1 KB per other tile) pulled from the peers' "
@@ -403,18 +405,25 @@ def main():
                 f.copied.record(copy_stream)
 
     def fork():  # the frames' streams start after everything already on `stream` (the start event)
-        for f in instances:
+        for f in instances + [f.e2e_alt for f in frames if getattr(f, "e2e_alt", None) is not None]:
             f.stream.wait_stream(stream)
 
     def join():  # ... and `stream` (the end event) waits for all of them, frame assembly included
-        for f in instances:
+        for f in instances + [f.e2e_alt for f in frames if getattr(f, "e2e_alt", None) is not None]:
             if dist is not None and not f.peer:
                 f.renderer.gather_wait()  # the frame's stream waits for its last gather
             stream.wait_stream(f.stream)
 
+    e2e_counter = [0]
+
     def step(e2e: bool):
+        # End to end, one GPU: two instances of every scene's renderer + frame buffers alternate, so the read-back of
+        # frame i (PCIe, the long pole) runs while frame i + 1 is built and rendered into the other buffer.
+        k = e2e_counter[0]
+        e2e_counter[0] += 1
         for f in frames:
-            render_frame(f, e2e)
+            g = f.e2e_alt if (e2e and getattr(f, "e2e_alt", None) is not None and k % 2 == 1) else f
+            render_frame(g, e2e)
 
     def timed(e2e: bool, steps: int):
         barrier()
@@ -517,8 +526,15 @@ def main():
         f.renderer.set_timing_enabled(False)
 
     # End to end: scene upload from host memory + render + read-back of the frame, every frame.
-    e2e_steps = max(3, min(args.steps, 10))
-    step(True)
+    e2e_steps = max(4, min(args.steps, 10))
+    e2e_in_flight = 1
+    if world == 1 and not args.no_e2e_double_buffer:
+        for i, (name, flat, xf, size) in enumerate(scene_list):
+            frames[i].e2e_alt = make_frame(name, flat, xf, size, 2 * len(scene_list) + i)
+            frames[i].e2e_alt.alt = None
+        e2e_in_flight = 2
+    for _ in range(2 * e2e_in_flight):
+        step(True)
     e2e_s = timed(True, e2e_steps)
     h2d = sum(int(f.flat.points.nbytes + f.flat.n_contours * 8 + len(f.flat.points) * 8) for f in frames)
     d2h = sum(f.size * f.size * 4 for f in frames)
@@ -542,7 +558,9 @@ def main():
         del f
         torch.cuda.empty_cache()
 
-    e2e_assembly = "device frame -> pinned host frame"
+    e2e_assembly = ("device frame -> pinned host frame; two renderer instances + frame buffers per scene alternate, so a "
+                    "frame's read-back overlaps the next frame's build and render" if e2e_in_flight == 2
+                    else "device frame -> pinned host frame")
     if dist is not None:
         e2e_assembly = ("every rank copies its strip into one shared %s host frame over its own PCIe link"
                         % ("page-locked" if all(f.host_registered for f in frames) else "pageable"))
@@ -645,7 +663,7 @@ def main():
                    "ms_per_frame": {f.name: stage_acc[f.name]["total_ms"] / args.steps for f in frames},
                    "stage_ms": {f.name: {k: v / args.steps for k, v in stage_acc[f.name].items()} for f in frames}},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "assembly": e2e_assembly,
-                "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
+                "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps, "frames_in_flight": e2e_in_flight},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

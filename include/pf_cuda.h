@@ -186,9 +186,9 @@ typedef struct PFFilter {
 /* The C-side form of TextureMetadataEntry (gpu_data.rs:336-344). NOT the memory layout of the Rust struct
  * (its Transform2F is a 16-byte aligned F32x4 + F32x2, its Filter a data-carrying enum, its BlendMode a one-byte
  * enum): the Rust glue converts every entry (integration/pathfinder_cuda/src/lib.rs
- * `texture_metadata_entry`). Evaluated: colour combine modes NONE and SRC_IN, every filter, every blend mode that is
- * not destructive (BlendMode::is_destructive: CLEAR, COPY, SRC_IN, DEST_IN, SRC_OUT, DEST_ATOP are refused with
- * PF_CUDA_ERROR_UNSUPPORTED, as is the DEST_IN combine mode). */
+ * `texture_metadata_entry`). Evaluated: every colour combine mode, every filter, every blend mode. The destructive
+ * modes (BlendMode::is_destructive: CLEAR, COPY, SRC_IN, DEST_IN, SRC_OUT, DEST_ATOP) act on the tiles the path draws —
+ * its tile map covers the view box (builder.rs:430-434) but empty tiles are never drawn (builder.rs:1014-1016). */
 typedef struct PFTextureMetadataEntry {
     PFTransform2F color_0_transform;
     uint32_t color_0_combine_mode;   /* PF_COLOR_COMBINE_MODE_* */
@@ -259,7 +259,8 @@ typedef struct PFTextureLocation {
 } PFTextureLocation;
 
 /* TextureSamplingFlags (gpu/src/lib.rs:521-528) and TileBatchTexture (gpu_data.rs:247-254). composite_op is
- * PaintCompositeOp (paint.rs): SrcIn (0) only; DestIn is refused. */
+ * PaintCompositeOp (paint.rs): carried, and like in the reference not read by the renderer (the texture metadata
+ * entry's color_0_combine_mode says how texture and base colour combine). */
 #define PF_TEXTURE_SAMPLING_FLAGS_REPEAT_U 0x1
 #define PF_TEXTURE_SAMPLING_FLAGS_REPEAT_V 0x2
 #define PF_TEXTURE_SAMPLING_FLAGS_NEAREST_MIN 0x4

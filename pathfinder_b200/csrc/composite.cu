@@ -638,7 +638,6 @@ __global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? 4 : PF_TILE_MIN_BLO
     __shared__ TileWarpShared<GENERAL> sh_all[TILE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TileWarpShared<GENERAL> &sh = sh_all[warp];
-    const int fb_w = a.fb.max_x - a.fb.min_x;
     const uint32_t n_queue = *a.queue_count; // written by k_tile_solid
     if (a.export_alpha_count && blockIdx.x == 0 && threadIdx.x == 0) *a.export_alpha_count = n_queue;
     const int x = lane & 15, half = lane >> 4;

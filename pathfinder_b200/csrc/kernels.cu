@@ -112,7 +112,10 @@ __device__ __forceinline__ float2 lerp_half(float2 a, float2 b) { // a + t * (b 
 }
 
 constexpr int DICE_MAX_DEPTH = 40; // f32 halving collapses long before; the oracle uses the same cap
-constexpr int DICE_SMEM_LEVELS = 8; // pending right halves kept in shared memory per thread
+#ifndef PF_DICE_SMEM_LEVELS
+#define PF_DICE_SMEM_LEVELS 5 // (8: 39 KB per block, 5 blocks per SM; 5: 26 KB, 7 blocks — random100k@8192 dice 0.210 -> 0.188 ms; deeper levels live in local memory)
+#endif
+constexpr int DICE_SMEM_LEVELS = PF_DICE_SMEM_LEVELS; // pending right halves kept in shared memory per thread
 constexpr int DICE_THREADS = 128;
 
 template <bool EMIT>
@@ -739,8 +742,11 @@ __device__ __forceinline__ void walk_line_warp(float2 from, float2 to, int from_
 
 constexpr int BIN_LONG_STEPS = 12; // tile crossings from which a line is walked by a whole warp
 
+#ifndef PF_BIN_MIN_BLOCKS
+#define PF_BIN_MIN_BLOCKS 16 // 32 registers: all 64 warps of an SM resident (latency-bound: random100k@8192 bin 0.250 -> 0.228 ms)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(BIN_THREADS) k_bin(BatchDev b, BinArgs a) {
+__global__ void __launch_bounds__(BIN_THREADS, PF_BIN_MIN_BLOCKS) k_bin(BatchDev b, BinArgs a) {
     __shared__ float4 s_line[BIN_THREADS];
     __shared__ uint32_t s_index[BIN_THREADS];
     __shared__ uint32_t s_queued;
@@ -877,8 +883,11 @@ int launch_sum_fill_counts(const uint32_t *tile_word, uint32_t n_tiles, unsigned
 // propagate — backdrop prefix sums down tile columns + occluder z-writes, one thread per column.
 // ---------------------------------------------------------------------------------------------
 
+#ifndef PF_PROPAGATE_MIN_BLOCKS
+#define PF_PROPAGATE_MIN_BLOCKS 16 // 32 registers, full occupancy (0.053 -> 0.048 ms)
+#endif
 template <bool HAS_CLIP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, PF_PROPAGATE_MIN_BLOCKS)
     k_propagate(BatchDev b, uint32_t *__restrict__ tile_word, const int32_t *__restrict__ col_backdrop,
                 int32_t *__restrict__ z_buffer, ClipDev clip, uint32_t *__restrict__ tile_clip,
                 uint32_t *__restrict__ tile_orig_count) {
@@ -994,7 +1003,10 @@ int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_
 constexpr int LIST_ITEMS = 8; // tiles per thread
 constexpr int LIST_TILE = 256 * LIST_ITEMS;
 
-__global__ void __launch_bounds__(256)
+#ifndef PF_LIST_MIN_BLOCKS
+#define PF_LIST_MIN_BLOCKS 8 // 32 registers, full occupancy (random100k@8192 sort 0.120 -> 0.102 ms)
+#endif
+__global__ void __launch_bounds__(256, PF_LIST_MIN_BLOCKS)
     k_list_count(BatchDev b, const uint32_t *__restrict__ tile_word, const int32_t *__restrict__ z_buffer,
                  uint32_t *__restrict__ tile_fb, uint32_t *__restrict__ fb_count,
                  uint32_t *__restrict__ tile_fill_pos, uint32_t *__restrict__ fill_cursor,
