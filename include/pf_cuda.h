@@ -515,6 +515,7 @@ typedef struct PFRenderTransform *PFRenderTransformRef;
 
 PFSceneRef PFSceneCreate(void);                 /* Scene::new, scene.rs:55-69 */
 void PFSceneDestroy(PFSceneRef scene);          /* c/src/lib.rs:786 */
+PFSceneRef PFSceneClone(PFSceneRef scene);      /* Scene: Clone (scene.rs:37): same content, id and epoch */
 void PFSceneSetViewBox(PFSceneRef scene, const PFRectF *view_box); /* scene.rs:223-226 */
 void PFSceneGetViewBox(PFSceneRef scene, PFRectF *view_box);
 void PFSceneGetBounds(PFSceneRef scene, PFRectF *bounds);
@@ -582,6 +583,7 @@ PFRenderTransformRef PFRenderTransformCreate2D(const PFTransform2F *transform); 
 void PFRenderTransformDestroy(PFRenderTransformRef transform);                  /* c/src/lib.rs:752 */
 PFBuildOptionsRef PFBuildOptionsCreate(void);                                   /* c/src/lib.rs:757 */
 void PFBuildOptionsDestroy(PFBuildOptionsRef options);                          /* c/src/lib.rs:762 */
+PFBuildOptionsRef PFBuildOptionsClone(PFBuildOptionsRef options);               /* BuildOptions: Clone (options.rs:73) */
 /* Consumes the transform (c/src/lib.rs:768-772). */
 void PFBuildOptionsSetTransform(PFBuildOptionsRef options, PFRenderTransformRef transform);
 void PFBuildOptionsSetDilation(PFBuildOptionsRef options, const PFVector2F *dilation); /* :774 */
@@ -678,6 +680,33 @@ void PFOutlineDilate(PFVector2F *points, const uint32_t *contour_offsets, uint32
  * (as PFSceneProxyBuildAndRenderGL, c/src/lib.rs:672-681). */
 PFCudaStatus PFSceneBuildAndRenderCuda(PFSceneRef scene, PFCudaRendererRef renderer,
                                        PFBuildOptionsRef options);
+
+/* ------------------------------------------------------------------------------------------- */
+/* SceneProxy (renderer/src/concurrent/scene_proxy.rs:35-157): a scene that lives on a thread of its own. Every call
+ * but the render calls returns at once; the worker thread applies them in order. One sink per proxy (scene_proxy.rs:70):
+ * a proxy feeds one renderer. Commands are handed over one at a time — a command's payload points into the scene's own
+ * arrays, so the worker waits in the listener while the command is consumed; what overlaps with the caller is the build
+ * up to each command (flattening, batch records), not the consumption.                                                 */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct PFSceneProxy *PFSceneProxyRef;
+/* SceneProxy::from_scene (c/src/lib.rs:791-797). Consumes the scene. */
+PFSceneProxyRef PFSceneProxyCreateFromScene(PFSceneRef scene);
+void PFSceneProxyDestroy(PFSceneProxyRef proxy);                                   /* c/src/lib.rs:800 */
+/* replace_scene (scene_proxy.rs:77-80). Consumes the new scene; the old one is destroyed by the worker. */
+PFCudaStatus PFSceneProxyReplaceScene(PFSceneProxyRef proxy, PFSceneRef new_scene);
+PFCudaStatus PFSceneProxySetViewBox(PFSceneProxyRef proxy, const PFRectF *view_box); /* scene_proxy.rs:83-86 */
+/* build (scene_proxy.rs:89-92): queues a build; borrows the options (copied). */
+PFCudaStatus PFSceneProxyBuild(PFSceneProxyRef proxy, PFBuildOptionsRef options);
+/* What render does with the commands, for any consumer: the commands of the oldest queued build, in order, up to and
+ * including Finish. Returns the build's status (a non-zero return of the listener aborts it). */
+PFCudaStatus PFSceneProxyReceive(PFSceneProxyRef proxy, PFRenderCommandListenerFn listener, void *userdata);
+/* render (scene_proxy.rs:95-105): begin_scene, the commands of the oldest queued build, end_scene. */
+PFCudaStatus PFSceneProxyRenderCuda(PFSceneProxyRef proxy, PFCudaRendererRef renderer);
+/* build_and_render (scene_proxy.rs:117-122; PFSceneProxyBuildAndRenderGL, c/src/lib.rs:672-681). The build is told the
+ * renderer's strip (multi-GPU) and that the renderer may copy the segment arrays without waiting. */
+PFCudaStatus PFSceneProxyBuildAndRenderCuda(PFSceneProxyRef proxy, PFCudaRendererRef renderer, PFBuildOptionsRef options);
+/* copy_scene (scene_proxy.rs:125-130): waits for the queued calls before it, returns a clone the caller owns. */
+PFSceneRef PFSceneProxyCopyScene(PFSceneProxyRef proxy);
 
 #ifdef __cplusplus
 }

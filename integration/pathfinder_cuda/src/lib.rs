@@ -381,3 +381,87 @@ pub fn build_and_render<E: Executor>(scene: &mut Scene, renderer: &mut CudaRende
     }
     renderer.end_scene();
 }
+
+/// `SceneProxy` (renderer/src/concurrent/scene_proxy.rs:35-157) for the CUDA backend. The reference's own proxy cannot
+/// be reused as it is: its `render` / `build_and_render` take `&mut Renderer<D>` and its receiver is private. This is the
+/// same thing — the scene on a thread of its own, messages in, owned `RenderCommand`s back through a channel — with
+/// `CudaRenderer` at the receiving end. (The C library has the equivalent for hosts without the Rust scene:
+/// `PFSceneProxyCreateFromScene` .. `PFSceneProxyBuildAndRenderCuda`, include/pf_cuda.h.)
+pub struct CudaSceneProxy {
+    sender: std::sync::mpsc::SyncSender<ProxyMsg>,
+    receiver: std::sync::mpsc::Receiver<RenderCommand>,
+    view_boxes: std::collections::VecDeque<RectF>, // the view box each queued build will see (the stream does not carry it)
+    view_box: RectF,
+}
+
+enum ProxyMsg {
+    ReplaceScene(Scene),
+    CopyScene(std::sync::mpsc::SyncSender<Scene>),
+    SetViewBox(RectF),
+    Build(BuildOptions),
+}
+
+const MAX_MESSAGES_IN_FLIGHT: usize = 1024; // scene_proxy.rs:33
+
+impl CudaSceneProxy {
+    /// `SceneProxy::from_scene` (scene_proxy.rs:60-74), always at `RendererLevel::D3D11`.
+    pub fn from_scene<E: Executor + Send + 'static>(scene: Scene, executor: E) -> CudaSceneProxy {
+        let (to_worker, from_main) = std::sync::mpsc::sync_channel(MAX_MESSAGES_IN_FLIGHT);
+        let (to_main, from_worker) = std::sync::mpsc::sync_channel(MAX_MESSAGES_IN_FLIGHT);
+        let to_main = Mutex::new(to_main);
+        let listener = RenderCommandListener::new(Box::new(move |command| drop(to_main.lock().unwrap().send(command))));
+        let view_box = scene.view_box();
+        std::thread::spawn(move || {
+            let mut scene = scene;
+            let mut sink = SceneSink::new(listener, RendererLevel::D3D11);
+            while let Ok(msg) = from_main.recv() {
+                match msg {
+                    ProxyMsg::ReplaceScene(new_scene) => scene = new_scene,
+                    ProxyMsg::CopyScene(reply) => drop(reply.send(scene.clone())),
+                    ProxyMsg::SetViewBox(view_box) => scene.set_view_box(view_box),
+                    ProxyMsg::Build(options) => scene.build(options, &mut sink, &executor),
+                }
+            }
+        });
+        CudaSceneProxy { sender: to_worker, receiver: from_worker, view_boxes: Default::default(), view_box }
+    }
+
+    pub fn replace_scene(&mut self, new_scene: Scene) {
+        self.view_box = new_scene.view_box();
+        self.sender.send(ProxyMsg::ReplaceScene(new_scene)).unwrap();
+    }
+
+    pub fn set_view_box(&mut self, new_view_box: RectF) {
+        self.view_box = new_view_box;
+        self.sender.send(ProxyMsg::SetViewBox(new_view_box)).unwrap();
+    }
+
+    pub fn build(&mut self, options: BuildOptions) {
+        self.view_boxes.push_back(self.view_box);
+        self.sender.send(ProxyMsg::Build(options)).unwrap();
+    }
+
+    /// `SceneProxy::render` (scene_proxy.rs:95-105).
+    pub fn render(&mut self, renderer: &mut CudaRenderer) {
+        renderer.set_view_box(self.view_boxes.pop_front().expect("render without a build"));
+        renderer.begin_scene();
+        while let Ok(command) = self.receiver.recv() {
+            renderer.render_command(&command);
+            if let RenderCommand::Finish { .. } = command {
+                break;
+            }
+        }
+        renderer.end_scene();
+    }
+
+    pub fn build_and_render(&mut self, renderer: &mut CudaRenderer, options: BuildOptions) {
+        self.build(options);
+        self.render(renderer);
+    }
+
+    pub fn copy_scene(&self) -> Scene {
+        let (reply, scene) = std::sync::mpsc::sync_channel(1);
+        self.sender.send(ProxyMsg::CopyScene(reply)).unwrap();
+        scene.recv().unwrap()
+    }
+}

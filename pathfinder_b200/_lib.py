@@ -334,6 +334,17 @@ SIGNATURES = {
     "PFSceneBuildForStrip": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(PFSceneSinkState), LISTENER_FN, C.c_void_p,
                                          C.c_int32, C.c_int32]),
     "PFSceneBuildAndRenderCuda": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "PFSceneClone": (C.c_void_p, [C.c_void_p]),
+    "PFBuildOptionsClone": (C.c_void_p, [C.c_void_p]),
+    "PFSceneProxyCreateFromScene": (C.c_void_p, [C.c_void_p]),
+    "PFSceneProxyDestroy": (None, [C.c_void_p]),
+    "PFSceneProxyReplaceScene": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "PFSceneProxySetViewBox": (C.c_int32, [C.c_void_p, C.POINTER(PFRectF)]),
+    "PFSceneProxyBuild": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "PFSceneProxyReceive": (C.c_int32, [C.c_void_p, LISTENER_FN, C.c_void_p]),
+    "PFSceneProxyRenderCuda": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "PFSceneProxyBuildAndRenderCuda": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "PFSceneProxyCopyScene": (C.c_void_p, [C.c_void_p]),
 }
 
 _lib = None

@@ -319,6 +319,74 @@ class Scene:
             pass
 
 
+class SceneProxy:
+    """renderer/src/concurrent/scene_proxy.rs SceneProxy: the scene lives on a worker thread of the library; every call
+    but the render calls returns at once."""
+
+    def __init__(self, scene: Scene):
+        """SceneProxy::from_scene: takes the scene over (the Scene object is empty afterwards)."""
+        self._h = L.lib().PFSceneProxyCreateFromScene(scene._h)
+        if not self._h:
+            raise L.PathfinderCudaError(L.PF_CUDA_ERROR_INVALID_ARGUMENT, L.lib().PFCudaGetLastError().decode("utf-8", "replace"))
+        scene._h = None
+
+    def replace_scene(self, scene: Scene):
+        L.check(L.lib().PFSceneProxyReplaceScene(self._h, scene._h))
+        scene._h = None
+
+    def set_view_box(self, view_box):
+        r = L.PFRectF(L.PFVector2F(view_box[0], view_box[1]), L.PFVector2F(view_box[2], view_box[3]))
+        L.check(L.lib().PFSceneProxySetViewBox(self._h, C.byref(r)))
+
+    def build(self, options: BuildOptions):
+        L.check(L.lib().PFSceneProxyBuild(self._h, options._h))
+
+    def receive(self, listener):
+        """The commands of the oldest queued build, to listener(PFRenderCommand), up to and including Finish."""
+        errors = []
+
+        def trampoline(cmd_ptr, _userdata):
+            try:
+                listener(cmd_ptr.contents)
+                return 0
+            except L.PathfinderCudaError as e:
+                errors.append(e)
+                return e.status
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+                return L.PF_CUDA_ERROR_INVALID_ARGUMENT
+
+        status = L.lib().PFSceneProxyReceive(self._h, L.LISTENER_FN(trampoline), None)
+        if errors:
+            raise errors[0]
+        L.check(status)
+
+    def render(self, renderer: "CudaRenderer"):
+        L.check(L.lib().PFSceneProxyRenderCuda(self._h, renderer._h))
+
+    def build_and_render(self, renderer: "CudaRenderer", options: BuildOptions):
+        L.check(L.lib().PFSceneProxyBuildAndRenderCuda(self._h, renderer._h, options._h))
+
+    def copy_scene(self) -> Scene:
+        h = L.lib().PFSceneProxyCopyScene(self._h)
+        if not h:
+            raise L.PathfinderCudaError(L.PF_CUDA_ERROR_PROTOCOL, L.lib().PFCudaGetLastError().decode("utf-8", "replace"))
+        s = Scene.__new__(Scene)
+        s._h = h
+        return s
+
+    def close(self):
+        if self._h:
+            L.lib().PFSceneProxyDestroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 LINE_CAP = {"butt": 0, "square": 1, "round": 2}
 LINE_JOIN = {"miter": 0, "bevel": 1, "round": 2}
 

@@ -21,6 +21,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <vector>
 
@@ -2121,6 +2122,298 @@ PFCudaStatus PFSceneBuildAndRenderCuda(PFSceneRef scene, PFCudaRendererRef r, PF
     }
     PFCudaStatus end = PFCudaRendererEndScene(r);
     return st != PF_CUDA_OK ? st : end;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SceneProxy (renderer/src/concurrent/scene_proxy.rs:35-157): the scene lives on a worker thread; replace_scene,
+// set_view_box and build are messages the worker applies in order, render pumps the commands of the oldest queued
+// build into the renderer. The reference moves owned commands through a channel; here a command's payload points into
+// the scene's own arrays, so commands are handed over one at a time: the worker waits inside its listener until the
+// caller has consumed the command. What runs beside the caller is the build up to each command.
+// ---------------------------------------------------------------------------------------------
+struct PFSceneProxy {
+    enum Kind { REPLACE, SET_VIEW_BOX, BUILD, COPY };
+    struct Msg {
+        Kind kind;
+        PFScene *scene;
+        PFRectF view_box;
+        PFBuildOptionsRef options;
+        bool persists;
+        int32_t strip[2];
+    };
+    PFScene *scene = nullptr;            // the worker's, once the thread runs
+    PFRectF view_box{};                  // caller-side copy of the scene's view box (what the next build will see)
+    std::deque<PFRectF> build_view_boxes; // ... as it was when each queued build was requested
+    PFSceneSinkState sink_state{0, 0, 0}; // one sink per proxy (scene_proxy.rs:70)
+    std::thread worker;
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<Msg> inbox;
+    bool quit = false;
+    const PFRenderCommand *pending = nullptr; // hand-over of one command: set by the worker, consumed by the caller
+    bool pending_ready = false, pending_done = false;
+    PFCudaStatus pending_result = PF_CUDA_OK;
+    bool build_done = false;             // the current build has ended; the worker goes on once the caller has seen it
+    PFCudaStatus build_status = PF_CUDA_OK;
+    std::string build_error;
+    uint32_t builds_queued = 0;
+    PFScene *copy_result = nullptr;
+    bool copy_done = false;
+};
+
+namespace {
+
+PFCudaStatus proxy_listener(const PFRenderCommand *command, void *userdata) {
+    PFSceneProxy *p = static_cast<PFSceneProxy *>(userdata);
+    std::unique_lock<std::mutex> lock(p->m);
+    if (p->quit) return PF_CUDA_ERROR_PROTOCOL;
+    p->pending = command;
+    p->pending_ready = true, p->pending_done = false;
+    p->cv.notify_all();
+    p->cv.wait(lock, [&] { return p->pending_done || p->quit; });
+    p->pending = nullptr;
+    p->pending_ready = false;
+    return p->pending_done ? p->pending_result : PF_CUDA_ERROR_PROTOCOL;
+}
+
+void proxy_thread(PFSceneProxy *p) {
+    for (;;) {
+        PFSceneProxy::Msg msg;
+        {
+            std::unique_lock<std::mutex> lock(p->m);
+            p->cv.wait(lock, [&] { return p->quit || (!p->inbox.empty() && !p->build_done); });
+            if (p->quit) return;
+            msg = p->inbox.front();
+            p->inbox.pop_front();
+        }
+        switch (msg.kind) {
+        case PFSceneProxy::REPLACE:
+            PFSceneDestroy(p->scene);
+            p->scene = msg.scene;
+            break;
+        case PFSceneProxy::SET_VIEW_BOX: PFSceneSetViewBox(p->scene, &msg.view_box); break;
+        case PFSceneProxy::COPY: {
+            PFScene *copy = PFSceneClone(p->scene);
+            std::lock_guard<std::mutex> lock(p->m);
+            p->copy_result = copy, p->copy_done = true;
+            p->cv.notify_all();
+            break;
+        }
+        case PFSceneProxy::BUILD: {
+            pf::g_scene_payload_persists = msg.persists;
+            pf::g_scene_strip[0] = msg.strip[0], pf::g_scene_strip[1] = msg.strip[1];
+            const PFCudaStatus st = PFSceneBuild(p->scene, msg.options, &p->sink_state, proxy_listener, p);
+            pf::g_scene_strip[0] = pf::g_scene_strip[1] = 0;
+            pf::g_scene_payload_persists = false;
+            const std::string error = st != PF_CUDA_OK ? std::string(PFCudaGetLastError()) : std::string();
+            PFBuildOptionsDestroy(msg.options);
+            std::lock_guard<std::mutex> lock(p->m);
+            p->build_done = true, p->build_status = st, p->build_error = error;
+            p->cv.notify_all();
+            break;
+        }
+        }
+    }
+}
+
+bool proxy_send(PFSceneProxy *p, const PFSceneProxy::Msg &msg) {
+    std::lock_guard<std::mutex> lock(p->m);
+    if (p->quit) return false;
+    p->inbox.push_back(msg);
+    p->cv.notify_all();
+    return true;
+}
+
+// The commands of the oldest queued build, one at a time, to `listener`. Returns once the build has ended; with
+// acknowledge = false the worker stays parked (the caller still has something to do with the idle scene).
+PFCudaStatus proxy_receive(PFSceneProxy *p, PFRenderCommandListenerFn listener, void *userdata, bool acknowledge) {
+    std::unique_lock<std::mutex> lock(p->m);
+    if (p->builds_queued == 0) {
+        set_last_error("scene proxy: render without a build");
+        return PF_CUDA_ERROR_PROTOCOL;
+    }
+    PFCudaStatus aborted = PF_CUDA_OK;
+    std::string abort_error;
+    for (;;) {
+        p->cv.wait(lock, [&] { return p->pending_ready || p->build_done; });
+        if (!p->pending_ready) break; // the build has ended
+        const PFRenderCommand *command = p->pending;
+        p->pending_ready = false;
+        lock.unlock();
+        const PFCudaStatus st = listener(command, userdata);
+        if (st != PF_CUDA_OK && aborted == PF_CUDA_OK) aborted = st, abort_error = PFCudaGetLastError();
+        lock.lock();
+        p->pending_result = st, p->pending_done = true;
+        p->cv.notify_all();
+    }
+    const PFCudaStatus status = aborted != PF_CUDA_OK ? aborted : p->build_status;
+    if (status != PF_CUDA_OK) set_last_error(aborted != PF_CUDA_OK ? abort_error : p->build_error);
+    if (acknowledge) {
+        p->build_done = false;
+        p->builds_queued--;
+        p->cv.notify_all();
+    }
+    return status;
+}
+
+void proxy_acknowledge(PFSceneProxy *p) {
+    std::lock_guard<std::mutex> lock(p->m);
+    p->build_done = false;
+    p->builds_queued--;
+    p->cv.notify_all();
+}
+
+PFCudaStatus proxy_queue_build(PFSceneProxy *p, PFBuildOptionsRef options, bool persists, int32_t y0, int32_t y1) {
+    if (!p || !options) {
+        set_last_error("scene proxy: null argument");
+        return PF_CUDA_ERROR_INVALID_ARGUMENT;
+    }
+    PFSceneProxy::Msg msg{PFSceneProxy::BUILD, nullptr, PFRectF{}, PFBuildOptionsClone(options), persists, {y0, y1}};
+    {
+        std::lock_guard<std::mutex> lock(p->m);
+        p->builds_queued++;
+        p->build_view_boxes.push_back(p->view_box);
+    }
+    if (!proxy_send(p, msg)) {
+        PFBuildOptionsDestroy(msg.options);
+        return PF_CUDA_ERROR_PROTOCOL;
+    }
+    return PF_CUDA_OK;
+}
+
+} // namespace
+
+PFSceneProxyRef PFSceneProxyCreateFromScene(PFSceneRef scene) {
+    if (!scene) {
+        set_last_error("PFSceneProxyCreateFromScene: null scene");
+        return nullptr;
+    }
+    PFSceneProxy *p = new PFSceneProxy();
+    p->scene = scene;
+    PFSceneGetViewBox(scene, &p->view_box);
+    p->worker = std::thread(proxy_thread, p);
+    return p;
+}
+
+void PFSceneProxyDestroy(PFSceneProxyRef p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lock(p->m);
+        p->quit = true;
+        p->cv.notify_all();
+    }
+    p->worker.join(); // (a build in flight is aborted: its listener returns an error)
+    for (PFSceneProxy::Msg &msg : p->inbox) {
+        if (msg.kind == PFSceneProxy::REPLACE) PFSceneDestroy(msg.scene);
+        if (msg.kind == PFSceneProxy::BUILD) PFBuildOptionsDestroy(msg.options);
+    }
+    PFSceneDestroy(p->scene);
+    delete p;
+}
+
+PFCudaStatus PFSceneProxyReplaceScene(PFSceneProxyRef p, PFSceneRef new_scene) {
+    if (!p || !new_scene) {
+        set_last_error("PFSceneProxyReplaceScene: null argument");
+        return PF_CUDA_ERROR_INVALID_ARGUMENT;
+    }
+    PFRectF vb;
+    PFSceneGetViewBox(new_scene, &vb);
+    {
+        std::lock_guard<std::mutex> lock(p->m);
+        p->view_box = vb;
+    }
+    return proxy_send(p, PFSceneProxy::Msg{PFSceneProxy::REPLACE, new_scene, vb, nullptr, false, {0, 0}}) ? PF_CUDA_OK : PF_CUDA_ERROR_PROTOCOL;
+}
+
+PFCudaStatus PFSceneProxySetViewBox(PFSceneProxyRef p, const PFRectF *view_box) {
+    if (!p || !view_box) {
+        set_last_error("PFSceneProxySetViewBox: null argument");
+        return PF_CUDA_ERROR_INVALID_ARGUMENT;
+    }
+    {
+        std::lock_guard<std::mutex> lock(p->m);
+        p->view_box = *view_box;
+    }
+    return proxy_send(p, PFSceneProxy::Msg{PFSceneProxy::SET_VIEW_BOX, nullptr, *view_box, nullptr, false, {0, 0}}) ? PF_CUDA_OK : PF_CUDA_ERROR_PROTOCOL;
+}
+
+PFCudaStatus PFSceneProxyBuild(PFSceneProxyRef p, PFBuildOptionsRef options) {
+    return proxy_queue_build(p, options, false, 0, 0);
+}
+
+PFCudaStatus PFSceneProxyReceive(PFSceneProxyRef p, PFRenderCommandListenerFn listener, void *userdata) {
+    if (!p || !listener) {
+        set_last_error("PFSceneProxyReceive: null argument");
+        return PF_CUDA_ERROR_INVALID_ARGUMENT;
+    }
+    {
+        std::lock_guard<std::mutex> lock(p->m);
+        if (!p->build_view_boxes.empty()) p->build_view_boxes.pop_front();
+    }
+    return proxy_receive(p, listener, userdata, true);
+}
+
+PFCudaStatus PFSceneProxyRenderCuda(PFSceneProxyRef p, PFCudaRendererRef r) {
+    if (!p || !r) {
+        set_last_error("PFSceneProxyRenderCuda: null argument");
+        return PF_CUDA_ERROR_INVALID_ARGUMENT;
+    }
+    PFRectF vb;
+    {
+        std::lock_guard<std::mutex> lock(p->m);
+        if (p->builds_queued == 0 || p->build_view_boxes.empty()) {
+            set_last_error("scene proxy: render without a build");
+            return PF_CUDA_ERROR_PROTOCOL;
+        }
+        vb = p->build_view_boxes.front();
+        p->build_view_boxes.pop_front();
+    }
+    PFCudaStatus st = PFCudaRendererSetViewBox(r, &vb);
+    if (st == PF_CUDA_OK) st = PFCudaRendererBeginScene(r);
+    if (st != PF_CUDA_OK) { // the build still has to be consumed: drop its commands
+        proxy_receive(p, [](const PFRenderCommand *, void *) -> PFCudaStatus { return PF_CUDA_ERROR_PROTOCOL; }, nullptr, true);
+        return st;
+    }
+    r->uploaded_scene_this_frame = false;
+    st = proxy_receive(p, forward_command, r, false);
+    if (r->uploaded_scene_this_frame) { // (the worker is parked until the acknowledgement: the scene is idle)
+        try {
+            pf::scene_note_borrowed(p->scene, r->stream, r->ordinal);
+        } catch (const Error &e) {
+            set_last_error(e.what());
+            if (st == PF_CUDA_OK) st = (PFCudaStatus)e.status;
+        }
+    }
+    proxy_acknowledge(p);
+    const PFCudaStatus end = PFCudaRendererEndScene(r);
+    return st != PF_CUDA_OK ? st : end;
+}
+
+PFCudaStatus PFSceneProxyBuildAndRenderCuda(PFSceneProxyRef p, PFCudaRendererRef r, PFBuildOptionsRef options) {
+    if (!p || !r || !options) {
+        set_last_error("PFSceneProxyBuildAndRenderCuda: null argument");
+        return PF_CUDA_ERROR_INVALID_ARGUMENT;
+    }
+    const PFCudaStatus st = proxy_queue_build(p, options, true, r->strip_y0, r->strip_y1);
+    return st != PF_CUDA_OK ? st : PFSceneProxyRenderCuda(p, r);
+}
+
+PFSceneRef PFSceneProxyCopyScene(PFSceneProxyRef p) {
+    if (!p) return nullptr;
+    {
+        std::lock_guard<std::mutex> lock(p->m);
+        if (p->builds_queued != 0) { // (the worker hands its commands over one at a time: it would never get to the copy)
+            set_last_error("scene proxy: copy_scene with a build still to be rendered");
+            return nullptr;
+        }
+        p->copy_done = false;
+    }
+    if (!proxy_send(p, PFSceneProxy::Msg{PFSceneProxy::COPY, nullptr, PFRectF{}, nullptr, false, {0, 0}})) return nullptr;
+    std::unique_lock<std::mutex> lock(p->m);
+    p->cv.wait(lock, [&] { return p->copy_done; });
+    PFScene *copy = p->copy_result;
+    p->copy_result = nullptr;
+    return copy;
 }
 
 PFCudaStatus PFCudaRendererGetStats(PFCudaRendererRef r, PFCudaRenderStats *stats) {

@@ -615,6 +615,21 @@ void PFSceneDestroy(PFSceneRef scene) {
     delete scene;
 }
 
+// Scene: Clone (scene.rs:37): the content — outlines, paths, palette, display list, bounds, view box — with the same
+// id and epoch; the build scratch (segment arrays, batch arrays) starts empty in the copy.
+PFSceneRef PFSceneClone(PFSceneRef s) {
+    if (!s) return nullptr;
+    PFScene *c = new PFScene();
+    c->points = s->points, c->flags = s->flags, c->contour_offsets = s->contour_offsets;
+    c->draw_paths = s->draw_paths, c->clip_paths = s->clip_paths;
+    c->paints = s->paints, c->paint_cache = s->paint_cache;
+    c->render_targets = s->render_targets, c->overlays = s->overlays, c->display_list = s->display_list;
+    c->any_blend = s->any_blend;
+    c->bounds = s->bounds, c->view_box = s->view_box;
+    c->id = s->id, c->epoch = s->epoch;
+    return c;
+}
+
 void PFSceneSetViewBox(PFSceneRef s, const PFRectF *vb) {
     s->view_box = RectF{vb->origin.x, vb->origin.y, vb->lower_right.x, vb->lower_right.y};
     s->epoch++;
@@ -854,6 +869,7 @@ PFRenderTransformRef PFRenderTransformCreate2D(const PFTransform2F *t) {
 }
 void PFRenderTransformDestroy(PFRenderTransformRef t) { delete t; }
 PFBuildOptionsRef PFBuildOptionsCreate(void) { return new PFBuildOptions(); }
+PFBuildOptionsRef PFBuildOptionsClone(PFBuildOptionsRef o) { return o ? new PFBuildOptions(*o) : nullptr; }
 void PFBuildOptionsDestroy(PFBuildOptionsRef o) { delete o; }
 void PFBuildOptionsSetTransform(PFBuildOptionsRef o, PFRenderTransformRef t) {
     o->transform = t->t;
