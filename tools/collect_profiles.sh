@@ -15,7 +15,11 @@ for scene in random100k tiger4k; do
         -o gpurun_out/${TAG}_${k}_${scene} python tools/stage_times.py $scene > gpurun_out/${TAG}_${k}_${scene}.log 2>&1
   done
 done
-ncu --set full --import-source on --clock-control none \
-    --metrics lts__t_sectors_op_atom.sum,lts__t_sectors_op_red.sum,lts__t_requests_op_atom.sum,lts__t_requests_op_red.sum,l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum,l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum,lts__t_sector_hit_rate.pct,lts__throughput.avg.pct_of_peak_sustained_elapsed \
-    -k regex:k_bin -s 4 -c 4 -f -o gpurun_out/${TAG}_k_bin_random100k python tools/stage_times.py random100k > gpurun_out/${TAG}_k_bin_random100k.log 2>&1
+# (k_bin<1> and k_bin<0> share the base name: the 5th / 6th launch named k_bin are the count and the emit pass of the
+#  third frame, a steady-state one)
+BIN_METRICS=lts__t_sectors_op_atom.sum,lts__t_sectors_op_red.sum,lts__t_requests_op_atom.sum,lts__t_requests_op_red.sum,l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum,l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum,lts__t_sector_hit_rate.pct,lts__throughput.avg.pct_of_peak_sustained_elapsed
+for pass in count:5 emit:6; do
+  ncu --set full --import-source on --clock-control none --metrics $BIN_METRICS --kernel-id ::k_bin:${pass#*:} -f \
+      -o gpurun_out/${TAG}_k_bin_${pass%:*}_random100k python tools/stage_times.py random100k > gpurun_out/${TAG}_k_bin_${pass%:*}_random100k.log 2>&1
+done
 ls -la gpurun_out | grep ${TAG}_

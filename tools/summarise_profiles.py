@@ -101,19 +101,19 @@ if len(traffic) == 2:
               open(os.path.join(out_dir, f"{tag}_fill_tile_traffic.json"), "w"), indent=1)
 
 # bin (count pass): the L2 atomic / reduction evidence the north star names
-rep = os.path.join(ROOT, "gpurun_out", f"{tag}_k_bin_random100k.ncu-rep")
-if os.path.exists(rep):
+reps = [(name, os.path.join(ROOT, "gpurun_out", f"{tag}_k_bin_{name}_random100k.ncu-rep")) for name in ("count", "emit")]
+if all(os.path.exists(rep) for _, rep in reps):
     BIN_KEYS = KEYS + ["lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum", "lts__t_requests_op_atom.sum", "lts__t_requests_op_red.sum",
                        "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum", "l1tex__t_set_accesses_pipe_lsu_mem_global_op_atom.sum",
                        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
-    lines = [f"# {tag} — `ncu --set full` of bin, one steady-state frame of random100k@8192: k_bin<1> + k_bin_long<1> (count pass), k_bin<0> + k_bin_long<0> (emit pass after the z-cull)", "",
+    lines = [f"# {tag} — `ncu --set full` of bin, one steady-state frame of random100k@8192: k_bin<1> (count pass) and k_bin<0> (emit pass after the z-cull)", "",
              "Every fill and every backdrop change of the count pass is one 32-bit L2 reduction (`RED`, no return value) on the "
              "tile word; the emit pass claims its slot with one `ATOMG` per surviving fill.", ""]
-    for launch in (0, 1, 2, 3):
-        m = raw_metrics(rep, launch)
+    for name, rep in reps:
+        m = raw_metrics(rep, 0)
         if not m:
             continue
-        lines += [f"## launch {launch}: `{m.get('Kernel Name', ('', '?'))[1]}`", "", "| metric | unit | value |", "|---|---|---:|"]
+        lines += [f"## {name} pass: `{m.get('Kernel Name', ('', '?'))[1]}`", "", "| metric | unit | value |", "|---|---|---:|"]
         for k in BIN_KEYS:
             if k in m:
                 lines.append(f"| `{k}` | {m[k][0]} | {m[k][1]} |")
