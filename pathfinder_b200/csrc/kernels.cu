@@ -883,11 +883,13 @@ int launch_sum_fill_counts(const uint32_t *tile_word, uint32_t n_tiles, unsigned
 // propagate — backdrop prefix sums down tile columns + occluder z-writes, one thread per column.
 // ---------------------------------------------------------------------------------------------
 
-#ifndef PF_PROPAGATE_MIN_BLOCKS
-#define PF_PROPAGATE_MIN_BLOCKS 16 // 32 registers, full occupancy (0.053 -> 0.048 ms)
-#endif
-template <bool HAS_CLIP>
-__global__ void __launch_bounds__(128, PF_PROPAGATE_MIN_BLOCKS)
+// Two register budgets: a batch with enough columns to fill the GPU runs at 32 registers with every warp slot of an
+// SM taken (random100k@8192: 1.05 M columns, 0.053 -> 0.048 ms); a batch of few, tall columns (tiger@4096: 9.6 k columns
+// of up to 256 rows) is one serial chain per thread whatever the occupancy, and the tighter budget only costs it
+// (0.033 -> 0.040 ms), so it keeps the registers the compiler asks for.
+constexpr uint32_t PROPAGATE_DENSE_COLUMNS = 262144;
+template <bool HAS_CLIP, bool DENSE>
+__global__ void __launch_bounds__(128, DENSE ? 16 : 8)
     k_propagate(BatchDev b, uint32_t *__restrict__ tile_word, const int32_t *__restrict__ col_backdrop,
                 int32_t *__restrict__ z_buffer, ClipDev clip, uint32_t *__restrict__ tile_clip,
                 uint32_t *__restrict__ tile_orig_count) {
@@ -974,12 +976,18 @@ __global__ void __launch_bounds__(128, PF_PROPAGATE_MIN_BLOCKS)
 int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_backdrop, int32_t *z_buffer,
                      const ClipDev *clip, uint32_t *tile_clip, uint32_t *tile_orig_count, cudaStream_t stream) {
     if (b.n_columns == 0) return 0;
-    if (clip && tile_clip)
-        k_propagate<true><<<div_up(b.n_columns, 128), 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, *clip,
-                                                                         tile_clip, tile_orig_count);
-    else
-        k_propagate<false><<<div_up(b.n_columns, 128), 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, ClipDev{},
-                                                                          nullptr, nullptr);
+    const bool dense = b.n_columns >= PROPAGATE_DENSE_COLUMNS;
+    const unsigned grid = div_up(b.n_columns, 128);
+    if (clip && tile_clip) {
+        if (dense)
+            k_propagate<true, true><<<grid, 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, *clip, tile_clip, tile_orig_count);
+        else
+            k_propagate<true, false><<<grid, 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, *clip, tile_clip, tile_orig_count);
+    } else if (dense) {
+        k_propagate<false, true><<<grid, 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, ClipDev{}, nullptr, nullptr);
+    } else {
+        k_propagate<false, false><<<grid, 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, ClipDev{}, nullptr, nullptr);
+    }
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
