@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <utility>
 
 #include <algorithm>
 #include <chrono>
@@ -80,6 +82,34 @@ extern thread_local int32_t g_scene_strip[2];
 void scene_note_borrowed(::PFScene *scene, cudaStream_t stream, int device);
 
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_chained may be scheduled while the kernel
+// before it on the stream is still draining — its blocks sit in chain_wait() until that kernel has completed and its
+// writes are visible — so the launch latency and the tail of one stage overlap with the next. Every kernel of the frame's
+// chain starts with chain_wait() (a no-op when it was launched the ordinary way) followed by chain_release(), which lets
+// the kernel after it be scheduled as soon as SM resources free up. PF_CUDA_NO_PDL=1 in the environment launches the
+// ordinary way.
+#ifdef __CUDACC__
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void chain_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool chained_launches_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("PF_CUDA_NO_PDL");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_chained(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = 0, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = chained_launches_enabled() ? 1 : 0;
+    PF_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+#endif
 
 // PF_HOST_TIMING=1: per-phase host times of the scene / batch build, printed to stderr.
 struct LapTimer {

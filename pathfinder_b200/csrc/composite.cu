@@ -167,6 +167,8 @@ __device__ __forceinline__ FillParams fill_params(uint2 fill) {
 #endif
 template <bool LOAD_DEST>
 __global__ void __launch_bounds__(128, PF_SOLID_MIN_BLOCKS) k_tile_solid(CompositeArgs a) {
+    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
+    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int fb_w = a.fb.max_x - a.fb.min_x;
@@ -635,6 +637,8 @@ __device__ __forceinline__ float4 blend_pixel(float4 d, float4 c, float m, uint3
 
 template <bool LOAD_DEST, bool GENERAL>
 __global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? 4 : PF_TILE_MIN_BLOCKS) k_tile_alpha(CompositeArgs a) {
+    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
+    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
     __shared__ TileWarpShared<GENERAL> sh_all[TILE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TileWarpShared<GENERAL> &sh = sh_all[warp];
@@ -946,9 +950,9 @@ int launch_composite(const CompositeArgs &args, cudaStream_t stream) {
     const uint64_t segments = (uint64_t)((fb_w + 31) / 32) * (uint64_t)rows;
     const unsigned solid_grid = (unsigned)((segments + 3) / 4); // 4 warps per block
     if (a.load_dest)
-        k_tile_solid<true><<<solid_grid, 128, 0, stream>>>(a);
+        launch_chained(k_tile_solid<true>, solid_grid, 128, stream, a);
     else
-        k_tile_solid<false><<<solid_grid, 128, 0, stream>>>(a);
+        launch_chained(k_tile_solid<false>, solid_grid, 128, stream, a);
     PF_CUDA_CHECK(cudaGetLastError());
     if (!a.entries) return 1; // a frame without batches: every list is empty, nothing was queued
 
@@ -961,13 +965,13 @@ int launch_composite(const CompositeArgs &args, cudaStream_t stream) {
     const int threads = 32 * TILE_WARPS;
     if (has_clip) {
         if (a.load_dest)
-            k_tile_alpha<true, true><<<grid, threads, 0, stream>>>(a);
+            launch_chained(k_tile_alpha<true, true>, grid, threads, stream, a);
         else
-            k_tile_alpha<false, true><<<grid, threads, 0, stream>>>(a);
+            launch_chained(k_tile_alpha<false, true>, grid, threads, stream, a);
     } else if (a.load_dest) {
-        k_tile_alpha<true, false><<<grid, threads, 0, stream>>>(a);
+        launch_chained(k_tile_alpha<true, false>, grid, threads, stream, a);
     } else {
-        k_tile_alpha<false, false><<<grid, threads, 0, stream>>>(a);
+        launch_chained(k_tile_alpha<false, false>, grid, threads, stream, a);
     }
     PF_CUDA_CHECK(cudaGetLastError());
     return 2;

@@ -382,6 +382,8 @@ __device__ __forceinline__ void dice_lockstep(DiceShared &sh, Cubic cur, int dep
 __global__ void __launch_bounds__(DICE_THREADS)
     k_dice_stream(BatchDev b, uint32_t segments_per_warp, float4 *__restrict__ lines, uint32_t *__restrict__ line_path,
                   uint32_t line_capacity, uint32_t *__restrict__ line_count) {
+    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
+    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
     __shared__ DiceShared sh;
     // A warp starts with segments_per_warp (<= 32) curves, one per low lane: on small scenes the other
     // lanes start idle and take the first right halves that appear, so even a few thousand curves
@@ -405,8 +407,8 @@ int launch_dice_stream(const BatchDev &b, float4 *lines, uint32_t *line_path, ui
     const uint32_t target_warps = (uint32_t)sm_count * 8u;
     const uint32_t per_warp = std::min(32u, std::max(1u, div_up(b.n_segments, target_warps)));
     const uint32_t warps = div_up(b.n_segments, per_warp);
-    k_dice_stream<<<div_up(warps, DICE_THREADS / 32), DICE_THREADS, 0, stream>>>(b, per_warp, lines, line_path,
-                                                                                  line_capacity, line_count);
+    launch_chained(k_dice_stream, div_up(warps, DICE_THREADS / 32), DICE_THREADS, stream, b, per_warp, lines, line_path,
+                   line_capacity, line_count);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -747,6 +749,8 @@ constexpr int BIN_LONG_STEPS = 12; // tile crossings from which a line is walked
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(BIN_THREADS, PF_BIN_MIN_BLOCKS) k_bin(BatchDev b, BinArgs a) {
+    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
+    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
     __shared__ float4 s_line[BIN_THREADS];
     __shared__ uint32_t s_index[BIN_THREADS];
     __shared__ uint32_t s_queued;
@@ -814,6 +818,8 @@ __global__ void __launch_bounds__(BIN_THREADS, PF_BIN_MIN_BLOCKS) k_bin(BatchDev
 // hundreds of tiles), one warp per line, warps pull from the queue the main kernel filled.
 template <int MODE>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_long(BatchDev b, BinArgs a) {
+    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
+    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
     const uint32_t n_long = min(*a.long_count, a.long_capacity);
     const float recip = 1.0f / 16.0f;
     for (;;) {
@@ -845,17 +851,17 @@ int launch_bin(int mode, const BatchDev &b, const BinArgs &args, cudaStream_t st
     int launches = 1;
     // (the caller hands every pass its own zeroed long_count / long_cursor words)
     if (mode == BIN_EMIT_LIVE)
-        k_bin<BIN_EMIT_LIVE><<<grid, BIN_THREADS, 0, stream>>>(b, args);
+        launch_chained(k_bin<BIN_EMIT_LIVE>, grid, BIN_THREADS, stream, b, args);
     else if (mode == BIN_COUNT)
-        k_bin<BIN_COUNT><<<grid, BIN_THREADS, 0, stream>>>(b, args);
+        launch_chained(k_bin<BIN_COUNT>, grid, BIN_THREADS, stream, b, args);
     else
         k_bin<BIN_EMIT><<<grid, BIN_THREADS, 0, stream>>>(b, args);
     if (mode != BIN_EMIT && args.long_queue) {
         const unsigned long_grid = (unsigned)sm_count_of_current_device() * 2u; // persistent warps; exits at once when the queue is empty
         if (mode == BIN_EMIT_LIVE)
-            k_bin_long<BIN_EMIT_LIVE><<<long_grid, BIN_THREADS, 0, stream>>>(b, args);
+            launch_chained(k_bin_long<BIN_EMIT_LIVE>, long_grid, BIN_THREADS, stream, b, args);
         else
-            k_bin_long<BIN_COUNT><<<long_grid, BIN_THREADS, 0, stream>>>(b, args);
+            launch_chained(k_bin_long<BIN_COUNT>, long_grid, BIN_THREADS, stream, b, args);
         launches++;
     }
     PF_CUDA_CHECK(cudaGetLastError());
@@ -893,6 +899,8 @@ __global__ void __launch_bounds__(128, DENSE ? 16 : 8)
     k_propagate(BatchDev b, uint32_t *__restrict__ tile_word, const int32_t *__restrict__ col_backdrop,
                 int32_t *__restrict__ z_buffer, ClipDev clip, uint32_t *__restrict__ tile_clip,
                 uint32_t *__restrict__ tile_orig_count) {
+    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
+    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= b.n_columns) return;
     uint32_t p = search_coarse(b.path_col_offset, b.col_index, c);
@@ -980,13 +988,13 @@ int launch_propagate(const BatchDev &b, uint32_t *tile_word, const int32_t *col_
     const unsigned grid = div_up(b.n_columns, 128);
     if (clip && tile_clip) {
         if (dense)
-            k_propagate<true, true><<<grid, 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, *clip, tile_clip, tile_orig_count);
+            launch_chained(k_propagate<true, true>, grid, 128, stream, b, tile_word, col_backdrop, z_buffer, *clip, tile_clip, tile_orig_count);
         else
-            k_propagate<true, false><<<grid, 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, *clip, tile_clip, tile_orig_count);
+            launch_chained(k_propagate<true, false>, grid, 128, stream, b, tile_word, col_backdrop, z_buffer, *clip, tile_clip, tile_orig_count);
     } else if (dense) {
-        k_propagate<false, true><<<grid, 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, ClipDev{}, nullptr, nullptr);
+        launch_chained(k_propagate<false, true>, grid, 128, stream, b, tile_word, col_backdrop, z_buffer, ClipDev{}, nullptr, nullptr);
     } else {
-        k_propagate<false, false><<<grid, 128, 0, stream>>>(b, tile_word, col_backdrop, z_buffer, ClipDev{}, nullptr, nullptr);
+        launch_chained(k_propagate<false, false>, grid, 128, stream, b, tile_word, col_backdrop, z_buffer, ClipDev{}, nullptr, nullptr);
     }
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
@@ -1021,6 +1029,8 @@ __global__ void __launch_bounds__(256, PF_LIST_MIN_BLOCKS)
                  uint32_t *__restrict__ path_live, int keep_all_fills, const uint32_t *__restrict__ run_counts,
                  uint32_t *__restrict__ live_tiles, uint32_t live_capacity, uint32_t *__restrict__ live_count,
                  uint32_t *__restrict__ fb_alpha, const uint32_t *__restrict__ tile_clip) {
+    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
+    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
     __shared__ uint32_t smem[256 / 32 + 1];
     __shared__ uint32_t s_base;
     const uint32_t base = blockIdx.x * LIST_TILE + threadIdx.x;
@@ -1119,10 +1129,9 @@ int launch_list_count(const BatchDev &b, const uint32_t *tile_word, const int32_
                       bool keep_all_fills, const uint32_t *run_counts, uint32_t *live_tiles, uint32_t live_capacity,
                       uint32_t *live_count, uint32_t *fb_alpha, const uint32_t *tile_clip, cudaStream_t stream) {
     if (b.n_tiles == 0) return 0;
-    k_list_count<<<div_up(b.n_tiles, LIST_TILE), 256, 0, stream>>>(b, tile_word, z_buffer, tile_fb, fb_count,
-                                                                    tile_fill_pos, fill_cursor, path_live,
-                                                                    keep_all_fills ? 1 : 0, run_counts, live_tiles,
-                                                                    live_capacity, live_count, fb_alpha, tile_clip);
+    launch_chained(k_list_count, div_up(b.n_tiles, LIST_TILE), 256, stream, b, tile_word, z_buffer, tile_fb, fb_count,
+                   tile_fill_pos, fill_cursor, path_live, keep_all_fills ? 1 : 0, run_counts, live_tiles, live_capacity,
+                   live_count, fb_alpha, tile_clip);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
@@ -1135,6 +1144,8 @@ __global__ void __launch_bounds__(256)
                 TileEntry *__restrict__ entries, uint32_t capacity, OverflowGuard guard, ClipDev clip,
                 const uint32_t *__restrict__ tile_clip, uint2 *__restrict__ entry_clip,
                 const uint32_t *__restrict__ live_tiles, uint32_t live_capacity, const uint32_t *__restrict__ live_count) {
+    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
+    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     // All totals are final by now. A batch that overflowed a stage buffer must leave the destination
     // untouched (the exact-sized re-run may have to load it): park the fused kernel's work counter
@@ -1188,13 +1199,13 @@ int launch_list_emit(const BatchDev &b, const uint32_t *tile_fb, const uint32_t 
     if (b.n_tiles == 0) return 0;
     const ClipDev clip_dev = clip && tile_clip ? *clip : ClipDev{};
     if (live_tiles)
-        k_list_emit<true><<<std::max(1u, div_up(live_capacity, 256)), 256, 0, stream>>>(
-            b, tile_fb, tile_word, tile_fill_pos, fb_start, fb_cursor, paints, entries, capacity, guard, clip_dev,
-            clip ? tile_clip : nullptr, entry_clip, live_tiles, live_capacity, live_count);
+        launch_chained(k_list_emit<true>, std::max(1u, div_up(live_capacity, 256)), 256, stream,
+                       b, tile_fb, tile_word, tile_fill_pos, fb_start, fb_cursor, paints, entries, capacity, guard, clip_dev,
+                       clip ? tile_clip : nullptr, entry_clip, live_tiles, live_capacity, live_count);
     else
-        k_list_emit<false><<<div_up(b.n_tiles, 256), 256, 0, stream>>>(
-            b, tile_fb, tile_word, tile_fill_pos, fb_start, fb_cursor, paints, entries, capacity, guard, clip_dev,
-            clip ? tile_clip : nullptr, entry_clip, nullptr, 0, nullptr);
+        launch_chained(k_list_emit<false>, div_up(b.n_tiles, 256), 256, stream,
+                       b, tile_fb, tile_word, tile_fill_pos, fb_start, fb_cursor, paints, entries, capacity, guard, clip_dev,
+                       clip ? tile_clip : nullptr, entry_clip, (const uint32_t *)nullptr, 0u, (const uint32_t *)nullptr);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(SCAN_THREADS)
            uint32_t *__restrict__ total_out, ScanState st) {
     __shared__ uint32_t smem[SCAN_THREADS / 32 + 1];
     __shared__ uint32_t s_tile, s_epoch, s_prefix;
+    chain_wait();    // (programmatic dependent launch, see common.cuh)
+    chain_release();
     if (n_dev) n = min(n, *n_dev);
     if (threadIdx.x == 0) {
         s_epoch = *reinterpret_cast<volatile uint32_t *>(st.control + 1) + 1; // read before the ticket
@@ -192,7 +194,7 @@ inline int exclusive_scan(InFn in, uint32_t *out, uint32_t n, uint32_t *total_ou
         PF_CUDA_CHECK(cudaMemsetAsync(scratch.status.ptr, 0, scratch.status.capacity * sizeof(unsigned long long), stream));
     }
     ScanState st{scratch.control.ptr, scratch.status.ptr};
-    k_scan<<<n_blocks, SCAN_THREADS, 0, stream>>>(in, n, n_dev, out, total_out, st);
+    launch_chained(k_scan<InFn>, n_blocks, SCAN_THREADS, stream, in, n, n_dev, out, total_out, st);
     PF_CUDA_CHECK(cudaGetLastError());
     return 1;
 }
