@@ -83,15 +83,15 @@ void scene_note_borrowed(::PFScene *scene, cudaStream_t stream, int device);
 
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
-// Programmatic dependent launch (sm_90+): a kernel launched with launch_chained may be scheduled while the kernel
-// before it on the stream is still draining — its blocks sit in chain_wait() until that kernel has completed and its
-// writes are visible — so the launch latency and the tail of one stage overlap with the next. Every kernel of the frame's
-// chain starts with chain_wait() (a no-op when it was launched the ordinary way) followed by chain_release(), which lets
-// the kernel after it be scheduled as soon as SM resources free up. PF_CUDA_NO_PDL=1 in the environment launches the
-// ordinary way.
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_chained is set up while the kernel before it
+// on the stream is still running and its blocks are scheduled as that kernel's blocks exit — they sit in chain_wait()
+// until it has completed and its writes are visible — so the launch latency of one stage hides behind the stage before
+// it. Every kernel of the frame's chain starts with chain_wait() (a no-op when it was launched the ordinary way). No
+// kernel triggers its dependents early (griddepcontrol.launch_dependents at the top of a kernel was measured: the
+// waiting blocks of the next stage then hold SM resources the other scenes' streams could use — isolated frames the
+// same, the three-scene step 4 % slower). PF_CUDA_NO_PDL=1 in the environment launches the ordinary way.
 #ifdef __CUDACC__
 __device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void chain_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 inline bool chained_launches_enabled() {
     static const bool on = [] {
         const char *e = getenv("PF_CUDA_NO_PDL");

@@ -167,8 +167,7 @@ __device__ __forceinline__ FillParams fill_params(uint2 fill) {
 #endif
 template <bool LOAD_DEST>
 __global__ void __launch_bounds__(128, PF_SOLID_MIN_BLOCKS) k_tile_solid(CompositeArgs a) {
-    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
-    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
+    chain_wait(); // (programmatic dependent launch: nothing is touched before the stage before this one has completed)
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int fb_w = a.fb.max_x - a.fb.min_x;
@@ -637,8 +636,7 @@ __device__ __forceinline__ float4 blend_pixel(float4 d, float4 c, float m, uint3
 
 template <bool LOAD_DEST, bool GENERAL>
 __global__ void __launch_bounds__(32 * TILE_WARPS, GENERAL ? 4 : PF_TILE_MIN_BLOCKS) k_tile_alpha(CompositeArgs a) {
-    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
-    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
+    chain_wait(); // (programmatic dependent launch: nothing is touched before the stage before this one has completed)
     __shared__ TileWarpShared<GENERAL> sh_all[TILE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TileWarpShared<GENERAL> &sh = sh_all[warp];

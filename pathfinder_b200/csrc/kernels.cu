@@ -382,8 +382,7 @@ __device__ __forceinline__ void dice_lockstep(DiceShared &sh, Cubic cur, int dep
 __global__ void __launch_bounds__(DICE_THREADS)
     k_dice_stream(BatchDev b, uint32_t segments_per_warp, float4 *__restrict__ lines, uint32_t *__restrict__ line_path,
                   uint32_t line_capacity, uint32_t *__restrict__ line_count) {
-    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
-    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
+    chain_wait(); // (programmatic dependent launch: nothing is touched before the stage before this one has completed)
     __shared__ DiceShared sh;
     // A warp starts with segments_per_warp (<= 32) curves, one per low lane: on small scenes the other
     // lanes start idle and take the first right halves that appear, so even a few thousand curves
@@ -749,8 +748,7 @@ constexpr int BIN_LONG_STEPS = 12; // tile crossings from which a line is walked
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(BIN_THREADS, PF_BIN_MIN_BLOCKS) k_bin(BatchDev b, BinArgs a) {
-    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
-    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
+    chain_wait(); // (programmatic dependent launch: nothing is touched before the stage before this one has completed)
     __shared__ float4 s_line[BIN_THREADS];
     __shared__ uint32_t s_index[BIN_THREADS];
     __shared__ uint32_t s_queued;
@@ -818,8 +816,7 @@ __global__ void __launch_bounds__(BIN_THREADS, PF_BIN_MIN_BLOCKS) k_bin(BatchDev
 // hundreds of tiles), one warp per line, warps pull from the queue the main kernel filled.
 template <int MODE>
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_long(BatchDev b, BinArgs a) {
-    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
-    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
+    chain_wait(); // (programmatic dependent launch: nothing is touched before the stage before this one has completed)
     const uint32_t n_long = min(*a.long_count, a.long_capacity);
     const float recip = 1.0f / 16.0f;
     for (;;) {
@@ -899,8 +896,7 @@ __global__ void __launch_bounds__(128, DENSE ? 16 : 8)
     k_propagate(BatchDev b, uint32_t *__restrict__ tile_word, const int32_t *__restrict__ col_backdrop,
                 int32_t *__restrict__ z_buffer, ClipDev clip, uint32_t *__restrict__ tile_clip,
                 uint32_t *__restrict__ tile_orig_count) {
-    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
-    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
+    chain_wait(); // (programmatic dependent launch: nothing is touched before the stage before this one has completed)
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= b.n_columns) return;
     uint32_t p = search_coarse(b.path_col_offset, b.col_index, c);
@@ -1029,8 +1025,7 @@ __global__ void __launch_bounds__(256, PF_LIST_MIN_BLOCKS)
                  uint32_t *__restrict__ path_live, int keep_all_fills, const uint32_t *__restrict__ run_counts,
                  uint32_t *__restrict__ live_tiles, uint32_t live_capacity, uint32_t *__restrict__ live_count,
                  uint32_t *__restrict__ fb_alpha, const uint32_t *__restrict__ tile_clip) {
-    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
-    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
+    chain_wait(); // (programmatic dependent launch: nothing is touched before the stage before this one has completed)
     __shared__ uint32_t smem[256 / 32 + 1];
     __shared__ uint32_t s_base;
     const uint32_t base = blockIdx.x * LIST_TILE + threadIdx.x;
@@ -1144,8 +1139,7 @@ __global__ void __launch_bounds__(256)
                 TileEntry *__restrict__ entries, uint32_t capacity, OverflowGuard guard, ClipDev clip,
                 const uint32_t *__restrict__ tile_clip, uint2 *__restrict__ entry_clip,
                 const uint32_t *__restrict__ live_tiles, uint32_t live_capacity, const uint32_t *__restrict__ live_count) {
-    chain_wait();    // (programmatic dependent launch: the stage before this one has completed ...
-    chain_release(); //  ... and the stage after it may be scheduled behind this one's blocks)
+    chain_wait(); // (programmatic dependent launch: nothing is touched before the stage before this one has completed)
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     // All totals are final by now. A batch that overflowed a stage buffer must leave the destination
     // untouched (the exact-sized re-run may have to load it): park the fused kernel's work counter

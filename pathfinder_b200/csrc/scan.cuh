@@ -73,8 +73,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
            uint32_t *__restrict__ total_out, ScanState st) {
     __shared__ uint32_t smem[SCAN_THREADS / 32 + 1];
     __shared__ uint32_t s_tile, s_epoch, s_prefix;
-    chain_wait();    // (programmatic dependent launch, see common.cuh)
-    chain_release();
+    chain_wait(); // (programmatic dependent launch, see common.cuh)
     if (n_dev) n = min(n, *n_dev);
     if (threadIdx.x == 0) {
         s_epoch = *reinterpret_cast<volatile uint32_t *>(st.control + 1) + 1; // read before the ticket
