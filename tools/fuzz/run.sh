@@ -22,6 +22,11 @@ nvcc -Wno-deprecated-gpu-targets -std=c++17 -O1 -g -Xcompiler -fsanitize=address
     -x cu scene_fuzz.cpp $CSRC/scene.cpp $CSRC/dilate.cpp -o "$OUT/scene_fuzz" && run scene-builder "$OUT/scene_fuzz"
 nvcc -Wno-deprecated-gpu-targets -std=c++17 -O1 -g -Xcompiler -fsanitize=thread \
     -x cu scene_tsan.cpp $CSRC/scene.cpp $CSRC/dilate.cpp -o "$OUT/scene_tsan" && run scene-builder-threads "$OUT/scene_tsan"
+# The scene proxy (worker thread, one-command hand-over, teardown with a build in flight) under ThreadSanitizer; the whole
+# library is linked in (the proxy lives next to the renderer), no GPU is touched.
+nvcc -Wno-deprecated-gpu-targets -gencode arch=compute_100a,code=sm_100a -std=c++17 -O1 -g -fmad=false -Xcompiler -fsanitize=thread \
+    -x cu proxy_tsan.cpp $CSRC/kernels.cu $CSRC/composite.cu $CSRC/renderer.cu $CSRC/scene.cpp $CSRC/stroke.cpp $CSRC/svg.cpp \
+    $CSRC/dilate.cpp $CSRC/font.cpp -o "$OUT/proxy_tsan" -ldl 2>/dev/null && run scene-proxy-threads "$OUT/proxy_tsan"
 g++ -O1 -g -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -msse4.1 -pthread $SAN -shared -o "$OUT/libpf_oracle_asan.so" ../../oracle/pf_oracle.cpp && \
     LD_PRELOAD="$(gcc -print-file-name=libasan.so):$(gcc -print-file-name=libubsan.so)" run oracle python "$PWD/oracle_asan.py" "$OUT/libpf_oracle_asan.so"
 # The CPU test suite against a build of the product library whose host code is instrumented (device code untouched).
