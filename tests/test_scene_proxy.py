@@ -157,3 +157,27 @@ def test_proxy_renders_the_same_frame():
     assert np.array_equal(got, r.read_pixels())
     r.close()
     proxy.close()
+
+
+def test_scene_clone_is_a_deep_copy_with_the_same_identity():
+    """Scene: Clone (scene.rs:37) keeps id and epoch — a sink that has seen the original takes the clone for the same
+    scene — and shares nothing with it afterwards."""
+    flat = small_scene(seed=8, n=60)
+    a = api.Scene.from_flat(flat)
+    h = L.lib().PFSceneClone(a._h)
+    b = api.Scene.__new__(api.Scene)
+    b._h = h
+    assert L.lib().PFSceneGetEpoch(a._h) == L.lib().PFSceneGetEpoch(b._h)
+    sink = L.PFSceneSinkState()
+    first, second = [], []
+    a.build(api.BuildOptions(), lambda cmd: first.append(digest(cmd)), sink_state=sink)
+    b.build(api.BuildOptions(), lambda cmd: second.append(digest(cmd)), sink_state=sink)
+    assert L.PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11 in [d[0] for d in first]
+    assert L.PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11 not in [d[0] for d in second]  # same scene, same epoch: not re-sent
+    assert [d for d in second] == [d for d in first if d[0] != L.PF_RENDER_COMMAND_UPLOAD_SCENE_D3D11]
+    # the original changes; the clone does not
+    a.set_view_box((0.0, 0.0, 100.0, 100.0))
+    assert b.view_box() == tuple(float(v) for v in flat.view_box)
+    third = []
+    b.build(api.BuildOptions(), lambda cmd: third.append(digest(cmd)), sink_state=L.PFSceneSinkState())
+    assert third == first
