@@ -1122,24 +1122,43 @@ PFCudaStatus PFSceneBuild(PFSceneRef s, PFBuildOptionsRef opts, PFSceneSinkState
         }
         s->strip_ids.clear();
         if (strip_on) {
-            // the rows of prepare_draw_path_for_gpu_binning's tile rect (builder.rs:1075-1079), as in pass 1 below
+            // the rows of prepare_draw_path_for_gpu_binning's tile rect (builder.rs:1075-1079), as in pass 1 below.
+            // (At N ranks this pass reads all the path records on a rank's share of the cores: it is kept to a few
+            // nanoseconds per path — invariants hoisted, floor / ceil without a libm call, ids compacted per chunk.)
             const size_t n = s->draw_paths.size();
             s->strip_included.assign(n, 0);
             const Transform identity_xf;
-            const Transform &sxf = prepared ? identity_xf : opts->transform;
-            parallel_ranges(n, 8192, [&](size_t begin, size_t end) {
+            const Transform sxf = prepared ? identity_xf : opts->transform;
+            const bool plain = !prepared && sxf.is_identity();
+            const RectF view_box = s->view_box;
+            const Path *paths = s->draw_paths.data();
+            const RectF *prepared_bounds = prepared ? s->prepared_draw_bounds.data() : nullptr;
+            uint8_t *included = s->strip_included.data();
+            // (int32_t)floorf(v) and (int32_t)ceilf(v) for the finite, in-range values a rect clipped to the view box has
+            auto floor_i = [](float v) { const int32_t t = (int32_t)v; return t - ((float)t > v ? 1 : 0); };
+            auto ceil_i = [](float v) { const int32_t t = (int32_t)v; return t + ((float)t < v ? 1 : 0); };
+            const float strip_lo_px = (float)strip_y0 * 16.0f, strip_lo_px_end = (float)strip_y1 * 16.0f;
+            const size_t chunks = pf::chunk_count(n, 8192);
+            std::vector<std::vector<uint32_t>> chunk_ids(chunks ? chunks : 1);
+            pf::parallel_chunks(n, chunks, [&](size_t c, size_t begin, size_t end) {
+                std::vector<uint32_t> &ids = chunk_ids[c];
+                ids.reserve((end - begin) / 4 + 16);
                 for (size_t i = begin; i < end; i++) {
-                    const Path &p = s->draw_paths[i];
-                    const RectF b = prepared ? s->prepared_draw_bounds[i] : sxf.is_identity() ? p.bounds : sxf.apply_rect(p.bounds);
+                    const RectF b = prepared_bounds ? prepared_bounds[i] : plain ? paths[i].bounds : sxf.apply_rect(paths[i].bounds);
+                    // Most paths lie wholly above or below the strip: floor(max(b.min_y, .) / 16) >= strip_y1 and
+                    // ceil(min(b.max_y, .) / 16) <= strip_y0 respectively (x / 16 is exact), whatever the view box does.
+                    if (b.min_y >= strip_lo_px_end || b.max_y <= strip_lo_px) continue;
                     RectF clipped;
-                    if (!rect_intersection(b, s->view_box, clipped)) continue;
+                    if (!rect_intersection(b, view_box, clipped)) continue;
                     const float k = 1.0f / 16.0f;
-                    const int32_t ty0 = (int32_t)floorf(clipped.min_y * k), ty1 = (int32_t)ceilf(clipped.max_y * k);
-                    s->strip_included[i] = (ty0 < strip_y1 && ty1 > strip_y0) ? 1 : 0;
+                    const int32_t ty0 = floor_i(clipped.min_y * k), ty1 = ceil_i(clipped.max_y * k);
+                    if (ty0 < strip_y1 && ty1 > strip_y0) {
+                        included[i] = 1;
+                        ids.push_back((uint32_t)i);
+                    }
                 }
             });
-            for (size_t i = 0; i < n; i++)
-                if (s->strip_included[i]) s->strip_ids.push_back((uint32_t)i);
+            for (const std::vector<uint32_t> &ids : chunk_ids) s->strip_ids.insert(s->strip_ids.end(), ids.begin(), ids.end());
         }
         seg_laps.lap("strip inclusion");
         build_segments(s, prepared ? s->prepared_points.data() : s->points.data(), strip_on ? &s->strip_ids : nullptr);
