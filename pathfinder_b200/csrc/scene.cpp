@@ -404,6 +404,8 @@ void build_path_segments(PFScene *s, const PFVector2F *scene_points, const std::
     uint32_t np = 0, ni = 0;
     for (size_t k = 0; k < n_items; k++) {
         const size_t pi = ids ? (*ids)[k] : k;
+        // (a strip's paths are scattered over the scene: their records are fetched ahead of this serial pass)
+        if (ids && k + 16 < n_items) __builtin_prefetch(&paths[(*ids)[k + 16]]);
         point_off[pi] = np, index_off[pi] = ni;
         np += paths[pi].segment_points;
         ni += paths[pi].segment_indices;
@@ -418,6 +420,19 @@ void build_path_segments(PFScene *s, const PFVector2F *scene_points, const std::
     parallel_ranges(n_items, ids ? 1024 : 4096, [&](size_t begin, size_t end) {
         for (size_t k = begin; k < end; k++) {
             const size_t pi = ids ? (*ids)[k] : k;
+            if (ids) {
+                // The paths of a strip lie far apart in the scene's arrays: the chain path record -> contour offsets ->
+                // points + flags is fetched a few paths ahead, one link per step.
+                if (k + 12 < end) __builtin_prefetch(&paths[(*ids)[k + 12]]);
+                if (k + 8 < end) __builtin_prefetch(&s->contour_offsets[paths[(*ids)[k + 8]].first_contour]);
+                if (k + 4 < end) {
+                    const uint32_t p_ahead = s->contour_offsets[paths[(*ids)[k + 4]].first_contour];
+                    __builtin_prefetch(scene_points + p_ahead);
+                    __builtin_prefetch(scene_points + p_ahead + 8);
+                    __builtin_prefetch(scene_points + p_ahead + 16);
+                    __builtin_prefetch(s->flags.data() + p_ahead);
+                }
+            }
             const Path &path = paths[pi];
             size_t wp = point_off[pi], wi = index_off[pi];
             segment_ranges[2 * pi] = (uint32_t)wi;
