@@ -32,7 +32,7 @@ g++ -O1 -g -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -msse4.1 -pthread $
 # The CPU test suite against a build of the product library whose host code is instrumented (device code untouched).
 ( cd $CSRC && nvcc -Wno-deprecated-gpu-targets -gencode arch=compute_100a,code=sm_100a -O1 -g -std=c++17 -fmad=false \
     -Xcompiler -fPIC,-O1,-ffp-contract=off,-fsanitize=address,-fsanitize=undefined,-fno-sanitize-recover=all \
-    -shared -o "$OUT/libpf_cuda_asan.so" kernels.cu renderer.cu -x cu scene.cpp stroke.cpp svg.cpp dilate.cpp font.cpp 2>/dev/null ) && \
+    -shared -o "$OUT/libpf_cuda_asan.so" kernels.cu composite.cu renderer.cu -x cu scene.cpp stroke.cpp svg.cpp dilate.cpp font.cpp 2>/dev/null ) && \
     LIMIT=$((LIMIT > 600 ? LIMIT : 600)) PF_CUDA_LIB="$OUT/libpf_cuda_asan.so" \
     LD_PRELOAD="$(gcc -print-file-name=libasan.so):$(gcc -print-file-name=libubsan.so)" \
     run cpu-suite-on-sanitizer-build python -m pytest "$PWD/../../tests" -x -q -m "not gpu" -p no:cacheprovider \
