@@ -144,3 +144,18 @@ def test_build_rs_compiles_what_the_makefile_compiles():
     integration_md = open(os.path.join(root, "INTEGRATION.md")).read()
     for f in srcs:
         assert f in integration_md, f"INTEGRATION.md does not mention {f}"
+
+
+def test_sanitizer_script_builds_the_whole_library():
+    """tools/fuzz/run.sh links two instrumented copies of the library (TSan for the scene proxy, ASan for the CPU suite):
+    each must name every source csrc/Makefile builds, or the copy fails to load and the step drops out unnoticed."""
+    import os
+    import re
+    root = _root()
+    makefile = open(os.path.join(root, "pathfinder_b200", "csrc", "Makefile")).read()
+    srcs = set(re.search(r"^SRCS := (.*)$", makefile, re.M).group(1).split())
+    script = open(os.path.join(root, "tools", "fuzz", "run.sh")).read().replace("\\\n", " ")
+    whole = [line for line in script.splitlines() if "kernels.cu" in line]
+    assert len(whole) == 2
+    for line in whole:
+        assert set(re.findall(r"(\w+\.(?:cu|cpp))\b", line)) - {"proxy_tsan.cpp"} == srcs, line
