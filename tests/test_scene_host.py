@@ -360,12 +360,17 @@ def collect_strip(scene, options, strip):
     return out
 
 
-def test_build_for_a_strip_keeps_only_the_paths_that_reach_it():
+@pytest.mark.parametrize("mode", ["transformed", "plain", "prepared"])
+def test_build_for_a_strip_keeps_only_the_paths_that_reach_it(mode):
     """Multi-GPU host side: a rank builds segments and records only for the paths with a tile in its rows; ids stay
     global; the strips together cover exactly the paths of the whole build; the kept paths' segments are the same
-    points in the same order."""
+    points in the same order. The three ways the builder gets a path's bounds: under the options' transform, as pushed
+    (identity), and from the prepared (transformed + dilated) copy of the points."""
     flat = scenes.random_paths(600, 512, 21, r_min=4.0, r_max=40.0)
-    options = api.BuildOptions(transform=api.Transform2F(0.9, 0.1, -0.05, 1.1, 6.0, -3.0))
+    options = {"transformed": lambda: api.BuildOptions(transform=api.Transform2F(0.9, 0.1, -0.05, 1.1, 6.0, -3.0)),
+               "plain": lambda: api.BuildOptions(),
+               "prepared": lambda: api.BuildOptions(transform=api.Transform2F(0.9, 0.1, -0.05, 1.1, 6.0, -3.0),
+                                                    dilation=(0.5, 0.25))}[mode]()
     whole = collect_strip(api.Scene.from_flat(flat), options, None)
     whole_draw = next(r for r in whole if r["kind"] == "DrawTilesD3D11")
     whole_up = next(r for r in whole if r["kind"] == "UploadSceneD3D11")
