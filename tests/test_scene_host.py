@@ -417,3 +417,41 @@ def test_build_for_a_strip_keeps_only_the_paths_that_reach_it(mode):
         assert "UploadSceneD3D11" in again3
     assert seen == set(whole_draw["global_path_ids"])
     assert len(keys) == 3 and whole_draw["content_key"] not in keys
+
+
+def test_strip_inclusion_edge_cases_and_chunks():
+    """The strip filter is exactly "the whole build's tile rect has a row in the strip": bounds that end on a strip
+    boundary, paths off every side of the view box, a NaN point, a frame-sized path; an empty strip (= no strip) and a
+    strip below the frame; enough paths that the inclusion pass runs in several chunks on the worker pool."""
+    flat = scenes.random_paths(20000, 1024, 77, r_min=2.0, r_max=30.0)
+    scene_whole, scene_strip = api.Scene.from_flat(flat), api.Scene.from_flat(flat)
+
+    def box(x0, y0, x1, y1):
+        return np.array([[x0, y0], [x1, y0], [x1, y1], [x0, y1]], dtype=np.float32)
+
+    extra = [box(10, 100, 50, 320),          # max_y on the boundary of rows 20: not in a strip that starts there
+             box(10, 320, 50, 400),          # min_y on it: not in a strip that ends there
+             box(10, 319.5, 50, 320.5),      # straddles it
+             box(-500, 300, -20, 340),       # left of the view box
+             box(1500, 300, 1600, 340),      # right of it
+             box(100, -300, 140, -20),       # above
+             box(100, 1100, 140, 1300),      # below
+             box(-100, -100, 1200, 1200),    # larger than the frame
+             np.array([[5, 5], [float("nan"), 50], [60, 60], [5, 60]], dtype=np.float32),
+             box(200, 0, 240, 1024)]         # every row
+    for s in (scene_whole, scene_strip):
+        for pts in extra:
+            s.push_draw_path(pts, np.zeros(len(pts), dtype=np.uint8), np.array([0, len(pts)], dtype=np.uint32), 0)
+    options = api.BuildOptions()
+    whole = next(r for r in collect_strip(scene_whole, options, None) if r["kind"] == "DrawTilesD3D11")
+    rect_of = dict(zip(whole["global_path_ids"], whole["rects"]))
+    for y0, y1 in ((0, 20), (20, 21), (20, 64), (63, 64), (30, 30), (64, 80), (0, 64)):
+        got = [r for r in collect_strip(scene_strip, options, (y0, y1)) if r["kind"] == "DrawTilesD3D11"]
+        want = [pid for pid, r in rect_of.items() if r[1] < y1 and r[3] > y0]
+        if y0 == y1:  # no rows: not a strip, the scene is built whole (a renderer never owns an empty strip)
+            want = list(rect_of)
+        if not want:
+            assert not got or got[0]["global_path_ids"] == []
+            continue
+        assert got[0]["global_path_ids"] == want, (y0, y1)
+        assert got[0]["rects"] == [rect_of[pid] for pid in want]
