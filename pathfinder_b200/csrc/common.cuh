@@ -204,9 +204,9 @@ class WorkerPool {
             // Spin for a short while (phases follow each other within microseconds), then sleep. The spin is a
             // thousand PAUSEs (tens of microseconds), not a bare load loop ten times as long: a busy spinner takes
             // issue slots from its hyper-thread sibling, and when the renderer processes of a multi-GPU job
-            // oversubscribe the host's cores it burns time slices that the thread it waits for needs (eight builders
-            // of two threads on eight cores: the slowest rank's build 5.0-6.0 -> 4.0-4.5 ms; one builder of eight
-            // threads alone: 3.2 -> 2.6 ms).
+            // oversubscribe the host's cores it burns time slices that the thread it waits for needs. (Eight builders
+            // of two threads on eight noisy cores: the slowest one's step 5.2 -> 4.9 ms, the median 4.1 -> 3.9 ms over
+            // six interleaved rounds — inside the noise of that machine, never slower.)
             bool woke = false;
             for (int spin = 0; spin < 1000 && !woke; spin++) {
                 woke = changed();
