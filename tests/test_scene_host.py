@@ -455,3 +455,27 @@ def test_strip_inclusion_edge_cases_and_chunks():
             continue
         assert got[0]["global_path_ids"] == want, (y0, y1)
         assert got[0]["rects"] == [rect_of[pid] for pid in want]
+
+
+@pytest.mark.parametrize("strip", [None, (0, 4)])
+def test_empty_and_ragged_scenes(strip):
+    """No paths, a path without contours, a contour without points: the builder still sends a well-formed frame
+    (Start .. Finish) and no batch, for a whole build and for a strip; the zero-area bounds of an empty outline do not
+    intersect the view box (RectF::intersection is strict, rect.rs:122-137), so prepare_draw_path_for_gpu_binning
+    (builder.rs:1075-1079) drops the path. A real path pushed after them keeps its global id."""
+    frame = ["Start", "UploadTextureMetadata", "UploadSceneD3D11", "Finish"]
+    scene = api.Scene()
+    scene.set_view_box((0, 0, 256, 256))
+    assert [r["kind"] for r in collect_strip(scene, api.BuildOptions(), strip)] == frame
+    scene.push_paint((255, 0, 0, 255))
+    none = np.zeros((0, 2), np.float32), np.zeros(0, np.uint8)
+    scene.push_draw_path(*none, np.array([0], np.uint32), 0)
+    assert [r["kind"] for r in collect_strip(scene, api.BuildOptions(), strip)] == frame
+    scene.push_draw_path(*none, np.array([0, 0], np.uint32), 0)
+    assert [r["kind"] for r in collect_strip(scene, api.BuildOptions(), strip)] == frame
+    scene.push_draw_path(np.array([[10, 10], [50, 10], [50, 50]], np.float32), np.zeros(3, np.uint8), np.array([0, 3], np.uint32), 0)
+    got = collect_strip(scene, api.BuildOptions(), strip)
+    assert [r["kind"] for r in got] == frame[:3] + ["DrawTilesD3D11", "Finish"]
+    draw = got[3]
+    assert draw["path_count"] == 1 and draw["global_path_ids"] == [2] and draw["rects"] == [(0, 0, 4, 4)]
+    assert draw["segment_count"] == 3 == got[2]["index_count"]
