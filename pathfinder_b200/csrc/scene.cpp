@@ -400,63 +400,101 @@ void build_path_segments(PFScene *s, const PFVector2F *scene_points, const std::
     // rank's share of the host cores would cost more than the strip's own work.
     const size_t n_paths = paths.size();
     const size_t n_items = ids ? ids->size() : n_paths;
-    path_offsets.resize(2 * (n_paths + 1));
-    uint32_t *point_off = path_offsets.data(), *index_off = point_off + (n_paths + 1);
-    uint32_t np = 0, ni = 0;
-    for (size_t k = 0; k < n_items; k++) {
-        const size_t pi = ids ? (*ids)[k] : k;
-        // (a strip's paths are scattered over the scene: their records are fetched ahead of this serial pass)
-        if (ids && k + 16 < n_items) __builtin_prefetch(&paths[(*ids)[k + 16]]);
-        point_off[pi] = np, index_off[pi] = ni;
-        np += paths[pi].segment_points;
-        ni += paths[pi].segment_indices;
-    }
-    point_off[n_paths] = np, index_off[n_paths] = ni;
-    seg_points.ensure((size_t)np + 1);
-    seg_indices.ensure((size_t)ni + 1);
-    segment_ranges.resize(2 * n_paths);
-    PFVector2F *out_points = seg_points.ptr;
-    PFSegmentIndicesD3D11 *out_indices = seg_indices.ptr;
     const uint8_t ctrl_mask = PF_POINT_FLAGS_CONTROL_POINT_0 | PF_POINT_FLAGS_CONTROL_POINT_1;
-    parallel_ranges(n_items, ids ? 1024 : 4096, [&](size_t begin, size_t end) {
-        for (size_t k = begin; k < end; k++) {
-            const size_t pi = ids ? (*ids)[k] : k;
-            if (ids) {
-                // The paths of a strip lie far apart in the scene's arrays: the chain path record -> contour offsets ->
-                // points + flags is fetched a few paths ahead, one link per step.
-                if (k + 12 < end) __builtin_prefetch(&paths[(*ids)[k + 12]]);
-                if (k + 8 < end) __builtin_prefetch(&s->contour_offsets[paths[(*ids)[k + 8]].first_contour]);
+    segment_ranges.resize(2 * n_paths);
+    // One path: its contours' points (each contour closed by its first point again, builder.rs:835) from `wp`, one index
+    // entry per on-curve point from `wi`; both cursors are left at the end of the path.
+    auto emit_path = [&](size_t pi, PFVector2F *out_points, PFSegmentIndicesD3D11 *out_indices, size_t &wp, size_t &wi) {
+        const Path &path = paths[pi];
+        segment_ranges[2 * pi] = (uint32_t)wi;
+        for (uint32_t c = path.first_contour; c < path.end_contour; c++) {
+            const uint32_t p0 = s->contour_offsets[c], point_count = s->contour_offsets[c + 1] - p0;
+            const uint8_t *flags = s->flags.data() + p0;
+            const PFVector2F *pts = scene_points + p0;
+            memcpy(out_points + wp, pts, (size_t)point_count * sizeof(PFVector2F));
+            for (uint32_t i = 0; i < point_count; i++) {
+                if (flags[i] & ctrl_mask) continue;
+                uint32_t f = 0;
+                if (i + 1 < point_count && (flags[i + 1] & PF_POINT_FLAGS_CONTROL_POINT_0))
+                    f = (i + 2 < point_count && (flags[i + 2] & PF_POINT_FLAGS_CONTROL_POINT_1))
+                            ? PF_CURVE_IS_CUBIC
+                            : PF_CURVE_IS_QUADRATIC;
+                out_indices[wi++] = PFSegmentIndicesD3D11{(uint32_t)(wp + i), f};
+            }
+            wp += point_count;
+            out_points[wp++] = pts[0]; // implicit close: the first point again (builder.rs:835)
+        }
+        segment_ranges[2 * pi + 1] = (uint32_t)wi;
+    };
+    uint32_t np = 0, ni = 0;
+    if (ids) {
+        // A strip's paths lie far apart in the scene's arrays, so every visit of a path record is a cache miss unless
+        // it is fetched ahead. Two-level scan over fixed chunks of the id list, both levels on the worker pool: pass A
+        // sums what a chunk's paths add to the two output cursors, pass B starts from the prefix over chunks and
+        // advances the cursors path by path (a chunk's paths are contiguous in the output) — no per-path offset
+        // arrays, no serial pass over the records, and a chunk's records are still in its thread's cache in pass B.
+        struct ChunkSum {
+            uint32_t points = 0, indices = 0;
+            uint32_t pad[14]; // one cache line per chunk
+        };
+        const size_t chunks = pf::chunk_count(n_items, 1024);
+        std::vector<ChunkSum> sums(chunks + 1);
+        const uint32_t *id = ids->data();
+        pf::parallel_chunks(n_items, chunks, [&](size_t c, size_t begin, size_t end) {
+            uint32_t points = 0, indices = 0;
+            for (size_t k = begin; k < end; k++) {
+                if (k + 16 < end) __builtin_prefetch(&paths[id[k + 16]]);
+                points += paths[id[k]].segment_points;
+                indices += paths[id[k]].segment_indices;
+            }
+            sums[c + 1].points = points, sums[c + 1].indices = indices;
+        });
+        for (size_t c = 1; c <= chunks; c++) // exclusive prefix: sums[c] = totals of the chunks before c
+            sums[c].points += sums[c - 1].points, sums[c].indices += sums[c - 1].indices;
+        np = sums[chunks].points, ni = sums[chunks].indices;
+        seg_points.ensure((size_t)np + 1);
+        seg_indices.ensure((size_t)ni + 1);
+        PFVector2F *out_points = seg_points.ptr;
+        PFSegmentIndicesD3D11 *out_indices = seg_indices.ptr;
+        pf::parallel_chunks(n_items, chunks, [&](size_t c, size_t begin, size_t end) {
+            size_t wp = sums[c].points, wi = sums[c].indices;
+            for (size_t k = begin; k < end; k++) {
+                // The chain path record -> contour offsets -> points + flags is fetched a few paths ahead, one link
+                // per step.
+                if (k + 12 < end) __builtin_prefetch(&paths[id[k + 12]]);
+                if (k + 8 < end) __builtin_prefetch(&s->contour_offsets[paths[id[k + 8]].first_contour]);
                 if (k + 4 < end) {
-                    const uint32_t p_ahead = s->contour_offsets[paths[(*ids)[k + 4]].first_contour];
+                    const uint32_t p_ahead = s->contour_offsets[paths[id[k + 4]].first_contour];
                     __builtin_prefetch(scene_points + p_ahead);
                     __builtin_prefetch(scene_points + p_ahead + 8);
                     __builtin_prefetch(scene_points + p_ahead + 16);
                     __builtin_prefetch(s->flags.data() + p_ahead);
                 }
+                emit_path(id[k], out_points, out_indices, wp, wi);
             }
-            const Path &path = paths[pi];
-            size_t wp = point_off[pi], wi = index_off[pi];
-            segment_ranges[2 * pi] = (uint32_t)wi;
-            for (uint32_t c = path.first_contour; c < path.end_contour; c++) {
-                const uint32_t p0 = s->contour_offsets[c], point_count = s->contour_offsets[c + 1] - p0;
-                const uint8_t *flags = s->flags.data() + p0;
-                const PFVector2F *pts = scene_points + p0;
-                memcpy(out_points + wp, pts, (size_t)point_count * sizeof(PFVector2F));
-                for (uint32_t i = 0; i < point_count; i++) {
-                    if (flags[i] & ctrl_mask) continue;
-                    uint32_t f = 0;
-                    if (i + 1 < point_count && (flags[i + 1] & PF_POINT_FLAGS_CONTROL_POINT_0))
-                        f = (i + 2 < point_count && (flags[i + 2] & PF_POINT_FLAGS_CONTROL_POINT_1))
-                                ? PF_CURVE_IS_CUBIC
-                                : PF_CURVE_IS_QUADRATIC;
-                    out_indices[wi++] = PFSegmentIndicesD3D11{(uint32_t)(wp + i), f};
-                }
-                wp += point_count;
-                out_points[wp++] = pts[0]; // implicit close: the first point again (builder.rs:835)
-            }
-            segment_ranges[2 * pi + 1] = (uint32_t)wi;
+        });
+    } else {
+        // Every path: output positions are prefix sums of the per-path counts (a sequential pass over the records),
+        // so that the paths are then filled in parallel.
+        path_offsets.resize(2 * (n_paths + 1));
+        uint32_t *point_off = path_offsets.data(), *index_off = point_off + (n_paths + 1);
+        for (size_t pi = 0; pi < n_paths; pi++) {
+            point_off[pi] = np, index_off[pi] = ni;
+            np += paths[pi].segment_points;
+            ni += paths[pi].segment_indices;
         }
-    });
+        point_off[n_paths] = np, index_off[n_paths] = ni;
+        seg_points.ensure((size_t)np + 1);
+        seg_indices.ensure((size_t)ni + 1);
+        PFVector2F *out_points = seg_points.ptr;
+        PFSegmentIndicesD3D11 *out_indices = seg_indices.ptr;
+        parallel_ranges(n_paths, 4096, [&](size_t begin, size_t end) {
+            for (size_t pi = begin; pi < end; pi++) {
+                size_t wp = point_off[pi], wi = index_off[pi];
+                emit_path(pi, out_points, out_indices, wp, wi);
+            }
+        });
+    }
     seg_point_count = np;
     seg_index_count = ni;
 }

@@ -1,5 +1,5 @@
 // tools/fuzz/scene_fuzz.cpp — random scenes (NaN / infinite / huge coordinates, stray control flags, empty contours, clip paths, transforms,
-// dilations) through PFSceneBuild under ASan + UBSan; the listener reads every payload byte and re-derives the tile count (see run.sh).
+// dilations) through PFSceneBuild and PFSceneBuildForStrip under ASan + UBSan; the listener reads every payload byte and re-derives the tile count (see run.sh).
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -113,6 +113,11 @@ int main() {
                 PFBuildOptionsSetDilation(o, &d);
             }
             PFSceneBuild(s, o, &sink, listener, nullptr);
+            {   // the same for a renderer that owns a strip of tile rows (multi-GPU): rows inside, across and below the frame
+                const int32_t y0 = rand() % 40 - 2, y1 = y0 + rand() % 24;
+                PFSceneSinkState strip_sink{0, 0, 0};
+                PFSceneBuildForStrip(s, o, &strip_sink, listener, nullptr, y0, y1);
+            }
             PFBuildOptionsDestroy(o);
         }
         PFSceneDestroy(s);
