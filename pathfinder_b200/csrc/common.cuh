@@ -123,6 +123,15 @@ struct LapTimer {
     }
 };
 
+// What a spinning host thread does between two looks at a flag.
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield" ::: "memory");
+#endif
+}
+
 // Persistent host worker threads (the reference parallelises its CPU-side scene work with Rayon's
 // global pool, renderer/src/concurrent/rayon.rs:17-24). Spawning threads per call costs more than
 // the per-frame work items themselves (a 100k-path batch build is ~1 ms), so the workers are kept
@@ -158,7 +167,7 @@ class WorkerPool {
         // Wait for chunks still running on workers.
         for (int spin = 0; remaining_.load(std::memory_order_acquire) != 0; spin++) {
             if (spin > 2000) std::this_thread::yield();
-            else __builtin_ia32_pause();
+            else cpu_relax();
         }
     }
 
@@ -210,7 +219,7 @@ class WorkerPool {
             bool woke = false;
             for (int spin = 0; spin < 1000 && !woke; spin++) {
                 woke = changed();
-                if (!woke) __builtin_ia32_pause();
+                if (!woke) cpu_relax();
             }
             if (!woke) {
                 std::unique_lock<std::mutex> lock(mutex_);
