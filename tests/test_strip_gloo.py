@@ -74,3 +74,54 @@ def test_strip_rows():
     for rows_px, world in [(8192, 8), (4096, 3), (1000, 7), (16384, 5)]:
         for g in range(world):
             assert api.strip_of_rank(partition.tile_rows(rows_px), g, world) == partition.strip_rows(rows_px, world, g)
+
+
+def _builder_worker(rank, world, port, out_path):
+    """Each rank runs the PRODUCT's strip-aware host build (PFSceneBuildForStrip through the Python mirror) for the
+    strip PFCudaStripOfRank gives it, and the ranks exchange what they kept."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pathfinder_b200 import api
+        from tests.test_scene_host import collect_strip
+        flat = scenes.random_paths(3000, 1024, 5, r_min=4.0, r_max=60.0)
+        y0, y1 = api.strip_of_rank(1024 // 16, rank, world)
+        got = collect_strip(api.Scene.from_flat(flat), api.BuildOptions(), (y0, y1))
+        draw = next(r for r in got if r["kind"] == "DrawTilesD3D11")
+        up = next(r for r in got if r["kind"] == "UploadSceneD3D11")
+        kept = torch.zeros(flat.n_paths, dtype=torch.int64)
+        kept[torch.tensor(draw["global_path_ids"], dtype=torch.int64)] = 1
+        rows_ok = all(r[1] < y1 and r[3] > y0 for r in draw["rects"])
+        stats = torch.tensor([draw["path_count"], draw["segment_count"], up["index_count"], int(rows_ok)], dtype=torch.int64)
+        all_stats = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(all_stats, stats)
+        dist.all_reduce(kept)  # how many ranks kept each path
+        if rank == 0:
+            np.savez(out_path, kept=kept.numpy(), stats=torch.stack(all_stats).numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_strip_aware_host_build_across_ranks(tmp_path, world):
+    """The library's host builder under the N > 1 launch: every path of the whole build is kept by at least one rank
+    (exactly the ranks whose rows its tile rect reaches), paths outside the view box by none, and a rank uploads only
+    the segments of its own batch."""
+    from pathfinder_b200 import api
+    from tests.test_scene_host import collect_strip
+    out = str(tmp_path / "built.npz")
+    mp.spawn(_builder_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    z = np.load(out)
+    flat = scenes.random_paths(3000, 1024, 5, r_min=4.0, r_max=60.0)
+    whole = next(r for r in collect_strip(api.Scene.from_flat(flat), api.BuildOptions(), None) if r["kind"] == "DrawTilesD3D11")
+    want = np.zeros(flat.n_paths, dtype=np.int64)
+    strips = [api.strip_of_rank(1024 // 16, g, world) for g in range(world)]
+    for pid, rect in zip(whole["global_path_ids"], whole["rects"]):
+        want[pid] = sum(1 for y0, y1 in strips if rect[1] < y1 and rect[3] > y0)
+    assert np.array_equal(z["kept"], want)
+    assert (want[whole["global_path_ids"]] >= 1).all()
+    stats = z["stats"]
+    assert stats[:, 3].all()                       # every kept rect reaches its rank's rows
+    assert (stats[:, 1] == stats[:, 2]).all()      # a rank uploads exactly its batch's segments
+    assert stats[:, 0].sum() == want.sum() and stats[:, 1].sum() >= whole["segment_count"]
