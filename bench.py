@@ -169,11 +169,18 @@ def run_reference(args):
     cores = max(1, os.cpu_count() or 1)
     scene_list = workload_scenes(args.workload)
     prepared = prepare_cpu(scene_list)
-    for _ in range(args.warmup):
-        cpu_tiler_step(prepared, cores)
+    # The port does not always scale to every core (its batch pack is sequential, like the reference's, and on the GPU
+    # box it peaked at half the logical cores): the warm-up steps try all the cores and half of them in turn, and the
+    # timed steps run on whichever was faster, so that the baseline is the port at its best, not at its widest.
+    candidates = [cores] if cores < 4 else [cores, cores // 2]
+    tried = {n: float("inf") for n in candidates}
+    for w in range(max(args.warmup, len(candidates))):
+        n_threads = candidates[w % len(candidates)]
+        tried[n_threads] = min(tried[n_threads], cpu_tiler_step(prepared, n_threads)[0])
+    threads = min(candidates, key=lambda n: tried[n])
     t_total, seg_total = 0.0, 0
     for _ in range(args.steps):
-        s, n = cpu_tiler_step(prepared, cores)
+        s, n = cpu_tiler_step(prepared, threads)
         t_total += s
         seg_total += n
     value = seg_total / t_total / 1e9
@@ -183,8 +190,10 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAMES[args.workload],
                    "note": "CPU tiler only (scene build: flatten + tile + propagate + pack), as cpu_build_time"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full builds of every scene of the workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} full builds of every scene of the workload",
+                         "host_cores": cores,
+                         "warmup_ms_per_step_by_threads": {str(n): round(t * 1e3, 3) for n, t in tried.items()}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -623,17 +632,32 @@ def main():
             seg_cpu += n
             reps += 1
         s1, n1 = cpu_tiler_step(prepared, 1)
-        # how the port scales with threads (one build each): the all-core figure is the reported baseline, and how
-        # far it is from cores x the single-thread figure says how much a better-parallelised tiler could gain
+        # how the port scales with threads (one build each below all cores): how far the best figure is from
+        # cores x the single-thread figure says how much a better-parallelised tiler could gain
         scaling = {"1": n1 / s1 / 1e9}
         for nt in (2, 4, 8, 16, 32, 64):
             if nt < cores:
                 st_, nn = cpu_tiler_step(prepared, nt)
                 scaling[str(nt)] = nn / st_ / 1e9
         scaling[str(cores)] = seg_cpu / t_cpu / 1e9
-        cpu_baseline = {"value": seg_cpu / t_cpu / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-                        "thread_scaling": scaling,
-                        "sample": f"{reps} full CPU-tiler builds of every scene of the workload (scene build only: "
+        # (the baseline is the port at its best thread count, as in the reference arm: on the GPU box it peaks below
+        # the number of logical cores)
+        best_threads = max(scaling, key=lambda k: scaling[k])
+        best_reps = reps
+        if int(best_threads) != cores:  # measured on one build so far: give it the sample the all-core figure had
+            best_reps, t_best, seg_best = 0, 0.0, 0
+            t_begin = time.perf_counter()
+            while best_reps < 3 or (time.perf_counter() - t_begin < 5.0 and best_reps < 50):
+                s, n = cpu_tiler_step(prepared, int(best_threads))
+                t_best += s
+                seg_best += n
+                best_reps += 1
+            scaling[best_threads] = seg_best / t_best / 1e9
+            if scaling[str(cores)] > scaling[best_threads]:
+                best_threads, best_reps = str(cores), reps
+        cpu_baseline = {"value": scaling[best_threads], "unit": UNIT, "cores": int(best_threads), "kind": "port",
+                        "host_cores": cores, "thread_scaling": scaling,
+                        "sample": f"{best_reps} full CPU-tiler builds of every scene of the workload (scene build only: "
                                   "flatten + tile + propagate + pack, the reference's cpu_build_time)",
                         "single_thread_value": n1 / s1 / 1e9}
 
